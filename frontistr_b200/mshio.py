@@ -1,0 +1,332 @@
+"""Minimal readers for the data formats either side of the hot path.
+
+* ``read_msh``  — HEC-MW entire mesh (.msh): !NODE, !ELEMENT (361/342), !SECTION, !MATERIAL,
+                  !NGROUP (list and GENERATE).  Mirrors what hecmw_get_mesh + hecmw2fstr_mesh_conv
+                  leave in hecmwST_local_mesh: unused nodes dropped and local ids assigned in
+                  ascending global-id order (hecmw1/src/common/hecmw_io_mesh.c:3039,3895), 342
+                  connectivity permuted to FrontISTR order (fistr1/src/common/hecmw2fstr_connect_conv.c:19).
+* ``read_cnt``  — the analysis control file: !BOUNDARY, !CLOAD, !SOLVER (fistr1/src/common/
+                  fstr_ctrl_common.f90:69-169, fstr_setup.f90:1473-1509).
+* ``read_dist_mesh`` — HECMW-DMD-ASCII (hecmw1/src/common/hecmw_io_dist.c:1888-2284) written by hecmw_part1.
+
+This is host-side plumbing for tests/bench; the reference's own readers stay in place in a real build.
+"""
+from __future__ import annotations
+
+import re
+
+import numpy as np
+
+from .hecmw_types import hecmwST_local_mesh, hecmwST_matrix, kel361IC
+from .meshgen import TABLE342
+
+_NN = {341: 4, 342: 10, 351: 6, 352: 15, 361: 8, 362: 20}
+
+
+def _opts(header: str) -> dict:
+    out = {}
+    for tok in header.split(",")[1:]:
+        tok = tok.strip()
+        if "=" in tok:
+            k, v = tok.split("=", 1)
+            out[k.strip().upper()] = v.strip()
+        elif tok:
+            out[tok.upper()] = True
+    return out
+
+
+def read_msh(path: str, elemopt361: int = kel361IC) -> hecmwST_local_mesh:
+    nodes = {}
+    elems = {}       # etype -> list[(eid, [nodes])]
+    ngroups = {}
+    materials = {}
+    sections = []
+    cur = None
+    opts = {}
+    mat_name = None
+    with open(path) as f:
+        for raw in f:
+            line = raw.strip()
+            if not line or line.startswith("!!") or line.startswith("#"):
+                continue
+            if line.startswith("!"):
+                key = line.split(",")[0].strip().upper()
+                opts = _opts(line)
+                cur = key
+                if key == "!MATERIAL":
+                    mat_name = opts.get("NAME")
+                    materials.setdefault(mat_name, {})
+                elif key == "!ITEM":
+                    # '!ITEM=1, SUBITEM=2'
+                    cur = "!ITEMDATA"
+                elif key.startswith("!ITEM="):
+                    cur = "!ITEMDATA"
+                elif key == "!SECTION":
+                    sections.append(dict(opts))
+                elif key == "!END":
+                    break
+                continue
+            vals = [v.strip() for v in line.split(",") if v.strip() != ""]
+            if cur == "!NODE":
+                nodes[int(vals[0])] = (float(vals[1]), float(vals[2]), float(vals[3]))
+            elif cur == "!ELEMENT":
+                et = int(opts["TYPE"])
+                elems.setdefault(et, []).append((int(vals[0]), [int(v) for v in vals[1:]]))
+            elif cur == "!NGROUP":
+                g = ngroups.setdefault(opts["NGRP"], [])
+                if opts.get("GENERATE"):
+                    a, b, s = int(vals[0]), int(vals[1]), int(vals[2]) if len(vals) > 2 else 1
+                    g.extend(range(a, b + 1, s))
+                else:
+                    g.extend(int(v) for v in vals)
+            elif cur == "!ITEMDATA":
+                if "E" not in materials[mat_name]:
+                    materials[mat_name]["E"] = float(vals[0])
+                    materials[mat_name]["nu"] = float(vals[1])
+            # !SECTION data line (thickness) and !HEADER text are ignored
+    for et in elems:
+        if et not in (361, 342):
+            raise NotImplementedError("element type %d is outside the hot-path scope" % et)
+    used = sorted({n for et in elems for _, c in elems[et] for n in c})
+    gid = np.array(used, np.int64)
+    loc = {g: i + 1 for i, g in enumerate(used)}
+    m = hecmwST_local_mesh()
+    m.n_node = m.nn_internal = len(used)
+    m.node = np.array([nodes[g] for g in used], np.float64).reshape(-1)
+    m.global_node_ID = gid.astype(np.int32)
+    types = sorted(elems)
+    tindex = [0]
+    nindex = [0]
+    items = []
+    for et in types:
+        lst = sorted(elems[et], key=lambda t: t[0])
+        for _, c in lst:
+            c = np.array([loc[v] for v in c], np.int32)
+            if et == 342:
+                c = c[TABLE342]
+            items.append(c)
+            nindex.append(nindex[-1] + len(c))
+        tindex.append(tindex[-1] + len(lst))
+    m.n_elem = tindex[-1]
+    m.n_elem_type = len(types)
+    m.elem_type_index = np.array(tindex, np.int32)
+    m.elem_type_item = np.array(types, np.int32)
+    m.elem_node_index = np.array(nindex, np.int32)
+    m.elem_node_item = np.concatenate(items).astype(np.int32)
+    m.section_ID = np.ones(m.n_elem, np.int32)
+    sec = sections[0] if sections else {}
+    mat = materials.get(sec.get("MATERIAL"), next(iter(materials.values())) if materials else {})
+    m.sections = [dict(elemopt361=elemopt361, E=mat.get("E", 0.0), nu=mat.get("nu", 0.0))]
+    # nodes removed as unused also leave their groups (hecmw_io_mesh.c:3039-3060)
+    m.node_group = {k: np.array([loc[g] for g in v if g in loc], np.int32) for k, v in ngroups.items()}
+    return m
+
+
+def read_cnt(path: str) -> dict:
+    out = dict(boundary=[], cload=[], solver=None)
+    cur = None
+    sol_lines = []
+    sol_opts = {}
+    with open(path) as f:
+        for raw in f:
+            line = raw.strip()
+            if not line or line.startswith("!!") or line.startswith("#"):
+                continue
+            if line.startswith("!"):
+                key = line.split(",")[0].strip().upper()
+                cur = key
+                if key == "!SOLVER":
+                    sol_opts = _opts(line)
+                if key == "!END":
+                    break
+                continue
+            vals = [v.strip() for v in line.split(",") if v.strip() != ""]
+            if cur == "!BOUNDARY":
+                out["boundary"].append((vals[0], int(vals[1]), int(vals[2]), float(vals[3]) if len(vals) > 3 else 0.0))
+            elif cur == "!CLOAD":
+                out["cload"].append((vals[0], int(vals[1]), float(vals[2])))
+            elif cur == "!SOLVER":
+                sol_lines.append(vals)
+    out["solver"] = (sol_opts, sol_lines)
+    return out
+
+
+_METHODS = {"CG": 1, "BICGSTAB": 2, "GMRES": 3, "GPBICG": 4}
+
+
+def apply_solver_card(hecMAT: hecmwST_matrix, solver) -> None:
+    """!SOLVER -> Iarray/Rarray, fistr1/src/common/fstr_setup.f90:1473-1509."""
+    opts, lines = solver
+    I, R = hecMAT.Iarray, hecMAT.Rarray
+    if "METHOD" in opts:
+        I[1] = _METHODS[opts["METHOD"].upper()]
+    if "PRECOND" in opts:
+        I[2] = int(opts["PRECOND"])
+    if "NSET" in opts:
+        I[3] = int(opts["NSET"])
+    yn = {"NO": 0, "YES": 1, "VERBOSE": 2}
+    if "ITERLOG" in opts:
+        I[20] = yn[opts["ITERLOG"].upper()]
+    if "TIMELOG" in opts:
+        I[21] = yn[opts["TIMELOG"].upper()]
+    if len(lines) > 0:
+        v = lines[0]
+        if len(v) > 0: I[0] = int(v[0])
+        if len(v) > 1: I[4] = min(4, max(0, int(v[1])))
+        if len(v) > 2: I[5] = int(v[2])
+        if len(v) > 3: I[33] = int(v[3])
+    if len(lines) > 1:
+        v = lines[1]
+        if len(v) > 0: R[0] = float(v[0])
+        if len(v) > 1: R[1] = float(v[1])
+        if len(v) > 2: R[2] = float(v[2])
+    I[98] = 1
+
+
+class _Tok:
+    def __init__(self, path):
+        with open(path) as f:
+            self.first = f.readline()
+            self.lines = f.read().split("\n")
+        self.li = 0
+        self.buf = []
+
+    def line(self):
+        """next raw line (for string fields)"""
+        self.buf = []
+        s = self.lines[self.li]
+        self.li += 1
+        return s
+
+    def _fill(self):
+        while not self.buf:
+            self.buf = self.lines[self.li].split()
+            self.li += 1
+
+    def i(self):
+        self._fill()
+        return int(self.buf.pop(0))
+
+    def f(self):
+        self._fill()
+        return float(self.buf.pop(0))
+
+    def ia(self, n):
+        out = np.empty(n, np.int64)
+        k = 0
+        while k < n:
+            self._fill()
+            t = min(n - k, len(self.buf))
+            out[k:k + t] = [int(v) for v in self.buf[:t]]
+            del self.buf[:t]
+            k += t
+        return out
+
+    def fa(self, n):
+        out = np.empty(n, np.float64)
+        k = 0
+        while k < n:
+            self._fill()
+            t = min(n - k, len(self.buf))
+            out[k:k + t] = [float(v) for v in self.buf[:t]]
+            del self.buf[:t]
+            k += t
+        return out
+
+
+def read_dist_mesh(path: str, elemopt361: int = kel361IC, E=None, nu=None) -> hecmwST_local_mesh:
+    """HECMW-DMD-ASCII reader following the field order of hecmw1/src/common/hecmw_io_dist.c
+    (get_global_info :245-, get_node_info, get_elem_info, get_comm_info; writer :1888-2284).
+    Only the leading blocks needed by the hot path are parsed (global, node, elem, comm);
+    material E/nu are supplied by the caller or parsed from the material block when simple."""
+    t = _Tok(path)
+    mver = re.search(r"version=(\d+)", t.first)
+    version = int(mver.group(1)) if mver else 0
+    # ---- global info
+    t.i()  # hecmw_flag_adapt
+    t.i()  # hecmw_flag_initcon
+    t.i()  # hecmw_flag_parttype
+    t.i()  # hecmw_flag_partdepth
+    t.i()  # hecmw_flag_version
+    if version >= 4:
+        t.i()  # hecmw_flag_partcontact
+    t.line() if False else None
+    # gridfile (one line, may be empty), then n_file, files, header line, zero_temp
+    t.buf = []
+    t.line()               # gridfile
+    nfile = t.i()
+    t.buf = []
+    for _ in range(nfile):
+        t.line()
+    t.line()               # header
+    zero_temp = t.f()
+    # ---- node info
+    n_node = t.i()
+    n_node_gross = t.i() if version >= 2 else n_node
+    nn_middle = t.i() if version >= 4 else n_node
+    nn_internal = t.i()
+    # node_internal_list only for element-based partitions (parttype==2): not supported here
+    node_ID = t.ia(2 * n_node).reshape(-1, 2)
+    global_node_ID = t.ia(n_node)
+    node = t.fa(3 * n_node)
+    n_dof = t.i()
+    n_dof_grp = t.i()
+    t.ia(n_dof_grp + 1)    # node_dof_index
+    t.ia(n_dof_grp)        # node_dof_item
+    # initial conditions absent when flag_initcon == 0
+    # ---- elem info
+    n_elem = t.i()
+    n_elem_gross = t.i() if version >= 2 else n_elem
+    ne_internal = t.i()
+    t.ia(ne_internal)      # elem_internal_list
+    t.ia(2 * n_elem)       # elem_ID
+    t.ia(n_elem)           # global_elem_ID
+    elem_type = t.ia(n_elem)
+    n_elem_type = t.i()
+    elem_type_index = t.ia(n_elem_type + 1)
+    elem_type_item = t.ia(n_elem_type)
+    elem_node_index = t.ia(n_elem + 1)
+    elem_node_item = t.ia(int(elem_node_index[-1]))
+    section_ID = t.ia(n_elem)
+    n_elem_mat_ID = t.i()
+    t.ia(n_elem + 1)       # elem_mat_ID_index
+    t.ia(n_elem_mat_ID)    # elem_mat_ID_item
+    # ---- comm info
+    zero = t.i()
+    t.i()                  # HECMW_COMM
+    PETOT = t.i()
+    t.i()                  # PEsmpTOT
+    my_rank = t.i()
+    t.i()                  # errnof
+    t.i()                  # n_subdomain
+    n_neighbor_pe = t.i()
+    neighbor_pe = t.ia(n_neighbor_pe)
+    import_index = t.ia(n_neighbor_pe + 1)
+    import_item = t.ia(int(import_index[-1]))
+    export_index = t.ia(n_neighbor_pe + 1)
+    export_item = t.ia(int(export_index[-1]))
+    m = hecmwST_local_mesh()
+    m.n_node, m.nn_internal, m.n_elem, m.n_dof = n_node, nn_internal, n_elem, n_dof
+    m.node = node
+    m.node_ID = node_ID.astype(np.int32)
+    m.global_node_ID = global_node_ID.astype(np.int32)
+    m.n_elem_type = n_elem_type
+    m.elem_type_index = elem_type_index.astype(np.int32)
+    m.elem_type_item = elem_type_item.astype(np.int32)
+    m.elem_node_index = elem_node_index.astype(np.int32)
+    eni = elem_node_item.astype(np.int32)
+    # hecmw2fstr_mesh_conv: 342 file order -> FrontISTR order
+    for e in np.nonzero(elem_type == 342)[0]:
+        s = elem_node_index[e]
+        eni[s:s + 10] = eni[s:s + 10][TABLE342]
+    m.elem_node_item = eni
+    m.section_ID = section_ID.astype(np.int32)
+    m.sections = [dict(elemopt361=elemopt361, E=E, nu=nu)]
+    m.n_neighbor_pe = n_neighbor_pe
+    m.neighbor_pe = neighbor_pe.astype(np.int32)
+    m.import_index = import_index.astype(np.int32)
+    m.import_item = import_item.astype(np.int32)
+    m.export_index = export_index.astype(np.int32)
+    m.export_item = export_item.astype(np.int32)
+    m.my_rank, m.PETOT, m.zero = my_rank, PETOT, zero
+    return m

@@ -1,0 +1,1313 @@
+/*
+ * ORACLE — TEST INFRASTRUCTURE ONLY (see hecmw_oracle.h for the full header).
+ * CPU restatement of the FrontISTR / HEC-MW linear-static hot path.
+ * Parity pinning: reference golden logs (exA ... displacements) + independent
+ * direct solve; iteration counts / K entries are pinned by restatement only.
+ * Citations are file:line in the reference tree (ricosjp/FrontISTR).
+ */
+#include "hecmw_oracle.h"
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* The reference is Fortran compiled with FMA contraction on every current
+ * target; the products/sums on the SpMV and preconditioner paths are written
+ * with explicit fma() in source order (left-to-right) so that the CUDA path
+ * can be compared bit-for-bit. */
+#define MADD3(acc, a1, x1, a2, x2, a3, x3) fma((a3), (x3), fma((a2), (x2), fma((a1), (x1), (acc))))
+#define MUL3(a1, x1, a2, x2, a3, x3) fma((a3), (x3), fma((a2), (x2), (a1) * (x1)))
+#define MSUB3(acc, a1, x1, a2, x2, a3, x3) fma(-(a3), (x3), fma(-(a2), (x2), fma(-(a1), (x1), (acc))))
+
+static double wtime(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
+/* ------------------------------------------------------------------------- */
+/* hecmw_mat_con  (hecmw1/src/solver/matrix/hecmw_mat_con.f90:23-268)          */
+/* ------------------------------------------------------------------------- */
+static int *g_con_indexL, *g_con_itemL, *g_con_indexU, *g_con_itemU;
+static int g_con_NP, g_con_NPL, g_con_NPU;
+
+static int etype_max_node(int ic_type) {
+  switch (ic_type) {
+    case 341: return 4;
+    case 342: return 10;
+    case 351: return 6;
+    case 352: return 15;
+    case 361: return 8;
+    case 362: return 20;
+    default: return -1;
+  }
+}
+
+/* hecmw_FIND_NODE (mat_con.f90:161-197): linear probe insert, fixed width */
+static void find_node(int NP, int NL, int NU, int *INL, int *IAL, int *INU, int *IAU,
+                      int ip1, int ip2, int *ierr) {
+  int kk, icou;
+  (void)NP;
+  if (ip1 > ip2) {
+    for (kk = 1; kk <= INL[ip1 - 1]; kk++)
+      if (ip2 == IAL[(size_t)(ip1 - 1) * NL + kk - 1]) return;
+    icou = INL[ip1 - 1] + 1;
+    if (icou > NL) { *ierr = 1; return; }
+    IAL[(size_t)(ip1 - 1) * NL + icou - 1] = ip2;
+    INL[ip1 - 1] = icou;
+    return;
+  }
+  if (ip2 > ip1) {
+    for (kk = 1; kk <= INU[ip1 - 1]; kk++)
+      if (ip2 == IAU[(size_t)(ip1 - 1) * NU + kk - 1]) return;
+    icou = INU[ip1 - 1] + 1;
+    if (icou > NU) { *ierr = 2; return; }
+    IAU[(size_t)(ip1 - 1) * NU + icou - 1] = ip2;
+    INU[ip1 - 1] = icou;
+    return;
+  }
+}
+
+/* hecmw_mSORT (mat_con.f90:203-227): bubble sort of an index vector, descending;
+ * the caller then reads it back-to-front => ascending rows. */
+static void msort(const int *STEM, int *INUM, int NN) {
+  int ii, jj, ITEM;
+  for (ii = 1; ii <= NN; ii++) INUM[ii - 1] = ii;
+  for (ii = 1; ii <= NN - 1; ii++)
+    for (jj = 1; jj <= NN - ii; jj++)
+      if (STEM[INUM[jj - 1] - 1] < STEM[INUM[jj] - 1]) {
+        ITEM = INUM[jj];
+        INUM[jj] = INUM[jj - 1];
+        INUM[jj - 1] = ITEM;
+      }
+}
+
+int orc_mat_con_build(const orc_mesh *mesh, int *N, int *NP_out, int *NPL, int *NPU) {
+  int NP = mesh->n_node;
+  int NL = 10, NU = 10;
+  int *INL, *INU, *IAL, *IAU;
+  int ierr, itype, icel, j, k, nn, nid[20];
+  int NCOL1[2048], NCOL2[2048];
+
+  INL = calloc(NP, sizeof(int)); INU = calloc(NP, sizeof(int));
+  IAL = calloc((size_t)NP * NL, sizeof(int)); IAU = calloc((size_t)NP * NU, sizeof(int));
+  /* restart-on-overflow loop, mat_con.f90:78-109,139-156 */
+  for (;;) {
+    ierr = 0;
+    for (itype = 1; itype <= mesh->n_elem_type && !ierr; itype++) {
+      int is = mesh->elem_type_index[itype - 1] + 1;
+      int iE = mesh->elem_type_index[itype];
+      int ic_type = mesh->elem_type_item[itype - 1];
+      nn = etype_max_node(ic_type);
+      if (nn < 0) return -1;
+      for (icel = is; icel <= iE && !ierr; icel++) {
+        int iS = mesh->elem_node_index[icel - 1];
+        for (j = 1; j <= nn; j++) nid[j - 1] = mesh->elem_node_item[iS + j - 1];
+        for (j = 1; j <= nn && !ierr; j++)
+          for (k = 1; k <= nn; k++)
+            if (k != j) {
+              find_node(NP, NL, NU, INL, IAL, INU, IAU, nid[j - 1], nid[k - 1], &ierr);
+              if (ierr) break;
+            }
+      }
+    }
+    if (!ierr) break;
+    free(INL); free(INU); free(IAL); free(IAU);
+    if (ierr == 1) NL += 5;
+    if (ierr == 2) NU += 5;
+    INL = calloc(NP, sizeof(int)); INU = calloc(NP, sizeof(int));
+    IAL = calloc((size_t)NP * NL, sizeof(int)); IAU = calloc((size_t)NP * NU, sizeof(int));
+  }
+  /* sorting, mat_con.f90:116-133 */
+  for (int inod = 1; inod <= NP; inod++) {
+    int NN = INL[inod - 1];
+    for (k = 1; k <= NN; k++) NCOL1[k - 1] = IAL[(size_t)(inod - 1) * NL + k - 1];
+    msort(NCOL1, NCOL2, NN);
+    for (k = NN; k >= 1; k--) IAL[(size_t)(inod - 1) * NL + NN - k] = NCOL1[NCOL2[k - 1] - 1];
+    NN = INU[inod - 1];
+    for (k = 1; k <= NN; k++) NCOL1[k - 1] = IAU[(size_t)(inod - 1) * NU + k - 1];
+    msort(NCOL1, NCOL2, NN);
+    for (k = NN; k >= 1; k--) IAU[(size_t)(inod - 1) * NU + NN - k] = NCOL1[NCOL2[k - 1] - 1];
+  }
+  /* hecmw_mat_con1, mat_con.f90:233-268 */
+  free(g_con_indexL); free(g_con_itemL); free(g_con_indexU); free(g_con_itemU);
+  g_con_indexL = calloc(NP + 1, sizeof(int));
+  g_con_indexU = calloc(NP + 1, sizeof(int));
+  for (int i = 1; i <= NP; i++) {
+    g_con_indexL[i] = g_con_indexL[i - 1] + INL[i - 1];
+    g_con_indexU[i] = g_con_indexU[i - 1] + INU[i - 1];
+  }
+  g_con_NP = NP;
+  g_con_NPL = g_con_indexL[NP];
+  g_con_NPU = g_con_indexU[NP];
+  g_con_itemL = malloc(sizeof(int) * (size_t)(g_con_NPL > 0 ? g_con_NPL : 1));
+  g_con_itemU = malloc(sizeof(int) * (size_t)(g_con_NPU > 0 ? g_con_NPU : 1));
+  for (int i = 1; i <= NP; i++) {
+    for (k = 1; k <= INL[i - 1]; k++) g_con_itemL[k + g_con_indexL[i - 1] - 1] = IAL[(size_t)(i - 1) * NL + k - 1];
+    for (k = 1; k <= INU[i - 1]; k++) g_con_itemU[k + g_con_indexU[i - 1] - 1] = IAU[(size_t)(i - 1) * NU + k - 1];
+  }
+  free(INL); free(INU); free(IAL); free(IAU);
+  *N = mesh->nn_internal; *NP_out = NP; *NPL = g_con_NPL; *NPU = g_con_NPU;
+  return 0;
+}
+
+int orc_mat_con_fetch(int *indexL, int *itemL, int *indexU, int *itemU) {
+  if (!g_con_indexL) return -1;
+  memcpy(indexL, g_con_indexL, sizeof(int) * (g_con_NP + 1));
+  memcpy(indexU, g_con_indexU, sizeof(int) * (g_con_NP + 1));
+  memcpy(itemL, g_con_itemL, sizeof(int) * (size_t)g_con_NPL);
+  memcpy(itemU, g_con_itemU, sizeof(int) * (size_t)g_con_NPU);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+/* element primitives                                                          */
+/* ------------------------------------------------------------------------- */
+/* quadrature.f90:83-91,221 (hex 2x2x2) and :124-128,236-238 (tet 4-pt) — the
+ * 15-digit literals verbatim. */
+static const double gauss3d2[8][3] = {
+    {-0.577350269189626, -0.577350269189626, -0.577350269189626},
+    {0.577350269189626, -0.577350269189626, -0.577350269189626},
+    {-0.577350269189626, 0.577350269189626, -0.577350269189626},
+    {0.577350269189626, 0.577350269189626, -0.577350269189626},
+    {-0.577350269189626, -0.577350269189626, 0.577350269189626},
+    {0.577350269189626, -0.577350269189626, 0.577350269189626},
+    {-0.577350269189626, 0.577350269189626, 0.577350269189626},
+    {0.577350269189626, 0.577350269189626, 0.577350269189626}};
+static const double weight3d2[8] = {1, 1, 1, 1, 1, 1, 1, 1};
+static const double gauss3d5[4][3] = {
+    {0.138196601125011, 0.138196601125011, 0.138196601125011},
+    {0.585410196624968, 0.138196601125011, 0.138196601125011},
+    {0.138196601125011, 0.585410196624968, 0.138196601125011},
+    {0.138196601125011, 0.138196601125011, 0.585410196624968}};
+static const double weight3d5[4] = {0.041666666666667, 0.041666666666667, 0.041666666666667,
+                                    0.041666666666667};
+
+/* ShapeDeriv_hex8n, lib/element/hex8n.f90:24-53 */
+static void shapederiv_hex8n(const double lc[3], double f[][3]) {
+  const double x = lc[0], y = lc[1], z = lc[2];
+  f[0][0] = -0.125 * (1.0 - y) * (1.0 - z);
+  f[1][0] = 0.125 * (1.0 - y) * (1.0 - z);
+  f[2][0] = 0.125 * (1.0 + y) * (1.0 - z);
+  f[3][0] = -0.125 * (1.0 + y) * (1.0 - z);
+  f[4][0] = -0.125 * (1.0 - y) * (1.0 + z);
+  f[5][0] = 0.125 * (1.0 - y) * (1.0 + z);
+  f[6][0] = 0.125 * (1.0 + y) * (1.0 + z);
+  f[7][0] = -0.125 * (1.0 + y) * (1.0 + z);
+
+  f[0][1] = -0.125 * (1.0 - x) * (1.0 - z);
+  f[1][1] = -0.125 * (1.0 + x) * (1.0 - z);
+  f[2][1] = 0.125 * (1.0 + x) * (1.0 - z);
+  f[3][1] = 0.125 * (1.0 - x) * (1.0 - z);
+  f[4][1] = -0.125 * (1.0 - x) * (1.0 + z);
+  f[5][1] = -0.125 * (1.0 + x) * (1.0 + z);
+  f[6][1] = 0.125 * (1.0 + x) * (1.0 + z);
+  f[7][1] = 0.125 * (1.0 - x) * (1.0 + z);
+
+  f[0][2] = -0.125 * (1.0 - x) * (1.0 - y);
+  f[1][2] = -0.125 * (1.0 + x) * (1.0 - y);
+  f[2][2] = -0.125 * (1.0 + x) * (1.0 + y);
+  f[3][2] = -0.125 * (1.0 - x) * (1.0 + y);
+  f[4][2] = 0.125 * (1.0 - x) * (1.0 - y);
+  f[5][2] = 0.125 * (1.0 + x) * (1.0 - y);
+  f[6][2] = 0.125 * (1.0 + x) * (1.0 + y);
+  f[7][2] = 0.125 * (1.0 - x) * (1.0 + y);
+}
+
+/* ShapeDeriv_tet10n, lib/element/tet10n.f90:29-75 */
+static void shapederiv_tet10n(const double vc[3], double s[][3]) {
+  const double xi = vc[0], et = vc[1], ze = vc[2];
+  const double a = 1.0 - xi - et - ze;
+  s[0][0] = 1.0 - 4.0 * a; s[1][0] = 4.0 * xi - 1.0; s[2][0] = 0.0; s[3][0] = 0.0;
+  s[4][0] = 4.0 * (1.0 - 2.0 * xi - et - ze); s[5][0] = 4.0 * et; s[6][0] = -4.0 * et;
+  s[7][0] = -4.0 * ze; s[8][0] = 4.0 * ze; s[9][0] = 0.0;
+  s[0][1] = 1.0 - 4.0 * a; s[1][1] = 0.0; s[2][1] = 4.0 * et - 1.0; s[3][1] = 0.0;
+  s[4][1] = -4.0 * xi; s[5][1] = 4.0 * xi; s[6][1] = 4.0 * (1.0 - xi - 2.0 * et - ze);
+  s[7][1] = -4.0 * ze; s[8][1] = 0.0; s[9][1] = 4.0 * ze;
+  s[0][2] = 1.0 - 4.0 * a; s[1][2] = 0.0; s[2][2] = 0.0; s[3][2] = 4.0 * ze - 1.0;
+  s[4][2] = -4.0 * xi; s[5][2] = 0.0; s[6][2] = -4.0 * et;
+  s[7][2] = 4.0 * (1.0 - xi - et - 2.0 * ze); s[8][2] = 4.0 * xi; s[9][2] = 4.0 * et;
+}
+
+static int num_quad_points(int etype) { return etype == 361 ? 8 : (etype == 342 ? 4 : -1); }
+static void get_quad_point(int etype, int LX, double pos[3]) {
+  const double *p = (etype == 361) ? gauss3d2[LX - 1] : gauss3d5[LX - 1];
+  pos[0] = p[0]; pos[1] = p[1]; pos[2] = p[2];
+}
+static double get_weight(int etype, int LX) {
+  return (etype == 361) ? weight3d2[LX - 1] : weight3d5[LX - 1];
+}
+static void get_shape_deriv(int etype, const double lc[3], double d[][3]) {
+  if (etype == 361) shapederiv_hex8n(lc, d); else shapederiv_tet10n(lc, d);
+}
+
+#define EC(i, n) ecoord[3 * ((n)-1) + ((i)-1)] /* ecoord(i,n), (3,nn) column-major */
+
+/* Jacobian, determinant and cofactor inverse — shared by getGlobalDeriv and
+ * getJacobian (lib/element/element.f90:693-741,772-819) */
+static void jacobian3(int nn, const double *ecoord, double deriv[][3], double XJ[3][3],
+                      double *det, double XJI[3][3]) {
+  for (int i = 1; i <= 3; i++)
+    for (int j = 1; j <= 3; j++) {
+      double s = 0.0;
+      for (int n = 1; n <= nn; n++) s += EC(i, n) * deriv[n - 1][j - 1];
+      XJ[i - 1][j - 1] = s;
+    }
+#define J(i, j) XJ[(i)-1][(j)-1]
+  double DET = J(1, 1) * J(2, 2) * J(3, 3) + J(2, 1) * J(3, 2) * J(1, 3) + J(3, 1) * J(1, 2) * J(2, 3) -
+               J(3, 1) * J(2, 2) * J(1, 3) - J(2, 1) * J(1, 2) * J(3, 3) - J(1, 1) * J(3, 2) * J(2, 3);
+  double DUM = 1.0 / DET;
+  XJI[0][0] = DUM * (J(2, 2) * J(3, 3) - J(3, 2) * J(2, 3));
+  XJI[0][1] = DUM * (-J(1, 2) * J(3, 3) + J(3, 2) * J(1, 3));
+  XJI[0][2] = DUM * (J(1, 2) * J(2, 3) - J(2, 2) * J(1, 3));
+  XJI[1][0] = DUM * (-J(2, 1) * J(3, 3) + J(3, 1) * J(2, 3));
+  XJI[1][1] = DUM * (J(1, 1) * J(3, 3) - J(3, 1) * J(1, 3));
+  XJI[1][2] = DUM * (-J(1, 1) * J(2, 3) + J(2, 1) * J(1, 3));
+  XJI[2][0] = DUM * (J(2, 1) * J(3, 2) - J(3, 1) * J(2, 2));
+  XJI[2][1] = DUM * (-J(1, 1) * J(3, 2) + J(3, 1) * J(1, 2));
+  XJI[2][2] = DUM * (J(1, 1) * J(2, 2) - J(2, 1) * J(1, 2));
+#undef J
+  *det = DET;
+}
+
+/* getGlobalDeriv, element.f90:693-741 */
+static void get_global_deriv(int etype, int nn, const double lc[3], const double *ecoord,
+                             double *det, double gderiv[][3]) {
+  double deriv[20][3], XJ[3][3], XJI[3][3];
+  get_shape_deriv(etype, lc, deriv);
+  jacobian3(nn, ecoord, deriv, XJ, det, XJI);
+  for (int n = 0; n < nn; n++)
+    for (int j = 0; j < 3; j++) {
+      double s = 0.0;
+      for (int k = 0; k < 3; k++) s += deriv[n][k] * XJI[k][j];
+      gderiv[n][j] = s;
+    }
+}
+
+/* calElasticMatrix, lib/physics/ElasticLinear.f90:15-59 (D3 branch) */
+static void cal_elastic_matrix(double EE, double PP, double D[6][6]) {
+  memset(D, 0, sizeof(double) * 36);
+  D[0][0] = EE * (1.0 - PP) / (1.0 - 2.0 * PP) / (1.0 + PP);
+  D[0][1] = EE * PP / (1.0 - 2.0 * PP) / (1.0 + PP);
+  D[0][2] = D[0][1];
+  D[1][0] = D[0][1];
+  D[1][1] = D[0][0];
+  D[1][2] = D[0][1];
+  D[2][0] = D[0][2];
+  D[2][1] = D[1][2];
+  D[2][2] = D[0][0];
+  D[3][3] = EE / (1.0 + PP) * 0.5;
+  D[4][4] = EE / (1.0 + PP) * 0.5;
+  D[5][5] = EE / (1.0 + PP) * 0.5;
+}
+
+/* calInverse, lib/utilities/utilities.f90:247-316 — Gauss-Jordan, row pivoting */
+void orc_calInverse(int NN, double *Aarr) {
+#define A(i, j) Aarr[((j)-1) * NN + ((i)-1)] /* column-major */
+  int I, J, K, IW, LR = 1, IP[64];
+  double W, WMAX, PIVOT, API, EPS = 1.0E-35f, DET = 1.0;
+  for (I = 1; I <= NN; I++) IP[I - 1] = I;
+  for (K = 1; K <= NN; K++) {
+    WMAX = 0.0;
+    for (I = K; I <= NN; I++) {
+      W = fabs(A(I, K));
+      if (W > WMAX) { WMAX = W; LR = I; }
+    }
+    PIVOT = A(LR, K);
+    API = fabs(PIVOT);
+    if (API <= EPS) { fprintf(stderr, "PIVOT ERROR AT %5d\n", K); abort(); }
+    DET = DET * PIVOT;
+    if (LR != K) {
+      DET = -DET;
+      IW = IP[K - 1]; IP[K - 1] = IP[LR - 1]; IP[LR - 1] = IW;
+      for (J = 1; J <= NN; J++) { W = A(K, J); A(K, J) = A(LR, J); A(LR, J) = W; }
+    }
+    for (I = 1; I <= NN; I++) A(K, I) = A(K, I) / PIVOT;
+    for (I = 1; I <= NN; I++) {
+      if (I != K) {
+        W = A(I, K);
+        if (W != 0.) {
+          for (J = 1; J <= NN; J++)
+            if (J != K) A(I, J) = A(I, J) - W * A(K, J);
+          A(I, K) = -W / PIVOT;
+        }
+      }
+    }
+    A(K, K) = 1.0 / PIVOT;
+  }
+  for (I = 1; I <= NN; I++) {
+    K = IP[I - 1];
+    if (K != I) {
+      IW = IP[K - 1]; IP[K - 1] = IP[I - 1]; IP[I - 1] = IW;
+      for (J = 1; J <= NN; J++) { W = A(J, I); A(J, I) = A(J, K); A(J, K) = W; }
+    }
+  }
+  (void)DET;
+#undef A
+}
+
+/* fill B(6, 3*ncol) from gderiv, static_LIB_3d.f90:120-131 */
+static void fill_B(int ncol, double gderiv[][3], double *B /* (6, 3*ncol) col-major */) {
+#define Bm(i, j) B[((j)-1) * 6 + ((i)-1)]
+  memset(B, 0, sizeof(double) * 6 * 3 * ncol);
+  for (int j = 1; j <= ncol; j++) {
+    Bm(1, 3 * j - 2) = gderiv[j - 1][0];
+    Bm(2, 3 * j - 1) = gderiv[j - 1][1];
+    Bm(3, 3 * j) = gderiv[j - 1][2];
+    Bm(4, 3 * j - 2) = gderiv[j - 1][1];
+    Bm(4, 3 * j - 1) = gderiv[j - 1][0];
+    Bm(5, 3 * j - 1) = gderiv[j - 1][2];
+    Bm(5, 3 * j) = gderiv[j - 1][1];
+    Bm(6, 3 * j - 2) = gderiv[j - 1][2];
+    Bm(6, 3 * j) = gderiv[j - 1][0];
+  }
+#undef Bm
+}
+
+/* stiff(ld x ld, col-major) += B^T (D B) * wg over m columns; static_LIB_3d.f90:164-167 */
+static void add_BtDB(int m, const double *B, double D[6][6], double wg, double *stiff, int ld) {
+  double DB[6 * 33];
+  for (int j = 0; j < m; j++)
+    for (int i = 0; i < 6; i++) {
+      double s = 0.0;
+      for (int k = 0; k < 6; k++) s += D[i][k] * B[j * 6 + k];
+      DB[j * 6 + i] = s;
+    }
+  for (int j = 0; j < m; j++)
+    for (int i = 0; i < m; i++) {
+      double s = 0.0;
+      for (int k = 0; k < 6; k++) s += B[i * 6 + k] * DB[j * 6 + k];
+      stiff[(size_t)j * ld + i] += s * wg;
+    }
+}
+
+/* STF_C3, lib/static_LIB_3d.f90:47-205 (flag == INFINITE branch) */
+void orc_STF_C3(int etype, int nn, const double *ecoord, double E, double nu, double *stiff) {
+  double D[6][6], B[6 * 30], gderiv[20][3], det, wg, nc[3];
+  int m = 3 * nn;
+  memset(stiff, 0, sizeof(double) * m * m);
+  for (int LX = 1; LX <= num_quad_points(etype); LX++) {
+    get_quad_point(etype, LX, nc);
+    get_global_deriv(etype, nn, nc, ecoord, &det, gderiv);
+    cal_elastic_matrix(E, nu, D); /* MatlMatrix -> calElasticMatrix per Gauss point */
+    wg = get_weight(etype, LX) * det;
+    fill_B(nn, gderiv, B);
+    add_BtDB(m, B, D, wg, stiff, m);
+  }
+}
+
+/* STF_C3D8Bbar, lib/static_LIB_C3D8.f90:23-198 (flag == INFINITE branch) */
+void orc_STF_C3D8Bbar(int nn, const double *ecoord, double E, double nu, double *stiff) {
+  const int etype = 361;
+  double D[6][6], B[6 * 24], gderiv[8][3], Bbar[8][3], det, wg, nc[3] = {0, 0, 0};
+  int m = 3 * nn;
+#define Bm(i, j) B[((j)-1) * 6 + ((i)-1)]
+  memset(stiff, 0, sizeof(double) * m * m);
+  get_global_deriv(etype, nn, nc, ecoord, &det, Bbar); /* dilatation at centroid, :72-74 */
+  for (int LX = 1; LX <= 8; LX++) {
+    get_quad_point(etype, LX, nc);
+    get_global_deriv(etype, nn, nc, ecoord, &det, gderiv);
+    cal_elastic_matrix(E, nu, D);
+    wg = get_weight(etype, LX) * det;
+    memset(B, 0, sizeof(B));
+    for (int j = 1; j <= nn; j++) { /* :103-125 */
+      double B4 = (Bbar[j - 1][0] - gderiv[j - 1][0]) / 3.0;
+      double B6 = (Bbar[j - 1][1] - gderiv[j - 1][1]) / 3.0;
+      double B8 = (Bbar[j - 1][2] - gderiv[j - 1][2]) / 3.0;
+      Bm(1, 3 * j - 2) = gderiv[j - 1][0] + B4; Bm(1, 3 * j - 1) = B6; Bm(1, 3 * j) = B8;
+      Bm(2, 3 * j - 2) = B4; Bm(2, 3 * j - 1) = gderiv[j - 1][1] + B6; Bm(2, 3 * j) = B8;
+      Bm(3, 3 * j - 2) = B4; Bm(3, 3 * j - 1) = B6; Bm(3, 3 * j) = gderiv[j - 1][2] + B8;
+      Bm(4, 3 * j - 2) = gderiv[j - 1][1]; Bm(4, 3 * j - 1) = gderiv[j - 1][0];
+      Bm(5, 3 * j - 1) = gderiv[j - 1][2]; Bm(5, 3 * j) = gderiv[j - 1][1];
+      Bm(6, 3 * j - 2) = gderiv[j - 1][2]; Bm(6, 3 * j) = gderiv[j - 1][0];
+    }
+    add_BtDB(m, B, D, wg, stiff, m);
+  }
+#undef Bm
+}
+
+/* STF_C3D8IC, lib/static_LIB_3dIC.f90:21-215 (flag == INFINITE: no nddisp passed) */
+void orc_STF_C3D8IC(int nn, const double *ecoord, double E, double nu, double *stiff) {
+  const int etype = 361, ndof = 3;
+  const int mt = (nn + 3) * ndof; /* 33 */
+  const int m = nn * ndof;        /* 24 */
+  double D[6][6], B[6 * 33], gderiv[11][3];
+  double xj[81], jacobian[3][3], inverse[3][3], deriv[8][3];
+  double tmpstiff[33 * 33], tmpk[24 * 9];
+  double det, det0, wg, nc[3] = {0, 0, 0};
+#define TS(i, j) tmpstiff[((j)-1) * mt + ((i)-1)]
+  /* inverse of Jacobian at element centre times det, :79-81 */
+  shapederiv_hex8n(nc, deriv);
+  jacobian3(nn, ecoord, deriv, jacobian, &det0, inverse);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) inverse[i][j] = inverse[i][j] * det0;
+  memset(tmpstiff, 0, sizeof(tmpstiff));
+  for (int LX = 1; LX <= 8; LX++) {
+    get_quad_point(etype, LX, nc);
+    get_global_deriv(etype, nn, nc, ecoord, &det, gderiv);
+    cal_elastic_matrix(E, nu, D);
+    for (int j = 0; j < 3; j++) { /* :120-122 */
+      gderiv[nn + 0][j] = -2.0 * nc[0] * inverse[0][j] / det;
+      gderiv[nn + 1][j] = -2.0 * nc[1] * inverse[1][j] / det;
+      gderiv[nn + 2][j] = -2.0 * nc[2] * inverse[2][j] / det;
+    }
+    wg = get_weight(etype, LX) * det;
+    fill_B(nn + 3, gderiv, B);
+    add_BtDB(mt, B, D, wg, tmpstiff, mt);
+  }
+  /* condensation, :210-213 */
+  for (int j = 1; j <= 9; j++)
+    for (int i = 1; i <= 9; i++) xj[(j - 1) * 9 + (i - 1)] = TS(m + i, m + j);
+  orc_calInverse(9, xj);
+  for (int j = 1; j <= 9; j++) /* tmpk = Kda * xj */
+    for (int i = 1; i <= m; i++) {
+      double s = 0.0;
+      for (int k = 1; k <= 9; k++) s += TS(i, m + k) * xj[(j - 1) * 9 + (k - 1)];
+      tmpk[(j - 1) * m + (i - 1)] = s;
+    }
+  for (int j = 1; j <= m; j++)
+    for (int i = 1; i <= m; i++) {
+      double s = 0.0;
+      for (int k = 1; k <= 9; k++) s += tmpk[(k - 1) * m + (i - 1)] * TS(m + k, j);
+      stiff[(size_t)(j - 1) * m + (i - 1)] = TS(i, j) - s;
+    }
+#undef TS
+}
+
+/* ------------------------------------------------------------------------- */
+/* assembly: hecmw_mat_ass_elem (solver/matrix/hecmw_mat_ass.f90:31-166)       */
+/* ------------------------------------------------------------------------- */
+/* hecmw_array_search_i, mat_ass.f90:136-166 */
+static int array_search_i(const int *array, int is, int iE, int ival) {
+  int left = is, right = iE, center, cval;
+  for (;;) {
+    if (left > right) { center = -1; break; }
+    center = (left + right) / 2;
+    cval = array[center - 1];
+    if (ival < cval) right = center - 1;
+    else if (cval < ival) left = center + 1;
+    else break;
+  }
+  return center;
+}
+
+/* hecmw_mat_add_node, mat_ass.f90:70-134 ('!$omp atomic' per scalar) */
+static int mat_add_node(orc_matrix *mat, int inod, int jnod, const double a[3][3]) {
+  const int NDOF = 3;
+  int is, iE, k;
+  size_t idx_base;
+  double *dst;
+  if (inod < jnod) {
+    is = mat->indexU[inod - 1] + 1; iE = mat->indexU[inod];
+    k = array_search_i(mat->itemU, is, iE, jnod);
+    if (k < is || iE < k) { fprintf(stderr, "###ERROR### : cannot find connectivity (1)\n"); return -1; }
+    idx_base = (size_t)NDOF * NDOF * (k - 1); dst = mat->AU;
+  } else if (inod > jnod) {
+    is = mat->indexL[inod - 1] + 1; iE = mat->indexL[inod];
+    k = array_search_i(mat->itemL, is, iE, jnod);
+    if (k < is || iE < k) { fprintf(stderr, "###ERROR### : cannot find connectivity (2)\n"); return -1; }
+    idx_base = (size_t)NDOF * NDOF * (k - 1); dst = mat->AL;
+  } else {
+    idx_base = (size_t)NDOF * NDOF * (inod - 1); dst = mat->D;
+  }
+  for (int idof = 0; idof < NDOF; idof++)
+    for (int jdof = 0; jdof < NDOF; jdof++) {
+#ifdef _OPENMP
+#pragma omp atomic
+#endif
+      dst[idx_base + idof * NDOF + jdof] += a[idof][jdof];
+    }
+  return 0;
+}
+
+int orc_mat_ass_elem(orc_matrix *mat, int nn, const int *nodLOCAL, const double *stiffness, int ld) {
+  const int ndof = 3;
+  double a[3][3];
+  for (int inod_e = 1; inod_e <= nn; inod_e++) {
+    int inod = nodLOCAL[inod_e - 1];
+    for (int jnod_e = 1; jnod_e <= nn; jnod_e++) {
+      int jnod = nodLOCAL[jnod_e - 1];
+      for (int i = 0; i < ndof; i++) /* stf_get_block, :54-68 */
+        for (int j = 0; j < ndof; j++)
+          a[i][j] = stiffness[(size_t)(ndof * (jnod_e - 1) + j) * ld + ndof * (inod_e - 1) + i];
+      if (mat_add_node(mat, inod, jnod, a)) return -1;
+    }
+  }
+  return 0;
+}
+
+/* fstr_StiffMatrix, fistr1/src/analysis/static/fstr_StiffMatrix.f90:18-212 */
+int orc_stiffmatrix(const orc_mesh *mesh, const orc_section *sections, orc_matrix *mat) {
+  int rc = 0;
+  /* hecmw_mat_clear, matrix_misc.f90:125-133 */
+  memset(mat->D, 0, sizeof(double) * 9 * (size_t)mat->NP);
+  memset(mat->AL, 0, sizeof(double) * 9 * (size_t)mat->NPL);
+  memset(mat->AU, 0, sizeof(double) * 9 * (size_t)mat->NPU);
+  for (int itype = 1; itype <= mesh->n_elem_type; itype++) {
+    int is = mesh->elem_type_index[itype - 1] + 1;
+    int iE = mesh->elem_type_index[itype];
+    int ic_type = mesh->elem_type_item[itype - 1];
+    int nn = etype_max_node(ic_type);
+    if (ic_type != 361 && ic_type != 342) return -2;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (int icel = is; icel <= iE; icel++) {
+      double stiffness[30 * 30], ecoord[3 * 10];
+      int nodLOCAL[10];
+      int iiS = mesh->elem_node_index[icel - 1];
+      for (int j = 1; j <= nn; j++) {
+        nodLOCAL[j - 1] = mesh->elem_node_item[iiS + j - 1];
+        for (int i = 1; i <= 3; i++) ecoord[3 * (j - 1) + i - 1] = mesh->node[3 * (size_t)nodLOCAL[j - 1] + i - 4];
+      }
+      int isect = mesh->section_ID ? mesh->section_ID[icel - 1] : 1;
+      const orc_section *sec = &sections[isect - 1];
+      if (ic_type == 361) {
+        if (sec->elemopt361 == 1) orc_STF_C3(361, nn, ecoord, sec->E, sec->nu, stiffness);
+        else if (sec->elemopt361 == 2) orc_STF_C3D8Bbar(nn, ecoord, sec->E, sec->nu, stiffness);
+        else orc_STF_C3D8IC(nn, ecoord, sec->E, sec->nu, stiffness);
+      } else {
+        orc_STF_C3(ic_type, nn, ecoord, sec->E, sec->nu, stiffness);
+      }
+      if (orc_mat_ass_elem(mat, nn, nodLOCAL, stiffness, 3 * nn)) {
+#ifdef _OPENMP
+#pragma omp atomic write
+#endif
+        rc = -1;
+      }
+    }
+  }
+  return rc;
+}
+
+/* hecmw_mat_ass_bc, solver/matrix/hecmw_mat_ass.f90:292-429 (NDOF=3, no conMAT) */
+void orc_mat_ass_bc(orc_matrix *mat, int inode, int idof, double RHS) {
+  const int NDOF = 3, ndof2 = 9;
+  int i, ii, iii, k, is, iE, iiS, iiE, ik, in, idx;
+  double val;
+  double *D = mat->D - 1, *AL = mat->AL - 1, *AU = mat->AU - 1, *B = mat->B - 1; /* 1-based views */
+  const int *itemL = mat->itemL - 1, *itemU = mat->itemU - 1;
+  if (NDOF < idof) return;
+  B[NDOF * inode - (NDOF - idof)] = RHS;
+  ii = ndof2 - idof;
+  for (i = NDOF - 1; i >= 0; i--) {
+    if (i != NDOF - idof) {
+      idx = NDOF * inode - i;
+      val = D[(size_t)ndof2 * inode - ii] * RHS;
+      B[idx] = B[idx] - val;
+    }
+    ii = ii - NDOF;
+  }
+  ii = ndof2 - 1 - (idof - 1) * NDOF; /* diagonal row to zero */
+  for (i = 0; i <= NDOF - 1; i++) D[(size_t)ndof2 * inode - ii + i] = 0.0;
+  ii = ndof2 - idof; /* diagonal column to zero, 1 on the diagonal */
+  for (i = 1; i <= NDOF; i++) {
+    if (i != idof) D[(size_t)ndof2 * inode - ii] = 0.0;
+    else D[(size_t)ndof2 * inode - ii] = 1.0;
+    ii = ii - NDOF;
+  }
+  /* off-diagonal blocks */
+  ii = ndof2 - 1 - (idof - 1) * NDOF;
+  is = mat->indexL[inode - 1] + 1; iE = mat->indexL[inode];
+  for (k = is; k <= iE; k++) {
+    for (i = 0; i <= NDOF - 1; i++) AL[(size_t)ndof2 * k - ii + i] = 0.0; /* row (left) */
+    in = itemL[k]; /* column (upper) */
+    iiS = mat->indexU[in - 1] + 1; iiE = mat->indexU[in];
+    for (ik = iiS; ik <= iiE; ik++) {
+      if (itemU[ik] == inode) {
+        iii = ndof2 - idof;
+        for (i = NDOF - 1; i >= 0; i--) {
+          idx = NDOF * in - i;
+          val = AU[(size_t)ndof2 * ik - iii] * RHS;
+          B[idx] = B[idx] - val;
+          AU[(size_t)ndof2 * ik - iii] = 0.0;
+          iii = iii - NDOF;
+        }
+        break;
+      }
+    }
+  }
+  ii = ndof2 - 1 - (idof - 1) * NDOF;
+  is = mat->indexU[inode - 1] + 1; iE = mat->indexU[inode];
+  for (k = is; k <= iE; k++) {
+    for (i = 0; i <= NDOF - 1; i++) AU[(size_t)ndof2 * k - ii + i] = 0.0; /* row (right) */
+    in = itemU[k]; /* column (lower) */
+    iiS = mat->indexL[in - 1] + 1; iiE = mat->indexL[in];
+    for (ik = iiS; ik <= iiE; ik++) {
+      if (itemL[ik] == inode) {
+        iii = ndof2 - idof;
+        for (i = NDOF - 1; i >= 0; i--) {
+          idx = NDOF * in - i;
+          val = AL[(size_t)ndof2 * ik - iii] * RHS;
+          B[idx] = B[idx] - val;
+          AL[(size_t)ndof2 * ik - iii] = 0.0;
+          iii = iii - NDOF;
+        }
+        break;
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------- */
+/* SpMV: hecmw_matvec_33_inner (solver/las/hecmw_solver_las_33.f90:135-351)    */
+/* ------------------------------------------------------------------------- */
+void orc_matvec_33_local(const orc_matrix *mat, const double *Xv, double *Yv) {
+  const int N = mat->N;
+  const int *indexL = mat->indexL, *indexU = mat->indexU;
+  const int *itemL = mat->itemL - 1, *itemU = mat->itemU - 1;
+  const double *D = mat->D - 1, *AL = mat->AL - 1, *AU = mat->AU - 1, *X = Xv - 1;
+  double *Y = Yv - 1;
+  /* rows 1..N only; per row: D first, then L ascending, then U ascending (:269-295) */
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+  for (int i = 1; i <= N; i++) {
+    double X1 = X[3 * (size_t)i - 2], X2 = X[3 * (size_t)i - 1], X3 = X[3 * (size_t)i];
+    size_t d = 9 * (size_t)i;
+    double YV1 = MUL3(D[d - 8], X1, D[d - 7], X2, D[d - 6], X3);
+    double YV2 = MUL3(D[d - 5], X1, D[d - 4], X2, D[d - 3], X3);
+    double YV3 = MUL3(D[d - 2], X1, D[d - 1], X2, D[d], X3);
+    for (int j = indexL[i - 1] + 1; j <= indexL[i]; j++) {
+      size_t in = itemL[j], a = 9 * (size_t)j;
+      X1 = X[3 * in - 2]; X2 = X[3 * in - 1]; X3 = X[3 * in];
+      YV1 = MADD3(YV1, AL[a - 8], X1, AL[a - 7], X2, AL[a - 6], X3);
+      YV2 = MADD3(YV2, AL[a - 5], X1, AL[a - 4], X2, AL[a - 3], X3);
+      YV3 = MADD3(YV3, AL[a - 2], X1, AL[a - 1], X2, AL[a], X3);
+    }
+    for (int j = indexU[i - 1] + 1; j <= indexU[i]; j++) {
+      size_t in = itemU[j], a = 9 * (size_t)j;
+      X1 = X[3 * in - 2]; X2 = X[3 * in - 1]; X3 = X[3 * in];
+      YV1 = MADD3(YV1, AU[a - 8], X1, AU[a - 7], X2, AU[a - 6], X3);
+      YV2 = MADD3(YV2, AU[a - 5], X1, AU[a - 4], X2, AU[a - 3], X3);
+      YV3 = MADD3(YV3, AU[a - 2], X1, AU[a - 1], X2, AU[a], X3);
+    }
+    Y[3 * (size_t)i - 2] = YV1; Y[3 * (size_t)i - 1] = YV2; Y[3 * (size_t)i] = YV3;
+  }
+}
+
+/* hecmw_update_3_R -> HECMW_SOLVE_SEND_RECV_33 (communication/hecmw_solver_SR_33.F90:42-124),
+ * rank-emulated: the k-th value exported by rank s to rank r lands in the k-th
+ * import slot that r holds for neighbour s. */
+void orc_update_3_R(int ndom, const orc_mesh *meshes, double **X) {
+  for (int r = 0; r < ndom; r++) {
+    const orc_mesh *mr = &meshes[r];
+    for (int nb = 0; nb < mr->n_neighbor_pe; nb++) {
+      int s = mr->neighbor_pe[nb];
+      const orc_mesh *ms = &meshes[s];
+      int nbs = -1;
+      for (int q = 0; q < ms->n_neighbor_pe; q++)
+        if (ms->neighbor_pe[q] == r) { nbs = q; break; }
+      if (nbs < 0) { fprintf(stderr, "orc_update_3_R: asymmetric neighbour tables\n"); abort(); }
+      int ir0 = mr->import_index[nb], inum = mr->import_index[nb + 1] - ir0;
+      int es0 = ms->export_index[nbs], enum_ = ms->export_index[nbs + 1] - es0;
+      if (inum != enum_) { fprintf(stderr, "orc_update_3_R: import/export count mismatch\n"); abort(); }
+      for (int k = 0; k < inum; k++) {
+        size_t src = 3 * (size_t)ms->export_item[es0 + k], dst = 3 * (size_t)mr->import_item[ir0 + k];
+        X[r][dst - 3] = X[s][src - 3]; X[r][dst - 2] = X[s][src - 2]; X[r][dst - 1] = X[s][src - 1];
+      }
+    }
+  }
+}
+
+static double g_time_Ax, g_time_precond, g_time_comm;
+
+void orc_matvec_33(int ndom, const orc_mesh *meshes, orc_matrix *mats, double **X, double **Y) {
+  double t0 = wtime();
+  if (ndom > 1) orc_update_3_R(ndom, meshes, X);
+  double t1 = wtime();
+  for (int d = 0; d < ndom; d++) orc_matvec_33_local(&mats[d], X[d], Y[d]);
+  g_time_comm += t1 - t0;
+  g_time_Ax += wtime() - t1;
+}
+
+/* hecmw_matresid_33, las_33.f90:358-380 */
+static void matresid_33(int ndom, const orc_mesh *meshes, orc_matrix *mats, double **X, double **B,
+                        double **R) {
+  orc_matvec_33(ndom, meshes, mats, X, R);
+  for (int d = 0; d < ndom; d++) {
+    int n3 = 3 * mats[d].N;
+    double *r = R[d];
+    const double *b = B[d];
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (int i = 0; i < n3; i++) r[i] = b[i] - r[i];
+  }
+}
+
+/* hecmw_InnerProduct_R, communication/hecmw_solver_misc.f90:46-70: serial sum over
+ * 3*nn_internal then allreduce(SUM) — emulated as a rank-ordered sum. */
+static double inner_product(int ndom, const orc_mesh *meshes, double **X, double **Y) {
+  double total = 0.0;
+  for (int d = 0; d < ndom; d++) {
+    double sum = 0.0;
+    int n3 = 3 * meshes[d].nn_internal;
+    const double *x = X[d], *y = Y[d];
+    for (int i = 0; i < n3; i++) sum = fma(x[i], y[i], sum);
+    total += sum;
+  }
+  return total;
+}
+
+/* ------------------------------------------------------------------------- */
+/* preconditioners                                                             */
+/* ------------------------------------------------------------------------- */
+struct orc_precond {
+  int kind; /* 3 = DIAG, 1/2 = SSOR */
+  int N;
+  double *ALU;
+  /* SSOR private permuted copy */
+  double *D, *AL, *AU;
+  int *indexL, *indexU, *itemL, *itemU;
+  int NColor, *COLORindex, *perm, *iperm;
+};
+
+/* 3x3 LU without pivoting storing reciprocal pivots, DIAG_33.f90:82-117 == SSOR_33.f90:178-213 */
+static void block_lu(int N, double *ALU, double SIGMA_DIAG) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+  for (int ii = 1; ii <= N; ii++) {
+    double T[4][4], PW[4];
+    double *a = ALU + 9 * (size_t)(ii - 1);
+    T[1][1] = a[0] * SIGMA_DIAG; T[1][2] = a[1]; T[1][3] = a[2];
+    T[2][1] = a[3]; T[2][2] = a[4] * SIGMA_DIAG; T[2][3] = a[5];
+    T[3][1] = a[6]; T[3][2] = a[7]; T[3][3] = a[8] * SIGMA_DIAG;
+    for (int k = 1; k <= 3; k++) {
+      T[k][k] = 1.0 / T[k][k];
+      for (int i = k + 1; i <= 3; i++) {
+        T[i][k] = T[i][k] * T[k][k];
+        for (int j = k + 1; j <= 3; j++) PW[j] = fma(-T[i][k], T[k][j], T[i][j]);
+        for (int j = k + 1; j <= 3; j++) T[i][j] = PW[j];
+      }
+    }
+    a[0] = T[1][1]; a[1] = T[1][2]; a[2] = T[1][3];
+    a[3] = T[2][1]; a[4] = T[2][2]; a[5] = T[2][3];
+    a[6] = T[3][1]; a[7] = T[3][2]; a[8] = T[3][3];
+  }
+}
+
+/* forward/back substitution with the factored 3x3 block, DIAG_33.f90:136-148 */
+static inline void block_solve(const double *a /* ALU(9*i-8 ..) */, double *X1p, double *X2p, double *X3p) {
+  double X1 = *X1p, X2 = *X2p, X3 = *X3p;
+  X2 = fma(-a[3], X1, X2);
+  X3 = fma(-a[7], X2, fma(-a[6], X1, X3));
+  X3 = a[8] * X3;
+  X2 = a[4] * fma(-a[5], X3, X2);
+  X1 = a[0] * fma(-a[1], X2, fma(-a[2], X3, X1));
+  *X1p = X1; *X2p = X2; *X3p = X3;
+}
+
+/* hecmw_matrix_ordering_CM / RCM, matrix/hecmw_matrix_ordering_CM.f90:15-190 */
+static void ordering_CM_inner(int N, const int *indexL, const int *itemL, const int *indexU,
+                              const int *itemU, int nstart, int *nlevel, int *lv_index, int *lv_item) {
+  int *iwk = calloc(N + 1, sizeof(int));
+  int cntall, cnt;
+  lv_index[0] = 0;
+  iwk[nstart] = 1;
+  cntall = 1;
+  lv_item[1 - 1] = nstart;
+  lv_index[1] = 1;
+  *nlevel = 1;
+  for (int level = 2; level <= N; level++) {
+    cnt = 0;
+    int done = 0;
+    for (int j = lv_index[level - 2] + 1; j <= lv_index[level - 1] && !done; j++) {
+      int jnode = lv_item[j - 1];
+      for (int k = indexL[jnode - 1] + 1; k <= indexL[jnode]; k++) {
+        int knode = itemL[k - 1];
+        if (iwk[knode] == 0) {
+          iwk[knode] = level; cnt++; cntall++;
+          lv_item[cntall - 1] = knode;
+          if (cntall == N) { done = 1; break; }
+        }
+      }
+      if (done) break;
+      for (int k = indexU[jnode - 1] + 1; k <= indexU[jnode]; k++) {
+        int knode = itemU[k - 1];
+        if (knode > N) continue;
+        if (iwk[knode] == 0) {
+          iwk[knode] = level; cnt++; cntall++;
+          lv_item[cntall - 1] = knode;
+          if (cntall == N) { done = 1; break; }
+        }
+      }
+    }
+    if (cnt == 0) {
+      for (int knode = 1; knode <= N; knode++)
+        if (iwk[knode] == 0) {
+          iwk[knode] = level; cnt++; cntall++;
+          lv_item[cntall - 1] = knode;
+          break;
+        }
+    }
+    lv_index[level] = cntall;
+    if (cntall == N) { *nlevel = level; break; }
+  }
+  free(iwk);
+}
+
+static void ordering_RCM(int N, const int *indexL, const int *itemL, const int *indexU, const int *itemU,
+                         int *perm, int *iperm) {
+  enum { NMINMAX = 5 };
+  int mins[NMINMAX], nmin = 0, degmin = N;
+  /* find_minimum_degrees, :146-176 */
+  for (int i = 1; i <= N; i++) {
+    int deg = indexL[i] - indexL[i - 1];
+    for (int j = indexU[i - 1] + 1; j <= indexU[i]; j++)
+      if (itemU[j - 1] <= N) deg++;
+    if (deg == 0) continue;
+    if (deg < degmin) { degmin = deg; nmin = 1; mins[0] = i; }
+    else if (deg == degmin) { nmin++; if (nmin <= NMINMAX) mins[nmin - 1] = i; }
+  }
+  if (nmin > NMINMAX) nmin = NMINMAX;
+  if (nmin == 0) { /* no connected node at all: identity */
+    for (int i = 1; i <= N; i++) { perm[i - 1] = i; iperm[i - 1] = i; }
+  } else {
+    int *nlevel = malloc(sizeof(int) * nmin);
+    int **lv_index = malloc(sizeof(int *) * nmin), **lv_item = malloc(sizeof(int *) * nmin);
+    for (int i = 0; i < nmin; i++) {
+      lv_index[i] = calloc(N + 1, sizeof(int));
+      lv_item[i] = calloc(N, sizeof(int));
+      ordering_CM_inner(N, indexL, itemL, indexU, itemU, mins[i], &nlevel[i], lv_index[i], lv_item[i]);
+    }
+    int nlevel_max = nlevel[0], max_id = 0;
+    for (int i = 1; i < nmin; i++)
+      if (nlevel[i] > nlevel_max) { nlevel_max = nlevel[i]; max_id = i; }
+    for (int i = 1; i <= N; i++) {
+      perm[i - 1] = lv_item[max_id][i - 1];
+      iperm[perm[i - 1] - 1] = i;
+    }
+    for (int i = 0; i < nmin; i++) { free(lv_index[i]); free(lv_item[i]); }
+    free(nlevel); free(lv_index); free(lv_item);
+  }
+  /* reverse_ordering, :178-188 — note: maps the node id, as the reference does */
+  for (int i = 1; i <= N; i++) {
+    perm[i - 1] = N + 1 - perm[i - 1];
+    iperm[perm[i - 1] - 1] = i;
+  }
+}
+
+/* hecmw_matrix_ordering_MC, matrix/hecmw_matrix_ordering_MC.f90:15-71 */
+static void ordering_MC(int N, const int *indexL, const int *itemL, const int *indexU, const int *itemU,
+                        const int *perm_cur, int ncolor_in, int *ncolor_out, int *COLORindex, int *perm,
+                        int *iperm) {
+  int *iwk = calloc(N + 1, sizeof(int));
+  int nn_color = N / ncolor_in, cntall = 0, cnt;
+  COLORindex[0] = 0;
+  *ncolor_out = 0;
+  for (int color = 1; color <= N; color++) {
+    cnt = 0;
+    for (int i = 1; i <= N; i++) {
+      int inode = perm_cur[i - 1];
+      if (iwk[inode] > 0 || iwk[inode] == -1) continue;
+      iwk[inode] = color;
+      cntall++;
+      perm[cntall - 1] = inode;
+      cnt++;
+      if (cnt == nn_color) break;
+      if (cntall == N) break;
+      for (int j = indexL[inode - 1] + 1; j <= indexL[inode]; j++) {
+        int jnode = itemL[j - 1];
+        if (iwk[jnode] == 0) iwk[jnode] = -1;
+      }
+      for (int j = indexU[inode - 1] + 1; j <= indexU[inode]; j++) {
+        int jnode = itemU[j - 1];
+        if (jnode > N) continue;
+        if (iwk[jnode] == 0) iwk[jnode] = -1;
+      }
+    }
+    COLORindex[color] = cntall;
+    if (cntall == N) { *ncolor_out = color; break; }
+    for (int i = 1; i <= N; i++)
+      if (iwk[i] == -1) iwk[i] = 0;
+  }
+  free(iwk);
+  for (int i = 1; i <= N; i++) iperm[perm[i - 1] - 1] = i;
+}
+
+static int cmp_int(const void *a, const void *b) { return *(const int *)a - *(const int *)b; }
+
+static int bsearch_int(const int *array, int is, int iE, int val) { /* 1-based positions, -1 if absent */
+  int lo = is, hi = iE;
+  while (lo <= hi) {
+    int c = (lo + hi) / 2;
+    if (array[c - 1] < val) lo = c + 1;
+    else if (array[c - 1] > val) hi = c - 1;
+    else return c;
+  }
+  return -1;
+}
+
+orc_precond *orc_precond_setup(const orc_matrix *mat, int precond, double sigma_diag, int ncolor_in,
+                               int nthreads_emulated) {
+  orc_precond *pc = calloc(1, sizeof(*pc));
+  const int N = mat->N;
+  pc->kind = precond;
+  pc->N = N;
+  if (precond == 3) { /* hecmw_precond_DIAG_33_setup, precond/33/hecmw_precond_DIAG_33.f90:27-123 */
+    pc->ALU = calloc(9 * (size_t)mat->NP, sizeof(double));
+    memcpy(pc->ALU, mat->D, sizeof(double) * 9 * (size_t)N);
+    block_lu(N, pc->ALU, sigma_diag);
+    return pc;
+  }
+  /* hecmw_precond_SSOR_33_setup, precond/33/hecmw_precond_SSOR_33.f90:55-220 */
+  pc->perm = malloc(sizeof(int) * (N > 0 ? N : 1));
+  pc->iperm = malloc(sizeof(int) * (N > 0 ? N : 1));
+  if (nthreads_emulated == 1) {
+    pc->NColor = 1;
+    pc->COLORindex = malloc(sizeof(int) * 2);
+    pc->COLORindex[0] = 0; pc->COLORindex[1] = N;
+    for (int i = 1; i <= N; i++) { pc->perm[i - 1] = i; pc->iperm[i - 1] = i; }
+  } else {
+    int *perm_tmp = malloc(sizeof(int) * (N > 0 ? N : 1));
+    pc->COLORindex = calloc(N + 1, sizeof(int));
+    ordering_RCM(N, mat->indexL, mat->itemL, mat->indexU, mat->itemU, perm_tmp, pc->iperm);
+    ordering_MC(N, mat->indexL, mat->itemL, mat->indexU, mat->itemU, perm_tmp, ncolor_in, &pc->NColor,
+                pc->COLORindex, pc->perm, pc->iperm);
+    free(perm_tmp);
+  }
+  int NPL = mat->indexL[N], NPU = mat->indexU[N];
+  pc->indexL = calloc(N + 1, sizeof(int)); pc->indexU = calloc(N + 1, sizeof(int));
+  pc->itemL = malloc(sizeof(int) * (size_t)(NPL + NPU + 1));
+  pc->itemU = malloc(sizeof(int) * (size_t)(NPL + NPU + 1));
+  /* hecmw_matrix_reorder_profile, matrix/hecmw_matrix_reorder.f90:19-65 (halo columns dropped) */
+  int cntL = 0, cntU = 0;
+  for (int inew = 1; inew <= N; inew++) {
+    int iold = pc->perm[inew - 1];
+    for (int j = mat->indexL[iold - 1] + 1; j <= mat->indexL[iold]; j++) {
+      int jold = mat->itemL[j - 1], jnew = pc->iperm[jold - 1];
+      if (jnew < inew) pc->itemL[cntL++] = jnew; else pc->itemU[cntU++] = jnew;
+    }
+    for (int j = mat->indexU[iold - 1] + 1; j <= mat->indexU[iold]; j++) {
+      int jold = mat->itemU[j - 1];
+      if (jold > N) continue;
+      int jnew = pc->iperm[jold - 1];
+      if (jnew < inew) pc->itemL[cntL++] = jnew; else pc->itemU[cntU++] = jnew;
+    }
+    pc->indexL[inew] = cntL; pc->indexU[inew] = cntU;
+    qsort(pc->itemL + pc->indexL[inew - 1], cntL - pc->indexL[inew - 1], sizeof(int), cmp_int);
+    qsort(pc->itemU + pc->indexU[inew - 1], cntU - pc->indexU[inew - 1], sizeof(int), cmp_int);
+  }
+  /* hecmw_matrix_reorder_values, :67-96 + reorder_diag2/off_diag2 :178-300 */
+  pc->D = calloc(9 * (size_t)(N > 0 ? N : 1), sizeof(double));
+  pc->AL = calloc(9 * (size_t)(cntL > 0 ? cntL : 1), sizeof(double));
+  pc->AU = calloc(9 * (size_t)(cntU > 0 ? cntU : 1), sizeof(double));
+  for (int iold = 1; iold <= N; iold++) {
+    int inew = pc->iperm[iold - 1];
+    memcpy(pc->D + 9 * (size_t)(inew - 1), mat->D + 9 * (size_t)(iold - 1), 9 * sizeof(double));
+    for (int pass = 0; pass < 2; pass++) {
+      const int *indexX = pass ? mat->indexU : mat->indexL, *itemX = pass ? mat->itemU : mat->itemL;
+      const double *AX = pass ? mat->AU : mat->AL;
+      for (int jold = indexX[iold - 1] + 1; jold <= indexX[iold]; jold++) {
+        int kold = itemX[jold - 1];
+        if (kold > N) continue;
+        int knew = pc->iperm[kold - 1], jnew;
+        if (knew < inew) {
+          jnew = bsearch_int(pc->itemL, pc->indexL[inew - 1] + 1, pc->indexL[inew], knew);
+          memcpy(pc->AL + 9 * (size_t)(jnew - 1), AX + 9 * (size_t)(jold - 1), 9 * sizeof(double));
+        } else {
+          jnew = bsearch_int(pc->itemU, pc->indexU[inew - 1] + 1, pc->indexU[inew], knew);
+          memcpy(pc->AU + 9 * (size_t)(jnew - 1), AX + 9 * (size_t)(jold - 1), 9 * sizeof(double));
+        }
+      }
+    }
+  }
+  /* hecmw_matrix_reorder_renum_item, :142-157: column ids back to OLD numbering */
+  for (int i = 0; i < cntL; i++) pc->itemL[i] = pc->perm[pc->itemL[i] - 1];
+  for (int i = 0; i < cntU; i++) pc->itemU[i] = pc->perm[pc->itemU[i] - 1];
+  pc->ALU = calloc(9 * (size_t)(N > 0 ? N : 1), sizeof(double));
+  memcpy(pc->ALU, pc->D, sizeof(double) * 9 * (size_t)N);
+  block_lu(N, pc->ALU, sigma_diag);
+  return pc;
+}
+
+int orc_precond_ncolor(const orc_precond *pc) { return pc->kind == 3 ? 0 : pc->NColor; }
+void orc_precond_perm(const orc_precond *pc, int *perm) {
+  if (pc->perm) memcpy(perm, pc->perm, sizeof(int) * pc->N);
+}
+
+void orc_precond_apply(const orc_precond *pc, double *ZPv) {
+  double *ZP = ZPv - 1;
+  const int N = pc->N;
+  if (pc->kind == 3) { /* hecmw_precond_DIAG_33_apply, DIAG_33.f90:125-152 */
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (int i = 1; i <= N; i++)
+      block_solve(pc->ALU + 9 * (size_t)(i - 1), &ZP[3 * (size_t)i - 2], &ZP[3 * (size_t)i - 1], &ZP[3 * (size_t)i]);
+    return;
+  }
+  /* hecmw_precond_SSOR_33_apply, SSOR_33.f90:222-420: rows visited in the new order colour by
+   * colour; inside a colour rows are independent, so a serial visit equals the threaded one. */
+  const int *itemL = pc->itemL - 1, *itemU = pc->itemU - 1;
+  const double *AL = pc->AL - 1, *AU = pc->AU - 1;
+  for (int ic = 1; ic <= pc->NColor; ic++) { /* FORWARD */
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (int i = pc->COLORindex[ic - 1] + 1; i <= pc->COLORindex[ic]; i++) {
+      size_t iold = pc->perm[i - 1];
+      double SW1 = ZP[3 * iold - 2], SW2 = ZP[3 * iold - 1], SW3 = ZP[3 * iold];
+      for (int j = pc->indexL[i - 1] + 1; j <= pc->indexL[i]; j++) {
+        size_t k = itemL[j], a = 9 * (size_t)j;
+        double X1 = ZP[3 * k - 2], X2 = ZP[3 * k - 1], X3 = ZP[3 * k];
+        SW1 = MSUB3(SW1, AL[a - 8], X1, AL[a - 7], X2, AL[a - 6], X3);
+        SW2 = MSUB3(SW2, AL[a - 5], X1, AL[a - 4], X2, AL[a - 3], X3);
+        SW3 = MSUB3(SW3, AL[a - 2], X1, AL[a - 1], X2, AL[a], X3);
+      }
+      block_solve(pc->ALU + 9 * (size_t)(i - 1), &SW1, &SW2, &SW3);
+      ZP[3 * iold - 2] = SW1; ZP[3 * iold - 1] = SW2; ZP[3 * iold] = SW3;
+    }
+  }
+  for (int ic = pc->NColor; ic >= 1; ic--) { /* BACKWARD */
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (int i = pc->COLORindex[ic]; i >= pc->COLORindex[ic - 1] + 1; i--) {
+      double SW1 = 0.0, SW2 = 0.0, SW3 = 0.0;
+      for (int j = pc->indexU[i]; j >= pc->indexU[i - 1] + 1; j--) {
+        size_t k = itemU[j], a = 9 * (size_t)j;
+        double X1 = ZP[3 * k - 2], X2 = ZP[3 * k - 1], X3 = ZP[3 * k];
+        SW1 = MADD3(SW1, AU[a - 8], X1, AU[a - 7], X2, AU[a - 6], X3);
+        SW2 = MADD3(SW2, AU[a - 5], X1, AU[a - 4], X2, AU[a - 3], X3);
+        SW3 = MADD3(SW3, AU[a - 2], X1, AU[a - 1], X2, AU[a], X3);
+      }
+      block_solve(pc->ALU + 9 * (size_t)(i - 1), &SW1, &SW2, &SW3);
+      size_t iold = pc->perm[i - 1];
+      ZP[3 * iold - 2] -= SW1; ZP[3 * iold - 1] -= SW2; ZP[3 * iold] -= SW3;
+    }
+  }
+}
+
+void orc_precond_free(orc_precond *pc) {
+  if (!pc) return;
+  free(pc->ALU); free(pc->D); free(pc->AL); free(pc->AU);
+  free(pc->indexL); free(pc->indexU); free(pc->itemL); free(pc->itemU);
+  free(pc->COLORindex); free(pc->perm); free(pc->iperm);
+  free(pc);
+}
+
+/* hecmw_precond_apply + hecmw_precond_33_apply (precond/hecmw_precond.f90:75-123,
+ * precond/33/hecmw_precond_33.f90:74-115) */
+static void precond_apply(int ndom, const orc_mesh *meshes, orc_matrix *mats, orc_precond **pcs,
+                          int iterPREmax, double **R, double **Z, double **ZP) {
+  if (iterPREmax <= 0) {
+    for (int d = 0; d < ndom; d++) memcpy(Z[d], R[d], sizeof(double) * 3 * (size_t)mats[d].N);
+    return;
+  }
+  for (int d = 0; d < ndom; d++) {
+    size_t nn = 3 * (size_t)mats[d].N, np = 3 * (size_t)mats[d].NP;
+    memcpy(ZP[d], R[d], sizeof(double) * nn);
+    memset(ZP[d] + nn, 0, sizeof(double) * (np - nn));
+    memset(Z[d], 0, sizeof(double) * np);
+  }
+  for (int iterPRE = 1; iterPRE <= iterPREmax; iterPRE++) {
+    double t0 = wtime();
+    for (int d = 0; d < ndom; d++) orc_precond_apply(pcs[d], ZP[d]);
+    g_time_precond += wtime() - t0;
+    for (int d = 0; d < ndom; d++) { /* additive Schwarz */
+      size_t nn = 3 * (size_t)mats[d].N;
+      for (size_t i = 0; i < nn; i++) Z[d][i] = Z[d][i] + ZP[d][i];
+    }
+    if (iterPRE == iterPREmax) break;
+    matresid_33(ndom, meshes, mats, Z, R, ZP); /* ZP = R - A Z */
+  }
+}
+
+/* ------------------------------------------------------------------------- */
+/* hecmw_solve -> hecmw_solve_iterative -> hecmw_solve_CG                      */
+/* (solver/hecmw_solver.f90:9-78, iterative/hecmw_solver_Iterative.f90:13-210, */
+/*  iterative/hecmw_solver_CG.f90:19-312)                                      */
+/* ------------------------------------------------------------------------- */
+#define IA(m, slot) ((m)->Iarray[(slot)-1])
+#define RA(m, slot) ((m)->Rarray[(slot)-1])
+
+/* module-level SAVE state of the reference preconditioners (one live factorisation) */
+static orc_precond **g_pcs;
+static int g_pcs_n;
+
+static void precond_clear_all(void) {
+  for (int d = 0; d < g_pcs_n; d++) orc_precond_free(g_pcs[d]);
+  free(g_pcs);
+  g_pcs = NULL; g_pcs_n = 0;
+}
+
+static int g_ssor_threads = 0; /* 0: follow OpenMP thread count like the reference */
+void orc_set_ssor_threads(int n) { g_ssor_threads = n; }
+
+int orc_solve(int ndom, const orc_mesh *meshes, orc_matrix *mats, int *iter_out, double *resid_out,
+              double *resid2_out, double *hist, int hist_len, double *times) {
+  orc_matrix *m0 = &mats[0];
+  int error = 0;
+  if (IA(m0, 99) != 1) return -99; /* direct solvers are out of scope */
+  int MAXIT = IA(m0, 1), METHOD = IA(m0, 2), PRECOND = IA(m0, 3), iterPREmax = IA(m0, 5);
+  int ITERlog = IA(m0, 21);
+  double TOL = RA(m0, 1), SIGMA_DIAG = RA(m0, 2);
+  int ITER = 0;
+  double RESID = 0.0;
+  if (SIGMA_DIAG < 0.0) SIGMA_DIAG = 1.0;
+  *iter_out = 0; *resid_out = 0.0; if (resid2_out) *resid2_out = 0.0;
+
+  /* hecmw_solve_check_zerorhs, Iterative.f90:246-278 */
+  {
+    double RHS = 0.0;
+    for (int d = 0; d < ndom; d++) {
+      double s = 0.0;
+      for (int i = 0; i < 3 * mats[d].N; i++) s += mats[d].B[i] * mats[d].B[i];
+      RHS += s;
+    }
+    if (RHS == 0.0) {
+      for (int d = 0; d < ndom; d++) memset(mats[d].X, 0, sizeof(double) * 3 * (size_t)mats[d].NP);
+      /* the reference only returns from the check routine; the driver continues and CG
+       * sees BNRM2==0 (CG.f90:124-129) and leaves with iter=0, X=0. */
+      error = 2002;
+    }
+  }
+  /* hecmw_solve_check_zerodiag, Iterative.f90:212-244 */
+  {
+    int zd = 0;
+    for (int d = 0; d < ndom; d++)
+      for (int i = 1; i <= mats[d].N; i++)
+        for (int j = 1; j <= 3; j++)
+          if (fabs(mats[d].D[9 * (size_t)(i - 1) + (j - 1) * 4]) == 0.0) zd = 2001;
+    if (zd && PRECOND < 10 && iterPREmax > 0) return 2001; /* reference aborts */
+  }
+  /* hecmw_mat_recycle_precond_setting, matrix_misc.f90:678-697 */
+  if (IA(m0, 98) >= 1) { IA(m0, 97) = 1; IA(m0, 96) = 0; }
+  else if (IA(m0, 97) > 1) { IA(m0, 96) = 0; IA(m0, 97) = 1; }
+  else if (IA(m0, 97) == 1) {
+    if (IA(m0, 96) < IA(m0, 35)) { IA(m0, 97) = 0; IA(m0, 96) = IA(m0, 96) + 1; }
+    else IA(m0, 96) = 0;
+  }
+  IA(m0, 81) = 0; IA(m0, 82) = 0;
+  if (METHOD != 1) return 1001;
+  if (!(PRECOND == 1 || PRECOND == 2 || PRECOND == 3)) return 1001;
+
+  g_time_Ax = g_time_precond = g_time_comm = 0.0;
+  double S_TIME = wtime();
+  /* ---- hecmw_solve_CG ---- */
+  double **R = malloc(sizeof(double *) * ndom), **Z = malloc(sizeof(double *) * ndom);
+  double **P = malloc(sizeof(double *) * ndom), **WK = malloc(sizeof(double *) * ndom);
+  double **X = malloc(sizeof(double *) * ndom), **B = malloc(sizeof(double *) * ndom);
+  for (int d = 0; d < ndom; d++) { /* WW(NDOF*NP,4)=0 ; R=1, Z=Q=2, P=3, WK=4 (CG.f90:47-51,94-95) */
+    size_t np = 3 * (size_t)mats[d].NP;
+    R[d] = calloc(np, sizeof(double)); Z[d] = calloc(np, sizeof(double));
+    P[d] = calloc(np, sizeof(double)); WK[d] = calloc(np, sizeof(double));
+    X[d] = mats[d].X; B[d] = mats[d].B;
+  }
+  double **Q = Z;
+  /* hecmw_precond_setup, honouring the recycle flags (DIAG_33.f90:38-41, SSOR_33.f90:72-80) */
+  if (iterPREmax > 0) {
+    int need = 1;
+    if (g_pcs && g_pcs_n == ndom && g_pcs[0]->kind == PRECOND && g_pcs[0]->N == mats[0].N) {
+      if (IA(m0, 98) == 0 && IA(m0, 97) == 0) need = 0;
+    }
+    if (need) {
+      precond_clear_all();
+      g_pcs = calloc(ndom, sizeof(*g_pcs)); g_pcs_n = ndom;
+      int nth = g_ssor_threads > 0 ? g_ssor_threads : orc_num_threads();
+      for (int d = 0; d < ndom; d++)
+        g_pcs[d] = orc_precond_setup(&mats[d], PRECOND, SIGMA_DIAG, IA(m0, 34), nth);
+    }
+    IA(m0, 98) = 0; IA(m0, 97) = 0;
+  }
+  matresid_33(ndom, meshes, mats, X, B, R);            /* r0 = b - A x0, CG.f90:120 */
+  double BNRM2 = inner_product(ndom, meshes, B, B);    /* :123 */
+  if (BNRM2 == 0.0) {
+    ITER = 0; MAXIT = 0; RESID = 0.0;
+    for (int d = 0; d < ndom; d++) memset(X[d], 0, sizeof(double) * 3 * (size_t)mats[d].NP);
+  }
+  double Tset = wtime() - S_TIME;
+  g_time_comm = 0.0;
+  double S1_TIME = wtime();
+  double RHO = 0.0, RHO1 = 0.0, BETA = 0.0, C1, ALPHA, DNRM2;
+  int n_indef_precond = 0, exited = 0;
+  for (ITER = 1; ITER <= MAXIT; ITER++) {
+    precond_apply(ndom, meshes, mats, g_pcs, iterPREmax, R, Z, WK); /* z = Minv r, :160 */
+    RHO = inner_product(ndom, meshes, R, Z);                        /* :168 */
+    if (RHO == 0.0) { exited = 1; break; }
+    else if (ITER > 1 && RHO * RHO1 <= 0) {
+      n_indef_precond++;
+      if (n_indef_precond >= 3) { error = 3003; exited = 1; break; }
+    }
+    if (ITER == 1) { /* :188-197, serial loops in the reference */
+      for (int d = 0; d < ndom; d++)
+        for (size_t i = 0; i < 3 * (size_t)mats[d].N; i++) P[d][i] = Z[d][i];
+    } else {
+      BETA = RHO / RHO1;
+      for (int d = 0; d < ndom; d++)
+        for (size_t i = 0; i < 3 * (size_t)mats[d].N; i++) P[d][i] = fma(BETA, P[d][i], Z[d][i]);
+    }
+    orc_matvec_33(ndom, meshes, mats, P, Q);           /* q = A p, :204 */
+    C1 = inner_product(ndom, meshes, P, Q);            /* :211 */
+    if (C1 <= 0) { error = 3002; exited = 1; break; }
+    ALPHA = RHO / C1;
+    for (int d = 0; d < ndom; d++)
+      for (size_t i = 0; i < 3 * (size_t)mats[d].N; i++) X[d][i] = fma(ALPHA, P[d][i], X[d][i]);
+    if (ITER % 50 == 0) {                              /* N_ITER_RECOMPUTE_R, :232-238 */
+      matresid_33(ndom, meshes, mats, X, B, R);
+    } else {
+      for (int d = 0; d < ndom; d++)
+        for (size_t i = 0; i < 3 * (size_t)mats[d].N; i++) R[d][i] = fma(-ALPHA, Q[d][i], R[d][i]);
+    }
+    DNRM2 = inner_product(ndom, meshes, R, R);         /* :240 */
+    RESID = sqrt(DNRM2 / BNRM2);
+    if (ITERlog == 1) printf("%7d%16.6E\n", ITER, RESID);
+    if (hist && ITER <= hist_len) hist[ITER - 1] = RESID;
+    if (RESID <= TOL) {                                /* :259-266 */
+      if (ITER % 50 == 0) { exited = 1; break; }
+      matresid_33(ndom, meshes, mats, X, B, R);
+      DNRM2 = inner_product(ndom, meshes, R, R);
+      RESID = sqrt(DNRM2 / BNRM2);
+      if (RESID <= TOL) { exited = 1; break; }
+    }
+    if (ITER == MAXIT) error = 3001;
+    RHO1 = RHO;
+  }
+  (void)exited; /* on natural loop end Fortran leaves ITER = MAXIT+1, as here */
+  if (ndom > 1) orc_update_3_R(ndom, meshes, X);       /* hecmw_update_m_R, :280 */
+  double Tsol = wtime() - S1_TIME;
+  /* ---- back in hecmw_solve_iterative ---- */
+  if (error == 3002 || error == 3003) IA(m0, 82) = 1;
+  /* resid2 = hecmw_rel_resid_L2, las_33.f90:387-415 */
+  {
+    double bnorm2 = inner_product(ndom, meshes, B, B);
+    if (bnorm2 == 0.0) bnorm2 = 1.0;
+    matresid_33(ndom, meshes, mats, X, B, WK);
+    double rnorm2 = inner_product(ndom, meshes, WK, WK);
+    double resid2 = sqrt(rnorm2 / bnorm2);
+    if (resid2_out) *resid2_out = resid2;
+    if (resid2 < RA(m0, 1)) IA(m0, 81) = 1;
+  }
+  for (int d = 1; d < ndom; d++) { /* every rank holds the same control arrays */
+    memcpy(mats[d].Iarray, m0->Iarray, sizeof(int) * 100);
+  }
+  *iter_out = ITER; *resid_out = RESID;
+  if (times) { times[0] = Tset; times[1] = Tsol; times[2] = g_time_comm; times[3] = g_time_Ax; times[4] = g_time_precond; }
+  for (int d = 0; d < ndom; d++) { free(R[d]); free(Z[d]); free(P[d]); free(WK[d]); }
+  free(R); free(Z); free(P); free(WK); free(X); free(B);
+  return error;
+}
+
+void orc_precond_clear(void) { precond_clear_all(); }

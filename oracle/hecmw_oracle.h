@@ -1,0 +1,109 @@
+/*
+ * ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the product path.
+ *
+ * CPU restatement (plain C, double precision) of the FrontISTR / HEC-MW
+ * linear-static hot path: element stiffness integration, assembly into the
+ * 3x3 block-CSR hecmwST_matrix, Dirichlet elimination, BCSR33 SpMV,
+ * DIAG / SSOR preconditioning and preconditioned CG.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library.  The product library
+ * (frontistr_b200/libfistr_b200.so) never links or calls it.
+ *
+ * Parity pinning: the reference's own implementation is Fortran 90 and no
+ * Fortran compiler exists in the build image, so this restatement is pinned
+ * against (a) the reference's golden logs examples/static/exA/A361_correct.log,
+ * A342_correct.log, ... (nodal displacement max/min, 5 significant digits,
+ * harness tolerance 1e-4 absolute, examples/test_FrontISTR.rb:10,225-237) and
+ * (b) an independent sparse direct solve of the same K (tests/test_oracle_*).
+ * Nothing in the reference tree pins CG iteration counts or K entries; for
+ * those quantities the parity is "pinned by restatement only".
+ *
+ * All citations are relative to the reference tree root (ricosjp/FrontISTR).
+ * Index arrays hold the reference's 1-based node ids verbatim; index*[0..NP]
+ * are 0-based offset prefix arrays exactly as hecmwST_matrix stores them
+ * (hecmw1/src/common/hecmw_util_f.F90:433-468).
+ */
+#ifndef HECMW_ORACLE_H
+#define HECMW_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* hecmwST_local_mesh, fields used on the path (hecmw_util_f.F90:232-381) */
+typedef struct orc_mesh {
+  int n_node, nn_internal, n_elem, n_elem_type;
+  const int *elem_type_index; /* 0..n_elem_type */
+  const int *elem_type_item;  /* 361, 342, ... */
+  const int *elem_node_index; /* 0..n_elem */
+  const int *elem_node_item;  /* 1-based local node ids */
+  const double *node;         /* xyz interleaved, 3*n_node */
+  const int *section_ID;      /* 1-based, n_elem */
+  int n_neighbor_pe;
+  const int *neighbor_pe;     /* 0-based rank ids */
+  const int *import_index, *import_item, *export_index, *export_item;
+  int my_rank, PETOT;
+} orc_mesh;
+
+/* per-section table (fstrSOLID%sections(:)%elemopt361 + material E, nu) */
+typedef struct orc_section {
+  int elemopt361; /* 1 FI, 2 BBAR, 3 IC  (fistr1/src/lib/m_fstr.f90:68-71) */
+  double E, nu;
+} orc_section;
+
+/* hecmwST_matrix (hecmw_util_f.F90:433-468) */
+typedef struct orc_matrix {
+  int N, NP, NPL, NPU, NDOF;
+  int *indexL, *itemL, *indexU, *itemU;
+  double *D, *AL, *AU, *B, *X;
+  int *Iarray;    /* 100, 1-based slots stored at [slot-1] */
+  double *Rarray; /* 100 */
+} orc_matrix;
+
+/* graph build: hecmw_mat_con (solver/matrix/hecmw_mat_con.f90:23-268).
+ * Two-phase for the caller: _build keeps the result in a static, _fetch copies. */
+int orc_mat_con_build(const orc_mesh *mesh, int *N, int *NP, int *NPL, int *NPU);
+int orc_mat_con_fetch(int *indexL, int *itemL, int *indexU, int *itemU);
+
+/* element kernels; ecoord is (3,nn) column-major, stiff is (3nn,3nn) column-major */
+void orc_STF_C3D8IC(int nn, const double *ecoord, double E, double nu, double *stiff);
+void orc_STF_C3(int etype, int nn, const double *ecoord, double E, double nu, double *stiff);
+void orc_STF_C3D8Bbar(int nn, const double *ecoord, double E, double nu, double *stiff);
+void orc_calInverse(int NN, double *A);
+
+/* fstr_StiffMatrix + hecmw_mat_ass_elem */
+int orc_stiffmatrix(const orc_mesh *mesh, const orc_section *sections, orc_matrix *mat);
+int orc_mat_ass_elem(orc_matrix *mat, int nn, const int *nodLOCAL, const double *stiffness, int ld);
+/* hecmw_mat_ass_bc (solver/matrix/hecmw_mat_ass.f90:292-429) */
+void orc_mat_ass_bc(orc_matrix *mat, int inode, int idof, double RHS);
+
+/* SpMV family on one subdomain; x must already hold its halo */
+void orc_matvec_33_local(const orc_matrix *mat, const double *X, double *Y);
+
+/* distributed (rank-emulated) solver: ndom subdomains processed in one process.
+ * hist (may be NULL) receives RESID per iteration, hist_len entries max. */
+int orc_solve(int ndom, const orc_mesh *meshes, orc_matrix *mats,
+              int *iter_out, double *resid_out, double *resid2_out,
+              double *hist, int hist_len, double *times /*[5] setup, sol, comm, matvec, precond*/);
+void orc_matvec_33(int ndom, const orc_mesh *meshes, orc_matrix *mats, double **X, double **Y);
+void orc_update_3_R(int ndom, const orc_mesh *meshes, double **X);
+
+/* preconditioners on one subdomain (state kept per call site in a handle) */
+typedef struct orc_precond orc_precond;
+orc_precond *orc_precond_setup(const orc_matrix *mat, int precond, double sigma_diag,
+                               int ncolor_in, int nthreads_emulated);
+void orc_precond_apply(const orc_precond *pc, double *ZP);
+void orc_precond_free(orc_precond *pc);
+int orc_precond_ncolor(const orc_precond *pc);
+void orc_precond_perm(const orc_precond *pc, int *perm /*N, 1-based new->old*/);
+
+void orc_precond_clear(void);       /* drop the cached factorisation (module SAVE state) */
+void orc_set_ssor_threads(int n);   /* 0: follow OpenMP; 1: natural order; >1: RCM+multicolour */
+int orc_num_threads(void);
+void orc_set_num_threads(int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
