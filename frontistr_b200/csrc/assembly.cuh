@@ -1,0 +1,201 @@
+// fstr_StiffMatrix + hecmw_mat_ass_elem on the device
+// (fistr1/src/analysis/static/fstr_StiffMatrix.f90:18-212, hecmw1/src/solver/matrix/hecmw_mat_ass.f90:31-166)
+// and hecmw_mat_ass_bc (hecmw_mat_ass.f90:292-429).
+//
+// The matrix values live in ONE device allocation laid out [ D (9*NP) | AL (9*NPL) | AU (9*NPU) ],
+// each part exactly in the hecmwST_matrix layout, so a block is addressed by a single 32-bit "slot"
+// (D: node-1, AL: NP+k, AU: NP+NPL+k).  The binary search that hecmw_mat_add_node repeats for every
+// element and every call (hecmw_mat_ass.f90:81-121) depends on topology only: it is done once per
+// structure into slot[e*nn*nn + i*nn + j].
+#pragma once
+#include "common.cuh"
+#include "element_math.cuh"
+
+namespace fb {
+
+constexpr unsigned kBadSlot = 0xFFFFFFFFu;
+
+__device__ __forceinline__ int bsearch_row(const int *__restrict__ item, int lo, int hi, int key) {
+  // hecmw_array_search_i, hecmw_mat_ass.f90:136-166 (0-based positions here)
+  while (lo <= hi) {
+    const int c = (lo + hi) >> 1;
+    const int v = item[c];
+    if (key < v) hi = c - 1;
+    else if (v < key) lo = c + 1;
+    else return c;
+  }
+  return -1;
+}
+
+__global__ void __launch_bounds__(256)
+slot_build_kernel(int e0, int e1, int nn, const int *__restrict__ elem_node_index,
+                  const int *__restrict__ elem_node_item, int NP, int NPL,
+                  const int *__restrict__ indexL, const int *__restrict__ itemL,
+                  const int *__restrict__ indexU, const int *__restrict__ itemU,
+                  unsigned *__restrict__ slot, size_t slot_base, int *err) {
+  const size_t nb = (size_t)nn * nn;
+  const size_t total = (size_t)(e1 - e0) * nb;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int e = e0 + (int)(t / nb), ij = (int)(t % nb), i = ij / nn, j = ij % nn;
+    const int *c = elem_node_item + elem_node_index[e];
+    const int inod = c[i], jnod = c[j];
+    unsigned s;
+    if (inod == jnod) s = (unsigned)(inod - 1);
+    else if (inod < jnod) {
+      const int k = bsearch_row(itemU, indexU[inod - 1], indexU[inod] - 1, jnod);
+      s = (k < 0) ? kBadSlot : (unsigned)NP + (unsigned)NPL + (unsigned)k;
+    } else {
+      const int k = bsearch_row(itemL, indexL[inod - 1], indexL[inod] - 1, jnod);
+      s = (k < 0) ? kBadSlot : (unsigned)NP + (unsigned)k;
+    }
+    if (s == kBadSlot) atomicExch(err, 1);   // "cannot find connectivity", hecmw_mat_ass.f90:86-90
+    slot[slot_base + t] = s;
+  }
+}
+
+// One element per warp.  sect[3*s..] = D11, D12, D44 of section s; sect_form[s] = elemopt361.
+template <int FORM, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+stiff_kernel(int e0, int e1, const int *__restrict__ elem_node_index, const int *__restrict__ elem_node_item,
+             const double *__restrict__ node, const int *__restrict__ section_ID,
+             const double *__restrict__ sectD, const int *__restrict__ sect_form,
+             const unsigned *__restrict__ slot, size_t slot_base, double *__restrict__ vals) {
+  using namespace elem;
+  constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
+  constexpr int NGP = (FORM == FORM_TET10) ? 4 : 8;
+  constexpr int NB = NN * NN;
+  constexpr int ROUNDS = (NB + 31) / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Scratch &S = reinterpret_cast<Scratch *>(smem_raw)[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const int wg = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  const int nw = gridDim.x * WARPS;
+  for (int e = e0 + wg; e < e1; e += nw) {
+    const int sec = section_ID[e] - 1;
+    if (FORM != FORM_TET10 && sect_form[sec] != FORM) continue;   // warp-uniform
+    const double D11 = sectD[3 * sec], D12 = sectD[3 * sec + 1], D44 = sectD[3 * sec + 2];
+    const int *conn = elem_node_item + elem_node_index[e];
+    if (lane < NN) {
+      const size_t n3 = 3 * (size_t)(conn[lane] - 1);
+      S.xc[3 * lane] = node[n3]; S.xc[3 * lane + 1] = node[n3 + 1]; S.xc[3 * lane + 2] = node[n3 + 2];
+    }
+    __syncwarp();
+    phase_geometry<FORM>(lane, S);
+    __syncwarp();
+    double kb[ROUNDS][9];
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+      const int t = r * 32 + lane;
+      if (t < NB) {
+        if (FORM == FORM_BBAR) pair_block_bbar(S, t / NN, t % NN, D11, D12, D44, kb[r]);
+        else pair_block_iso<(FORM == FORM_IC) ? 11 : NN, NGP>(S, t / NN, t % NN, D11, D12, D44, kb[r]);
+      }
+    }
+    if (FORM == FORM_IC) {
+      ic_phase_coupling(lane, S, D11, D12, D44);
+      ic_inv_init(lane, S);
+      __syncwarp();
+      for (int K = 0; K < 9; K++) {
+        ic_inv_pivot(lane, S, K);
+        __syncwarp();
+        ic_inv_swap(lane, S, K);
+        __syncwarp();
+        double colK[9];
+#pragma unroll
+        for (int I = 0; I < 9; I++) colK[I] = S.Kaa[I * 9 + K];
+        __syncwarp();
+        ic_inv_step(lane, S, K, colK);
+        __syncwarp();
+      }
+      ic_inv_unpermute(lane, S);
+      __syncwarp();
+      ic_phase_W(lane, S);
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < ROUNDS; r++) {
+        const int t = r * 32 + lane;
+        if (t < NB) ic_condense_block(S, t / NN, t % NN, kb[r]);
+      }
+    }
+    // hecmw_mat_add_node: 9 scalar atomic adds per block ('!$omp atomic', hecmw_mat_ass.f90:96,117,128)
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+      const int t = r * 32 + lane;
+      if (t < NB) {
+        const unsigned s = slot[slot_base + (size_t)(e - e0) * NB + t];
+        if (s != kBadSlot) {
+          double *dst = vals + 9 * (size_t)s;
+#pragma unroll
+          for (int a = 0; a < 9; a++) atomicAdd(dst + a, kb[r][a]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---- hecmw_mat_ass_bc, batched ---------------------------------------------------------------
+// One thread per (constraint c, entry t of node n's row): t = 0 is the diagonal block,
+// 1..nL the L entries, then the U entries.  STAGE 0 subtracts K(:,c)*rhs from B (reading the
+// still-unmodified matrix); STAGE 1 zeroes row/column and puts 1 on the diagonal; the caller then
+// writes B(c) = rhs.  Equals the reference's one-constraint-at-a-time elimination because a
+// constraint only ever zeroes its own row and column.
+template <int STAGE>
+__global__ void __launch_bounds__(256)
+bc_kernel(int nbc, const int *__restrict__ bc_node, const int *__restrict__ bc_dof,
+          const double *__restrict__ bc_val, const int *__restrict__ bc_ptr /* nbc+1 work offsets */,
+          int NP, int NPL, const int *__restrict__ indexL, const int *__restrict__ itemL,
+          const int *__restrict__ indexU, const int *__restrict__ itemU, double *__restrict__ vals,
+          double *__restrict__ B) {
+  const int total = bc_ptr[nbc];
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x) {
+    int lo = 0, hi = nbc - 1;   // constraint owning work item w
+    while (lo < hi) { const int m = (lo + hi + 1) >> 1; if (bc_ptr[m] <= w) lo = m; else hi = m - 1; }
+    const int c = lo, t = w - bc_ptr[c];
+    const int n = bc_node[c], d = bc_dof[c] - 1;
+    const double rhs = bc_val[c];
+    double *Dn = vals + 9 * (size_t)(n - 1);
+    const int nL = indexL[n] - indexL[n - 1];
+    if (t == 0) {
+      if (STAGE == 0) {
+        for (int i = 0; i < 3; i++)
+          if (i != d) atomicAdd(&B[3 * (size_t)(n - 1) + i], -(Dn[3 * i + d] * rhs));
+      } else {
+        for (int i = 0; i < 3; i++) { Dn[3 * d + i] = 0.0; Dn[3 * i + d] = 0.0; }
+        Dn[3 * d + d] = 1.0;
+      }
+      continue;
+    }
+    double *own, *tr;   // block (n, in) in n's row; transposed-position block (in, n)
+    int in;
+    if (t - 1 < nL) {
+      const int k = indexL[n - 1] + t - 1;
+      in = itemL[k];
+      own = vals + 9 * ((size_t)NP + k);
+      const int ik = bsearch_row(itemU, indexU[in - 1], indexU[in] - 1, n);
+      tr = (ik < 0) ? nullptr : vals + 9 * ((size_t)NP + NPL + ik);
+    } else {
+      const int k = indexU[n - 1] + t - 1 - nL;
+      in = itemU[k];
+      own = vals + 9 * ((size_t)NP + NPL + k);
+      const int ik = bsearch_row(itemL, indexL[in - 1], indexL[in] - 1, n);
+      tr = (ik < 0) ? nullptr : vals + 9 * ((size_t)NP + ik);
+    }
+    if (STAGE == 0) {
+      if (tr)
+        for (int i = 0; i < 3; i++) atomicAdd(&B[3 * (size_t)(in - 1) + i], -(tr[3 * i + d] * rhs));
+    } else {
+      for (int i = 0; i < 3; i++) own[3 * d + i] = 0.0;
+      if (tr)
+        for (int i = 0; i < 3; i++) tr[3 * i + d] = 0.0;
+    }
+  }
+}
+
+__global__ void bc_set_rhs_kernel(int nbc, const int *__restrict__ bc_node, const int *__restrict__ bc_dof,
+                                  const double *__restrict__ bc_val, double *__restrict__ B) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < nbc) B[3 * (size_t)(bc_node[c] - 1) + bc_dof[c] - 1] = bc_val[c];
+}
+
+}  // namespace fb

@@ -1,0 +1,106 @@
+// Process-wide state of the fistr_b200 library: one GPU, one live matrix (as the reference's
+// preconditioner modules keep module-level SAVE state, precond/33/hecmw_precond_DIAG_33.f90:20-23).
+#pragma once
+#include <chrono>
+#include <map>
+#include <vector>
+
+#include "../../include/fistr_b200.h"
+#include "assembly.cuh"
+#include "cg_kernels.cuh"
+#include "comm.hpp"
+#include "common.cuh"
+#include "matcon.hpp"
+#include "spmv.cuh"
+#include "ssor.cuh"
+
+namespace fb {
+
+enum {
+  HECMW_SOLVER_ERROR_INCONS_PC_ = 1001, HECMW_SOLVER_ERROR_ZERO_DIAG_ = 2001, HECMW_SOLVER_ERROR_ZERO_RHS_ = 2002,
+  HECMW_SOLVER_ERROR_NOCONV_MAXIT_ = 3001, HECMW_SOLVER_ERROR_DIVERGE_MAT_ = 3002, HECMW_SOLVER_ERROR_DIVERGE_PC_ = 3003
+};   // hecmw1/src/solver/init/hecmw_solve_error.f90:9-15
+
+struct Halo {
+  int n_neighbor = 0;
+  std::vector<int> neighbor_pe, import_index, import_item, export_index, export_item;
+  DevBuf<int> d_export_item, d_import_item;
+  DevBuf<double> send_p, send_x, recv;
+  bool import_contiguous = true;   // import_item == N+1..NP in order -> receive straight into x
+  int n_export() const { return export_index.empty() ? 0 : export_index.back(); }
+  int n_import() const { return import_index.empty() ? 0 : import_index.back(); }
+};
+
+struct Context {
+  bool inited = false;
+  int device = 0, sm_count = kNumSM;
+  cudaStream_t stream = nullptr;
+  std::map<std::string, int64_t> opt;
+
+  // ---- matrix structure (hecmwST_matrix index part)
+  int N = 0, NP = 0, NPL = 0, NPU = 0;
+  bool have_structure = false;
+  const int *key_indexL = nullptr, *key_itemL = nullptr;   // identity of the host arrays last declared
+  std::vector<int> h_indexL, h_indexU;
+  DevBuf<int> indexL, itemL, indexU, itemU;
+  Halo halo;
+
+  // ---- values: [D | AL | AU], RHS, solution, CG work vectors
+  DevBuf<double> vals, B, X, R, Z, P, Q, WK;
+  bool values_on_device = false;
+  double *dD() { return vals.p; }
+  double *dAL() { return vals.p + 9 * (size_t)NP; }
+  double *dAU() { return vals.p + 9 * ((size_t)NP + NPL); }
+
+  // ---- solver-private copies
+  SellMatrix sell;
+  bool sell_valid = false;
+  DevBuf<double> alu;      // DIAG: SoA [9][alu_ld]
+  size_t alu_ld = 0;
+  int pc_kind = 0;         // 0 none, 3 DIAG, 1 SSOR
+  double pc_sigma = 0.0;
+  Ssor ssor;
+
+  // ---- reductions / control
+  DevBuf<double> red, partial, hist;
+  DevBuf<unsigned> counter;
+  DevBuf<CgCtl> ctl;
+  DevBuf<int> flag;
+  std::vector<double> last_hist;
+  double last_resid2 = 0.0;
+
+  // ---- assembly
+  DevBuf<unsigned> slot;
+  DevBuf<int> m_eni, m_enn, m_sec, m_form;
+  DevBuf<double> m_node, m_sectD;
+  const int *key_elem_node_item = nullptr;
+  bool slot_valid = false;
+
+  // ---- hecmw_mat_con result held between _count and _fill
+  MatCon con;
+
+  // ---- communication
+  Nccl nccl;
+  ncclComm_t_ comm = nullptr;
+  int rank = 0, petot = 1;
+
+  int64_t get(const char *k, int64_t dflt) const {
+    auto it = opt.find(k);
+    return it == opt.end() ? dflt : it->second;
+  }
+  int grid_for(size_t items, int block, int per_sm = 8) const {
+    size_t g = (items + block - 1) / block;
+    size_t cap = (size_t)sm_count * per_sm;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+  }
+};
+
+Context &ctx();
+
+inline double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace fb

@@ -1,0 +1,295 @@
+// Element stiffness integration for STF_C3D8IC / STF_C3 / STF_C3D8Bbar
+// (fistr1/src/lib/static_LIB_3dIC.f90:21-215, static_LIB_3d.f90:47-205, static_LIB_C3D8.f90:23-198),
+// written as per-lane phase functions over a per-warp scratch block.  In the CUDA kernel a phase is
+// executed by the 32 lanes of one warp with __syncwarp() between phases; the host emulation used by
+// the CPU unit tests (tests/test_element_emul.py via csrc/emul_test.cpp) runs the same functions in
+// a lane loop.  One element per warp; FP64 throughout.
+//
+// For an isotropic elastic D (ElasticLinear.f90:48-59: D11, D12, D44) the 3x3 block coupling
+// "nodes" i and j at one Gauss point is evaluated in closed form,
+//     K_ij[a][a] += w (D11 gi[a] gj[a] + D44 sum_{c!=a} gi[c] gj[c])
+//     K_ij[a][b] += w (D12 gi[a] gj[b] + D44 gi[b] gj[a])            a != b
+// which is B_i^T D B_j of static_LIB_3d.f90:120-167 with the structural zeros of B removed.
+// The incompatible-mode element treats its 3 enhanced modes as nodes 8..10 and condenses them
+// with the reference's own pivoted Gauss-Jordan (lib/utilities/utilities.f90:247-316).
+#pragma once
+#include <math.h>
+
+#ifdef __CUDACC__
+#define FB_HD __host__ __device__ __forceinline__
+#else
+#define FB_HD inline
+#endif
+
+namespace fb {
+namespace elem {
+
+enum Form { FORM_FI = 1, FORM_BBAR = 2, FORM_IC = 3, FORM_TET10 = 10 };
+
+constexpr double kGaussHex = 0.577350269189626;     // quadrature.f90:83-91
+constexpr double kTetA = 0.138196601125011;         // quadrature.f90:124-128
+constexpr double kTetB = 0.585410196624968;
+constexpr double kTetW = 0.041666666666667;         // quadrature.f90:236-238
+
+// per-warp scratch (doubles).  MAXN = nodes + enhanced modes, NGP Gauss points
+struct Scratch {
+  double xc[10 * 3];        // element coordinates, node-major
+  double gd[8 * 11 * 3];    // gderiv[g][n][3]  (hex: 8 GP x 11; tet10: 4 GP x 10 fits as well)
+  double bb[8 * 8 * 3];     // B-bar correction (Bbar - gderiv)/3 per GP,node (B-bar only)
+  double wdet[8];           // weight * det per GP
+  double Kda[24 * 9];       // IC: K(d, alpha)
+  double Kaa[9 * 9];        // IC: K(alpha, alpha) -> inverse, row-major [r][c]
+  double W[24 * 9];         // IC: Kda * Kaa^-1
+  double piv[16];           // IC: pivot bookkeeping
+};
+
+FB_HD void hex_shape_deriv(double x, double y, double z, double (*d)[3]) {
+  // ShapeDeriv_hex8n, lib/element/hex8n.f90:24-53
+  const double sx[8] = {-1, 1, 1, -1, -1, 1, 1, -1};
+  const double sy[8] = {-1, -1, 1, 1, -1, -1, 1, 1};
+  const double sz[8] = {-1, -1, -1, -1, 1, 1, 1, 1};
+  for (int n = 0; n < 8; n++) {
+    d[n][0] = (0.125 * sx[n]) * (1.0 + sy[n] * y) * (1.0 + sz[n] * z);
+    d[n][1] = (0.125 * sy[n]) * (1.0 + sx[n] * x) * (1.0 + sz[n] * z);
+    d[n][2] = (0.125 * sz[n]) * (1.0 + sx[n] * x) * (1.0 + sy[n] * y);
+  }
+}
+
+FB_HD void tet10_shape_deriv(double xi, double et, double ze, double (*s)[3]) {
+  // ShapeDeriv_tet10n, lib/element/tet10n.f90:29-75
+  const double a = 1.0 - xi - et - ze;
+  s[0][0] = 1.0 - 4.0 * a; s[1][0] = 4.0 * xi - 1.0; s[2][0] = 0.0; s[3][0] = 0.0;
+  s[4][0] = 4.0 * (1.0 - 2.0 * xi - et - ze); s[5][0] = 4.0 * et; s[6][0] = -4.0 * et;
+  s[7][0] = -4.0 * ze; s[8][0] = 4.0 * ze; s[9][0] = 0.0;
+  s[0][1] = 1.0 - 4.0 * a; s[1][1] = 0.0; s[2][1] = 4.0 * et - 1.0; s[3][1] = 0.0;
+  s[4][1] = -4.0 * xi; s[5][1] = 4.0 * xi; s[6][1] = 4.0 * (1.0 - xi - 2.0 * et - ze);
+  s[7][1] = -4.0 * ze; s[8][1] = 0.0; s[9][1] = 4.0 * ze;
+  s[0][2] = 1.0 - 4.0 * a; s[1][2] = 0.0; s[2][2] = 0.0; s[3][2] = 4.0 * ze - 1.0;
+  s[4][2] = -4.0 * xi; s[5][2] = 0.0; s[6][2] = -4.0 * et;
+  s[7][2] = 4.0 * (1.0 - xi - et - 2.0 * ze); s[8][2] = 4.0 * xi; s[9][2] = 4.0 * et;
+}
+
+// J = X^T dN, det, cofactor inverse (getGlobalDeriv / getJacobian, element.f90:693-741,772-819)
+FB_HD void jacobian(int nn, const double *xc, const double (*d)[3], double &det, double (*inv)[3]) {
+  double J[3][3];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double s = 0.0;
+      for (int n = 0; n < nn; n++) s += xc[3 * n + i] * d[n][j];
+      J[i][j] = s;
+    }
+  det = J[0][0] * J[1][1] * J[2][2] + J[1][0] * J[2][1] * J[0][2] + J[2][0] * J[0][1] * J[1][2] -
+        J[2][0] * J[1][1] * J[0][2] - J[1][0] * J[0][1] * J[2][2] - J[0][0] * J[2][1] * J[1][2];
+  const double dum = 1.0 / det;
+  inv[0][0] = dum * (J[1][1] * J[2][2] - J[2][1] * J[1][2]);
+  inv[0][1] = dum * (-J[0][1] * J[2][2] + J[2][1] * J[0][2]);
+  inv[0][2] = dum * (J[0][1] * J[1][2] - J[1][1] * J[0][2]);
+  inv[1][0] = dum * (-J[1][0] * J[2][2] + J[2][0] * J[1][2]);
+  inv[1][1] = dum * (J[0][0] * J[2][2] - J[2][0] * J[0][2]);
+  inv[1][2] = dum * (-J[0][0] * J[1][2] + J[1][0] * J[0][2]);
+  inv[2][0] = dum * (J[1][0] * J[2][1] - J[2][0] * J[1][1]);
+  inv[2][1] = dum * (-J[0][0] * J[2][1] + J[2][0] * J[0][1]);
+  inv[2][2] = dum * (J[0][0] * J[1][1] - J[1][0] * J[0][1]);
+}
+
+// ---- phase G: lane g < NGP computes the geometry of Gauss point g --------------------------
+template <int FORM>
+FB_HD void phase_geometry(int lane, Scratch &S) {
+  constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
+  constexpr int NGP = (FORM == FORM_TET10) ? 4 : 8;
+  constexpr int NT = (FORM == FORM_IC) ? 11 : NN;
+  if (lane >= NGP) return;
+  double d[10][3], inv[3][3], det;
+  double nc[3];
+  if (FORM == FORM_TET10) {
+    nc[0] = (lane == 1) ? kTetB : kTetA; nc[1] = (lane == 2) ? kTetB : kTetA; nc[2] = (lane == 3) ? kTetB : kTetA;
+    tet10_shape_deriv(nc[0], nc[1], nc[2], d);
+  } else {
+    nc[0] = (lane & 1) ? kGaussHex : -kGaussHex; nc[1] = (lane & 2) ? kGaussHex : -kGaussHex;
+    nc[2] = (lane & 4) ? kGaussHex : -kGaussHex;
+    hex_shape_deriv(nc[0], nc[1], nc[2], d);
+  }
+  jacobian(NN, S.xc, d, det, inv);
+  double *gd = S.gd + lane * NT * 3;
+  for (int n = 0; n < NN; n++)
+    for (int j = 0; j < 3; j++) {
+      double s = 0.0;
+      for (int k = 0; k < 3; k++) s += d[n][k] * inv[k][j];
+      gd[3 * n + j] = s;
+    }
+  S.wdet[lane] = ((FORM == FORM_TET10) ? kTetW : 1.0) * det;
+  if (FORM == FORM_IC || FORM == FORM_BBAR) {
+    double d0[10][3], inv0[3][3], det0;
+    hex_shape_deriv(0.0, 0.0, 0.0, d0);
+    jacobian(8, S.xc, d0, det0, inv0);
+    if (FORM == FORM_IC) {
+      // gderiv(nn+m,:) = -2 xi_m (J0^-1 det0)(m,:) / det, static_LIB_3dIC.f90:79-81,120-122
+      for (int m = 0; m < 3; m++)
+        for (int j = 0; j < 3; j++) gd[3 * (8 + m) + j] = -2.0 * nc[m] * (inv0[m][j] * det0) / det;
+    } else {
+      // B4,B6,B8 = (Bbar - gderiv)/3 with Bbar the centroid derivative, static_LIB_C3D8.f90:72-74,104-106
+      double *bb = S.bb + lane * 8 * 3;
+      for (int n = 0; n < 8; n++)
+        for (int j = 0; j < 3; j++) {
+          double s = 0.0;
+          for (int k = 0; k < 3; k++) s += d0[n][k] * inv0[k][j];
+          bb[3 * n + j] = (s - gd[3 * n + j]) / 3.0;
+        }
+    }
+  }
+}
+
+// closed-form isotropic pair block, accumulated over the Gauss points
+template <int NT, int NGP>
+FB_HD void pair_block_iso(const Scratch &S, int i, int j, double D11, double D12, double D44, double *k9) {
+  for (int a = 0; a < 9; a++) k9[a] = 0.0;
+  for (int g = 0; g < NGP; g++) {
+    const double *gi = S.gd + (g * NT + i) * 3, *gj = S.gd + (g * NT + j) * 3;
+    const double w = S.wdet[g];
+    const double gi0 = gi[0], gi1 = gi[1], gi2 = gi[2];
+    const double h0 = w * gj[0], h1 = w * gj[1], h2 = w * gj[2];
+    const double p0 = gi0 * h0, p1 = gi1 * h1, p2 = gi2 * h2;
+    k9[0] += D11 * p0 + D44 * (p1 + p2);
+    k9[4] += D11 * p1 + D44 * (p0 + p2);
+    k9[8] += D11 * p2 + D44 * (p0 + p1);
+    k9[1] += D12 * (gi0 * h1) + D44 * (gi1 * h0);
+    k9[2] += D12 * (gi0 * h2) + D44 * (gi2 * h0);
+    k9[3] += D12 * (gi1 * h0) + D44 * (gi0 * h1);
+    k9[5] += D12 * (gi1 * h2) + D44 * (gi2 * h1);
+    k9[6] += D12 * (gi2 * h0) + D44 * (gi0 * h2);
+    k9[7] += D12 * (gi2 * h1) + D44 * (gi1 * h2);
+  }
+}
+
+// B-bar pair block: B rows 1-3 carry the volumetric correction (static_LIB_C3D8.f90:103-125)
+FB_HD void pair_block_bbar(const Scratch &S, int i, int j, double D11, double D12, double D44, double *k9) {
+  for (int a = 0; a < 9; a++) k9[a] = 0.0;
+  for (int g = 0; g < 8; g++) {
+    const double *gi = S.gd + (g * 8 + i) * 3, *gj = S.gd + (g * 8 + j) * 3;
+    const double *bi = S.bb + (g * 8 + i) * 3, *bj = S.bb + (g * 8 + j) * 3;
+    const double w = S.wdet[g];
+    double Bi[6][3], Bj[6][3];
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) {
+        Bi[r][c] = bi[c] + ((r == c) ? gi[c] : 0.0);
+        Bj[r][c] = bj[c] + ((r == c) ? gj[c] : 0.0);
+      }
+    for (int c = 0; c < 3; c++) { Bi[3][c] = Bi[4][c] = Bi[5][c] = 0.0; Bj[3][c] = Bj[4][c] = Bj[5][c] = 0.0; }
+    Bi[3][0] = gi[1]; Bi[3][1] = gi[0]; Bi[4][1] = gi[2]; Bi[4][2] = gi[1]; Bi[5][0] = gi[2]; Bi[5][2] = gi[0];
+    Bj[3][0] = gj[1]; Bj[3][1] = gj[0]; Bj[4][1] = gj[2]; Bj[4][2] = gj[1]; Bj[5][0] = gj[2]; Bj[5][2] = gj[0];
+    for (int b = 0; b < 3; b++) {
+      double DB[6];
+      DB[0] = D11 * Bj[0][b] + D12 * Bj[1][b] + D12 * Bj[2][b];
+      DB[1] = D12 * Bj[0][b] + D11 * Bj[1][b] + D12 * Bj[2][b];
+      DB[2] = D12 * Bj[0][b] + D12 * Bj[1][b] + D11 * Bj[2][b];
+      DB[3] = D44 * Bj[3][b]; DB[4] = D44 * Bj[4][b]; DB[5] = D44 * Bj[5][b];
+      for (int a = 0; a < 3; a++) {
+        double s = 0.0;
+        for (int r = 0; r < 6; r++) s += Bi[r][a] * DB[r];
+        k9[3 * a + b] += s * w;
+      }
+    }
+  }
+}
+
+// ---- IC condensation ----------------------------------------------------------------------
+// round 2 of the IC task list: lanes 0..23 -> K(d_i, alpha_m) blocks, lanes 24..29 -> K(alpha,alpha)
+FB_HD void ic_phase_coupling(int lane, Scratch &S, double D11, double D12, double D44) {
+  double k9[9];
+  if (lane < 24) {
+    const int i = lane / 3, m = lane % 3;
+    pair_block_iso<11, 8>(S, i, 8 + m, D11, D12, D44, k9);
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) S.Kda[(3 * i + a) * 9 + 3 * m + b] = k9[3 * a + b];
+  } else if (lane < 30) {
+    const int pm[6] = {0, 0, 0, 1, 1, 2}, pn[6] = {0, 1, 2, 1, 2, 2};
+    const int m = pm[lane - 24], n = pn[lane - 24];
+    pair_block_iso<11, 8>(S, 8 + m, 8 + n, D11, D12, D44, k9);
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) {
+        S.Kaa[(3 * m + a) * 9 + 3 * n + b] = k9[3 * a + b];
+        if (m != n) S.Kaa[(3 * n + b) * 9 + 3 * m + a] = k9[3 * a + b];
+      }
+  }
+}
+
+// calInverse(9, Kaa) (utilities.f90:247-316), column-parallel over lanes 0..8.  The caller runs
+//   for K in 0..8: ic_inv_pivot(lane,S,K); sync; ic_inv_swap(lane,S,K); sync; ic_inv_elim_a(...); sync; ic_inv_elim_b(...); sync
+//   then ic_inv_unpermute on lane 0; sync.
+// piv[0..8] = IP(:), piv[9] = LR of the current step, piv[10] = PIVOT.
+FB_HD void ic_inv_init(int lane, Scratch &S) {
+  if (lane < 9) S.piv[lane] = (double)lane;
+}
+FB_HD void ic_inv_pivot(int lane, Scratch &S, int K) {
+  if (lane != 0) return;
+  double wmax = 0.0;
+  int LR = K;
+  for (int I = K; I < 9; I++) {
+    const double w = fabs(S.Kaa[I * 9 + K]);
+    if (w > wmax) { wmax = w; LR = I; }
+  }
+  S.piv[9] = (double)LR;
+  S.piv[10] = S.Kaa[LR * 9 + K];
+  if (LR != K) { const double t = S.piv[K]; S.piv[K] = S.piv[LR]; S.piv[LR] = t; }
+}
+// lane c (<9) owns column c: row swap, scaling of row K, elimination
+FB_HD void ic_inv_step(int lane, Scratch &S, int K, const double *colK /* A(:,K) before this step, after the swap */) {
+  if (lane >= 9) return;
+  const int c = lane;
+  const double PIVOT = S.piv[10];
+  if (c == K) {
+    for (int I = 0; I < 9; I++)
+      if (I != K) { const double W = colK[I]; if (W != 0.0) S.Kaa[I * 9 + K] = -W / PIVOT; }
+    S.Kaa[K * 9 + K] = 1.0 / PIVOT;
+  } else {
+    const double akc = S.Kaa[K * 9 + c] / PIVOT;
+    S.Kaa[K * 9 + c] = akc;
+    for (int I = 0; I < 9; I++)
+      if (I != K) { const double W = colK[I]; if (W != 0.0) S.Kaa[I * 9 + c] = S.Kaa[I * 9 + c] - W * akc; }
+  }
+}
+FB_HD void ic_inv_swap(int lane, Scratch &S, int K) {
+  if (lane >= 9) return;
+  const int LR = (int)S.piv[9];
+  if (LR != K) { const double t = S.Kaa[K * 9 + lane]; S.Kaa[K * 9 + lane] = S.Kaa[LR * 9 + lane]; S.Kaa[LR * 9 + lane] = t; }
+}
+FB_HD void ic_inv_unpermute(int lane, Scratch &S) {
+  if (lane != 0) return;
+  int IP[9];
+  for (int I = 0; I < 9; I++) IP[I] = (int)S.piv[I];
+  for (int I = 0; I < 9; I++) {   // utilities.f90:301-314, quirks included
+    const int K = IP[I];
+    if (K != I) {
+      const int IW = IP[K]; IP[K] = IP[I]; IP[I] = IW;
+      for (int J = 0; J < 9; J++) { const double W = S.Kaa[J * 9 + I]; S.Kaa[J * 9 + I] = S.Kaa[J * 9 + K]; S.Kaa[J * 9 + K] = W; }
+    }
+  }
+}
+// W = Kda * Kaa^-1   (tmpk, static_LIB_3dIC.f90:212): 216 entries over 32 lanes
+FB_HD void ic_phase_W(int lane, Scratch &S) {
+  for (int t = lane; t < 216; t += 32) {
+    const int r = t / 9, c = t % 9;
+    double s = 0.0;
+    for (int k = 0; k < 9; k++) s += S.Kda[r * 9 + k] * S.Kaa[k * 9 + c];
+    S.W[t] = s;
+  }
+}
+// K_ij -= W_i * Kad_j   (static_LIB_3dIC.f90:213; Kad = Kda^T by symmetry of D)
+FB_HD void ic_condense_block(const Scratch &S, int i, int j, double *k9) {
+  for (int a = 0; a < 3; a++)
+    for (int b = 0; b < 3; b++) {
+      double s = 0.0;
+      for (int k = 0; k < 9; k++) s += S.W[(3 * i + a) * 9 + k] * S.Kda[(3 * j + b) * 9 + k];
+      k9[3 * a + b] -= s;
+    }
+}
+
+// isotropic elastic constants, ElasticLinear.f90:48-59
+FB_HD void elastic_constants(double EE, double PP, double &D11, double &D12, double &D44) {
+  D11 = EE * (1.0 - PP) / (1.0 - 2.0 * PP) / (1.0 + PP);
+  D12 = EE * PP / (1.0 - 2.0 * PP) / (1.0 + PP);
+  D44 = EE / (1.0 + PP) * 0.5;
+}
+
+}  // namespace elem
+}  // namespace fb

@@ -1,0 +1,96 @@
+// TEST-ONLY host emulation of the warp-cooperative element kernel (assembly.cuh: stiff_kernel) and of
+// the host-side orderings.  The per-lane phase functions of element_math.cuh are run in a lane loop,
+// with the warp barriers of the CUDA kernel becoming loop boundaries, so the CPU unit tests can check
+// the element algebra against the oracle without a GPU.  Built as libfistr_b200_emul.so; the product
+// library never links it and no product entry point can reach it.
+#include <cstring>
+#include <vector>
+
+#include "element_math.cuh"
+
+using namespace fb::elem;
+
+template <int FORM>
+static void run_element(const double *ecoord /* (nn,3) */, double E, double nu, double *K /* (3nn,3nn) row-major */) {
+  constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
+  constexpr int NGP = (FORM == FORM_TET10) ? 4 : 8;
+  constexpr int NB = NN * NN;
+  constexpr int ROUNDS = (NB + 31) / 32;
+  Scratch S;
+  std::memset(&S, 0, sizeof S);
+  double D11, D12, D44;
+  elastic_constants(E, nu, D11, D12, D44);
+  for (int lane = 0; lane < NN; lane++)
+    for (int d = 0; d < 3; d++) S.xc[3 * lane + d] = ecoord[3 * lane + d];
+  for (int lane = 0; lane < 32; lane++) phase_geometry<FORM>(lane, S);
+  std::vector<double> kb(32 * ROUNDS * 9, 0.0);
+  for (int lane = 0; lane < 32; lane++)
+    for (int r = 0; r < ROUNDS; r++) {
+      const int t = r * 32 + lane;
+      if (t < NB) {
+        double *k9 = &kb[(lane * ROUNDS + r) * 9];
+        if (FORM == FORM_BBAR) pair_block_bbar(S, t / NN, t % NN, D11, D12, D44, k9);
+        else pair_block_iso<(FORM == FORM_IC) ? 11 : NN, NGP>(S, t / NN, t % NN, D11, D12, D44, k9);
+      }
+    }
+  if (FORM == FORM_IC) {
+    for (int lane = 0; lane < 32; lane++) ic_phase_coupling(lane, S, D11, D12, D44);
+    for (int lane = 0; lane < 32; lane++) ic_inv_init(lane, S);
+    for (int Kk = 0; Kk < 9; Kk++) {
+      for (int lane = 0; lane < 32; lane++) ic_inv_pivot(lane, S, Kk);
+      for (int lane = 0; lane < 32; lane++) ic_inv_swap(lane, S, Kk);
+      double colK[32][9];
+      for (int lane = 0; lane < 32; lane++)
+        for (int I = 0; I < 9; I++) colK[lane][I] = S.Kaa[I * 9 + Kk];
+      for (int lane = 0; lane < 32; lane++) ic_inv_step(lane, S, Kk, colK[lane]);
+    }
+    for (int lane = 0; lane < 32; lane++) ic_inv_unpermute(lane, S);
+    for (int lane = 0; lane < 32; lane++) ic_phase_W(lane, S);
+    for (int lane = 0; lane < 32; lane++)
+      for (int r = 0; r < ROUNDS; r++) {
+        const int t = r * 32 + lane;
+        if (t < NB) ic_condense_block(S, t / NN, t % NN, &kb[(lane * ROUNDS + r) * 9]);
+      }
+  }
+  for (int lane = 0; lane < 32; lane++)
+    for (int r = 0; r < ROUNDS; r++) {
+      const int t = r * 32 + lane;
+      if (t >= NB) continue;
+      const int i = t / NN, j = t % NN;
+      for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) K[(3 * i + a) * (3 * NN) + 3 * j + b] = kb[(lane * ROUNDS + r) * 9 + 3 * a + b];
+    }
+}
+
+extern "C" {
+
+int fbemul_element_stiffness(int form, const double *ecoord, double E, double nu, double *K) {
+  switch (form) {
+    case FORM_FI: run_element<FORM_FI>(ecoord, E, nu, K); return 0;
+    case FORM_BBAR: run_element<FORM_BBAR>(ecoord, E, nu, K); return 0;
+    case FORM_IC: run_element<FORM_IC>(ecoord, E, nu, K); return 0;
+    case FORM_TET10: run_element<FORM_TET10>(ecoord, E, nu, K); return 0;
+  }
+  return -1;
+}
+
+// calInverse(9) through the column-parallel phases alone
+int fbemul_inverse9(double *A /* row-major 9x9, in place */) {
+  Scratch S;
+  std::memset(&S, 0, sizeof S);
+  std::memcpy(S.Kaa, A, sizeof(double) * 81);
+  for (int lane = 0; lane < 32; lane++) ic_inv_init(lane, S);
+  for (int Kk = 0; Kk < 9; Kk++) {
+    for (int lane = 0; lane < 32; lane++) ic_inv_pivot(lane, S, Kk);
+    for (int lane = 0; lane < 32; lane++) ic_inv_swap(lane, S, Kk);
+    double colK[32][9];
+    for (int lane = 0; lane < 32; lane++)
+      for (int I = 0; I < 9; I++) colK[lane][I] = S.Kaa[I * 9 + Kk];
+    for (int lane = 0; lane < 32; lane++) ic_inv_step(lane, S, Kk, colK[lane]);
+  }
+  for (int lane = 0; lane < 32; lane++) ic_inv_unpermute(lane, S);
+  std::memcpy(A, S.Kaa, sizeof(double) * 81);
+  return 0;
+}
+
+}  // extern "C"

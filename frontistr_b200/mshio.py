@@ -245,27 +245,30 @@ def read_dist_mesh(path: str, elemopt361: int = kel361IC, E=None, nu=None) -> he
     # ---- global info
     t.i()  # hecmw_flag_adapt
     t.i()  # hecmw_flag_initcon
-    t.i()  # hecmw_flag_parttype
+    parttype = t.i()  # hecmw_flag_parttype (1 node-based, 2 element-based)
     t.i()  # hecmw_flag_partdepth
     t.i()  # hecmw_flag_version
     if version >= 4:
         t.i()  # hecmw_flag_partcontact
-    t.line() if False else None
-    # gridfile (one line, may be empty), then n_file, files, header line, zero_temp
+    # gridfile (one line, may be empty), n_file, files, header flag (+ header line), zero_temp
     t.buf = []
     t.line()               # gridfile
     nfile = t.i()
     t.buf = []
     for _ in range(nfile):
         t.line()
-    t.line()               # header
+    flag_header = t.i()
+    t.buf = []
+    if flag_header == 1:
+        t.line()           # header
     zero_temp = t.f()
     # ---- node info
     n_node = t.i()
     n_node_gross = t.i() if version >= 2 else n_node
     nn_middle = t.i() if version >= 4 else n_node
     nn_internal = t.i()
-    # node_internal_list only for element-based partitions (parttype==2): not supported here
+    if parttype != 1 and nn_internal > 0:     # element-based / unknown: node_internal_list
+        t.ia(nn_internal)
     node_ID = t.ia(2 * n_node).reshape(-1, 2)
     global_node_ID = t.ia(n_node)
     node = t.fa(3 * n_node)
@@ -278,7 +281,8 @@ def read_dist_mesh(path: str, elemopt361: int = kel361IC, E=None, nu=None) -> he
     n_elem = t.i()
     n_elem_gross = t.i() if version >= 2 else n_elem
     ne_internal = t.i()
-    t.ia(ne_internal)      # elem_internal_list
+    if parttype != 2 and ne_internal > 0:     # node-based / unknown: elem_internal_list
+        t.ia(ne_internal)
     t.ia(2 * n_elem)       # elem_ID
     t.ia(n_elem)           # global_elem_ID
     elem_type = t.ia(n_elem)
@@ -288,9 +292,9 @@ def read_dist_mesh(path: str, elemopt361: int = kel361IC, E=None, nu=None) -> he
     elem_node_index = t.ia(n_elem + 1)
     elem_node_item = t.ia(int(elem_node_index[-1]))
     section_ID = t.ia(n_elem)
-    n_elem_mat_ID = t.i()
-    t.ia(n_elem + 1)       # elem_mat_ID_index
-    t.ia(n_elem_mat_ID)    # elem_mat_ID_item
+    emi = t.ia(n_elem + 1)     # elem_mat_ID_index
+    t.ia(int(emi[-1]))         # elem_mat_ID_item
+    t.i()                      # n_elem_mat_ID
     # ---- comm info
     zero = t.i()
     t.i()                  # HECMW_COMM

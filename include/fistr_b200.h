@@ -1,0 +1,142 @@
+/*
+ * fistr_b200 — C-ABI of the B200-native linear-static hot path for FrontISTR / HEC-MW.
+ *
+ * Every entry point is what a Fortran `interface ... bind(C)` (ISO_C_BINDING) stub binds:
+ * plain pointers and sizes, scalars by value, arrays exactly as hecmwST_matrix /
+ * hecmwST_local_mesh hold them (1-based node ids, 0:NP prefix arrays, row-major 3x3 blocks).
+ * Host pointers are borrowed for the duration of the call only.  One process drives one GPU;
+ * like the reference's preconditioner modules (module-level SAVE state) the library keeps ONE
+ * live matrix / factorisation per process.
+ *
+ * There is NO CPU fallback: every compute entry point returns FISTR_B200_ERR_CUDA (-2) if no
+ * CUDA device is usable.  Return value convention: 0 success, >0 HEC-MW solver code
+ * (hecmw1/src/solver/init/hecmw_solve_error.f90:9-15), <0 library error
+ * (fistr_b200_last_error() gives the text).
+ *
+ * Citations are file:line in the reference tree (ricosjp/FrontISTR).
+ */
+#ifndef FISTR_B200_H
+#define FISTR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FISTR_B200_OK 0
+#define FISTR_B200_ERR_ARG (-1)
+#define FISTR_B200_ERR_CUDA (-2)
+#define FISTR_B200_ERR_COMM (-3)
+#define FISTR_B200_ERR_STATE (-4)
+#define FISTR_B200_ERR_CONNECTIVITY (-5) /* "cannot find connectivity", hecmw_mat_ass.f90:86-90 */
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+/* replaces nothing in the reference (there is no accelerator boundary today); called once after
+ * hecmw_init (hecmw1/src/common/hecmw_util_f.F90:478-520). */
+int fistr_b200_init(int device_ordinal);
+int fistr_b200_finalize(void);
+const char *fistr_b200_last_error(void);
+/* integer tuning knobs ("spmv_variant", "cg_fused", "launch_count_reset", ...) */
+int fistr_b200_set_option(const char *key, int64_t value);
+int64_t fistr_b200_get_option(const char *key);
+
+/* ---- communication: replaces the MPI layer under hecmw_update_3_R / hecmw_allreduce_R1 ------
+ * (hecmw1/src/solver/communication/hecmw_comm_f.F90:346-393,669-694; hecmw_solver_SR_33.F90:42-124).
+ * Rank 0 obtains an id (NCCL unique id, 128 bytes) and broadcasts it with the host's own
+ * transport (MPI_Bcast in fistr1, torch.distributed in the Python harness). */
+int fistr_b200_comm_get_unique_id(void *id128);
+int fistr_b200_comm_init(const void *id128, int my_rank, int petot);
+int fistr_b200_comm_finalize(void);
+
+/* ---- hecmw_mat_con (hecmw1/src/solver/matrix/hecmw_mat_con.f90:23-268) -----------------------
+ * count builds the node graph and keeps it; fill copies it into caller-allocated arrays
+ * indexL/indexU(0:NP), itemL(NPL), itemU(NPU) — sorted ascending per row, 1-based. */
+int fistr_b200_mat_con_count(int n_node, int nn_internal, int n_elem_type, const int *elem_type_index,
+                             const int *elem_type_item, const int *elem_node_index,
+                             const int *elem_node_item, int *N, int *NP, int *NPL, int *NPU);
+int fistr_b200_mat_con_fill(int *indexL, int *itemL, int *indexU, int *itemU);
+
+/* ---- matrix residency ---------------------------------------------------------------------
+ * Declares the structure of THE matrix (hecmwST_matrix, hecmw_util_f.F90:433-468) and the halo
+ * tables of the subdomain (hecmwST_local_mesh comm fields, :304-312).  Called implicitly by
+ * solve/matvec/stiffmatrix when the structure pointers or sizes change or Iarray(98)=1. */
+int fistr_b200_mat_structure(int N, int NP, int NPL, int NPU, const int *indexL, const int *itemL,
+                             const int *indexU, const int *itemU, int n_neighbor_pe,
+                             const int *neighbor_pe, const int *import_index, const int *import_item,
+                             const int *export_index, const int *export_item);
+/* values/RHS between host arrays and the device-resident copy (any pointer may be NULL = skip) */
+int fistr_b200_mat_upload(const double *D, const double *AL, const double *AU, const double *B);
+int fistr_b200_mat_download(double *D, double *AL, double *AU, double *B, double *X);
+
+/* ---- fstr_StiffMatrix + hecmw_mat_ass_elem ---------------------------------------------------
+ * (fistr1/src/analysis/static/fstr_StiffMatrix.f90:18-212; STF_C3D8IC static_LIB_3dIC.f90:21-215;
+ *  STF_C3 static_LIB_3d.f90:47-205; STF_C3D8Bbar static_LIB_C3D8.f90:23-198;
+ *  hecmw_mat_ass_elem hecmw_mat_ass.f90:31-134).  Element types 361 (elemopt361 = 1 FI, 2 B-bar,
+ *  3 IC) and 342, linear elastic (nlgeom_flag == INFINITE).  The matrix structure must have been
+ *  declared.  D/AL/AU: host destinations in the hecmwST_matrix layout, or NULL to leave the
+ *  assembled matrix on the device only.  Zeroes the matrix first (hecmw_mat_clear). */
+int fistr_b200_stiffmatrix_3d(int n_node, const double *node, int n_elem, int n_elem_type,
+                              const int *elem_type_index, const int *elem_type_item,
+                              const int *elem_node_index, const int *elem_node_item,
+                              const int *section_ID, int n_sect, const int *sect_elemopt361,
+                              const double *sect_E, const double *sect_nu, double *D, double *AL,
+                              double *AU, double *time_ms /* [2]: integrate+scatter kernel, total */);
+
+/* ---- hecmw_mat_ass_bc (hecmw_mat_ass.f90:292-429), batched over the constrained DOFs that
+ * fstr_AddBC (fistr1/src/analysis/static/fstr_AddBC.f90:54-109) visits.  Operates on the
+ * device-resident matrix and RHS. */
+int fistr_b200_mat_ass_bc(int nbc, const int *inode, const int *idof, const double *rhs);
+
+/* ---- hecmw_solve (hecmw1/src/solver/hecmw_solver.f90:9-78 -> hecmw_solve_iterative
+ * iterative/hecmw_solver_Iterative.f90:13-210 -> hecmw_solve_CG iterative/hecmw_solver_CG.f90:19-312).
+ * Reads ITER/METHOD/PRECOND/iterPREmax/ITERLOG/TIMELOG/NCOLOR_IN and flags 96/97/98 from Iarray,
+ * RESID/SIGMA_DIAG from Rarray (slot map hecmw_matrix_misc.f90:89-121); writes X(1:3*NP) including
+ * halo, Iarray(81/82/96/97/98).  D/AL/AU/B == NULL means "use the device-resident copy".
+ * Collective over all ranks of the communicator.  time_out[5] = set-up, solver, comm, matvec,
+ * precond seconds (the TIMELOG summary, Iterative.f90:192-208). */
+int fistr_b200_solve_33(int N, int NP, int NPL, int NPU, const double *D, const double *AL,
+                        const double *AU, const int *indexL, const int *itemL, const int *indexU,
+                        const int *itemU, const double *B, double *X, int *Iarray, double *Rarray,
+                        int n_neighbor_pe, const int *neighbor_pe, const int *import_index,
+                        const int *import_item, const int *export_index, const int *export_item,
+                        int my_rank, int petot, int *iter_out, double *resid_out, double *time_out);
+/* residual history of the last solve (RESID per iteration, what ITERLOG=YES prints, CG.f90:245) */
+int fistr_b200_solve_history(double *hist, int max_len);
+/* final true relative residual of the last solve (hecmw_rel_resid_L2, Iterative.f90:166) */
+int fistr_b200_solve_resid2(double *resid2);
+
+/* ---- hecmw_matvec_33 (hecmw1/src/solver/las/hecmw_solver_las_33.f90:50-74,135-351):
+ * halo exchange of X then Y(1:3N) = A X.  Uses the device-resident matrix; X is read for 3*NP
+ * values (halo part overwritten by the exchange when petot>1), Y receives 3*N values. */
+int fistr_b200_matvec_33(const double *X, double *Y);
+/* SpMV micro-benchmark on the resident matrix: nrep launches, x_i = sin(i); returns mean ms/launch */
+int fistr_b200_matvec_bench(int nrep, int flush_l2, double *ms_mean, double *ms_min);
+
+/* ---- hecmw_precond_33_{setup,apply,clear} (precond/33/hecmw_precond_33.f90:27-115;
+ * DIAG precond/33/hecmw_precond_DIAG_33.f90:27-159; SSOR precond/33/hecmw_precond_SSOR_33.f90:55-467) */
+int fistr_b200_precond_33_setup(int precond, double sigma_diag, int ncolor_in);
+int fistr_b200_precond_33_apply(double *ZP /* 3*NP in/out */);
+int fistr_b200_precond_33_clear(void);
+int fistr_b200_precond_33_info(int *ncolor, int *perm /* N or NULL */);
+
+/* ---- hecmw_update_3_R (communication/hecmw_comm_f.F90:669-694) on a host vector */
+int fistr_b200_update_3_R(double *X /* 3*NP in/out */);
+
+/* host-only (no GPU): the multicolour ordering (RCM + greedy colouring, hecmw_matrix_ordering_CM.f90 /
+ * hecmw_matrix_ordering_MC.f90) the device SSOR uses; perm[new-1]=old (1-based), color_index has ncolor+1 entries */
+int fistr_b200_debug_ssor_order(int N, const int *indexL, const int *itemL, const int *indexU, const int *itemU,
+                                int ncolor_in, int *perm, int *ncolor, int *color_index);
+
+/* ---- instrumentation */
+int64_t fistr_b200_launch_count(void);   /* kernels launched by this library since init/reset */
+int fistr_b200_device_info(char *name, int name_len, int *sm_count, int64_t *mem_bytes);
+/* FP64 FMA micro-benchmark (roofline denominator for element integration); TFLOP/s */
+int fistr_b200_fp64_peak(double *tflops);
+/* HBM copy micro-benchmark (cross-check of MEASURED_PEAKS.json); GB/s read+write */
+int fistr_b200_hbm_copy_peak(double *gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,75 @@
+"""Generates the golden fixtures under tests/golden/ from the reference tree (run in the build
+container where /root/reference is mounted; the GPU box only sees the committed .npz/.json files).
+
+For every deck that pins the hot path with a CLOAD-only load case:
+  * the mesh as parsed by frontistr_b200.mshio.read_msh (arrays only, no reference source text)
+  * the !BOUNDARY / !CLOAD / !SOLVER cards
+  * the nodal displacement max/min lines of '##### Global Summary' from <deck>_correct.log
+    (the quantities the reference's own harness compares, examples/test_FrontISTR.rb:148-237)
+Also stores the 2-rank halo-table fixture examples/static/refine/cube/P02/sample_P02.{0,1}.
+"""
+import json
+import os
+import re
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
+from frontistr_b200 import mshio  # noqa: E402
+
+REF = os.environ.get("FISTR_REFERENCE", "/root/reference")
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+DECKS = [
+    ("A361", "examples/static/exA/A361.msh", "examples/static/exA/A300.cnt", "examples/static/exA/A361_correct.log"),
+    ("A342", "examples/static/exA/A342.msh", "examples/static/exA/A300.cnt", "examples/static/exA/A342_correct.log"),
+    ("G361", "examples/static/exG/A361.msh", "examples/static/exG/G300.cnt", "examples/static/exG/A361_correct.log"),
+    ("G342", "examples/static/exG/A342.msh", "examples/static/exG/G300.cnt", "examples/static/exG/A342_correct.log"),
+]
+
+
+def parse_log(path):
+    out = {}
+    with open(path) as f:
+        txt = f.read()
+    blk = txt.split("##### Global Summary")[1]
+    for line in blk.splitlines():
+        m = re.match(r"\s*//(U[123])\s+(\S+)\s+(\S+)", line)
+        if m:
+            out[m.group(1)] = [float(m.group(2)), float(m.group(3))]
+        if line.strip().startswith("##### @Element"):
+            break
+    return out
+
+
+def main():
+    meta = {}
+    for name, msh, cnt, log in DECKS:
+        m = mshio.read_msh(os.path.join(REF, msh))
+        c = mshio.read_cnt(os.path.join(REF, cnt))
+        np.savez_compressed(os.path.join(OUT, name + ".npz"),
+                            node=m.node, elem_type_index=m.elem_type_index, elem_type_item=m.elem_type_item,
+                            elem_node_index=m.elem_node_index, elem_node_item=m.elem_node_item,
+                            global_node_ID=m.global_node_ID,
+                            **{"ngrp_" + k: v for k, v in m.node_group.items()})
+        meta[name] = dict(source=dict(msh=msh, cnt=cnt, log=log), E=m.sections[0]["E"], nu=m.sections[0]["nu"],
+                          boundary=c["boundary"], cload=c["cload"], solver=[c["solver"][0], c["solver"][1]],
+                          golden=parse_log(os.path.join(REF, log)), tolerance_abs=1.0e-4)
+    # 2-rank halo fixture
+    for r in (0, 1):
+        d = mshio.read_dist_mesh(os.path.join(REF, "examples/static/refine/cube/P02/sample_P02.%d" % r))
+        np.savez_compressed(os.path.join(OUT, "sample_P02_%d.npz" % r),
+                            n_node=d.n_node, nn_internal=d.nn_internal, node=d.node, node_ID=d.node_ID,
+                            global_node_ID=d.global_node_ID, elem_type_index=d.elem_type_index,
+                            elem_type_item=d.elem_type_item, elem_node_index=d.elem_node_index,
+                            elem_node_item=d.elem_node_item, neighbor_pe=d.neighbor_pe,
+                            import_index=d.import_index, import_item=d.import_item,
+                            export_index=d.export_index, export_item=d.export_item, my_rank=d.my_rank, PETOT=d.PETOT)
+    with open(os.path.join(OUT, "golden.json"), "w") as f:
+        json.dump(meta, f, indent=1)
+    print("wrote", sorted(os.listdir(OUT)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,162 @@
+"""Oracle unit checks and CPU-side checks of product host logic against the oracle."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from frontistr_b200 import meshgen
+import fb_util as util
+
+
+def test_matvec_equals_scipy():
+    from oracle import oracle as orc
+    mesh = util.distort(meshgen.hex_cube(5))
+    A = util.oracle_problem(mesh, util.cube_cnt())
+    x = np.sin(np.arange(1, 3 * A.NP + 1, dtype=float))
+    y = orc.matvec(A, x)[: 3 * A.N]
+    assert util.rel_l2(y, A.to_scipy() @ x) < 1e-14
+
+
+def test_calinverse_spd_and_reference_quirk():
+    from oracle import oracle as orc
+    rng = np.random.default_rng(1)
+    M = rng.standard_normal((9, 9)); S = M @ M.T + 9 * np.eye(9)
+    Af = np.asfortranarray(S.copy())
+    orc.lib().orc_calInverse(9, Af.ctypes.data_as(C.POINTER(C.c_double)))
+    assert np.abs(Af @ S - np.eye(9)).max() < 1e-12
+
+
+def test_bc_elimination_properties():
+    mesh = meshgen.hex_cube(3)
+    cnt = util.cube_cnt()
+    cnt["boundary"] = [("FIX", 1, 3, 0.0), ("CL1", 1, 1, 0.25)]   # a non-zero prescribed displacement too
+    A0 = util.oracle_problem(mesh, cnt, apply_bc=False)
+    A = util.oracle_problem(mesh, cnt, apply_bc=True)
+    K0 = A0.to_scipy().toarray(); K = A.to_scipy().toarray()
+    from frontistr_b200 import hecmw
+    n, d, v = hecmw.boundary_dofs(mesh, cnt["boundary"])
+    c = 3 * (n - 1) + d - 1
+    ubar = np.zeros(3 * A.N); ubar[c] = v
+    free = np.setdiff1d(np.arange(3 * A.N), c)
+    # two separately assembled matrices: OpenMP atomics make the summation order free
+    assert np.allclose(K[np.ix_(free, free)], K0[np.ix_(free, free)], rtol=1e-13, atol=1e-13 * abs(K0).max())
+    assert np.all(K[c][:, free] == 0) and np.all(K[free][:, c] == 0)
+    assert np.allclose(K[np.ix_(c, c)], np.eye(len(c)))
+    assert np.allclose(A.B[c], v)
+    assert np.allclose(A.B[free], A0.B[free] - (K0 @ ubar)[free], rtol=1e-12, atol=1e-12 * abs(K0).max())
+
+
+@pytest.mark.parametrize("maker", [lambda: meshgen.hex_cube(4), lambda: meshgen.tet10_cube(2)])
+def test_product_mat_con_equals_oracle(maker):
+    """hecmw_mat_con host implementation of the product (no GPU needed) == oracle restatement."""
+    from oracle import oracle as orc
+    from frontistr_b200 import hecmw
+    mesh = maker()
+    A = orc.mat_con(mesh)
+    P = hecmw.hecmw_mat_con(mesh)
+    assert (A.N, A.NP, A.NPL, A.NPU) == (P.N, P.NP, P.NPL, P.NPU)
+    for k in ("indexL", "itemL", "indexU", "itemU"):
+        assert np.array_equal(getattr(A, k), getattr(P, k)), k
+
+
+def test_hex_cube_counts_match_survey():
+    """SURVEY §8 sizes: blocks (incl. diag) of an n^3 hex cube = (3n+1)^3."""
+    from frontistr_b200 import hecmw
+    n = 6
+    P = hecmw.hecmw_mat_con(meshgen.hex_cube(n))
+    assert P.NP == (n + 1) ** 3
+    assert P.NP + P.NPL + P.NPU == (3 * n + 1) ** 3
+    assert P.NPL == P.NPU
+
+
+def test_product_ssor_ordering_equals_oracle():
+    from oracle import oracle as orc
+    from frontistr_b200 import hecmw
+    for mesh in (util.distort(meshgen.hex_cube(5)), meshgen.tet10_cube(2)):
+        A = util.oracle_problem(mesh, util.cube_cnt())
+        pc = orc.Precond(A, precond=1, ncolor_in=10, nthreads=2)
+        perm, nc, ci = hecmw.debug_ssor_order(A, 10)
+        assert nc == pc.ncolor
+        assert np.array_equal(perm, pc.perm())
+        # colours are independent sets
+        K = A.to_scipy()[:, : 3 * A.N]
+        adj = (abs(K) > 0).astype(int)
+        for c in range(nc):
+            rows = perm[ci[c]:ci[c + 1]] - 1
+            sub = adj[3 * rows][:, 3 * rows].toarray()
+            assert np.all(sub == np.diag(np.diag(sub)))
+
+
+def test_element_emulation_equals_oracle():
+    """The per-lane phase functions the CUDA element kernel is made of, run on the host."""
+    from oracle import oracle as orc
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "frontistr_b200", "libfistr_b200_emul.so")
+    if not os.path.exists(so):
+        import __graft_entry__ as g
+        g.build_emul()
+    em = C.CDLL(so)
+    dp = C.POINTER(C.c_double)
+    rng = np.random.default_rng(0)
+    base = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)
+    for trial in range(4):
+        ec = np.ascontiguousarray(base * [0.7, 1.3, 0.9] + 0.15 * rng.standard_normal((8, 3)) * (trial > 0))
+        for form, kind in ((3, "IC"), (1, "FI"), (2, "BBAR")):
+            K0 = orc.element_stiffness(kind, ec, 210000.0, 0.3)
+            K1 = np.zeros_like(K0)
+            assert em.fbemul_element_stiffness(form, ec.ctypes.data_as(dp), C.c_double(210000.0), C.c_double(0.3), K1.ctypes.data_as(dp)) == 0
+            assert np.abs(K0 - K1).max() <= 5e-15 * np.abs(K0).max()
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], float)
+    e = [(0, 1), (1, 2), (2, 0), (0, 3), (1, 3), (2, 3)]
+    for trial in range(3):
+        vv = v + 0.1 * rng.standard_normal((4, 3)) * (trial > 0)
+        ec = np.ascontiguousarray(np.vstack([vv, [(vv[a] + vv[b]) / 2 for a, b in e]]))
+        K0 = orc.element_stiffness("C3", ec, 4000.0, 0.3, etype=342)
+        K1 = np.zeros_like(K0)
+        assert em.fbemul_element_stiffness(10, ec.ctypes.data_as(dp), C.c_double(4000.0), C.c_double(0.3), K1.ctypes.data_as(dp)) == 0
+        assert np.abs(K0 - K1).max() <= 5e-15 * np.abs(K0).max()
+
+
+def test_partitioned_oracle_equals_serial():
+    """DIAG-CG is partition invariant up to rounding: 1 vs 2 vs 3 rank-emulated subdomains."""
+    from oracle import oracle as orc
+    mesh = util.distort(meshgen.hex_cube(6))
+    cnt = util.cube_cnt(tol=1e-10)
+    A = util.oracle_problem(mesh, cnt)
+    orc.precond_clear()
+    r1 = orc.solve(mesh, A)
+    for nparts in (2, 3):
+        parts = util.simple_partition(mesh, nparts)
+        mats = [util.oracle_problem(p, cnt) for p in parts]
+        orc.precond_clear()
+        r = orc.solve(parts, mats)
+        assert r["error"] == 0 and abs(r["iter"] - r1["iter"]) <= 2
+        ug = np.zeros(3 * mesh.n_node)
+        for p, Ap in zip(parts, mats):
+            g = p.global_node_ID[: p.nn_internal] - 1
+            ug.reshape(-1, 3)[g] = Ap.X.reshape(-1, 3)[: p.nn_internal]
+            # halo of X filled by hecmw_update_m_R
+            gh = p.global_node_ID[p.nn_internal:] - 1
+        assert util.rel_l2(ug, A.X) < 1e-8
+    orc.precond_clear()
+
+
+def test_halo_fixture_tables():
+    """The reference's checked-in 2-rank fixture examples/static/refine/cube/P02/sample_P02.{0,1}."""
+    from oracle import oracle as orc
+    import ctypes
+    m0, m1 = util.load_dist_fixture("sample_P02", 0), util.load_dist_fixture("sample_P02", 1)
+    assert (m0.n_node, m0.nn_internal, m0.n_neighbor_pe) == (7, 4, 1)
+    assert m0.import_item.tolist() == [5, 6, 7] and m0.export_item.tolist() == [2, 3, 4]
+    xs = []
+    for m in (m0, m1):
+        x = np.zeros(3 * m.n_node)
+        x.reshape(-1, 3)[: m.nn_internal] = m.global_node_ID[: m.nn_internal, None] + 0.1 * np.arange(3)
+        xs.append(x)
+    cms = [orc.c_mesh(m) for m in (m0, m1)]
+    arr = (orc.orc_mesh * 2)(*[c.s for c in cms])
+    ptrs = (orc.c_dbl_p * 2)(*[x.ctypes.data_as(orc.c_dbl_p) for x in xs])
+    orc.lib().orc_update_3_R(2, arr, ptrs)
+    for m, x in zip((m0, m1), xs):
+        want = m.global_node_ID[:, None] + 0.1 * np.arange(3)
+        assert np.array_equal(x.reshape(-1, 3), want)
