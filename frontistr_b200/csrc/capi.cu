@@ -4,6 +4,7 @@
 #include <cstdarg>
 
 #include "context.hpp"
+#include "partition.hpp"
 
 namespace fb {
 thread_local std::string g_last_error;
@@ -744,6 +745,9 @@ int fistr_b200_solve_33(int N, int NP, int NPL, int NPU, const double *D, const 
   FB_REQUIRE_INIT();
   Context &C = ctx();
   const double t_entry = now_s();
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  FB_CUDA(cudaEventCreate(&ev_in)); FB_CUDA(cudaEventCreate(&ev_out));
+  FB_CUDA(cudaEventRecord(ev_in, C.stream));
   if (petot != C.petot) return fail(FISTR_B200_ERR_COMM, "solve_33: petot=%d but the communicator has %d ranks", petot, C.petot);
   (void)my_rank;
   if (IA(99) != 1) return fail(FISTR_B200_ERR_ARG, "solve_33: Iarray(99)=%d (direct solvers are not on this path)", IA(99));
@@ -756,7 +760,8 @@ int fistr_b200_solve_33(int N, int NP, int NPL, int NPU, const double *D, const 
   // --- structure / values residency
   bool structure_changed = false;
   const bool same_sizes = C.have_structure && C.N == N && C.NP == NP && C.NPL == NPL && C.NPU == NPU;
-  if (!same_sizes || (indexL && (C.key_indexL != indexL || C.key_itemL != itemL))) {
+  // Iarray(98)=1 with host values given: the caller declares a (possibly) new structure -> re-upload it
+  if (!same_sizes || (indexL && (C.key_indexL != indexL || C.key_itemL != itemL)) || (IA(98) >= 1 && indexL && D)) {
     if (!indexL) return fail(FISTR_B200_ERR_STATE, "solve_33: no structure on the device and none given");
     const bool keep_vals = same_sizes && C.values_on_device && !D;   // same shape re-declared, values device-only
     FB_TRY(fistr_b200_mat_structure(N, NP, NPL, NPU, indexL, itemL, indexU, itemU, n_neighbor_pe, neighbor_pe,
@@ -979,7 +984,11 @@ int fistr_b200_solve_33(int N, int NP, int NPL, int NPU, const double *D, const 
   double rnorm2;
   FB_CUDA(cudaMemcpyAsync(&rnorm2, red + RED_TMP, sizeof rnorm2, cudaMemcpyDeviceToHost, C.stream));
   if (X) FB_CUDA(cudaMemcpyAsync(X, C.X.p, sizeof(double) * np3, cudaMemcpyDeviceToHost, C.stream));
+  FB_CUDA(cudaEventRecord(ev_out, C.stream));
   FB_CUDA(cudaStreamSynchronize(C.stream));
+  float ev_ms = 0.f;
+  cudaEventElapsedTime(&ev_ms, ev_in, ev_out);
+  cudaEventDestroy(ev_in); cudaEventDestroy(ev_out);
   const double resid2 = std::sqrt(rnorm2 / (BNRM2 == 0.0 ? 1.0 : BNRM2));
   if (resid2 < TOL) IA(81) = 1;
   C.last_resid2 = resid2;
@@ -997,7 +1006,7 @@ int fistr_b200_solve_33(int N, int NP, int NPL, int NPU, const double *D, const 
   }
   if (iter_out) *iter_out = ITER;
   if (resid_out) *resid_out = RESID;
-  if (time_out) { time_out[0] = Tset; time_out[1] = Tsol; time_out[2] = Tcomm; time_out[3] = time_Ax; time_out[4] = 0.0; }
+  if (time_out) { time_out[0] = Tset; time_out[1] = Tsol; time_out[2] = Tcomm; time_out[3] = time_Ax; time_out[4] = ev_ms * 1e-3; }
   if (error) {
     static const char *msg[] = {"not converged within ceratin iterations", "diverged due to indefinite or negative definite matrix", "diverged due to indefinite preconditioner"};
     if (C.rank == 0) printf("\n  #### HEC-MW-SOLVER-W-%d: \n    %s\n\n", error, msg[error - 3001]);
@@ -1007,6 +1016,13 @@ int fistr_b200_solve_33(int N, int NP, int NPL, int NPU, const double *D, const 
     if (C.rank == 0) printf("\n  #### HEC-MW-SOLVER-W-2002: \n    ZERO RHS norm\n\n");
     return ret_warn;
   }
+  return 0;
+}
+
+// hecmw_part1's RCB (host-only, no GPU): domain of every node, hecmw_partition.c:1570-1660
+int fistr_b200_part_rcb(int n_node, const double *node, int n_div, const int *axes, int *domain) {
+  const int rc = rcb_partition(n_node, node, n_div, axes, domain);
+  if (rc) return fail(FISTR_B200_ERR_ARG, "part_rcb failed (%d)", rc);
   return 0;
 }
 

@@ -93,8 +93,9 @@ int fistr_b200_mat_ass_bc(int nbc, const int *inode, const int *idof, const doub
  * Reads ITER/METHOD/PRECOND/iterPREmax/ITERLOG/TIMELOG/NCOLOR_IN and flags 96/97/98 from Iarray,
  * RESID/SIGMA_DIAG from Rarray (slot map hecmw_matrix_misc.f90:89-121); writes X(1:3*NP) including
  * halo, Iarray(81/82/96/97/98).  D/AL/AU/B == NULL means "use the device-resident copy".
- * Collective over all ranks of the communicator.  time_out[5] = set-up, solver, comm, matvec,
- * precond seconds (the TIMELOG summary, Iterative.f90:192-208). */
+ * Collective over all ranks of the communicator.  time_out[5] = set-up, solver, comm, matvec seconds
+ * (the TIMELOG summary, Iterative.f90:192-208; matvec = sampled CUDA-event SpMV time x iterations) and
+ * [4] = CUDA-event time of the whole call on the library stream, H2D/D2H copies included. */
 int fistr_b200_solve_33(int N, int NP, int NPL, int NPU, const double *D, const double *AL,
                         const double *AU, const int *indexL, const int *itemL, const int *indexU,
                         const int *itemU, const double *B, double *X, int *Iarray, double *Rarray,
@@ -122,6 +123,10 @@ int fistr_b200_precond_33_info(int *ncolor, int *perm /* N or NULL */);
 
 /* ---- hecmw_update_3_R (communication/hecmw_comm_f.F90:669-694) on a host vector */
 int fistr_b200_update_3_R(double *X /* 3*NP in/out */);
+
+/* ---- hecmw_part1 in-process: node-based RCB (hecmw1/tools/partitioner/hecmw_partition.c:1570-1660),
+ * axes[i] in {0,1,2} per bisection level (the 'x,y,z' line of hecmw_part_ctrl.dat); host-only */
+int fistr_b200_part_rcb(int n_node, const double *node, int n_div, const int *axes, int *domain);
 
 /* host-only (no GPU): the multicolour ordering (RCM + greedy colouring, hecmw_matrix_ordering_CM.f90 /
  * hecmw_matrix_ordering_MC.f90) the device SSOR uses; perm[new-1]=old (1-based), color_index has ncolor+1 entries */

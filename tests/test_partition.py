@@ -1,0 +1,61 @@
+"""The in-process partitioner (frontistr_b200/partition.py + fistr_b200_part_rcb) against the REAL
+hecmw_part1 of the reference (fixtures made by tests/golden/make_partition_golden.py with
+oracle/_ref/hecmw_part1): node->domain map incl. the tie behaviour of its quick sort, local numbering,
+element selection and every communication table must be identical."""
+import os
+
+import numpy as np
+import pytest
+
+import fb_util as util
+from frontistr_b200 import meshgen, partition
+
+CASES = {"hex5_xy": lambda: meshgen.hex_cube(5), "hex6_xyz": lambda: meshgen.hex_cube(6),
+         "hex7_zyx": lambda: meshgen.hex_cube(7), "tet2_xy": lambda: meshgen.tet10_cube(2)}
+KEYS = ("global_node_ID", "node_ID", "elem_type_index", "elem_type_item", "elem_node_index", "elem_node_item",
+        "neighbor_pe", "import_index", "import_item", "export_index", "export_item")
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_partition_equals_hecmw_part1(name):
+    d = np.load(os.path.join(util.GOLDEN, "part_%s.npz" % name))
+    parts = partition.partition(CASES[name](), str(d["axes"]))
+    assert len(parts) == int(d["ndomain"])
+    for r, p in enumerate(parts):
+        assert p.n_node == int(d["r%d_n_node" % r]) and p.nn_internal == int(d["r%d_nn_internal" % r])
+        for k in KEYS:
+            assert np.array_equal(getattr(p, k), d["r%d_%s" % (r, k)]), (r, k)
+
+
+def test_partition_tables_are_consistent():
+    """export list of p towards q == import list of q from p (as global ids), every node owned once."""
+    mesh = meshgen.hex_cube(9)
+    parts = partition.partition(mesh, "xyz")
+    owned = np.concatenate([p.global_node_ID[: p.nn_internal] for p in parts])
+    assert np.array_equal(np.sort(owned), np.arange(1, mesh.n_node + 1))
+    for p in parts:
+        for a, q in enumerate(p.neighbor_pe):
+            qm = parts[q]
+            b = int(np.nonzero(qm.neighbor_pe == p.my_rank)[0][0])
+            exp = p.global_node_ID[p.export_item[p.export_index[a]: p.export_index[a + 1]] - 1]
+            imp = qm.global_node_ID[qm.import_item[qm.import_index[b]: qm.import_index[b + 1]] - 1]
+            assert np.array_equal(exp, imp)
+
+
+def test_partitioned_solve_with_real_tables():
+    """Oracle CG on the 8 subdomains hecmw_part1 would produce == serial solve (DIAG is partition invariant)."""
+    from oracle import oracle as orc
+    mesh = util.distort(meshgen.hex_cube(6))
+    cnt = util.cube_cnt(tol=1e-10)
+    A = util.oracle_problem(mesh, cnt)
+    orc.precond_clear()
+    r1 = orc.solve(mesh, A)
+    parts = partition.partition(mesh, "xyz")
+    mats = [util.oracle_problem(p, cnt) for p in parts]
+    orc.precond_clear()
+    r = orc.solve(parts, mats)
+    assert r["error"] == 0 and abs(r["iter"] - r1["iter"]) <= 2
+    for p, Ap in zip(parts, mats):
+        g = p.global_node_ID - 1
+        assert util.rel_l2(Ap.X.reshape(-1, 3), A.X.reshape(-1, 3)[g]) < 1e-8    # halo included (update_m_R)
+    orc.precond_clear()
