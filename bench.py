@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native FrontISTR linear-static hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n 150]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], SURVEY §8d "H150"): synthetic C3D8 hex cube, 150^3 elements
+(10.3 M DOF), E=210000, nu=0.3, face x=0 fixed, CLOAD -1 (dof 3) on face x=1, C3D8 incompatible-mode
+elements (the reference default for linear static), `!SOLVER, METHOD=CG, PRECOND=3` (3x3 block-Jacobi
+"DIAG"), RESID=1e-8.  One STEP = one complete hecmw_solve of that system (all CG iterations to
+convergence, X0 = 0) — the reference's `solve_LINEQ` call.
+
+Metric: CG iterations per second (whole job).
+  value : matrix and RHS already resident in HBM (assembled there by the library's own
+          fstr_StiffMatrix + hecmw_mat_ass_bc kernels); timed region = K solves.
+  e2e   : the literal drop-in call: fistr_b200_solve_33 with HOST hecMAT%D/AL/AU/B/X (pinned) — the
+          6.6 GB matrix upload, the private SELL repack, the preconditioner set-up and the download
+          of X are all inside the timed region, every step.
+For N > 1 the same global mesh is partitioned with the in-process restatement of hecmw_part1's RCB
+(one subdomain per GPU; halo exchange + dot-product all-reduce over NCCL/NVLink): strong scaling.
+
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/, OpenMP, all host
+cores) on the same workload, bounded to a few CG iterations per step (the reference itself is
+Fortran 90 and cannot be built in this image: no Fortran compiler — see DESIGN.md).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "cg_iterations_per_second"
+UNIT = "CG iter/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=150, help="hex cube edge in elements (150 = configs[1], 200 = configs[2])")
+    ap.add_argument("--tol", type=float, default=1.0e-8)
+    ap.add_argument("--precond", type=int, default=3)
+    ap.add_argument("--maxit", type=int, default=20000)
+    ap.add_argument("--ref-iters", type=int, default=0, help="CG iterations per reference-arm step (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(n):
+    return {150: "H150", 200: "H200"}.get(n, "H%d" % n) + ": C3D8(IC) hex cube %d^3 el, %d DOF, CG+DIAG(3x3 block-Jacobi)" % (
+        n, 3 * (n + 1) ** 3)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def build_problem_host(args, rank, world):
+    """Mesh (partitioned for world > 1) + solver card; pure host work, shared by both arms."""
+    import fb_util as util
+    from frontistr_b200 import meshgen
+    mesh = meshgen.hex_cube(args.n)
+    if world > 1:
+        from frontistr_b200 import partition
+        axes = {2: "x", 4: "xy", 8: "xyz"}[world]
+        dom = partition.rcb_domains(mesh, axes)
+        mesh = partition.local_mesh(mesh, dom, rank, world)
+    cnt = util.cube_cnt(tol=args.tol, precond=args.precond, maxit=args.maxit)
+    return mesh, cnt
+
+
+def run_reference(args):
+    """Reference arm: the CPU restatement of the reference's own algorithm (oracle/), all host threads,
+    on the same workload; each step = `ref_iters` CG iterations of the H150 solve (MAXIT-bounded)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import fb_util as util
+    from frontistr_b200 import hecmw as host_helpers   # load/BC bookkeeping helpers only (numpy)
+    from frontistr_b200.mshio import apply_solver_card
+    from oracle import oracle as orc
+    t0 = time.time()
+    args_local = argparse.Namespace(**vars(args))
+    mesh, cnt = build_problem_host(args_local, 0, 1)
+    A = orc.mat_con(mesh)
+    t1 = time.time()
+    orc.stiffmatrix(mesh, A)
+    t2 = time.time()
+    host_helpers.fstr_ass_load_cload(mesh, A, cnt["cload"])
+    n, d, v = host_helpers.boundary_dofs(mesh, cnt["boundary"])
+    for i in range(len(n)):
+        orc.mat_ass_bc(A, int(n[i]), int(d[i]), float(v[i]))
+    t3 = time.time()
+    cores = orc.num_threads()
+    iters = args.ref_iters
+    if iters <= 0:   # size a step to ~6 s: one probe iteration pair
+        apply_solver_card(A, cnt["solver"]); A.Iarray[20] = 0; A.Iarray[21] = 0
+        A.Iarray[0] = 2; A.X[:] = 0.0
+        orc.precond_clear()
+        r = orc.solve(mesh, A)
+        per_it = max(r["times"][1] / 2.0, 1e-4)
+        iters = int(min(200, max(4, round(6.0 / per_it))))
+    apply_solver_card(A, cnt["solver"]); A.Iarray[20] = 0; A.Iarray[21] = 0
+    A.Iarray[0] = iters
+    tot_it, tot_s = 0, 0.0
+    for step in range(args.warmup + args.steps):
+        A.X[:] = 0.0
+        A.Iarray[96] = 1
+        orc.precond_clear()
+        r = orc.solve(mesh, A)
+        if step >= args.warmup:
+            tot_it += iters
+            tot_s += float(r["times"][1])
+    value = tot_it / tot_s
+    sample = ("%d CG iterations per step (MAXIT-bounded) of the full %s system on the host, solver-loop time "
+              "(the reference's TIMELOG 'solver time'); untimed set-up: mat_con %.1fs, stiffness %.1fs "
+              "(%.3f M elem/s), BC %.1fs" % (iters, "H%d" % args.n, t1 - t0, t2 - t1,
+                                             mesh.n_elem / (t2 - t1) / 1e6, t3 - t2))
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(args.steps, 1),
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": workload_name(args.n), "tol": args.tol, "precond": args.precond},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "assembly_elements_per_s": mesh.n_elem / (t2 - t1)}
+    print(json.dumps(out), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus %d must be launched with torch.distributed.run --nproc-per-node %d"
+                             % (args.gpus, args.gpus))
+        args.gpus = world
+    if world not in (1, 2, 4, 8):
+        raise SystemExit("RCB partitioning needs a power-of-two rank count (hecmw_part_get_control.c:271-340)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import fb_util as util
+    from frontistr_b200 import hecmw
+    from frontistr_b200.mshio import apply_solver_card
+
+    hecmw.init(local_rank)
+    if world > 1:
+        hecmw.comm_init_from_torch()
+    dev = hecmw.device_info()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- problem set-up: mat_con (host), fstr_StiffMatrix + hecmw_mat_ass_bc (device) -------------
+    t0 = time.time()
+    mesh, cnt = build_problem_host(args, rank, world)
+    t_mesh = time.time() - t0
+    t0 = time.time()
+    A = hecmw.hecmw_mat_con(mesh)
+    t_con = time.time() - t0
+    A.fstr_mat_init().hecMAT_init()
+    hecmw.mat_structure(mesh, A)
+    asm = [hecmw.fstr_StiffMatrix(mesh, A, to_host=False) for _ in range(3)]   # 2 warm-ups + 1 reported
+    asm_kernel_ms = allmax(asm[-1]["kernel_ms"])
+    asm_total_ms = allmax(asm[-1]["total_ms"])
+    n_elem_global = args.n ** 3
+    hecmw.fstr_ass_load_cload(mesh, A, cnt["cload"])
+    hecmw.mat_upload(A, values=False, rhs=True)
+    bn, bd, bv = hecmw.boundary_dofs(mesh, cnt["boundary"])
+    hecmw.hecmw_mat_ass_bc(bn, bd, bv)
+    apply_solver_card(A, cnt["solver"]); A.Iarray[20] = 0; A.Iarray[21] = 0
+    hecmw.set_option("time_ax", 1)
+    fp64_peak = hecmw.fp64_peak() if rank == 0 else 0.0
+    spmv_bytes_local = A.spmv_bytes()
+    spmv_bytes_global = allsum(spmv_bytes_local)
+
+    def one_solve(device_resident):
+        A.X[:] = 0.0
+        A.Iarray[96] = 1      # values "changed": numeric preconditioner set-up every solve (fstr_solve_NonLinear.f90:81-86)
+        r = hecmw.hecmw_solve(mesh, A, device_resident=device_resident)
+        if r["error"] != 0 or A.Iarray[80] != 1:
+            raise SystemExit("solve failed: error=%d converged=%d resid2=%g" % (r["error"], A.Iarray[80], r["resid2"]))
+        return r
+
+    def timed_block(device_resident, steps, warmup):
+        for _ in range(warmup):
+            one_solve(device_resident)
+        barrier()
+        c0 = hecmw.launch_count()
+        sampler = ClockSampler(local_rank).start() if rank == 0 else None
+        w0 = time.perf_counter()
+        ev_s, iters, ax_s = 0.0, 0, 0.0
+        last = None
+        for _ in range(steps):
+            last = one_solve(device_resident)
+            ev_s += float(last["times"][4])      # CUDA-event time of the whole call on the library stream
+            ax_s += float(last["times"][3])      # sampled CUDA-event SpMV time x iterations
+            iters += int(last["iter"])
+        barrier()
+        wall = time.perf_counter() - w0
+        clocks = sampler.stop() if sampler else None
+        return dict(ev_s=allmax(ev_s), wall_s=allmax(wall), iters=iters, ax_s=allmax(ax_s),
+                    launches=hecmw.launch_count() - c0, clocks=clocks, last=last)
+
+    # ---- device-resident arm: `value` ---------------------------------------------------------------
+    res = timed_block(True, args.steps, args.warmup)
+    value = res["iters"] / res["ev_s"]
+    spmv_ms = 1e3 * res["ax_s"] / max(res["iters"], 1)          # average SpMV launch duration (max over ranks)
+    peak, peak_src = measured_peaks()
+    achieved = spmv_bytes_global / world / (spmv_ms * 1e-3) / 1e9   # per-GPU GB/s
+    # ---- end-to-end arm: host hecMAT through the C-ABI, copies inside the timed region -------------
+    e2e = None
+    if not args.no_e2e:
+        hecmw.mat_download(A, values=True, rhs=True)
+        hecmw.host_register(A.D, A.AL, A.AU, A.B, A.X)
+        A.Iarray[97] = 0
+        r2 = timed_block(False, args.steps, max(1, min(args.warmup, 3)))
+        h2d = 8 * (A.D.size + A.AL.size + A.AU.size + A.B.size + A.X.size)
+        d2h = 8 * A.X.size
+        e2e = {"value": r2["iters"] / r2["wall_s"], "unit": UNIT, "h2d_bytes_per_step": int(allsum(h2d)),
+               "d2h_bytes_per_step": int(allsum(d2h)), "ms_per_step": 1e3 * r2["wall_s"] / args.steps,
+               "device_ms_per_step": 1e3 * r2["ev_s"] / args.steps,
+               "what": "fistr_b200_solve_33 with pinned host D/AL/AU/B/X: upload + SELL repack + precond set-up + "
+                       "CG + X download per step, wall clock between barriers"}
+    # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample of the same system ---------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as orc
+        if A.D is None or args.no_e2e:
+            hecmw.mat_download(A, values=True, rhs=True)
+        Ao = A                      # the oracle reads the host copy of the very same system
+        keep_I = A.Iarray.copy()
+        Ao.Iarray[0] = 2; Ao.X[:] = 0.0
+        orc.precond_clear()
+        r0 = orc.solve(mesh, Ao)
+        per_it = max(float(r0["times"][1]) / 2.0, 1e-4)
+        iters = int(min(400, max(4, round(15.0 / per_it))))
+        Ao.Iarray[0] = iters; Ao.X[:] = 0.0; Ao.Iarray[96] = 1
+        orc.precond_clear()
+        r1 = orc.solve(mesh, Ao)
+        cpu = {"value": iters / float(r1["times"][1]), "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+               "sample": "%d CG+DIAG iterations (MAXIT-bounded) of the same %d-DOF system, OpenMP oracle, solver-loop "
+                         "time %.1f s" % (iters, 3 * A.N, float(r1["times"][1]))}
+        A.Iarray[:] = keep_I
+    if rank == 0:
+        last = res["last"]
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": 1e3 * res["ev_s"] / args.steps, "higher_is_better": True,
+               "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": workload_name(args.n), "tol": args.tol, "precond": args.precond,
+                          "partition": "none" if world == 1 else "RCB-%s (in-process hecmw_part1 restatement), 1 subdomain/GPU"
+                          % {2: "x", 4: "xy", 8: "xyz"}[world],
+                          "l2": "inputs larger than L2: %.2f GB matrix streamed per SpMV per GPU vs 126 MB L2"
+                          % (spmv_bytes_global / world / 1e9)},
+               "iterations_per_step": res["iters"] // args.steps, "resid": float(last["resid"]),
+               "resid_true": float(last["resid2"]), "wall_ms_per_step": 1e3 * res["wall_s"] / args.steps,
+               "gpu_launches": int(res["launches"]), "clocks": res["clocks"], "e2e": e2e,
+               "roofline": {"bound": "hbm", "kernel": "spmv_sell2_kernel<0,256> (hecmw_matvec_33 + p.q)",
+                            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            "peak_source": peak_src, "traffic": None,
+                            "algorithmic_bytes_per_launch": spmv_bytes_global / world,
+                            "avg_launch_ms": spmv_ms,
+                            "cg_iteration": {"algorithmic_bytes": spmv_bytes_global / world + 112.0 * 3 * (args.n + 1) ** 3 / world,
+                                             "achieved_gbs": (spmv_bytes_global / world + 112.0 * 3 * (args.n + 1) ** 3 / world)
+                                             * value / 1e9}},
+               "cpu_baseline": cpu,
+               "assembly": {"elements_per_s_kernel": n_elem_global / (asm_kernel_ms * 1e-3),
+                            "elements_per_s_call": n_elem_global / (asm_total_ms * 1e-3),
+                            "kernel_ms": asm_kernel_ms, "fp64_peak_tflops_measured": fp64_peak,
+                            "fp64_frac": (150e3 * n_elem_global / world / (asm_kernel_ms * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None,
+                            "note": "STF_C3D8IC + scatter-add into BCSR slots, matrix zeroing included; 150 kflop/element (SURVEY a5)"},
+               "setup_s": {"mesh+partition": t_mesh, "mat_con": t_con}, "device": dev["name"]}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        hecmw.comm_finalize()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

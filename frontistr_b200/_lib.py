@@ -35,6 +35,8 @@ def lib():
         L.fistr_b200_get_option.restype = C.c_int64
         L.fistr_b200_set_option.argtypes = [C.c_char_p, C.c_int64]
         L.fistr_b200_get_option.argtypes = [C.c_char_p]
+        L.fistr_b200_host_register.argtypes = [C.c_void_p, C.c_int64]
+        L.fistr_b200_host_unregister.argtypes = [C.c_void_p]
         L.fistr_b200_precond_33_setup.argtypes = [C.c_int, C.c_double, C.c_int]
         _lib = L
     return _lib
@@ -59,6 +61,7 @@ EXPORTED = [
     "fistr_b200_get_option", "fistr_b200_comm_get_unique_id", "fistr_b200_comm_init",
     "fistr_b200_comm_finalize", "fistr_b200_mat_con_count", "fistr_b200_mat_con_fill",
     "fistr_b200_mat_structure", "fistr_b200_mat_upload", "fistr_b200_mat_download",
+    "fistr_b200_host_register", "fistr_b200_host_unregister",
     "fistr_b200_stiffmatrix_3d", "fistr_b200_mat_ass_bc", "fistr_b200_solve_33",
     "fistr_b200_solve_history", "fistr_b200_solve_resid2", "fistr_b200_matvec_33",
     "fistr_b200_matvec_bench", "fistr_b200_precond_33_setup", "fistr_b200_precond_33_apply",

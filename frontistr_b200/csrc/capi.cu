@@ -474,6 +474,18 @@ int fistr_b200_mat_download(double *D, double *AL, double *AU, double *B, double
   return 0;
 }
 
+int fistr_b200_host_register(void *ptr, int64_t bytes) {
+  FB_REQUIRE_INIT();
+  if (!ptr || bytes <= 0) return 0;
+  FB_CUDA(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+  return 0;
+}
+int fistr_b200_host_unregister(void *ptr) {
+  if (!ptr || !ctx().inited) return 0;
+  FB_CUDA(cudaHostUnregister(ptr));
+  return 0;
+}
+
 // ---- fstr_StiffMatrix --------------------------------------------------------------------------
 int fistr_b200_stiffmatrix_3d(int n_node, const double *node, int n_elem, int n_elem_type,
                               const int *elem_type_index, const int *elem_type_item,

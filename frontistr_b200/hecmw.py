@@ -120,6 +120,19 @@ def mat_download(hecMAT, values=True, rhs=True, x=False):
                                             dp(A.X) if x else None))
 
 
+def host_register(*arrays):
+    """Page-lock numpy arrays that will be passed repeatedly through the borrowed-pointer C-ABI."""
+    for a in arrays:
+        if a is not None and a.size:
+            check(_lib.lib().fistr_b200_host_register(a.ctypes.data, a.nbytes))
+
+
+def host_unregister(*arrays):
+    for a in arrays:
+        if a is not None and a.size:
+            check(_lib.lib().fistr_b200_host_unregister(a.ctypes.data))
+
+
 # ---- fstr_StiffMatrix ------------------------------------------------------------------------
 def fstr_StiffMatrix(hecMESH, hecMAT, to_host: bool = True):
     """Element integration + assembly on the device.  With to_host the D/AL/AU arrays of hecMAT are

@@ -68,6 +68,11 @@ int fistr_b200_mat_structure(int N, int NP, int NPL, int NPU, const int *indexL,
 /* values/RHS between host arrays and the device-resident copy (any pointer may be NULL = skip) */
 int fistr_b200_mat_upload(const double *D, const double *AL, const double *AU, const double *B);
 int fistr_b200_mat_download(double *D, double *AL, double *AU, double *B, double *X);
+/* Page-lock / release a host array the caller will pass repeatedly (hecMAT%D/AL/AU/B/X after
+ * hecMAT_init, fistr1/src/lib/m_fstr.f90:807-857) so the borrowed-pointer copies run at full PCIe
+ * rate.  Optional: unregistered (pageable) arrays work, only slower. */
+int fistr_b200_host_register(void *ptr, int64_t bytes);
+int fistr_b200_host_unregister(void *ptr);
 
 /* ---- fstr_StiffMatrix + hecmw_mat_ass_elem ---------------------------------------------------
  * (fistr1/src/analysis/static/fstr_StiffMatrix.f90:18-212; STF_C3D8IC static_LIB_3dIC.f90:21-215;
