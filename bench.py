@@ -64,6 +64,16 @@ def workload_name(n):
         n, 3 * (n + 1) ** 3)
 
 
+def ncu_traffic(n, world):
+    """dram__bytes_read+write per launch of the dominant kernel from the committed ncu --set full capture
+    (only valid for the workload it was captured on)."""
+    p = os.path.join(ROOT, "profiles", "r1_spmv_sell2_full.json")
+    if n == 150 and world == 1 and os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["traffic_bytes_per_launch"])
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -353,7 +363,7 @@ def run_b200(args):
                "gpu_launches": int(res["launches"]), "clocks": res["clocks"], "e2e": e2e,
                "roofline": {"bound": "hbm", "kernel": "spmv_sell2_kernel<0,256> (hecmw_matvec_33 + p.q)",
                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "peak_source": peak_src, "traffic": None,
+                            "peak_source": peak_src, "traffic": ncu_traffic(args.n, world),
                             "algorithmic_bytes_per_launch": spmv_bytes_global / world,
                             "avg_launch_ms": spmv_ms,
                             "cg_iteration": {"algorithmic_bytes": spmv_bytes_global / world + 112.0 * 3 * (args.n + 1) ** 3 / world,

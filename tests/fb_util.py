@@ -88,6 +88,22 @@ def product_problem(hecmw, mesh, cnt, to_host=True, apply_bc=True):
     return A
 
 
+def oracle_iteration_spread(mesh, cnt, axes_list=("x", "z", "xy", "xyz")):
+    """CG iteration counts of the reference algorithm (oracle) on the same system decomposed into 2/4/8
+    subdomains: DIAG-preconditioned CG is partition-invariant mathematically, so the spread of these counts
+    is the reference's own sensitivity to the association order of its dot products."""
+    from oracle import oracle as orc
+    from frontistr_b200 import partition
+    out = []
+    for axes in axes_list:
+        parts = partition.partition(mesh, axes)
+        mats = [oracle_problem(p, cnt) for p in parts]
+        orc.precond_clear()
+        out.append(int(orc.solve(parts, mats)["iter"]))
+    orc.precond_clear()
+    return out
+
+
 def distort(mesh, amp=0.15, seed=0):
     """Move interior nodes of a structured cube so elements are no longer congruent."""
     rng = np.random.default_rng(seed)

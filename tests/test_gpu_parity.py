@@ -131,10 +131,18 @@ def test_solve_golden_decks(gpu, name):
     orc.precond_clear()
     ro = orc.solve(mesh, Ao)
     assert r["error"] == 0 and A.Iarray[80] == 1 and A.Iarray[81] == 0
-    # A361 (70 iterations): +-2.  A342 needs ~720 iterations for 1575 DOF: CG has long lost orthogonality
-    # there and the count depends on the summation order of the dot products at the 1e-16 level (the
-    # reference itself would differ between 1 and 2 MPI ranks); allow 2 % and pin the early history instead.
-    assert abs(r["iter"] - ro["iter"]) <= max(2, int(0.02 * ro["iter"]))
+    # A361 (70 iterations): +-2 of the oracle.  A342 needs ~720 iterations for 1575 DOF: CG has long lost
+    # orthogonality there and the count depends on the summation order of the dot products at the 1e-16
+    # level — the REFERENCE ALGORITHM ITSELF gives 704..733 depending on how many MPI ranks it runs on
+    # (tests/test_oracle_units.py::test_iteration_count_spread_of_the_reference_algorithm).  The GPU count
+    # must lie inside that spread (+-2); the residual history is pinned while the recurrences still agree.
+    counts = [ro["iter"]] + util.oracle_iteration_spread(mesh, cnt)
+    assert min(counts) - 2 <= r["iter"] <= max(counts) + 2, (r["iter"], counts)
+    if name == "A361":
+        assert abs(r["iter"] - ro["iter"]) <= 2
+    orc.precond_clear()
+    roh = orc.solve(mesh, util.oracle_problem(mesh, cnt), hist_len=64)
+    assert np.allclose(r["hist"][:20], roh["hist"][:20], rtol=1e-8)
     assert r["resid2"] < A.Rarray[0]
     U = A.X.reshape(-1, 3)
     for d, key in enumerate(("U1", "U2", "U3")):

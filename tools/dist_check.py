@@ -1,0 +1,72 @@
+"""Multi-GPU parity check (run under torchrun on N GPUs of one box, N in 2/4/8):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
+        tools/dist_check.py [--n 24] [--tet 0] [--precond 3]
+
+Every rank partitions the same global mesh (in-process hecmw_part1/RCB), assembles and solves its subdomain
+through the C-ABI with halo exchange + all-reduce over NCCL; rank 0 gathers the displacements by global node id
+and compares them with the ORACLE's serial solve of the same system (checker only): iteration count within +-2,
+relative L2 error <= 1e-9, final true residual below RESID.  Prints one PASS/FAIL line per case.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=24)
+    ap.add_argument("--tet", type=int, default=0)
+    ap.add_argument("--precond", type=int, default=3)
+    ap.add_argument("--tol", type=float, default=1e-10)
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    import fb_util as util
+    from frontistr_b200 import hecmw, meshgen, partition
+    hecmw.init(lr)
+    hecmw.comm_init_from_torch()
+    gmesh = meshgen.tet10_cube(args.tet) if args.tet else util.distort(meshgen.hex_cube(args.n))
+    axes = {2: "x", 4: "xy", 8: "xyz"}[world]
+    dom = partition.rcb_domains(gmesh, axes)
+    m = partition.local_mesh(gmesh, dom, rank, world)
+    cnt = util.cube_cnt(tol=args.tol, precond=args.precond)
+    A = util.product_problem(hecmw, m, cnt, to_host=False)
+    r = hecmw.hecmw_solve(m, A, device_resident=True)
+    # halo consistency: X on external nodes must equal the owner's value (hecmw_update_m_R at CG exit)
+    xg = torch.zeros(3 * gmesh.n_node, dtype=torch.float64, device="cuda")
+    own = torch.from_numpy(m.global_node_ID[: m.nn_internal].astype(np.int64) - 1).cuda()
+    xl = torch.from_numpy(A.X.reshape(-1, 3)[: m.nn_internal].copy()).cuda()
+    xg.view(-1, 3)[own] = xl
+    dist.all_reduce(xg)
+    xgl = xg.cpu().numpy().reshape(-1, 3)
+    halo_err = float(np.abs(A.X.reshape(-1, 3) - xgl[m.global_node_ID - 1]).max())
+    t = torch.tensor([halo_err], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ok = True
+    if rank == 0:
+        from oracle import oracle as orc
+        Ao = util.oracle_problem(gmesh, cnt)
+        orc.precond_clear()
+        ro = orc.solve(gmesh, Ao)
+        err = util.rel_l2(xgl.reshape(-1), Ao.X)
+        it_ok = abs(r["iter"] - ro["iter"]) <= 2 if args.precond == 3 else True   # SSOR is subdomain-local
+        ok = (r["error"] == 0 and it_ok and err <= 1e-9 and r["resid2"] < args.tol and float(t.item()) == 0.0)
+        print("%s dist_check world=%d mesh=%s precond=%d: iter gpu=%d oracle=%d  rel_l2=%.2e  resid2=%.2e  halo_err=%.1e  neighbors=%d"
+              % ("PASS" if ok else "FAIL", world, ("tet%d" % args.tet) if args.tet else ("hex%d" % args.n), args.precond,
+                 r["iter"], ro["iter"], err, r["resid2"], float(t.item()), m.n_neighbor_pe), flush=True)
+    hecmw.comm_finalize()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
