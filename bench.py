@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=150, help="hex cube edge in elements (150 = configs[1], 200 = configs[2])")
+    ap.add_argument("--n", "--hex", dest="n", type=int, default=150, help="hex cube edge in elements (150 = configs[1], 200 = configs[2])")
     ap.add_argument("--tol", type=float, default=1.0e-8)
     ap.add_argument("--precond", type=int, default=3)
     ap.add_argument("--maxit", type=int, default=20000)
