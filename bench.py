@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--ref-iters", type=int, default=0, help="CG iterations per reference-arm step (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: halo exchange + dot-product all-reduce by peer-memory stores from the CG kernels (default) or NCCL")
     return ap.parse_args()
 
 
@@ -235,6 +237,7 @@ def run_b200(args):
 
     hecmw.init(local_rank)
     if world > 1:
+        hecmw.set_option("p2p", 1 if args.comm == "p2p" else 0)
         hecmw.comm_init_from_torch()
     dev = hecmw.device_info()
 
@@ -356,6 +359,7 @@ def run_b200(args):
                "config": {"workload": workload_name(args.n), "tol": args.tol, "precond": args.precond,
                           "partition": "none" if world == 1 else "RCB-%s (in-process hecmw_part1 restatement), 1 subdomain/GPU"
                           % {2: "x", 4: "xy", 8: "xyz"}[world],
+                          "comm": "none" if world == 1 else ("p2p" if hecmw.get_option("p2p_active") == 1 else "nccl"),
                           "l2": "inputs larger than L2: %.2f GB matrix streamed per SpMV per GPU vs 126 MB L2"
                           % (spmv_bytes_global / world / 1e9)},
                "iterations_per_step": res["iters"] // args.steps, "resid": float(last["resid"]),

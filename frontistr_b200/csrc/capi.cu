@@ -7,6 +7,10 @@
 #include "partition.hpp"
 
 namespace fb {
+__global__ void add_const_kernel(size_t n, int *a, int c) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] += c;
+}
 thread_local std::string g_last_error;
 int64_t g_launch_count = 0;
 Context &ctx() {
@@ -117,7 +121,7 @@ static int build_sell(Context &C) {
 
 // mode 0: y = A x (red_out <- x.y), mode 1: y = b - A x (red_out <- y.y).  x must hold its halo.
 static int launch_spmv(Context &C, int mode, const double *x, const double *b, double *y, double *red_out,
-                       const int *phase) {
+                       const int *phase, const P2PArgs &pa = P2PArgs()) {
   if (!C.sell_valid) FB_TRY(build_sell(C));
   constexpr int BLOCK = 256;
   const int per_sm = (int)C.get("spmv_blocks_per_sm", 8);
@@ -133,8 +137,8 @@ static int launch_spmv(Context &C, int mode, const double *x, const double *b, d
       if (mode == 0) spmv_sell1_kernel<0, BLOCK><<<grid, BLOCK, 0, C.stream>>>(S.N, S.nslice, S.slice_ptr.p, S.val.p, S.col.p, x, b, y, C.partial.p, C.counter.p, red_out, phase);
       else spmv_sell1_kernel<1, BLOCK><<<grid, BLOCK, 0, C.stream>>>(S.N, S.nslice, S.slice_ptr.p, S.val.p, S.col.p, x, b, y, C.partial.p, C.counter.p, red_out, phase);
     } else {
-      if (mode == 0) spmv_sell2_kernel<0, BLOCK><<<grid, BLOCK, 0, C.stream>>>(S.N, S.nslice, S.slice_ptr.p, S.val.p, S.col.p, x, b, y, C.partial.p, C.counter.p, red_out, phase);
-      else spmv_sell2_kernel<1, BLOCK><<<grid, BLOCK, 0, C.stream>>>(S.N, S.nslice, S.slice_ptr.p, S.val.p, S.col.p, x, b, y, C.partial.p, C.counter.p, red_out, phase);
+      if (mode == 0) spmv_sell2_kernel<0, BLOCK><<<grid, BLOCK, 0, C.stream>>>(S.N, S.nslice, S.slice_ptr.p, S.val.p, S.col.p, x, b, y, C.partial.p, C.counter.p, red_out, phase, C.p2p.view, C.p2p.nbrs, pa);
+      else spmv_sell2_kernel<1, BLOCK><<<grid, BLOCK, 0, C.stream>>>(S.N, S.nslice, S.slice_ptr.p, S.val.p, S.col.p, x, b, y, C.partial.p, C.counter.p, red_out, phase, C.p2p.view, C.p2p.nbrs, pa);
     }
   }
   FB_LAUNCH_CHECK();
@@ -270,6 +274,119 @@ static int precond_apply_generic(Context &C, int iterPREmax, const int *phase) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// peer-memory arena (p2p.cuh): allocate, exchange IPC handles over the NCCL communicator, map the peers
+// ------------------------------------------------------------------------------------------
+static void p2p_teardown(Context &C) {
+  Context::P2P &T = C.p2p;
+  if (!T.arena) return;
+  cudaStreamSynchronize(C.stream);
+  for (int r = 0; r < kP2PMaxRanks; r++) {
+    if (T.peer_base[r] && r != C.rank) cudaIpcCloseMemHandle(T.peer_base[r]);
+    T.peer_base[r] = nullptr;
+  }
+  if (C.comm) {   // nobody may free its arena while a peer could still store into it
+    if (C.red.p && C.nccl.AllReduce(C.red.p + RED_TMP, C.red.p + RED_TMP, 1, ncclFloat64_, ncclSum_, C.comm, C.stream) == 0)
+      cudaStreamSynchronize(C.stream);
+  }
+  if (!C.P.owned) C.P.release();
+  cudaFree(T.arena);
+  T.arena = nullptr; T.active = false; T.bytes = 0;
+  T.view = P2PView();
+}
+
+static int p2p_setup(Context &C) {
+  Context::P2P &T = C.p2p;
+  p2p_teardown(C);
+  T.active = false;
+  if (C.petot <= 1 || C.petot > kP2PMaxRanks || C.get("p2p", 1) == 0 || !C.comm) return 0;
+  const Halo &H = C.halo;
+  constexpr size_t OFF_FLAGS = sizeof(P2PEntry) * P2P_NQ * 2 * kP2PMaxRanks, OFF_P = 4096;
+  static_assert(OFF_FLAGS + 8 * kP2PMaxRanks <= OFF_P, "arena header");
+  const size_t np3 = 3 * (size_t)std::max(C.NP, 1) + 8;
+  size_t bytes = OFF_P + np3 * sizeof(double);
+  bytes = (bytes + (2u << 20) - 1) / (2u << 20) * (2u << 20);   // own 2 MiB-granular allocation => own IPC handle
+  FB_CUDA(cudaMalloc(&T.arena, bytes));
+  T.bytes = bytes;
+  FB_CUDA(cudaMemsetAsync(T.arena, 0, bytes, C.stream));
+  struct Card { cudaIpcMemHandle_t h; long long np; long long ok; };
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  Card mine;
+  memset(&mine, 0, sizeof mine);
+  mine.ok = (cudaIpcGetMemHandle(&mine.h, T.arena) == cudaSuccess);
+  mine.np = C.NP;
+  DevBuf<char> d_send, d_recv;
+  if (d_send.alloc(sizeof(Card)) || d_recv.alloc(sizeof(Card) * C.petot)) return FISTR_B200_ERR_CUDA;
+  FB_CUDA(cudaMemcpyAsync(d_send.p, &mine, sizeof mine, cudaMemcpyHostToDevice, C.stream));
+  FB_NCCL(C.nccl.AllGather(d_send.p, d_recv.p, sizeof(Card), ncclChar_, C.comm, C.stream));
+  std::vector<Card> cards(C.petot);
+  FB_CUDA(cudaMemcpyAsync(cards.data(), d_recv.p, sizeof(Card) * C.petot, cudaMemcpyDeviceToHost, C.stream));
+  FB_CUDA(cudaStreamSynchronize(C.stream));
+  bool ok = true;
+  for (int r = 0; r < C.petot; r++) ok = ok && cards[r].ok;
+  for (int r = 0; r < C.petot && ok; r++) {
+    if (r == C.rank) { T.peer_base[r] = T.arena; continue; }
+    void *base = nullptr;
+    if (cudaIpcOpenMemHandle(&base, cards[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+    T.peer_base[r] = base;
+  }
+  // every rank must take the same decision
+  double flag = ok ? 0.0 : 1.0;
+  FB_CUDA(cudaMemcpyAsync(C.red.p + RED_TMP, &flag, sizeof flag, cudaMemcpyHostToDevice, C.stream));
+  FB_NCCL(C.nccl.AllReduce(C.red.p + RED_TMP, C.red.p + RED_TMP, 1, ncclFloat64_, ncclSum_, C.comm, C.stream));
+  FB_CUDA(cudaMemcpyAsync(&flag, C.red.p + RED_TMP, sizeof flag, cudaMemcpyDeviceToHost, C.stream));
+  FB_CUDA(cudaStreamSynchronize(C.stream));
+  d_send.release(); d_recv.release();
+  if (flag != 0.0) {   // no peer access on this box: stay on the NCCL path
+    for (int r = 0; r < kP2PMaxRanks; r++) {
+      if (T.peer_base[r] && r != C.rank) cudaIpcCloseMemHandle(T.peer_base[r]);
+      T.peer_base[r] = nullptr;
+    }
+    cudaFree(T.arena); T.arena = nullptr; T.bytes = 0;
+    if (C.get("p2p", 1) >= 2) return fail(FISTR_B200_ERR_COMM, "p2p: peer memory could not be mapped");
+    return 0;
+  }
+  T.view = P2PView();
+  T.view.nranks = C.petot; T.view.me = C.rank;
+  for (int r = 0; r < C.petot; r++) {
+    char *b = (char *)T.peer_base[r];
+    T.view.ar[r] = (P2PEntry *)b;
+    T.view.hflag[r] = (unsigned long long *)(b + OFF_FLAGS);
+    T.view.vecP[r] = (double *)(b + OFF_P);
+  }
+  if (T.err.alloc(4)) return FISTR_B200_ERR_CUDA;
+  FB_CUDA(cudaMemsetAsync(T.err.p, 0, sizeof(int) * 4, C.stream));
+  T.view.err = T.err.p;
+  T.nbrs = P2PNeighbors();
+  if (H.n_neighbor > kP2PMaxRanks) return fail(FISTR_B200_ERR_COMM, "p2p: too many neighbours");
+  T.nbrs.n = H.n_neighbor;
+  for (int a = 0; a < H.n_neighbor; a++) T.nbrs.rank[a] = H.neighbor_pe[a];
+  // destination of every export entry: the neighbour's own local id of that node = its import_item list for us
+  const size_t nexp = (size_t)H.n_export();
+  if (T.exp_peer.alloc(nexp) || T.exp_remote.alloc(nexp)) return FISTR_B200_ERR_CUDA;
+  std::vector<int> peer(nexp);
+  for (int a = 0; a < H.n_neighbor; a++)
+    for (int e = H.export_index[a]; e < H.export_index[a + 1]; e++) peer[e] = H.neighbor_pe[a];
+  if (nexp) FB_CUDA(cudaMemcpyAsync(T.exp_peer.p, peer.data(), sizeof(int) * nexp, cudaMemcpyHostToDevice, C.stream));
+  FB_NCCL(C.nccl.GroupStart());
+  for (int a = 0; a < H.n_neighbor; a++) {
+    const size_t ns = (size_t)(H.import_index[a + 1] - H.import_index[a]);
+    const size_t nr = (size_t)(H.export_index[a + 1] - H.export_index[a]);
+    if (ns) FB_NCCL(C.nccl.Send(H.d_import_item.p + H.import_index[a], ns, ncclInt32_, H.neighbor_pe[a], C.comm, C.stream));
+    if (nr) FB_NCCL(C.nccl.Recv(T.exp_remote.p + H.export_index[a], nr, ncclInt32_, H.neighbor_pe[a], C.comm, C.stream));
+  }
+  FB_NCCL(C.nccl.GroupEnd());
+  if (nexp) {
+    add_const_kernel<<<(int)((nexp + 255) / 256), 256, 0, C.stream>>>(nexp, T.exp_remote.p, -1);   // 1-based -> 0-based
+    FB_LAUNCH_CHECK();
+  }
+  FB_CUDA(cudaStreamSynchronize(C.stream));
+  C.P.view(T.view.vecP[C.rank], np3);
+  T.seq[0] = T.seq[1] = 0; T.halo_seq = 0;
+  T.active = true;
+  return 0;
+}
+
 static int ensure_work(Context &C) {
   const size_t np3 = 3 * (size_t)std::max(C.NP, 1) + 8;
   if (C.B.alloc(np3) || C.X.alloc(np3) || C.R.alloc(np3) || C.Z.alloc(np3) || C.P.alloc(np3) ||
@@ -312,6 +429,7 @@ int fistr_b200_finalize(void) {
   Context &C = ctx();
   if (!C.inited) return 0;
   cudaStreamSynchronize(C.stream);
+  p2p_teardown(C);
   if (C.comm) { C.nccl.CommDestroy(C.comm); C.comm = nullptr; }
   cudaStreamDestroy(C.stream);
   C = Context();
@@ -328,7 +446,10 @@ int fistr_b200_set_option(const char *key, int64_t value) {
   if (!strcmp(key, "launch_count_reset")) g_launch_count = 0;
   return 0;
 }
-int64_t fistr_b200_get_option(const char *key) { return ctx().get(key, -1); }
+int64_t fistr_b200_get_option(const char *key) {
+  if (!strcmp(key, "p2p_active")) return ctx().p2p.active ? 1 : 0;
+  return ctx().get(key, -1);
+}
 
 int64_t fistr_b200_launch_count(void) { return g_launch_count; }
 
@@ -368,6 +489,7 @@ int fistr_b200_comm_init(const void *id128, int my_rank, int petot) {
 
 int fistr_b200_comm_finalize(void) {
   Context &C = ctx();
+  p2p_teardown(C);
   if (C.comm) { cudaStreamSynchronize(C.stream); C.nccl.CommDestroy(C.comm); C.comm = nullptr; }
   C.petot = 1; C.rank = 0;
   return 0;
@@ -416,6 +538,7 @@ int fistr_b200_mat_structure(int N, int NP, int NPL, int NPU, const int *indexL,
   if (NPU) FB_CUDA(cudaMemcpy(C.itemU.p, itemU, sizeof(int) * (size_t)NPU, cudaMemcpyHostToDevice));
   const size_t nblk = (size_t)NP + NPL + NPU;
   if (C.vals.alloc(9 * nblk)) return FISTR_B200_ERR_CUDA;
+  p2p_teardown(C);   // P may alias the old peer arena
   FB_TRY(ensure_work(C));
   FB_CUDA(cudaMemsetAsync(C.X.p, 0, sizeof(double) * 3 * (size_t)NP, C.stream));
   FB_CUDA(cudaMemsetAsync(C.B.p, 0, sizeof(double) * 3 * (size_t)NP, C.stream));
@@ -438,6 +561,7 @@ int fistr_b200_mat_structure(int N, int NP, int NPL, int NPU, const int *indexL,
       H.recv.alloc(3 * H.import_item.size())) return FISTR_B200_ERR_CUDA;
   if (!H.export_item.empty()) FB_CUDA(cudaMemcpy(H.d_export_item.p, H.export_item.data(), sizeof(int) * H.export_item.size(), cudaMemcpyHostToDevice));
   if (!H.import_item.empty()) FB_CUDA(cudaMemcpy(H.d_import_item.p, H.import_item.data(), sizeof(int) * H.import_item.size(), cudaMemcpyHostToDevice));
+  FB_TRY(p2p_setup(C));
   C.key_indexL = indexL; C.key_itemL = itemL;
   C.have_structure = true;
   C.values_on_device = false;
@@ -848,7 +972,9 @@ int fistr_b200_solve_33(int N, int NP, int NPL, int NPU, const double *D, const 
   }
   if (!C.sell_valid) FB_TRY(build_sell(C));
   const bool fused = (PRECOND == 3 && iterPREmax == 1 && C.get("cg_fused", 1) != 0);
-  const int check_interval = (int)std::max<int64_t>(1, C.get("cg_check_interval", 8));
+  // peer-memory mode has no host-visible communication inside the loop: look at the control block less often
+  const bool p2p_mode = C.p2p.active && fused && C.petot > 1;
+  const int check_interval = (int)std::max<int64_t>(1, C.get("cg_check_interval", p2p_mode ? 16 : 8));
 
   // --- control block, history
   const int hist_len = std::max(MAXIT, 1);
@@ -899,21 +1025,32 @@ int fistr_b200_solve_33(int N, int NP, int NPL, int NPU, const double *D, const 
   if (MAXIT >= 1) FB_TRY(z_and_rho(1));
   int k = 1;
   bool done = (MAXIT < 1);
+  // peer-memory mode (p2p.cuh): inside the fused DIAG iteration the halo exchange and the two all-reduces are
+  // issued by the compute kernels themselves; the 1-in-50 true-residual iterations stay on NCCL.
+  Context::P2P &T = C.p2p;
+  const bool p2p = T.active && fused && C.sell.variant == 2 && C.petot > 1;
+  unsigned long long pending_rrrz = 0;   // sequence number of the (r.r, r.z) publication the next prologue must consume
   while (!done) {
     // ---- launch iterations k .. kend speculatively
     const int kend = std::min(MAXIT, (k + check_interval - 1) / check_interval * check_interval);
     for (; k <= kend; k++) {
       const int parn = (k + 1) & 1;
+      const bool recompute = (k % 50 == 0);   // N_ITER_RECOMPUTE_R, CG.f90:232-233
+      P2PArgs ap, as, af;
+      ap.consume_seq = pending_rrrz; pending_rrrz = 0;
+      if (p2p) { ap.halo_seq = ++T.halo_seq; as.halo_seq = ap.halo_seq; }
+      if (p2p && !recompute) { as.publish_seq = ++T.seq[P2P_Q_PQ]; af.consume_seq = as.publish_seq; af.publish_seq = ++T.seq[P2P_Q_RRRZ]; }
       cg_update_p_kernel<256><<<gvec, BLOCK, 0, C.stream>>>(k, n3, C.Z.p, C.P.p, red, C.ctl.p, C.hist.p, hist_len,
-                                                            C.halo.n_export(), C.halo.d_export_item.p, C.halo.send_p.p);
+                                                            C.halo.n_export(), C.halo.d_export_item.p, C.halo.send_p.p,
+                                                            T.view, T.nbrs, ap, T.exp_peer.p, T.exp_remote.p, C.counter.p + 1);
       FB_LAUNCH_CHECK();
-      FB_TRY(exchange(C, C.P.p, true));
+      if (!p2p) FB_TRY(exchange(C, C.P.p, true));
       const bool sample = time_ax && (k % check_interval == 1 || check_interval == 1);
       if (sample) FB_CUDA(cudaEventRecord(evA0, C.stream));
-      FB_TRY(launch_spmv(C, 0, C.P.p, nullptr, C.Q.p, red + RED_PQ, phase));
+      FB_TRY(launch_spmv(C, 0, C.P.p, nullptr, C.Q.p, red + RED_PQ, phase, as));
       if (sample) FB_CUDA(cudaEventRecord(evA1, C.stream));
-      FB_TRY(allreduce(C, red + RED_PQ, 1));
-      if (k % 50 == 0) {   // N_ITER_RECOMPUTE_R, CG.f90:232-233
+      if (!as.publish_seq) FB_TRY(allreduce(C, red + RED_PQ, 1));
+      if (recompute) {
         cg_update_xr_kernel<256><<<gvec, BLOCK, 0, C.stream>>>(k, n3, C.P.p, C.Q.p, C.X.p, nullptr, red, C.ctl.p, C.partial.p, C.counter.p);
         FB_LAUNCH_CHECK();
         FB_TRY(exchange(C, C.X.p, false));
@@ -921,9 +1058,10 @@ int fistr_b200_solve_33(int N, int NP, int NPL, int NPU, const double *D, const 
         FB_TRY(allreduce(C, red + 2 * parn, 1));
         FB_TRY(z_and_rho(parn));
       } else if (fused) {
-        cg_fused_update_kernel<256><<<gnode, BLOCK, 0, C.stream>>>(k, N, C.P.p, C.Q.p, C.X.p, C.R.p, C.Z.p, C.alu.p, C.alu_ld, red, C.ctl.p, C.partial.p, C.counter.p);
+        cg_fused_update_kernel<256><<<gnode, BLOCK, 0, C.stream>>>(k, N, C.P.p, C.Q.p, C.X.p, C.R.p, C.Z.p, C.alu.p, C.alu_ld, red, C.ctl.p, C.partial.p, C.counter.p, T.view, af);
         FB_LAUNCH_CHECK();
-        FB_TRY(allreduce(C, red + 2 * parn, 2));
+        if (af.publish_seq) pending_rrrz = af.publish_seq;
+        else FB_TRY(allreduce(C, red + 2 * parn, 2));
       } else {
         cg_update_xr_kernel<256><<<gvec, BLOCK, 0, C.stream>>>(k, n3, C.P.p, C.Q.p, C.X.p, C.R.p, red, C.ctl.p, C.partial.p, C.counter.p);
         FB_LAUNCH_CHECK();
@@ -932,13 +1070,22 @@ int fistr_b200_solve_33(int N, int NP, int NPL, int NPU, const double *D, const 
       }
     }
     // ---- evaluate the last launched iteration's RESID, then look at the control block
-    cg_check_kernel<<<1, 1, 0, C.stream>>>(k, red, C.ctl.p, C.hist.p, hist_len);
-    FB_LAUNCH_CHECK();
+    {
+      P2PArgs ac;
+      ac.consume_seq = pending_rrrz; pending_rrrz = 0;   // the check kernel leaves the sums in red[] for the next batch
+      cg_check_kernel<<<1, 1, 0, C.stream>>>(k, red, C.ctl.p, C.hist.p, hist_len, T.view, ac);
+      FB_LAUNCH_CHECK();
+    }
     FB_CUDA(cudaMemcpyAsync(&h_ctl, C.ctl.p, sizeof h_ctl, cudaMemcpyDeviceToHost, C.stream));
     FB_CUDA(cudaStreamSynchronize(C.stream));
     if (time_ax) {
       float ms = 0.f;
       if (cudaEventElapsedTime(&ms, evA0, evA1) == cudaSuccess) { time_Ax += ms * 1e-3; ax_samples++; }
+    }
+    if (p2p) {
+      int perr = 0;
+      FB_CUDA(cudaMemcpy(&perr, T.err.p, sizeof perr, cudaMemcpyDeviceToHost));
+      if (perr) return fail(FISTR_B200_ERR_COMM, "solve_33: peer-memory wait timed out (code %d) at iteration <= %d", perr, k);
     }
     if (h_ctl.phase == 0) {
       if (k > MAXIT) { error = HECMW_SOLVER_ERROR_NOCONV_MAXIT_; ITER = MAXIT + 1; done = true; }

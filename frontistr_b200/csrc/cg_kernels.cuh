@@ -13,6 +13,7 @@
 //   red[4]       = p.q (C1, CG.f90:211)   red[5] = b.b (BNRM2, :123)   red[6] = scratch r.r
 #pragma once
 #include "common.cuh"
+#include "p2p.cuh"
 
 namespace fb {
 
@@ -25,6 +26,14 @@ struct CgCtl {          // device-resident control block
 };
 
 enum { RED_PQ = 4, RED_BNRM2 = 5, RED_TMP = 6, RED_COUNT = 8 };
+
+// Per-launch communication plan of the peer-memory mode (p2p.cuh).  All zero = the scalars are in red[]
+// (single rank, or NCCL all-reduce between the kernels) and no halo traffic is issued by the kernel.
+struct P2PArgs {
+  unsigned long long consume_seq = 0;   // > 0: take the reduced scalars from the peer table, not from red[]
+  unsigned long long publish_seq = 0;   // > 0: publish this kernel's partial sums to all ranks, not to red[]
+  unsigned long long halo_seq = 0;      // > 0: update_p pushes the export values + signals; SpMV waits
+};
 
 // ALU is stored SoA: alu[c*ld + node], c = 0..8 (reference ALU(9*i-8+c)), coalesced per lane.
 __device__ __forceinline__ void diag_solve(const double *__restrict__ alu, size_t ld, size_t i,
@@ -112,12 +121,10 @@ dot_kernel(size_t n, const double *__restrict__ a, const double *__restrict__ b,
 // Prologue of iteration k (k>=1): convergence test of iteration k-1, RHO tests of iteration k.
 // Returns false when the iteration must not run.  `leader` (one thread of block 0) records events.
 __device__ __forceinline__ bool cg_iter_prologue(int k, const double *red, CgCtl *ctl, double *hist,
-                                                 int hist_len, bool leader, double &beta) {
-  if (ctl->phase != 0) return false;
+                                                 int hist_len, bool leader, double rr, double rz, double &beta) {
   const int par = k & 1;
-  const double rz = red[2 * par + 1];
   if (k > 1) {
-    const double resid = sqrt(red[2 * par] / red[RED_BNRM2]);  // RESID of iteration k-1, CG.f90:242
+    const double resid = sqrt(rr / red[RED_BNRM2]);            // RESID of iteration k-1, CG.f90:242
     if (leader && hist && k - 2 < hist_len) hist[k - 2] = resid;
     if (resid <= ctl->tol) {                                   // CG.f90:259
       if (leader) { ctl->event_iter = k - 1; ctl->event_resid = resid; __threadfence(); ctl->phase = 1; }
@@ -142,38 +149,74 @@ __device__ __forceinline__ bool cg_iter_prologue(int k, const double *red, CgCtl
   return true;
 }
 
-// p = z + beta p  (p = z on the first iteration) + gather of the export halo values of p
+// (r.r, r.z) that iteration k starts from: red[] or, in peer-memory mode, the sum over all ranks' partials.
+// Block-uniform result; block 0 also stores the sums in red[] for the kernels that follow in the stream.
+__device__ __forceinline__ void cg_fetch_rr_rz(int k, double *red, const P2PView &pv, const P2PArgs &a,
+                                               double &rr, double &rz) {
+  const int par = k & 1;
+  if (a.consume_seq == 0) { rr = red[2 * par]; rz = red[2 * par + 1]; return; }
+  __shared__ double s_rrrz[2];
+  if (threadIdx.x == 0) {
+    double s0, s1;
+    p2p_consume(pv, P2P_Q_RRRZ, a.consume_seq, s0, s1);
+    s_rrrz[0] = s0; s_rrrz[1] = s1;
+    if (blockIdx.x == 0) { red[2 * par] = s0; red[2 * par + 1] = s1; }
+  }
+  __syncthreads();
+  rr = s_rrrz[0]; rz = s_rrrz[1];
+}
+
+// p = z + beta p  (p = z on the first iteration) + gather of the export halo values of p.
+// Peer-memory mode (a.halo_seq > 0): the export values are also stored straight into the halo part of the
+// neighbours' p vectors and the last block signals exchange number a.halo_seq to every neighbour.
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 cg_update_p_kernel(int k, size_t n3, const double *__restrict__ z, double *__restrict__ p,
-                   const double *red, CgCtl *ctl, double *hist, int hist_len,
-                   int n_export, const int *__restrict__ export_item, double *__restrict__ sendbuf) {
-  double beta;
-  if (!cg_iter_prologue(k, red, ctl, hist, hist_len, blockIdx.x == 0 && threadIdx.x == 0, beta)) return;
+                   double *red, CgCtl *ctl, double *hist, int hist_len,
+                   int n_export, const int *__restrict__ export_item, double *__restrict__ sendbuf,
+                   P2PView pv, P2PNeighbors nb, P2PArgs a, const int *__restrict__ exp_peer,
+                   const int *__restrict__ exp_remote, unsigned int *ticket) {
+  if (ctl->phase != 0) return;
+  double beta, rr, rz;
+  cg_fetch_rr_rz(k, red, pv, a, rr, rz);
+  if (!cg_iter_prologue(k, red, ctl, hist, hist_len, blockIdx.x == 0 && threadIdx.x == 0, rr, rz, beta)) return;
   const size_t stride = (size_t)gridDim.x * BLOCK;
+  // export pack first (hecmw_solver_SR_33.F90:72-81) so the peer stores are in flight while p is updated;
+  // recomputed from z and the previous export value, so no grid-wide ordering with the update below is needed.
+  for (size_t e = (size_t)blockIdx.x * BLOCK + threadIdx.x; e < 3 * (size_t)n_export; e += stride) {
+    const size_t en = e / 3, c = e % 3;
+    const size_t i = 3 * (size_t)(export_item[en] - 1) + c;
+    const double v = (k == 1) ? z[i] : fma(beta, sendbuf[e], z[i]);
+    sendbuf[e] = v;
+    if (a.halo_seq) st_relaxed_sys(pv.vecP[exp_peer[en]] + 3 * (size_t)exp_remote[en] + c, v);
+  }
   if (k == 1) {
     for (size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x; i < n3; i += stride) p[i] = z[i];
   } else {
     for (size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x; i < n3; i += stride) p[i] = fma(beta, p[i], z[i]);
   }
-  // export pack (hecmw_solver_SR_33.F90:72-81): recomputed from z,p_old so no grid-wide ordering
-  // is needed between the update above and the gather.
-  for (size_t e = (size_t)blockIdx.x * BLOCK + threadIdx.x; e < 3 * (size_t)n_export; e += stride) {
-    const size_t node = (size_t)(export_item[e / 3] - 1), i = 3 * node + e % 3;
-    // the owning thread may or may not have stored p[i] yet: derive the value independently
-    sendbuf[e] = (k == 1) ? z[i] : fma(beta, sendbuf[e], z[i]);
+  if (a.halo_seq) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int t = atomicAdd(ticket, 1u);
+      if (t == gridDim.x - 1) {
+        *ticket = 0u;
+        p2p_signal_halo(pv, nb, a.halo_seq);
+      }
+    }
   }
 }
 
-// standalone check used after the last iteration of the loop (k = MAXIT+1)
-__global__ void cg_check_kernel(int k, const double *red, CgCtl *ctl, double *hist, int hist_len) {
-  double beta;
-  cg_iter_prologue(k, red, ctl, hist, hist_len, true, beta);
+// standalone check used after the last iteration of a launch batch
+__global__ void cg_check_kernel(int k, double *red, CgCtl *ctl, double *hist, int hist_len, P2PView pv, P2PArgs a) {
+  if (ctl->phase != 0) return;
+  double beta, rr, rz;
+  cg_fetch_rr_rz(k, red, pv, a, rr, rz);
+  cg_iter_prologue(k, red, ctl, hist, hist_len, true, rr, rz, beta);
 }
 
-__device__ __forceinline__ bool cg_alpha_prologue(int k, const double *red, CgCtl *ctl, bool leader, double &alpha) {
-  if (ctl->phase != 0) return false;
-  const double c1 = red[RED_PQ];
+__device__ __forceinline__ bool cg_alpha_prologue(int k, const double *red, CgCtl *ctl, bool leader, double c1, double &alpha) {
   if (c1 <= 0) {                                               // CG.f90:213-217
     if (leader) { ctl->event_iter = k; __threadfence(); ctl->phase = 3002; }
     return false;
@@ -189,9 +232,16 @@ __global__ void __launch_bounds__(BLOCK)
 cg_fused_update_kernel(int k, int N, const double *__restrict__ p, const double *__restrict__ q,
                        double *__restrict__ x, double *__restrict__ r, double *__restrict__ z,
                        const double *__restrict__ alu, size_t ld, double *red, CgCtl *ctl,
-                       double *partial, unsigned int *counter) {
-  double alpha;
-  if (!cg_alpha_prologue(k, red, ctl, blockIdx.x == 0 && threadIdx.x == 0, alpha)) return;
+                       double *partial, unsigned int *counter, P2PView pv, P2PArgs a) {
+  if (ctl->phase != 0) return;
+  double alpha, c1;
+  if (a.consume_seq) {        // p.q = sum over all ranks' partials (peer table), block-uniform
+    __shared__ double s_pq;
+    if (threadIdx.x == 0) { double s0, s1; p2p_consume(pv, P2P_Q_PQ, a.consume_seq, s0, s1); s_pq = s0; }
+    __syncthreads();
+    c1 = s_pq;
+  } else c1 = red[RED_PQ];
+  if (!cg_alpha_prologue(k, red, ctl, blockIdx.x == 0 && threadIdx.x == 0, c1, alpha)) return;
   double acc[2] = {0.0, 0.0};
   for (size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x; i < (size_t)N; i += (size_t)gridDim.x * BLOCK) {
     const size_t j = 3 * i;
@@ -205,7 +255,10 @@ cg_fused_update_kernel(int k, int N, const double *__restrict__ p, const double 
     acc[1] = fma(r0, a, acc[1]); acc[1] = fma(r1, b, acc[1]); acc[1] = fma(r2, c, acc[1]);
   }
   double *out = red + 2 * ((k + 1) & 1);
-  grid_reduce<2, BLOCK>(acc, partial, counter, [=](double(&o)[2]) { out[0] = o[0]; out[1] = o[1]; });
+  grid_reduce<2, BLOCK>(acc, partial, counter, [=](double(&o)[2]) {
+    if (a.publish_seq) p2p_publish(pv, P2P_Q_RRRZ, a.publish_seq, o[0], o[1]);
+    else { out[0] = o[0]; out[1] = o[1]; }
+  });
 }
 
 // x += alpha p only (iterations where r is recomputed from b - A x, CG.f90:227-233), or
@@ -215,8 +268,9 @@ __global__ void __launch_bounds__(BLOCK)
 cg_update_xr_kernel(int k, size_t n3, const double *__restrict__ p, const double *__restrict__ q,
                     double *__restrict__ x, double *__restrict__ r, double *red, CgCtl *ctl,
                     double *partial, unsigned int *counter) {
+  if (ctl->phase != 0) return;
   double alpha;
-  if (!cg_alpha_prologue(k, red, ctl, blockIdx.x == 0 && threadIdx.x == 0, alpha)) return;
+  if (!cg_alpha_prologue(k, red, ctl, blockIdx.x == 0 && threadIdx.x == 0, red[RED_PQ], alpha)) return;
   double acc[1] = {0.0};
   for (size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x; i < n3; i += (size_t)gridDim.x * BLOCK) {
     x[i] = fma(alpha, p[i], x[i]);

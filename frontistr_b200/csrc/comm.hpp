@@ -11,7 +11,7 @@ namespace fb {
 
 typedef struct ncclComm *ncclComm_t_;
 struct ncclUniqueId_ { char internal[128]; };
-enum { ncclSum_ = 0, ncclFloat64_ = 8 };
+enum { ncclSum_ = 0, ncclChar_ = 0, ncclInt32_ = 2, ncclFloat64_ = 8 };
 
 struct Nccl {
   void *h = nullptr;
@@ -19,6 +19,7 @@ struct Nccl {
   int (*CommInitRank)(ncclComm_t_ *, int, ncclUniqueId_, int) = nullptr;
   int (*CommDestroy)(ncclComm_t_) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t_, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, ncclComm_t_, cudaStream_t) = nullptr;
   int (*Send)(const void *, size_t, int, int, ncclComm_t_, cudaStream_t) = nullptr;
   int (*Recv)(void *, size_t, int, int, ncclComm_t_, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
@@ -40,6 +41,7 @@ struct Nccl {
     FB_SYM(CommInitRank, "ncclCommInitRank");
     FB_SYM(CommDestroy, "ncclCommDestroy");
     FB_SYM(AllReduce, "ncclAllReduce");
+    FB_SYM(AllGather, "ncclAllGather");
     FB_SYM(Send, "ncclSend");
     FB_SYM(Recv, "ncclRecv");
     FB_SYM(GroupStart, "ncclGroupStart");

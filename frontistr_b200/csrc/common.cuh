@@ -133,6 +133,11 @@ template <class T>
 struct DevBuf {
   T *p = nullptr;
   size_t n = 0;
+  bool owned = true;
+  void view(T *ptr, size_t count) {   // non-owning alias (memory lives in the peer-mapped arena)
+    release();
+    p = ptr; n = count; owned = false;
+  }
   int alloc(size_t count) {
     if (count <= n && p) return 0;
     release();
@@ -148,9 +153,10 @@ struct DevBuf {
     return 0;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p && owned) cudaFree(p);
     p = nullptr;
     n = 0;
+    owned = true;
   }
 };
 

@@ -11,6 +11,7 @@
 #include "comm.hpp"
 #include "common.cuh"
 #include "matcon.hpp"
+#include "p2p.cuh"
 #include "spmv.cuh"
 #include "ssor.cuh"
 
@@ -78,6 +79,19 @@ struct Context {
 
   // ---- hecmw_mat_con result held between _count and _fill
   MatCon con;
+
+  // ---- peer-memory communication of the fused CG loop (p2p.cuh)
+  struct P2P {
+    bool active = false;
+    void *arena = nullptr;
+    size_t bytes = 0;
+    void *peer_base[kP2PMaxRanks] = {nullptr};
+    P2PView view;
+    P2PNeighbors nbrs;
+    DevBuf<int> exp_peer, exp_remote;     // per export entry: destination rank, 0-based node index there
+    unsigned long long seq[P2P_NQ] = {0, 0}, halo_seq = 0;
+    DevBuf<int> err;
+  } p2p;
 
   // ---- communication
   Nccl nccl;

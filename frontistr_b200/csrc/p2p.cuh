@@ -1,0 +1,111 @@
+// NVLink peer-memory communication for the CG hot loop: replaces, inside the fused DIAG-CG iteration, the
+// MPI traffic of hecmw_update_3_R (communication/hecmw_comm_f.F90:669-694, hecmw_solver_SR_33.F90:42-124)
+// and hecmw_allreduce_R1 (hecmw_comm_f.F90:346-393) by stores into the neighbours' memory issued from the
+// compute kernels themselves:
+//
+//   * halo:  the kernel that forms p = z + beta p writes the export values straight into the halo part of
+//            each neighbour's p vector (peer stores over NVLink); when the whole grid has done so the last
+//            block publishes a sequence number in every neighbour's flag word.  The neighbour's SpMV waits
+//            for the flags of all its neighbours before it reads x.
+//   * dots:  the last block of the deterministic grid reduction writes its rank's partial sum (with a
+//            sequence tag) into a slot of EVERY rank's table; the prologue of the next kernel waits for all
+//            tags and sums the partials in rank order, so every rank obtains the bit-identical value — no
+//            separate all-reduce kernel, no host involvement.
+//
+// Every rank owns one "arena" (plain cudaMalloc memory exported with cudaIpcGetMemHandle); layout:
+//   [ P2PEntry table [P2P_NQ][2][8] | halo flags u64[8] | p vector (3*NP+8 doubles) ]
+// One process drives one GPU, so a kernel spinning on a word written by another GPU cannot starve its
+// producer.  Every spin has a time-out that raises an error flag instead of hanging the device.
+#pragma once
+#include "common.cuh"
+
+namespace fb {
+
+constexpr int kP2PMaxRanks = 8;
+enum { P2P_Q_PQ = 0, P2P_Q_RRRZ = 1, P2P_NQ = 2 };
+
+struct P2PEntry {
+  double v[2];
+  unsigned long long tag;
+  unsigned long long pad;
+};
+
+struct P2PView {
+  int nranks = 0, me = 0;
+  P2PEntry *ar[kP2PMaxRanks];              // ar[r]: entry table of rank r (peer-mapped for r != me)
+  unsigned long long *hflag[kP2PMaxRanks]; // hflag[r]: halo flags of rank r, indexed by source rank
+  double *vecP[kP2PMaxRanks];              // p vector of rank r
+  int *err;                                // local error word (spin time-out)
+};
+
+struct P2PNeighbors {
+  int n = 0;
+  int rank[kP2PMaxRanks];
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys(double *p, double v) {
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double *p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long p2p_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr unsigned long long kP2PTimeoutNs = 4000000000ull;   // 4 s
+
+// ONE thread: hand this rank's partial sums to every rank (itself included)
+__device__ __forceinline__ void p2p_publish(const P2PView &pv, int q, unsigned long long seq, double v0, double v1) {
+  const int slot = (q * 2 + (int)(seq & 1ull)) * kP2PMaxRanks + pv.me;
+  for (int r = 0; r < pv.nranks; r++) {
+    st_relaxed_sys(&pv.ar[r][slot].v[0], v0);
+    st_relaxed_sys(&pv.ar[r][slot].v[1], v1);
+  }
+  __threadfence_system();
+  for (int r = 0; r < pv.nranks; r++) st_release_sys(&pv.ar[r][slot].tag, seq);
+}
+
+// ONE thread per block: wait for all ranks' partials of (q, seq) and sum them in rank order
+__device__ __forceinline__ void p2p_consume(const P2PView &pv, int q, unsigned long long seq, double &s0, double &s1) {
+  const P2PEntry *base = pv.ar[pv.me] + (q * 2 + (int)(seq & 1ull)) * kP2PMaxRanks;
+  s0 = 0.0; s1 = 0.0;
+  const unsigned long long t0 = p2p_now_ns();
+  for (int r = 0; r < pv.nranks; r++) {
+    while (ld_acquire_sys(&base[r].tag) != seq) {
+      if (p2p_now_ns() - t0 > kP2PTimeoutNs) { atomicExch(pv.err, 1); break; }
+    }
+    s0 += ld_relaxed_sys(&base[r].v[0]);
+    s1 += ld_relaxed_sys(&base[r].v[1]);
+  }
+}
+
+// ONE thread per block: wait until every neighbour has delivered halo exchange number `seq`
+__device__ __forceinline__ void p2p_wait_halo(const P2PView &pv, const P2PNeighbors &nb, unsigned long long seq) {
+  const unsigned long long *f = pv.hflag[pv.me];
+  const unsigned long long t0 = p2p_now_ns();
+  for (int a = 0; a < nb.n; a++) {
+    while (ld_acquire_sys(f + nb.rank[a]) < seq) {
+      if (p2p_now_ns() - t0 > kP2PTimeoutNs) { atomicExch(pv.err, 2); break; }
+    }
+  }
+}
+
+// ONE thread (of the last block to finish its peer stores): tell every neighbour that exchange `seq` landed
+__device__ __forceinline__ void p2p_signal_halo(const P2PView &pv, const P2PNeighbors &nb, unsigned long long seq) {
+  __threadfence_system();
+  for (int a = 0; a < nb.n; a++) st_release_sys(pv.hflag[nb.rank[a]] + pv.me, seq);
+}
+
+}  // namespace fb

@@ -17,6 +17,7 @@
 // Variant 2 interleaves two block columns so each lane issues 16-byte double2 loads.
 #pragma once
 #include "common.cuh"
+#include "cg_kernels.cuh"
 
 namespace fb {
 
@@ -139,8 +140,13 @@ __global__ void __launch_bounds__(BLOCK)
 spmv_sell2_kernel(int N, int nslice, const long long *__restrict__ slice_ptr,
                   const double *__restrict__ val, const int *__restrict__ col,
                   const double *__restrict__ x, const double *__restrict__ b, double *__restrict__ y,
-                  double *partial, unsigned int *counter, double *red_out, const int *phase) {
+                  double *partial, unsigned int *counter, double *red_out, const int *phase,
+                  P2PView pv, P2PNeighbors nb, P2PArgs a) {
   if (phase && *phase != 0) return;
+  if (a.halo_seq) {   // peer-memory mode: the neighbours store their export values of x into our halo rows
+    if (threadIdx.x == 0) p2p_wait_halo(pv, nb, a.halo_seq);
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31;
   const int wg = (blockIdx.x * BLOCK + threadIdx.x) >> 5;
   const int nw = (gridDim.x * BLOCK) >> 5;
@@ -178,7 +184,10 @@ spmv_sell2_kernel(int N, int nslice, const long long *__restrict__ slice_ptr,
       y[r3] = y0; y[r3 + 1] = y1; y[r3 + 2] = y2;
     }
   }
-  grid_reduce<1, BLOCK>(dot, partial, counter, [=](double(&o)[1]) { if (red_out) *red_out = o[0]; });
+  grid_reduce<1, BLOCK>(dot, partial, counter, [=](double(&o)[1]) {
+    if (a.publish_seq) p2p_publish(pv, P2P_Q_PQ, a.publish_seq, o[0], 0.0);
+    else if (red_out) *red_out = o[0];
+  });
 }
 
 // variant 0: no private copy — one thread per scalar row straight on D/AL/AU (same accumulation

@@ -38,6 +38,10 @@ def set_option(key: str, value: int):
     check(_lib.lib().fistr_b200_set_option(key.encode(), int(value)))
 
 
+def get_option(key: str) -> int:
+    return int(_lib.lib().fistr_b200_get_option(key.encode()))
+
+
 def launch_count() -> int:
     return int(_lib.lib().fistr_b200_launch_count())
 

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--tet", type=int, default=0)
     ap.add_argument("--precond", type=int, default=3)
     ap.add_argument("--tol", type=float, default=1e-10)
+    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"])
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -33,6 +34,7 @@ def main():
     import fb_util as util
     from frontistr_b200 import hecmw, meshgen, partition
     hecmw.init(lr)
+    hecmw.set_option("p2p", 2 if args.comm == "p2p" else 0)   # 2 = fail loudly if peer memory cannot be mapped
     hecmw.comm_init_from_torch()
     gmesh = meshgen.tet10_cube(args.tet) if args.tet else util.distort(meshgen.hex_cube(args.n))
     axes = {2: "x", 4: "xy", 8: "xyz"}[world]
@@ -60,8 +62,8 @@ def main():
         err = util.rel_l2(xgl.reshape(-1), Ao.X)
         it_ok = abs(r["iter"] - ro["iter"]) <= 2 if args.precond == 3 else True   # SSOR is subdomain-local
         ok = (r["error"] == 0 and it_ok and err <= 1e-9 and r["resid2"] < args.tol and float(t.item()) == 0.0)
-        print("%s dist_check world=%d mesh=%s precond=%d: iter gpu=%d oracle=%d  rel_l2=%.2e  resid2=%.2e  halo_err=%.1e  neighbors=%d"
-              % ("PASS" if ok else "FAIL", world, ("tet%d" % args.tet) if args.tet else ("hex%d" % args.n), args.precond,
+        print("%s dist_check world=%d comm=%s mesh=%s precond=%d: iter gpu=%d oracle=%d  rel_l2=%.2e  resid2=%.2e  halo_err=%.1e  neighbors=%d"
+              % ("PASS" if ok else "FAIL", world, args.comm, ("tet%d" % args.tet) if args.tet else ("hex%d" % args.n), args.precond,
                  r["iter"], ro["iter"], err, r["resid2"], float(t.item()), m.n_neighbor_pe), flush=True)
     hecmw.comm_finalize()
     dist.destroy_process_group()
