@@ -364,7 +364,9 @@ def run_b200(args):
                           % (spmv_bytes_global / world / 1e9)},
                "iterations_per_step": res["iters"] // args.steps, "resid": float(last["resid"]),
                "resid_true": float(last["resid2"]), "wall_ms_per_step": 1e3 * res["wall_s"] / args.steps,
-               "gpu_launches": int(res["launches"]), "clocks": res["clocks"], "e2e": e2e,
+               "gpu_launches": int(res["launches"]),
+               "iteration_profile_us": dict(zip(("p_update+halo", "spmv", "tail+reductions", "iteration"),
+                                                [round(1e6 * float(v), 2) for v in last["profile"]])), "clocks": res["clocks"], "e2e": e2e,
                "roofline": {"bound": "hbm", "kernel": "spmv_sell2_kernel<0,256> (hecmw_matvec_33 + p.q)",
                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                             "peak_source": peak_src, "traffic": ncu_traffic(args.n, world),

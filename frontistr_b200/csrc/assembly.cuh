@@ -59,7 +59,8 @@ __global__ void __launch_bounds__(WARPS * 32)
 stiff_kernel(int e0, int e1, const int *__restrict__ elem_node_index, const int *__restrict__ elem_node_item,
              const double *__restrict__ node, const int *__restrict__ section_ID,
              const double *__restrict__ sectD, const int *__restrict__ sect_form,
-             const unsigned *__restrict__ slot, size_t slot_base, double *__restrict__ vals) {
+             const unsigned *__restrict__ slot, size_t slot_base, double *__restrict__ vals, int probe = 0) {
+  // probe (development timing switches, 0 in production): 1 = no scatter, 2 = no IC condensation
   using namespace elem;
   constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
   constexpr int NGP = (FORM == FORM_TET10) ? 4 : 8;
@@ -91,7 +92,7 @@ stiff_kernel(int e0, int e1, const int *__restrict__ elem_node_index, const int 
         else pair_block_iso<(FORM == FORM_IC) ? 11 : NN, NGP>(S, t / NN, t % NN, D11, D12, D44, kb[r]);
       }
     }
-    if (FORM == FORM_IC) {
+    if (FORM == FORM_IC && !(probe & 2)) {
       ic_phase_coupling(lane, S, D11, D12, D44);
       ic_inv_init(lane, S);
       __syncwarp();
@@ -116,6 +117,16 @@ stiff_kernel(int e0, int e1, const int *__restrict__ elem_node_index, const int 
         const int t = r * 32 + lane;
         if (t < NB) ic_condense_block(S, t / NN, t % NN, kb[r]);
       }
+    }
+    if (probe & 1) {
+      double sum = 0.0;
+#pragma unroll
+      for (int r = 0; r < ROUNDS; r++)
+#pragma unroll
+        for (int a = 0; a < 9; a++) sum += kb[r][a];
+      if (sum == 1.2345e300) vals[0] = sum;
+      __syncwarp();
+      continue;
     }
     // hecmw_mat_add_node: 9 scalar atomic adds per block ('!$omp atomic', hecmw_mat_ass.f90:96,117,128)
 #pragma unroll

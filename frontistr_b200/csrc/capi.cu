@@ -104,15 +104,15 @@ static int build_sell(Context &C) {
   }
   S.N = N; S.NP = C.NP; S.nslice = nslice; S.variant = variant; S.total_cols = sp[nslice];
   const size_t cols = (size_t)S.total_cols * (variant == 2 ? 2 : 1);
-  if (S.slice_ptr.alloc((size_t)nslice + 1) || S.val.alloc(cols * 288) || S.col.alloc(cols * 32)) return FISTR_B200_ERR_CUDA;
+  if (S.slice_ptr.alloc((size_t)nslice + 1) || S.val.alloc(cols * 288) || S.col.alloc(cols * 32) || S.halo_slice.alloc((size_t)nslice + 1)) return FISTR_B200_ERR_CUDA;
   FB_CUDA(cudaMemcpyAsync(S.slice_ptr.p, sp.data(), sizeof(long long) * sp.size(), cudaMemcpyHostToDevice, C.stream));
   FB_CUDA(cudaStreamSynchronize(C.stream));   // sp is a local
   if (nslice > 0) {
     const int blocks = (nslice * 32 + 255) / 256;
     if (variant == 2)
-      sell_fill_kernel<2><<<blocks, 256, 0, C.stream>>>(N, C.dD(), C.dAL(), C.dAU(), C.indexL.p, C.itemL.p, C.indexU.p, C.itemU.p, S.slice_ptr.p, S.val.p, S.col.p);
+      sell_fill_kernel<2><<<blocks, 256, 0, C.stream>>>(N, C.dD(), C.dAL(), C.dAU(), C.indexL.p, C.itemL.p, C.indexU.p, C.itemU.p, S.slice_ptr.p, S.val.p, S.col.p, S.halo_slice.p);
     else
-      sell_fill_kernel<1><<<blocks, 256, 0, C.stream>>>(N, C.dD(), C.dAL(), C.dAU(), C.indexL.p, C.itemL.p, C.indexU.p, C.itemU.p, S.slice_ptr.p, S.val.p, S.col.p);
+      sell_fill_kernel<1><<<blocks, 256, 0, C.stream>>>(N, C.dD(), C.dAL(), C.dAU(), C.indexL.p, C.itemL.p, C.indexU.p, C.itemU.p, S.slice_ptr.p, S.val.p, S.col.p, S.halo_slice.p);
     FB_LAUNCH_CHECK();
   }
   C.sell_valid = true;
@@ -137,8 +137,8 @@ static int launch_spmv(Context &C, int mode, const double *x, const double *b, d
       if (mode == 0) spmv_sell1_kernel<0, BLOCK><<<grid, BLOCK, 0, C.stream>>>(S.N, S.nslice, S.slice_ptr.p, S.val.p, S.col.p, x, b, y, C.partial.p, C.counter.p, red_out, phase);
       else spmv_sell1_kernel<1, BLOCK><<<grid, BLOCK, 0, C.stream>>>(S.N, S.nslice, S.slice_ptr.p, S.val.p, S.col.p, x, b, y, C.partial.p, C.counter.p, red_out, phase);
     } else {
-      if (mode == 0) spmv_sell2_kernel<0, BLOCK><<<grid, BLOCK, 0, C.stream>>>(S.N, S.nslice, S.slice_ptr.p, S.val.p, S.col.p, x, b, y, C.partial.p, C.counter.p, red_out, phase, C.p2p.view, C.p2p.nbrs, pa);
-      else spmv_sell2_kernel<1, BLOCK><<<grid, BLOCK, 0, C.stream>>>(S.N, S.nslice, S.slice_ptr.p, S.val.p, S.col.p, x, b, y, C.partial.p, C.counter.p, red_out, phase, C.p2p.view, C.p2p.nbrs, pa);
+      if (mode == 0) spmv_sell2_kernel<0, BLOCK><<<grid, BLOCK, 0, C.stream>>>(S.N, S.nslice, S.slice_ptr.p, S.val.p, S.col.p, x, b, y, C.partial.p, C.counter.p, red_out, phase, C.p2p.view, C.p2p.nbrs, pa, S.halo_slice.p);
+      else spmv_sell2_kernel<1, BLOCK><<<grid, BLOCK, 0, C.stream>>>(S.N, S.nslice, S.slice_ptr.p, S.val.p, S.col.p, x, b, y, C.partial.p, C.counter.p, red_out, phase, C.p2p.view, C.p2p.nbrs, pa, S.halo_slice.p);
     }
   }
   FB_LAUNCH_CHECK();
@@ -686,12 +686,13 @@ int fistr_b200_stiffmatrix_3d(int n_node, const double *node, int n_elem, int n_
     FB_CUDA(cudaFuncSetAttribute(stiff_kernel<elem::FORM_TET10, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
+  const int probe = (int)C.get("asm_probe", 0);
   for (int it = 0; it < n_elem_type; it++) {
     const int e0 = elem_type_index[it], e1 = elem_type_index[it + 1];
     if (e1 <= e0) continue;
     const int grid = C.grid_for((size_t)(e1 - e0) * 32, WARPS * 32, 8);
     if (elem_type_item[it] == 342) {
-      stiff_kernel<elem::FORM_TET10, WARPS><<<grid, WARPS * 32, smem, C.stream>>>(e0, e1, C.m_eni.p, C.m_enn.p, C.m_node.p, C.m_sec.p, C.m_sectD.p, C.m_form.p, C.slot.p, slot_base[it], C.vals.p);
+      stiff_kernel<elem::FORM_TET10, WARPS><<<grid, WARPS * 32, smem, C.stream>>>(e0, e1, C.m_eni.p, C.m_enn.p, C.m_node.p, C.m_sec.p, C.m_sectD.p, C.m_form.p, C.slot.p, slot_base[it], C.vals.p, probe);
       FB_LAUNCH_CHECK();
     } else {
       bool has[5] = {false, false, false, false, false};
@@ -700,9 +701,9 @@ int fistr_b200_stiffmatrix_3d(int n_node, const double *node, int n_elem, int n_
           return fail(FISTR_B200_ERR_ARG, "stiffmatrix_3d: elemopt361=%d not supported (1 FI, 2 BBAR, 3 IC)", sect_elemopt361[s]);
         has[sect_elemopt361[s]] = true;
       }
-      if (has[3]) { stiff_kernel<elem::FORM_IC, WARPS><<<grid, WARPS * 32, smem, C.stream>>>(e0, e1, C.m_eni.p, C.m_enn.p, C.m_node.p, C.m_sec.p, C.m_sectD.p, C.m_form.p, C.slot.p, slot_base[it], C.vals.p); FB_LAUNCH_CHECK(); }
-      if (has[1]) { stiff_kernel<elem::FORM_FI, WARPS><<<grid, WARPS * 32, smem, C.stream>>>(e0, e1, C.m_eni.p, C.m_enn.p, C.m_node.p, C.m_sec.p, C.m_sectD.p, C.m_form.p, C.slot.p, slot_base[it], C.vals.p); FB_LAUNCH_CHECK(); }
-      if (has[2]) { stiff_kernel<elem::FORM_BBAR, WARPS><<<grid, WARPS * 32, smem, C.stream>>>(e0, e1, C.m_eni.p, C.m_enn.p, C.m_node.p, C.m_sec.p, C.m_sectD.p, C.m_form.p, C.slot.p, slot_base[it], C.vals.p); FB_LAUNCH_CHECK(); }
+      if (has[3]) { stiff_kernel<elem::FORM_IC, WARPS><<<grid, WARPS * 32, smem, C.stream>>>(e0, e1, C.m_eni.p, C.m_enn.p, C.m_node.p, C.m_sec.p, C.m_sectD.p, C.m_form.p, C.slot.p, slot_base[it], C.vals.p, probe); FB_LAUNCH_CHECK(); }
+      if (has[1]) { stiff_kernel<elem::FORM_FI, WARPS><<<grid, WARPS * 32, smem, C.stream>>>(e0, e1, C.m_eni.p, C.m_enn.p, C.m_node.p, C.m_sec.p, C.m_sectD.p, C.m_form.p, C.slot.p, slot_base[it], C.vals.p, probe); FB_LAUNCH_CHECK(); }
+      if (has[2]) { stiff_kernel<elem::FORM_BBAR, WARPS><<<grid, WARPS * 32, smem, C.stream>>>(e0, e1, C.m_eni.p, C.m_enn.p, C.m_node.p, C.m_sec.p, C.m_sectD.p, C.m_form.p, C.slot.p, slot_base[it], C.vals.p, probe); FB_LAUNCH_CHECK(); }
     }
   }
   FB_CUDA(cudaEventRecord(ev1, C.stream));
@@ -857,6 +858,11 @@ int fistr_b200_solve_resid2(double *resid2) {
   return 0;
 }
 
+int fistr_b200_solve_profile(double *seconds4) {
+  memcpy(seconds4, ctx().last_profile, sizeof(double) * 4);
+  return 0;
+}
+
 int fistr_b200_solve_history(double *hist, int max_len) {
   Context &C = ctx();
   const int n = (int)std::min<size_t>(C.last_hist.size(), (size_t)std::max(max_len, 0));
@@ -1007,9 +1013,10 @@ int fistr_b200_solve_33(int N, int NP, int NPL, int NPU, const double *D, const 
   double RESID = TOL;
   C.last_hist.clear();
   double Tcomm = 0.0, time_Ax = 0.0;
-  cudaEvent_t evA0 = nullptr, evA1 = nullptr;
+  cudaEvent_t evA0 = nullptr, evA1 = nullptr, evP0 = nullptr, evF1 = nullptr;
+  double prof_p = 0.0, prof_f = 0.0, prof_it = 0.0;
   const bool time_ax = TIMElog >= 1 || C.get("time_ax", 0) != 0;
-  if (time_ax) { FB_CUDA(cudaEventCreate(&evA0)); FB_CUDA(cudaEventCreate(&evA1)); }
+  if (time_ax) { FB_CUDA(cudaEventCreate(&evA0)); FB_CUDA(cudaEventCreate(&evA1)); FB_CUDA(cudaEventCreate(&evP0)); FB_CUDA(cudaEventCreate(&evF1)); }
   int ax_samples = 0;
 
   if (BNRM2 == 0.0) {
@@ -1040,12 +1047,13 @@ int fistr_b200_solve_33(int N, int NP, int NPL, int NPU, const double *D, const 
       ap.consume_seq = pending_rrrz; pending_rrrz = 0;
       if (p2p) { ap.halo_seq = ++T.halo_seq; as.halo_seq = ap.halo_seq; }
       if (p2p && !recompute) { as.publish_seq = ++T.seq[P2P_Q_PQ]; af.consume_seq = as.publish_seq; af.publish_seq = ++T.seq[P2P_Q_RRRZ]; }
+      const bool sample = time_ax && (k % check_interval == 1 || check_interval == 1);
+      if (sample) FB_CUDA(cudaEventRecord(evP0, C.stream));
       cg_update_p_kernel<256><<<gvec, BLOCK, 0, C.stream>>>(k, n3, C.Z.p, C.P.p, red, C.ctl.p, C.hist.p, hist_len,
                                                             C.halo.n_export(), C.halo.d_export_item.p, C.halo.send_p.p,
                                                             T.view, T.nbrs, ap, T.exp_peer.p, T.exp_remote.p, C.counter.p + 1);
       FB_LAUNCH_CHECK();
       if (!p2p) FB_TRY(exchange(C, C.P.p, true));
-      const bool sample = time_ax && (k % check_interval == 1 || check_interval == 1);
       if (sample) FB_CUDA(cudaEventRecord(evA0, C.stream));
       FB_TRY(launch_spmv(C, 0, C.P.p, nullptr, C.Q.p, red + RED_PQ, phase, as));
       if (sample) FB_CUDA(cudaEventRecord(evA1, C.stream));
@@ -1068,12 +1076,13 @@ int fistr_b200_solve_33(int N, int NP, int NPL, int NPU, const double *D, const 
         FB_TRY(allreduce(C, red + 2 * parn, 1));
         FB_TRY(z_and_rho(parn));
       }
+      if (sample) FB_CUDA(cudaEventRecord(evF1, C.stream));
     }
     // ---- evaluate the last launched iteration's RESID, then look at the control block
     {
       P2PArgs ac;
       ac.consume_seq = pending_rrrz; pending_rrrz = 0;   // the check kernel leaves the sums in red[] for the next batch
-      cg_check_kernel<<<1, 1, 0, C.stream>>>(k, red, C.ctl.p, C.hist.p, hist_len, T.view, ac);
+      cg_check_kernel<<<1, 32, 0, C.stream>>>(k, red, C.ctl.p, C.hist.p, hist_len, T.view, ac);
       FB_LAUNCH_CHECK();
     }
     FB_CUDA(cudaMemcpyAsync(&h_ctl, C.ctl.p, sizeof h_ctl, cudaMemcpyDeviceToHost, C.stream));
@@ -1081,6 +1090,9 @@ int fistr_b200_solve_33(int N, int NP, int NPL, int NPU, const double *D, const 
     if (time_ax) {
       float ms = 0.f;
       if (cudaEventElapsedTime(&ms, evA0, evA1) == cudaSuccess) { time_Ax += ms * 1e-3; ax_samples++; }
+      if (cudaEventElapsedTime(&ms, evP0, evA0) == cudaSuccess) prof_p += ms * 1e-3;
+      if (cudaEventElapsedTime(&ms, evA1, evF1) == cudaSuccess) prof_f += ms * 1e-3;
+      if (cudaEventElapsedTime(&ms, evP0, evF1) == cudaSuccess) prof_it += ms * 1e-3;
     }
     if (p2p) {
       int perr = 0;
@@ -1151,7 +1163,11 @@ int fistr_b200_solve_33(int N, int NP, int NPL, int NPU, const double *D, const 
   const double resid2 = std::sqrt(rnorm2 / (BNRM2 == 0.0 ? 1.0 : BNRM2));
   if (resid2 < TOL) IA(81) = 1;
   C.last_resid2 = resid2;
-  if (time_ax) { cudaEventDestroy(evA0); cudaEventDestroy(evA1); }
+  if (time_ax) { cudaEventDestroy(evA0); cudaEventDestroy(evA1); cudaEventDestroy(evP0); cudaEventDestroy(evF1); }
+  if (ax_samples > 0) {   // per-iteration profile of the sampled iterations: p-update(+halo), SpMV, tail(+all-reduces), whole
+    C.last_profile[0] = prof_p / ax_samples; C.last_profile[1] = time_Ax / ax_samples;
+    C.last_profile[2] = prof_f / ax_samples; C.last_profile[3] = prof_it / ax_samples;
+  }
   const int niter_done = std::max(1, std::min(ITER, MAXIT));
   if (ax_samples > 0) time_Ax = time_Ax / ax_samples * niter_done;
   if (C.rank == 0 && (ITERlog == 1 || TIMElog >= 1)) printf("### Relative residual =%12.5E\n", resid2);

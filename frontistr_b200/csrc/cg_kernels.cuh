@@ -156,11 +156,13 @@ __device__ __forceinline__ void cg_fetch_rr_rz(int k, double *red, const P2PView
   const int par = k & 1;
   if (a.consume_seq == 0) { rr = red[2 * par]; rz = red[2 * par + 1]; return; }
   __shared__ double s_rrrz[2];
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {
     double s0, s1;
-    p2p_consume(pv, P2P_Q_RRRZ, a.consume_seq, s0, s1);
-    s_rrrz[0] = s0; s_rrrz[1] = s1;
-    if (blockIdx.x == 0) { red[2 * par] = s0; red[2 * par + 1] = s1; }
+    p2p_consume_warp(pv, P2P_Q_RRRZ, a.consume_seq, s0, s1);
+    if (threadIdx.x == 0) {
+      s_rrrz[0] = s0; s_rrrz[1] = s1;
+      if (blockIdx.x == 0) { red[2 * par] = s0; red[2 * par + 1] = s1; }
+    }
   }
   __syncthreads();
   rr = s_rrrz[0]; rz = s_rrrz[1];
@@ -196,9 +198,9 @@ cg_update_p_kernel(int k, size_t n3, const double *__restrict__ z, double *__res
     for (size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x; i < n3; i += stride) p[i] = fma(beta, p[i], z[i]);
   }
   if (a.halo_seq) {
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
+      __threadfence_system();   // cumulative: orders the peer stores of the whole block (bar.sync above) before the ticket
       const unsigned int t = atomicAdd(ticket, 1u);
       if (t == gridDim.x - 1) {
         *ticket = 0u;
@@ -213,7 +215,7 @@ __global__ void cg_check_kernel(int k, double *red, CgCtl *ctl, double *hist, in
   if (ctl->phase != 0) return;
   double beta, rr, rz;
   cg_fetch_rr_rz(k, red, pv, a, rr, rz);
-  cg_iter_prologue(k, red, ctl, hist, hist_len, true, rr, rz, beta);
+  if (threadIdx.x == 0) cg_iter_prologue(k, red, ctl, hist, hist_len, true, rr, rz, beta);
 }
 
 __device__ __forceinline__ bool cg_alpha_prologue(int k, const double *red, CgCtl *ctl, bool leader, double c1, double &alpha) {
@@ -237,7 +239,11 @@ cg_fused_update_kernel(int k, int N, const double *__restrict__ p, const double 
   double alpha, c1;
   if (a.consume_seq) {        // p.q = sum over all ranks' partials (peer table), block-uniform
     __shared__ double s_pq;
-    if (threadIdx.x == 0) { double s0, s1; p2p_consume(pv, P2P_Q_PQ, a.consume_seq, s0, s1); s_pq = s0; }
+    if (threadIdx.x < 32) {
+      double s0, s1;
+      p2p_consume_warp(pv, P2P_Q_PQ, a.consume_seq, s0, s1);
+      if (threadIdx.x == 0) s_pq = s0;
+    }
     __syncthreads();
     c1 = s_pq;
   } else c1 = red[RED_PQ];
@@ -255,9 +261,9 @@ cg_fused_update_kernel(int k, int N, const double *__restrict__ p, const double 
     acc[1] = fma(r0, a, acc[1]); acc[1] = fma(r1, b, acc[1]); acc[1] = fma(r2, c, acc[1]);
   }
   double *out = red + 2 * ((k + 1) & 1);
-  grid_reduce<2, BLOCK>(acc, partial, counter, [=](double(&o)[2]) {
-    if (a.publish_seq) p2p_publish(pv, P2P_Q_RRRZ, a.publish_seq, o[0], o[1]);
-    else { out[0] = o[0]; out[1] = o[1]; }
+  grid_reduce<2, BLOCK, true>(acc, partial, counter, [=](double(&o)[2]) {
+    if (a.publish_seq) p2p_publish_warp(pv, P2P_Q_RRRZ, a.publish_seq, o[0], o[1]);
+    else if (threadIdx.x == 0) { out[0] = o[0]; out[1] = o[1]; }
   });
 }
 

@@ -76,7 +76,9 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Deterministic grid reduction of NV doubles per thread.  Every block writes its partial to
 // partial[blockIdx.x*NV + k]; the last block to arrive (atomic ticket) sums the partials in a
 // fixed order and calls `fin(sums)` from thread 0.  counter must be zero on entry; it is reset.
-template <int NV, int BLOCK, class Fin>
+// WARP_FIN = true: `fin(sums)` is called by all 32 lanes of warp 0 of the last block instead (the
+// peer-memory publication uses one lane per destination rank).
+template <int NV, int BLOCK, bool WARP_FIN = false, class Fin>
 __device__ __forceinline__ void grid_reduce(double (&v)[NV], double *partial, unsigned int *counter, Fin fin) {
   __shared__ double sm[NV][BLOCK / kWarp];
   __shared__ bool is_last;
@@ -124,7 +126,20 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], double *partial, un
         out[k] = s;
       }
       *counter = 0u;
-      fin(out);
+      if (!WARP_FIN) fin(out);
+      else {
+#pragma unroll
+        for (int k = 0; k < NV; k++) sm[k][0] = out[k];
+      }
+    }
+    if (WARP_FIN) {
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        double out[NV];
+#pragma unroll
+        for (int k = 0; k < NV; k++) out[k] = sm[k][0];
+        fin(out);
+      }
     }
   }
 }

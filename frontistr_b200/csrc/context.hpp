@@ -69,6 +69,7 @@ struct Context {
   DevBuf<int> flag;
   std::vector<double> last_hist;
   double last_resid2 = 0.0;
+  double last_profile[4] = {0, 0, 0, 0};
 
   // ---- assembly
   DevBuf<unsigned> slot;

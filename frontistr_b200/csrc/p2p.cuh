@@ -66,46 +66,61 @@ __device__ __forceinline__ unsigned long long p2p_now_ns() {
 }
 constexpr unsigned long long kP2PTimeoutNs = 4000000000ull;   // 4 s
 
-// ONE thread: hand this rank's partial sums to every rank (itself included)
-__device__ __forceinline__ void p2p_publish(const P2PView &pv, int q, unsigned long long seq, double v0, double v1) {
-  const int slot = (q * 2 + (int)(seq & 1ull)) * kP2PMaxRanks + pv.me;
-  for (int r = 0; r < pv.nranks; r++) {
-    st_relaxed_sys(&pv.ar[r][slot].v[0], v0);
-    st_relaxed_sys(&pv.ar[r][slot].v[1], v1);
-  }
-  __threadfence_system();
-  for (int r = 0; r < pv.nranks; r++) st_release_sys(&pv.ar[r][slot].tag, seq);
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// ONE thread per block: wait for all ranks' partials of (q, seq) and sum them in rank order
-__device__ __forceinline__ void p2p_consume(const P2PView &pv, int q, unsigned long long seq, double &s0, double &s1) {
+// ONE WARP (all 32 lanes call): lane r hands this rank's partial sums to rank r (itself included):
+// values, one system-scope fence, then the tag (fence + relaxed store = release pattern).
+__device__ __forceinline__ void p2p_publish_warp(const P2PView &pv, int q, unsigned long long seq, double v0, double v1) {
+  const int lane = threadIdx.x & 31;
+  if (lane < pv.nranks) {
+    P2PEntry *e = pv.ar[lane] + (q * 2 + (int)(seq & 1ull)) * kP2PMaxRanks + pv.me;
+    st_relaxed_sys(&e->v[0], v0);
+    st_relaxed_sys(&e->v[1], v1);
+    __threadfence_system();
+    st_relaxed_sys(&e->tag, seq);
+  }
+}
+
+// FIRST WARP of a block (all 32 lanes call): lane r waits for rank r's partials of (q, seq); the partials are
+// then summed in rank order by every lane, so all lanes (and all ranks) obtain the bit-identical sums.
+__device__ __forceinline__ void p2p_consume_warp(const P2PView &pv, int q, unsigned long long seq, double &s0, double &s1) {
+  const int lane = threadIdx.x & 31;
   const P2PEntry *base = pv.ar[pv.me] + (q * 2 + (int)(seq & 1ull)) * kP2PMaxRanks;
-  s0 = 0.0; s1 = 0.0;
-  const unsigned long long t0 = p2p_now_ns();
-  for (int r = 0; r < pv.nranks; r++) {
-    while (ld_acquire_sys(&base[r].tag) != seq) {
+  double v0 = 0.0, v1 = 0.0;
+  if (lane < pv.nranks) {
+    const unsigned long long t0 = p2p_now_ns();
+    while (ld_acquire_sys(&base[lane].tag) != seq) {
       if (p2p_now_ns() - t0 > kP2PTimeoutNs) { atomicExch(pv.err, 1); break; }
     }
-    s0 += ld_relaxed_sys(&base[r].v[0]);
-    s1 += ld_relaxed_sys(&base[r].v[1]);
+    v0 = ld_relaxed_sys(&base[lane].v[0]);
+    v1 = ld_relaxed_sys(&base[lane].v[1]);
+  }
+  s0 = 0.0; s1 = 0.0;
+  for (int r = 0; r < pv.nranks; r++) {
+    s0 += __shfl_sync(0xffffffffu, v0, r);
+    s1 += __shfl_sync(0xffffffffu, v1, r);
   }
 }
 
-// ONE thread per block: wait until every neighbour has delivered halo exchange number `seq`
-__device__ __forceinline__ void p2p_wait_halo(const P2PView &pv, const P2PNeighbors &nb, unsigned long long seq) {
-  const unsigned long long *f = pv.hflag[pv.me];
-  const unsigned long long t0 = p2p_now_ns();
-  for (int a = 0; a < nb.n; a++) {
-    while (ld_acquire_sys(f + nb.rank[a]) < seq) {
+// ONE WARP (all 32 lanes call): lane a waits until neighbour a has delivered halo exchange number `seq`
+__device__ __forceinline__ void p2p_wait_halo_warp(const P2PView &pv, const P2PNeighbors &nb, unsigned long long seq) {
+  const int lane = threadIdx.x & 31;
+  if (lane < nb.n) {
+    const unsigned long long *f = pv.hflag[pv.me] + nb.rank[lane];
+    const unsigned long long t0 = p2p_now_ns();
+    while (ld_acquire_sys(f) < seq) {
       if (p2p_now_ns() - t0 > kP2PTimeoutNs) { atomicExch(pv.err, 2); break; }
     }
   }
+  __syncwarp();
 }
 
 // ONE thread (of the last block to finish its peer stores): tell every neighbour that exchange `seq` landed
 __device__ __forceinline__ void p2p_signal_halo(const P2PView &pv, const P2PNeighbors &nb, unsigned long long seq) {
   __threadfence_system();
-  for (int a = 0; a < nb.n; a++) st_release_sys(pv.hflag[nb.rank[a]] + pv.me, seq);
+  for (int a = 0; a < nb.n; a++) st_relaxed_sys(pv.hflag[nb.rank[a]] + pv.me, seq);
 }
 
 }  // namespace fb

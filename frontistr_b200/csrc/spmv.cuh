@@ -27,6 +27,7 @@ struct SellMatrix {
   DevBuf<long long> slice_ptr;     // nslice+1
   DevBuf<double> val;
   DevBuf<int> col;
+  DevBuf<unsigned char> halo_slice;   // 1 if any row of the slice has a column in the halo (>= N)
   size_t bytes() const { return val.n * 8 + col.n * 4 + slice_ptr.n * 8; }
 };
 
@@ -37,7 +38,7 @@ sell_fill_kernel(int N, const double *__restrict__ D, const double *__restrict__
                  const double *__restrict__ AU, const int *__restrict__ indexL,
                  const int *__restrict__ itemL, const int *__restrict__ indexU,
                  const int *__restrict__ itemU, const long long *__restrict__ slice_ptr,
-                 double *__restrict__ val, int *__restrict__ col) {
+                 double *__restrict__ val, int *__restrict__ col, unsigned char *__restrict__ halo_slice) {
   const int lane = threadIdx.x & 31;
   const long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long row = s * 32 + lane;  // 0-based
@@ -50,6 +51,7 @@ sell_fill_kernel(int N, const double *__restrict__ D, const double *__restrict__
     l0 = indexL[row]; nL = indexL[row + 1] - (int)l0;
     u0 = indexU[row]; nU = indexU[row + 1] - (int)u0;
   }
+  bool has_halo = false;
   for (int j = 0; j < w; j++) {
     const double *src = nullptr;
     int c = (row < N) ? (int)row : 0;
@@ -58,6 +60,7 @@ sell_fill_kernel(int N, const double *__restrict__ D, const double *__restrict__
       else if (j - 1 < nL) { src = AL + 9 * (l0 + j - 1); c = itemL[l0 + j - 1] - 1; }
       else if (j - 1 - nL < nU) { src = AU + 9 * (u0 + j - 1 - nL); c = itemU[u0 + j - 1 - nL] - 1; }
     }
+    has_halo = has_halo || (c >= N);
     if (VARIANT == 1) {
       const long long p = p0 + j;
       col[p * 32 + lane] = c;
@@ -70,6 +73,8 @@ sell_fill_kernel(int N, const double *__restrict__ D, const double *__restrict__
       for (int k = 0; k < 9; k++) val[((p * 9 + k) * 32 + lane) * 2 + (j & 1)] = src ? src[k] : 0.0;
     }
   }
+  const unsigned any = __ballot_sync(0xffffffffu, has_halo);
+  if (lane == 0) halo_slice[s] = any ? 1 : 0;
 }
 
 #define FB_ROW_FMA(y, a0, a1, a2, x0, x1, x2) y = fma((a2), (x2), fma((a1), (x1), fma((a0), (x0), (y))))
@@ -141,17 +146,17 @@ spmv_sell2_kernel(int N, int nslice, const long long *__restrict__ slice_ptr,
                   const double *__restrict__ val, const int *__restrict__ col,
                   const double *__restrict__ x, const double *__restrict__ b, double *__restrict__ y,
                   double *partial, unsigned int *counter, double *red_out, const int *phase,
-                  P2PView pv, P2PNeighbors nb, P2PArgs a) {
+                  P2PView pv, P2PNeighbors nb, P2PArgs a, const unsigned char *__restrict__ halo_slice) {
   if (phase && *phase != 0) return;
-  if (a.halo_seq) {   // peer-memory mode: the neighbours store their export values of x into our halo rows
-    if (threadIdx.x == 0) p2p_wait_halo(pv, nb, a.halo_seq);
-    __syncthreads();
-  }
   const int lane = threadIdx.x & 31;
   const int wg = (blockIdx.x * BLOCK + threadIdx.x) >> 5;
   const int nw = (gridDim.x * BLOCK) >> 5;
   double dot[1] = {0.0};
+  // peer-memory mode: the neighbours store their export values of x straight into our halo rows; only a warp
+  // about to process a slice that reads halo columns waits for their flags — interior slices overlap the exchange
+  bool halo_ready = (a.halo_seq == 0);
   for (int s = wg; s < nslice; s += nw) {
+    if (!halo_ready && halo_slice[s]) { p2p_wait_halo_warp(pv, nb, a.halo_seq); halo_ready = true; }
     const long long p0 = slice_ptr[s], p1 = slice_ptr[s + 1];
     const double2 *v = reinterpret_cast<const double2 *>(val) + p0 * 288 + lane;
     const int2 *cp = reinterpret_cast<const int2 *>(col) + p0 * 32 + lane;
@@ -184,9 +189,9 @@ spmv_sell2_kernel(int N, int nslice, const long long *__restrict__ slice_ptr,
       y[r3] = y0; y[r3 + 1] = y1; y[r3 + 2] = y2;
     }
   }
-  grid_reduce<1, BLOCK>(dot, partial, counter, [=](double(&o)[1]) {
-    if (a.publish_seq) p2p_publish(pv, P2P_Q_PQ, a.publish_seq, o[0], 0.0);
-    else if (red_out) *red_out = o[0];
+  grid_reduce<1, BLOCK, true>(dot, partial, counter, [=](double(&o)[1]) {
+    if (a.publish_seq) p2p_publish_warp(pv, P2P_Q_PQ, a.publish_seq, o[0], 0.0);
+    else if (red_out && threadIdx.x == 0) *red_out = o[0];
   });
 }
 

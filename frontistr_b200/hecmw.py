@@ -194,7 +194,9 @@ def hecmw_solve(hecMESH, hecMAT, device_resident: bool = False):
     nh = L.fistr_b200_solve_history(dp(hist), len(hist))
     r2 = C.c_double()
     L.fistr_b200_solve_resid2(C.byref(r2))
-    return dict(error=rc, iter=it.value, resid=rs.value, resid2=r2.value, times=times, hist=hist[:nh])
+    prof = np.zeros(4)
+    L.fistr_b200_solve_profile(dp(prof))
+    return dict(error=rc, iter=it.value, resid=rs.value, resid2=r2.value, times=times, hist=hist[:nh], profile=prof)
 
 
 def hecmw_matvec(X: np.ndarray, n_internal3: int) -> np.ndarray:

@@ -109,6 +109,9 @@ int fistr_b200_solve_33(int N, int NP, int NPL, int NPU, const double *D, const 
                         int my_rank, int petot, int *iter_out, double *resid_out, double *time_out);
 /* residual history of the last solve (RESID per iteration, what ITERLOG=YES prints, CG.f90:245) */
 int fistr_b200_solve_history(double *hist, int max_len);
+/* CUDA-event profile of the last solve (needs the "time_ax" option or TIMELOG): mean seconds per sampled
+ * iteration of [p-update incl. halo push, SpMV, tail kernel incl. dot-product reductions, whole iteration] */
+int fistr_b200_solve_profile(double *seconds4);
 /* final true relative residual of the last solve (hecmw_rel_resid_L2, Iterative.f90:166) */
 int fistr_b200_solve_resid2(double *resid2);
 
