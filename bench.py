@@ -390,6 +390,12 @@ def run_b200(args):
 
 def main():
     args = parse_args()
+    # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner, HEC-MW style
+    # solver warnings of the oracle) is sent to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if args.impl == "reference":
         run_reference(args)
     else:
