@@ -53,13 +53,102 @@ slot_build_kernel(int e0, int e1, int nn, const int *__restrict__ elem_node_inde
   }
 }
 
+// ---- deterministic assembly: element matrices are stored, every matrix block gathers its own -------
+// hecmw_mat_add_node adds nn*nn blocks per element with 9 scalar atomics each (hecmw_mat_ass.f90:96,117,128).
+// On the GPU that is ~2 G atomic adds at H150.  Instead the element kernel writes its nn*nn blocks to a
+// scratch buffer ke[g*9 .. g*9+8], g = contribution index (the same index the slot table uses), and a second
+// kernel lets every matrix block sum the contributions that point at it — in ascending g, i.e. in the
+// reference's own 1-thread element order (mat_ass.f90:42-50) — and write the block ONCE.  No atomics, no
+// zero-fill pass, bit-reproducible.  The inverse map (gptr/gsrc) depends on topology only.
+__global__ void __launch_bounds__(256)
+gather_count_kernel(size_t ncontrib, const unsigned *__restrict__ slot, unsigned *__restrict__ cnt) {
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ncontrib; g += (size_t)gridDim.x * blockDim.x) {
+    const unsigned s = slot[g];
+    if (s != kBadSlot) atomicAdd(cnt + s, 1u);
+  }
+}
+__global__ void __launch_bounds__(256)
+gather_fill_kernel(size_t ncontrib, const unsigned *__restrict__ slot, const unsigned *__restrict__ gptr,
+                   unsigned *__restrict__ cursor, unsigned *__restrict__ gsrc) {
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < ncontrib; g += (size_t)gridDim.x * blockDim.x) {
+    const unsigned s = slot[g];
+    if (s != kBadSlot) gsrc[gptr[s] + atomicAdd(cursor + s, 1u)] = (unsigned)g;
+  }
+}
+// ascending contribution index inside every block's list (lists are short: <= 8 for a hex mesh)
+__global__ void __launch_bounds__(256)
+gather_sort_kernel(size_t nblk, const unsigned *__restrict__ gptr, unsigned *__restrict__ gsrc) {
+  for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nblk; b += (size_t)gridDim.x * blockDim.x) {
+    const unsigned k0 = gptr[b], k1 = gptr[b + 1];
+    for (unsigned i = k0 + 1; i < k1; i++) {
+      const unsigned v = gsrc[i];
+      unsigned j = i;
+      while (j > k0 && gsrc[j - 1] > v) { gsrc[j] = gsrc[j - 1]; j--; }
+      gsrc[j] = v;
+    }
+  }
+}
+// one thread per scalar entry of the matrix: vals[9*b + c] = sum_k ke[9*gsrc[k] + c]
+__global__ void __launch_bounds__(256)
+gather_sum_kernel(size_t nblk, const unsigned *__restrict__ gptr, const unsigned *__restrict__ gsrc,
+                  const double *__restrict__ ke, double *__restrict__ vals) {
+  const size_t total = 9 * nblk;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = t / 9;
+    const unsigned c = (unsigned)(t - 9 * b);
+    const unsigned k0 = gptr[b], k1 = gptr[b + 1];
+    double acc = 0.0;
+    for (unsigned k = k0; k < k1; k++) acc += ld_stream(ke + 9 * (size_t)gsrc[k] + c);
+    vals[t] = acc;
+  }
+}
+
+// calInverse(9, Kaa) for the IC condensation: column c of Kaa in the registers of lane c, cross-lane traffic by
+// warp shuffles only (per-lane steps: element_math.cuh gj_*).  Reads S.Kaa, writes the inverse back to S.Kaa.
+__device__ __forceinline__ void ic_inverse_warp(int lane, elem::Scratch &S) {
+  using namespace elem;
+  constexpr unsigned FULL = 0xffffffffu;
+  const int c = (lane < 9) ? lane : 8;      // lanes >= 9 shadow column 8 (results discarded)
+  double a[9];
+  int ip[9];
+#pragma unroll
+  for (int I = 0; I < 9; I++) { a[I] = S.Kaa[I * 9 + c]; ip[I] = I; }
+#pragma unroll
+  for (int K = 0; K < 9; K++) {
+    int LR;
+    double pivot;
+    gj_pivot_local(K, a, LR, pivot);
+    LR = __shfl_sync(FULL, LR, K);
+    gj_swap_rows(K, LR, a, ip);
+    double w[9];
+#pragma unroll
+    for (int I = 0; I < 9; I++) w[I] = __shfl_sync(FULL, a[I], K);
+    gj_update(c, K, a, w);
+  }
+#pragma unroll
+  for (int I = 0; I < 9; I++) {
+    const int K = gj_unpermute_step(I, ip);   // warp-uniform (ip is identical in every lane)
+    if (K >= 0) {
+      const int other = (lane == I) ? K : ((lane == K) ? I : lane);
+#pragma unroll
+      for (int r = 0; r < 9; r++) a[r] = __shfl_sync(FULL, a[r], other);
+    }
+  }
+  __syncwarp();
+  if (lane < 9) {
+#pragma unroll
+    for (int I = 0; I < 9; I++) S.Kaa[I * 9 + lane] = a[I];
+  }
+}
+
 // One element per warp.  sect[3*s..] = D11, D12, D44 of section s; sect_form[s] = elemopt361.
 template <int FORM, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 stiff_kernel(int e0, int e1, const int *__restrict__ elem_node_index, const int *__restrict__ elem_node_item,
              const double *__restrict__ node, const int *__restrict__ section_ID,
              const double *__restrict__ sectD, const int *__restrict__ sect_form,
-             const unsigned *__restrict__ slot, size_t slot_base, double *__restrict__ vals, int probe = 0) {
+             const unsigned *__restrict__ slot, size_t slot_base, double *__restrict__ vals,
+             double *__restrict__ ke_out, int probe = 0) {
   // probe (development timing switches, 0 in production): 1 = no scatter, 2 = no IC condensation
   using namespace elem;
   constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
@@ -94,21 +183,8 @@ stiff_kernel(int e0, int e1, const int *__restrict__ elem_node_index, const int 
     }
     if (FORM == FORM_IC && !(probe & 2)) {
       ic_phase_coupling(lane, S, D11, D12, D44);
-      ic_inv_init(lane, S);
       __syncwarp();
-      for (int K = 0; K < 9; K++) {
-        ic_inv_pivot(lane, S, K);
-        __syncwarp();
-        ic_inv_swap(lane, S, K);
-        __syncwarp();
-        double colK[9];
-#pragma unroll
-        for (int I = 0; I < 9; I++) colK[I] = S.Kaa[I * 9 + K];
-        __syncwarp();
-        ic_inv_step(lane, S, K, colK);
-        __syncwarp();
-      }
-      ic_inv_unpermute(lane, S);
+      ic_inverse_warp(lane, S);
       __syncwarp();
       ic_phase_W(lane, S);
       __syncwarp();
@@ -125,6 +201,24 @@ stiff_kernel(int e0, int e1, const int *__restrict__ elem_node_index, const int 
 #pragma unroll
         for (int a = 0; a < 9; a++) sum += kb[r][a];
       if (sum == 1.2345e300) vals[0] = sum;
+      __syncwarp();
+      continue;
+    }
+    if (ke_out) {
+      // gather mode: stage the nn*nn blocks in shared memory, then stream them out as coalesced 16-byte stores
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < ROUNDS; r++) {
+        const int t = r * 32 + lane;
+        if (t < NB) {
+#pragma unroll
+          for (int a = 0; a < 9; a++) S.stage[t * 9 + a] = kb[r][a];
+        }
+      }
+      __syncwarp();
+      double2 *dst = reinterpret_cast<double2 *>(ke_out + 9 * (slot_base + (size_t)(e - e0) * NB));
+      const double2 *src = reinterpret_cast<const double2 *>(S.stage);
+      for (int q = lane; q < NB * 9 / 2; q += 32) dst[q] = src[q];
       __syncwarp();
       continue;
     }

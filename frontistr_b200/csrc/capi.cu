@@ -3,6 +3,8 @@
 #include <cmath>
 #include <cstdarg>
 
+#include <cub/device/device_scan.cuh>
+
 #include "context.hpp"
 #include "partition.hpp"
 
@@ -670,12 +672,46 @@ int fistr_b200_stiffmatrix_3d(int n_node, const double *node, int n_elem, int n_
     if (err) return fail(FISTR_B200_ERR_CONNECTIVITY, "###ERROR### : cannot find connectivity");
     C.slot_valid = true;
     C.key_elem_node_item = elem_node_item;
+    // inverse map of the slot table for the gather assembly (topology only)
+    C.gather_valid = false;
+    const size_t ncontrib = slot_base.back(), nblk = (size_t)C.NP + C.NPL + C.NPU;
+    if (C.get("asm_gather", 1) != 0 && ncontrib < 0xFFFFFFF0ull && ncontrib > 0) {
+      DevBuf<unsigned> cursor;
+      DevBuf<unsigned char> tmp;
+      size_t tmp_bytes = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (unsigned *)nullptr, (unsigned *)nullptr, (int)1);
+      if (!(C.gptr.alloc(nblk + 1) || C.gsrc.alloc(ncontrib) || cursor.alloc(nblk + 1))) {
+        FB_CUDA(cudaMemsetAsync(cursor.p, 0, sizeof(unsigned) * (nblk + 1), C.stream));
+        gather_count_kernel<<<C.grid_for(ncontrib, 256, 16), 256, 0, C.stream>>>(ncontrib, C.slot.p, cursor.p);
+        FB_LAUNCH_CHECK();
+        // exclusive scan in chunks of < 2^31 items (CUB takes an int count), carrying the running offset
+        FB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cursor.p, C.gptr.p, (int)std::min<size_t>(nblk + 1, 1u << 30), C.stream));
+        if (tmp.alloc(tmp_bytes + 16)) return FISTR_B200_ERR_CUDA;
+        if (nblk + 1 > (1u << 30)) return fail(FISTR_B200_ERR_ARG, "stiffmatrix_3d: too many blocks for the gather map");
+        FB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, cursor.p, C.gptr.p, (int)(nblk + 1), C.stream));
+        FB_CUDA(cudaMemsetAsync(cursor.p, 0, sizeof(unsigned) * (nblk + 1), C.stream));
+        gather_fill_kernel<<<C.grid_for(ncontrib, 256, 16), 256, 0, C.stream>>>(ncontrib, C.slot.p, C.gptr.p, cursor.p, C.gsrc.p);
+        FB_LAUNCH_CHECK();
+        gather_sort_kernel<<<C.grid_for(nblk, 256, 16), 256, 0, C.stream>>>(nblk, C.gptr.p, C.gsrc.p);
+        FB_LAUNCH_CHECK();
+        FB_CUDA(cudaStreamSynchronize(C.stream));
+        cursor.release(); tmp.release();
+        C.gather_valid = true;
+      } else {
+        C.gptr.release(); C.gsrc.release(); cursor.release();   // not enough memory: atomic scatter path
+        cudaGetLastError();
+      }
+    }
   }
+  // element-matrix scratch of the gather assembly; falls back to the atomic scatter if it does not fit
+  bool use_gather = C.gather_valid && C.get("asm_gather", 1) != 0;
+  if (use_gather && C.ke.alloc(9 * slot_base.back())) { cudaGetLastError(); use_gather = false; }
+  double *ke_out = use_gather ? C.ke.p : nullptr;
   // hecmw_mat_clear + element loop
   cudaEvent_t ev0, ev1;
   FB_CUDA(cudaEventCreate(&ev0)); FB_CUDA(cudaEventCreate(&ev1));
   FB_CUDA(cudaEventRecord(ev0, C.stream));
-  FB_CUDA(cudaMemsetAsync(C.vals.p, 0, sizeof(double) * 9 * ((size_t)C.NP + C.NPL + C.NPU), C.stream));
+  if (!use_gather) FB_CUDA(cudaMemsetAsync(C.vals.p, 0, sizeof(double) * 9 * ((size_t)C.NP + C.NPL + C.NPU), C.stream));   // hecmw_mat_clear
   constexpr int WARPS = 4;
   const size_t smem = sizeof(elem::Scratch) * WARPS;
   static bool attr_set = false;
@@ -692,7 +728,7 @@ int fistr_b200_stiffmatrix_3d(int n_node, const double *node, int n_elem, int n_
     if (e1 <= e0) continue;
     const int grid = C.grid_for((size_t)(e1 - e0) * 32, WARPS * 32, 8);
     if (elem_type_item[it] == 342) {
-      stiff_kernel<elem::FORM_TET10, WARPS><<<grid, WARPS * 32, smem, C.stream>>>(e0, e1, C.m_eni.p, C.m_enn.p, C.m_node.p, C.m_sec.p, C.m_sectD.p, C.m_form.p, C.slot.p, slot_base[it], C.vals.p, probe);
+      stiff_kernel<elem::FORM_TET10, WARPS><<<grid, WARPS * 32, smem, C.stream>>>(e0, e1, C.m_eni.p, C.m_enn.p, C.m_node.p, C.m_sec.p, C.m_sectD.p, C.m_form.p, C.slot.p, slot_base[it], C.vals.p, ke_out, probe);
       FB_LAUNCH_CHECK();
     } else {
       bool has[5] = {false, false, false, false, false};
@@ -701,10 +737,15 @@ int fistr_b200_stiffmatrix_3d(int n_node, const double *node, int n_elem, int n_
           return fail(FISTR_B200_ERR_ARG, "stiffmatrix_3d: elemopt361=%d not supported (1 FI, 2 BBAR, 3 IC)", sect_elemopt361[s]);
         has[sect_elemopt361[s]] = true;
       }
-      if (has[3]) { stiff_kernel<elem::FORM_IC, WARPS><<<grid, WARPS * 32, smem, C.stream>>>(e0, e1, C.m_eni.p, C.m_enn.p, C.m_node.p, C.m_sec.p, C.m_sectD.p, C.m_form.p, C.slot.p, slot_base[it], C.vals.p, probe); FB_LAUNCH_CHECK(); }
-      if (has[1]) { stiff_kernel<elem::FORM_FI, WARPS><<<grid, WARPS * 32, smem, C.stream>>>(e0, e1, C.m_eni.p, C.m_enn.p, C.m_node.p, C.m_sec.p, C.m_sectD.p, C.m_form.p, C.slot.p, slot_base[it], C.vals.p, probe); FB_LAUNCH_CHECK(); }
-      if (has[2]) { stiff_kernel<elem::FORM_BBAR, WARPS><<<grid, WARPS * 32, smem, C.stream>>>(e0, e1, C.m_eni.p, C.m_enn.p, C.m_node.p, C.m_sec.p, C.m_sectD.p, C.m_form.p, C.slot.p, slot_base[it], C.vals.p, probe); FB_LAUNCH_CHECK(); }
+      if (has[3]) { stiff_kernel<elem::FORM_IC, WARPS><<<grid, WARPS * 32, smem, C.stream>>>(e0, e1, C.m_eni.p, C.m_enn.p, C.m_node.p, C.m_sec.p, C.m_sectD.p, C.m_form.p, C.slot.p, slot_base[it], C.vals.p, ke_out, probe); FB_LAUNCH_CHECK(); }
+      if (has[1]) { stiff_kernel<elem::FORM_FI, WARPS><<<grid, WARPS * 32, smem, C.stream>>>(e0, e1, C.m_eni.p, C.m_enn.p, C.m_node.p, C.m_sec.p, C.m_sectD.p, C.m_form.p, C.slot.p, slot_base[it], C.vals.p, ke_out, probe); FB_LAUNCH_CHECK(); }
+      if (has[2]) { stiff_kernel<elem::FORM_BBAR, WARPS><<<grid, WARPS * 32, smem, C.stream>>>(e0, e1, C.m_eni.p, C.m_enn.p, C.m_node.p, C.m_sec.p, C.m_sectD.p, C.m_form.p, C.slot.p, slot_base[it], C.vals.p, ke_out, probe); FB_LAUNCH_CHECK(); }
     }
+  }
+  if (use_gather) {
+    const size_t nblk = (size_t)C.NP + C.NPL + C.NPU;
+    gather_sum_kernel<<<C.grid_for(9 * nblk, 256, 8), 256, 0, C.stream>>>(nblk, C.gptr.p, C.gsrc.p, C.ke.p, C.vals.p);
+    FB_LAUNCH_CHECK();
   }
   FB_CUDA(cudaEventRecord(ev1, C.stream));
   FB_CUDA(cudaStreamSynchronize(C.stream));

@@ -72,6 +72,9 @@ struct Context {
   double last_profile[4] = {0, 0, 0, 0};
 
   // ---- assembly
+  DevBuf<unsigned> gptr, gsrc;     // inverse of the slot table: block -> its contributions (ascending)
+  DevBuf<double> ke;               // element-matrix scratch of the gather assembly
+  bool gather_valid = false;
   DevBuf<unsigned> slot;
   DevBuf<int> m_eni, m_enn, m_sec, m_form;
   DevBuf<double> m_node, m_sectD;

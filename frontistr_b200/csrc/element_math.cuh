@@ -32,15 +32,15 @@ constexpr double kTetB = 0.585410196624968;
 constexpr double kTetW = 0.041666666666667;         // quadrature.f90:236-238
 
 // per-warp scratch (doubles).  MAXN = nodes + enhanced modes, NGP Gauss points
-struct Scratch {
+struct alignas(16) Scratch {
+  double stage[100 * 9];    // gather-mode output staging: nn*nn blocks of 9 (tet10: 100 blocks); 16-byte aligned
   double xc[10 * 3];        // element coordinates, node-major
   double gd[8 * 11 * 3];    // gderiv[g][n][3]  (hex: 8 GP x 11; tet10: 4 GP x 10 fits as well)
   double bb[8 * 8 * 3];     // B-bar correction (Bbar - gderiv)/3 per GP,node (B-bar only)
   double wdet[8];           // weight * det per GP
-  double Kda[24 * 9];       // IC: K(d, alpha)
+  double Kda[24 * 10];      // IC: K(d, alpha), row stride 10 (16-byte aligned rows)
   double Kaa[9 * 9];        // IC: K(alpha, alpha) -> inverse, row-major [r][c]
-  double W[24 * 9];         // IC: Kda * Kaa^-1
-  double piv[16];           // IC: pivot bookkeeping
+  double W[24 * 10];        // IC: Kda * Kaa^-1, row stride 10
 };
 
 FB_HD void hex_shape_deriv(double x, double y, double z, double (*d)[3]) {
@@ -200,7 +200,7 @@ FB_HD void ic_phase_coupling(int lane, Scratch &S, double D11, double D12, doubl
     const int i = lane / 3, m = lane % 3;
     pair_block_iso<11, 8>(S, i, 8 + m, D11, D12, D44, k9);
     for (int a = 0; a < 3; a++)
-      for (int b = 0; b < 3; b++) S.Kda[(3 * i + a) * 9 + 3 * m + b] = k9[3 * a + b];
+      for (int b = 0; b < 3; b++) S.Kda[(3 * i + a) * 10 + 3 * m + b] = k9[3 * a + b];
   } else if (lane < 30) {
     const int pm[6] = {0, 0, 0, 1, 1, 2}, pn[6] = {0, 1, 2, 1, 2, 2};
     const int m = pm[lane - 24], n = pn[lane - 24];
@@ -213,75 +213,86 @@ FB_HD void ic_phase_coupling(int lane, Scratch &S, double D11, double D12, doubl
   }
 }
 
-// calInverse(9, Kaa) (utilities.f90:247-316), column-parallel over lanes 0..8.  The caller runs
-//   for K in 0..8: ic_inv_pivot(lane,S,K); sync; ic_inv_swap(lane,S,K); sync; ic_inv_elim_a(...); sync; ic_inv_elim_b(...); sync
-//   then ic_inv_unpermute on lane 0; sync.
-// piv[0..8] = IP(:), piv[9] = LR of the current step, piv[10] = PIVOT.
-FB_HD void ic_inv_init(int lane, Scratch &S) {
-  if (lane < 9) S.piv[lane] = (double)lane;
-}
-FB_HD void ic_inv_pivot(int lane, Scratch &S, int K) {
-  if (lane != 0) return;
+// ---- calInverse(9) (utilities.f90:247-316) with one matrix COLUMN per lane held in registers ---------
+// Lane c < 9 owns column c (a[0..8] = rows); values cross lanes only by broadcast / pairwise exchange, which
+// the CUDA kernel does with warp shuffles (assembly.cuh: ic_inverse_warp) and the host emulation with plain
+// arrays (emul_test.cpp).  K is always a compile-time constant after unrolling, so a[] stays in registers.
+// Same operations in the same order as the reference: partial (row) pivoting, IP bookkeeping, the W != 0
+// skips and the final column un-permutation "quirks included".
+FB_HD void gj_pivot_local(int K, const double (&a)[9], int &LR, double &pivot) {   // meaningful on lane K only
   double wmax = 0.0;
-  int LR = K;
-  for (int I = K; I < 9; I++) {
-    const double w = fabs(S.Kaa[I * 9 + K]);
-    if (w > wmax) { wmax = w; LR = I; }
-  }
-  S.piv[9] = (double)LR;
-  S.piv[10] = S.Kaa[LR * 9 + K];
-  if (LR != K) { const double t = S.piv[K]; S.piv[K] = S.piv[LR]; S.piv[LR] = t; }
+  LR = K;
+#pragma unroll
+  for (int I = 0; I < 9; I++)
+    if (I >= K) { const double w = fabs(a[I]); if (w > wmax) { wmax = w; LR = I; } }
+  pivot = 0.0;
+#pragma unroll
+  for (int I = 0; I < 9; I++) if (I == LR) pivot = a[I];
 }
-// lane c (<9) owns column c: row swap, scaling of row K, elimination
-FB_HD void ic_inv_step(int lane, Scratch &S, int K, const double *colK /* A(:,K) before this step, after the swap */) {
-  if (lane >= 9) return;
-  const int c = lane;
-  const double PIVOT = S.piv[10];
-  if (c == K) {
-    for (int I = 0; I < 9; I++)
-      if (I != K) { const double W = colK[I]; if (W != 0.0) S.Kaa[I * 9 + K] = -W / PIVOT; }
-    S.Kaa[K * 9 + K] = 1.0 / PIVOT;
-  } else {
-    const double akc = S.Kaa[K * 9 + c] / PIVOT;
-    S.Kaa[K * 9 + c] = akc;
-    for (int I = 0; I < 9; I++)
-      if (I != K) { const double W = colK[I]; if (W != 0.0) S.Kaa[I * 9 + c] = S.Kaa[I * 9 + c] - W * akc; }
-  }
-}
-FB_HD void ic_inv_swap(int lane, Scratch &S, int K) {
-  if (lane >= 9) return;
-  const int LR = (int)S.piv[9];
-  if (LR != K) { const double t = S.Kaa[K * 9 + lane]; S.Kaa[K * 9 + lane] = S.Kaa[LR * 9 + lane]; S.Kaa[LR * 9 + lane] = t; }
-}
-FB_HD void ic_inv_unpermute(int lane, Scratch &S) {
-  if (lane != 0) return;
-  int IP[9];
-  for (int I = 0; I < 9; I++) IP[I] = (int)S.piv[I];
-  for (int I = 0; I < 9; I++) {   // utilities.f90:301-314, quirks included
-    const int K = IP[I];
-    if (K != I) {
-      const int IW = IP[K]; IP[K] = IP[I]; IP[I] = IW;
-      for (int J = 0; J < 9; J++) { const double W = S.Kaa[J * 9 + I]; S.Kaa[J * 9 + I] = S.Kaa[J * 9 + K]; S.Kaa[J * 9 + K] = W; }
+FB_HD void gj_swap_rows(int K, int LR, double (&a)[9], int (&ip)[9]) {
+#pragma unroll
+  for (int I = 0; I < 9; I++)
+    if (I > K && I == LR) {
+      const double t = a[K]; a[K] = a[I]; a[I] = t;
+      const int q = ip[K]; ip[K] = ip[I]; ip[I] = q;
     }
+}
+// w[I] = A(I,K) after the row swap (column K, broadcast from lane K); w[K] is the pivot
+FB_HD void gj_update(int c, int K, double (&a)[9], const double (&w)[9]) {
+  const double PIVOT = w[K];
+  if (c == K) {
+#pragma unroll
+    for (int I = 0; I < 9; I++)
+      if (I != K) { if (w[I] != 0.0) a[I] = -w[I] / PIVOT; }
+    a[K] = 1.0 / PIVOT;
+  } else {
+    const double akc = a[K] / PIVOT;
+    a[K] = akc;
+#pragma unroll
+    for (int I = 0; I < 9; I++)
+      if (I != K) { if (w[I] != 0.0) a[I] = a[I] - w[I] * akc; }
   }
 }
+// un-permutation step I (utilities.f90:301-314): returns the column K to exchange with column I, or -1
+FB_HD int gj_unpermute_step(int I, int (&ip)[9]) {
+  int K = 0;
+#pragma unroll
+  for (int J = 0; J < 9; J++) if (J == I) K = ip[J];
+  if (K == I) return -1;
+  int IW = 0;
+#pragma unroll
+  for (int J = 0; J < 9; J++) if (J == K) IW = ip[J];
+#pragma unroll
+  for (int J = 0; J < 9; J++) if (J == K) ip[J] = K;   // IP(K) = IP(I) (= K)
+#pragma unroll
+  for (int J = 0; J < 9; J++) if (J == I) ip[J] = IW;
+  return K;
+}
+
 // W = Kda * Kaa^-1   (tmpk, static_LIB_3dIC.f90:212): 216 entries over 32 lanes
 FB_HD void ic_phase_W(int lane, Scratch &S) {
   for (int t = lane; t < 216; t += 32) {
     const int r = t / 9, c = t % 9;
     double s = 0.0;
-    for (int k = 0; k < 9; k++) s += S.Kda[r * 9 + k] * S.Kaa[k * 9 + c];
-    S.W[t] = s;
+    for (int k = 0; k < 9; k++) s += S.Kda[r * 10 + k] * S.Kaa[k * 9 + c];
+    S.W[r * 10 + c] = s;
   }
 }
-// K_ij -= W_i * Kad_j   (static_LIB_3dIC.f90:213; Kad = Kda^T by symmetry of D)
+// K_ij -= W_i * Kad_j   (static_LIB_3dIC.f90:213; Kad = Kda^T by symmetry of D).  The three Kda rows of
+// node j are read once; every W row once.
 FB_HD void ic_condense_block(const Scratch &S, int i, int j, double *k9) {
-  for (int a = 0; a < 3; a++)
+  double kd[3][9];
+  for (int b = 0; b < 3; b++)
+    for (int k = 0; k < 9; k++) kd[b][k] = S.Kda[(3 * j + b) * 10 + k];
+  for (int a = 0; a < 3; a++) {
+    double w[9];
+    for (int k = 0; k < 9; k++) w[k] = S.W[(3 * i + a) * 10 + k];
     for (int b = 0; b < 3; b++) {
       double s = 0.0;
-      for (int k = 0; k < 9; k++) s += S.W[(3 * i + a) * 9 + k] * S.Kda[(3 * j + b) * 9 + k];
+      for (int k = 0; k < 9; k++) s += w[k] * kd[b][k];
       k9[3 * a + b] -= s;
     }
+  }
 }
 
 // isotropic elastic constants, ElasticLinear.f90:48-59

@@ -10,6 +10,39 @@
 
 using namespace fb::elem;
 
+// calInverse(9) as the warp does it: one column per lane, shuffles replaced by array reads
+static void emul_inverse_warp(Scratch &S) {
+  double a[32][9];
+  int ip[32][9];
+  for (int lane = 0; lane < 32; lane++) {
+    const int c = lane < 9 ? lane : 8;
+    for (int I = 0; I < 9; I++) { a[lane][I] = S.Kaa[I * 9 + c]; ip[lane][I] = I; }
+  }
+  for (int K = 0; K < 9; K++) {
+    int LR[32];
+    double pv[32];
+    for (int lane = 0; lane < 32; lane++) gj_pivot_local(K, a[lane], LR[lane], pv[lane]);
+    for (int lane = 0; lane < 32; lane++) gj_swap_rows(K, LR[K], a[lane], ip[lane]);
+    double w[9];
+    for (int I = 0; I < 9; I++) w[I] = a[K][I];
+    for (int lane = 0; lane < 32; lane++) gj_update(lane < 9 ? lane : 8, K, a[lane], w);
+  }
+  for (int I = 0; I < 9; I++) {
+    int K = -1;
+    for (int lane = 0; lane < 32; lane++) K = gj_unpermute_step(I, ip[lane]);
+    if (K >= 0) {
+      double snap[32][9];
+      std::memcpy(snap, a, sizeof snap);
+      for (int lane = 0; lane < 32; lane++) {
+        const int other = (lane == I) ? K : ((lane == K) ? I : lane);
+        for (int r = 0; r < 9; r++) a[lane][r] = snap[other][r];
+      }
+    }
+  }
+  for (int lane = 0; lane < 9; lane++)
+    for (int I = 0; I < 9; I++) S.Kaa[I * 9 + lane] = a[lane][I];
+}
+
 template <int FORM>
 static void run_element(const double *ecoord /* (nn,3) */, double E, double nu, double *K /* (3nn,3nn) row-major */) {
   constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
@@ -35,16 +68,7 @@ static void run_element(const double *ecoord /* (nn,3) */, double E, double nu, 
     }
   if (FORM == FORM_IC) {
     for (int lane = 0; lane < 32; lane++) ic_phase_coupling(lane, S, D11, D12, D44);
-    for (int lane = 0; lane < 32; lane++) ic_inv_init(lane, S);
-    for (int Kk = 0; Kk < 9; Kk++) {
-      for (int lane = 0; lane < 32; lane++) ic_inv_pivot(lane, S, Kk);
-      for (int lane = 0; lane < 32; lane++) ic_inv_swap(lane, S, Kk);
-      double colK[32][9];
-      for (int lane = 0; lane < 32; lane++)
-        for (int I = 0; I < 9; I++) colK[lane][I] = S.Kaa[I * 9 + Kk];
-      for (int lane = 0; lane < 32; lane++) ic_inv_step(lane, S, Kk, colK[lane]);
-    }
-    for (int lane = 0; lane < 32; lane++) ic_inv_unpermute(lane, S);
+    emul_inverse_warp(S);
     for (int lane = 0; lane < 32; lane++) ic_phase_W(lane, S);
     for (int lane = 0; lane < 32; lane++)
       for (int r = 0; r < ROUNDS; r++) {
@@ -79,16 +103,7 @@ int fbemul_inverse9(double *A /* row-major 9x9, in place */) {
   Scratch S;
   std::memset(&S, 0, sizeof S);
   std::memcpy(S.Kaa, A, sizeof(double) * 81);
-  for (int lane = 0; lane < 32; lane++) ic_inv_init(lane, S);
-  for (int Kk = 0; Kk < 9; Kk++) {
-    for (int lane = 0; lane < 32; lane++) ic_inv_pivot(lane, S, Kk);
-    for (int lane = 0; lane < 32; lane++) ic_inv_swap(lane, S, Kk);
-    double colK[32][9];
-    for (int lane = 0; lane < 32; lane++)
-      for (int I = 0; I < 9; I++) colK[lane][I] = S.Kaa[I * 9 + Kk];
-    for (int lane = 0; lane < 32; lane++) ic_inv_step(lane, S, Kk, colK[lane]);
-  }
-  for (int lane = 0; lane < 32; lane++) ic_inv_unpermute(lane, S);
+  emul_inverse_warp(S);
   std::memcpy(A, S.Kaa, sizeof(double) * 81);
   return 0;
 }

@@ -40,6 +40,24 @@ def test_assembly_matches_oracle(gpu, name):
         assert np.abs(a - b).max() <= 1e-12 * scale, k
 
 
+@pytest.mark.parametrize("name", ["hex5_ic", "tet3", "hex_ragged"])
+def test_assembly_gather_equals_scatter_and_is_reproducible(gpu, name):
+    """The deterministic gather assembly (element matrices stored, each block sums its contributions in
+    ascending element order) against the atomic scatter-add path: same K to rounding; the gather result is
+    bit-identical from run to run."""
+    mesh = _meshes()[name]()
+    cnt = util.cube_cnt()
+    Ks = {}
+    for mode in (1, 0, 1):
+        gpu.set_option("asm_gather", mode)
+        A = util.product_problem(gpu, mesh, cnt, to_host=True, apply_bc=False)
+        Ks.setdefault(mode, []).append(np.concatenate([A.D, A.AL, A.AU]))
+    gpu.set_option("asm_gather", 1)
+    assert np.array_equal(Ks[1][0], Ks[1][1])
+    scale = np.abs(Ks[0][0]).max()
+    assert np.abs(Ks[1][0] - Ks[0][0]).max() <= 1e-13 * scale
+
+
 def test_assembly_golden_decks(gpu):
     for name in ("A361", "A342"):
         mesh, cnt, _ = util.load_golden_mesh(name)
@@ -175,7 +193,8 @@ def test_solve_matches_oracle(gpu, meshname, precond, fused):
     # residual histories: identical to 1e-8 early on, then rounding differences of the dot products grow
     n = min(len(r["hist"]), len(ro["hist"])) - 3
     assert np.allclose(r["hist"][:40], ro["hist"][:40], rtol=1e-8)
-    assert np.allclose(r["hist"][:n], ro["hist"][:n], rtol=5e-2)
+    assert np.allclose(r["hist"][: n // 2], ro["hist"][: n // 2], rtol=1e-3)
+    assert np.allclose(r["hist"][:n], ro["hist"][:n], rtol=0.25)    # tail: same decay, rounding has decorrelated
 
 
 def test_solve_iterpremax2(gpu):
