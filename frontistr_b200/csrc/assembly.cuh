@@ -103,44 +103,6 @@ gather_sum_kernel(size_t nblk, const unsigned *__restrict__ gptr, const unsigned
   }
 }
 
-// calInverse(9, Kaa) for the IC condensation: column c of Kaa in the registers of lane c, cross-lane traffic by
-// warp shuffles only (per-lane steps: element_math.cuh gj_*).  Reads S.Kaa, writes the inverse back to S.Kaa.
-__device__ __forceinline__ void ic_inverse_warp(int lane, elem::Scratch &S) {
-  using namespace elem;
-  constexpr unsigned FULL = 0xffffffffu;
-  const int c = (lane < 9) ? lane : 8;      // lanes >= 9 shadow column 8 (results discarded)
-  double a[9];
-  int ip[9];
-#pragma unroll
-  for (int I = 0; I < 9; I++) { a[I] = S.Kaa[I * 9 + c]; ip[I] = I; }
-#pragma unroll
-  for (int K = 0; K < 9; K++) {
-    int LR;
-    double pivot;
-    gj_pivot_local(K, a, LR, pivot);
-    LR = __shfl_sync(FULL, LR, K);
-    gj_swap_rows(K, LR, a, ip);
-    double w[9];
-#pragma unroll
-    for (int I = 0; I < 9; I++) w[I] = __shfl_sync(FULL, a[I], K);
-    gj_update(c, K, a, w);
-  }
-#pragma unroll
-  for (int I = 0; I < 9; I++) {
-    const int K = gj_unpermute_step(I, ip);   // warp-uniform (ip is identical in every lane)
-    if (K >= 0) {
-      const int other = (lane == I) ? K : ((lane == K) ? I : lane);
-#pragma unroll
-      for (int r = 0; r < 9; r++) a[r] = __shfl_sync(FULL, a[r], other);
-    }
-  }
-  __syncwarp();
-  if (lane < 9) {
-#pragma unroll
-    for (int I = 0; I < 9; I++) S.Kaa[I * 9 + lane] = a[I];
-  }
-}
-
 // One element per warp.  sect[3*s..] = D11, D12, D44 of section s; sect_form[s] = elemopt361.
 template <int FORM, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
@@ -184,7 +146,7 @@ stiff_kernel(int e0, int e1, const int *__restrict__ elem_node_index, const int 
     if (FORM == FORM_IC && !(probe & 2)) {
       ic_phase_coupling(lane, S, D11, D12, D44);
       __syncwarp();
-      ic_inverse_warp(lane, S);
+      elem::ic_inverse_warp(lane, S);
       __syncwarp();
       ic_phase_W(lane, S);
       __syncwarp();

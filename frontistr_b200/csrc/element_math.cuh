@@ -21,6 +21,24 @@
 #define FB_HD inline
 #endif
 
+// Warp collectives used by the element code.  In the CUDA kernels they are the hardware shuffles; the
+// TEST-ONLY host emulation (emul_test.cpp) defines FB_EMUL_WARP and supplies lock-step versions (32 host
+// threads + barriers), so the very same source is what the CPU unit tests execute.
+#if defined(FB_EMUL_WARP)
+namespace fb { namespace emulwarp {
+double shfl(double v, int src);
+int shfl(int v, int src);
+void syncwarp();
+} }
+#define FB_WARP_FN inline
+#define FB_SHFL(v, src) fb::emulwarp::shfl((v), (src))
+#define FB_SYNCWARP() fb::emulwarp::syncwarp()
+#elif defined(__CUDACC__)
+#define FB_WARP_FN __device__ __forceinline__
+#define FB_SHFL(v, src) __shfl_sync(0xffffffffu, (v), (src))
+#define FB_SYNCWARP() __syncwarp()
+#endif
+
 namespace fb {
 namespace elem {
 
@@ -268,6 +286,45 @@ FB_HD int gj_unpermute_step(int I, int (&ip)[9]) {
   for (int J = 0; J < 9; J++) if (J == I) ip[J] = IW;
   return K;
 }
+
+#ifdef FB_WARP_FN
+// calInverse(9, Kaa) for the IC condensation, executed by all 32 lanes of the warp that owns the element:
+// column c of Kaa in the registers of lane c, cross-lane traffic by warp shuffles only.  Reads S.Kaa, writes
+// the inverse back to S.Kaa.
+FB_WARP_FN void ic_inverse_warp(int lane, Scratch &S) {
+  const int c = (lane < 9) ? lane : 8;      // lanes >= 9 shadow column 8 (results discarded)
+  double a[9];
+  int ip[9];
+#pragma unroll
+  for (int I = 0; I < 9; I++) { a[I] = S.Kaa[I * 9 + c]; ip[I] = I; }
+#pragma unroll
+  for (int K = 0; K < 9; K++) {
+    int LR;
+    double pivot;
+    gj_pivot_local(K, a, LR, pivot);
+    LR = FB_SHFL(LR, K);
+    gj_swap_rows(K, LR, a, ip);
+    double w[9];
+#pragma unroll
+    for (int I = 0; I < 9; I++) w[I] = FB_SHFL(a[I], K);
+    gj_update(c, K, a, w);
+  }
+#pragma unroll
+  for (int I = 0; I < 9; I++) {
+    const int K = gj_unpermute_step(I, ip);   // warp-uniform (ip is identical in every lane)
+    if (K >= 0) {
+      const int other = (lane == I) ? K : ((lane == K) ? I : lane);
+#pragma unroll
+      for (int r = 0; r < 9; r++) a[r] = FB_SHFL(a[r], other);
+    }
+  }
+  FB_SYNCWARP();
+  if (lane < 9) {
+#pragma unroll
+    for (int I = 0; I < 9; I++) S.Kaa[I * 9 + lane] = a[I];
+  }
+}
+#endif
 
 // W = Kda * Kaa^-1   (tmpk, static_LIB_3dIC.f90:212): 216 entries over 32 lanes
 FB_HD void ic_phase_W(int lane, Scratch &S) {

@@ -3,44 +3,51 @@
 // with the warp barriers of the CUDA kernel becoming loop boundaries, so the CPU unit tests can check
 // the element algebra against the oracle without a GPU.  Built as libfistr_b200_emul.so; the product
 // library never links it and no product entry point can reach it.
+#include <pthread.h>
+
 #include <cstring>
+#include <thread>
 #include <vector>
 
+#define FB_EMUL_WARP 1
 #include "element_math.cuh"
 
 using namespace fb::elem;
 
-// calInverse(9) as the warp does it: one column per lane, shuffles replaced by array reads
+// ---- lock-step warp emulation: 32 host threads, every collective is a barrier-separated exchange -----
+namespace fb { namespace emulwarp {
+static pthread_barrier_t g_bar;
+static thread_local int t_lane = 0;
+static double g_slot_d[32];
+static int g_slot_i[32];
+double shfl(double v, int src) {
+  g_slot_d[t_lane] = v;
+  pthread_barrier_wait(&g_bar);
+  const double r = g_slot_d[src & 31];
+  pthread_barrier_wait(&g_bar);
+  return r;
+}
+int shfl(int v, int src) {
+  g_slot_i[t_lane] = v;
+  pthread_barrier_wait(&g_bar);
+  const int r = g_slot_i[src & 31];
+  pthread_barrier_wait(&g_bar);
+  return r;
+}
+void syncwarp() { pthread_barrier_wait(&g_bar); }
+template <class F>
+static void run_warp(F f) {   // f(lane) on 32 threads in lock step
+  pthread_barrier_init(&g_bar, nullptr, 32);
+  std::vector<std::thread> th;
+  for (int lane = 0; lane < 32; lane++) th.emplace_back([lane, &f]() { t_lane = lane; f(lane); });
+  for (auto &t : th) t.join();
+  pthread_barrier_destroy(&g_bar);
+}
+} }
+
+// calInverse(9) exactly as the CUDA warp executes it (same source: element_math.cuh ic_inverse_warp)
 static void emul_inverse_warp(Scratch &S) {
-  double a[32][9];
-  int ip[32][9];
-  for (int lane = 0; lane < 32; lane++) {
-    const int c = lane < 9 ? lane : 8;
-    for (int I = 0; I < 9; I++) { a[lane][I] = S.Kaa[I * 9 + c]; ip[lane][I] = I; }
-  }
-  for (int K = 0; K < 9; K++) {
-    int LR[32];
-    double pv[32];
-    for (int lane = 0; lane < 32; lane++) gj_pivot_local(K, a[lane], LR[lane], pv[lane]);
-    for (int lane = 0; lane < 32; lane++) gj_swap_rows(K, LR[K], a[lane], ip[lane]);
-    double w[9];
-    for (int I = 0; I < 9; I++) w[I] = a[K][I];
-    for (int lane = 0; lane < 32; lane++) gj_update(lane < 9 ? lane : 8, K, a[lane], w);
-  }
-  for (int I = 0; I < 9; I++) {
-    int K = -1;
-    for (int lane = 0; lane < 32; lane++) K = gj_unpermute_step(I, ip[lane]);
-    if (K >= 0) {
-      double snap[32][9];
-      std::memcpy(snap, a, sizeof snap);
-      for (int lane = 0; lane < 32; lane++) {
-        const int other = (lane == I) ? K : ((lane == K) ? I : lane);
-        for (int r = 0; r < 9; r++) a[lane][r] = snap[other][r];
-      }
-    }
-  }
-  for (int lane = 0; lane < 9; lane++)
-    for (int I = 0; I < 9; I++) S.Kaa[I * 9 + lane] = a[lane][I];
+  fb::emulwarp::run_warp([&S](int lane) { ic_inverse_warp(lane, S); });
 }
 
 template <int FORM>
