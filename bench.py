@@ -56,8 +56,10 @@ def parse_args():
     ap.add_argument("--ref-iters", type=int, default=0, help="CG iterations per reference-arm step (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
-                    help="N>1: halo exchange + dot-product all-reduce by peer-memory stores from the CG kernels (default) or NCCL")
+    ap.add_argument("--comm", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="N>1 transport of the halo exchange + dot-product all-reduce: peer-memory stores issued by the CG "
+                         "kernels (p2p) or NCCL.  auto = p2p at N=2 (the configuration it was validated on a B200 box), "
+                         "NCCL at N=4/8 (validated at N=8)")
     return ap.parse_args()
 
 
@@ -237,7 +239,8 @@ def run_b200(args):
 
     hecmw.init(local_rank)
     if world > 1:
-        hecmw.set_option("p2p", 1 if args.comm == "p2p" else 0)
+        use_p2p = args.comm == "p2p" or (args.comm == "auto" and world == 2)
+        hecmw.set_option("p2p", 1 if use_p2p else 0)
         hecmw.comm_init_from_torch()
     dev = hecmw.device_info()
 

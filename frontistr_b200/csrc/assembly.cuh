@@ -114,7 +114,6 @@ stiff_kernel(int e0, int e1, const int *__restrict__ elem_node_index, const int 
   // probe (development timing switches, 0 in production): 1 = no scatter, 2 = no IC condensation
   using namespace elem;
   constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
-  constexpr int NGP = (FORM == FORM_TET10) ? 4 : 8;
   constexpr int NB = NN * NN;
   constexpr int ROUNDS = (NB + 31) / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -132,30 +131,8 @@ stiff_kernel(int e0, int e1, const int *__restrict__ elem_node_index, const int 
       S.xc[3 * lane] = node[n3]; S.xc[3 * lane + 1] = node[n3 + 1]; S.xc[3 * lane + 2] = node[n3 + 2];
     }
     __syncwarp();
-    phase_geometry<FORM>(lane, S);
-    __syncwarp();
     double kb[ROUNDS][9];
-#pragma unroll
-    for (int r = 0; r < ROUNDS; r++) {
-      const int t = r * 32 + lane;
-      if (t < NB) {
-        if (FORM == FORM_BBAR) pair_block_bbar(S, t / NN, t % NN, D11, D12, D44, kb[r]);
-        else pair_block_iso<(FORM == FORM_IC) ? 11 : NN, NGP>(S, t / NN, t % NN, D11, D12, D44, kb[r]);
-      }
-    }
-    if (FORM == FORM_IC && !(probe & 2)) {
-      ic_phase_coupling(lane, S, D11, D12, D44);
-      __syncwarp();
-      elem::ic_inverse_warp(lane, S);
-      __syncwarp();
-      ic_phase_W(lane, S);
-      __syncwarp();
-#pragma unroll
-      for (int r = 0; r < ROUNDS; r++) {
-        const int t = r * 32 + lane;
-        if (t < NB) ic_condense_block(S, t / NN, t % NN, kb[r]);
-      }
-    }
+    element_stiffness_warp<FORM>(lane, S, D11, D12, D44, kb, !(probe & 2));
     if (probe & 1) {
       double sum = 0.0;
 #pragma unroll

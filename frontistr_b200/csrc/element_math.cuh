@@ -352,6 +352,44 @@ FB_HD void ic_condense_block(const Scratch &S, int i, int j, double *k9) {
   }
 }
 
+#ifdef FB_WARP_FN
+// The whole element: executed by the 32 lanes of one warp after S.xc holds the element coordinates (and the
+// warp has synchronised).  On return lane `l` holds in kb[r] the 3x3 block t = 32 r + l (i = t / nn, j = t % nn)
+// of the element stiffness matrix.  This is the body of assembly.cuh:stiff_kernel AND of the host emulation.
+template <int FORM>
+FB_WARP_FN void element_stiffness_warp(int lane, Scratch &S, double D11, double D12, double D44,
+                                       double (&kb)[((FORM == FORM_TET10 ? 100 : 64) + 31) / 32][9],
+                                       bool condense = true) {
+  constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
+  constexpr int NGP = (FORM == FORM_TET10) ? 4 : 8;
+  constexpr int NB = NN * NN;
+  constexpr int ROUNDS = (NB + 31) / 32;
+  phase_geometry<FORM>(lane, S);
+  FB_SYNCWARP();
+#pragma unroll
+  for (int r = 0; r < ROUNDS; r++) {
+    const int t = r * 32 + lane;
+    if (t < NB) {
+      if (FORM == FORM_BBAR) pair_block_bbar(S, t / NN, t % NN, D11, D12, D44, kb[r]);
+      else pair_block_iso<(FORM == FORM_IC) ? 11 : NN, NGP>(S, t / NN, t % NN, D11, D12, D44, kb[r]);
+    }
+  }
+  if (FORM == FORM_IC && condense) {
+    ic_phase_coupling(lane, S, D11, D12, D44);
+    FB_SYNCWARP();
+    ic_inverse_warp(lane, S);
+    FB_SYNCWARP();
+    ic_phase_W(lane, S);
+    FB_SYNCWARP();
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+      const int t = r * 32 + lane;
+      if (t < NB) ic_condense_block(S, t / NN, t % NN, kb[r]);
+    }
+  }
+}
+#endif
+
 // isotropic elastic constants, ElasticLinear.f90:48-59
 FB_HD void elastic_constants(double EE, double PP, double &D11, double &D12, double &D44) {
   D11 = EE * (1.0 - PP) / (1.0 - 2.0 * PP) / (1.0 + PP);

@@ -53,44 +53,26 @@ static void emul_inverse_warp(Scratch &S) {
 template <int FORM>
 static void run_element(const double *ecoord /* (nn,3) */, double E, double nu, double *K /* (3nn,3nn) row-major */) {
   constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
-  constexpr int NGP = (FORM == FORM_TET10) ? 4 : 8;
   constexpr int NB = NN * NN;
   constexpr int ROUNDS = (NB + 31) / 32;
-  Scratch S;
+  static Scratch S;
   std::memset(&S, 0, sizeof S);
   double D11, D12, D44;
   elastic_constants(E, nu, D11, D12, D44);
+  // what stiff_kernel does before the body: lanes < nn fetch the coordinates, then the warp synchronises
   for (int lane = 0; lane < NN; lane++)
     for (int d = 0; d < 3; d++) S.xc[3 * lane + d] = ecoord[3 * lane + d];
-  for (int lane = 0; lane < 32; lane++) phase_geometry<FORM>(lane, S);
-  std::vector<double> kb(32 * ROUNDS * 9, 0.0);
-  for (int lane = 0; lane < 32; lane++)
-    for (int r = 0; r < ROUNDS; r++) {
-      const int t = r * 32 + lane;
-      if (t < NB) {
-        double *k9 = &kb[(lane * ROUNDS + r) * 9];
-        if (FORM == FORM_BBAR) pair_block_bbar(S, t / NN, t % NN, D11, D12, D44, k9);
-        else pair_block_iso<(FORM == FORM_IC) ? 11 : NN, NGP>(S, t / NN, t % NN, D11, D12, D44, k9);
-      }
-    }
-  if (FORM == FORM_IC) {
-    for (int lane = 0; lane < 32; lane++) ic_phase_coupling(lane, S, D11, D12, D44);
-    emul_inverse_warp(S);
-    for (int lane = 0; lane < 32; lane++) ic_phase_W(lane, S);
-    for (int lane = 0; lane < 32; lane++)
-      for (int r = 0; r < ROUNDS; r++) {
-        const int t = r * 32 + lane;
-        if (t < NB) ic_condense_block(S, t / NN, t % NN, &kb[(lane * ROUNDS + r) * 9]);
-      }
-  }
-  for (int lane = 0; lane < 32; lane++)
+  fb::emulwarp::run_warp([&](int lane) {
+    double kb[ROUNDS][9];
+    element_stiffness_warp<FORM>(lane, S, D11, D12, D44, kb);
     for (int r = 0; r < ROUNDS; r++) {
       const int t = r * 32 + lane;
       if (t >= NB) continue;
       const int i = t / NN, j = t % NN;
       for (int a = 0; a < 3; a++)
-        for (int b = 0; b < 3; b++) K[(3 * i + a) * (3 * NN) + 3 * j + b] = kb[(lane * ROUNDS + r) * 9 + 3 * a + b];
+        for (int b = 0; b < 3; b++) K[(3 * i + a) * (3 * NN) + 3 * j + b] = kb[r][3 * a + b];
     }
+  });
 }
 
 extern "C" {
