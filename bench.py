@@ -323,37 +323,45 @@ def run_b200(args):
     # ---- end-to-end arm: host hecMAT through the C-ABI, copies inside the timed region -------------
     e2e = None
     if not args.no_e2e:
-        hecmw.mat_download(A, values=True, rhs=True)
-        hecmw.host_register(A.D, A.AL, A.AU, A.B, A.X)
-        A.Iarray[97] = 0
-        r2 = timed_block(False, args.steps, max(1, min(args.warmup, 3)))
-        h2d = 8 * (A.D.size + A.AL.size + A.AU.size + A.B.size + A.X.size)
-        d2h = 8 * A.X.size
-        e2e = {"value": r2["iters"] / r2["wall_s"], "unit": UNIT, "h2d_bytes_per_step": int(allsum(h2d)),
-               "d2h_bytes_per_step": int(allsum(d2h)), "ms_per_step": 1e3 * r2["wall_s"] / args.steps,
-               "device_ms_per_step": 1e3 * r2["ev_s"] / args.steps,
-               "what": "fistr_b200_solve_33 with pinned host D/AL/AU/B/X: upload + SELL repack + precond set-up + "
-                       "CG + X download per step, wall clock between barriers"}
+        try:
+            hecmw.mat_download(A, values=True, rhs=True)
+            hecmw.host_register(A.D, A.AL, A.AU, A.B, A.X)
+            A.Iarray[97] = 0
+            r2 = timed_block(False, args.steps, max(1, min(args.warmup, 3)))
+            h2d = 8 * (A.D.size + A.AL.size + A.AU.size + A.B.size + A.X.size)
+            d2h = 8 * A.X.size
+            e2e = {"value": r2["iters"] / r2["wall_s"], "unit": UNIT, "h2d_bytes_per_step": int(allsum(h2d)),
+                   "d2h_bytes_per_step": int(allsum(d2h)), "ms_per_step": 1e3 * r2["wall_s"] / args.steps,
+                   "device_ms_per_step": 1e3 * r2["ev_s"] / args.steps,
+                   "what": "fistr_b200_solve_33 with pinned host D/AL/AU/B/X: upload + SELL repack + precond set-up + "
+                           "CG + X download per step, wall clock between barriers"}
+        except Exception as exc:      # the device-resident line above is still valid; say why e2e is missing
+            if world > 1:
+                raise                  # collective: do not leave the other ranks waiting
+            e2e = {"value": None, "unit": UNIT, "error": "%s: %s" % (type(exc).__name__, exc)}
     # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample of the same system ---------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import oracle as orc
-        if A.D is None or args.no_e2e:
-            hecmw.mat_download(A, values=True, rhs=True)
-        Ao = A                      # the oracle reads the host copy of the very same system
-        keep_I = A.Iarray.copy()
-        Ao.Iarray[0] = 2; Ao.X[:] = 0.0
-        orc.precond_clear()
-        r0 = orc.solve(mesh, Ao)
-        per_it = max(float(r0["times"][1]) / 2.0, 1e-4)
-        iters = int(min(400, max(4, round(15.0 / per_it))))
-        Ao.Iarray[0] = iters; Ao.X[:] = 0.0; Ao.Iarray[96] = 1
-        orc.precond_clear()
-        r1 = orc.solve(mesh, Ao)
-        cpu = {"value": iters / float(r1["times"][1]), "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
-               "sample": "%d CG+DIAG iterations (MAXIT-bounded) of the same %d-DOF system, OpenMP oracle, solver-loop "
-                         "time %.1f s" % (iters, 3 * A.N, float(r1["times"][1]))}
-        A.Iarray[:] = keep_I
+        try:
+            from oracle import oracle as orc
+            if A.D is None or args.no_e2e:
+                hecmw.mat_download(A, values=True, rhs=True)
+            Ao = A                      # the oracle reads the host copy of the very same system
+            keep_I = A.Iarray.copy()
+            Ao.Iarray[0] = 2; Ao.X[:] = 0.0
+            orc.precond_clear()
+            r0 = orc.solve(mesh, Ao)
+            per_it = max(float(r0["times"][1]) / 2.0, 1e-4)
+            iters = int(min(400, max(4, round(15.0 / per_it))))
+            Ao.Iarray[0] = iters; Ao.X[:] = 0.0; Ao.Iarray[96] = 1
+            orc.precond_clear()
+            r1 = orc.solve(mesh, Ao)
+            cpu = {"value": iters / float(r1["times"][1]), "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+                   "sample": "%d CG+DIAG iterations (MAXIT-bounded) of the same %d-DOF system, OpenMP oracle, solver-loop "
+                             "time %.1f s" % (iters, 3 * A.N, float(r1["times"][1]))}
+            A.Iarray[:] = keep_I
+        except Exception as exc:
+            cpu = {"value": None, "unit": UNIT, "error": "%s: %s" % (type(exc).__name__, exc)}
     if rank == 0:
         last = res["last"]
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
