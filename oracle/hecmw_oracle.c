@@ -1311,3 +1311,254 @@ int orc_solve(int ndom, const orc_mesh *meshes, orc_matrix *mats, int *iter_out,
 }
 
 void orc_precond_clear(void) { precond_clear_all(); }
+
+/* =============================================================================================
+ * Geometrically nonlinear static analysis, total Lagrangian, linear elastic (St.Venant-Kirchhoff) material:
+ * the path `!STATIC, TYPE=NLGEOM` takes for element types 361 (B-bar, the default under NLGEOM:
+ * fistr1/src/common/fstr_setup.f90:364-379) and 342.  SURVEY §8(f) rank 2 — restated here first so that the
+ * Newton loop is pinned against the reference's golden logs (examples/static/exI) before any GPU kernel exists.
+ * ============================================================================================= */
+
+/* BL = BL0 + BL1, static_LIB_3d.f90:120-160 / static_LIB_C3D8.f90:100-156.  gdd = dudx(i,j), 0-based [i][j].
+ * Bbar != NULL selects the B-bar rows 1..3 (static_LIB_C3D8.f90:103-118). */
+static void fill_B_TL(int nn, double gderiv[][3], double (*Bbar)[3], double gdd[3][3], int with_BL1, double *B) {
+#define Bm(i, j) B[((j)-1) * 6 + ((i)-1)]
+  memset(B, 0, sizeof(double) * 6 * 3 * nn);
+  for (int j = 1; j <= nn; j++) {
+    const double g1 = gderiv[j - 1][0], g2 = gderiv[j - 1][1], g3 = gderiv[j - 1][2];
+    if (Bbar) {
+      const double B4 = (Bbar[j - 1][0] - g1) / 3.0, B6 = (Bbar[j - 1][1] - g2) / 3.0, B8 = (Bbar[j - 1][2] - g3) / 3.0;
+      Bm(1, 3 * j - 2) = g1 + B4; Bm(1, 3 * j - 1) = B6; Bm(1, 3 * j) = B8;
+      Bm(2, 3 * j - 2) = B4; Bm(2, 3 * j - 1) = g2 + B6; Bm(2, 3 * j) = B8;
+      Bm(3, 3 * j - 2) = B4; Bm(3, 3 * j - 1) = B6; Bm(3, 3 * j) = g3 + B8;
+    } else {
+      Bm(1, 3 * j - 2) = g1; Bm(2, 3 * j - 1) = g2; Bm(3, 3 * j) = g3;
+    }
+    Bm(4, 3 * j - 2) = g2; Bm(4, 3 * j - 1) = g1;
+    Bm(5, 3 * j - 1) = g3; Bm(5, 3 * j) = g2;
+    Bm(6, 3 * j - 2) = g3; Bm(6, 3 * j) = g1;
+    if (with_BL1) {
+      for (int c = 1; c <= 3; c++) { /* column 3j-3+c <-> displacement component c */
+        const double d1 = gdd[c - 1][0], d2 = gdd[c - 1][1], d3 = gdd[c - 1][2]; /* gdispderiv(c,1..3) */
+        Bm(1, 3 * j - 3 + c) += d1 * g1;
+        Bm(2, 3 * j - 3 + c) += d2 * g2;
+        Bm(3, 3 * j - 3 + c) += d3 * g3;
+        Bm(4, 3 * j - 3 + c) += d2 * g1 + d1 * g2;
+        Bm(5, 3 * j - 3 + c) += d2 * g3 + d3 * g2;
+        Bm(6, 3 * j - 3 + c) += d3 * g1 + d1 * g3;
+      }
+    }
+  }
+#undef Bm
+}
+
+/* gdispderiv = u(3,nn) * gderiv(nn,3) */
+static void disp_gradient(int nn, const double *u /* (3,nn) col-major */, double gderiv[][3], double gdd[3][3]) {
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double s = 0.0;
+      for (int n = 0; n < nn; n++) s += u[3 * n + i] * gderiv[n][j];
+      gdd[i][j] = s;
+    }
+}
+
+/* STF_C3 / STF_C3D8Bbar with flag == TOTALLAG: material + initial-stress stiffness.
+ * u = unode + dunode (fstr_StiffMatrix.f90:66-72), stress(6,ngp) = 2nd Piola-Kirchhoff at the Gauss points. */
+void orc_STF_C3_TL(int etype, int nn, const double *ecoord, const double *u, const double *stress, double E,
+                   double nu, int bbar, double *stiff) {
+  double D[6][6], B[6 * 30], gderiv[20][3], Bbar[20][3], gdd[3][3], det, wg, nc[3] = {0, 0, 0};
+  const int m = 3 * nn;
+  memset(stiff, 0, sizeof(double) * m * m);
+  if (bbar) get_global_deriv(etype, nn, nc, ecoord, &det, Bbar);
+  for (int LX = 1; LX <= num_quad_points(etype); LX++) {
+    get_quad_point(etype, LX, nc);
+    get_global_deriv(etype, nn, nc, ecoord, &det, gderiv);
+    cal_elastic_matrix(E, nu, D);
+    wg = get_weight(etype, LX) * det;
+    disp_gradient(nn, u, gderiv, gdd);
+    fill_B_TL(nn, gderiv, bbar ? Bbar : NULL, gdd, 1, B);
+    add_BtDB(m, B, D, wg, stiff, m);
+    /* initial stress matrix BN^T S BN, static_LIB_3d.f90:170-201: couples equal dof of nodes i,j with
+     * g_i^T [S] g_j where [S] is the 3x3 stress tensor */
+    const double *s = stress + 6 * (LX - 1);
+    const double S[3][3] = {{s[0], s[3], s[5]}, {s[3], s[1], s[4]}, {s[5], s[4], s[2]}};
+    for (int j = 0; j < nn; j++)
+      for (int i = 0; i < nn; i++) {
+        double v = 0.0;
+        for (int a = 0; a < 3; a++)
+          for (int b = 0; b < 3; b++) v += gderiv[i][a] * S[a][b] * gderiv[j][b];
+        for (int c = 0; c < 3; c++) stiff[(size_t)(3 * j + c) * m + 3 * i + c] += v * wg;
+      }
+  }
+}
+
+/* UPDATE_C3 (static_LIB_3d.f90:516-837) / Update_C3D8Bbar (static_LIB_C3D8.f90:203-552), flag == TOTALLAG,
+ * elastic: Green-Lagrange strain, S = D E, qf = sum_gp BL^T S wg.  u = unode, du = dunode. */
+void orc_UPDATE_C3_TL(int etype, int nn, const double *ecoord, const double *u, const double *du, double E,
+                      double nu, int bbar, double *qf, double *strain, double *stress) {
+  double D[6][6], B[6 * 30], gderiv[20][3], Bbar[20][3], gdd[3][3], tot[3 * 20], det, wg, nc[3] = {0, 0, 0};
+  const int m = 3 * nn;
+  double vol0 = 0.0;
+  memset(qf, 0, sizeof(double) * m);
+  for (int k = 0; k < m; k++) tot[k] = u[k] + du[k];
+  if (bbar) { /* dilatation at centroid, static_LIB_C3D8.f90:268-272 */
+    double dd[3][3];
+    get_global_deriv(etype, nn, nc, ecoord, &det, Bbar);
+    disp_gradient(nn, tot, Bbar, dd);
+    vol0 = (dd[0][0] + dd[1][1] + dd[2][2]) / 3.0;
+  }
+  for (int LX = 1; LX <= num_quad_points(etype); LX++) {
+    get_quad_point(etype, LX, nc);
+    get_global_deriv(etype, nn, nc, ecoord, &det, gderiv);
+    disp_gradient(nn, tot, gderiv, gdd);
+    const double dvol = bbar ? vol0 - (gdd[0][0] + gdd[1][1] + gdd[2][2]) / 3.0 : 0.0;
+    cal_elastic_matrix(E, nu, D);
+    double e[6];
+    e[0] = gdd[0][0] + dvol; e[1] = gdd[1][1] + dvol; e[2] = gdd[2][2] + dvol;
+    e[3] = gdd[0][1] + gdd[1][0]; e[4] = gdd[1][2] + gdd[2][1]; e[5] = gdd[2][0] + gdd[0][2];
+    /* Green-Lagrange strain */
+    e[0] += 0.5 * (gdd[0][0] * gdd[0][0] + gdd[1][0] * gdd[1][0] + gdd[2][0] * gdd[2][0]);
+    e[1] += 0.5 * (gdd[0][1] * gdd[0][1] + gdd[1][1] * gdd[1][1] + gdd[2][1] * gdd[2][1]);
+    e[2] += 0.5 * (gdd[0][2] * gdd[0][2] + gdd[1][2] * gdd[1][2] + gdd[2][2] * gdd[2][2]);
+    e[3] += gdd[0][0] * gdd[0][1] + gdd[1][0] * gdd[1][1] + gdd[2][0] * gdd[2][1];
+    e[4] += gdd[0][1] * gdd[0][2] + gdd[1][1] * gdd[1][2] + gdd[2][1] * gdd[2][2];
+    e[5] += gdd[0][0] * gdd[0][2] + gdd[1][0] * gdd[1][2] + gdd[2][0] * gdd[2][2];
+    double *eo = strain + 6 * (LX - 1), *so = stress + 6 * (LX - 1);
+    for (int i = 0; i < 6; i++) {
+      double s = 0.0;
+      for (int k = 0; k < 6; k++) s += D[i][k] * e[k];
+      eo[i] = e[i];
+      so[i] = s;
+    }
+    fill_B_TL(nn, gderiv, bbar ? Bbar : NULL, gdd, 1, B);
+    wg = get_weight(etype, LX) * det;
+    for (int j = 0; j < m; j++) {
+      double s = 0.0;
+      for (int k = 0; k < 6; k++) s += so[k] * B[j * 6 + k];
+      qf[j] += s * wg;
+    }
+  }
+}
+
+/* fstr_solve_NLGEOM + fstr_Newton (analysis/static/fstr_solve_NLGEOM.f90:84-160, fstr_solve_NonLinear.f90:29-167)
+ * for ONE loading step of `substeps` equal sub-steps, no amplitude table, single subdomain.
+ * Element option for 361: B-bar (the NLGEOM default) when sections[].elemopt361 == 2, full integration when 1.
+ * Returns 0, or -1 "Fail to Converge", -2 unsupported element option, >0 solver code. */
+int orc_nlgeom_static(const orc_mesh *mesh, const orc_section *sections, orc_matrix *mat, int nbc,
+                      const int *bc_node, const int *bc_dof, const double *bc_val, int ncl, const int *cl_node,
+                      const int *cl_dof, const double *cl_val, int substeps, double converg, int max_iter,
+                      double *unode, double *unode_steps /* [substeps][3*n_node] or NULL */,
+                      int *newton_iters /* [substeps] */, int *cg_iters_total) {
+  const int NP = mesh->n_node, n3 = 3 * NP, n_elem = mesh->n_elem;
+  const double maxres = 1.0e10; /* m_step.f90:78 */
+  double *dunode = calloc(n3, sizeof(double)), *GL = calloc(n3, sizeof(double)), *QF = calloc(n3, sizeof(double));
+  double *gstrain = calloc((size_t)n_elem * 8 * 6, sizeof(double)), *gstress = calloc((size_t)n_elem * 8 * 6, sizeof(double));
+  int rc = 0, cg_total = 0;
+  memset(unode, 0, sizeof(double) * n3);
+  double time = 0.0;
+  const double dt = 1.0 / substeps; /* fstr_ctrl_common.f90:224 */
+  for (int sub = 1; sub <= substeps && rc == 0; sub++) {
+    double f1 = time / 1.0, f2 = (time + dt) / 1.0; /* table_nlsta, no amplitude */
+    if (f1 > 1.0) f1 = 1.0;
+    if (f2 > 1.0) f2 = 1.0;
+    memset(dunode, 0, sizeof(double) * n3);
+    /* fstr_ass_load: CLOAD, fstr_ass_load.f90:59-93, then B = GL - QFORCE (:273) */
+    memset(GL, 0, sizeof(double) * n3);
+    for (int c = 0; c < ncl; c++) GL[3 * (cl_node[c] - 1) + cl_dof[c] - 1] += f2 * cl_val[c];
+    for (int i = 0; i < n3; i++) mat->B[i] = GL[i] - QF[i];
+    int iter, converged = 0;
+    for (iter = 1; iter <= max_iter; iter++) {
+      /* fstr_StiffMatrix with u = unode + dunode */
+      memset(mat->D, 0, sizeof(double) * 9 * (size_t)mat->NP);
+      memset(mat->AL, 0, sizeof(double) * 9 * (size_t)mat->NPL);
+      memset(mat->AU, 0, sizeof(double) * 9 * (size_t)mat->NPU);
+      for (int itype = 1; itype <= mesh->n_elem_type && rc == 0; itype++) {
+        const int is = mesh->elem_type_index[itype - 1] + 1, iE = mesh->elem_type_index[itype];
+        const int ic_type = mesh->elem_type_item[itype - 1], nn = etype_max_node(ic_type);
+        if (ic_type != 361 && ic_type != 342) { rc = -2; break; }
+        for (int icel = is; icel <= iE; icel++) {
+          double stiffness[30 * 30], ecoord[30], u[30];
+          int nod[10];
+          const int iiS = mesh->elem_node_index[icel - 1];
+          for (int j = 0; j < nn; j++) {
+            nod[j] = mesh->elem_node_item[iiS + j];
+            for (int i = 0; i < 3; i++) {
+              ecoord[3 * j + i] = mesh->node[3 * (size_t)(nod[j] - 1) + i];
+              u[3 * j + i] = unode[3 * (nod[j] - 1) + i] + dunode[3 * (nod[j] - 1) + i];
+            }
+          }
+          const orc_section *sec = &sections[(mesh->section_ID ? mesh->section_ID[icel - 1] : 1) - 1];
+          int bbar = 0;
+          if (ic_type == 361) {
+            if (sec->elemopt361 == 2) bbar = 1;
+            else if (sec->elemopt361 != 1) { rc = -2; break; } /* IC aborts under NLGEOM, fstr_StiffMatrix.f90:118 */
+          }
+          orc_STF_C3_TL(ic_type, nn, ecoord, u, gstress + (size_t)(icel - 1) * 48, sec->E, sec->nu, bbar, stiffness);
+          if (orc_mat_ass_elem(mat, nn, nod, stiffness, 3 * nn)) rc = -3;
+        }
+      }
+      if (rc) break;
+      /* fstr_AddBC: RHS = value * (factor(2) - factor(1)) on the first iteration, 0 afterwards (fstr_AddBC.f90:54-63) */
+      for (int c = 0; c < nbc; c++) orc_mat_ass_bc(mat, bc_node[c], bc_dof[c], iter > 1 ? 0.0 : bc_val[c] * (f2 - f1));
+      if (sub == 1 && iter == 1) mat->Iarray[97] = 1;          /* Iarray(98) */
+      mat->Iarray[96] = (iter == 1) ? 2 : 1;                   /* Iarray(97) */
+      memset(mat->X, 0, sizeof(double) * n3);
+      int it;
+      double rs, rs2;
+      const int err = orc_solve(1, mesh, mat, &it, &rs, &rs2, NULL, 0, NULL);
+      cg_total += it;
+      if (err != 0 && err != 2002) { rc = err; break; }
+      for (int i = 0; i < n3; i++) dunode[i] += mat->X[i];
+      /* fstr_UpdateNewton */
+      memset(QF, 0, sizeof(double) * n3);
+      for (int itype = 1; itype <= mesh->n_elem_type; itype++) {
+        const int is = mesh->elem_type_index[itype - 1] + 1, iE = mesh->elem_type_index[itype];
+        const int ic_type = mesh->elem_type_item[itype - 1], nn = etype_max_node(ic_type);
+        for (int icel = is; icel <= iE; icel++) {
+          double qf[30], ecoord[30], u[30], du[30];
+          int nod[10];
+          const int iiS = mesh->elem_node_index[icel - 1];
+          for (int j = 0; j < nn; j++) {
+            nod[j] = mesh->elem_node_item[iiS + j];
+            for (int i = 0; i < 3; i++) {
+              ecoord[3 * j + i] = mesh->node[3 * (size_t)(nod[j] - 1) + i];
+              u[3 * j + i] = unode[3 * (nod[j] - 1) + i];
+              du[3 * j + i] = dunode[3 * (nod[j] - 1) + i];
+            }
+          }
+          const orc_section *sec = &sections[(mesh->section_ID ? mesh->section_ID[icel - 1] : 1) - 1];
+          const int bbar = (ic_type == 361 && sec->elemopt361 == 2);
+          orc_UPDATE_C3_TL(ic_type, nn, ecoord, u, du, sec->E, sec->nu, bbar, qf, gstrain + (size_t)(icel - 1) * 48,
+                           gstress + (size_t)(icel - 1) * 48);
+          for (int j = 0; j < nn; j++)
+            for (int i = 0; i < 3; i++) QF[3 * (nod[j] - 1) + i] += qf[3 * j + i];
+        }
+      }
+      /* fstr_Update_NDForce: B = GL - QFORCE, SPC rows cleared (fstr_Residual.f90:44-59,100-133) */
+      for (int i = 0; i < n3; i++) mat->B[i] = GL[i] - QF[i];
+      for (int c = 0; c < nbc; c++) mat->B[3 * (bc_node[c] - 1) + bc_dof[c] - 1] = 0.0;
+      /* convergence check, fstr_solve_NonLinear.f90:110-134 (single subdomain: all nodes internal) */
+      double res = 0.0, xnrm = 0.0, qnrm = 0.0, dunrm = 0.0;
+      for (int i = 0; i < 3 * mesh->nn_internal; i++) {
+        res += mat->B[i] * mat->B[i]; xnrm += mat->X[i] * mat->X[i]; qnrm += QF[i] * QF[i]; dunrm += dunode[i] * dunode[i];
+      }
+      res = sqrt(res); xnrm = sqrt(xnrm); qnrm = sqrt(qnrm); dunrm = sqrt(dunrm);
+      if (qnrm < 1.0e-8) qnrm = 1.0;
+      if (iter == 1) dunrm = xnrm;
+      const double rres = res / qnrm, rxnrm = xnrm / dunrm;
+      if (mat->Iarray[80] == 1) { /* hecmw_mat_get_flag_converged */
+        if (rres < converg || rxnrm < converg) { converged = 1; break; }
+      }
+      if (iter == max_iter || rres > maxres) { rc = -1; break; }
+    }
+    if (rc) break;
+    if (!converged) { rc = -1; break; }
+    if (newton_iters) newton_iters[sub - 1] = iter;
+    for (int i = 0; i < n3; i++) unode[i] += dunode[i];
+    if (unode_steps) memcpy(unode_steps + (size_t)(sub - 1) * n3, unode, sizeof(double) * n3);
+    time += dt;
+  }
+  if (cg_iters_total) *cg_iters_total = cg_total;
+  free(dunode); free(GL); free(QF); free(gstrain); free(gstress);
+  return rc;
+}

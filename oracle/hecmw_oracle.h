@@ -103,6 +103,17 @@ void orc_set_ssor_threads(int n);   /* 0: follow OpenMP; 1: natural order; >1: R
 int orc_num_threads(void);
 void orc_set_num_threads(int n);
 
+/* ---- geometrically nonlinear static (total Lagrangian, elastic): SURVEY 8(f) rank 2, pinned against
+ * examples/static/exI/A361_correct.log, A342_correct.log.  u, du: (3,nn) column-major; stress/strain: (6,ngp). */
+void orc_STF_C3_TL(int etype, int nn, const double *ecoord, const double *u, const double *stress, double E,
+                   double nu, int bbar, double *stiff);
+void orc_UPDATE_C3_TL(int etype, int nn, const double *ecoord, const double *u, const double *du, double E,
+                      double nu, int bbar, double *qf, double *strain, double *stress);
+int orc_nlgeom_static(const orc_mesh *mesh, const orc_section *sections, orc_matrix *mat, int nbc,
+                      const int *bc_node, const int *bc_dof, const double *bc_val, int ncl, const int *cl_node,
+                      const int *cl_dof, const double *cl_val, int substeps, double converg, int max_iter,
+                      double *unode, double *unode_steps, int *newton_iters, int *cg_iters_total);
+
 #ifdef __cplusplus
 }
 #endif

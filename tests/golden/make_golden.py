@@ -29,11 +29,20 @@ DECKS = [
 ]
 
 
-def parse_log(path):
+# geometrically nonlinear decks (examples/static/exI, `!STATIC, TYPE=NLGEOM`, `!STEP, SUBSTEPS=10`): same meshes
+# as exA, so only the cards and the golden summary are stored; "mesh" names the fixture to load
+NL_DECKS = [
+    ("I361", "A361", "examples/static/exI/I300.cnt", "examples/static/exI/A361_correct.log"),
+    ("I342", "A342", "examples/static/exI/I300.cnt", "examples/static/exI/A342_correct.log"),
+]
+
+
+def parse_log(path, which=1):
+    """Displacement max/min of the `which`-th '##### Global Summary' block (1-based; NL logs have one per sub-step)."""
     out = {}
     with open(path) as f:
         txt = f.read()
-    blk = txt.split("##### Global Summary")[1]
+    blk = txt.split("##### Global Summary")[which]
     for line in blk.splitlines():
         m = re.match(r"\s*//(U[123])\s+(\S+)\s+(\S+)", line)
         if m:
@@ -56,6 +65,18 @@ def main():
         meta[name] = dict(source=dict(msh=msh, cnt=cnt, log=log), E=m.sections[0]["E"], nu=m.sections[0]["nu"],
                           boundary=c["boundary"], cload=c["cload"], solver=[c["solver"][0], c["solver"][1]],
                           golden=parse_log(os.path.join(REF, log)), tolerance_abs=1.0e-4)
+    for name, mesh_name, cnt, log in NL_DECKS:
+        with open(os.path.join(REF, cnt)) as f:
+            txt = f.read()
+        assert re.search(r"!STATIC\s*,\s*TYPE\s*=\s*NLGEOM", txt)
+        c = mshio.read_cnt(os.path.join(REF, cnt))
+        E, nu = [float(x) for x in re.search(r"!ELASTIC\s*\n\s*([^\n]+)", txt).group(1).replace(",", " ").split()[:2]]
+        meta[name] = dict(source=dict(mesh=mesh_name, cnt=cnt, log=log), mesh=mesh_name, E=E, nu=nu,
+                          boundary=c["boundary"], cload=c["cload"], solver=[c["solver"][0], c["solver"][1]],
+                          nlgeom=dict(substeps=int(re.search(r"SUBSTEPS\s*=\s*(\d+)", txt).group(1)),
+                                      converg=1.0e-3, max_iter=50),   # defaults of lib/m_step.f90:69,77
+                          golden_steps=[parse_log(os.path.join(REF, log), k) for k in range(1, 11)],
+                          tolerance_abs=1.0e-4)
     # 2-rank halo fixture
     for r in (0, 1):
         d = mshio.read_dist_mesh(os.path.join(REF, "examples/static/refine/cube/P02/sample_P02.%d" % r))
