@@ -1242,6 +1242,34 @@ int fistr_b200_part_rcb(int n_node, const double *node, int n_div, const int *ax
   return 0;
 }
 
+// hecmw_part1 in-process, second half: the distributed mesh of one rank from the node->domain map (host-only)
+int fistr_b200_part_local_count(int n_node, int n_elem_type, const int *elem_type_index, const int *elem_type_item,
+                                const int *elem_node_index, const int *elem_node_item, const int *domain, int rank,
+                                int nparts, int *sizes /* [8] */) {
+  LocalMesh &M = ctx().part;
+  const int rc = M.build(n_node, n_elem_type, elem_type_index, elem_type_item, elem_node_index, elem_node_item, domain,
+                         rank, nparts, etype_max_node);
+  if (rc) return fail(FISTR_B200_ERR_ARG, "part_local: invalid input (%d)", rc);
+  sizes[0] = M.n_node; sizes[1] = M.nn_internal; sizes[2] = M.n_elem; sizes[3] = (int)M.elem_type_item.size();
+  sizes[4] = (int)M.elem_node_item.size(); sizes[5] = (int)M.neighbor_pe.size();
+  sizes[6] = (int)M.import_item.size(); sizes[7] = (int)M.export_item.size();
+  return 0;
+}
+
+int fistr_b200_part_local_fill(int *global_node, int *node_ID, int *elem_type_index, int *elem_type_item,
+                               int *elem_node_index, int *elem_node_item, int *global_elem, int *neighbor_pe,
+                               int *import_index, int *import_item, int *export_index, int *export_item) {
+  LocalMesh &M = ctx().part;
+  if (M.elem_type_index.empty()) return fail(FISTR_B200_ERR_STATE, "part_local_fill before part_local_count");
+  auto put = [](int *dst, const std::vector<int> &v) { if (dst && !v.empty()) memcpy(dst, v.data(), sizeof(int) * v.size()); };
+  put(global_node, M.global_node); put(node_ID, M.node_ID); put(elem_type_index, M.elem_type_index);
+  put(elem_type_item, M.elem_type_item); put(elem_node_index, M.elem_node_index); put(elem_node_item, M.elem_node_item);
+  put(global_elem, M.global_elem); put(neighbor_pe, M.neighbor_pe); put(import_index, M.import_index);
+  put(import_item, M.import_item); put(export_index, M.export_index); put(export_item, M.export_item);
+  M = LocalMesh();
+  return 0;
+}
+
 // host-only view of the multicolour ordering (no GPU needed): lets CPU tests compare the ordering
 // with the oracle's restatement of hecmw_matrix_ordering_{CM,MC}
 int fistr_b200_debug_ssor_order(int N, const int *indexL, const int *itemL, const int *indexU, const int *itemU,

@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "matcon.hpp"
 #include "p2p.cuh"
+#include "partition.hpp"
 #include "spmv.cuh"
 #include "ssor.cuh"
 
@@ -83,6 +84,7 @@ struct Context {
 
   // ---- hecmw_mat_con result held between _count and _fill
   MatCon con;
+  LocalMesh part;   // hecmw_part1 result of one rank held between _count and _fill
 
   // ---- peer-memory communication of the fused CG loop (p2p.cuh)
   struct P2P {

@@ -32,6 +32,51 @@ def rcb_domains(mesh: hecmwST_local_mesh, axes: str) -> np.ndarray:
 
 
 def local_mesh(mesh: hecmwST_local_mesh, domain: np.ndarray, rank: int, nparts: int) -> hecmwST_local_mesh:
+    """The distributed mesh of `rank` (what hecmw_part1 writes to <name>.<rank>), built by the library's native
+    host code (csrc/partition.hpp: LocalMesh) from the node->domain map."""
+    L = _lib.lib()
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    eti, ett = i32(mesh.elem_type_index), i32(mesh.elem_type_item)
+    eni, enn = i32(mesh.elem_node_index), i32(mesh.elem_node_item)
+    dom = i32(domain)
+    sizes = np.zeros(8, np.int32)
+    check(L.fistr_b200_part_local_count(mesh.n_node, mesh.n_elem_type, ip(eti), ip(ett), ip(eni), ip(enn), ip(dom),
+                                        int(rank), int(nparts), ip(sizes)))
+    n_node, nn_int, n_elem, n_type, n_conn, n_nb, n_imp, n_exp = [int(v) for v in sizes]
+    z = lambda n: np.zeros(max(n, 1), np.int32)
+    gnode, node_ID = z(n_node), z(2 * n_node)
+    l_eti, l_ett, l_eni, l_enn, gelem = z(n_type + 1), z(n_type), z(n_elem + 1), z(n_conn), z(n_elem)
+    nb, imp_i, imp, exp_i, exp = z(n_nb), z(n_nb + 1), z(n_imp), z(n_nb + 1), z(n_exp)
+    check(L.fistr_b200_part_local_fill(ip(gnode), ip(node_ID), ip(l_eti), ip(l_ett), ip(l_eni), ip(l_enn), ip(gelem),
+                                       ip(nb), ip(imp_i), ip(imp), ip(exp_i), ip(exp)))
+    gnode = gnode[:n_node].astype(np.int64)
+    m = hecmwST_local_mesh()
+    m.n_node, m.nn_internal, m.n_elem, m.n_elem_type = n_node, nn_int, n_elem, n_type
+    m.node = np.ascontiguousarray(mesh.node.reshape(-1, 3)[gnode].reshape(-1))
+    m.global_node_ID = mesh.global_node_ID[gnode].astype(np.int32)
+    m.node_ID = node_ID[: 2 * n_node].reshape(-1, 2).copy()
+    m.elem_type_index, m.elem_type_item = l_eti[: n_type + 1].copy(), l_ett[:n_type].copy()
+    m.elem_node_index, m.elem_node_item = l_eni[: n_elem + 1].copy(), l_enn[:n_conn].copy()
+    kg = gelem[:n_elem].astype(np.int64)
+    m.section_ID = (mesh.section_ID[kg] if mesh.section_ID is not None else np.ones(len(kg))).astype(np.int32)
+    m.global_elem_ID = (kg + 1).astype(np.int32)
+    m.sections = mesh.sections
+    m.my_rank = rank; m.PETOT = nparts; m.zero = 1 if rank == 0 else 0
+    g2l = np.zeros(mesh.n_node, np.int32)
+    g2l[gnode] = np.arange(1, n_node + 1, dtype=np.int32)
+    m.node_group = {}
+    for k, v in mesh.node_group.items():
+        l = g2l[np.asarray(v, np.int64) - 1]
+        m.node_group[k] = l[l > 0].astype(np.int32)
+    m.n_neighbor_pe = n_nb
+    m.neighbor_pe = nb[:n_nb].copy()
+    m.import_index, m.import_item = imp_i[: n_nb + 1].copy(), imp[:n_imp].copy()
+    m.export_index, m.export_item = exp_i[: n_nb + 1].copy(), exp[:n_exp].copy()
+    return m
+
+
+def _local_mesh_numpy(mesh: hecmwST_local_mesh, domain: np.ndarray, rank: int, nparts: int) -> hecmwST_local_mesh:
+    """Independent numpy formulation of local_mesh (kept as a cross-check of the native builder)."""
     owner = domain
     n_glob = mesh.n_node
     # owner-local numbering of every node: position among its owner's nodes in ascending global id

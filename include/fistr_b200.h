@@ -136,6 +136,20 @@ int fistr_b200_update_3_R(double *X /* 3*NP in/out */);
  * axes[i] in {0,1,2} per bisection level (the 'x,y,z' line of hecmw_part_ctrl.dat); host-only */
 int fistr_b200_part_rcb(int n_node, const double *node, int n_div, const int *axes, int *domain);
 
+/* ... and the distributed mesh of ONE rank from that node->domain map, exactly as hecmw_part1 writes it
+ * (hecmw1/src/common/hecmw_io_dist.c:1991-2284: internal nodes first, then external; elements touching an
+ * internal node; neighbour / import / export tables).  _count builds and returns
+ * sizes[8] = {n_node, nn_internal, n_elem, n_elem_type, len(elem_node_item), n_neighbor_pe, n_import, n_export};
+ * _fill copies into caller arrays: global_node (0-based global index per local node), node_ID (2*n_node),
+ * elem_type_index (n_elem_type+1), elem_type_item, elem_node_index (n_elem+1), elem_node_item (1-based local ids),
+ * global_elem (0-based), neighbor_pe, import_index/export_index (n_neighbor_pe+1), import_item, export_item. */
+int fistr_b200_part_local_count(int n_node, int n_elem_type, const int *elem_type_index, const int *elem_type_item,
+                                const int *elem_node_index, const int *elem_node_item, const int *domain, int rank,
+                                int nparts, int *sizes);
+int fistr_b200_part_local_fill(int *global_node, int *node_ID, int *elem_type_index, int *elem_type_item,
+                               int *elem_node_index, int *elem_node_item, int *global_elem, int *neighbor_pe,
+                               int *import_index, int *import_item, int *export_index, int *export_item);
+
 /* host-only (no GPU): the multicolour ordering (RCM + greedy colouring, hecmw_matrix_ordering_CM.f90 /
  * hecmw_matrix_ordering_MC.f90) the device SSOR uses; perm[new-1]=old (1-based), color_index has ncolor+1 entries */
 int fistr_b200_debug_ssor_order(int N, const int *indexL, const int *itemL, const int *indexU, const int *itemU,

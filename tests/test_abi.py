@@ -45,3 +45,27 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "liboracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_plain_c_consumer_links_and_runs(tmp_path):
+    """include/fistr_b200.h is valid C and a C program needs nothing but the shared library (INTEGRATION.md 4);
+    the host-only entry points (hecmw_mat_con, RCB) work from C without a GPU."""
+    import subprocess
+    from frontistr_b200 import _lib
+    _lib.lib()
+    exe = str(tmp_path / "c_consumer")
+    pkg = os.path.join(ROOT, "frontistr_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "integration", "c_consumer.c"), "-o", exe,
+                           "-L", pkg, "-lfistr_b200", "-Wl,-rpath," + pkg])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "c_consumer ok" in out.stdout
+
+
+def test_fortran_interface_matches_header():
+    """Every bind(C) name in integration/hecmw_b200_if.f90 is a symbol the header declares."""
+    txt = open(os.path.join(ROOT, "integration", "hecmw_b200_if.f90")).read()
+    names = set(re.findall(r'bind\(C,\s*name="(fistr_b200_\w+)"\)', txt))
+    assert len(names) >= 18
+    assert names <= set(declared_symbols())

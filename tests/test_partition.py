@@ -27,6 +27,24 @@ def test_partition_equals_hecmw_part1(name):
             assert np.array_equal(getattr(p, k), d["r%d_%s" % (r, k)]), (r, k)
 
 
+@pytest.mark.parametrize("case", ["hex9_xyz", "tet3_xy", "hexrag_zx"])
+def test_native_local_mesh_equals_numpy_formulation(case):
+    """csrc/partition.hpp:LocalMesh (what bench.py and tools/dist_check.py use) against the independent numpy
+    formulation on meshes the hecmw_part1 fixtures do not cover."""
+    mesh, axes = {"hex9_xyz": (meshgen.hex_cube(9), "xyz"), "tet3_xy": (meshgen.tet10_cube(3), "xy"),
+                  "hexrag_zx": (meshgen.hex_cube(3, nx=7, ny=2, nz=5), "zx")}[case]
+    dom = partition.rcb_domains(mesh, axes)
+    nparts = 1 << len(axes)
+    for r in range(nparts):
+        a = partition.local_mesh(mesh, dom, r, nparts)
+        b = partition._local_mesh_numpy(mesh, dom, r, nparts)
+        assert (a.n_node, a.nn_internal, a.n_elem, a.n_neighbor_pe) == (b.n_node, b.nn_internal, b.n_elem, b.n_neighbor_pe)
+        for k in KEYS + ("node", "section_ID"):
+            assert np.array_equal(getattr(a, k), getattr(b, k)), (r, k)
+        for g in mesh.node_group:
+            assert np.array_equal(a.node_group[g], b.node_group[g])
+
+
 def test_partition_tables_are_consistent():
     """export list of p towards q == import list of q from p (as global ids), every node owned once."""
     mesh = meshgen.hex_cube(9)
