@@ -1319,6 +1319,99 @@ void orc_precond_clear(void) { precond_clear_all(); }
  * Newton loop is pinned against the reference's golden logs (examples/static/exI) before any GPU kernel exists.
  * ============================================================================================= */
 
+/* cderiv, lib/physics/Hyperelastic.f90:13-131: reduced invariants of C = 2E + 1 and their first / second
+ * derivatives with respect to C.  Index order [i][j][inv] / [i][j][k][l][inv] as in the Fortran arrays. */
+static void cderiv(const double strain[6], double *inv1b, double *inv2b, double *inv3b, double dibdc[3][3][3],
+                   double d2ibdc2[3][3][3][3][3]) {
+  double delta[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, ctn[3][3], ctninv[3][3], didc[3][3][3];
+  static double d2idc2[3][3][3][3][3];
+#pragma omp threadprivate(d2idc2)
+  ctn[0][0] = strain[0] * 2.0 + 1.0; ctn[1][1] = strain[1] * 2.0 + 1.0; ctn[2][2] = strain[2] * 2.0 + 1.0;
+  ctn[0][1] = ctn[1][0] = strain[3]; ctn[1][2] = ctn[2][1] = strain[4]; ctn[2][0] = ctn[0][2] = strain[5];
+  const double inv1 = ctn[0][0] + ctn[1][1] + ctn[2][2];
+  const double inv2 = ctn[1][1] * ctn[2][2] + ctn[0][0] * ctn[2][2] + ctn[0][0] * ctn[1][1] - ctn[1][2] * ctn[1][2] -
+                      ctn[0][2] * ctn[0][2] - ctn[0][1] * ctn[0][1];
+  const double inv3 = ctn[0][0] * ctn[1][1] * ctn[2][2] + ctn[1][0] * ctn[2][1] * ctn[0][2] + ctn[2][0] * ctn[0][1] * ctn[1][2] -
+                      ctn[2][0] * ctn[1][1] * ctn[0][2] - ctn[1][0] * ctn[0][1] * ctn[2][2] - ctn[0][0] * ctn[2][1] * ctn[1][2];
+  const double inv33 = pow(inv3, -1.0 / 3.0);
+  ctninv[0][0] = (ctn[1][1] * ctn[2][2] - ctn[1][2] * ctn[1][2]) / inv3;
+  ctninv[1][1] = (ctn[0][0] * ctn[2][2] - ctn[0][2] * ctn[0][2]) / inv3;
+  ctninv[2][2] = (ctn[0][0] * ctn[1][1] - ctn[0][1] * ctn[0][1]) / inv3;
+  ctninv[0][1] = ctninv[1][0] = (ctn[0][2] * ctn[1][2] - ctn[0][1] * ctn[2][2]) / inv3;
+  ctninv[0][2] = ctninv[2][0] = (ctn[0][1] * ctn[1][2] - ctn[1][1] * ctn[0][2]) / inv3;
+  ctninv[1][2] = ctninv[2][1] = (ctn[0][1] * ctn[0][2] - ctn[0][0] * ctn[1][2]) / inv3;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      didc[i][j][0] = delta[i][j];
+      didc[i][j][1] = inv1 * delta[i][j] - ctn[i][j];
+      didc[i][j][2] = inv3 * ctninv[i][j];
+    }
+  for (int k = 0; k < 3; k++)
+    for (int l = 0; l < 3; l++)
+      for (int m = 0; m < 3; m++)
+        for (int n = 0; n < 3; n++) {
+          d2idc2[k][l][m][n][0] = 0.0;
+          d2idc2[k][l][m][n][1] = delta[k][l] * delta[m][n] - (delta[k][m] * delta[l][n] + delta[k][n] * delta[l][m]) / 2.0;
+          d2idc2[k][l][m][n][2] = inv3 * (ctninv[m][n] * ctninv[k][l] - (ctninv[k][m] * ctninv[n][l] + ctninv[k][n] * ctninv[m][l]) / 2.0);
+        }
+  *inv1b = inv1 * inv33;
+  *inv2b = inv2 * inv33 * inv33;
+  *inv3b = sqrt(inv3);
+  const double i33_2 = inv33 * inv33, i33_4 = i33_2 * i33_2, i33_5 = i33_4 * inv33, i33_7 = i33_5 * i33_2, i33_8 = i33_4 * i33_4;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      dibdc[i][j][0] = -i33_4 * inv1 * didc[i][j][2] / 3.0 + inv33 * didc[i][j][0];
+      dibdc[i][j][1] = -2.0 * i33_5 * inv2 * didc[i][j][2] / 3.0 + i33_2 * didc[i][j][1];
+      dibdc[i][j][2] = didc[i][j][2] / (2.0 * sqrt(inv3));
+    }
+  if (!d2ibdc2) return;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+      for (int k = 0; k < 3; k++)
+        for (int l = 0; l < 3; l++) {
+          d2ibdc2[i][j][k][l][0] = 4.0 / 9.0 * i33_7 * inv1 * didc[i][j][2] * didc[k][l][2] -
+                                   i33_4 / 3.0 * (didc[k][l][0] * didc[i][j][2] + didc[i][j][0] * didc[k][l][2]) -
+                                   i33_4 / 3.0 * inv1 * d2idc2[i][j][k][l][2] + inv33 * d2idc2[i][j][k][l][0];
+          d2ibdc2[i][j][k][l][1] = 10.0 / 9.0 * i33_8 * inv2 * didc[i][j][2] * didc[k][l][2] -
+                                   2.0 / 3.0 * i33_5 * (didc[k][l][1] * didc[i][j][2] + didc[i][j][1] * didc[k][l][2]) -
+                                   2.0 / 3.0 * i33_5 * inv2 * d2idc2[i][j][k][l][2] + i33_2 * d2idc2[i][j][k][l][1];
+          d2ibdc2[i][j][k][l][2] = -didc[i][j][2] * didc[k][l][2] / (4.0 * pow(inv3, 1.5)) +
+                                   d2idc2[i][j][k][l][2] / (2.0 * sqrt(inv3));
+        }
+}
+
+/* calElasticMooneyRivlin (Hyperelastic.f90:221-246) + mat_c2d (calMatMatrix.f90:154-197, D3) */
+void orc_mooney_rivlin_tangent(const double c[3], const double strain[6], double D[6][6]) {
+  double i1, i2, i3, dib[3][3][3];
+  static double d2[3][3][3][3][3];
+#pragma omp threadprivate(d2)
+  cderiv(strain, &i1, &i2, &i3, dib, d2);
+  static const int vi[6] = {0, 1, 2, 0, 1, 2}, vj[6] = {0, 1, 2, 1, 2, 0}; /* 11 22 33 12 23 31 */
+  for (int a = 0; a < 6; a++)
+    for (int b = 0; b < 6; b++) {
+      const int k = vi[a], l = vj[a], m = vi[b], n = vj[b];
+      const double cijkl = d2[k][l][m][n][0] * c[0] + d2[k][l][m][n][1] * c[1] +
+                           2.0 * (dib[k][l][2] * dib[m][n][2] + (i3 - 1.0) * d2[k][l][m][n][2]) / c[2];
+      D[a][b] = 4.0 * cijkl;
+    }
+}
+
+/* calUpdateElasticMooneyRivlin (Hyperelastic.f90:250-284) */
+void orc_mooney_rivlin_stress(const double c[3], const double strain[6], double stress[6]) {
+  double i1, i2, i3, dib[3][3][3], dudc[3][3];
+  cderiv(strain, &i1, &i2, &i3, dib, NULL);
+  for (int k = 0; k < 3; k++)
+    for (int l = 0; l < 3; l++) dudc[k][l] = dib[k][l][0] * c[0] + dib[k][l][1] * c[1] + 2.0 * (i3 - 1.0) * dib[k][l][2] / c[2];
+  stress[0] = 2.0 * dudc[0][0]; stress[1] = 2.0 * dudc[1][1]; stress[2] = 2.0 * dudc[2][2];
+  stress[3] = 2.0 * dudc[0][1]; stress[4] = 2.0 * dudc[1][2]; stress[5] = 2.0 * dudc[0][2];
+}
+
+/* MatlMatrix (calMatMatrix.f90:29-112) for the two material types of the nonlinear path */
+static void matl_matrix(const orc_section *sec, const double *gp_strain, double D[6][6]) {
+  if (sec->mtype == 1) orc_mooney_rivlin_tangent(sec->hyper, gp_strain, D);
+  else cal_elastic_matrix(sec->E, sec->nu, D);
+}
+
 /* BL = BL0 + BL1, static_LIB_3d.f90:120-160 / static_LIB_C3D8.f90:100-156.  gdd = dudx(i,j), 0-based [i][j].
  * Bbar != NULL selects the B-bar rows 1..3 (static_LIB_C3D8.f90:103-118). */
 static void fill_B_TL(int nn, double gderiv[][3], double (*Bbar)[3], double gdd[3][3], int with_BL1, double *B) {
@@ -1364,8 +1457,8 @@ static void disp_gradient(int nn, const double *u /* (3,nn) col-major */, double
 
 /* STF_C3 / STF_C3D8Bbar with flag == TOTALLAG: material + initial-stress stiffness.
  * u = unode + dunode (fstr_StiffMatrix.f90:66-72), stress(6,ngp) = 2nd Piola-Kirchhoff at the Gauss points. */
-void orc_STF_C3_TL(int etype, int nn, const double *ecoord, const double *u, const double *stress, double E,
-                   double nu, int bbar, double *stiff) {
+void orc_STF_C3_TL(int etype, int nn, const double *ecoord, const double *u, const double *strain,
+                   const double *stress, const orc_section *sec, int bbar, double *stiff) {
   double D[6][6], B[6 * 30], gderiv[20][3], Bbar[20][3], gdd[3][3], det, wg, nc[3] = {0, 0, 0};
   const int m = 3 * nn;
   memset(stiff, 0, sizeof(double) * m * m);
@@ -1373,7 +1466,7 @@ void orc_STF_C3_TL(int etype, int nn, const double *ecoord, const double *u, con
   for (int LX = 1; LX <= num_quad_points(etype); LX++) {
     get_quad_point(etype, LX, nc);
     get_global_deriv(etype, nn, nc, ecoord, &det, gderiv);
-    cal_elastic_matrix(E, nu, D);
+    matl_matrix(sec, strain + 6 * (LX - 1), D); /* tangent at the strain stored by the last update */
     wg = get_weight(etype, LX) * det;
     disp_gradient(nn, u, gderiv, gdd);
     fill_B_TL(nn, gderiv, bbar ? Bbar : NULL, gdd, 1, B);
@@ -1394,8 +1487,8 @@ void orc_STF_C3_TL(int etype, int nn, const double *ecoord, const double *u, con
 
 /* UPDATE_C3 (static_LIB_3d.f90:516-837) / Update_C3D8Bbar (static_LIB_C3D8.f90:203-552), flag == TOTALLAG,
  * elastic: Green-Lagrange strain, S = D E, qf = sum_gp BL^T S wg.  u = unode, du = dunode. */
-void orc_UPDATE_C3_TL(int etype, int nn, const double *ecoord, const double *u, const double *du, double E,
-                      double nu, int bbar, double *qf, double *strain, double *stress) {
+void orc_UPDATE_C3_TL(int etype, int nn, const double *ecoord, const double *u, const double *du,
+                      const orc_section *sec, int bbar, double *qf, double *strain, double *stress) {
   double D[6][6], B[6 * 30], gderiv[20][3], Bbar[20][3], gdd[3][3], tot[3 * 20], det, wg, nc[3] = {0, 0, 0};
   const int m = 3 * nn;
   double vol0 = 0.0;
@@ -1412,7 +1505,7 @@ void orc_UPDATE_C3_TL(int etype, int nn, const double *ecoord, const double *u, 
     get_global_deriv(etype, nn, nc, ecoord, &det, gderiv);
     disp_gradient(nn, tot, gderiv, gdd);
     const double dvol = bbar ? vol0 - (gdd[0][0] + gdd[1][1] + gdd[2][2]) / 3.0 : 0.0;
-    cal_elastic_matrix(E, nu, D);
+    if (sec->mtype != 1) cal_elastic_matrix(sec->E, sec->nu, D);
     double e[6];
     e[0] = gdd[0][0] + dvol; e[1] = gdd[1][1] + dvol; e[2] = gdd[2][2] + dvol;
     e[3] = gdd[0][1] + gdd[1][0]; e[4] = gdd[1][2] + gdd[2][1]; e[5] = gdd[2][0] + gdd[0][2];
@@ -1424,11 +1517,16 @@ void orc_UPDATE_C3_TL(int etype, int nn, const double *ecoord, const double *u, 
     e[4] += gdd[0][1] * gdd[0][2] + gdd[1][1] * gdd[1][2] + gdd[2][1] * gdd[2][2];
     e[5] += gdd[0][0] * gdd[0][2] + gdd[1][0] * gdd[1][2] + gdd[2][0] * gdd[2][2];
     double *eo = strain + 6 * (LX - 1), *so = stress + 6 * (LX - 1);
-    for (int i = 0; i < 6; i++) {
-      double s = 0.0;
-      for (int k = 0; k < 6; k++) s += D[i][k] * e[k];
-      eo[i] = e[i];
-      so[i] = s;
+    if (sec->mtype == 1) { /* StressUpdate -> calUpdateElasticMooneyRivlin, static_LIB_3d.f90:683-686 */
+      for (int i = 0; i < 6; i++) eo[i] = e[i];
+      orc_mooney_rivlin_stress(sec->hyper, e, so);
+    } else {
+      for (int i = 0; i < 6; i++) {
+        double s = 0.0;
+        for (int k = 0; k < 6; k++) s += D[i][k] * e[k];
+        eo[i] = e[i];
+        so[i] = s;
+      }
     }
     fill_B_TL(nn, gderiv, bbar ? Bbar : NULL, gdd, 1, B);
     wg = get_weight(etype, LX) * det;
@@ -1493,7 +1591,8 @@ int orc_nlgeom_static(const orc_mesh *mesh, const orc_section *sections, orc_mat
             if (sec->elemopt361 == 2) bbar = 1;
             else if (sec->elemopt361 != 1) { rc = -2; break; } /* IC aborts under NLGEOM, fstr_StiffMatrix.f90:118 */
           }
-          orc_STF_C3_TL(ic_type, nn, ecoord, u, gstress + (size_t)(icel - 1) * 48, sec->E, sec->nu, bbar, stiffness);
+          orc_STF_C3_TL(ic_type, nn, ecoord, u, gstrain + (size_t)(icel - 1) * 48, gstress + (size_t)(icel - 1) * 48, sec,
+                        bbar, stiffness);
           if (orc_mat_ass_elem(mat, nn, nod, stiffness, 3 * nn)) rc = -3;
         }
       }
@@ -1528,7 +1627,7 @@ int orc_nlgeom_static(const orc_mesh *mesh, const orc_section *sections, orc_mat
           }
           const orc_section *sec = &sections[(mesh->section_ID ? mesh->section_ID[icel - 1] : 1) - 1];
           const int bbar = (ic_type == 361 && sec->elemopt361 == 2);
-          orc_UPDATE_C3_TL(ic_type, nn, ecoord, u, du, sec->E, sec->nu, bbar, qf, gstrain + (size_t)(icel - 1) * 48,
+          orc_UPDATE_C3_TL(ic_type, nn, ecoord, u, du, sec, bbar, qf, gstrain + (size_t)(icel - 1) * 48,
                            gstress + (size_t)(icel - 1) * 48);
           for (int j = 0; j < nn; j++)
             for (int i = 0; i < 3; i++) QF[3 * (nod[j] - 1) + i] += qf[3 * j + i];

@@ -50,6 +50,8 @@ typedef struct orc_mesh {
 typedef struct orc_section {
   int elemopt361; /* 1 FI, 2 BBAR, 3 IC  (fistr1/src/lib/m_fstr.f90:68-71) */
   double E, nu;
+  int mtype;       /* 0 ELASTIC; 1 MOONEYRIVLIN (lib/physics/material.f90), nonlinear path only */
+  double hyper[3]; /* Mooney-Rivlin C10, C01, D (M_PLCONST1..3) */
 } orc_section;
 
 /* hecmwST_matrix (hecmw_util_f.F90:433-468) */
@@ -105,10 +107,14 @@ void orc_set_num_threads(int n);
 
 /* ---- geometrically nonlinear static (total Lagrangian, elastic): SURVEY 8(f) rank 2, pinned against
  * examples/static/exI/A361_correct.log, A342_correct.log.  u, du: (3,nn) column-major; stress/strain: (6,ngp). */
-void orc_STF_C3_TL(int etype, int nn, const double *ecoord, const double *u, const double *stress, double E,
-                   double nu, int bbar, double *stiff);
-void orc_UPDATE_C3_TL(int etype, int nn, const double *ecoord, const double *u, const double *du, double E,
-                      double nu, int bbar, double *qf, double *strain, double *stress);
+void orc_STF_C3_TL(int etype, int nn, const double *ecoord, const double *u, const double *strain,
+                   const double *stress, const orc_section *sec, int bbar, double *stiff);
+void orc_UPDATE_C3_TL(int etype, int nn, const double *ecoord, const double *u, const double *du,
+                      const orc_section *sec, int bbar, double *qf, double *strain, double *stress);
+/* Mooney-Rivlin (lib/physics/Hyperelastic.f90:13-131,221-286): tangent D(6,6) row-major and 2nd Piola-Kirchhoff
+ * stress from the Green-Lagrange strain (engineering shear components) */
+void orc_mooney_rivlin_tangent(const double c[3], const double strain[6], double D[6][6]);
+void orc_mooney_rivlin_stress(const double c[3], const double strain[6], double stress[6]);
 int orc_nlgeom_static(const orc_mesh *mesh, const orc_section *sections, orc_matrix *mat, int nbc,
                       const int *bc_node, const int *bc_dof, const double *bc_val, int ncl, const int *cl_node,
                       const int *cl_dof, const double *cl_val, int substeps, double converg, int max_iter,

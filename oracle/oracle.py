@@ -30,7 +30,8 @@ class orc_mesh(C.Structure):
 
 
 class orc_section(C.Structure):
-    _fields_ = [("elemopt361", C.c_int), ("E", C.c_double), ("nu", C.c_double)]
+    _fields_ = [("elemopt361", C.c_int), ("E", C.c_double), ("nu", C.c_double),
+                ("mtype", C.c_int), ("hyper", C.c_double * 3)]
 
 
 class orc_matrix(C.Structure):
@@ -107,6 +108,9 @@ def c_sections(m):
     arr = (orc_section * len(m.sections))()
     for i, s in enumerate(m.sections):
         arr[i].elemopt361 = int(s["elemopt361"]); arr[i].E = float(s["E"]); arr[i].nu = float(s["nu"])
+        arr[i].mtype = int(s.get("mtype", 0))
+        for k, v in enumerate(s.get("hyper", (0.0, 0.0, 0.0))):
+            arr[i].hyper[k] = float(v)
     return arr
 
 

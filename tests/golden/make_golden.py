@@ -77,6 +77,19 @@ def main():
                                       converg=1.0e-3, max_iter=50),   # defaults of lib/m_step.f90:69,77
                           golden_steps=[parse_log(os.path.join(REF, log), k) for k in range(1, 11)],
                           tolerance_abs=1.0e-4)
+    # tutorial/03_hyperelastic_cylinder (BASELINE.json configs[4]): mesh + cards only — the reference ships no golden
+    # log for it, so this deck is a run-only fixture (Newton convergence, prescribed displacement, symmetry planes)
+    m = mshio.read_msh(os.path.join(REF, "tutorial/03_hyperelastic_cylinder/cylinder.msh"))
+    c = mshio.read_cnt(os.path.join(REF, "tutorial/03_hyperelastic_cylinder/cylinder.cnt"))
+    np.savez_compressed(os.path.join(OUT, "cylinder.npz"),
+                        node=m.node, elem_type_index=m.elem_type_index, elem_type_item=m.elem_type_item,
+                        elem_node_index=m.elem_node_index, elem_node_item=m.elem_node_item,
+                        global_node_ID=m.global_node_ID, **{"ngrp_" + k: v for k, v in m.node_group.items()})
+    meta["cylinder"] = dict(source=dict(msh="tutorial/03_hyperelastic_cylinder/cylinder.msh",
+                                        cnt="tutorial/03_hyperelastic_cylinder/cylinder.cnt", log=None),
+                            E=1.0, nu=0.3, mooney_rivlin=[0.1486, 0.4849, 0.0789], boundary=c["boundary"], cload=[],
+                            solver=[c["solver"][0], c["solver"][1]], nlgeom=dict(substeps=5, converg=1.0e-5, max_iter=50),
+                            golden={}, tolerance_abs=None)
     # 2-rank halo fixture
     for r in (0, 1):
         d = mshio.read_dist_mesh(os.path.join(REF, "examples/static/refine/cube/P02/sample_P02.%d" % r))

@@ -70,3 +70,68 @@ def test_nlgeom_newton_against_reference_logs(name):
             assert abs(U[:, d].max() - gold[key][0]) <= g["tolerance_abs"], (k, key)
             assert abs(U[:, d].min() - gold[key][1]) <= g["tolerance_abs"], (k, key)
             assert abs(U[:, d].min() - gold[key][1]) <= 6e-5 * max(abs(gold[key][1]), 1e-3)   # printed digits
+
+
+def test_mooney_rivlin_is_the_derivative_of_its_energy():
+    """calUpdateElasticMooneyRivlin / calElasticMooneyRivlin restated (Hyperelastic.f90): S = dW/dE and D = dS/dE for
+    W = C10 (I1b - 3) + C01 (I2b - 3) + (J - 1)^2 / D, checked by central differences.  The reference ships no golden
+    log with this material on the 361/342 B-bar/TL path, so this known-answer test is what pins the restatement."""
+    import ctypes as C
+    from oracle import oracle as orc
+    L = orc.lib()
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    c = np.array([0.1486, 0.4849, 0.0789])          # tutorial/03 constants
+
+    def W(e):
+        Cm = np.array([[2 * e[0] + 1, e[3], e[5]], [e[3], 2 * e[1] + 1, e[4]], [e[5], e[4], 2 * e[2] + 1]])
+        I1 = np.trace(Cm); I2 = 0.5 * (I1 ** 2 - np.trace(Cm @ Cm)); I3 = np.linalg.det(Cm)
+        return c[0] * (I1 * I3 ** (-1 / 3) - 3) + c[1] * (I2 * I3 ** (-2 / 3) - 3) + (np.sqrt(I3) - 1) ** 2 / c[2]
+
+    def S(e):
+        s = np.zeros(6)
+        L.orc_mooney_rivlin_stress(dp(c), dp(np.ascontiguousarray(e)), dp(s))
+        return s
+
+    rng = np.random.default_rng(1)
+    h = 1e-6
+    for trial in range(5):
+        F = np.eye(3) + (0.0 if trial == 0 else 0.25) * rng.standard_normal((3, 3))     # a real deformation gradient
+        G = 0.5 * (F.T @ F - np.eye(3))
+        e0 = np.array([G[0, 0], G[1, 1], G[2, 2], 2 * G[0, 1], 2 * G[1, 2], 2 * G[2, 0]])
+        D = np.zeros((6, 6))
+        L.orc_mooney_rivlin_tangent(dp(c), dp(e0), dp(D))
+        Sfd = np.array([(W(e0 + h * np.eye(6)[i]) - W(e0 - h * np.eye(6)[i])) / (2 * h) for i in range(6)])
+        Dfd = np.array([(S(e0 + h * np.eye(6)[j]) - S(e0 - h * np.eye(6)[j])) / (2 * h) for j in range(6)]).T
+        assert np.abs(S(e0) - Sfd).max() < 1e-7 and np.abs(D - Dfd).max() < 1e-6 and np.abs(D - D.T).max() < 1e-12
+    assert np.abs(S(np.zeros(6))).max() < 1e-14          # stress-free reference configuration
+
+
+def test_hyperelastic_cylinder_newton_loop_runs():
+    """BASELINE.json configs[4] (tutorial/03_hyperelastic_cylinder: 432 C3D8 B-bar, Mooney-Rivlin, 5 sub-steps of a
+    prescribed 7.0 end displacement = 26 % stretch, CG + SSOR) through the restated Newton loop: quadratic
+    convergence in <= 5 iterations per sub-step, prescribed / symmetry displacements hit exactly, and the outer
+    radius contracts as a nearly incompressible bar must (lambda_r ~ lambda^-1/2: -0.70 for an incompressible
+    material, a little less with the finite bulk modulus 2/D).  Run-only: no golden log exists in the reference."""
+    from oracle import oracle as orc
+    from frontistr_b200 import hecmw
+    from frontistr_b200.hecmw_types import kel361BBAR
+    from frontistr_b200.mshio import apply_solver_card
+    g = util.golden_meta()["cylinder"]
+    mesh, _, _ = util.load_golden_mesh("cylinder", elemopt361=kel361BBAR)
+    mesh.sections = [dict(elemopt361=kel361BBAR, E=1.0, nu=0.3, mtype=1, hyper=tuple(g["mooney_rivlin"]))]
+    A = orc.mat_con(mesh)
+    apply_solver_card(A, (g["solver"][0], g["solver"][1]))
+    A.Iarray[20] = 0; A.Iarray[21] = 0
+    bc = hecmw.boundary_dofs(mesh, [tuple(b) for b in g["boundary"]])
+    nl = g["nlgeom"]
+    r = orc.nlgeom_static(mesh, A, bc, ([], [], []), nl["substeps"], nl["converg"], nl["max_iter"])
+    assert r["error"] == 0 and np.all(r["newton_iters"] <= 5)
+    U = r["unode"].reshape(-1, 3)
+    xyz = mesh.node.reshape(-1, 3)
+    assert np.allclose(U[mesh.node_group["LOADS"] - 1, 2], -7.0, atol=1e-8)
+    assert np.abs(U[mesh.node_group["FIX"] - 1, 2]).max() < 1e-12
+    assert np.abs(U[mesh.node_group["XSYMM"] - 1, 0]).max() < 1e-12 and np.abs(U[mesh.node_group["YSYMM"] - 1, 1]).max() < 1e-12
+    radial = (U[:, 0] * xyz[:, 0] + U[:, 1] * xyz[:, 1]) / np.maximum(np.hypot(xyz[:, 0], xyz[:, 1]), 1e-12)
+    lam = (26.667 + 7.0) / 26.667
+    incompressible = 6.413 * (1.0 - lam ** -0.5)
+    assert radial.max() <= 1e-9 and 0.9 * incompressible < -radial.min() < 1.0 * incompressible
