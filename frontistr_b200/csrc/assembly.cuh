@@ -178,6 +178,105 @@ stiff_kernel(int e0, int e1, const int *__restrict__ elem_node_index, const int 
   }
 }
 
+// ---- geometrically nonlinear (total Lagrangian) assembly and update, SURVEY 8(f) rank 2 -----------
+// fstr_StiffMatrix with material%nlgeom_flag == TOTALLAG (fstr_StiffMatrix.f90:60-150 -> STF_C3 / STF_C3D8Bbar) and
+// fstr_UpdateNewton (fstr_Update.f90:25-293 -> UPDATE_C3 / Update_C3D8Bbar).  One element per warp; the
+// Gauss-point state lives in gp_strain / gp_stress [element][8][6].  u = unode + dunode (3 per node).
+template <int FORM, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+stiff_tl_kernel(int e0, int e1, const int *__restrict__ elem_node_index, const int *__restrict__ elem_node_item,
+                const double *__restrict__ node, const double *__restrict__ u, const int *__restrict__ section_ID,
+                const elem::MatlTL *__restrict__ matl, const int *__restrict__ sect_form,
+                const double *__restrict__ gp_strain, const double *__restrict__ gp_stress,
+                const unsigned *__restrict__ slot, size_t slot_base, double *__restrict__ vals,
+                double *__restrict__ ke_out) {
+  using namespace elem;
+  constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
+  constexpr int NB = NN * NN;
+  constexpr int ROUNDS = (NB + 31) / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ScratchTL &S = reinterpret_cast<ScratchTL *>(smem_raw)[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const int wg = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  const int nw = gridDim.x * WARPS;
+  for (int e = e0 + wg; e < e1; e += nw) {
+    const int sec = section_ID[e] - 1;
+    if (FORM != FORM_TET10 && sect_form[sec] != FORM) continue;   // warp-uniform
+    const MatlTL M = matl[sec];
+    const int *conn = elem_node_item + elem_node_index[e];
+    if (lane < NN) {
+      const size_t n3 = 3 * (size_t)(conn[lane] - 1);
+#pragma unroll
+      for (int c = 0; c < 3; c++) { S.xc[3 * lane + c] = node[n3 + c]; S.uc[3 * lane + c] = u[n3 + c]; }
+    }
+    __syncwarp();
+    double kb[ROUNDS][9];
+    element_stiffness_tl_warp<FORM>(lane, S, M, gp_strain + 48 * (size_t)e, gp_stress + 48 * (size_t)e, kb);
+    if (ke_out) {
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < ROUNDS; r++) {
+        const int t = r * 32 + lane;
+        if (t < NB) {
+#pragma unroll
+          for (int a = 0; a < 9; a++) S.stage[t * 9 + a] = kb[r][a];
+        }
+      }
+      __syncwarp();
+      double2 *dst = reinterpret_cast<double2 *>(ke_out + 9 * (slot_base + (size_t)(e - e0) * NB));
+      const double2 *src = reinterpret_cast<const double2 *>(S.stage);
+      for (int q = lane; q < NB * 9 / 2; q += 32) dst[q] = src[q];
+      __syncwarp();
+      continue;
+    }
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+      const int t = r * 32 + lane;
+      if (t < NB) {
+        const unsigned s = slot[slot_base + (size_t)(e - e0) * NB + t];
+        if (s != kBadSlot) {
+          double *dst = vals + 9 * (size_t)s;
+#pragma unroll
+          for (int a = 0; a < 9; a++) atomicAdd(dst + a, kb[r][a]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// utot = unode + dunode; writes the new strain / stress of every Gauss point and adds the element's internal
+// force into qforce (zeroed by the caller)
+template <int FORM, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+update_tl_kernel(int e0, int e1, const int *__restrict__ elem_node_index, const int *__restrict__ elem_node_item,
+                 const double *__restrict__ node, const double *__restrict__ utot, const int *__restrict__ section_ID,
+                 const elem::MatlTL *__restrict__ matl, const int *__restrict__ sect_form,
+                 double *__restrict__ gp_strain, double *__restrict__ gp_stress, double *__restrict__ qforce) {
+  using namespace elem;
+  constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ScratchTL &S = reinterpret_cast<ScratchTL *>(smem_raw)[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const int wg = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  const int nw = gridDim.x * WARPS;
+  for (int e = e0 + wg; e < e1; e += nw) {
+    const int sec = section_ID[e] - 1;
+    if (FORM != FORM_TET10 && sect_form[sec] != FORM) continue;
+    const MatlTL M = matl[sec];
+    const int *conn = elem_node_item + elem_node_index[e];
+    if (lane < NN) {
+      const size_t n3 = 3 * (size_t)(conn[lane] - 1);
+#pragma unroll
+      for (int c = 0; c < 3; c++) { S.xc[3 * lane + c] = node[n3 + c]; S.uc[3 * lane + c] = utot[n3 + c]; }
+    }
+    __syncwarp();
+    const double q = element_update_tl_warp<FORM>(lane, S, M, gp_strain + 48 * (size_t)e, gp_stress + 48 * (size_t)e);
+    if (lane < 3 * NN) atomicAdd(qforce + 3 * (size_t)(conn[lane / 3] - 1) + lane % 3, q);
+    __syncwarp();
+  }
+}
+
 // ---- hecmw_mat_ass_bc, batched ---------------------------------------------------------------
 // One thread per (constraint c, entry t of node n's row): t = 0 is the diagonal block,
 // 1..nL the L entries, then the U entries.  STAGE 0 subtracts K(:,c)*rhs from B (reading the

@@ -613,20 +613,20 @@ int fistr_b200_host_unregister(void *ptr) {
 }
 
 // ---- fstr_StiffMatrix --------------------------------------------------------------------------
-int fistr_b200_stiffmatrix_3d(int n_node, const double *node, int n_elem, int n_elem_type,
-                              const int *elem_type_index, const int *elem_type_item,
-                              const int *elem_node_index, const int *elem_node_item,
-                              const int *section_ID, int n_sect, const int *sect_elemopt361,
-                              const double *sect_E, const double *sect_nu, double *D, double *AL,
-                              double *AU, double *time_ms) {
+// Shared front half of the assembly entry points: mesh / section upload (connectivity only when the host array
+// changes identity), slot table and its inverse (gather map), element-matrix scratch.
+static int assembly_prepare(const char *who, int n_node, const double *node, int n_elem, int n_elem_type,
+                            const int *elem_type_index, const int *elem_type_item, const int *elem_node_index,
+                            const int *elem_node_item, const int *section_ID, int n_sect,
+                            const int *sect_elemopt361, const double *sect_E, const double *sect_nu,
+                            std::vector<size_t> &slot_base, double *&ke_out, bool &use_gather) {
   FB_REQUIRE_INIT();
   Context &C = ctx();
-  if (!C.have_structure) return fail(FISTR_B200_ERR_STATE, "stiffmatrix_3d before mat_structure");
-  if (n_node != C.NP) return fail(FISTR_B200_ERR_ARG, "stiffmatrix_3d: n_node (%d) != NP (%d)", n_node, C.NP);
-  const double t_begin = now_s();
+  if (!C.have_structure) return fail(FISTR_B200_ERR_STATE, "%s before mat_structure", who);
+  if (n_node != C.NP) return fail(FISTR_B200_ERR_ARG, "%s: n_node (%d) != NP (%d)", who, n_node, C.NP);
   for (int it = 0; it < n_elem_type; it++)
     if (elem_type_item[it] != 361 && elem_type_item[it] != 342)
-      return fail(FISTR_B200_ERR_ARG, "stiffmatrix_3d: element type %d is outside the hot-path scope (361, 342)", elem_type_item[it]);
+      return fail(FISTR_B200_ERR_ARG, "%s: element type %d is outside the hot-path scope (361, 342)", who, elem_type_item[it]);
   const size_t nconn = (size_t)elem_node_index[n_elem];
   // mesh upload (connectivity is re-uploaded only when the host array changes identity)
   const bool new_mesh = (C.key_elem_node_item != elem_node_item) || !C.slot_valid;
@@ -641,7 +641,7 @@ int fistr_b200_stiffmatrix_3d(int n_node, const double *node, int n_elem, int n_
     std::vector<int> sec((size_t)n_elem, 1);
     if (section_ID) sec.assign(section_ID, section_ID + n_elem);
     for (int e = 0; e < n_elem; e++)
-      if (sec[e] < 1 || sec[e] > n_sect) return fail(FISTR_B200_ERR_ARG, "stiffmatrix_3d: section_ID out of range");
+      if (sec[e] < 1 || sec[e] > n_sect) return fail(FISTR_B200_ERR_ARG, "%s: section_ID out of range", who);
     FB_CUDA(cudaMemcpy(C.m_sec.p, sec.data(), sizeof(int) * (size_t)n_elem, cudaMemcpyHostToDevice));
     std::vector<double> sd(3 * (size_t)n_sect);
     for (int s = 0; s < n_sect; s++) elem::elastic_constants(sect_E[s], sect_nu[s], sd[3 * s], sd[3 * s + 1], sd[3 * s + 2]);
@@ -649,7 +649,7 @@ int fistr_b200_stiffmatrix_3d(int n_node, const double *node, int n_elem, int n_
     FB_CUDA(cudaMemcpy(C.m_form.p, sect_elemopt361, sizeof(int) * (size_t)n_sect, cudaMemcpyHostToDevice));
   }
   // slot table (topology only)
-  std::vector<size_t> slot_base((size_t)n_elem_type + 1, 0);
+  slot_base.assign((size_t)n_elem_type + 1, 0);
   for (int it = 0; it < n_elem_type; it++) {
     const int nn = etype_max_node(elem_type_item[it]);
     slot_base[it + 1] = slot_base[it] + (size_t)(elem_type_index[it + 1] - elem_type_index[it]) * nn * nn;
@@ -687,7 +687,7 @@ int fistr_b200_stiffmatrix_3d(int n_node, const double *node, int n_elem, int n_
         // exclusive scan in chunks of < 2^31 items (CUB takes an int count), carrying the running offset
         FB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cursor.p, C.gptr.p, (int)std::min<size_t>(nblk + 1, 1u << 30), C.stream));
         if (tmp.alloc(tmp_bytes + 16)) return FISTR_B200_ERR_CUDA;
-        if (nblk + 1 > (1u << 30)) return fail(FISTR_B200_ERR_ARG, "stiffmatrix_3d: too many blocks for the gather map");
+        if (nblk + 1 > (1u << 30)) return fail(FISTR_B200_ERR_ARG, "%s: too many blocks for the gather map", who);
         FB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, cursor.p, C.gptr.p, (int)(nblk + 1), C.stream));
         FB_CUDA(cudaMemsetAsync(cursor.p, 0, sizeof(unsigned) * (nblk + 1), C.stream));
         gather_fill_kernel<<<C.grid_for(ncontrib, 256, 16), 256, 0, C.stream>>>(ncontrib, C.slot.p, C.gptr.p, cursor.p, C.gsrc.p);
@@ -704,9 +704,26 @@ int fistr_b200_stiffmatrix_3d(int n_node, const double *node, int n_elem, int n_
     }
   }
   // element-matrix scratch of the gather assembly; falls back to the atomic scatter if it does not fit
-  bool use_gather = C.gather_valid && C.get("asm_gather", 1) != 0;
+  use_gather = C.gather_valid && C.get("asm_gather", 1) != 0;
   if (use_gather && C.ke.alloc(9 * slot_base.back())) { cudaGetLastError(); use_gather = false; }
-  double *ke_out = use_gather ? C.ke.p : nullptr;
+  ke_out = use_gather ? C.ke.p : nullptr;
+  return 0;
+}
+
+int fistr_b200_stiffmatrix_3d(int n_node, const double *node, int n_elem, int n_elem_type,
+                              const int *elem_type_index, const int *elem_type_item,
+                              const int *elem_node_index, const int *elem_node_item,
+                              const int *section_ID, int n_sect, const int *sect_elemopt361,
+                              const double *sect_E, const double *sect_nu, double *D, double *AL,
+                              double *AU, double *time_ms) {
+  const double t_begin = now_s();
+  std::vector<size_t> slot_base;
+  double *ke_out = nullptr;
+  bool use_gather = false;
+  FB_TRY(assembly_prepare("stiffmatrix_3d", n_node, node, n_elem, n_elem_type, elem_type_index, elem_type_item,
+                          elem_node_index, elem_node_item, section_ID, n_sect, sect_elemopt361, sect_E, sect_nu,
+                          slot_base, ke_out, use_gather));
+  Context &C = ctx();
   // hecmw_mat_clear + element loop
   cudaEvent_t ev0, ev1;
   FB_CUDA(cudaEventCreate(&ev0)); FB_CUDA(cudaEventCreate(&ev1));
@@ -756,6 +773,183 @@ int fistr_b200_stiffmatrix_3d(int n_node, const double *node, int n_elem, int n_
   C.sell_valid = false;
   FB_TRY(fistr_b200_mat_download(D, AL, AU, nullptr, nullptr));
   if (time_ms) { time_ms[0] = ms; time_ms[1] = (now_s() - t_begin) * 1e3; }
+  return 0;
+}
+
+// ---- nonlinear (total Lagrangian) assembly / update: fstr_StiffMatrix + fstr_UpdateNewton under NLGEOM ------
+static int nl_upload_materials(Context &C, int n_sect, const int *sect_elemopt361, const double *sect_E,
+                               const double *sect_nu, const int *sect_mtype, const double *sect_hyper, const int *ett,
+                               int n_elem_type) {
+  std::vector<elem::MatlTL> ml((size_t)n_sect);
+  bool has361 = false;
+  for (int it = 0; it < n_elem_type; it++) has361 = has361 || (ett[it] == 361);
+  for (int s = 0; s < n_sect; s++) {
+    elem::MatlTL &M = ml[s];
+    M.mtype = sect_mtype ? sect_mtype[s] : 0;
+    if (M.mtype != elem::MAT_ELASTIC && M.mtype != elem::MAT_MOONEYRIVLIN)
+      return fail(FISTR_B200_ERR_ARG, "nl: material type %d not supported (0 ELASTIC, 1 MOONEYRIVLIN)", M.mtype);
+    elem::elastic_constants(sect_E[s], sect_nu[s], M.D11, M.D12, M.D44);
+    for (int k = 0; k < 3; k++) M.c[k] = sect_hyper ? sect_hyper[3 * s + k] : 0.0;
+    if (M.mtype == elem::MAT_MOONEYRIVLIN && !(M.c[2] > 0.0)) return fail(FISTR_B200_ERR_ARG, "nl: Mooney-Rivlin D must be > 0");
+    // the 361 IC element aborts under NLGEOM in the reference (fstr_StiffMatrix.f90:118, fstr_Update.f90:163)
+    if (has361 && sect_elemopt361[s] != 1 && sect_elemopt361[s] != 2)
+      return fail(FISTR_B200_ERR_ARG, "###ERROR### : nonlinear analysis not supported with 361 IC element (elemopt361=%d)", sect_elemopt361[s]);
+  }
+  if (C.m_matl.alloc((size_t)n_sect)) return FISTR_B200_ERR_CUDA;
+  FB_CUDA(cudaMemcpy(C.m_matl.p, ml.data(), sizeof(elem::MatlTL) * ml.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static int nl_ensure_state(Context &C, int n_elem) {
+  if (C.nl_n_elem == n_elem && C.gp_strain.p) return 0;
+  const size_t n = 48 * (size_t)std::max(n_elem, 1);
+  if (C.gp_strain.alloc(n) || C.gp_stress.alloc(n)) return FISTR_B200_ERR_CUDA;
+  FB_CUDA(cudaMemsetAsync(C.gp_strain.p, 0, sizeof(double) * n, C.stream));
+  FB_CUDA(cudaMemsetAsync(C.gp_stress.p, 0, sizeof(double) * n, C.stream));
+  C.nl_n_elem = n_elem;
+  return 0;
+}
+
+constexpr int kNlWarps = 2;   // warps (= elements in flight) per block of the TL kernels: ScratchTL is 16 KB per warp
+static int nl_set_attrs() {
+  constexpr int WARPS = kNlWarps;
+  static bool done = false;
+  if (done) return 0;
+  const int smem = (int)(sizeof(elem::ScratchTL) * WARPS);
+  FB_CUDA(cudaFuncSetAttribute(stiff_tl_kernel<elem::FORM_FI, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  FB_CUDA(cudaFuncSetAttribute(stiff_tl_kernel<elem::FORM_BBAR, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  FB_CUDA(cudaFuncSetAttribute(stiff_tl_kernel<elem::FORM_TET10, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  FB_CUDA(cudaFuncSetAttribute(update_tl_kernel<elem::FORM_FI, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  FB_CUDA(cudaFuncSetAttribute(update_tl_kernel<elem::FORM_BBAR, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  FB_CUDA(cudaFuncSetAttribute(update_tl_kernel<elem::FORM_TET10, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  done = true;
+  return 0;
+}
+
+int fistr_b200_nl_state_reset(int n_elem) {
+  FB_REQUIRE_INIT();
+  Context &C = ctx();
+  C.nl_n_elem = -1;
+  FB_TRY(nl_ensure_state(C, n_elem));
+  FB_CUDA(cudaStreamSynchronize(C.stream));
+  return 0;
+}
+
+int fistr_b200_nl_state_download(double *strain, double *stress) {
+  FB_REQUIRE_INIT();
+  Context &C = ctx();
+  if (C.nl_n_elem <= 0) return fail(FISTR_B200_ERR_STATE, "nl_state_download: no Gauss-point state");
+  FB_CUDA(cudaStreamSynchronize(C.stream));
+  if (strain) FB_CUDA(cudaMemcpy(strain, C.gp_strain.p, sizeof(double) * 48 * (size_t)C.nl_n_elem, cudaMemcpyDeviceToHost));
+  if (stress) FB_CUDA(cudaMemcpy(stress, C.gp_stress.p, sizeof(double) * 48 * (size_t)C.nl_n_elem, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int fistr_b200_nl_stiffmatrix_3d(int n_node, const double *node, int n_elem, int n_elem_type,
+                                 const int *elem_type_index, const int *elem_type_item,
+                                 const int *elem_node_index, const int *elem_node_item, const int *section_ID,
+                                 int n_sect, const int *sect_elemopt361, const double *sect_E, const double *sect_nu,
+                                 const int *sect_mtype, const double *sect_hyper, const double *u, double *D,
+                                 double *AL, double *AU, double *time_ms) {
+  const double t_begin = now_s();
+  std::vector<size_t> slot_base;
+  double *ke_out = nullptr;
+  bool use_gather = false;
+  FB_TRY(assembly_prepare("nl_stiffmatrix_3d", n_node, node, n_elem, n_elem_type, elem_type_index, elem_type_item,
+                          elem_node_index, elem_node_item, section_ID, n_sect, sect_elemopt361, sect_E, sect_nu,
+                          slot_base, ke_out, use_gather));
+  Context &C = ctx();
+  FB_TRY(nl_upload_materials(C, n_sect, sect_elemopt361, sect_E, sect_nu, sect_mtype, sect_hyper, elem_type_item, n_elem_type));
+  FB_TRY(nl_ensure_state(C, n_elem));
+  if (C.m_u.alloc(3 * (size_t)n_node)) return FISTR_B200_ERR_CUDA;
+  if (u) FB_CUDA(cudaMemcpyAsync(C.m_u.p, u, sizeof(double) * 3 * (size_t)n_node, cudaMemcpyHostToDevice, C.stream));
+  else FB_CUDA(cudaMemsetAsync(C.m_u.p, 0, sizeof(double) * 3 * (size_t)n_node, C.stream));
+  constexpr int WARPS = kNlWarps;
+  FB_TRY(nl_set_attrs());
+  const size_t smem = sizeof(elem::ScratchTL) * WARPS;
+  cudaEvent_t ev0, ev1;
+  FB_CUDA(cudaEventCreate(&ev0)); FB_CUDA(cudaEventCreate(&ev1));
+  FB_CUDA(cudaEventRecord(ev0, C.stream));
+  if (!use_gather) FB_CUDA(cudaMemsetAsync(C.vals.p, 0, sizeof(double) * 9 * ((size_t)C.NP + C.NPL + C.NPU), C.stream));
+  for (int it = 0; it < n_elem_type; it++) {
+    const int e0 = elem_type_index[it], e1 = elem_type_index[it + 1];
+    if (e1 <= e0) continue;
+    const int grid = C.grid_for((size_t)(e1 - e0) * 32, WARPS * 32, 8);
+#define FB_TL_STIFF(FORM_)                                                                                              \
+  stiff_tl_kernel<FORM_, WARPS><<<grid, WARPS * 32, smem, C.stream>>>(e0, e1, C.m_eni.p, C.m_enn.p, C.m_node.p, C.m_u.p, \
+      C.m_sec.p, C.m_matl.p, C.m_form.p, C.gp_strain.p, C.gp_stress.p, C.slot.p, slot_base[it], C.vals.p, ke_out);       \
+  FB_LAUNCH_CHECK();
+    if (elem_type_item[it] == 342) { FB_TL_STIFF(elem::FORM_TET10) }
+    else {
+      bool has[3] = {false, false, false};
+      for (int s = 0; s < n_sect; s++) has[sect_elemopt361[s]] = true;   // 1 or 2, validated above
+      if (has[1]) { FB_TL_STIFF(elem::FORM_FI) }
+      if (has[2]) { FB_TL_STIFF(elem::FORM_BBAR) }
+    }
+#undef FB_TL_STIFF
+  }
+  if (use_gather) {
+    const size_t nblk = (size_t)C.NP + C.NPL + C.NPU;
+    gather_sum_kernel<<<C.grid_for(9 * nblk, 256, 8), 256, 0, C.stream>>>(nblk, C.gptr.p, C.gsrc.p, C.ke.p, C.vals.p);
+    FB_LAUNCH_CHECK();
+  }
+  FB_CUDA(cudaEventRecord(ev1, C.stream));
+  FB_CUDA(cudaStreamSynchronize(C.stream));
+  float ms = 0.f;
+  FB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+  cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+  C.values_on_device = true;
+  C.sell_valid = false;
+  FB_TRY(fistr_b200_mat_download(D, AL, AU, nullptr, nullptr));
+  if (time_ms) { time_ms[0] = ms; time_ms[1] = (now_s() - t_begin) * 1e3; }
+  return 0;
+}
+
+int fistr_b200_nl_update_3d(int n_node, const double *node, int n_elem, int n_elem_type,
+                            const int *elem_type_index, const int *elem_type_item, const int *elem_node_index,
+                            const int *elem_node_item, const int *section_ID, int n_sect,
+                            const int *sect_elemopt361, const double *sect_E, const double *sect_nu,
+                            const int *sect_mtype, const double *sect_hyper, const double *unode,
+                            const double *dunode, double *QFORCE) {
+  std::vector<size_t> slot_base;
+  double *ke_out = nullptr;
+  bool use_gather = false;
+  FB_TRY(assembly_prepare("nl_update_3d", n_node, node, n_elem, n_elem_type, elem_type_index, elem_type_item,
+                          elem_node_index, elem_node_item, section_ID, n_sect, sect_elemopt361, sect_E, sect_nu,
+                          slot_base, ke_out, use_gather));
+  Context &C = ctx();
+  FB_TRY(nl_upload_materials(C, n_sect, sect_elemopt361, sect_E, sect_nu, sect_mtype, sect_hyper, elem_type_item, n_elem_type));
+  FB_TRY(nl_ensure_state(C, n_elem));
+  const size_t n3 = 3 * (size_t)n_node;
+  if (C.m_u.alloc(n3) || C.m_qf.alloc(n3)) return FISTR_B200_ERR_CUDA;
+  {   // totaldisp = unode + dunode (UPDATE_C3: static_LIB_3d.f90:561)
+    std::vector<double> tot(n3);
+    for (size_t i = 0; i < n3; i++) tot[i] = (unode ? unode[i] : 0.0) + (dunode ? dunode[i] : 0.0);
+    FB_CUDA(cudaMemcpy(C.m_u.p, tot.data(), sizeof(double) * n3, cudaMemcpyHostToDevice));
+  }
+  FB_CUDA(cudaMemsetAsync(C.m_qf.p, 0, sizeof(double) * n3, C.stream));
+  constexpr int WARPS = kNlWarps;
+  FB_TRY(nl_set_attrs());
+  const size_t smem = sizeof(elem::ScratchTL) * WARPS;
+  for (int it = 0; it < n_elem_type; it++) {
+    const int e0 = elem_type_index[it], e1 = elem_type_index[it + 1];
+    if (e1 <= e0) continue;
+    const int grid = C.grid_for((size_t)(e1 - e0) * 32, WARPS * 32, 8);
+#define FB_TL_UPDATE(FORM_)                                                                                              \
+  update_tl_kernel<FORM_, WARPS><<<grid, WARPS * 32, smem, C.stream>>>(e0, e1, C.m_eni.p, C.m_enn.p, C.m_node.p, C.m_u.p, \
+      C.m_sec.p, C.m_matl.p, C.m_form.p, C.gp_strain.p, C.gp_stress.p, C.m_qf.p);                                         \
+  FB_LAUNCH_CHECK();
+    if (elem_type_item[it] == 342) { FB_TL_UPDATE(elem::FORM_TET10) }
+    else {
+      bool has[3] = {false, false, false};
+      for (int s = 0; s < n_sect; s++) has[sect_elemopt361[s]] = true;
+      if (has[1]) { FB_TL_UPDATE(elem::FORM_FI) }
+      if (has[2]) { FB_TL_UPDATE(elem::FORM_BBAR) }
+    }
+#undef FB_TL_UPDATE
+  }
+  FB_CUDA(cudaMemcpyAsync(QFORCE, C.m_qf.p, sizeof(double) * n3, cudaMemcpyDeviceToHost, C.stream));
+  FB_CUDA(cudaStreamSynchronize(C.stream));
   return 0;
 }
 

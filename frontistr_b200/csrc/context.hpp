@@ -75,6 +75,10 @@ struct Context {
   // ---- assembly
   DevBuf<unsigned> gptr, gsrc;     // inverse of the slot table: block -> its contributions (ascending)
   DevBuf<double> ke;               // element-matrix scratch of the gather assembly
+  DevBuf<double> gp_strain, gp_stress;   // nonlinear path: Gauss-point state [element][8][6]
+  DevBuf<elem::MatlTL> m_matl;           // nonlinear path: per-section material records
+  DevBuf<double> m_u, m_qf;              // nonlinear path: nodal displacement in, internal force out
+  int nl_n_elem = 0;
   bool gather_valid = false;
   DevBuf<unsigned> slot;
   DevBuf<int> m_eni, m_enn, m_sec, m_form;

@@ -111,8 +111,8 @@ FB_HD void jacobian(int nn, const double *xc, const double (*d)[3], double &det,
 }
 
 // ---- phase G: lane g < NGP computes the geometry of Gauss point g --------------------------
-template <int FORM>
-FB_HD void phase_geometry(int lane, Scratch &S) {
+template <int FORM, class SCR>
+FB_HD void phase_geometry(int lane, SCR &S) {
   constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
   constexpr int NGP = (FORM == FORM_TET10) ? 4 : 8;
   constexpr int NT = (FORM == FORM_IC) ? 11 : NN;
@@ -387,6 +387,271 @@ FB_WARP_FN void element_stiffness_warp(int lane, Scratch &S, double D11, double 
       if (t < NB) ic_condense_block(S, t / NN, t % NN, kb[r]);
     }
   }
+}
+#endif
+
+// =============================================================================================
+// Geometrically nonlinear path (total Lagrangian): STF_C3 / STF_C3D8Bbar with flag == TOTALLAG
+// (static_LIB_3d.f90:47-205, static_LIB_C3D8.f90:23-198) and UPDATE_C3 / Update_C3D8Bbar
+// (static_LIB_3d.f90:516-837, static_LIB_C3D8.f90:203-552) for ELASTIC and MOONEYRIVLIN materials.
+// One element per warp as above; per-Gauss-point state (Green-Lagrange strain, 2nd Piola-Kirchhoff stress) lives in
+// dense device arrays [element][8][6].  SURVEY 8(f) rank 2.
+// =============================================================================================
+struct alignas(16) ScratchTL {
+  double stage[100 * 9];    // gather-mode output staging (must stay first: 16-byte aligned)
+  double xc[10 * 3];        // element coordinates
+  double uc[10 * 3];        // nodal displacement the deformation gradient is formed from
+  double gd[8 * 10 * 3];    // gderiv[g][n][3]
+  double bb[8 * 8 * 3];     // B-bar correction (Bbar - gderiv)/3
+  double wdet[8];           // weight * det
+  double F[8 * 9];          // dudx(i,j) per Gauss point, [g][3*i+j]
+  double Dm[8 * 36];        // material tangent per Gauss point, row-major 6x6
+  double sg[8 * 6];         // 2nd Piola-Kirchhoff stress per Gauss point (xx yy zz xy yz zx)
+  double qf[8 * 30];        // update: internal-force contribution of every Gauss point
+};
+
+enum Material { MAT_ELASTIC = 0, MAT_MOONEYRIVLIN = 1 };
+
+// reduced invariants of C = 2E + 1 and their derivatives (cderiv, lib/physics/Hyperelastic.f90:13-131);
+// d2 == nullptr skips the second derivatives
+FB_HD void mr_cderiv(const double *strain, double &inv3b, double (*dib)[3][3], double (*d2)[3][3][3][3]) {
+  const double delta[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  double ctn[3][3], ci[3][3], didc[3][3][3];
+  ctn[0][0] = strain[0] * 2.0 + 1.0; ctn[1][1] = strain[1] * 2.0 + 1.0; ctn[2][2] = strain[2] * 2.0 + 1.0;
+  ctn[0][1] = ctn[1][0] = strain[3]; ctn[1][2] = ctn[2][1] = strain[4]; ctn[2][0] = ctn[0][2] = strain[5];
+  const double inv1 = ctn[0][0] + ctn[1][1] + ctn[2][2];
+  const double inv2 = ctn[1][1] * ctn[2][2] + ctn[0][0] * ctn[2][2] + ctn[0][0] * ctn[1][1] - ctn[1][2] * ctn[1][2] -
+                      ctn[0][2] * ctn[0][2] - ctn[0][1] * ctn[0][1];
+  const double inv3 = ctn[0][0] * ctn[1][1] * ctn[2][2] + ctn[1][0] * ctn[2][1] * ctn[0][2] + ctn[2][0] * ctn[0][1] * ctn[1][2] -
+                      ctn[2][0] * ctn[1][1] * ctn[0][2] - ctn[1][0] * ctn[0][1] * ctn[2][2] - ctn[0][0] * ctn[2][1] * ctn[1][2];
+  const double inv33 = pow(inv3, -1.0 / 3.0);
+  ci[0][0] = (ctn[1][1] * ctn[2][2] - ctn[1][2] * ctn[1][2]) / inv3;
+  ci[1][1] = (ctn[0][0] * ctn[2][2] - ctn[0][2] * ctn[0][2]) / inv3;
+  ci[2][2] = (ctn[0][0] * ctn[1][1] - ctn[0][1] * ctn[0][1]) / inv3;
+  ci[0][1] = ci[1][0] = (ctn[0][2] * ctn[1][2] - ctn[0][1] * ctn[2][2]) / inv3;
+  ci[0][2] = ci[2][0] = (ctn[0][1] * ctn[1][2] - ctn[1][1] * ctn[0][2]) / inv3;
+  ci[1][2] = ci[2][1] = (ctn[0][1] * ctn[0][2] - ctn[0][0] * ctn[1][2]) / inv3;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      didc[0][i][j] = delta[i][j];
+      didc[1][i][j] = inv1 * delta[i][j] - ctn[i][j];
+      didc[2][i][j] = inv3 * ci[i][j];
+    }
+  inv3b = sqrt(inv3);
+  const double i2 = inv33 * inv33, i4 = i2 * i2, i5 = i4 * inv33, i7 = i5 * i2, i8 = i4 * i4;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      dib[0][i][j] = -i4 * inv1 * didc[2][i][j] / 3.0 + inv33 * didc[0][i][j];
+      dib[1][i][j] = -2.0 * i5 * inv2 * didc[2][i][j] / 3.0 + i2 * didc[1][i][j];
+      dib[2][i][j] = didc[2][i][j] / (2.0 * sqrt(inv3));
+    }
+  if (!d2) return;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+      for (int k = 0; k < 3; k++)
+        for (int l = 0; l < 3; l++) {
+          const double h2 = delta[i][j] * delta[k][l] - (delta[i][k] * delta[j][l] + delta[i][l] * delta[j][k]) / 2.0;
+          const double h3 = inv3 * (ci[k][l] * ci[i][j] - (ci[i][k] * ci[l][j] + ci[i][l] * ci[k][j]) / 2.0);
+          d2[0][i][j][k][l] = 4.0 / 9.0 * i7 * inv1 * didc[2][i][j] * didc[2][k][l] -
+                              i4 / 3.0 * (didc[0][k][l] * didc[2][i][j] + didc[0][i][j] * didc[2][k][l]) - i4 / 3.0 * inv1 * h3;
+          d2[1][i][j][k][l] = 10.0 / 9.0 * i8 * inv2 * didc[2][i][j] * didc[2][k][l] -
+                              2.0 / 3.0 * i5 * (didc[1][k][l] * didc[2][i][j] + didc[1][i][j] * didc[2][k][l]) -
+                              2.0 / 3.0 * i5 * inv2 * h3 + i2 * h2;
+          d2[2][i][j][k][l] = -didc[2][i][j] * didc[2][k][l] / (4.0 * pow(inv3, 1.5)) + h3 / (2.0 * sqrt(inv3));
+        }
+}
+
+// calUpdateElasticMooneyRivlin (Hyperelastic.f90:250-284): S from the Green-Lagrange strain
+FB_HD void mr_stress(const double *c, const double *strain, double *stress) {
+  double i3, dib[3][3][3];
+  mr_cderiv(strain, i3, dib, nullptr);
+  const int vi[6] = {0, 1, 2, 0, 1, 0}, vj[6] = {0, 1, 2, 1, 2, 2};
+  for (int a = 0; a < 6; a++) {
+    const int k = vi[a], l = vj[a];
+    stress[a] = 2.0 * (dib[0][k][l] * c[0] + dib[1][k][l] * c[1] + 2.0 * (i3 - 1.0) * dib[2][k][l] / c[2]);
+  }
+}
+
+// calElasticMooneyRivlin + mat_c2d (Hyperelastic.f90:221-246, calMatMatrix.f90:154-197): D(6,6) row-major
+FB_HD void mr_tangent(const double *c, const double *strain, double *D) {
+  double i3, dib[3][3][3], d2[3][3][3][3][3];
+  mr_cderiv(strain, i3, dib, d2);
+  const int vi[6] = {0, 1, 2, 0, 1, 2}, vj[6] = {0, 1, 2, 1, 2, 0};   // 11 22 33 12 23 31
+  for (int a = 0; a < 6; a++)
+    for (int b = 0; b < 6; b++) {
+      const int k = vi[a], l = vj[a], m = vi[b], n = vj[b];
+      D[6 * a + b] = 4.0 * (d2[0][k][l][m][n] * c[0] + d2[1][k][l][m][n] * c[1] +
+                            2.0 * (dib[2][k][l] * dib[2][m][n] + (i3 - 1.0) * d2[2][k][l][m][n]) / c[2]);
+    }
+}
+
+// per-section material record handed to the TL kernels
+struct MatlTL {
+  int mtype;             // MAT_ELASTIC / MAT_MOONEYRIVLIN
+  double D11, D12, D44;  // elastic constants (ElasticLinear.f90:48-59)
+  double c[3];           // Mooney-Rivlin C10, C01, D
+};
+
+FB_HD void tl_tangent(const MatlTL &M, const double *strain, double *D) {   // MatlMatrix, calMatMatrix.f90:29-112
+  if (M.mtype == MAT_MOONEYRIVLIN) { mr_tangent(M.c, strain, D); return; }
+  for (int a = 0; a < 36; a++) D[a] = 0.0;
+  D[0] = D[7] = D[14] = M.D11;
+  D[1] = D[2] = D[6] = D[8] = D[12] = D[13] = M.D12;
+  D[21] = D[28] = D[35] = M.D44;
+}
+
+// BL = BL0 + BL1 of one node (6x3): gderiv g[3], B-bar correction bbn[3] (nullptr: plain), dudx F[9]
+FB_HD void tl_build_B(const double *g, const double *bbn, const double *F, double (*B)[3]) {
+  for (int c = 0; c < 3; c++) {
+    const double d0 = F[3 * c + 0], d1 = F[3 * c + 1], d2 = F[3 * c + 2];   // gdispderiv(c,1..3)
+    const double vol = bbn ? bbn[c] : 0.0;
+    B[0][c] = vol + (c == 0 ? g[0] : 0.0) + d0 * g[0];
+    B[1][c] = vol + (c == 1 ? g[1] : 0.0) + d1 * g[1];
+    B[2][c] = vol + (c == 2 ? g[2] : 0.0) + d2 * g[2];
+    B[3][c] = (c == 0 ? g[1] : (c == 1 ? g[0] : 0.0)) + d1 * g[0] + d0 * g[1];
+    B[4][c] = (c == 1 ? g[2] : (c == 2 ? g[1] : 0.0)) + d1 * g[2] + d2 * g[1];
+    B[5][c] = (c == 0 ? g[2] : (c == 2 ? g[0] : 0.0)) + d2 * g[0] + d0 * g[2];
+  }
+}
+
+// lane g < NGP: dudx at Gauss point g from S.uc; optionally the tangent at the stored strain and the stored stress
+template <int FORM>
+FB_HD void tl_phase_state(int lane, ScratchTL &S, const MatlTL &M, const double *gp_strain, const double *gp_stress) {
+  constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
+  constexpr int NGP = (FORM == FORM_TET10) ? 4 : 8;
+  if (lane >= NGP) return;
+  const double *gd = S.gd + lane * NN * 3;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double s = 0.0;
+      for (int n = 0; n < NN; n++) s += S.uc[3 * n + i] * gd[3 * n + j];
+      S.F[9 * lane + 3 * i + j] = s;
+    }
+  if (gp_strain) tl_tangent(M, gp_strain + 6 * lane, S.Dm + 36 * lane);
+  if (gp_stress)
+    for (int k = 0; k < 6; k++) S.sg[6 * lane + k] = gp_stress[6 * lane + k];
+}
+
+// 3x3 block (i,j) of the tangent stiffness: sum_g w (B_i^T D B_j + (g_i^T S g_j) 1)
+template <int FORM>
+FB_HD void tl_pair_block(const ScratchTL &S, int i, int j, double *k9) {
+  constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
+  constexpr int NGP = (FORM == FORM_TET10) ? 4 : 8;
+  for (int a = 0; a < 9; a++) k9[a] = 0.0;
+  for (int g = 0; g < NGP; g++) {
+    const double *gi = S.gd + (g * NN + i) * 3, *gj = S.gd + (g * NN + j) * 3;
+    const double *F = S.F + 9 * g, *D = S.Dm + 36 * g, *sg = S.sg + 6 * g;
+    const double w = S.wdet[g];
+    double Bi[6][3], Bj[6][3];
+    tl_build_B(gi, FORM == FORM_BBAR ? S.bb + (g * 8 + i) * 3 : nullptr, F, Bi);
+    tl_build_B(gj, FORM == FORM_BBAR ? S.bb + (g * 8 + j) * 3 : nullptr, F, Bj);
+    for (int b = 0; b < 3; b++) {
+      double DB[6];
+      for (int r = 0; r < 6; r++) {
+        double s = 0.0;
+        for (int k = 0; k < 6; k++) s += D[6 * r + k] * Bj[k][b];
+        DB[r] = s;
+      }
+      for (int a = 0; a < 3; a++) {
+        double s = 0.0;
+        for (int r = 0; r < 6; r++) s += Bi[r][a] * DB[r];
+        k9[3 * a + b] += s * w;
+      }
+    }
+    // initial-stress matrix BN^T S BN (static_LIB_3d.f90:170-201)
+    const double t0 = sg[0] * gj[0] + sg[3] * gj[1] + sg[5] * gj[2];
+    const double t1 = sg[3] * gj[0] + sg[1] * gj[1] + sg[4] * gj[2];
+    const double t2 = sg[5] * gj[0] + sg[4] * gj[1] + sg[2] * gj[2];
+    const double geo = (gi[0] * t0 + gi[1] * t1 + gi[2] * t2) * w;
+    k9[0] += geo; k9[4] += geo; k9[8] += geo;
+  }
+}
+
+// lane g < NGP of the update: Green-Lagrange strain, stress, internal-force contribution of Gauss point g
+// (S.uc = unode + dunode).  Writes strain/stress of the point to gp_strain/gp_stress (element-local [g][6]).
+template <int FORM>
+FB_HD void tl_phase_update(int lane, ScratchTL &S, const MatlTL &M, double *gp_strain, double *gp_stress) {
+  constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
+  constexpr int NGP = (FORM == FORM_TET10) ? 4 : 8;
+  if (lane >= NGP) return;
+  const double *gd = S.gd + lane * NN * 3;
+  const double *F = S.F + 9 * lane;
+  double dvol = 0.0;
+  if (FORM == FORM_BBAR) {   // dilatation at the centroid, static_LIB_C3D8.f90:268-272,291
+    const double *bb = S.bb + lane * 8 * 3;
+    double tr = 0.0;
+    for (int n = 0; n < 8; n++)
+      for (int c = 0; c < 3; c++) tr += S.uc[3 * n + c] * (gd[3 * n + c] + 3.0 * bb[3 * n + c]);   // Bbar = gderiv + 3 bb
+    dvol = tr / 3.0 - (F[0] + F[4] + F[8]) / 3.0;
+  }
+  double e[6];
+  e[0] = F[0] + dvol; e[1] = F[4] + dvol; e[2] = F[8] + dvol;
+  e[3] = F[1] + F[3]; e[4] = F[5] + F[7]; e[5] = F[6] + F[2];
+  e[0] += 0.5 * (F[0] * F[0] + F[3] * F[3] + F[6] * F[6]);
+  e[1] += 0.5 * (F[1] * F[1] + F[4] * F[4] + F[7] * F[7]);
+  e[2] += 0.5 * (F[2] * F[2] + F[5] * F[5] + F[8] * F[8]);
+  e[3] += F[0] * F[1] + F[3] * F[4] + F[6] * F[7];
+  e[4] += F[1] * F[2] + F[4] * F[5] + F[7] * F[8];
+  e[5] += F[0] * F[2] + F[3] * F[5] + F[6] * F[8];
+  double sg[6];
+  if (M.mtype == MAT_MOONEYRIVLIN) mr_stress(M.c, e, sg);
+  else {
+    double D[36];
+    tl_tangent(M, e, D);
+    for (int r = 0; r < 6; r++) {
+      double s = 0.0;
+      for (int k = 0; k < 6; k++) s += D[6 * r + k] * e[k];
+      sg[r] = s;
+    }
+  }
+  for (int k = 0; k < 6; k++) { gp_strain[6 * lane + k] = e[k]; gp_stress[6 * lane + k] = sg[k]; }
+  const double w = S.wdet[lane];
+  for (int n = 0; n < NN; n++) {
+    double B[6][3];
+    tl_build_B(gd + 3 * n, FORM == FORM_BBAR ? S.bb + (lane * 8 + n) * 3 : nullptr, F, B);
+    for (int c = 0; c < 3; c++) {
+      double s = 0.0;
+      for (int r = 0; r < 6; r++) s += sg[r] * B[r][c];
+      S.qf[30 * lane + 3 * n + c] = s * w;
+    }
+  }
+}
+
+#ifdef FB_WARP_FN
+// Tangent stiffness of one element (all 32 lanes; S.xc and S.uc = unode + dunode filled and synchronised).
+template <int FORM>
+FB_WARP_FN void element_stiffness_tl_warp(int lane, ScratchTL &S, const MatlTL &M, const double *gp_strain,
+                                          const double *gp_stress, double (&kb)[((FORM == FORM_TET10 ? 100 : 64) + 31) / 32][9]) {
+  constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
+  constexpr int NB = NN * NN;
+  constexpr int ROUNDS = (NB + 31) / 32;
+  phase_geometry<FORM>(lane, S);
+  FB_SYNCWARP();
+  tl_phase_state<FORM>(lane, S, M, gp_strain, gp_stress);
+  FB_SYNCWARP();
+#pragma unroll
+  for (int r = 0; r < ROUNDS; r++) {
+    const int t = r * 32 + lane;
+    if (t < NB) tl_pair_block<FORM>(S, t / NN, t % NN, kb[r]);
+  }
+}
+
+// Strain / stress update + internal force of one element (S.xc, S.uc = unode + dunode filled and synchronised).
+// On return lane t < 3 nn holds qf[t] = internal force of local dof t.
+template <int FORM>
+FB_WARP_FN double element_update_tl_warp(int lane, ScratchTL &S, const MatlTL &M, double *gp_strain, double *gp_stress) {
+  constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
+  constexpr int NGP = (FORM == FORM_TET10) ? 4 : 8;
+  phase_geometry<FORM>(lane, S);
+  FB_SYNCWARP();
+  tl_phase_state<FORM>(lane, S, M, nullptr, nullptr);
+  FB_SYNCWARP();
+  tl_phase_update<FORM>(lane, S, M, gp_strain, gp_stress);
+  FB_SYNCWARP();
+  double q = 0.0;
+  if (lane < 3 * NN)
+    for (int g = 0; g < NGP; g++) q += S.qf[30 * g + lane];
+  return q;
 }
 #endif
 

@@ -75,7 +75,72 @@ static void run_element(const double *ecoord /* (nn,3) */, double E, double nu, 
   });
 }
 
+static MatlTL make_matl(int mtype, double E, double nu, const double *hyper) {
+  MatlTL M;
+  M.mtype = mtype;
+  elastic_constants(E, nu, M.D11, M.D12, M.D44);
+  for (int k = 0; k < 3; k++) M.c[k] = hyper ? hyper[k] : 0.0;
+  return M;
+}
+
+template <int FORM>
+static void run_element_tl(const double *ecoord, const double *u, const double *gp_strain, const double *gp_stress,
+                           const MatlTL &M, double *K) {
+  constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
+  constexpr int NB = NN * NN;
+  constexpr int ROUNDS = (NB + 31) / 32;
+  static ScratchTL S;
+  std::memset(&S, 0, sizeof S);
+  for (int k = 0; k < 3 * NN; k++) { S.xc[k] = ecoord[k]; S.uc[k] = u[k]; }
+  fb::emulwarp::run_warp([&](int lane) {
+    double kb[ROUNDS][9];
+    element_stiffness_tl_warp<FORM>(lane, S, M, gp_strain, gp_stress, kb);
+    for (int r = 0; r < ROUNDS; r++) {
+      const int t = r * 32 + lane;
+      if (t >= NB) continue;
+      const int i = t / NN, j = t % NN;
+      for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) K[(3 * i + a) * (3 * NN) + 3 * j + b] = kb[r][3 * a + b];
+    }
+  });
+}
+
+template <int FORM>
+static void run_update_tl(const double *ecoord, const double *utot, const MatlTL &M, double *qf, double *strain,
+                          double *stress) {
+  constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
+  static ScratchTL S;
+  std::memset(&S, 0, sizeof S);
+  for (int k = 0; k < 3 * NN; k++) { S.xc[k] = ecoord[k]; S.uc[k] = utot[k]; }
+  fb::emulwarp::run_warp([&](int lane) {
+    const double q = element_update_tl_warp<FORM>(lane, S, M, strain, stress);
+    if (lane < 3 * NN) qf[lane] = q;
+  });
+}
+
 extern "C" {
+
+// total-Lagrangian tangent stiffness / update of one element exactly as the CUDA warp executes them
+int fbemul_element_stiffness_tl(int form, const double *ecoord, const double *u, const double *gp_strain,
+                                const double *gp_stress, int mtype, double E, double nu, const double *hyper, double *K) {
+  const MatlTL M = make_matl(mtype, E, nu, hyper);
+  switch (form) {
+    case FORM_FI: run_element_tl<FORM_FI>(ecoord, u, gp_strain, gp_stress, M, K); return 0;
+    case FORM_BBAR: run_element_tl<FORM_BBAR>(ecoord, u, gp_strain, gp_stress, M, K); return 0;
+    case FORM_TET10: run_element_tl<FORM_TET10>(ecoord, u, gp_strain, gp_stress, M, K); return 0;
+  }
+  return -1;
+}
+int fbemul_element_update_tl(int form, const double *ecoord, const double *utot, int mtype, double E, double nu,
+                             const double *hyper, double *qf, double *strain, double *stress) {
+  const MatlTL M = make_matl(mtype, E, nu, hyper);
+  switch (form) {
+    case FORM_FI: run_update_tl<FORM_FI>(ecoord, utot, M, qf, strain, stress); return 0;
+    case FORM_BBAR: run_update_tl<FORM_BBAR>(ecoord, utot, M, qf, strain, stress); return 0;
+    case FORM_TET10: run_update_tl<FORM_TET10>(ecoord, utot, M, qf, strain, stress); return 0;
+  }
+  return -1;
+}
 
 int fbemul_element_stiffness(int form, const double *ecoord, double E, double nu, double *K) {
   switch (form) {

@@ -162,6 +162,115 @@ def fstr_StiffMatrix(hecMESH, hecMAT, to_host: bool = True):
     return dict(kernel_ms=float(t[0]), total_ms=float(t[1]))
 
 
+# ---- nonlinear static (total Lagrangian): fstr_StiffMatrix / fstr_UpdateNewton under NLGEOM, fstr_Newton ----------
+def _nl_args(m):
+    eti, ett = _i32(m.elem_type_index), _i32(m.elem_type_item)
+    if not hasattr(m, "_conn") or m._conn[2] is not m.elem_node_item:
+        m._conn = (_i32(m.elem_node_index), _i32(m.elem_node_item), m.elem_node_item)
+    eni, enn = m._conn[0], m._conn[1]
+    sec = _i32(m.section_ID)
+    ns = len(m.sections)
+    form = np.array([s["elemopt361"] for s in m.sections], np.int32)
+    E = np.array([s["E"] for s in m.sections], np.float64)
+    nu = np.array([s["nu"] for s in m.sections], np.float64)
+    mtype = np.array([s.get("mtype", 0) for s in m.sections], np.int32)
+    hyper = np.array([list(s.get("hyper", (0.0, 0.0, 0.0))) for s in m.sections], np.float64).reshape(-1)
+    node = np.ascontiguousarray(m.node, np.float64)
+    keep = (eti, ett, eni, enn, sec, form, E, nu, mtype, hyper, node)
+    return keep, (m.n_node, dp(node), m.n_elem, m.n_elem_type, ip(eti), ip(ett), ip(eni), ip(enn), ip(sec), ns, ip(form),
+                  dp(E), dp(nu), ip(mtype), dp(hyper))
+
+
+def nl_state_reset(hecMESH):
+    check(_lib.lib().fistr_b200_nl_state_reset(hecMESH.n_elem))
+
+
+def nl_state_download(hecMESH):
+    e = np.zeros((hecMESH.n_elem, 8, 6)); s = np.zeros((hecMESH.n_elem, 8, 6))
+    check(_lib.lib().fistr_b200_nl_state_download(dp(e), dp(s)))
+    return e, s
+
+
+def fstr_StiffMatrix_NL(hecMESH, hecMAT, u):
+    """fstr_StiffMatrix with nlgeom_flag == TOTALLAG: tangent stiffness at u = unode + dunode, left on the device."""
+    keep, args = _nl_args(hecMESH)
+    u = np.ascontiguousarray(u, np.float64)
+    t = np.zeros(2)
+    check(_lib.lib().fistr_b200_nl_stiffmatrix_3d(*args, dp(u), None, None, None, dp(t)))
+    return dict(kernel_ms=float(t[0]), total_ms=float(t[1]))
+
+
+def fstr_UpdateNewton(hecMESH, unode, dunode):
+    """fstr_UpdateNewton: strain / stress of every Gauss point (device) and QFORCE (returned)."""
+    keep, args = _nl_args(hecMESH)
+    un = np.ascontiguousarray(unode, np.float64); dun = np.ascontiguousarray(dunode, np.float64)
+    qf = np.zeros(3 * hecMESH.n_node)
+    check(_lib.lib().fistr_b200_nl_update_3d(*args, dp(un), dp(dun), dp(qf)))
+    return qf
+
+
+def fstr_solve_NLGEOM(hecMESH, hecMAT, boundary, cload, substeps=10, converg=1.0e-3, max_iter=50):
+    """One loading step of `!STATIC, TYPE=NLGEOM` (fstr_solve_NLGEOM.f90:84-160 + fstr_Newton,
+    fstr_solve_NonLinear.f90:29-167), single subdomain: tangent assembly, Dirichlet elimination, CG solve and the
+    strain / stress / internal-force update all run on the device through the C-ABI; this loop only moves the
+    3*n_node vectors.  boundary = (nodes, dofs, values) as fstr_AddBC visits them, cload likewise.
+    Returns dict(error, unode, unode_steps, newton_iters, cg_iters)."""
+    m, A = hecMESH, hecMAT
+    n3 = 3 * m.n_node
+    bn, bd, bv = _i32(boundary[0]), _i32(boundary[1]), np.ascontiguousarray(boundary[2], np.float64)
+    cn, cd, cv = np.asarray(cload[0], np.int64), np.asarray(cload[1], np.int64), np.asarray(cload[2], np.float64)
+    if A.X is None or A.B is None:
+        A.B = np.zeros(n3); A.X = np.zeros(n3)
+    mat_structure(m, A)
+    nl_state_reset(m)
+    unode = np.zeros(n3); QF = np.zeros(n3)
+    steps = np.zeros((substeps, n3)); nit = np.zeros(substeps, np.int32)
+    cg_total, time, dt, rc = 0, 0.0, 1.0 / substeps, 0
+    bidx = 3 * (bn.astype(np.int64) - 1) + bd - 1
+    for sub in range(1, substeps + 1):
+        f1, f2 = min(time, 1.0), min(time + dt, 1.0)
+        dunode = np.zeros(n3)
+        GL = np.zeros(n3)
+        if len(cn):
+            np.add.at(GL, 3 * (cn - 1) + cd - 1, f2 * cv)
+        B = GL - QF
+        converged = False
+        for it in range(1, max_iter + 1):
+            fstr_StiffMatrix_NL(m, A, unode + dunode)
+            A.B[:] = B
+            mat_upload(A, values=False, rhs=True)
+            hecmw_mat_ass_bc(bn, bd, bv * (f2 - f1) if it == 1 else np.zeros(len(bv)))
+            if sub == 1 and it == 1:
+                A.Iarray[97] = 1
+            A.Iarray[96] = 2 if it == 1 else 1
+            A.X[:] = 0.0
+            r = hecmw_solve(m, A, device_resident=True)
+            cg_total += r["iter"]
+            if r["error"] not in (0, 2002):
+                rc = r["error"]; break
+            dunode += A.X
+            QF = fstr_UpdateNewton(m, unode, dunode)
+            B = GL - QF
+            B[bidx] = 0.0
+            N3 = 3 * m.nn_internal
+            res = np.sqrt(B[:N3] @ B[:N3]); xnrm = np.sqrt(A.X[:N3] @ A.X[:N3]); qnrm = np.sqrt(QF[:N3] @ QF[:N3])
+            if qnrm < 1.0e-8:
+                qnrm = 1.0
+            dunrm = xnrm if it == 1 else np.sqrt(dunode[:N3] @ dunode[:N3])
+            if A.Iarray[80] == 1 and (res / qnrm < converg or xnrm / dunrm < converg):
+                converged = True; break
+            if it == max_iter or res / qnrm > 1.0e10:
+                rc = -1; break
+        if rc or not converged:
+            rc = rc or -1
+            break
+        nit[sub - 1] = it
+        unode += dunode
+        steps[sub - 1] = unode
+        time += dt
+    return dict(error=rc, unode=unode, unode_steps=steps, newton_iters=nit, cg_iters=cg_total)
+
+
 # ---- hecmw_mat_ass_bc ------------------------------------------------------------------------
 def hecmw_mat_ass_bc(nodes, dofs, values):
     """Batched Dirichlet elimination on the device-resident matrix/RHS (one entry per constrained DOF,

@@ -88,6 +88,34 @@ int fistr_b200_stiffmatrix_3d(int n_node, const double *node, int n_elem, int n_
                               const double *sect_E, const double *sect_nu, double *D, double *AL,
                               double *AU, double *time_ms /* [2]: integrate+scatter kernel, total */);
 
+/* ---- geometrically nonlinear static analysis (`!STATIC, TYPE=NLGEOM` / `!SOLUTION, TYPE=NLSTATIC`), total
+ * Lagrangian, SURVEY 8(f) rank 2.  The Newton loop itself (fistr1/src/analysis/static/fstr_solve_NonLinear.f90:
+ * 29-167) stays in the caller; per Newton iteration it calls
+ *   nl_stiffmatrix_3d  = fstr_StiffMatrix with nlgeom_flag == TOTALLAG (fstr_StiffMatrix.f90:60-150; STF_C3
+ *                        static_LIB_3d.f90:47-205, STF_C3D8Bbar static_LIB_C3D8.f90:23-198): tangent stiffness at
+ *                        u = unode + dunode incl. the initial-stress matrix of the stored Gauss-point stress,
+ *   mat_ass_bc, solve_33 (above), and
+ *   nl_update_3d       = fstr_UpdateNewton (fstr_Update.f90:25-293; UPDATE_C3 static_LIB_3d.f90:516-837,
+ *                        Update_C3D8Bbar static_LIB_C3D8.f90:203-552): Green-Lagrange strain and 2nd Piola-Kirchhoff
+ *                        stress of every Gauss point (kept on the device, [element][8][6]) and QFORCE(3*n_node).
+ * Element types 361 (elemopt361 = 1 FI, 2 B-bar; 3 IC is rejected as in the reference) and 342.  Materials per
+ * section: sect_mtype 0 ELASTIC (sect_E, sect_nu), 1 MOONEYRIVLIN (sect_hyper[3*s..] = C10, C01, D;
+ * lib/physics/Hyperelastic.f90:221-286).  sect_mtype / sect_hyper may be NULL (all elastic). */
+int fistr_b200_nl_state_reset(int n_elem);                          /* zero strain / stress (start of the analysis) */
+int fistr_b200_nl_state_download(double *strain, double *stress);   /* [n_elem][8][6] each, either may be NULL */
+int fistr_b200_nl_stiffmatrix_3d(int n_node, const double *node, int n_elem, int n_elem_type,
+                                 const int *elem_type_index, const int *elem_type_item,
+                                 const int *elem_node_index, const int *elem_node_item, const int *section_ID,
+                                 int n_sect, const int *sect_elemopt361, const double *sect_E, const double *sect_nu,
+                                 const int *sect_mtype, const double *sect_hyper, const double *u, double *D,
+                                 double *AL, double *AU, double *time_ms);
+int fistr_b200_nl_update_3d(int n_node, const double *node, int n_elem, int n_elem_type,
+                            const int *elem_type_index, const int *elem_type_item, const int *elem_node_index,
+                            const int *elem_node_item, const int *section_ID, int n_sect,
+                            const int *sect_elemopt361, const double *sect_E, const double *sect_nu,
+                            const int *sect_mtype, const double *sect_hyper, const double *unode,
+                            const double *dunode, double *QFORCE);
+
 /* ---- hecmw_mat_ass_bc (hecmw_mat_ass.f90:292-429), batched over the constrained DOFs that
  * fstr_AddBC (fistr1/src/analysis/static/fstr_AddBC.f90:54-109) visits.  Operates on the
  * device-resident matrix and RHS. */

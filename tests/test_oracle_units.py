@@ -117,6 +117,61 @@ def test_element_emulation_equals_oracle():
         assert np.abs(K0 - K1).max() <= 5e-15 * np.abs(K0).max()
 
 
+def test_tl_element_emulation_equals_oracle():
+    """The total-Lagrangian element code of the CUDA kernels (element_math.cuh: element_stiffness_tl_warp /
+    element_update_tl_warp, run in lock step on the host) against the oracle's restatement of STF_C3 / STF_C3D8Bbar /
+    UPDATE_C3 / Update_C3D8Bbar with flag == TOTALLAG, for ELASTIC and MOONEYRIVLIN materials, at finite strain."""
+    from oracle import oracle as orc
+    import __graft_entry__ as g
+    em = C.CDLL(g.build_emul())
+    L = orc.lib()
+    dp = C.POINTER(C.c_double)
+    d = lambda a: a.ctypes.data_as(dp)
+    rng = np.random.default_rng(3)
+    hexc = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], float)
+    edges = [(0, 1), (1, 2), (2, 0), (0, 3), (1, 3), (2, 3)]
+    tetc = np.vstack([v, [(v[a] + v[b]) / 2 for a, b in edges]])
+    hyper = np.array([0.1486, 0.4849, 0.0789])
+    for form, etype, base, bbar in ((2, 361, hexc, 1), (1, 361, hexc, 0), (10, 342, tetc, 0)):
+        nn = base.shape[0]
+        ngp = 4 if etype == 342 else 8
+        for mtype in (0, 1):
+            sec = orc.orc_section(2 if bbar else 1, 210.0, 0.3, mtype, (C.c_double * 3)(*hyper))
+            ec = np.ascontiguousarray(base * [0.9, 1.2, 1.1] + 0.08 * rng.standard_normal((nn, 3)))
+            u = np.ascontiguousarray(0.12 * rng.standard_normal((nn, 3)))        # unode
+            du = np.ascontiguousarray(0.05 * rng.standard_normal((nn, 3)))       # dunode
+            # update: oracle vs warp code
+            qf0 = np.zeros(3 * nn); e0 = np.zeros((ngp, 6)); s0 = np.zeros((ngp, 6))
+            L.orc_UPDATE_C3_TL(etype, nn, d(ec), d(u), d(du), C.byref(sec), bbar, d(qf0), d(e0), d(s0))
+            qf1 = np.zeros(3 * nn); e1 = np.zeros((8, 6)); s1 = np.zeros((8, 6))
+            tot = np.ascontiguousarray(u + du)
+            assert em.fbemul_element_update_tl(form, d(ec), d(tot), mtype, C.c_double(210.0), C.c_double(0.3), d(hyper),
+                                               d(qf1), d(e1), d(s1)) == 0
+            assert np.abs(e1[:ngp] - e0).max() <= 1e-14 * max(np.abs(e0).max(), 1)
+            assert np.abs(s1[:ngp] - s0).max() <= 1e-12 * np.abs(s0).max()
+            assert np.abs(qf1 - qf0).max() <= 1e-12 * np.abs(qf0).max()
+            # tangent stiffness at the updated state
+            K0 = np.zeros((3 * nn, 3 * nn))
+            L.orc_STF_C3_TL(etype, nn, d(ec), d(tot), d(e0), d(s0), C.byref(sec), bbar, d(K0))
+            K1 = np.zeros((3 * nn, 3 * nn))
+            assert em.fbemul_element_stiffness_tl(form, d(ec), d(tot), d(e1), d(s1), mtype, C.c_double(210.0),
+                                                  C.c_double(0.3), d(hyper), d(K1)) == 0
+            assert np.abs(K1 - K0.T).max() <= 1e-12 * np.abs(K0).max(), (form, mtype)
+            assert np.abs(K0 - K0.T).max() <= 1e-11 * np.abs(K0).max()          # symmetric tangent
+            # consistency: K is the derivative of the internal force (central differences on one dof)
+            if mtype == 1 or bbar == 0:
+                h = 1e-6
+                col = np.zeros(3 * nn)
+                for sgn in (1, -1):
+                    t2 = tot.copy().reshape(-1); t2[4] += sgn * h
+                    q = np.zeros(3 * nn); ee = np.zeros((8, 6)); ss = np.zeros((8, 6))
+                    em.fbemul_element_update_tl(form, d(ec), d(t2), mtype, C.c_double(210.0), C.c_double(0.3), d(hyper),
+                                                d(q), d(ee), d(ss))
+                    col += sgn * q / (2 * h)
+                assert np.abs(col - K1[:, 4]).max() <= 2e-5 * np.abs(K1).max(), (form, mtype)
+
+
 def test_warp_inverse_equals_calInverse_with_pivoting():
     """calInverse(9) as the CUDA warp executes it (same source, run in lock step by 32 host threads: one column
     per lane, shuffles) against the oracle's restatement of utilities.f90:247-316 — on matrices that force row
