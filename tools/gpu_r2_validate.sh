@@ -1,0 +1,14 @@
+#!/bin/bash
+# First GPU call of the next round (1 GPU, ~6 min): validates everything written after GPU access closed in round 1.
+#   1. the validated suite (must stay green)        2. the opt-in nonlinear GPU tests (first hardware run)
+#   3. assembly probe after the IC-condensation rewrite   4. the bench line   5. ncu of the assembly kernels
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -8 | tee gpurun_out/pytest_gpu.log
+FISTR_B200_RUN_NL_GPU=1 timeout 900 python -m pytest tests/test_gpu_z_nonlinear.py -m gpu -q -rA 2>&1 | tail -25 | tee gpurun_out/pytest_gpu_nl.log
+timeout 600 python tools/asm_probe.py --n 100 2>&1 | tee gpurun_out/asm_probe.log
+timeout 600 python tools/asm_probe.py --tet 40 --probes 0,1 2>&1 | tee -a gpurun_out/asm_probe.log
+timeout 900 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"; cat gpurun_out/bench_n1.json
+CMD="python tools/asm_probe.py --n 100 --probes 0"
+timeout 300 $CMD > gpurun_out/plain_asm.log 2>&1 &&
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"stiff_kernel|gather_sum" -c 4 -o gpurun_out/prof_asm_r2 $CMD > gpurun_out/ncu_asm.log 2>&1
+echo "ncu rc=$?"; tail -3 gpurun_out/ncu_asm.log
