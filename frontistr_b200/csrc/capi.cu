@@ -95,12 +95,31 @@ static int build_sell(Context &C) {
   SellMatrix &S = C.sell;
   const int N = C.N;
   const int nslice = (N + 31) / 32;
+  auto width = [&](int r) { return 1 + (C.h_indexL[r + 1] - C.h_indexL[r]) + (C.h_indexU[r + 1] - C.h_indexU[r]); };
+  // SELL-C-sigma (option "sell_sigma" > 1, off by default): rows are sorted by descending block count inside windows
+  // of sigma rows before they are cut into 32-row slices, which removes most of the zero padding on meshes whose
+  // rows differ a lot in length (tet10: vertex vs mid-edge nodes, 1.5x -> 1.05x; hex: 1.06x -> 1.04x).  Row order
+  // inside a row is untouched, so each row's result stays bit-identical.
+  const int sigma = (int)C.get("sell_sigma", 0);
+  std::vector<int> rowperm;
+  S.permuted = sigma > 1 && nslice > 0;
+  if (S.permuted) {
+    rowperm.assign((size_t)nslice * 32, -1);
+    for (int r = 0; r < N; r++) rowperm[r] = r;
+    for (int s0 = 0; s0 < N; s0 += sigma) {
+      const int s1 = std::min(N, s0 + sigma);
+      std::stable_sort(rowperm.begin() + s0, rowperm.begin() + s1, [&](int a, int b) { return width(a) > width(b); });
+    }
+    if (S.rowperm.alloc(rowperm.size())) return FISTR_B200_ERR_CUDA;
+    FB_CUDA(cudaMemcpyAsync(S.rowperm.p, rowperm.data(), sizeof(int) * rowperm.size(), cudaMemcpyHostToDevice, C.stream));
+  }
   std::vector<long long> sp((size_t)nslice + 1, 0);
   for (int s = 0; s < nslice; s++) {
     int w = 0;
-    const int r1 = std::min(N, 32 * (s + 1));
-    for (int r = 32 * s; r < r1; r++)
-      w = std::max(w, 1 + (C.h_indexL[r + 1] - C.h_indexL[r]) + (C.h_indexU[r + 1] - C.h_indexU[r]));
+    for (int l = 0; l < 32; l++) {
+      const int r = S.permuted ? rowperm[(size_t)s * 32 + l] : ((s * 32 + l < N) ? s * 32 + l : -1);
+      if (r >= 0) w = std::max(w, width(r));
+    }
     if (variant == 2) w = (w + 1) / 2;
     sp[s + 1] = sp[s] + w;
   }
@@ -108,13 +127,14 @@ static int build_sell(Context &C) {
   const size_t cols = (size_t)S.total_cols * (variant == 2 ? 2 : 1);
   if (S.slice_ptr.alloc((size_t)nslice + 1) || S.val.alloc(cols * 288) || S.col.alloc(cols * 32) || S.halo_slice.alloc((size_t)nslice + 1)) return FISTR_B200_ERR_CUDA;
   FB_CUDA(cudaMemcpyAsync(S.slice_ptr.p, sp.data(), sizeof(long long) * sp.size(), cudaMemcpyHostToDevice, C.stream));
-  FB_CUDA(cudaStreamSynchronize(C.stream));   // sp is a local
+  FB_CUDA(cudaStreamSynchronize(C.stream));   // sp, rowperm are locals
+  const int *rp = S.permuted ? S.rowperm.p : nullptr;
   if (nslice > 0) {
     const int blocks = (nslice * 32 + 255) / 256;
     if (variant == 2)
-      sell_fill_kernel<2><<<blocks, 256, 0, C.stream>>>(N, C.dD(), C.dAL(), C.dAU(), C.indexL.p, C.itemL.p, C.indexU.p, C.itemU.p, S.slice_ptr.p, S.val.p, S.col.p, S.halo_slice.p);
+      sell_fill_kernel<2><<<blocks, 256, 0, C.stream>>>(N, C.dD(), C.dAL(), C.dAU(), C.indexL.p, C.itemL.p, C.indexU.p, C.itemU.p, S.slice_ptr.p, S.val.p, S.col.p, S.halo_slice.p, rp);
     else
-      sell_fill_kernel<1><<<blocks, 256, 0, C.stream>>>(N, C.dD(), C.dAL(), C.dAU(), C.indexL.p, C.itemL.p, C.indexU.p, C.itemU.p, S.slice_ptr.p, S.val.p, S.col.p, S.halo_slice.p);
+      sell_fill_kernel<1><<<blocks, 256, 0, C.stream>>>(N, C.dD(), C.dAL(), C.dAU(), C.indexL.p, C.itemL.p, C.indexU.p, C.itemU.p, S.slice_ptr.p, S.val.p, S.col.p, S.halo_slice.p, rp);
     FB_LAUNCH_CHECK();
   }
   C.sell_valid = true;
@@ -134,13 +154,14 @@ static int launch_spmv(Context &C, int mode, const double *x, const double *b, d
     else spmv_native_kernel<1, BLOCK><<<grid, BLOCK, 0, C.stream>>>(C.N, C.dD(), C.dAL(), C.dAU(), C.indexL.p, C.itemL.p, C.indexU.p, C.itemU.p, x, b, y, C.partial.p, C.counter.p, red_out, phase);
   } else {
     const SellMatrix &S = C.sell;
+    const int *rp = S.permuted ? S.rowperm.p : nullptr;
     const int grid = C.grid_for((size_t)S.nslice * 32, BLOCK, per_sm);
     if (S.variant == 1) {
-      if (mode == 0) spmv_sell1_kernel<0, BLOCK><<<grid, BLOCK, 0, C.stream>>>(S.N, S.nslice, S.slice_ptr.p, S.val.p, S.col.p, x, b, y, C.partial.p, C.counter.p, red_out, phase);
-      else spmv_sell1_kernel<1, BLOCK><<<grid, BLOCK, 0, C.stream>>>(S.N, S.nslice, S.slice_ptr.p, S.val.p, S.col.p, x, b, y, C.partial.p, C.counter.p, red_out, phase);
+      if (mode == 0) spmv_sell1_kernel<0, BLOCK><<<grid, BLOCK, 0, C.stream>>>(S.N, S.nslice, S.slice_ptr.p, S.val.p, S.col.p, x, b, y, C.partial.p, C.counter.p, red_out, phase, rp);
+      else spmv_sell1_kernel<1, BLOCK><<<grid, BLOCK, 0, C.stream>>>(S.N, S.nslice, S.slice_ptr.p, S.val.p, S.col.p, x, b, y, C.partial.p, C.counter.p, red_out, phase, rp);
     } else {
-      if (mode == 0) spmv_sell2_kernel<0, BLOCK><<<grid, BLOCK, 0, C.stream>>>(S.N, S.nslice, S.slice_ptr.p, S.val.p, S.col.p, x, b, y, C.partial.p, C.counter.p, red_out, phase, C.p2p.view, C.p2p.nbrs, pa, S.halo_slice.p);
-      else spmv_sell2_kernel<1, BLOCK><<<grid, BLOCK, 0, C.stream>>>(S.N, S.nslice, S.slice_ptr.p, S.val.p, S.col.p, x, b, y, C.partial.p, C.counter.p, red_out, phase, C.p2p.view, C.p2p.nbrs, pa, S.halo_slice.p);
+      if (mode == 0) spmv_sell2_kernel<0, BLOCK><<<grid, BLOCK, 0, C.stream>>>(S.N, S.nslice, S.slice_ptr.p, S.val.p, S.col.p, x, b, y, C.partial.p, C.counter.p, red_out, phase, C.p2p.view, C.p2p.nbrs, pa, S.halo_slice.p, rp);
+      else spmv_sell2_kernel<1, BLOCK><<<grid, BLOCK, 0, C.stream>>>(S.N, S.nslice, S.slice_ptr.p, S.val.p, S.col.p, x, b, y, C.partial.p, C.counter.p, red_out, phase, C.p2p.view, C.p2p.nbrs, pa, S.halo_slice.p, rp);
     }
   }
   FB_LAUNCH_CHECK();
@@ -444,7 +465,7 @@ const char *fistr_b200_last_error(void) { return g_last_error.c_str(); }
 int fistr_b200_set_option(const char *key, int64_t value) {
   Context &C = ctx();
   C.opt[key] = value;
-  if (!strcmp(key, "spmv_variant")) C.sell_valid = false;
+  if (!strcmp(key, "spmv_variant") || !strcmp(key, "sell_sigma")) C.sell_valid = false;
   if (!strcmp(key, "launch_count_reset")) g_launch_count = 0;
   return 0;
 }

@@ -28,6 +28,8 @@ struct SellMatrix {
   DevBuf<double> val;
   DevBuf<int> col;
   DevBuf<unsigned char> halo_slice;   // 1 if any row of the slice has a column in the halo (>= N)
+  DevBuf<int> rowperm;                // SELL-C-sigma: matrix row held by lane l of slice s = rowperm[32 s + l] (-1: none)
+  bool permuted = false;              // rowperm in use (option "sell_sigma" > 1), else rows are in natural order
   size_t bytes() const { return val.n * 8 + col.n * 4 + slice_ptr.n * 8; }
 };
 
@@ -38,11 +40,14 @@ sell_fill_kernel(int N, const double *__restrict__ D, const double *__restrict__
                  const double *__restrict__ AU, const int *__restrict__ indexL,
                  const int *__restrict__ itemL, const int *__restrict__ indexU,
                  const int *__restrict__ itemU, const long long *__restrict__ slice_ptr,
-                 double *__restrict__ val, int *__restrict__ col, unsigned char *__restrict__ halo_slice) {
+                 double *__restrict__ val, int *__restrict__ col, unsigned char *__restrict__ halo_slice,
+                 const int *__restrict__ rowperm) {
   const int lane = threadIdx.x & 31;
   const long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long row = s * 32 + lane;  // 0-based
   if (s * 32 >= N) return;
+  // 0-based matrix row of this lane; N (= "no row") for the padding lanes of the last slice / of a permuted slice
+  long long row = s * 32 + lane;
+  if (rowperm) { const int pr = rowperm[row]; row = pr < 0 ? (long long)N : (long long)pr; }
   const long long p0 = slice_ptr[s], p1 = slice_ptr[s + 1];
   const int w = (int)(p1 - p0) * (VARIANT == 2 ? 2 : 1);
   int nL = 0, nU = 0;
@@ -86,7 +91,8 @@ __global__ void __launch_bounds__(BLOCK)
 spmv_sell1_kernel(int N, int nslice, const long long *__restrict__ slice_ptr,
                   const double *__restrict__ val, const int *__restrict__ col,
                   const double *__restrict__ x, const double *__restrict__ b, double *__restrict__ y,
-                  double *partial, unsigned int *counter, double *red_out, const int *phase) {
+                  double *partial, unsigned int *counter, double *red_out, const int *phase,
+                  const int *__restrict__ rowperm) {
   if (phase && *phase != 0) return;
   const int lane = threadIdx.x & 31;
   const int wg = (blockIdx.x * BLOCK + threadIdx.x) >> 5;
@@ -124,8 +130,8 @@ spmv_sell1_kernel(int N, int nslice, const long long *__restrict__ slice_ptr,
       FB_ROW_FMA(y1, a[3], a[4], a[5], xa0, xa1, xa2);
       FB_ROW_FMA(y2, a[6], a[7], a[8], xa0, xa1, xa2);
     }
-    const int row = s * 32 + lane;
-    if (row < N) {
+    const int row = rowperm ? rowperm[s * 32 + lane] : s * 32 + lane;   // SELL-C-sigma: permuted row (-1: padding lane)
+    if (row >= 0 && row < N) {
       const size_t r3 = 3 * (size_t)row;
       if (MODE == 1) {
         y0 = b[r3] - y0; y1 = b[r3 + 1] - y1; y2 = b[r3 + 2] - y2;
@@ -146,7 +152,8 @@ spmv_sell2_kernel(int N, int nslice, const long long *__restrict__ slice_ptr,
                   const double *__restrict__ val, const int *__restrict__ col,
                   const double *__restrict__ x, const double *__restrict__ b, double *__restrict__ y,
                   double *partial, unsigned int *counter, double *red_out, const int *phase,
-                  P2PView pv, P2PNeighbors nb, P2PArgs a, const unsigned char *__restrict__ halo_slice) {
+                  P2PView pv, P2PNeighbors nb, P2PArgs a, const unsigned char *__restrict__ halo_slice,
+                  const int *__restrict__ rowperm) {
   if (phase && *phase != 0) return;
   const int lane = threadIdx.x & 31;
   const int wg = (blockIdx.x * BLOCK + threadIdx.x) >> 5;
@@ -177,8 +184,8 @@ spmv_sell2_kernel(int N, int nslice, const long long *__restrict__ slice_ptr,
       FB_ROW_FMA(y1, a[3].y, a[4].y, a[5].y, xb0, xb1, xb2);
       FB_ROW_FMA(y2, a[6].y, a[7].y, a[8].y, xb0, xb1, xb2);
     }
-    const int row = s * 32 + lane;
-    if (row < N) {
+    const int row = rowperm ? rowperm[s * 32 + lane] : s * 32 + lane;   // SELL-C-sigma: permuted row (-1: padding lane)
+    if (row >= 0 && row < N) {
       const size_t r3 = 3 * (size_t)row;
       if (MODE == 1) {
         y0 = b[r3] - y0; y1 = b[r3 + 1] - y1; y2 = b[r3 + 2] - y2;

@@ -1,4 +1,7 @@
-"""GPU parity of the geometrically nonlinear path: total-Lagrangian tangent assembly and
+"""GPU tests of device code that was written after GPU access had been closed for round 1 and has therefore never
+run on hardware: (1) the geometrically nonlinear path, (2) the SELL-C-sigma row ordering of the SpMV copy.
+
+(1) GPU parity of the geometrically nonlinear path: total-Lagrangian tangent assembly and
 strain / stress / internal-force update on the device, driven by the fstr_Newton mirror in frontistr_b200/hecmw.py,
 against the oracle (which reproduces the reference's exI golden logs at every sub-step).
 
@@ -6,7 +9,8 @@ STATUS: these kernels were written after GPU access had been closed for round 1 
 element code is verified against the oracle through the lock-step host emulation of the SAME source
 (tests/test_oracle_units.py::test_tl_element_emulation_equals_oracle) but has not run on hardware yet.  Until
 they have, nothing here executes by default — a fault in a never-run kernel must not be able to take the GPU (and
-the validated tests, smoke() and bench.py with it) down at round end.  Run with FISTR_B200_RUN_NL_GPU=1 to validate;
+the validated tests, smoke() and bench.py with it) down at round end.  Run with FISTR_B200_RUN_NL_GPU=1 to validate
+(tools/gpu_r2_validate.sh does);
 the tests are additionally non-strict xfail so the first hardware run cannot turn the suite red."""
 import os
 
@@ -103,3 +107,25 @@ def test_tl_tangent_and_update_match_oracle_elementwise(gpu):
     scale = np.abs(Ao.D).max()
     for k in ("D", "AL", "AU"):
         assert np.abs(getattr(A, k) - getattr(Ao, k)).max() <= 1e-12 * scale, k
+
+
+@pytest.mark.parametrize("meshname", ["tet3", "hex_ragged"])
+def test_sell_sigma_is_bitwise_identical_per_row(gpu, meshname):
+    """(2) SELL-C-sigma ("sell_sigma" option): rows are only re-distributed over the 32-row slices, every row keeps
+    its own accumulation order, so y = A x must be bit-identical to the natural ordering; CG must take the same
+    number of iterations (the dot products are summed in a different order => last-bit differences only)."""
+    from frontistr_b200 import meshgen
+    mesh = meshgen.tet10_cube(3) if meshname == "tet3" else meshgen.hex_cube(3, nx=7, ny=2, nz=1)
+    cnt = util.cube_cnt(tol=1e-10)
+    A = util.product_problem(gpu, mesh, cnt, to_host=True)
+    x = np.sin(np.arange(3 * A.NP, dtype=float) + 1.0)
+    ys, its = [], []
+    for sigma in (0, 64, 0):
+        gpu.set_option("sell_sigma", sigma)
+        ys.append(gpu.hecmw_matvec(x, 3 * A.N))
+        A.X[:] = 0.0
+        A.Iarray[96] = 1
+        its.append(gpu.hecmw_solve(mesh, A)["iter"])
+    gpu.set_option("sell_sigma", 0)
+    assert np.array_equal(ys[0], ys[1]) and np.array_equal(ys[0], ys[2])
+    assert abs(its[0] - its[1]) <= 1 and its[0] == its[2]

@@ -20,6 +20,7 @@ ap.add_argument("--solve", type=int, default=1)
 ap.add_argument("--precond", type=int, default=3)
 ap.add_argument("--maxit", type=int, default=10000)
 ap.add_argument("--bps", default="8")
+ap.add_argument("--sigma", default="0", help="comma list of sell_sigma values to time (0 = natural row order)")
 args = ap.parse_args()
 
 hecmw.init(0)
@@ -45,13 +46,15 @@ hecmw.hecmw_mat_ass_bc(n, d, v)
 from frontistr_b200.mshio import apply_solver_card
 apply_solver_card(A, cnt["solver"]); A.Iarray[20] = 0; A.Iarray[21] = 0
 nb = A.spmv_bytes()
-for bps in [int(x) for x in args.bps.split(",")]:
-    hecmw.set_option("spmv_blocks_per_sm", bps)
-    for v_ in [int(x) for x in args.variants.split(",")]:
-        hecmw.set_option("spmv_variant", v_)
-        mean, mn = hecmw.matvec_bench(20, False)
-        print("spmv variant %d bps %d: mean %.4f ms min %.4f ms  -> %.0f GB/s algorithmic (%.3f GB)" % (v_, bps, mean, mn, nb / mean / 1e6, nb / 1e9))
-hecmw.set_option("spmv_variant", 2); hecmw.set_option("spmv_blocks_per_sm", 8)
+for sigma in [int(x) for x in args.sigma.split(",")]:
+    hecmw.set_option("sell_sigma", sigma)
+    for bps in [int(x) for x in args.bps.split(",")]:
+        hecmw.set_option("spmv_blocks_per_sm", bps)
+        for v_ in [int(x) for x in args.variants.split(",")]:
+            hecmw.set_option("spmv_variant", v_)
+            mean, mn = hecmw.matvec_bench(20, False)
+            print("spmv variant %d bps %d sigma %d: mean %.4f ms min %.4f ms  -> %.0f GB/s algorithmic (%.3f GB)" % (v_, bps, sigma, mean, mn, nb / mean / 1e6, nb / 1e9))
+hecmw.set_option("spmv_variant", 2); hecmw.set_option("spmv_blocks_per_sm", 8); hecmw.set_option("sell_sigma", 0)
 if args.solve:
     hecmw.set_option("time_ax", 1)
     for rep in range(2):
