@@ -95,33 +95,14 @@ static int build_sell(Context &C) {
   SellMatrix &S = C.sell;
   const int N = C.N;
   const int nslice = (N + 31) / 32;
-  auto width = [&](int r) { return 1 + (C.h_indexL[r + 1] - C.h_indexL[r]) + (C.h_indexU[r + 1] - C.h_indexU[r]); };
-  // SELL-C-sigma (option "sell_sigma" > 1, off by default): rows are sorted by descending block count inside windows
-  // of sigma rows before they are cut into 32-row slices, which removes most of the zero padding on meshes whose
-  // rows differ a lot in length (tet10: vertex vs mid-edge nodes, 1.5x -> 1.05x; hex: 1.06x -> 1.04x).  Row order
-  // inside a row is untouched, so each row's result stays bit-identical.
-  const int sigma = (int)C.get("sell_sigma", 0);
+  // row placement and slice widths (spmv.cuh: sell_layout; SELL-C-sigma when option "sell_sigma" > 1, off by default)
   std::vector<int> rowperm;
-  S.permuted = sigma > 1 && nslice > 0;
+  std::vector<long long> sp;
+  sell_layout(N, C.h_indexL.data(), C.h_indexU.data(), (int)C.get("sell_sigma", 0), variant, rowperm, sp);
+  S.permuted = !rowperm.empty();
   if (S.permuted) {
-    rowperm.assign((size_t)nslice * 32, -1);
-    for (int r = 0; r < N; r++) rowperm[r] = r;
-    for (int s0 = 0; s0 < N; s0 += sigma) {
-      const int s1 = std::min(N, s0 + sigma);
-      std::stable_sort(rowperm.begin() + s0, rowperm.begin() + s1, [&](int a, int b) { return width(a) > width(b); });
-    }
     if (S.rowperm.alloc(rowperm.size())) return FISTR_B200_ERR_CUDA;
     FB_CUDA(cudaMemcpyAsync(S.rowperm.p, rowperm.data(), sizeof(int) * rowperm.size(), cudaMemcpyHostToDevice, C.stream));
-  }
-  std::vector<long long> sp((size_t)nslice + 1, 0);
-  for (int s = 0; s < nslice; s++) {
-    int w = 0;
-    for (int l = 0; l < 32; l++) {
-      const int r = S.permuted ? rowperm[(size_t)s * 32 + l] : ((s * 32 + l < N) ? s * 32 + l : -1);
-      if (r >= 0) w = std::max(w, width(r));
-    }
-    if (variant == 2) w = (w + 1) / 2;
-    sp[s + 1] = sp[s] + w;
   }
   S.N = N; S.NP = C.NP; S.nslice = nslice; S.variant = variant; S.total_cols = sp[nslice];
   const size_t cols = (size_t)S.total_cols * (variant == 2 ? 2 : 1);
@@ -1483,6 +1464,18 @@ int fistr_b200_part_local_fill(int *global_node, int *node_ID, int *elem_type_in
   put(import_item, M.import_item); put(export_index, M.export_index); put(export_item, M.export_item);
   M = LocalMesh();
   return 0;
+}
+
+// host-only: the SELL(-C-sigma) layout the SpMV copy would use (rowperm: 32*nslice entries, -1 = empty lane; left
+// untouched for the natural order; slice_ptr: nslice+1 block-column offsets).  Returns 1 if rows are permuted.
+int fistr_b200_debug_sell_layout(int N, const int *indexL, const int *indexU, int sigma, int variant, int *rowperm,
+                                 long long *slice_ptr) {
+  std::vector<int> rp;
+  std::vector<long long> sp;
+  sell_layout(N, indexL, indexU, sigma, variant, rp, sp);
+  if (!rp.empty() && rowperm) memcpy(rowperm, rp.data(), sizeof(int) * rp.size());
+  if (slice_ptr) memcpy(slice_ptr, sp.data(), sizeof(long long) * sp.size());
+  return rp.empty() ? 0 : 1;
 }
 
 // host-only view of the multicolour ordering (no GPU needed): lets CPU tests compare the ordering

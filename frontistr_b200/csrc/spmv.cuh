@@ -16,6 +16,8 @@
 // warp access with an L1::no_allocate hint; x is gathered through L1/L2.
 // Variant 2 interleaves two block columns so each lane issues 16-byte double2 loads.
 #pragma once
+#include <algorithm>
+
 #include "common.cuh"
 #include "cg_kernels.cuh"
 
@@ -32,6 +34,36 @@ struct SellMatrix {
   bool permuted = false;              // rowperm in use (option "sell_sigma" > 1), else rows are in natural order
   size_t bytes() const { return val.n * 8 + col.n * 4 + slice_ptr.n * 8; }
 };
+
+// ---- layout (host, topology only): which row sits in which lane of which slice, and the slice widths -------
+// SELL-C-sigma (sigma > 1): rows are sorted by descending block count inside windows of sigma rows before they are
+// cut into 32-row slices, which removes most of the zero padding on meshes whose rows differ a lot in length
+// (tet10: vertex vs mid-edge nodes, 1.5x -> 1.05x; hex: 1.06x -> 1.04x).  The order INSIDE a row is untouched, so
+// each row's result stays bit-identical.  rowperm is left empty for the natural order (sigma <= 1).
+inline void sell_layout(int N, const int *indexL, const int *indexU, int sigma, int variant, std::vector<int> &rowperm,
+                        std::vector<long long> &slice_ptr) {
+  const int nslice = (N + 31) / 32;
+  auto width = [&](int r) { return 1 + (indexL[r + 1] - indexL[r]) + (indexU[r + 1] - indexU[r]); };
+  rowperm.clear();
+  if (sigma > 1 && nslice > 0) {
+    rowperm.assign((size_t)nslice * 32, -1);
+    for (int r = 0; r < N; r++) rowperm[r] = r;
+    for (int s0 = 0; s0 < N; s0 += sigma) {
+      const int s1 = std::min(N, s0 + sigma);
+      std::stable_sort(rowperm.begin() + s0, rowperm.begin() + s1, [&](int a, int b) { return width(a) > width(b); });
+    }
+  }
+  slice_ptr.assign((size_t)nslice + 1, 0);
+  for (int s = 0; s < nslice; s++) {
+    int w = 0;
+    for (int l = 0; l < 32; l++) {
+      const int r = !rowperm.empty() ? rowperm[(size_t)s * 32 + l] : ((s * 32 + l < N) ? s * 32 + l : -1);
+      if (r >= 0) w = std::max(w, width(r));
+    }
+    if (variant == 2) w = (w + 1) / 2;
+    slice_ptr[s + 1] = slice_ptr[s] + w;
+  }
+}
 
 // ---- repack: hecmw layout -> SELL (runs once per numeric change) --------------------------
 template <int VARIANT>

@@ -183,6 +183,11 @@ int fistr_b200_part_local_fill(int *global_node, int *node_ID, int *elem_type_in
 int fistr_b200_debug_ssor_order(int N, const int *indexL, const int *itemL, const int *indexU, const int *itemU,
                                 int ncolor_in, int *perm, int *ncolor, int *color_index);
 
+/* host-only: layout of the private sliced-ELL SpMV copy (row -> slice/lane, slice widths) for `sigma`
+ * ("sell_sigma" option; <= 1 natural order) and `variant` (1 or 2).  rowperm[32*nslice], slice_ptr[nslice+1]. */
+int fistr_b200_debug_sell_layout(int N, const int *indexL, const int *indexU, int sigma, int variant, int *rowperm,
+                                 long long *slice_ptr);
+
 /* ---- instrumentation */
 int64_t fistr_b200_launch_count(void);   /* kernels launched by this library since init/reset */
 int fistr_b200_device_info(char *name, int name_len, int *sm_count, int64_t *mem_bytes);
