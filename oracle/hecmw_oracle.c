@@ -1062,9 +1062,11 @@ void orc_precond_apply(const orc_precond *pc, double *ZPv) {
    * colour; inside a colour rows are independent, so a serial visit equals the threaded one. */
   const int *itemL = pc->itemL - 1, *itemU = pc->itemU - 1;
   const double *AL = pc->AL - 1, *AU = pc->AU - 1;
+  /* natural order (the reference's 1-thread path) is ONE colour of DEPENDENT rows: it must be swept serially */
+  const int par = pc->NColor > 1;
   for (int ic = 1; ic <= pc->NColor; ic++) { /* FORWARD */
 #ifdef _OPENMP
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (par)
 #endif
     for (int i = pc->COLORindex[ic - 1] + 1; i <= pc->COLORindex[ic]; i++) {
       size_t iold = pc->perm[i - 1];
@@ -1082,7 +1084,7 @@ void orc_precond_apply(const orc_precond *pc, double *ZPv) {
   }
   for (int ic = pc->NColor; ic >= 1; ic--) { /* BACKWARD */
 #ifdef _OPENMP
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (par)
 #endif
     for (int i = pc->COLORindex[ic]; i >= pc->COLORindex[ic - 1] + 1; i--) {
       double SW1 = 0.0, SW2 = 0.0, SW3 = 0.0;

@@ -26,6 +26,27 @@ def test_oracle_matches_reference_log(name):
                 assert abs(got - want) <= 0.6e-4 * abs(want) + 1e-12
 
 
+@pytest.mark.parametrize("threads", [1, 2])
+@pytest.mark.parametrize("name", ["A361", "A342"])
+def test_oracle_ssor_matches_reference_log(name, threads):
+    """The same golden logs through PRECOND=1 (SSOR) — natural ordering (1 thread) and RCM + multicolour ordering
+    (>1 thread, the ordering the GPU path uses): the converged displacements do not depend on the preconditioner,
+    so both SSOR restatements are pinned by the reference's own vectors too."""
+    from oracle import oracle as orc
+    mesh, cnt, meta = util.load_golden_mesh(name)
+    cnt = dict(cnt)
+    cnt["solver"] = ({**cnt["solver"][0], "PRECOND": "1"}, cnt["solver"][1])
+    A = util.oracle_problem(mesh, cnt)
+    orc.precond_clear()
+    r = orc.solve(mesh, A, ssor_threads=threads)
+    orc.precond_clear()
+    assert r["error"] == 0 and A.Iarray[80] == 1
+    U = A.X.reshape(-1, 3)
+    for d, key in enumerate(("U1", "U2", "U3")):
+        gmax, gmin = meta["golden"][key]
+        assert abs(U[:, d].max() - gmax) <= meta["tolerance_abs"] and abs(U[:, d].min() - gmin) <= meta["tolerance_abs"]
+
+
 @pytest.mark.parametrize("name", ["A361", "A342"])
 def test_oracle_vs_direct_solve(name):
     import scipy.sparse.linalg as spl
