@@ -226,3 +226,69 @@ def test_newton_driver_mirror_with_oracle_backend(monkeypatch):
         U = r["unode_steps"][k].reshape(-1, 3)
         for dd, key in enumerate(("U1", "U2", "U3")):
             assert abs(U[:, dd].max() - gold[key][0]) <= g["tolerance_abs"] and abs(U[:, dd].min() - gold[key][1]) <= g["tolerance_abs"]
+
+
+@pytest.mark.parametrize("name", ["A361", "A342"])
+def test_oracle_iterpremax2_matches_reference_log(name):
+    """iterPREmax = 2 (the additive-Schwarz double sweep of hecmw_precond_33_apply, precond_33.f90:86-114) with SSOR
+    converges to the same golden displacements.  With DIAG the double sweep is M^-1 (2 - A M^-1), indefinite as soon
+    as an eigenvalue of M^-1 A exceeds 2 — on these decks the reference algorithm then stops with
+    HECMW_SOLVER_ERROR_DIVERGE_PC (3003), which is asserted as well."""
+    from oracle import oracle as orc
+    mesh, cnt, meta = util.load_golden_mesh(name)
+    cnt = dict(cnt)
+    cnt["solver"] = (cnt["solver"][0], [[cnt["solver"][1][0][0], "2"], cnt["solver"][1][1]])
+    Ad = util.oracle_problem(mesh, cnt)
+    orc.precond_clear()
+    assert orc.solve(mesh, Ad)["error"] == 3003 and Ad.Iarray[81] == 1      # flag_diverged
+    cnt["solver"] = ({**cnt["solver"][0], "PRECOND": "1"}, cnt["solver"][1])
+    A = util.oracle_problem(mesh, cnt)
+    assert A.Iarray[4] == 2
+    orc.precond_clear()
+    r = orc.solve(mesh, A, ssor_threads=2)
+    orc.precond_clear()
+    assert r["error"] == 0 and A.Iarray[80] == 1
+    U = A.X.reshape(-1, 3)
+    for d, key in enumerate(("U1", "U2", "U3")):
+        gmax, gmin = meta["golden"][key]
+        assert abs(U[:, d].max() - gmax) <= meta["tolerance_abs"] and abs(U[:, d].min() - gmin) <= meta["tolerance_abs"]
+
+
+@pytest.mark.parametrize("form", ["IC", "FI", "BBAR", "TET10"])
+def test_patch_test_every_element_formulation(form):
+    """Known-answer test independent of any log: a linear displacement field prescribed on the whole boundary of a
+    distorted mesh must be reproduced exactly in the interior by every element formulation on the path (constant
+    strain patch test) — also exercises hecmw_mat_ass_bc with non-zero prescribed values on many nodes."""
+    from oracle import oracle as orc
+    from frontistr_b200 import meshgen
+    from frontistr_b200.hecmw_types import kel361BBAR, kel361FI, kel361IC
+    from frontistr_b200.mshio import apply_solver_card
+    if form == "TET10":
+        mesh = meshgen.tet10_cube(3)
+        xyz = mesh.node.reshape(-1, 3)
+    else:
+        mesh = meshgen.hex_cube(4, elemopt361={"IC": kel361IC, "FI": kel361FI, "BBAR": kel361BBAR}[form])
+        # FrontISTR's B-bar takes the dilatational part from the CENTROID derivative (static_LIB_C3D8.f90:72-74), which
+        # is only exactly consistent on parallelepipeds: it passes the patch test on the regular mesh, FI / IC also on
+        # a distorted one
+        if form != "BBAR":
+            mesh = util.distort(mesh)
+        xyz = mesh.node.reshape(-1, 3)
+    G = np.array([[1.0e-3, 2.0e-4, -3.0e-4], [-1.0e-4, -5.0e-4, 4.0e-4], [2.5e-4, 1.5e-4, 7.0e-4]])
+    uex = xyz @ G.T + np.array([1e-3, -2e-3, 5e-4])
+    lo, hi = xyz.min(0), xyz.max(0)
+    bnd = np.nonzero(np.any((np.abs(xyz - lo) < 1e-12) | (np.abs(xyz - hi) < 1e-12), axis=1))[0]
+    A = orc.mat_con(mesh)
+    orc.stiffmatrix(mesh, A)
+    for n in bnd:
+        for d in range(3):
+            orc.mat_ass_bc(A, int(n) + 1, d + 1, float(uex[n, d]))
+    apply_solver_card(A, util.cube_cnt(tol=1e-12)["solver"])
+    A.Iarray[20] = 0; A.Iarray[21] = 0
+    orc.precond_clear()
+    r = orc.solve(mesh, A)
+    orc.precond_clear()
+    assert r["error"] in (0, 3001) or r["resid2"] < 1e-10
+    U = A.X.reshape(-1, 3)
+    assert len(bnd) < mesh.n_node
+    assert np.abs(U - uex).max() <= 1e-9 * np.abs(uex).max()
