@@ -1546,7 +1546,8 @@ void orc_UPDATE_C3_TL(int etype, int nn, const double *ecoord, const double *u, 
  * Returns 0, or -1 "Fail to Converge", -2 unsupported element option, >0 solver code. */
 int orc_nlgeom_static(const orc_mesh *mesh, const orc_section *sections, orc_matrix *mat, int nbc,
                       const int *bc_node, const int *bc_dof, const double *bc_val, int ncl, const int *cl_node,
-                      const int *cl_dof, const double *cl_val, int substeps, double converg, int max_iter,
+                      const int *cl_dof, const double *cl_val, int nsp, const int *sp_node, const int *sp_dof,
+                      const double *sp_val, int substeps, double converg, int max_iter,
                       double *unode, double *unode_steps /* [substeps][3*n_node] or NULL */,
                       int *newton_iters /* [substeps] */, int *cg_iters_total) {
   const int NP = mesh->n_node, n3 = 3 * NP, n_elem = mesh->n_elem;
@@ -1566,6 +1567,12 @@ int orc_nlgeom_static(const orc_mesh *mesh, const orc_section *sections, orc_mat
     memset(GL, 0, sizeof(double) * n3);
     for (int c = 0; c < ncl; c++) GL[3 * (cl_node[c] - 1) + cl_dof[c] - 1] += f2 * cl_val[c];
     for (int i = 0; i < n3; i++) mat->B[i] = GL[i] - QF[i];
+    /* !SPRING: fstr_Update_NDForce_spring (fstr_Spring.f90:47-77); a negative constant fades out with the load factor */
+#define SPRING_K(c) (sp_val[c] < 0.0 ? -sp_val[c] * (1.0 - f2) : sp_val[c])
+    for (int c = 0; c < nsp; c++) {
+      const int idx = 3 * (sp_node[c] - 1) + sp_dof[c] - 1;
+      mat->B[idx] -= SPRING_K(c) * (dunode[idx] + unode[idx]);
+    }
     int iter, converged = 0;
     for (iter = 1; iter <= max_iter; iter++) {
       /* fstr_StiffMatrix with u = unode + dunode */
@@ -1599,6 +1606,9 @@ int orc_nlgeom_static(const orc_mesh *mesh, const orc_section *sections, orc_mat
         }
       }
       if (rc) break;
+      /* fstr_AddSPRING (fstr_Spring.f90:10-45): spring constant on the diagonal entry of the dof */
+      for (int c = 0; c < nsp; c++)
+        mat->D[9 * (size_t)(sp_node[c] - 1) + 3 * (sp_dof[c] - 1) + (sp_dof[c] - 1)] += SPRING_K(c);
       /* fstr_AddBC: RHS = value * (factor(2) - factor(1)) on the first iteration, 0 afterwards (fstr_AddBC.f90:54-63) */
       for (int c = 0; c < nbc; c++) orc_mat_ass_bc(mat, bc_node[c], bc_dof[c], iter > 1 ? 0.0 : bc_val[c] * (f2 - f1));
       if (sub == 1 && iter == 1) mat->Iarray[97] = 1;          /* Iarray(98) */
@@ -1637,6 +1647,10 @@ int orc_nlgeom_static(const orc_mesh *mesh, const orc_section *sections, orc_mat
       }
       /* fstr_Update_NDForce: B = GL - QFORCE, SPC rows cleared (fstr_Residual.f90:44-59,100-133) */
       for (int i = 0; i < n3; i++) mat->B[i] = GL[i] - QF[i];
+      for (int c = 0; c < nsp; c++) {
+        const int idx = 3 * (sp_node[c] - 1) + sp_dof[c] - 1;
+        mat->B[idx] -= SPRING_K(c) * (dunode[idx] + unode[idx]);
+      }
       for (int c = 0; c < nbc; c++) mat->B[3 * (bc_node[c] - 1) + bc_dof[c] - 1] = 0.0;
       /* convergence check, fstr_solve_NonLinear.f90:110-134 (single subdomain: all nodes internal) */
       double res = 0.0, xnrm = 0.0, qnrm = 0.0, dunrm = 0.0;
@@ -1659,6 +1673,7 @@ int orc_nlgeom_static(const orc_mesh *mesh, const orc_section *sections, orc_mat
     if (unode_steps) memcpy(unode_steps + (size_t)(sub - 1) * n3, unode, sizeof(double) * n3);
     time += dt;
   }
+#undef SPRING_K
   if (cg_iters_total) *cg_iters_total = cg_total;
   free(dunode); free(GL); free(QF); free(gstrain); free(gstress);
   return rc;

@@ -117,7 +117,8 @@ void orc_mooney_rivlin_tangent(const double c[3], const double strain[6], double
 void orc_mooney_rivlin_stress(const double c[3], const double strain[6], double stress[6]);
 int orc_nlgeom_static(const orc_mesh *mesh, const orc_section *sections, orc_matrix *mat, int nbc,
                       const int *bc_node, const int *bc_dof, const double *bc_val, int ncl, const int *cl_node,
-                      const int *cl_dof, const double *cl_val, int substeps, double converg, int max_iter,
+                      const int *cl_dof, const double *cl_val, int nsp, const int *sp_node, const int *sp_dof,
+                      const double *sp_val, int substeps, double converg, int max_iter,
                       double *unode, double *unode_steps, int *newton_iters, int *cg_iters_total);
 
 #ifdef __cplusplus

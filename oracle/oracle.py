@@ -184,21 +184,23 @@ def solve(meshes, mats, hist_len: int = 0, ssor_threads: int = 0):
                 hist=hist[: min(hist_len, max(it.value, 0))], times=times)
 
 
-def nlgeom_static(mesh, A, boundary, cload, substeps=10, converg=1.0e-3, max_iter=50):
+def nlgeom_static(mesh, A, boundary, cload, substeps=10, converg=1.0e-3, max_iter=50, spring=((), (), ())):
     """`!STATIC, TYPE=NLGEOM` with one `!STEP, SUBSTEPS=n` (fstr_solve_NLGEOM + fstr_Newton), total Lagrangian,
-    elastic.  boundary = (nodes, dofs, values) triplets as fstr_AddBC visits them; cload = (nodes, dofs, values).
+    elastic.  boundary = (nodes, dofs, values) triplets as fstr_AddBC visits them; cload, spring = (nodes, dofs, values).
     Returns dict(error, unode, unode_steps[substeps, 3*n_node], newton_iters, cg_iters)."""
     L = lib()
     cm = c_mesh(mesh); ca = c_matrix(A); sec = c_sections(mesh)
     bn, bd, bv = _i32(boundary[0]), _i32(boundary[1]), np.ascontiguousarray(boundary[2], np.float64)
     cn, cd, cv = _i32(cload[0]), _i32(cload[1]), np.ascontiguousarray(cload[2], np.float64)
+    sn, sd, sv = _i32(spring[0]), _i32(spring[1]), np.ascontiguousarray(spring[2], np.float64)
     un = np.zeros(3 * mesh.n_node)
     steps = np.zeros((substeps, 3 * mesh.n_node))
     nit = np.zeros(substeps, np.int32)
     cg = C.c_int()
     precond_clear()
     rc = L.orc_nlgeom_static(C.byref(cm.s), sec, C.byref(ca.s), len(bn), _ip(bn), _ip(bd), _dp(bv), len(cn), _ip(cn),
-                             _ip(cd), _dp(cv), C.c_int(substeps), C.c_double(converg), C.c_int(max_iter), _dp(un),
+                             _ip(cd), _dp(cv), len(sn), _ip(sn), _ip(sd), _dp(sv), C.c_int(substeps), C.c_double(converg),
+                             C.c_int(max_iter), _dp(un),
                              _dp(steps), _ip(nit), C.byref(cg))
     precond_clear()
     return dict(error=rc, unode=un, unode_steps=steps, newton_iters=nit, cg_iters=cg.value)

@@ -77,6 +77,19 @@ def main():
                                       converg=1.0e-3, max_iter=50),   # defaults of lib/m_step.f90:69,77
                           golden_steps=[parse_log(os.path.join(REF, log), k) for k in range(1, 11)],
                           tolerance_abs=1.0e-4)
+    # spring_boundary/SB1: NLSTATIC, 2 C3D8 (B-bar), !SPRING, CG + SSOR with iterPREmax=2, 5 sub-steps, golden log per step
+    m = mshio.read_msh(os.path.join(REF, "examples/static/spring_boundary/SB.msh"))
+    c = mshio.read_cnt(os.path.join(REF, "examples/static/spring_boundary/SB1.cnt"))
+    np.savez_compressed(os.path.join(OUT, "SB.npz"),
+                        node=m.node, elem_type_index=m.elem_type_index, elem_type_item=m.elem_type_item,
+                        elem_node_index=m.elem_node_index, elem_node_item=m.elem_node_item,
+                        global_node_ID=m.global_node_ID, **{"ngrp_" + k: v for k, v in m.node_group.items()})
+    sb_log = os.path.join(REF, "examples/static/spring_boundary/SB_correct.log")
+    meta["SB1"] = dict(source=dict(msh="examples/static/spring_boundary/SB.msh", cnt="examples/static/spring_boundary/SB1.cnt",
+                                   log="examples/static/spring_boundary/SB_correct.log"),
+                       mesh="SB", E=100.0, nu=0.3, boundary=c["boundary"], cload=c["cload"], spring=[["SET-2", 2, 1.0]],
+                       solver=[c["solver"][0], c["solver"][1]], nlgeom=dict(substeps=5, converg=1.0e-6, max_iter=15),
+                       golden_steps=[parse_log(sb_log, k) for k in range(1, 6)], golden={}, tolerance_abs=1.0e-4)
     # tutorial/03_hyperelastic_cylinder (BASELINE.json configs[4]): mesh + cards only — the reference ships no golden
     # log for it, so this deck is a run-only fixture (Newton convergence, prescribed displacement, symmetry planes)
     m = mshio.read_msh(os.path.join(REF, "tutorial/03_hyperelastic_cylinder/cylinder.msh"))

@@ -63,11 +63,12 @@ def test_oracle_vs_direct_solve(name):
     assert abs(K - K.T).max() < 1e-9 * abs(K).max()
 
 
-@pytest.mark.parametrize("name", ["I361", "I342"])
+@pytest.mark.parametrize("name", ["I361", "I342", "SB1"])
 def test_nlgeom_newton_against_reference_logs(name):
     """SURVEY 8(f) rank 2 groundwork: the restated Newton loop (fstr_Newton) with total-Lagrangian B-bar C3D8 /
-    C3D10 elements reproduces examples/static/exI/*_correct.log at EVERY one of the 10 sub-steps (nodal
-    displacement max/min, 1e-4 absolute = the reference harness tolerance; in fact all 5 printed digits)."""
+    C3D10 elements reproduces examples/static/exI/*_correct.log at EVERY one of the 10 sub-steps, and
+    examples/static/spring_boundary/SB_correct.log (NLSTATIC + !SPRING, CG + SSOR with iterPREmax = 2) at every one
+    of its 5 (nodal displacement max/min, 1e-4 absolute = the reference harness tolerance; in fact all 5 digits)."""
     from oracle import oracle as orc
     from frontistr_b200 import hecmw
     from frontistr_b200.hecmw_types import kel361BBAR
@@ -82,8 +83,12 @@ def test_nlgeom_newton_against_reference_logs(name):
     for grp, dof, val in g["cload"]:
         ids = list(mesh.node_group[grp])
         cn += ids; cd += [dof] * len(ids); cv += [val] * len(ids)
+    sn, sd, sv = [], [], []
+    for grp, dof, val in g.get("spring", []):      # spring_boundary/SB1: !SPRING + SSOR with two sweeps
+        ids = list(mesh.node_group[grp])
+        sn += ids; sd += [dof] * len(ids); sv += [val] * len(ids)
     nl = g["nlgeom"]
-    r = orc.nlgeom_static(mesh, A, bc, (cn, cd, cv), nl["substeps"], nl["converg"], nl["max_iter"])
+    r = orc.nlgeom_static(mesh, A, bc, (cn, cd, cv), nl["substeps"], nl["converg"], nl["max_iter"], spring=(sn, sd, sv))
     assert r["error"] == 0 and np.all(r["newton_iters"] >= 1) and np.all(r["newton_iters"] <= 5)
     for k, gold in enumerate(g["golden_steps"]):
         U = r["unode_steps"][k].reshape(-1, 3)
