@@ -9,6 +9,9 @@ timeout 600 python tools/asm_probe.py --n 100 2>&1 | tee gpurun_out/asm_probe.lo
 timeout 600 python tools/asm_probe.py --tet 40 --probes 0,1 2>&1 | tee -a gpurun_out/asm_probe.log
 timeout 600 python tools/perf_probe.py --tet 40 --variants 2 --sigma 0,256,1024,4096 --solve 0 2>&1 | tee gpurun_out/probe_tet40_sigma.log
 timeout 900 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"; cat gpurun_out/bench_n1.json
+for c in 0 2 3; do timeout 900 python tools/run_configs.py --config $c 2>&1 | tail -1 | tee gpurun_out/config_$c.json; done
+timeout 900 python tools/run_configs.py --config 3 --sigma 1024 2>&1 | tail -1 | tee gpurun_out/config_3_sigma1024.json
+FISTR_B200_RUN_NL_GPU=1 timeout 600 python tools/run_configs.py --config 4 2>&1 | tail -1 | tee gpurun_out/config_4.json
 CMD="python tools/asm_probe.py --n 100 --probes 0"
 timeout 300 $CMD > gpurun_out/plain_asm.log 2>&1 &&
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"stiff_kernel|gather_sum" -c 4 -o gpurun_out/prof_asm_r2 $CMD > gpurun_out/ncu_asm.log 2>&1
