@@ -13,9 +13,12 @@
  * Parity pinning: the reference's own implementation is Fortran 90 and no
  * Fortran compiler exists in the build image, so this restatement is pinned
  * against (a) the reference's golden logs examples/static/exA/A361_correct.log,
- * A342_correct.log, ... (nodal displacement max/min, 5 significant digits,
- * harness tolerance 1e-4 absolute, examples/test_FrontISTR.rb:10,225-237) and
- * (b) an independent sparse direct solve of the same K (tests/test_oracle_*).
+ * A342_correct.log, exG, exI (nonlinear, every sub-step), spring_boundary/SB1
+ * (nonlinear + springs + SSOR, every sub-step) (nodal displacement max/min, 5
+ * significant digits, harness tolerance 1e-4 absolute,
+ * examples/test_FrontISTR.rb:10,225-237), (b) an independent sparse direct solve
+ * of the same K, (c) patch tests and an energy-derivative test of the hyperelastic
+ * law (tests/test_oracle_*).
  * Nothing in the reference tree pins CG iteration counts or K entries; for
  * those quantities the parity is "pinned by restatement only".
  *
