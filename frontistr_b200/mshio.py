@@ -159,7 +159,8 @@ def apply_solver_card(hecMAT: hecmwST_matrix, solver) -> None:
     opts, lines = solver
     I, R = hecMAT.Iarray, hecMAT.Rarray
     if "METHOD" in opts:
-        I[1] = _METHODS[opts["METHOD"].upper()]
+        mth = opts["METHOD"].upper()      # name or the reference's numeric code (examples/static/exD/D300.cnt: METHOD=1)
+        I[1] = int(mth) if mth.isdigit() else _METHODS[mth]
     if "PRECOND" in opts:
         I[2] = int(opts["PRECOND"])
     if "NSET" in opts:

@@ -1314,6 +1314,66 @@ int orc_solve(int ndom, const orc_mesh *meshes, orc_matrix *mats, int *iter_out,
 
 void orc_precond_clear(void) { precond_clear_all(); }
 
+/* ---------------------------------------------------------------------------------------------
+ * DL_C3, volume loads (lib/static_LIB_3d.f90:210-377): LTYPE 1 BX, 2 BY, 3 BZ, 4 GRAV, 5 CENT.
+ * The caller side of the hot path (fstr_ass_load.f90:131-260); restated so that the reference's exC / exD / exE
+ * golden logs pin the same K / solve path through three more right-hand sides.  ecoord (3,nn) column-major.
+ * --------------------------------------------------------------------------------------------- */
+static void shapefunc_hex8n(const double lc[3], double f[8]) { /* lib/element/hex8n.f90:9-21 */
+  const double sx[8] = {-1, 1, 1, -1, -1, 1, 1, -1}, sy[8] = {-1, -1, 1, 1, -1, -1, 1, 1}, sz[8] = {-1, -1, -1, -1, 1, 1, 1, 1};
+  for (int n = 0; n < 8; n++) f[n] = 0.125 * (1.0 + sx[n] * lc[0]) * (1.0 + sy[n] * lc[1]) * (1.0 + sz[n] * lc[2]);
+}
+static void shapefunc_tet10n(const double vc[3], double s[10]) { /* lib/element/tet10n.f90:9-26 */
+  const double xi = vc[0], et = vc[1], ze = vc[2], a = 1.0 - xi - et - ze;
+  s[0] = (2.0 * a - 1.0) * a; s[1] = xi * (2.0 * xi - 1.0); s[2] = et * (2.0 * et - 1.0); s[3] = ze * (2.0 * ze - 1.0);
+  s[4] = 4.0 * xi * a; s[5] = 4.0 * xi * et; s[6] = 4.0 * et * a; s[7] = 4.0 * ze * a; s[8] = 4.0 * xi * ze; s[9] = 4.0 * et * ze;
+}
+
+int orc_DL_C3_volume(int etype, int nn, const double *ecoord, double RHO, int LTYPE, const double *PARAMS /* 0:6 */,
+                     double *VECT /* 3*nn */) {
+  if (LTYPE < 1 || LTYPE > 5 || (etype != 361 && etype != 342)) return -1;
+  const double val = PARAMS[0];
+  double PLX[20] = {0}, PLY[20] = {0}, PLZ[20] = {0}, H[20], deriv[20][3], XJ[3][3], lc[3];
+  memset(VECT, 0, sizeof(double) * 3 * nn);
+  for (int LX = 1; LX <= num_quad_points(etype); LX++) {
+    get_quad_point(etype, LX, lc);
+    if (etype == 361) shapefunc_hex8n(lc, H); else shapefunc_tet10n(lc, H);
+    get_shape_deriv(etype, lc, deriv);
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        double sum = 0.0;
+        for (int n = 0; n < nn; n++) sum += ecoord[3 * n + i] * deriv[n][j];
+        XJ[i][j] = sum;
+      }
+    const double DET = XJ[0][0] * XJ[1][1] * XJ[2][2] + XJ[1][0] * XJ[2][1] * XJ[0][2] + XJ[2][0] * XJ[0][1] * XJ[1][2] -
+                       XJ[2][0] * XJ[1][1] * XJ[0][2] - XJ[1][0] * XJ[0][1] * XJ[2][2] - XJ[0][0] * XJ[2][1] * XJ[1][2];
+    double COEFX = 1.0, COEFY = 1.0, COEFZ = 1.0;
+    if (LTYPE == 5) { /* centrifugal: axis through (AX,AY,AZ) with direction (RX,RY,RZ), val = angular velocity */
+      const double AX = PARAMS[1], AY = PARAMS[2], AZ = PARAMS[3], RX = PARAMS[4], RY = PARAMS[5], RZ = PARAMS[6];
+      double XC = 0.0, YC = 0.0, ZC = 0.0;
+      for (int n = 0; n < nn; n++) { XC += H[n] * ecoord[3 * n]; YC += H[n] * ecoord[3 * n + 1]; ZC += H[n] * ecoord[3 * n + 2]; }
+      const double t = ((XC - AX) * RX + (YC - AY) * RY + (ZC - AZ) * RZ) / (RX * RX + RY * RY + RZ * RZ);
+      COEFX = RHO * val * val * (XC - (AX + t * RX));
+      COEFY = RHO * val * val * (YC - (AY + t * RY));
+      COEFZ = RHO * val * val * (ZC - (AZ + t * RZ));
+    }
+    const double WG = get_weight(etype, LX) * DET;
+    for (int n = 0; n < nn; n++) { PLX[n] += H[n] * WG * COEFX; PLY[n] += H[n] * WG * COEFY; PLZ[n] += H[n] * WG * COEFZ; }
+  }
+  for (int n = 0; n < nn; n++) {
+    if (LTYPE == 1) VECT[3 * n] = val * PLX[n];
+    else if (LTYPE == 2) VECT[3 * n + 1] = val * PLY[n];
+    else if (LTYPE == 3) VECT[3 * n + 2] = val * PLZ[n];
+    else if (LTYPE == 4) {
+      const double nrm = sqrt(PARAMS[1] * PARAMS[1] + PARAMS[2] * PARAMS[2] + PARAMS[3] * PARAMS[3]);
+      VECT[3 * n] = val * PLX[n] * RHO * (PARAMS[1] / nrm);
+      VECT[3 * n + 1] = val * PLY[n] * RHO * (PARAMS[2] / nrm);
+      VECT[3 * n + 2] = val * PLZ[n] * RHO * (PARAMS[3] / nrm);
+    } else { VECT[3 * n] = PLX[n]; VECT[3 * n + 1] = PLY[n]; VECT[3 * n + 2] = PLZ[n]; }
+  }
+  return 0;
+}
+
 /* =============================================================================================
  * Geometrically nonlinear static analysis, total Lagrangian, linear elastic (St.Venant-Kirchhoff) material:
  * the path `!STATIC, TYPE=NLGEOM` takes for element types 361 (B-bar, the default under NLGEOM:

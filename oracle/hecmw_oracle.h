@@ -108,6 +108,9 @@ void orc_set_ssor_threads(int n);   /* 0: follow OpenMP; 1: natural order; >1: R
 int orc_num_threads(void);
 void orc_set_num_threads(int n);
 
+/* DL_C3 volume loads (BX 1, BY 2, BZ 3, GRAV 4, CENT 5), lib/static_LIB_3d.f90:210-377; PARAMS(0:6) as in !DLOAD */
+int orc_DL_C3_volume(int etype, int nn, const double *ecoord, double RHO, int LTYPE, const double *PARAMS, double *VECT);
+
 /* ---- geometrically nonlinear static (total Lagrangian, elastic): SURVEY 8(f) rank 2, pinned against
  * examples/static/exI/A361_correct.log, A342_correct.log.  u, du: (3,nn) column-major; stress/strain: (6,ngp). */
 void orc_STF_C3_TL(int etype, int nn, const double *ecoord, const double *u, const double *strain,

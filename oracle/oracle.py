@@ -152,6 +152,23 @@ def element_stiffness(kind: str, ecoord: np.ndarray, E: float, nu: float, etype:
     return K.T.copy()   # column-major (i,j) -> K[i,j]
 
 
+def ass_dload_volume(mesh, A, ltype: int, params, rho: float):
+    """!DLOAD on EGRP=ALL, volume types (fstr_ass_load.f90:131-260 -> DL_C3): adds the element load vectors into A.B."""
+    L = lib()
+    nodes = mesh.node.reshape(-1, 3)
+    pr = np.zeros(7)
+    pr[: len(params)] = params
+    for it in range(mesh.n_elem_type):
+        et = int(mesh.elem_type_item[it])
+        for e in range(int(mesh.elem_type_index[it]), int(mesh.elem_type_index[it + 1])):
+            nod = mesh.elem_node_item[mesh.elem_node_index[e]: mesh.elem_node_index[e + 1]]
+            ec = np.ascontiguousarray(nodes[nod - 1])
+            v = np.zeros(3 * len(nod))
+            rc = L.orc_DL_C3_volume(et, len(nod), _dp(ec), C.c_double(rho), int(ltype), _dp(pr), _dp(v))
+            assert rc == 0
+            np.add.at(A.B.reshape(-1, 3), nod - 1, v.reshape(-1, 3))
+
+
 def mat_ass_bc(A, inode: int, idof: int, rhs: float):
     ca = c_matrix(A)
     lib().orc_mat_ass_bc(C.byref(ca.s), int(inode), int(idof), float(rhs))

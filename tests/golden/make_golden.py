@@ -37,6 +37,18 @@ NL_DECKS = [
 ]
 
 
+# volume-load decks (examples/static/exC BZ, exD GRAV, exE CENT): !DLOAD on EGRP=ALL; density from the mesh's ITEM=2
+DLOAD_DECKS = [
+    ("C361", "examples/static/exC/C361.msh", "examples/static/exC/C300.cnt", "examples/static/exC/C361_correct.log"),
+    ("C342", "examples/static/exC/C342.msh", "examples/static/exC/C300.cnt", "examples/static/exC/C342_correct.log"),
+    ("D361", "examples/static/exD/D361.msh", "examples/static/exD/D300.cnt", "examples/static/exD/D361_correct.log"),
+    ("D342", "examples/static/exD/D342.msh", "examples/static/exD/D300.cnt", "examples/static/exD/D342_correct.log"),
+    ("E361", "examples/static/exE/E361.msh", "examples/static/exE/E300.cnt", "examples/static/exE/E361_correct.log"),
+    ("E342", "examples/static/exE/E342.msh", "examples/static/exE/E300.cnt", "examples/static/exE/E342_correct.log"),
+]
+LTYPE = {"BX": 1, "BY": 2, "BZ": 3, "GRAV": 4, "CENT": 5}
+
+
 def parse_log(path, which=1):
     """Displacement max/min of the `which`-th '##### Global Summary' block (1-based; NL logs have one per sub-step)."""
     out = {}
@@ -65,6 +77,24 @@ def main():
         meta[name] = dict(source=dict(msh=msh, cnt=cnt, log=log), E=m.sections[0]["E"], nu=m.sections[0]["nu"],
                           boundary=c["boundary"], cload=c["cload"], solver=[c["solver"][0], c["solver"][1]],
                           golden=parse_log(os.path.join(REF, log)), tolerance_abs=1.0e-4)
+    for name, msh, cnt, log in DLOAD_DECKS:
+        m = mshio.read_msh(os.path.join(REF, msh))
+        c = mshio.read_cnt(os.path.join(REF, cnt))
+        with open(os.path.join(REF, msh)) as f:
+            mtxt = f.read()
+        with open(os.path.join(REF, cnt)) as f:
+            ctxt = f.read()
+        rho = float(re.search(r"!ITEM\s*=\s*2[^\n]*\n\s*([^\s,]+)", mtxt).group(1))
+        dl = re.search(r"!DLOAD[^\n]*\n\s*([^\n]+)", ctxt).group(1).replace(",", " ").split()
+        assert dl[0] == "ALL" and dl[1] in LTYPE
+        np.savez_compressed(os.path.join(OUT, name + ".npz"),
+                            node=m.node, elem_type_index=m.elem_type_index, elem_type_item=m.elem_type_item,
+                            elem_node_index=m.elem_node_index, elem_node_item=m.elem_node_item,
+                            global_node_ID=m.global_node_ID, **{"ngrp_" + k: v for k, v in m.node_group.items()})
+        meta[name] = dict(source=dict(msh=msh, cnt=cnt, log=log), E=m.sections[0]["E"], nu=m.sections[0]["nu"], rho=rho,
+                          boundary=c["boundary"], cload=[], dload=dict(ltype=LTYPE[dl[1]], params=[float(x) for x in dl[2:]]),
+                          solver=[c["solver"][0], c["solver"][1]], golden=parse_log(os.path.join(REF, log)),
+                          tolerance_abs=1.0e-4)
     for name, mesh_name, cnt, log in NL_DECKS:
         with open(os.path.join(REF, cnt)) as f:
             txt = f.read()

@@ -26,6 +26,35 @@ def test_oracle_matches_reference_log(name):
                 assert abs(got - want) <= 0.6e-4 * abs(want) + 1e-12
 
 
+@pytest.mark.parametrize("name", ["C361", "C342", "D361", "D342", "E361", "E342"])
+def test_oracle_matches_reference_log_volume_loads(name):
+    """exC (body force BZ), exD (gravity), exE (centrifugal): the same K / BC / CG path through three more right-hand
+    sides, each against the reference's own golden log."""
+    from oracle import oracle as orc
+    from frontistr_b200 import hecmw
+    from frontistr_b200.mshio import apply_solver_card
+    mesh, cnt, meta = util.load_golden_mesh(name)
+    A = orc.mat_con(mesh)
+    orc.stiffmatrix(mesh, A)
+    orc.ass_dload_volume(mesh, A, meta["dload"]["ltype"], meta["dload"]["params"], meta["rho"])
+    n, d, v = hecmw.boundary_dofs(mesh, cnt["boundary"])
+    for i in range(len(n)):
+        orc.mat_ass_bc(A, int(n[i]), int(d[i]), float(v[i]))
+    apply_solver_card(A, cnt["solver"])
+    A.Iarray[20] = 0; A.Iarray[21] = 0
+    orc.precond_clear()
+    r = orc.solve(mesh, A)
+    orc.precond_clear()
+    assert r["error"] == 0 and A.Iarray[80] == 1
+    U = A.X.reshape(-1, 3)
+    for dd, key in enumerate(("U1", "U2", "U3")):
+        gmax, gmin = meta["golden"][key]
+        assert abs(U[:, dd].max() - gmax) <= meta["tolerance_abs"] and abs(U[:, dd].min() - gmin) <= meta["tolerance_abs"]
+        for got, want in ((U[:, dd].max(), gmax), (U[:, dd].min(), gmin)):
+            if abs(want) > 1e-8:
+                assert abs(got - want) <= 1.0e-4 * abs(want)      # 5 printed digits
+
+
 @pytest.mark.parametrize("threads", [1, 2])
 @pytest.mark.parametrize("name", ["A361", "A342"])
 def test_oracle_ssor_matches_reference_log(name, threads):
