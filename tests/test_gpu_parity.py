@@ -169,6 +169,31 @@ def test_solve_golden_decks(gpu, name):
         assert abs(U[:, d].max() - gmax) <= 1e-4 and abs(U[:, d].min() - gmin) <= 1e-4
 
 
+@pytest.mark.parametrize("name", ["C361", "C342", "D361", "D342", "E361", "E342"])
+def test_solve_golden_decks_volume_loads(gpu, name):
+    """exC (BZ), exD (GRAV), exE (CENT): assembly, BC elimination and CG on the device, the !DLOAD right-hand side
+    from the restated DL_C3 (caller side of the path); displacement max/min of the reference's golden logs."""
+    from oracle import oracle as orc
+    from frontistr_b200.mshio import apply_solver_card
+    mesh, cnt, meta = util.load_golden_mesh(name)
+    A = gpu.hecmw_mat_con(mesh)
+    A.fstr_mat_init().hecMAT_init()
+    gpu.mat_structure(mesh, A)
+    gpu.fstr_StiffMatrix(mesh, A, to_host=False)
+    orc.ass_dload_volume(mesh, A, meta["dload"]["ltype"], meta["dload"]["params"], meta["rho"])
+    gpu.mat_upload(A, values=False, rhs=True)
+    n, d, v = gpu.boundary_dofs(mesh, cnt["boundary"])
+    gpu.hecmw_mat_ass_bc(n, d, v)
+    apply_solver_card(A, cnt["solver"])
+    A.Iarray[20] = 0; A.Iarray[21] = 0
+    r = gpu.hecmw_solve(mesh, A, device_resident=True)
+    assert r["error"] == 0 and A.Iarray[80] == 1 and r["resid2"] < A.Rarray[0]
+    U = A.X.reshape(-1, 3)
+    for dd, key in enumerate(("U1", "U2", "U3")):
+        gmax, gmin = meta["golden"][key]
+        assert abs(U[:, dd].max() - gmax) <= 1e-4 and abs(U[:, dd].min() - gmin) <= 1e-4
+
+
 @pytest.mark.parametrize("precond,fused", [(3, 1), (3, 0), (1, 0)])
 @pytest.mark.parametrize("meshname", ["hex12", "tet4"])
 def test_solve_matches_oracle(gpu, meshname, precond, fused):
