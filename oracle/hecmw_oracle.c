@@ -1374,6 +1374,126 @@ int orc_DL_C3_volume(int etype, int nn, const double *ecoord, double RHO, int LT
   return 0;
 }
 
+/* DL_C3, surface pressure P1..P6 (LTYPE = 10 * face; lib/static_LIB_3d.f90:271-294): getSubFace
+ * (lib/element/element.f90:199-250, FrontISTR-internal node order), ShapeFunc/ShapeDeriv of quad4n / tri6n,
+ * quadrature gauss2d2 / gauss2d5 (quadrature.f90:51-55,70-73,204,213-214), SurfaceNormal (element.f90:822-854). */
+int orc_DL_C3_surface(int etype, int nn, const double *ecoord, int face, double val, double *VECT /* 3*nn */) {
+  static const int hexface[6][4] = {{1, 2, 3, 4}, {8, 7, 6, 5}, {5, 6, 2, 1}, {6, 7, 3, 2}, {7, 8, 4, 3}, {8, 5, 1, 4}};
+  static const int tetface[4][6] = {{1, 2, 3, 5, 6, 7}, {4, 2, 1, 9, 5, 8}, {4, 3, 2, 10, 6, 9}, {4, 1, 3, 8, 7, 10}};
+  static const double g2d2[4][2] = {{-0.577350269189626, -0.577350269189626}, {0.577350269189626, -0.577350269189626},
+                                    {-0.577350269189626, 0.577350269189626}, {0.577350269189626, 0.577350269189626}};
+  static const double g2d5[3][2] = {{0.166666666666667, 0.166666666666667}, {0.666666666666667, 0.166666666666667},
+                                    {0.166666666666667, 0.666666666666667}};
+  memset(VECT, 0, sizeof(double) * 3 * nn);
+  int NSUR, NOD[6], nq;
+  if (etype == 361) { if (face < 1 || face > 6) return -1; NSUR = 4; nq = 4; for (int i = 0; i < 4; i++) NOD[i] = hexface[face - 1][i]; }
+  else if (etype == 342) { if (face < 1 || face > 4) return -1; NSUR = 6; nq = 3; for (int i = 0; i < 6; i++) NOD[i] = tetface[face - 1][i]; }
+  else return -1;
+  for (int IG2 = 0; IG2 < nq; IG2++) {
+    double H[6], dv[6][2], WG;
+    if (etype == 361) {
+      const double x = g2d2[IG2][0], y = g2d2[IG2][1];
+      H[0] = 0.25 * (1 - x) * (1 - y); H[1] = 0.25 * (1 + x) * (1 - y); H[2] = 0.25 * (1 + x) * (1 + y); H[3] = 0.25 * (1 - x) * (1 + y);
+      dv[0][0] = -0.25 * (1 - y); dv[1][0] = 0.25 * (1 - y); dv[2][0] = 0.25 * (1 + y); dv[3][0] = -0.25 * (1 + y);
+      dv[0][1] = -0.25 * (1 - x); dv[1][1] = -0.25 * (1 + x); dv[2][1] = 0.25 * (1 + x); dv[3][1] = 0.25 * (1 - x);
+      WG = 1.0;
+    } else {
+      const double xi = g2d5[IG2][0], et = g2d5[IG2][1], st = 1.0 - xi - et;
+      H[0] = st * (2 * st - 1); H[1] = xi * (2 * xi - 1); H[2] = et * (2 * et - 1); H[3] = 4 * xi * st; H[4] = 4 * xi * et; H[5] = 4 * et * st;
+      dv[0][0] = 1 - 4 * st; dv[1][0] = 4 * xi - 1; dv[2][0] = 0; dv[3][0] = 4 * (st - xi); dv[4][0] = 4 * et; dv[5][0] = -4 * et;
+      dv[0][1] = 1 - 4 * st; dv[1][1] = 0; dv[2][1] = 4 * et - 1; dv[3][1] = -4 * xi; dv[4][1] = 4 * xi; dv[5][1] = 4 * (st - et);
+      WG = 0.166666666666666;
+    }
+    double gd[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    for (int i = 0; i < NSUR; i++)
+      for (int c = 0; c < 3; c++) { gd[c][0] += ecoord[3 * (NOD[i] - 1) + c] * dv[i][0]; gd[c][1] += ecoord[3 * (NOD[i] - 1) + c] * dv[i][1]; }
+    const double normal[3] = {gd[1][0] * gd[2][1] - gd[2][0] * gd[1][1], gd[2][0] * gd[0][1] - gd[0][0] * gd[2][1],
+                              gd[0][0] * gd[1][1] - gd[1][0] * gd[0][1]};
+    for (int i = 0; i < NSUR; i++)
+      for (int c = 0; c < 3; c++) VECT[3 * (NOD[i] - 1) + c] += val * WG * H[i] * normal[c];
+  }
+  return 0;
+}
+
+/* Thermal load vectors: TLOAD_C3 (lib/static_LIB_3d.f90:381-511; 342 and 361 FI/B-bar... the reference calls it for
+ * every solid element that is not the 361 IC element) and TLOAD_C3D8IC (lib/static_LIB_3dIC.f90:458-628).
+ * Isotropic expansion coefficient alp (no temperature table), nodal temperatures TT / T0, reference temperature. */
+void orc_TLOAD_C3(int etype, int nn, const double *ecoord, const double *TT, const double *T0, double E, double nu,
+                  double alp, double ref_temp, double *VECT) {
+  double D[6][6], B[6 * 30], gderiv[20][3], H[20], det, nc[3];
+  memset(VECT, 0, sizeof(double) * 3 * nn);
+  for (int LX = 1; LX <= num_quad_points(etype); LX++) {
+    get_quad_point(etype, LX, nc);
+    if (etype == 361) shapefunc_hex8n(nc, H); else shapefunc_tet10n(nc, H);
+    get_global_deriv(etype, nn, nc, ecoord, &det, gderiv);
+    const double wg = get_weight(etype, LX) * det;
+    fill_B(nn, gderiv, B);
+    double TEMPC = 0.0, TEMP0 = 0.0;
+    for (int n = 0; n < nn; n++) { TEMPC += H[n] * TT[n]; TEMP0 += H[n] * T0[n]; }
+    cal_elastic_matrix(E, nu, D);
+    const double eps = alp * (TEMPC - ref_temp) - alp * (TEMP0 - ref_temp);
+    double SGM[6];
+    for (int i = 0; i < 6; i++) SGM[i] = (D[i][0] + D[i][1] + D[i][2]) * eps;
+    for (int j = 0; j < 3 * nn; j++) {
+      double sum = 0.0;
+      for (int k = 0; k < 6; k++) sum += SGM[k] * B[j * 6 + k];
+      VECT[j] += sum * wg;
+    }
+  }
+}
+
+void orc_TLOAD_C3D8IC(int nn, const double *ecoord, const double *TT, const double *T0, double E, double nu, double alp,
+                      double ref_temp, double *VECT) {
+  const int etype = 361, mt = 33, m = 24;
+  double D[6][6], B[6 * 33], gderiv[11][3], H[8], xj[81], jacobian[3][3], inverse[3][3], deriv[8][3];
+  double stiff[33 * 33], tmpvect[33], icdisp[9], det, det0, nc[3] = {0, 0, 0};
+#define TS(i, j) stiff[((j)-1) * mt + ((i)-1)]
+  shapederiv_hex8n(nc, deriv);
+  jacobian3(nn, ecoord, deriv, jacobian, &det0, inverse);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) inverse[i][j] = inverse[i][j] * det0;
+  memset(stiff, 0, sizeof(stiff));
+  memset(tmpvect, 0, sizeof(tmpvect));
+  for (int IC = 1; IC <= 8; IC++) {
+    get_quad_point(etype, IC, nc);
+    get_global_deriv(etype, nn, nc, ecoord, &det, gderiv);
+    shapefunc_hex8n(nc, H);
+    double TEMPC = 0.0, TEMP0 = 0.0;
+    for (int n = 0; n < nn; n++) { TEMPC += H[n] * TT[n]; TEMP0 += H[n] * T0[n]; }
+    cal_elastic_matrix(E, nu, D);
+    for (int j = 0; j < 3; j++) {
+      gderiv[nn + 0][j] = -2.0 * nc[0] * inverse[0][j] / det;
+      gderiv[nn + 1][j] = -2.0 * nc[1] * inverse[1][j] / det;
+      gderiv[nn + 2][j] = -2.0 * nc[2] * inverse[2][j] / det;
+    }
+    const double wg = get_weight(etype, IC) * det;
+    fill_B(nn + 3, gderiv, B);
+    add_BtDB(mt, B, D, wg, stiff, mt);
+    const double eps = alp * (TEMPC - ref_temp) - alp * (TEMP0 - ref_temp);
+    double SGM[6];
+    for (int i = 0; i < 6; i++) SGM[i] = (D[i][0] + D[i][1] + D[i][2]) * eps;
+    for (int j = 0; j < mt; j++) {
+      double sum = 0.0;
+      for (int k = 0; k < 6; k++) sum += SGM[k] * B[j * 6 + k];
+      tmpvect[j] += sum * wg;
+    }
+  }
+  for (int j = 1; j <= 9; j++)
+    for (int i = 1; i <= 9; i++) xj[(j - 1) * 9 + (i - 1)] = TS(m + i, m + j);
+  orc_calInverse(9, xj);
+  for (int i = 0; i < 9; i++) { /* icdisp = xj * tmpvect(25:33) */
+    double sum = 0.0;
+    for (int k = 0; k < 9; k++) sum += xj[k * 9 + i] * tmpvect[m + k];
+    icdisp[i] = sum;
+  }
+  for (int i = 1; i <= m; i++) { /* vect = tmpvect(1:24) - K(d,alpha) icdisp */
+    double sum = 0.0;
+    for (int k = 1; k <= 9; k++) sum += TS(i, m + k) * icdisp[k - 1];
+    VECT[i - 1] = tmpvect[i - 1] - sum;
+  }
+#undef TS
+}
+
 /* =============================================================================================
  * Geometrically nonlinear static analysis, total Lagrangian, linear elastic (St.Venant-Kirchhoff) material:
  * the path `!STATIC, TYPE=NLGEOM` takes for element types 361 (B-bar, the default under NLGEOM:

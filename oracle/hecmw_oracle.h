@@ -12,8 +12,9 @@
  *
  * Parity pinning: the reference's own implementation is Fortran 90 and no
  * Fortran compiler exists in the build image, so this restatement is pinned
- * against (a) the reference's golden logs examples/static/exA/A361_correct.log,
- * A342_correct.log, exG, exI (nonlinear, every sub-step), spring_boundary/SB1
+ * against (a) the reference's golden logs examples/static/ex{A,B,C,D,E,F,G}/
+ * *361_correct.log and *342_correct.log (CLOAD, face pressure, body force, gravity,
+ * centrifugal, thermal), exI (nonlinear, every sub-step), spring_boundary/SB1
  * (nonlinear + springs + SSOR, every sub-step) (nodal displacement max/min, 5
  * significant digits, harness tolerance 1e-4 absolute,
  * examples/test_FrontISTR.rb:10,225-237), (b) an independent sparse direct solve
@@ -110,6 +111,15 @@ void orc_set_num_threads(int n);
 
 /* DL_C3 volume loads (BX 1, BY 2, BZ 3, GRAV 4, CENT 5), lib/static_LIB_3d.f90:210-377; PARAMS(0:6) as in !DLOAD */
 int orc_DL_C3_volume(int etype, int nn, const double *ecoord, double RHO, int LTYPE, const double *PARAMS, double *VECT);
+
+/* DL_C3 surface pressure P<face> on one element face (361: faces 1-6, 342: faces 1-4) */
+int orc_DL_C3_surface(int etype, int nn, const double *ecoord, int face, double val, double *VECT);
+
+/* thermal load vectors: TLOAD_C3 (static_LIB_3d.f90:381-511), TLOAD_C3D8IC (static_LIB_3dIC.f90:458-628) */
+void orc_TLOAD_C3(int etype, int nn, const double *ecoord, const double *TT, const double *T0, double E, double nu,
+                  double alp, double ref_temp, double *VECT);
+void orc_TLOAD_C3D8IC(int nn, const double *ecoord, const double *TT, const double *T0, double E, double nu, double alp,
+                      double ref_temp, double *VECT);
 
 /* ---- geometrically nonlinear static (total Lagrangian, elastic): SURVEY 8(f) rank 2, pinned against
  * examples/static/exI/A361_correct.log, A342_correct.log.  u, du: (3,nn) column-major; stress/strain: (6,ngp). */

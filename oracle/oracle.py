@@ -169,6 +169,42 @@ def ass_dload_volume(mesh, A, ltype: int, params, rho: float):
             np.add.at(A.B.reshape(-1, 3), nod - 1, v.reshape(-1, 3))
 
 
+def ass_thermal_load(mesh, A, temp, temp0, alp: float, ref_temp: float):
+    """!TEMPERATURE load (fstr_ass_load.f90:277-430): TLOAD_C3D8IC for the 361 IC element, TLOAD_C3 otherwise."""
+    L = lib()
+    nodes = mesh.node.reshape(-1, 3)
+    for it in range(mesh.n_elem_type):
+        et = int(mesh.elem_type_item[it])
+        for e in range(int(mesh.elem_type_index[it]), int(mesh.elem_type_index[it + 1])):
+            nod = mesh.elem_node_item[mesh.elem_node_index[e]: mesh.elem_node_index[e + 1]]
+            sec = mesh.sections[int(mesh.section_ID[e]) - 1]
+            ec = np.ascontiguousarray(nodes[nod - 1])
+            tt = np.ascontiguousarray(np.asarray(temp, float)[nod - 1]); t0 = np.ascontiguousarray(np.asarray(temp0, float)[nod - 1])
+            v = np.zeros(3 * len(nod))
+            if et == 361 and sec["elemopt361"] == 3:
+                L.orc_TLOAD_C3D8IC(len(nod), _dp(ec), _dp(tt), _dp(t0), C.c_double(sec["E"]), C.c_double(sec["nu"]),
+                                   C.c_double(alp), C.c_double(ref_temp), _dp(v))
+            else:
+                L.orc_TLOAD_C3(et, len(nod), _dp(ec), _dp(tt), _dp(t0), C.c_double(sec["E"]), C.c_double(sec["nu"]),
+                               C.c_double(alp), C.c_double(ref_temp), _dp(v))
+            np.add.at(A.B.reshape(-1, 3), nod - 1, v.reshape(-1, 3))
+
+
+def ass_dload_pressure(mesh, A, elems, face: int, val: float):
+    """!DLOAD P<face> on an element group (0-based element indices): adds the face pressure load vectors into A.B."""
+    L = lib()
+    nodes = mesh.node.reshape(-1, 3)
+    et_of = np.empty(mesh.n_elem, np.int32)
+    for it in range(mesh.n_elem_type):
+        et_of[mesh.elem_type_index[it]: mesh.elem_type_index[it + 1]] = mesh.elem_type_item[it]
+    for e in elems:
+        nod = mesh.elem_node_item[mesh.elem_node_index[e]: mesh.elem_node_index[e + 1]]
+        ec = np.ascontiguousarray(nodes[nod - 1])
+        v = np.zeros(3 * len(nod))
+        assert L.orc_DL_C3_surface(int(et_of[e]), len(nod), _dp(ec), int(face), C.c_double(val), _dp(v)) == 0
+        np.add.at(A.B.reshape(-1, 3), nod - 1, v.reshape(-1, 3))
+
+
 def mat_ass_bc(A, inode: int, idof: int, rhs: float):
     ca = c_matrix(A)
     lib().orc_mat_ass_bc(C.byref(ca.s), int(inode), int(idof), float(rhs))

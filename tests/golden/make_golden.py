@@ -47,6 +47,33 @@ DLOAD_DECKS = [
     ("E342", "examples/static/exE/E342.msh", "examples/static/exE/E300.cnt", "examples/static/exE/E342_correct.log"),
 ]
 LTYPE = {"BX": 1, "BY": 2, "BZ": 3, "GRAV": 4, "CENT": 5}
+# face-pressure decks (examples/static/exB): !DLOAD <EGRP>, P<face>, value
+PRESSURE_DECKS = [
+    ("B361", "examples/static/exB/B361.msh", "examples/static/exB/B361.cnt", "examples/static/exB/B361_correct.log"),
+    ("B342", "examples/static/exB/B342.msh", "examples/static/exB/B342.cnt", "examples/static/exB/B342_correct.log"),
+]
+
+
+def element_ids(mtxt):
+    """Element ids in file order (first integer of every data line of the !ELEMENT blocks)."""
+    ids, inside = [], False
+    for line in mtxt.splitlines():
+        t = line.strip()
+        if t.startswith("!"):
+            inside = t.upper().startswith("!ELEMENT")
+            continue
+        if inside and t and not t.startswith("#"):
+            ids.append(int(t.replace(",", " ").split()[0]))
+    return ids
+
+
+def egroup(mtxt, name):
+    m = re.search(r"!EGROUP\s*,\s*EGRP\s*=\s*%s\s*(,\s*GENERATE)?\s*\n((?:\s*[-0-9][^\n]*\n)+)" % re.escape(name), mtxt)
+    out = []
+    for line in m.group(2).strip().splitlines():
+        v = [int(x) for x in line.replace(",", " ").split()]
+        out += list(range(v[0], v[1] + 1, v[2])) if m.group(1) else v
+    return out
 
 
 def parse_log(path, which=1):
@@ -93,6 +120,48 @@ def main():
                             global_node_ID=m.global_node_ID, **{"ngrp_" + k: v for k, v in m.node_group.items()})
         meta[name] = dict(source=dict(msh=msh, cnt=cnt, log=log), E=m.sections[0]["E"], nu=m.sections[0]["nu"], rho=rho,
                           boundary=c["boundary"], cload=[], dload=dict(ltype=LTYPE[dl[1]], params=[float(x) for x in dl[2:]]),
+                          solver=[c["solver"][0], c["solver"][1]], golden=parse_log(os.path.join(REF, log)),
+                          tolerance_abs=1.0e-4)
+    for name, msh, cnt, log in PRESSURE_DECKS:
+        m = mshio.read_msh(os.path.join(REF, msh))
+        c = mshio.read_cnt(os.path.join(REF, cnt))
+        with open(os.path.join(REF, msh)) as f:
+            mtxt = f.read()
+        with open(os.path.join(REF, cnt)) as f:
+            ctxt = f.read()
+        dl = re.search(r"!DLOAD[^\n]*\n\s*([^\n]+)", ctxt).group(1).replace(",", " ").split()
+        ids = element_ids(mtxt)
+        assert len(ids) == m.n_elem and re.fullmatch(r"P[1-6]", dl[1])
+        pos = {eid: k for k, eid in enumerate(ids)}
+        np.savez_compressed(os.path.join(OUT, name + ".npz"),
+                            node=m.node, elem_type_index=m.elem_type_index, elem_type_item=m.elem_type_item,
+                            elem_node_index=m.elem_node_index, elem_node_item=m.elem_node_item,
+                            global_node_ID=m.global_node_ID, **{"ngrp_" + k: v for k, v in m.node_group.items()})
+        meta[name] = dict(source=dict(msh=msh, cnt=cnt, log=log), E=m.sections[0]["E"], nu=m.sections[0]["nu"],
+                          boundary=c["boundary"], cload=[],
+                          pressure=dict(face=int(dl[1][1]), value=float(dl[2]), elems=[pos[e] for e in egroup(mtxt, dl[0])]),
+                          solver=[c["solver"][0], c["solver"][1]], golden=parse_log(os.path.join(REF, log)),
+                          tolerance_abs=1.0e-4)
+    # thermal-stress decks (examples/static/exF): !TEMPERATURE ALL, 120 ; !REFTEMP 20 ; initial temperature 20 ; ITEM=3 = alpha
+    for name in ("F361", "F342"):
+        msh = "examples/static/exF/%s.msh" % name
+        cnt, log = "examples/static/exF/F300.cnt", "examples/static/exF/%s_correct.log" % name
+        m = mshio.read_msh(os.path.join(REF, msh))
+        c = mshio.read_cnt(os.path.join(REF, cnt))
+        with open(os.path.join(REF, msh)) as f:
+            mtxt = f.read()
+        with open(os.path.join(REF, cnt)) as f:
+            ctxt = f.read()
+        alp = float(re.search(r"!ITEM\s*=\s*3[^\n]*\n\s*([^\s,]+)", mtxt).group(1))
+        t0 = float(re.search(r"!INITIAL CONDITION\s*,\s*TYPE\s*=\s*TEMPERATURE\s*\n\s*ALL\s*,\s*([^\s,]+)", mtxt).group(1))
+        tt = float(re.search(r"!TEMPERATURE[^\n]*\n\s*ALL\s*,\s*([^\s,]+)", ctxt).group(1))
+        ref = float(re.search(r"!REFTEMP[^\n]*\n\s*([^\s,]+)", ctxt).group(1))
+        np.savez_compressed(os.path.join(OUT, name + ".npz"),
+                            node=m.node, elem_type_index=m.elem_type_index, elem_type_item=m.elem_type_item,
+                            elem_node_index=m.elem_node_index, elem_node_item=m.elem_node_item,
+                            global_node_ID=m.global_node_ID, **{"ngrp_" + k: v for k, v in m.node_group.items()})
+        meta[name] = dict(source=dict(msh=msh, cnt=cnt, log=log), E=m.sections[0]["E"], nu=m.sections[0]["nu"],
+                          boundary=c["boundary"], cload=[], thermal=dict(alpha=alp, temperature=tt, initial=t0, reftemp=ref),
                           solver=[c["solver"][0], c["solver"][1]], golden=parse_log(os.path.join(REF, log)),
                           tolerance_abs=1.0e-4)
     for name, mesh_name, cnt, log in NL_DECKS:

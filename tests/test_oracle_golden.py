@@ -26,6 +26,66 @@ def test_oracle_matches_reference_log(name):
                 assert abs(got - want) <= 0.6e-4 * abs(want) + 1e-12
 
 
+@pytest.mark.parametrize("name", ["F361", "F342"])
+def test_oracle_matches_reference_log_thermal_load(name):
+    """exF: uniform heating 20 -> 120 degrees of the clamped block (TLOAD_C3D8IC for the default 361 IC element,
+    TLOAD_C3 for 342) against the reference's golden logs."""
+    from oracle import oracle as orc
+    from frontistr_b200 import hecmw
+    from frontistr_b200.mshio import apply_solver_card
+    mesh, cnt, meta = util.load_golden_mesh(name)
+    A = orc.mat_con(mesh)
+    orc.stiffmatrix(mesh, A)
+    th = meta["thermal"]
+    orc.ass_thermal_load(mesh, A, np.full(mesh.n_node, th["temperature"]), np.full(mesh.n_node, th["initial"]),
+                         th["alpha"], th["reftemp"])
+    n, d, v = hecmw.boundary_dofs(mesh, cnt["boundary"])
+    for i in range(len(n)):
+        orc.mat_ass_bc(A, int(n[i]), int(d[i]), float(v[i]))
+    apply_solver_card(A, cnt["solver"])
+    A.Iarray[20] = 0; A.Iarray[21] = 0
+    orc.precond_clear()
+    r = orc.solve(mesh, A)
+    orc.precond_clear()
+    assert r["error"] == 0 and A.Iarray[80] == 1
+    U = A.X.reshape(-1, 3)
+    for dd, key in enumerate(("U1", "U2", "U3")):
+        gmax, gmin = meta["golden"][key]
+        for got, want in ((U[:, dd].max(), gmax), (U[:, dd].min(), gmin)):
+            assert abs(got - want) <= meta["tolerance_abs"]
+            if abs(want) > 1e-8:
+                assert abs(got - want) <= 1.0e-4 * abs(want)
+
+
+@pytest.mark.parametrize("name", ["B361", "B342"])
+def test_oracle_matches_reference_log_face_pressure(name):
+    """exB: !DLOAD face pressure (P2 on hexahedra, P3 on 10-node tetrahedra) against the reference's golden logs."""
+    from oracle import oracle as orc
+    from frontistr_b200 import hecmw
+    from frontistr_b200.mshio import apply_solver_card
+    mesh, cnt, meta = util.load_golden_mesh(name)
+    A = orc.mat_con(mesh)
+    orc.stiffmatrix(mesh, A)
+    pr = meta["pressure"]
+    orc.ass_dload_pressure(mesh, A, pr["elems"], pr["face"], pr["value"])
+    n, d, v = hecmw.boundary_dofs(mesh, cnt["boundary"])
+    for i in range(len(n)):
+        orc.mat_ass_bc(A, int(n[i]), int(d[i]), float(v[i]))
+    apply_solver_card(A, cnt["solver"])
+    A.Iarray[20] = 0; A.Iarray[21] = 0
+    orc.precond_clear()
+    r = orc.solve(mesh, A)
+    orc.precond_clear()
+    assert r["error"] == 0 and A.Iarray[80] == 1
+    U = A.X.reshape(-1, 3)
+    for dd, key in enumerate(("U1", "U2", "U3")):
+        gmax, gmin = meta["golden"][key]
+        for got, want in ((U[:, dd].max(), gmax), (U[:, dd].min(), gmin)):
+            assert abs(got - want) <= meta["tolerance_abs"]
+            if abs(want) > 1e-8:
+                assert abs(got - want) <= 1.0e-4 * abs(want)
+
+
 @pytest.mark.parametrize("name", ["C361", "C342", "D361", "D342", "E361", "E342"])
 def test_oracle_matches_reference_log_volume_loads(name):
     """exC (body force BZ), exD (gravity), exE (centrifugal): the same K / BC / CG path through three more right-hand
