@@ -169,10 +169,11 @@ def test_solve_golden_decks(gpu, name):
         assert abs(U[:, d].max() - gmax) <= 1e-4 and abs(U[:, d].min() - gmin) <= 1e-4
 
 
-@pytest.mark.parametrize("name", ["C361", "C342", "D361", "D342", "E361", "E342"])
-def test_solve_golden_decks_volume_loads(gpu, name):
-    """exC (BZ), exD (GRAV), exE (CENT): assembly, BC elimination and CG on the device, the !DLOAD right-hand side
-    from the restated DL_C3 (caller side of the path); displacement max/min of the reference's golden logs."""
+@pytest.mark.parametrize("name", ["B361", "B342", "C361", "C342", "D361", "D342", "E361", "E342", "F361", "F342"])
+def test_solve_golden_decks_distributed_loads(gpu, name):
+    """exB (face pressure), exC (BZ), exD (GRAV), exE (CENT), exF (thermal): assembly, BC elimination and CG on the
+    device; the right-hand side comes from the restated load routines DL_C3 / TLOAD_C3 / TLOAD_C3D8IC (caller side of
+    the path, test infrastructure); displacement max/min of the reference's golden logs."""
     from oracle import oracle as orc
     from frontistr_b200.mshio import apply_solver_card
     mesh, cnt, meta = util.load_golden_mesh(name)
@@ -180,7 +181,14 @@ def test_solve_golden_decks_volume_loads(gpu, name):
     A.fstr_mat_init().hecMAT_init()
     gpu.mat_structure(mesh, A)
     gpu.fstr_StiffMatrix(mesh, A, to_host=False)
-    orc.ass_dload_volume(mesh, A, meta["dload"]["ltype"], meta["dload"]["params"], meta["rho"])
+    if "dload" in meta:
+        orc.ass_dload_volume(mesh, A, meta["dload"]["ltype"], meta["dload"]["params"], meta["rho"])
+    elif "pressure" in meta:
+        orc.ass_dload_pressure(mesh, A, meta["pressure"]["elems"], meta["pressure"]["face"], meta["pressure"]["value"])
+    else:
+        th = meta["thermal"]
+        orc.ass_thermal_load(mesh, A, np.full(mesh.n_node, th["temperature"]), np.full(mesh.n_node, th["initial"]),
+                             th["alpha"], th["reftemp"])
     gpu.mat_upload(A, values=False, rhs=True)
     n, d, v = gpu.boundary_dofs(mesh, cnt["boundary"])
     gpu.hecmw_mat_ass_bc(n, d, v)
