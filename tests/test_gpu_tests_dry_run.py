@@ -1,0 +1,23 @@
+"""Dry-runs, on the CPU, the bodies of the GPU tests that were added or changed after the last hardware run, with the
+oracle-backed stand-in of tests/shadow_backend.py in place of the `gpu` fixture.  Catches Python-level mistakes in
+those tests (they would otherwise only surface on the GPU box, where `-x` stops the suite at the first failure);
+says nothing about the product."""
+import pytest
+
+import test_gpu_parity as G
+from shadow_backend import ShadowBackend
+
+
+@pytest.mark.parametrize("name", ["B361", "C342", "D361", "E342", "F361", "F342"])
+def test_dry_run_distributed_load_decks(name):
+    G.test_solve_golden_decks_distributed_loads(ShadowBackend(), name)
+
+
+@pytest.mark.parametrize("name", ["A361", "A342"])
+def test_dry_run_golden_decks(name):
+    G.test_solve_golden_decks(ShadowBackend(), name)
+
+
+@pytest.mark.parametrize("meshname,precond,fused", [("hex12", 3, 1), ("tet4", 1, 0)])
+def test_dry_run_solve_matches_oracle(meshname, precond, fused):
+    G.test_solve_matches_oracle(ShadowBackend(), meshname, precond, fused)
