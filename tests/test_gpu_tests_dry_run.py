@@ -21,3 +21,8 @@ def test_dry_run_golden_decks(name):
 @pytest.mark.parametrize("meshname,precond,fused", [("hex12", 3, 1), ("tet4", 1, 0)])
 def test_dry_run_solve_matches_oracle(meshname, precond, fused):
     G.test_solve_matches_oracle(ShadowBackend(), meshname, precond, fused)
+
+
+def test_dry_run_mixed_types_and_sections():
+    import test_gpu_z_unvalidated as Z
+    Z.test_assembly_mixed_types_and_sections(ShadowBackend())
