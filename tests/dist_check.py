@@ -1,7 +1,7 @@
 """Multi-GPU parity check (run under torchrun on N GPUs of one box, N in 2/4/8):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
-        tools/dist_check.py [--n 24] [--tet 0] [--precond 3]
+        tests/dist_check.py [--n 24] [--tet 0] [--precond 3]
 
 Every rank partitions the same global mesh (in-process hecmw_part1/RCB), assembles and solves its subdomain
 through the C-ABI with halo exchange + all-reduce over NCCL; rank 0 gathers the displacements by global node id
@@ -14,7 +14,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # repo root (this file lives in tests/: it uses the oracle as checker)
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 

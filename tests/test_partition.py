@@ -29,7 +29,7 @@ def test_partition_equals_hecmw_part1(name):
 
 @pytest.mark.parametrize("case", ["hex9_xyz", "tet3_xy", "hexrag_zx"])
 def test_native_local_mesh_equals_numpy_formulation(case):
-    """csrc/partition.hpp:LocalMesh (what bench.py and tools/dist_check.py use) against the independent numpy
+    """csrc/partition.hpp:LocalMesh (what bench.py and tests/dist_check.py use) against the independent numpy
     formulation on meshes the hecmw_part1 fixtures do not cover."""
     mesh, axes = {"hex9_xyz": (meshgen.hex_cube(9), "xyz"), "tet3_xy": (meshgen.tet10_cube(3), "xy"),
                   "hexrag_zx": (meshgen.hex_cube(3, nx=7, ny=2, nz=5), "zx")}[case]

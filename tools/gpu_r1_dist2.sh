@@ -3,7 +3,7 @@
 N=${1:-2}; shift
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
-timeout 300 $TR tools/dist_check.py --hex 24 2>&1 | grep -E "PASS|FAIL|rror" | head -5 | tee gpurun_out/dist_check_n$N.log
+timeout 300 $TR tests/dist_check.py --hex 24 2>&1 | grep -E "PASS|FAIL|rror" | head -5 | tee gpurun_out/dist_check_n$N.log
 for comm in "$@"; do
   timeout 900 $TR bench.py --gpus $N --steps 3 --warmup 3 --comm $comm --no-e2e > gpurun_out/bench_n${N}_$comm.json 2> gpurun_out/bench_n${N}_$comm.err; echo "bench $comm rc=$?"
   python - <<PY
