@@ -335,3 +335,148 @@ def read_dist_mesh(path: str, elemopt361: int = kel361IC, E=None, nu=None) -> he
     m.export_item = export_item.astype(np.int32)
     m.my_rank, m.PETOT, m.zero = my_rank, PETOT, zero
     return m
+
+
+# ---------------------------------------------------------------------------------------------------
+# HECMW-DMD-ASCII writer: what hecmw_part1 writes per rank (hecmw1/src/common/hecmw_io_dist.c:1888-2839,
+# print_header .. print_contact_info), so that a mesh partitioned in-process (frontistr_b200/partition.py) can
+# be handed to an unmodified fistr1.  Byte-identical to the real tool for the meshes meshgen.write_msh emits
+# (tests/test_partition.py::test_dist_writer_equals_hecmw_part1).
+# ---------------------------------------------------------------------------------------------------
+def _fmt_int_ary(vals, cols=10):
+    """print_int_ary (hecmw_io_dist.c:1819-1843): '%d' + (' ' | newline every `cols`), trailing newline if ragged."""
+    vals = [int(v) for v in vals]
+    if not vals:
+        return ""
+    s = []
+    for i, v in enumerate(vals):
+        s.append("%d%s" % (v, " " if (i + 1) % cols else "\n"))
+    if len(vals) % cols:
+        s.append("\n")
+    return "".join(s)
+
+
+def _fmt_dbl_ary(vals, cols):
+    vals = [float(v) for v in vals]
+    if not vals:
+        return ""
+    s = []
+    for i, v in enumerate(vals):
+        s.append("%.16E%s" % (v, " " if (i + 1) % cols else "\n"))
+    if len(vals) % cols:
+        s.append("\n")
+    return "".join(s)
+
+
+def write_dist_mesh(path: str, local: hecmwST_local_mesh, global_mesh: hecmwST_local_mesh, domain: np.ndarray,
+                    gridfile: str = "cube.msh", header: str = "synthetic cube", material_name: str = "M1") -> None:
+    """`local` = partition.local_mesh(global_mesh, domain, rank, nparts).  Element connectivity of type 342 is
+    converted back to the HEC-MW file order (fistr1/src/common/hecmw2fstr_connect_conv.c:19)."""
+    from .partition import _NN
+    rank, nparts = local.my_rank, local.PETOT
+    owner = np.asarray(domain)
+    # ---- element ownership (set_elem_belong_domain_nb, hecmw_partition.c:3163-3181): lowest node domain;
+    # elem_ID = (running number among the owner's own elements, owner); shared elements per neighbour
+    n_elem_g = global_mesh.n_elem
+    eown = np.empty(n_elem_g, np.int64)
+    touch = np.zeros((n_elem_g, nparts), bool)
+    for it in range(global_mesh.n_elem_type):
+        nn = _NN[int(global_mesh.elem_type_item[it])]
+        e0, e1 = int(global_mesh.elem_type_index[it]), int(global_mesh.elem_type_index[it + 1])
+        s0 = int(global_mesh.elem_node_index[e0])
+        conn = global_mesh.elem_node_item[s0: s0 + (e1 - e0) * nn].reshape(-1, nn)
+        ow = owner[conn - 1]
+        eown[e0:e1] = ow.min(axis=1)
+        for q in range(nparts):
+            touch[e0:e1, q] = (ow == q).any(axis=1)
+    own_id = np.zeros(n_elem_g, np.int64)                 # running number of every element among its owner's own elements
+    for q in range(nparts):
+        mine = np.nonzero(eown == q)[0]
+        own_id[mine] = np.arange(1, len(mine) + 1)
+    ge = local.global_elem_ID.astype(np.int64) - 1       # 0-based global element index of my elements
+    etype_of = np.empty(n_elem_g, np.int64)
+    for it in range(global_mesh.n_elem_type):
+        etype_of[global_mesh.elem_type_index[it]: global_mesh.elem_type_index[it + 1]] = global_mesh.elem_type_item[it]
+    internal = np.nonzero(eown[ge] == rank)[0] + 1
+    out = []
+    w = out.append
+    w("!HECMW-DMD-ASCII version=4\n")
+    # ---- global info (print_global_info :1909-1990)
+    for v in (0, 0, 1, 1, 4, 0):                          # adapt, initcon, parttype NODE-BASED, depth 1, version 4, contact
+        w("%d\n" % v)
+    w("%s\n" % gridfile)
+    w("0\n")                                             # n_file
+    w("1\n%s\n" % header)                               # header flag + header
+    w("%.16E\n" % 0.0)                                   # zero_temp
+    # ---- node info (:1991-2083)
+    w("%d\n%d\n%d\n%d\n" % (local.n_node, local.n_node, 0, local.nn_internal))
+    w(_fmt_int_ary(local.node_ID.reshape(-1), 2))
+    w(_fmt_int_ary(local.global_node_ID))
+    w(_fmt_dbl_ary(local.node, 3))
+    w("3\n1\n")
+    w(_fmt_int_ary([0, local.nn_internal]))
+    w(_fmt_int_ary([3]))
+    # ---- elem info (:2084-2191)
+    w("%d\n%d\n%d\n" % (local.n_elem, local.n_elem, len(internal)))
+    w(_fmt_int_ary(internal))
+    eid = np.stack([own_id[ge], eown[ge]], axis=1).reshape(-1)
+    w(_fmt_int_ary(eid, 2))
+    w(_fmt_int_ary(ge + 1))
+    w(_fmt_int_ary(etype_of[ge]))
+    w("%d\n" % local.n_elem_type)
+    w(_fmt_int_ary(local.elem_type_index))
+    w(_fmt_int_ary(local.elem_type_item))
+    w(_fmt_int_ary(local.elem_node_index))
+    eni = np.array(local.elem_node_item, np.int64)
+    inv342 = np.argsort(TABLE342)                          # FrontISTR order -> file order
+    for e in np.nonzero(etype_of[ge] == 342)[0]:
+        s0 = int(local.elem_node_index[e])
+        tmp = np.empty(10, np.int64); tmp[TABLE342] = eni[s0:s0 + 10]
+        eni[s0:s0 + 10] = tmp
+    w(_fmt_int_ary(eni))
+    w(_fmt_int_ary(local.section_ID))
+    w(_fmt_int_ary(np.arange(local.n_elem + 1)))          # elem_mat_ID_index
+    w(_fmt_int_ary(np.ones(local.n_elem, np.int64)))      # elem_mat_ID_item
+    w("%d\n" % local.n_elem)                              # n_elem_mat_ID
+    # ---- comm info (:2192-2283)
+    for v in (1 if rank == 0 else 0, 0, nparts, 1, rank, 0, nparts, local.n_neighbor_pe):
+        w("%d\n" % v)
+    w(_fmt_int_ary(local.neighbor_pe))
+    w(_fmt_int_ary(local.import_index)); w(_fmt_int_ary(local.import_item))
+    w(_fmt_int_ary(local.export_index)); w(_fmt_int_ary(local.export_item))
+    sh_index, sh_item = [0], []
+    for q in local.neighbor_pe:
+        sh = np.nonzero(touch[ge, int(q)])[0] + 1
+        sh_item += sh.tolist(); sh_index.append(len(sh_item))
+    w(_fmt_int_ary(sh_index)); w(_fmt_int_ary(sh_item))
+    # ---- section info (:2351-2410): one SOLID section, thickness 1.0, material 1
+    w("1\n"); w(_fmt_int_ary([1])); w(_fmt_int_ary([0])); w(_fmt_int_ary([0, 1])); w(_fmt_int_ary([1]))
+    w(_fmt_int_ary([0, 0])); w(_fmt_int_ary([0, 1])); w(_fmt_dbl_ary([1.0], 5))
+    # ---- material info (:2411-2473): ITEM=1, SUBITEM=2 (E, nu)
+    sct = global_mesh.sections[0]
+    w("1\n1\n2\n2\n%s\n" % material_name)
+    w(_fmt_int_ary([0, 1])); w(_fmt_int_ary([0, 2])); w(_fmt_int_ary([0, 1, 2]))
+    w(_fmt_dbl_ary([sct["E"], sct["nu"]], 5)); w(_fmt_dbl_ary([0.0, 0.0], 5))
+    # ---- mpc, amplitude (:2474-2570)
+    w("0\n0\n")
+    # ---- node groups (:2571-2602): ALL + the mesh's groups, members in ascending global id mapped to local ids
+    g2l = np.zeros(global_mesh.n_node + 1, np.int64)
+    g2l[local.global_node_ID] = np.arange(1, local.n_node + 1)
+    names = ["ALL"] + list(global_mesh.node_group.keys())
+    members = [np.arange(1, global_mesh.n_node + 1)] + [np.asarray(global_mesh.global_node_ID)[np.asarray(v) - 1]
+                                                        for v in global_mesh.node_group.values()]
+    w("%d\n" % len(names))
+    for nm in names:
+        w("%s\n" % nm)
+    idx, items = [0], []
+    for mem in members:
+        l = g2l[np.asarray(mem, np.int64)]
+        items += l[l > 0].tolist(); idx.append(len(items))
+    w(_fmt_int_ary(idx)); w(_fmt_int_ary(items))
+    # ---- element groups (:2603-2634): ALL
+    w("1\nALL\n"); w(_fmt_int_ary([0, local.n_elem])); w(_fmt_int_ary(np.arange(1, local.n_elem + 1)))
+    # ---- surface groups, refine info, contact pairs
+    w("0\n0\n0\n")
+    with open(path, "w") as f:
+        f.write("".join(out))
+

@@ -11,7 +11,8 @@ import fb_util as util
 from frontistr_b200 import meshgen, partition
 
 CASES = {"hex5_xy": lambda: meshgen.hex_cube(5), "hex6_xyz": lambda: meshgen.hex_cube(6),
-         "hex7_zyx": lambda: meshgen.hex_cube(7), "tet2_xy": lambda: meshgen.tet10_cube(2)}
+         "hex7_zyx": lambda: meshgen.hex_cube(7), "tet2_xy": lambda: meshgen.tet10_cube(2),
+         "tet3_xyz": lambda: meshgen.tet10_cube(3)}
 KEYS = ("global_node_ID", "node_ID", "elem_type_index", "elem_type_item", "elem_node_index", "elem_node_item",
         "neighbor_pe", "import_index", "import_item", "export_index", "export_item")
 
@@ -43,6 +44,29 @@ def test_native_local_mesh_equals_numpy_formulation(case):
             assert np.array_equal(getattr(a, k), getattr(b, k)), (r, k)
         for g in mesh.node_group:
             assert np.array_equal(a.node_group[g], b.node_group[g])
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_dist_writer_equals_hecmw_part1(name, tmp_path):
+    """mshio.write_dist_mesh (HECMW-DMD-ASCII, what an unmodified fistr1 reads) is BYTE-IDENTICAL to the files the real
+    hecmw_part1 wrote for the same .msh and the same RCB control card (sha256 of every rank file stored by
+    tests/golden/make_partition_golden.py): global/node/element/communication/section/material/group blocks,
+    element ownership, shared-element lists, number formats and line breaks."""
+    import hashlib
+    from frontistr_b200 import mshio
+    d = np.load(os.path.join(util.GOLDEN, "part_%s.npz" % name))
+    axes, nd = str(d["axes"]), int(d["ndomain"])
+    msh = str(tmp_path / "cube.msh")
+    meshgen.write_msh(CASES[name](), msh)
+    mesh = mshio.read_msh(msh)          # coordinates exactly as the text file carries them
+    dom = partition.rcb_domains(mesh, axes)
+    for r in range(nd):
+        path = str(tmp_path / ("cube_p.%d" % r))
+        mshio.write_dist_mesh(path, partition.local_mesh(mesh, dom, r, nd), mesh, dom)
+        with open(path, "rb") as f:
+            assert hashlib.sha256(f.read()).hexdigest() == str(d["r%d_sha256" % r]), (name, r)
+        back = mshio.read_dist_mesh(path)           # and it reads back
+        assert back.n_node == int(d["r%d_n_node" % r]) and np.array_equal(back.export_item, d["r%d_export_item" % r])
 
 
 def test_partition_tables_are_consistent():
