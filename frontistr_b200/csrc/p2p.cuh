@@ -15,7 +15,8 @@
 // Every rank owns one "arena" (plain cudaMalloc memory exported with cudaIpcGetMemHandle); layout:
 //   [ P2PEntry table [P2P_NQ][2][8] | halo flags u64[8] | p vector (3*NP+8 doubles) ]
 // One process drives one GPU, so a kernel spinning on a word written by another GPU cannot starve its
-// producer.  Every spin has a time-out that raises an error flag instead of hanging the device.
+// producer.  Every spin has a time-out that raises an error flag instead of hanging the device; after the first
+// time-out all later waits on that GPU return immediately, so a broken exchange costs seconds, not minutes.
 #pragma once
 #include "common.cuh"
 
@@ -64,7 +65,7 @@ __device__ __forceinline__ unsigned long long p2p_now_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-constexpr unsigned long long kP2PTimeoutNs = 4000000000ull;   // 4 s
+constexpr unsigned long long kP2PTimeoutNs = 2000000000ull;   // 2 s; once any wait on this GPU has timed out, later waits give up at once
 
 __device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -92,6 +93,7 @@ __device__ __forceinline__ void p2p_consume_warp(const P2PView &pv, int q, unsig
   if (lane < pv.nranks) {
     const unsigned long long t0 = p2p_now_ns();
     while (ld_acquire_sys(&base[lane].tag) != seq) {
+      if (*(volatile int *)pv.err != 0) break;
       if (p2p_now_ns() - t0 > kP2PTimeoutNs) { atomicExch(pv.err, 1); break; }
     }
     v0 = ld_relaxed_sys(&base[lane].v[0]);
@@ -111,6 +113,7 @@ __device__ __forceinline__ void p2p_wait_halo_warp(const P2PView &pv, const P2PN
     const unsigned long long *f = pv.hflag[pv.me] + nb.rank[lane];
     const unsigned long long t0 = p2p_now_ns();
     while (ld_acquire_sys(f) < seq) {
+      if (*(volatile int *)pv.err != 0) break;
       if (p2p_now_ns() - t0 > kP2PTimeoutNs) { atomicExch(pv.err, 2); break; }
     }
   }
