@@ -163,3 +163,102 @@ int fbemul_inverse9(double *A /* row-major 9x9, in place */) {
 }
 
 }  // extern "C"
+
+// =============================================================================================
+// TEST-ONLY model of the peer-memory protocol of the fused CG iteration (p2p.cuh + the sequence numbering of
+// api_solver.inc): R ranks = R host threads, each rank's "arena" = a block of atomics that every other rank may write.
+// One iteration per rank is   update_p: consume (rr,rz)[k-1] -> push halo values to the neighbours -> signal
+//                             spmv    : wait for the neighbours' halo flags -> read halo -> publish p.q
+//                             tail    : consume p.q -> publish (rr,rz)
+// exactly as the kernels do (tagged partial sums in parity-double-buffered slots, one flag word per source rank,
+// monotone sequence numbers).  Threads are de-synchronised with random spinning.  Checked invariants: every consume
+// sees, for every rank, the payload that belongs to ITS sequence number (no slot is overwritten before all readers
+// are done), and every halo read sees the value of the current iteration (no neighbour runs ahead into our halo).
+// Lets the N = 8 logic (incl. ranks that are not neighbours of each other) be exercised without 8 GPUs.
+// =============================================================================================
+#include <atomic>
+#include <random>
+
+namespace p2pmodel {
+constexpr int MAXR = 8;
+struct Entry { std::atomic<double> v0{0}, v1{0}; std::atomic<unsigned long long> tag{0}; };
+struct Arena {
+  Entry ar[2][2][MAXR];                       // [quantity][parity][source rank]
+  std::atomic<unsigned long long> hflag[MAXR];
+  std::atomic<double> halo[MAXR];             // one halo value per source rank (stands for the halo rows of p)
+};
+
+static int run(int R, const int *nbr /* R x R adjacency */, int iters, unsigned seed, int recompute_every,
+               int break_halo_wait /* negative control: do not wait for the neighbours' flags */) {
+  std::vector<Arena> arena(R);
+  for (auto &a : arena) for (int r = 0; r < MAXR; r++) { a.hflag[r] = 0; a.halo[r] = -1.0; }
+  std::atomic<int> errors{0};
+  auto payload = [](int q, int rank, unsigned long long seq) { return 1000.0 * q + 10.0 * rank + 1e-3 * (double)seq; };
+  std::vector<std::thread> th;
+  // the 1-in-`recompute_every` iterations go through the "NCCL" path: modelled as a full barrier that publishes nothing
+  pthread_barrier_t bar;
+  pthread_barrier_init(&bar, nullptr, R);
+  for (int me = 0; me < R; me++)
+    th.emplace_back([&, me]() {
+      std::mt19937 rng(seed * 131 + me);
+      auto jitter = [&]() { volatile int x = 0; for (int i = 0, n = rng() % 400; i < n; i++) x += i; if (rng() % 7 == 0) std::this_thread::yield(); };
+      unsigned long long seq_pq = 0, seq_rrrz = 0, halo_seq = 0, pending = 0;
+      auto publish = [&](int q, unsigned long long seq) {
+        for (int r = 0; r < R; r++) {
+          Entry &e = arena[r].ar[q][seq & 1][me];
+          e.v0.store(payload(q, me, seq), std::memory_order_relaxed);
+          e.v1.store(-payload(q, me, seq), std::memory_order_relaxed);
+          e.tag.store(seq, std::memory_order_release);
+          jitter();
+        }
+      };
+      auto consume = [&](int q, unsigned long long seq) {
+        for (int r = 0; r < R; r++) {
+          Entry &e = arena[me].ar[q][seq & 1][r];
+          while (e.tag.load(std::memory_order_acquire) != seq) std::this_thread::yield();
+          const double v0 = e.v0.load(std::memory_order_relaxed), v1 = e.v1.load(std::memory_order_relaxed);
+          jitter();
+          if (v0 != payload(q, r, seq) || v1 != -v0 || e.tag.load(std::memory_order_acquire) != seq) errors++;
+        }
+      };
+      for (int k = 1; k <= iters; k++) {
+        const bool recompute = recompute_every > 0 && k % recompute_every == 0;
+        // ---- update_p(k)
+        if (pending) consume(1, pending);
+        pending = 0;
+        jitter();
+        ++halo_seq;
+        for (int q = 0; q < R; q++) if (nbr[me * R + q]) arena[q].halo[me].store((double)k, std::memory_order_relaxed);
+        for (int q = 0; q < R; q++) if (nbr[me * R + q]) arena[q].hflag[me].store(halo_seq, std::memory_order_release);
+        // ---- spmv(k)
+        jitter();
+        if (!break_halo_wait)
+          for (int q = 0; q < R; q++) if (nbr[me * R + q]) while (arena[me].hflag[q].load(std::memory_order_acquire) < halo_seq) std::this_thread::yield();
+        for (int q = 0; q < R; q++) if (nbr[me * R + q]) { jitter(); if (arena[me].halo[q].load(std::memory_order_relaxed) != (double)k) errors++; }
+        if (recompute) {   // NCCL iteration: collectives = barriers, nothing published
+          pthread_barrier_wait(&bar);
+          jitter();
+          pthread_barrier_wait(&bar);
+          continue;
+        }
+        const unsigned long long spq = ++seq_pq;
+        publish(0, spq);
+        // ---- tail(k)
+        jitter();
+        consume(0, spq);
+        const unsigned long long srz = ++seq_rrrz;
+        publish(1, srz);
+        pending = srz;
+      }
+    });
+  for (auto &t : th) t.join();
+  pthread_barrier_destroy(&bar);
+  return errors.load();
+}
+}  // namespace p2pmodel
+
+extern "C" int fbemul_p2p_protocol_model(int R, const int *nbr, int iters, unsigned seed, int recompute_every,
+                                         int break_halo_wait) {
+  if (R < 1 || R > p2pmodel::MAXR) return -1;
+  return p2pmodel::run(R, nbr, iters, seed, recompute_every, break_halo_wait);
+}

@@ -112,3 +112,33 @@ def test_two_rank_cg_over_gloo_equals_serial(world, tmp_path):
         assert abs(int(d["iters"]) - r1["iter"]) <= 2
         ref = A.X.reshape(-1, 3)[d["gid"] - 1]
         assert util.rel_l2(d["x"].reshape(-1, 3), ref) < 1e-8      # halo included
+
+
+def test_p2p_protocol_model_eight_ranks():
+    """Threaded model (csrc/emul_test.cpp: p2pmodel) of the peer-memory protocol of the fused CG iteration — tagged
+    partial sums in parity-double-buffered slots written into every rank's table, one halo flag per source rank,
+    monotone sequence numbers, a 1-in-50 iteration on the collective path — with 8 de-synchronised ranks on a fully
+    connected and on a chain topology (ranks that are NOT neighbours of each other): no consume may ever see another
+    sequence number's payload and no halo read another iteration's value.  The hardware run covered N = 2 only; this
+    exercises the N = 8 sequencing logic.  Negative control: without the halo wait the model does report violations."""
+    import ctypes as C
+    import __graft_entry__ as g
+    em = C.CDLL(g.build_emul())
+
+    def run(nbr, iters, seed, rec, broken=0):
+        a = np.ascontiguousarray(nbr, np.int32)
+        return em.fbemul_p2p_protocol_model(len(a), a.ctypes.data_as(C.POINTER(C.c_int)), iters, seed, rec, broken)
+
+    full = 1 - np.eye(8, dtype=np.int32)
+    chain = np.zeros((8, 8), np.int32)
+    for i in range(7):
+        chain[i, i + 1] = chain[i + 1, i] = 1
+    cube = np.zeros((8, 8), np.int32)            # 2x2x2 blocks that only exchange across faces
+    for a in range(8):
+        for b in (1, 2, 4):
+            cube[a, a ^ b] = 1
+    for topo in (full, chain, cube):
+        for seed in range(3):
+            assert run(topo, 300, seed, 50) == 0
+    assert run(1 - np.eye(2, dtype=np.int32), 300, 0, 7) == 0
+    assert sum(run(chain, 300, seed, 50, broken=1) for seed in range(3)) > 0
