@@ -54,3 +54,77 @@ class ShadowBackend:
     def hecmw_matvec(self, X, n_internal3):
         from oracle import oracle as orc
         return orc.matvec(self._A, np.ascontiguousarray(X, float))[:n_internal3]
+
+
+def patch_nonlinear(monkeypatch):
+    """Replaces the five device calls used by frontistr_b200.hecmw.fstr_solve_NLGEOM with oracle-backed stand-ins
+    (module-level patch: fstr_solve_NLGEOM calls them as module functions).  Returns the hecmw module, usable as `gpu`."""
+    import ctypes as C
+
+    from oracle import oracle as orc
+    from frontistr_b200 import hecmw
+    L = orc.lib()
+    d = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    st = {}
+
+    def _elems(m):
+        for it in range(m.n_elem_type):
+            et = int(m.elem_type_item[it])
+            for e in range(int(m.elem_type_index[it]), int(m.elem_type_index[it + 1])):
+                yield e, et, np.ascontiguousarray(m.elem_node_item[m.elem_node_index[e]: m.elem_node_index[e + 1]], np.int32)
+
+    def _sec(m, e, et):
+        sec = orc.c_sections(m)
+        s = sec[int(m.section_ID[e]) - 1]
+        return sec, s, int(et == 361 and s.elemopt361 == 2)
+
+    def nl_state_reset(m):
+        st["e"] = np.zeros((m.n_elem, 8, 6)); st["s"] = np.zeros((m.n_elem, 8, 6))
+
+    def mat_structure(m, A):
+        st["A"] = A
+        if A.D is None:
+            A.hecMAT_init()
+
+    def stiff_nl(m, A, u):
+        A.D[:] = 0; A.AL[:] = 0; A.AU[:] = 0
+        cm = orc.c_matrix(A)
+        xyz = m.node.reshape(-1, 3)
+        for e, et, nod in _elems(m):
+            keep, s, bbar = _sec(m, e, et)
+            ec = np.ascontiguousarray(xyz[nod - 1]); ue = np.ascontiguousarray(np.asarray(u).reshape(-1, 3)[nod - 1])
+            K = np.zeros((3 * len(nod), 3 * len(nod)))
+            L.orc_STF_C3_TL(et, len(nod), d(ec), d(ue), d(st["e"][e]), d(st["s"][e]), C.byref(s), bbar, d(K))
+            L.orc_mat_ass_elem(C.byref(cm.s), len(nod), nod.ctypes.data_as(C.POINTER(C.c_int)), d(K), 3 * len(nod))
+        return {}
+
+    def update(m, unode, dunode):
+        qf = np.zeros(3 * m.n_node)
+        xyz = m.node.reshape(-1, 3)
+        for e, et, nod in _elems(m):
+            keep, s, bbar = _sec(m, e, et)
+            ec = np.ascontiguousarray(xyz[nod - 1])
+            u = np.ascontiguousarray(unode.reshape(-1, 3)[nod - 1]); du = np.ascontiguousarray(dunode.reshape(-1, 3)[nod - 1])
+            q = np.zeros(3 * len(nod))
+            L.orc_UPDATE_C3_TL(et, len(nod), d(ec), d(u), d(du), C.byref(s), bbar, d(q), d(st["e"][e]), d(st["s"][e]))
+            np.add.at(qf.reshape(-1, 3), nod - 1, q.reshape(-1, 3))
+        return qf
+
+    def ass_bc(nodes, dofs, vals):
+        for n, dof, v in zip(nodes, dofs, vals):
+            orc.mat_ass_bc(st["A"], int(n), int(dof), float(v))
+
+    def solve(m, A, device_resident=False):
+        orc.precond_clear()
+        r = orc.solve(m, A)
+        orc.precond_clear()
+        return r
+
+    monkeypatch.setattr(hecmw, "mat_structure", mat_structure)
+    monkeypatch.setattr(hecmw, "nl_state_reset", nl_state_reset)
+    monkeypatch.setattr(hecmw, "mat_upload", lambda A, values=True, rhs=True: None)
+    monkeypatch.setattr(hecmw, "fstr_StiffMatrix_NL", stiff_nl)
+    monkeypatch.setattr(hecmw, "fstr_UpdateNewton", update)
+    monkeypatch.setattr(hecmw, "hecmw_mat_ass_bc", ass_bc)
+    monkeypatch.setattr(hecmw, "hecmw_solve", solve)
+    return hecmw

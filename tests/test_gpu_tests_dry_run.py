@@ -26,3 +26,11 @@ def test_dry_run_solve_matches_oracle(meshname, precond, fused):
 def test_dry_run_mixed_types_and_sections():
     import test_gpu_z_unvalidated as Z
     Z.test_assembly_mixed_types_and_sections(ShadowBackend())
+
+
+@pytest.mark.parametrize("name", ["I361", "I342", "cylinder"])
+def test_dry_run_nonlinear_newton(name, monkeypatch):
+    """Body of the opt-in nonlinear GPU test with the device calls of the Newton-driver mirror replaced by the oracle."""
+    import test_gpu_z_unvalidated as Z
+    from shadow_backend import patch_nonlinear
+    Z.test_nlgeom_newton_matches_oracle_and_golden(patch_nonlinear(monkeypatch), name)

@@ -252,76 +252,6 @@ def test_hyperelastic_cylinder_newton_loop_runs():
     assert radial.max() <= 1e-9 and 0.9 * incompressible < -radial.min() < 1.0 * incompressible
 
 
-def test_newton_driver_mirror_with_oracle_backend(monkeypatch):
-    """Host logic of frontistr_b200.hecmw.fstr_solve_NLGEOM (the fstr_Newton mirror that drives the device path):
-    its five device calls are replaced by oracle-backed stand-ins, so the loop structure, load factors, recycle
-    flags and convergence logic are exercised on the CPU and must reproduce the reference's exI/A361 log."""
-    import ctypes as C
-    from oracle import oracle as orc
-    from frontistr_b200 import hecmw
-    from frontistr_b200.hecmw_types import kel361BBAR
-    from frontistr_b200.mshio import apply_solver_card
-    g = util.golden_meta()["I361"]
-    mesh, _, _ = util.load_golden_mesh(g["mesh"], elemopt361=kel361BBAR)
-    A = orc.mat_con(mesh)
-    apply_solver_card(A, (g["solver"][0], g["solver"][1]))
-    A.Iarray[20] = 0; A.Iarray[21] = 0
-    L = orc.lib()
-    d = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
-    sec = orc.c_sections(mesh)
-    state = dict(e=np.zeros((mesh.n_elem, 8, 6)), s=np.zeros((mesh.n_elem, 8, 6)))
-    xyz = mesh.node.reshape(-1, 3)
-
-    def stiff_nl(m, mat, u):
-        mat.D[:] = 0; mat.AL[:] = 0; mat.AU[:] = 0
-        cm = orc.c_matrix(mat)
-        for e in range(m.n_elem):
-            nod = np.ascontiguousarray(m.elem_node_item[8 * e: 8 * e + 8], np.int32)
-            ec = np.ascontiguousarray(xyz[nod - 1]); ue = np.ascontiguousarray(u.reshape(-1, 3)[nod - 1])
-            K = np.zeros((24, 24))
-            L.orc_STF_C3_TL(361, 8, d(ec), d(ue), d(state["e"][e]), d(state["s"][e]), C.byref(sec[0]), 1, d(K))
-            L.orc_mat_ass_elem(C.byref(cm.s), 8, nod.ctypes.data_as(C.POINTER(C.c_int)), d(K), 24)
-        return {}
-
-    def update(m, unode, dunode):
-        qf = np.zeros(3 * m.n_node)
-        for e in range(m.n_elem):
-            nod = m.elem_node_item[8 * e: 8 * e + 8]
-            ec = np.ascontiguousarray(xyz[nod - 1])
-            u = np.ascontiguousarray(unode.reshape(-1, 3)[nod - 1]); du = np.ascontiguousarray(dunode.reshape(-1, 3)[nod - 1])
-            q = np.zeros(24)
-            L.orc_UPDATE_C3_TL(361, 8, d(ec), d(u), d(du), C.byref(sec[0]), 1, d(q), d(state["e"][e]), d(state["s"][e]))
-            np.add.at(qf.reshape(-1, 3), nod - 1, q.reshape(8, 3))
-        return qf
-
-    def ass_bc(nodes, dofs, vals):
-        for n, dof, v in zip(nodes, dofs, vals):
-            orc.mat_ass_bc(A, int(n), int(dof), float(v))
-
-    def solve(m, mat, device_resident=False):
-        orc.precond_clear()
-        return orc.solve(m, mat)
-
-    monkeypatch.setattr(hecmw, "mat_structure", lambda m, mat: None)
-    monkeypatch.setattr(hecmw, "nl_state_reset", lambda m: None)
-    monkeypatch.setattr(hecmw, "mat_upload", lambda mat, values=True, rhs=True: None)
-    monkeypatch.setattr(hecmw, "fstr_StiffMatrix_NL", stiff_nl)
-    monkeypatch.setattr(hecmw, "fstr_UpdateNewton", update)
-    monkeypatch.setattr(hecmw, "hecmw_mat_ass_bc", ass_bc)
-    monkeypatch.setattr(hecmw, "hecmw_solve", solve)
-    bc = hecmw.boundary_dofs(mesh, [tuple(b) for b in g["boundary"]])
-    cn, cd, cv = [], [], []
-    for grp, dof, val in g["cload"]:
-        ids = list(mesh.node_group[grp]); cn += ids; cd += [dof] * len(ids); cv += [val] * len(ids)
-    nl = g["nlgeom"]
-    r = hecmw.fstr_solve_NLGEOM(mesh, A, bc, (cn, cd, cv), nl["substeps"], nl["converg"], nl["max_iter"])
-    assert r["error"] == 0 and np.all(r["newton_iters"] == 2)
-    for k, gold in enumerate(g["golden_steps"]):
-        U = r["unode_steps"][k].reshape(-1, 3)
-        for dd, key in enumerate(("U1", "U2", "U3")):
-            assert abs(U[:, dd].max() - gold[key][0]) <= g["tolerance_abs"] and abs(U[:, dd].min() - gold[key][1]) <= g["tolerance_abs"]
-
-
 @pytest.mark.parametrize("name", ["A361", "A342"])
 def test_oracle_iterpremax2_matches_reference_log(name):
     """iterPREmax = 2 (the additive-Schwarz double sweep of hecmw_precond_33_apply, precond_33.f90:86-114) with SSOR
