@@ -109,10 +109,6 @@ def _local_mesh_numpy(mesh: hecmwST_local_mesh, domain: np.ndarray, rank: int, n
     m.node_ID = np.stack([local_in_owner[loc_nodes], owner[loc_nodes]], axis=1).astype(np.int32)
     m.n_elem = tindex[-1]; m.n_elem_type = len(types)
     m.elem_type_index = np.array(tindex, np.int32); m.elem_type_item = np.array(types, np.int32)
-    nidx = [0]
-    for c in items:
-        nidx.extend((nidx[-1] + c.shape[1] * np.arange(1, c.shape[0] + 1)).tolist() if c.shape[0] < 1000 else [])
-    # vectorised elem_node_index
     sizes = np.concatenate([np.full(c.shape[0], c.shape[1], np.int64) for c in items]) if items else np.zeros(0, np.int64)
     m.elem_node_index = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
     m.elem_node_item = np.concatenate([g2l[c - 1].reshape(-1) for c in items]).astype(np.int32) if items else np.zeros(0, np.int32)
