@@ -391,7 +391,11 @@ def run_b200(args):
                             "elements_per_s_call": n_elem_global / (asm_total_ms * 1e-3),
                             "kernel_ms": asm_kernel_ms, "fp64_peak_tflops_measured": fp64_peak,
                             "fp64_frac": (150e3 * n_elem_global / world / (asm_kernel_ms * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None,
-                            "note": "STF_C3D8IC + scatter-add into BCSR slots, matrix zeroing included; 150 kflop/element (SURVEY a5)"},
+                            "gather": int(hecmw.get_option("asm_gather") != 0),
+                            "ic_inverse": {1: "registers+shuffles (device self-test passed)",
+                                           0: "shared memory (fallback)"}.get(hecmw.get_option("ic_inverse_active"), "?"),
+                            "note": "STF_C3D8IC (one element per warp) + deterministic gather into precomputed BCSR slots "
+                                    "(atomic scatter-add incl. matrix zeroing if gather=0); 150 kflop/element (SURVEY a5)"},
                "setup_s": {"mesh+partition": t_mesh, "mat_con": t_con}, "device": dev["name"]}
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -104,7 +104,8 @@ gather_sum_kernel(size_t nblk, const unsigned *__restrict__ gptr, const unsigned
 }
 
 // One element per warp.  sect[3*s..] = D11, D12, D44 of section s; sect_form[s] = elemopt361.
-template <int FORM, int WARPS>
+// ICINV (IC element only): calInverse in registers + shuffles (1) or through shared memory (0), see element_math.cuh.
+template <int FORM, int WARPS, int ICINV = 1>
 __global__ void __launch_bounds__(WARPS * 32)
 stiff_kernel(int e0, int e1, const int *__restrict__ elem_node_index, const int *__restrict__ elem_node_item,
              const double *__restrict__ node, const int *__restrict__ section_ID,
@@ -132,7 +133,7 @@ stiff_kernel(int e0, int e1, const int *__restrict__ elem_node_index, const int 
     }
     __syncwarp();
     double kb[ROUNDS][9];
-    element_stiffness_warp<FORM>(lane, S, D11, D12, D44, kb, !(probe & 2));
+    element_stiffness_warp<FORM, ICINV>(lane, S, D11, D12, D44, kb, !(probe & 2));
     if (probe & 1) {
       double sum = 0.0;
 #pragma unroll
@@ -176,6 +177,47 @@ stiff_kernel(int e0, int e1, const int *__restrict__ elem_node_index, const int 
     }
     __syncwarp();
   }
+}
+
+// Device self-test of the IC element: the condensed stiffness of a few distorted hexahedra through BOTH calInverse
+// implementations (one warp, one block).  out[0] = max |K_shuffle - K_smem|, out[1] = max |K_smem|.  The host
+// (api_assembly.inc: ic_inverse_mode) uses the register/shuffle kernel only if the two agree to rounding.
+__global__ void __launch_bounds__(32) ic_selftest_kernel(double *__restrict__ out) {
+  using namespace elem;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Scratch &S = *reinterpret_cast<Scratch *>(smem_raw);
+  const int lane = threadIdx.x & 31;
+  double D11, D12, D44;
+  elastic_constants(210000.0, 0.3, D11, D12, D44);
+  double maxdiff = 0.0, maxabs = 0.0;
+  for (int trial = 0; trial < 4; trial++) {
+    if (lane < 8) {
+      const double corner[3] = {(double)((lane ^ (lane >> 1)) & 1), (double)((lane >> 1) & 1), (double)((lane >> 2) & 1)};
+      for (int d = 0; d < 3; d++)   // unit cube (hex8n node order) with a deterministic distortion that grows with trial
+        S.xc[3 * lane + d] = corner[d] * (1.0 + 0.5 * d) + 0.07 * trial * sin(1.7 * (3 * lane + d) + 0.9 * trial);
+    }
+    __syncwarp();
+    double ka[2][9], kb[2][9];
+    element_stiffness_warp<FORM_IC, 0>(lane, S, D11, D12, D44, ka);
+    __syncwarp();
+    element_stiffness_warp<FORM_IC, 1>(lane, S, D11, D12, D44, kb);
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+#pragma unroll
+      for (int a = 0; a < 9; a++) {
+        const double d = fabs(ka[r][a] - kb[r][a]);
+        maxdiff = (d != d || maxdiff != maxdiff) ? d + maxdiff : fmax(maxdiff, d);   // NaN-propagating max
+        maxabs = fmax(maxabs, fabs(ka[r][a]));
+      }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double d = __shfl_xor_sync(0xffffffffu, maxdiff, o), m = __shfl_xor_sync(0xffffffffu, maxabs, o);
+    maxdiff = (d != d || maxdiff != maxdiff) ? d + maxdiff : fmax(maxdiff, d);
+    maxabs = fmax(maxabs, m);
+  }
+  if (lane == 0) { out[0] = maxdiff; out[1] = maxabs; }
 }
 
 // ---- geometrically nonlinear (total Lagrangian) assembly and update, SURVEY 8(f) rank 2 -----------

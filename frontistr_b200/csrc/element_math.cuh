@@ -59,6 +59,7 @@ struct alignas(16) Scratch {
   double Kda[24 * 10];      // IC: K(d, alpha), row stride 10 (16-byte aligned rows)
   double Kaa[9 * 9];        // IC: K(alpha, alpha) -> inverse, row-major [r][c]
   double W[24 * 10];        // IC: Kda * Kaa^-1, row stride 10
+  double piv[12];           // IC, shared-memory inverse only: IP(0..8), LR, PIVOT
 };
 
 FB_HD void hex_shape_deriv(double x, double y, double z, double (*d)[3]) {
@@ -326,6 +327,76 @@ FB_WARP_FN void ic_inverse_warp(int lane, Scratch &S) {
 }
 #endif
 
+// ---- the same calInverse(9) through shared memory (the first implementation, the one every hardware run of
+// round 1 used): the matrix stays in S.Kaa, lane 0 searches the pivot, lanes 0..8 own one column each, warp barriers
+// between the phases.  Kept as the arbiter of the register/shuffle version above: the library compares the two on
+// the device once per process (assembly.cuh: ic_selftest_kernel) and falls back to this one if they ever disagree.
+FB_HD void ic_inv_pivot(int lane, Scratch &S, int K) {
+  if (lane != 0) return;
+  double wmax = 0.0;
+  int LR = K;
+  for (int I = K; I < 9; I++) {
+    const double w = fabs(S.Kaa[I * 9 + K]);
+    if (w > wmax) { wmax = w; LR = I; }
+  }
+  S.piv[9] = (double)LR;
+  S.piv[10] = S.Kaa[LR * 9 + K];
+  if (LR != K) { const double t = S.piv[K]; S.piv[K] = S.piv[LR]; S.piv[LR] = t; }
+}
+FB_HD void ic_inv_swap(int lane, Scratch &S, int K) {
+  if (lane >= 9) return;
+  const int LR = (int)S.piv[9];
+  if (LR != K) { const double t = S.Kaa[K * 9 + lane]; S.Kaa[K * 9 + lane] = S.Kaa[LR * 9 + lane]; S.Kaa[LR * 9 + lane] = t; }
+}
+// lane c (<9) owns column c: scaling of row K, elimination; colK = A(:,K) after the swap, before this step
+FB_HD void ic_inv_step(int lane, Scratch &S, int K, const double *colK) {
+  if (lane >= 9) return;
+  const int c = lane;
+  const double PIVOT = S.piv[10];
+  if (c == K) {
+    for (int I = 0; I < 9; I++)
+      if (I != K) { const double W = colK[I]; if (W != 0.0) S.Kaa[I * 9 + K] = -W / PIVOT; }
+    S.Kaa[K * 9 + K] = 1.0 / PIVOT;
+  } else {
+    const double akc = S.Kaa[K * 9 + c] / PIVOT;
+    S.Kaa[K * 9 + c] = akc;
+    for (int I = 0; I < 9; I++)
+      if (I != K) { const double W = colK[I]; if (W != 0.0) S.Kaa[I * 9 + c] = S.Kaa[I * 9 + c] - W * akc; }
+  }
+}
+FB_HD void ic_inv_unpermute(int lane, Scratch &S) {
+  if (lane != 0) return;
+  int IP[9];
+  for (int I = 0; I < 9; I++) IP[I] = (int)S.piv[I];
+  for (int I = 0; I < 9; I++) {   // utilities.f90:301-314, quirks included
+    const int K = IP[I];
+    if (K != I) {
+      const int IW = IP[K]; IP[K] = IP[I]; IP[I] = IW;
+      for (int J = 0; J < 9; J++) { const double W = S.Kaa[J * 9 + I]; S.Kaa[J * 9 + I] = S.Kaa[J * 9 + K]; S.Kaa[J * 9 + K] = W; }
+    }
+  }
+}
+#ifdef FB_WARP_FN
+FB_WARP_FN void ic_inverse_smem_warp(int lane, Scratch &S) {
+  if (lane < 9) S.piv[lane] = (double)lane;
+  FB_SYNCWARP();
+  for (int K = 0; K < 9; K++) {
+    ic_inv_pivot(lane, S, K);
+    FB_SYNCWARP();
+    ic_inv_swap(lane, S, K);
+    FB_SYNCWARP();
+    double colK[9];
+#pragma unroll
+    for (int I = 0; I < 9; I++) colK[I] = S.Kaa[I * 9 + K];
+    FB_SYNCWARP();
+    ic_inv_step(lane, S, K, colK);
+    FB_SYNCWARP();
+  }
+  ic_inv_unpermute(lane, S);
+  FB_SYNCWARP();
+}
+#endif
+
 // W = Kda * Kaa^-1   (tmpk, static_LIB_3dIC.f90:212): 216 entries over 32 lanes
 FB_HD void ic_phase_W(int lane, Scratch &S) {
   for (int t = lane; t < 216; t += 32) {
@@ -356,7 +427,8 @@ FB_HD void ic_condense_block(const Scratch &S, int i, int j, double *k9) {
 // The whole element: executed by the 32 lanes of one warp after S.xc holds the element coordinates (and the
 // warp has synchronised).  On return lane `l` holds in kb[r] the 3x3 block t = 32 r + l (i = t / nn, j = t % nn)
 // of the element stiffness matrix.  This is the body of assembly.cuh:stiff_kernel AND of the host emulation.
-template <int FORM>
+// ICINV selects the calInverse implementation of the IC element: 1 = registers + shuffles, 0 = shared memory.
+template <int FORM, int ICINV = 1>
 FB_WARP_FN void element_stiffness_warp(int lane, Scratch &S, double D11, double D12, double D44,
                                        double (&kb)[((FORM == FORM_TET10 ? 100 : 64) + 31) / 32][9],
                                        bool condense = true) {
@@ -377,7 +449,8 @@ FB_WARP_FN void element_stiffness_warp(int lane, Scratch &S, double D11, double 
   if (FORM == FORM_IC && condense) {
     ic_phase_coupling(lane, S, D11, D12, D44);
     FB_SYNCWARP();
-    ic_inverse_warp(lane, S);
+    if (ICINV == 1) ic_inverse_warp(lane, S);
+    else ic_inverse_smem_warp(lane, S);
     FB_SYNCWARP();
     ic_phase_W(lane, S);
     FB_SYNCWARP();

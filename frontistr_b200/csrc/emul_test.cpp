@@ -50,7 +50,7 @@ static void emul_inverse_warp(Scratch &S) {
   fb::emulwarp::run_warp([&S](int lane) { ic_inverse_warp(lane, S); });
 }
 
-template <int FORM>
+template <int FORM, int ICINV = 1>
 static void run_element(const double *ecoord /* (nn,3) */, double E, double nu, double *K /* (3nn,3nn) row-major */) {
   constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
   constexpr int NB = NN * NN;
@@ -64,7 +64,7 @@ static void run_element(const double *ecoord /* (nn,3) */, double E, double nu, 
     for (int d = 0; d < 3; d++) S.xc[3 * lane + d] = ecoord[3 * lane + d];
   fb::emulwarp::run_warp([&](int lane) {
     double kb[ROUNDS][9];
-    element_stiffness_warp<FORM>(lane, S, D11, D12, D44, kb);
+    element_stiffness_warp<FORM, ICINV>(lane, S, D11, D12, D44, kb);
     for (int r = 0; r < ROUNDS; r++) {
       const int t = r * 32 + lane;
       if (t >= NB) continue;
@@ -150,6 +150,20 @@ int fbemul_element_stiffness(int form, const double *ecoord, double E, double nu
     case FORM_TET10: run_element<FORM_TET10>(ecoord, E, nu, K); return 0;
   }
   return -1;
+}
+
+// IC element through the shared-memory calInverse (the arbiter of the device self-test)
+int fbemul_element_stiffness_ic_smem(const double *ecoord, double E, double nu, double *K) {
+  run_element<FORM_IC, 0>(ecoord, E, nu, K);
+  return 0;
+}
+int fbemul_inverse9_smem(double *A /* row-major 9x9, in place */) {
+  Scratch S;
+  std::memset(&S, 0, sizeof S);
+  std::memcpy(S.Kaa, A, sizeof(double) * 81);
+  fb::emulwarp::run_warp([&S](int lane) { ic_inverse_smem_warp(lane, S); });
+  std::memcpy(A, S.Kaa, sizeof(double) * 81);
+  return 0;
 }
 
 // calInverse(9) through the column-parallel phases alone

@@ -23,6 +23,11 @@ def test_dry_run_solve_matches_oracle(meshname, precond, fused):
     G.test_solve_matches_oracle(ShadowBackend(), meshname, precond, fused)
 
 
+def test_dry_run_ic_inverse_variants():
+    G.test_ic_inverse_selftest_picks_a_kernel_that_matches_the_oracle(ShadowBackend())
+    G.test_ic_inverse_register_kernel_matches_the_oracle(ShadowBackend())
+
+
 def test_dry_run_mixed_types_and_sections():
     import test_gpu_z_unvalidated as Z
     Z.test_assembly_mixed_types_and_sections(ShadowBackend())

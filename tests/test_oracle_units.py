@@ -136,6 +136,50 @@ def test_ic_element_emulation_on_many_distorted_elements():
         assert np.abs(K0 - K1).max() <= 1e-14 * np.abs(K0).max(), trial
 
 
+def test_ic_shared_memory_inverse_equals_register_inverse_and_oracle():
+    """The two calInverse implementations of the IC kernel (element_math.cuh: ic_inverse_warp in registers + shuffles,
+    ic_inverse_smem_warp through shared memory — the one every hardware run of round 1 used and the arbiter of the
+    device self-test assembly.cuh:ic_selftest_kernel) in the lock-step emulation: both equal the oracle, on whole
+    IC elements and on pivoting-heavy 9x9 matrices, and they agree far inside the self-test's 1e-10 gate.  The last
+    block replays the self-test's own four elements (same formula as the kernel)."""
+    from oracle import oracle as orc
+    import __graft_entry__ as g
+    em = C.CDLL(g.build_emul())
+    dp = C.POINTER(C.c_double)
+    rng = np.random.default_rng(5)
+    base = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)
+    elems = []
+    for trial in range(20):
+        sc = rng.uniform(0.2, 3.0, 3)
+        elems.append(np.ascontiguousarray(base * sc + 0.22 * sc.min() * rng.standard_normal((8, 3))))
+    for trial in range(4):      # ic_selftest_kernel's elements
+        ec = np.zeros((8, 3))
+        for lane in range(8):
+            corner = [(lane ^ (lane >> 1)) & 1, (lane >> 1) & 1, (lane >> 2) & 1]
+            for d in range(3):
+                ec[lane, d] = corner[d] * (1.0 + 0.5 * d) + 0.07 * trial * np.sin(1.7 * (3 * lane + d) + 0.9 * trial)
+        elems.append(ec)
+    for k, ec in enumerate(elems):
+        K0 = orc.element_stiffness("IC", ec, 210000.0, 0.3)
+        K1 = np.zeros_like(K0); K2 = np.zeros_like(K0)
+        assert em.fbemul_element_stiffness(3, ec.ctypes.data_as(dp), C.c_double(210000.0), C.c_double(0.3), K1.ctypes.data_as(dp)) == 0
+        assert em.fbemul_element_stiffness_ic_smem(ec.ctypes.data_as(dp), C.c_double(210000.0), C.c_double(0.3), K2.ctypes.data_as(dp)) == 0
+        assert np.isfinite(K0).all() and np.abs(K0).max() > 0
+        assert np.abs(K0 - K2).max() <= 1e-14 * np.abs(K0).max(), k
+        assert np.abs(K1 - K2).max() <= 1e-13 * np.abs(K2).max(), k      # the device gate is 1e-10
+    for trial in range(12):
+        A = rng.standard_normal((9, 9))
+        if trial % 3 == 0:
+            A = A @ A.T + 9 * np.eye(9)
+        if trial % 3 == 1:
+            A = A * 0.05 + np.fliplr(np.eye(9)) * (2.0 + np.arange(9))
+        ref = np.asfortranarray(A.copy())
+        orc.lib().orc_calInverse(9, ref.ctypes.data_as(dp))
+        mine = np.ascontiguousarray(A.copy())
+        assert em.fbemul_inverse9_smem(mine.ctypes.data_as(dp)) == 0
+        assert np.abs(mine - ref).max() <= 1e-13 * np.abs(ref).max(), trial
+
+
 def test_tl_element_emulation_equals_oracle():
     """The total-Lagrangian element code of the CUDA kernels (element_math.cuh: element_stiffness_tl_warp /
     element_update_tl_warp, run in lock step on the host) against the oracle's restatement of STF_C3 / STF_C3D8Bbar /
