@@ -1858,3 +1858,283 @@ int orc_nlgeom_static(const orc_mesh *mesh, const orc_section *sections, orc_mat
   free(dunode); free(GL); free(QF); free(gstrain); free(gstress);
   return rc;
 }
+
+/* =============================================================================================
+ * Strain / stress recovery of the linear static analysis: fstr_UpdateNewton with nlgeom_flag == INFINITE
+ * (analysis/static/fstr_Update.f90:25-293 -> UPDATE_C3 static_LIB_3d.f90:516-837, Update_C3D8Bbar
+ * static_LIB_C3D8.f90:203-552, UpdateST_C3D8IC static_LIB_3dIC.f90:220-455) and fstr_NodalStress3D
+ * (analysis/static/fstr_NodalStress.f90:13-272).  SURVEY 8(f) rank 2.  This is what produces the E11..E13,
+ * S11..S13 and SMS lines of the reference's golden logs, so every such line pins the restatement (and through it
+ * the displacement field far more sharply than the U1..U3 extrema do).
+ * Isotropic elastic material, optional thermal strain with a constant expansion coefficient (TT == NULL: none).
+ * ecoord / u: (3,nn) column-major; strain / stress: [gp][6] (xx yy zz xy yz zx, engineering shear).
+ * ============================================================================================= */
+static void shapefunc_any(int etype, const double nc[3], double *H) {
+  if (etype == 361) shapefunc_hex8n(nc, H); else shapefunc_tet10n(nc, H);
+}
+
+/* UPDATE_C3 (bbar == 0) / Update_C3D8Bbar (bbar != 0), flag == INFINITE; utot = unode + dunode */
+void orc_UPDATE_C3_lin(int etype, int nn, const double *ecoord, const double *utot, double E, double nu, int bbar,
+                       const double *TT, const double *T0, double alp, double ref_temp, double *qf, double *strain,
+                       double *stress) {
+  double D[6][6], B[6 * 30], gderiv[20][3], Bbar[20][3], gdd[3][3], H[20], det, wg, nc[3] = {0, 0, 0};
+  const int m = 3 * nn;
+  double vol0 = 0.0;
+  memset(qf, 0, sizeof(double) * m);
+  if (bbar) { /* dilatation at centroid, static_LIB_C3D8.f90:270-274 */
+    double dd[3][3];
+    get_global_deriv(etype, nn, nc, ecoord, &det, Bbar);
+    disp_gradient(nn, utot, Bbar, dd);
+    vol0 = (dd[0][0] + dd[1][1] + dd[2][2]) / 3.0;
+  }
+  for (int LX = 1; LX <= num_quad_points(etype); LX++) {
+    get_quad_point(etype, LX, nc);
+    get_global_deriv(etype, nn, nc, ecoord, &det, gderiv);
+    double EPSTH[6] = {0, 0, 0, 0, 0, 0};
+    if (TT) { /* static_LIB_3d.f90:597-633 */
+      shapefunc_any(etype, nc, H);
+      double ttc = 0.0, tt0 = 0.0;
+      for (int n = 0; n < nn; n++) { ttc += TT[n] * H[n]; tt0 += T0[n] * H[n]; }
+      EPSTH[0] = EPSTH[1] = EPSTH[2] = alp * (ttc - ref_temp) - alp * (tt0 - ref_temp);
+    }
+    cal_elastic_matrix(E, nu, D);
+    disp_gradient(nn, utot, gderiv, gdd);
+    const double dvol = bbar ? vol0 - (gdd[0][0] + gdd[1][1] + gdd[2][2]) / 3.0 : 0.0;
+    double ds[6]; /* small strain, :641-648 */
+    ds[0] = gdd[0][0] + dvol; ds[1] = gdd[1][1] + dvol; ds[2] = gdd[2][2] + dvol;
+    ds[3] = gdd[0][1] + gdd[1][0]; ds[4] = gdd[1][2] + gdd[2][1]; ds[5] = gdd[2][0] + gdd[0][2];
+    for (int i = 0; i < 6; i++) ds[i] = ds[i] - EPSTH[i];
+    double *eo = strain + 6 * (LX - 1), *so = stress + 6 * (LX - 1);
+    for (int i = 0; i < 6; i++) { /* :650-653 */
+      double s = 0.0;
+      for (int k = 0; k < 6; k++) s += D[i][k] * ds[k];
+      eo[i] = ds[i] + EPSTH[i];
+      so[i] = s;
+    }
+    fill_B_TL(nn, gderiv, bbar ? Bbar : NULL, gdd, 0, B);
+    wg = get_weight(etype, LX) * det;
+    for (int j = 0; j < m; j++) {
+      double s = 0.0;
+      for (int k = 0; k < 6; k++) s += so[k] * B[j * 6 + k];
+      qf[j] += s * wg;
+    }
+  }
+}
+
+/* UpdateST_C3D8IC, static_LIB_3dIC.f90:220-455; edisp = unode + dunode (fstr_Update.f90:162) */
+void orc_UpdateST_C3D8IC(int nn, const double *ecoord, const double *edisp, double E, double nu, const double *TT,
+                         const double *T0, double alp, double ref_temp, double *qf, double *strain, double *stress) {
+  const int etype = 361, mt = 33, m = 24;
+  double D[6][6], B[6 * 33], gderiv[11][3], H[8], xj[81], jacobian[3][3], inverse[3][3], deriv[8][3];
+  double stiff[33 * 33], tmpforce[9], cdisp[33], vect[24], det, det0, nc[3] = {0, 0, 0};
+#define TS(i, j) stiff[((j)-1) * mt + ((i)-1)]
+  shapederiv_hex8n(nc, deriv);
+  jacobian3(nn, ecoord, deriv, jacobian, &det0, inverse);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) inverse[i][j] = inverse[i][j] * det0;
+  memset(stiff, 0, sizeof(stiff));
+  for (int IC = 1; IC <= 8; IC++) { /* :279-328 */
+    get_quad_point(etype, IC, nc);
+    get_global_deriv(etype, nn, nc, ecoord, &det, gderiv);
+    cal_elastic_matrix(E, nu, D);
+    for (int j = 0; j < 3; j++) {
+      gderiv[nn + 0][j] = -2.0 * nc[0] * inverse[0][j] / det;
+      gderiv[nn + 1][j] = -2.0 * nc[1] * inverse[1][j] / det;
+      gderiv[nn + 2][j] = -2.0 * nc[2] * inverse[2][j] / det;
+    }
+    const double wg = get_weight(etype, IC) * det;
+    fill_B(nn + 3, gderiv, B);
+    add_BtDB(mt, B, D, wg, stiff, mt);
+  }
+  for (int j = 1; j <= 9; j++)
+    for (int i = 1; i <= 9; i++) xj[(j - 1) * 9 + (i - 1)] = TS(m + i, m + j);
+  orc_calInverse(9, xj);
+  for (int i = 1; i <= 9; i++) { /* tmpforce = Kad * edisp, :332 */
+    double s = 0.0;
+    for (int k = 1; k <= m; k++) s += TS(m + i, k) * edisp[k - 1];
+    tmpforce[i - 1] = s;
+  }
+  for (int k = 0; k < m; k++) cdisp[k] = edisp[k];
+  for (int i = 0; i < 9; i++) { /* cdisp(25:33) = -xj * tmpforce, :335 */
+    double s = 0.0;
+    for (int k = 0; k < 9; k++) s += xj[k * 9 + i] * tmpforce[k];
+    cdisp[m + i] = -s;
+  }
+  if (qf) { /* :337-343 */
+    for (int i = 1; i <= m; i++) {
+      double s = 0.0;
+      for (int k = 1; k <= mt; k++) s += TS(i, k) * cdisp[k - 1];
+      qf[i - 1] = s;
+    }
+    if (TT) {
+      orc_TLOAD_C3D8IC(nn, ecoord, TT, T0, E, nu, alp, ref_temp, vect);
+      for (int i = 0; i < m; i++) qf[i] -= vect[i];
+    }
+  }
+  for (int IC = 1; IC <= 8; IC++) { /* strain and stress, :346-452 */
+    get_quad_point(etype, IC, nc);
+    shapefunc_hex8n(nc, H);
+    get_global_deriv(etype, nn, nc, ecoord, &det, gderiv);
+    for (int j = 0; j < 3; j++) {
+      gderiv[nn + 0][j] = -2.0 * nc[0] * inverse[0][j] / det;
+      gderiv[nn + 1][j] = -2.0 * nc[1] * inverse[1][j] / det;
+      gderiv[nn + 2][j] = -2.0 * nc[2] * inverse[2][j] / det;
+    }
+    fill_B(nn + 3, gderiv, B);
+    double EPSTH[6] = {0, 0, 0, 0, 0, 0};
+    if (TT) {
+      double TEMPC = 0.0, TEMP0 = 0.0;
+      for (int n = 0; n < nn; n++) { TEMPC += H[n] * TT[n]; TEMP0 += H[n] * T0[n]; }
+      EPSTH[0] = EPSTH[1] = EPSTH[2] = alp * (TEMPC - ref_temp) - alp * (TEMP0 - ref_temp);
+    }
+    cal_elastic_matrix(E, nu, D);
+    double EPSA[6];
+    for (int i = 0; i < 6; i++) {
+      double s = 0.0;
+      for (int k = 0; k < mt; k++) s += B[k * 6 + i] * cdisp[k];
+      EPSA[i] = s;
+    }
+    for (int j = 0; j < 6; j++) {
+      double s = 0.0;
+      for (int k = 0; k < 6; k++) s = s + D[j][k] * (EPSA[k] - EPSTH[k]);
+      stress[6 * (IC - 1) + j] = s;
+      strain[6 * (IC - 1) + j] = EPSA[j];
+    }
+  }
+#undef TS
+}
+
+/* element loop of fstr_UpdateNewton for a linear static step (fstr_Update.f90:60-293): utot = unode + dunode
+ * (3*n_node); TT / T0 nodal temperatures or NULL; gp_strain / gp_stress [n_elem][8][6] (4 points used by 342);
+ * QFORCE(3*n_node) or NULL.  Returns -2 for an unsupported element type. */
+int orc_update_linear(const orc_mesh *mesh, const orc_section *sections, const double *utot, const double *TT,
+                      const double *T0, double alp, double ref_temp, double *gp_strain, double *gp_stress,
+                      double *QFORCE) {
+  if (QFORCE) memset(QFORCE, 0, sizeof(double) * 3 * (size_t)mesh->n_node);
+  for (int itype = 1; itype <= mesh->n_elem_type; itype++) {
+    const int is = mesh->elem_type_index[itype - 1] + 1, iE = mesh->elem_type_index[itype];
+    const int ic_type = mesh->elem_type_item[itype - 1];
+    if (ic_type != 361 && ic_type != 342) return -2;
+    const int nn = etype_max_node(ic_type);
+    for (int icel = is; icel <= iE; icel++) {
+      double ecoord[30], u[30], tt[10], t0[10], qf[30];
+      int nod[10];
+      const int iiS = mesh->elem_node_index[icel - 1];
+      for (int j = 0; j < nn; j++) {
+        nod[j] = mesh->elem_node_item[iiS + j];
+        for (int i = 0; i < 3; i++) {
+          ecoord[3 * j + i] = mesh->node[3 * (size_t)(nod[j] - 1) + i];
+          u[3 * j + i] = utot[3 * (size_t)(nod[j] - 1) + i];
+        }
+        if (TT) { tt[j] = TT[nod[j] - 1]; t0[j] = T0[nod[j] - 1]; }
+      }
+      const orc_section *sec = &sections[(mesh->section_ID ? mesh->section_ID[icel - 1] : 1) - 1];
+      double *e = gp_strain + 48 * (size_t)(icel - 1), *s = gp_stress + 48 * (size_t)(icel - 1);
+      if (ic_type == 361 && sec->elemopt361 == 3)
+        orc_UpdateST_C3D8IC(nn, ecoord, u, sec->E, sec->nu, TT ? tt : NULL, TT ? t0 : NULL, alp, ref_temp, qf, e, s);
+      else
+        orc_UPDATE_C3_lin(ic_type, nn, ecoord, u, sec->E, sec->nu, ic_type == 361 && sec->elemopt361 == 2,
+                          TT ? tt : NULL, TT ? t0 : NULL, alp, ref_temp, qf, e, s);
+      if (QFORCE)
+        for (int j = 0; j < nn; j++)
+          for (int i = 0; i < 3; i++) QFORCE[3 * (size_t)(nod[j] - 1) + i] += qf[3 * j + i];
+    }
+  }
+  return 0;
+}
+
+/* inverse_func, fstr_NodalStress.f90:714-748: Gauss-Jordan without pivoting; a (n x n, row-major [i][j]) is destroyed */
+static void inverse_func(int n, double *a, double *inv_a, int ld) {
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) inv_a[i * ld + j] = (i == j) ? 1.0 : 0.0;
+  for (int i = 0; i < n; i++) {
+    double buf = 1.0 / a[i * ld + i];
+    for (int j = 0; j < n; j++) { a[i * ld + j] = a[i * ld + j] * buf; inv_a[i * ld + j] = inv_a[i * ld + j] * buf; }
+    for (int j = 0; j < n; j++)
+      if (i != j) {
+        buf = a[j * ld + i];
+        for (int k = 0; k < n; k++) {
+          a[j * ld + k] = a[j * ld + k] - a[i * ld + k] * buf;
+          inv_a[j * ld + k] = inv_a[j * ld + k] - inv_a[i * ld + k] * buf;
+        }
+      }
+  }
+}
+
+/* get_mises, fstr_NodalStress.f90:483-500 */
+double orc_get_mises(const double *s) {
+  const double ps = (s[0] + s[1] + s[2]) / 3.0;
+  const double sm = 0.5 * ((s[0] - ps) * (s[0] - ps) + (s[1] - ps) * (s[1] - ps) + (s[2] - ps) * (s[2] - ps)) +
+                    s[3] * s[3] + s[4] * s[4] + s[5] * s[5];
+  return sqrt(3.0 * sm);
+}
+
+/* extrapolation matrix of fstr_NodalStress3D (:64-81): inverse of the shape functions (hex8n; tet4n for 342)
+ * evaluated at the Gauss points.  inv[ni*ni] row-major; returns ni. */
+int orc_nodal_extrapolation(int etype, double *inv) {
+  const int ni = num_quad_points(etype);
+  double func[64], nc[3], H[10];
+  for (int i = 0; i < ni; i++) {
+    get_quad_point(etype, i + 1, nc);
+    if (etype == 361) shapefunc_hex8n(nc, H);
+    else { H[1] = nc[0]; H[2] = nc[1]; H[3] = nc[2]; H[0] = 1.0 - nc[0] - nc[1] - nc[2]; } /* ShapeFunc_tet4n, tet4n.f90:11-16 */
+    for (int j = 0; j < ni; j++) func[i * ni + j] = H[j];
+  }
+  inverse_func(ni, func, inv, ni);
+  return ni;
+}
+
+/* fstr_NodalStress3D for element types 361 / 342 (NodalStress_INV3 :337-400, ElementStress_C3 static_LIB_3d.f90:881-913):
+ * STRAIN / STRESS (6*n_node), MISES (n_node), ESTRAIN / ESTRESS (6*n_elem), EMISES (n_elem). */
+int orc_nodal_stress_3d(const orc_mesh *mesh, const double *gp_strain, const double *gp_stress, double *STRAIN,
+                        double *STRESS, double *MISES, double *ESTRAIN, double *ESTRESS, double *EMISES) {
+  const size_t nnode = (size_t)mesh->n_node, nelem = (size_t)mesh->n_elem;
+  int *nnumber = (int *)calloc(nnode ? nnode : 1, sizeof(int));
+  memset(STRAIN, 0, sizeof(double) * 6 * nnode); memset(STRESS, 0, sizeof(double) * 6 * nnode);
+  memset(ESTRAIN, 0, sizeof(double) * 6 * nelem); memset(ESTRESS, 0, sizeof(double) * 6 * nelem);
+  static const int mid[6][2] = {{1, 2}, {2, 3}, {3, 1}, {1, 4}, {2, 4}, {3, 4}}; /* nodes 5..10 of tet10n, :361-378 */
+  for (int itype = 1; itype <= mesh->n_elem_type; itype++) {
+    const int is = mesh->elem_type_index[itype - 1] + 1, iE = mesh->elem_type_index[itype];
+    const int ic_type = mesh->elem_type_item[itype - 1];
+    if (ic_type != 361 && ic_type != 342) { free(nnumber); return -2; }
+    const int nn = etype_max_node(ic_type);
+    double inv[64];
+    const int ni = orc_nodal_extrapolation(ic_type, inv);
+    for (int icel = is; icel <= iE; icel++) {
+      const double *ge = gp_strain + 48 * (size_t)(icel - 1), *gs = gp_stress + 48 * (size_t)(icel - 1);
+      double nde[10][6], nds[10][6], ee[6], es[6];
+      memset(nde, 0, sizeof nde); memset(nds, 0, sizeof nds);
+      for (int i = 0; i < ni; i++)
+        for (int j = 0; j < ni; j++)
+          for (int k = 0; k < 6; k++) {
+            nde[i][k] = nde[i][k] + inv[i * ni + j] * ge[6 * j + k];
+            nds[i][k] = nds[i][k] + inv[i * ni + j] * gs[6 * j + k];
+          }
+      if (ic_type == 342)
+        for (int q = 0; q < 6; q++)
+          for (int k = 0; k < 6; k++) {
+            nde[4 + q][k] = (nde[mid[q][0] - 1][k] + nde[mid[q][1] - 1][k]) / 2.0;
+            nds[4 + q][k] = (nds[mid[q][0] - 1][k] + nds[mid[q][1] - 1][k]) / 2.0;
+          }
+      for (int k = 0; k < 6; k++) { ee[k] = 0.0; es[k] = 0.0; }
+      for (int i = 0; i < ni; i++)
+        for (int k = 0; k < 6; k++) { ee[k] = ee[k] + ge[6 * i + k]; es[k] = es[k] + gs[6 * i + k]; }
+      for (int k = 0; k < 6; k++) { ee[k] = ee[k] / ni; es[k] = es[k] / ni; }
+      const int jS = mesh->elem_node_index[icel - 1];
+      for (int j = 0; j < nn; j++) {
+        const size_t ic = (size_t)mesh->elem_node_item[jS + j] - 1;
+        for (int k = 0; k < 6; k++) { STRAIN[6 * ic + k] += nde[j][k]; STRESS[6 * ic + k] += nds[j][k]; }
+        nnumber[ic]++;
+      }
+      for (int k = 0; k < 6; k++) { ESTRAIN[6 * (size_t)(icel - 1) + k] += ee[k]; ESTRESS[6 * (size_t)(icel - 1) + k] += es[k]; }
+    }
+  }
+  for (size_t i = 0; i < nnode; i++) {
+    if (nnumber[i] == 0) continue;
+    for (int k = 0; k < 6; k++) { STRAIN[6 * i + k] = STRAIN[6 * i + k] / nnumber[i]; STRESS[6 * i + k] = STRESS[6 * i + k] / nnumber[i]; }
+  }
+  for (size_t i = 0; i < nnode; i++) MISES[i] = orc_get_mises(STRESS + 6 * i);
+  for (size_t i = 0; i < nelem; i++) EMISES[i] = orc_get_mises(ESTRESS + 6 * i);
+  free(nnumber);
+  return 0;
+}

@@ -137,6 +137,23 @@ int orc_nlgeom_static(const orc_mesh *mesh, const orc_section *sections, orc_mat
                       const double *sp_val, int substeps, double converg, int max_iter,
                       double *unode, double *unode_steps, int *newton_iters, int *cg_iters_total);
 
+/* ---- strain / stress recovery of the linear static analysis: fstr_UpdateNewton with
+ * nlgeom_flag == INFINITE and fstr_NodalStress3D; pinned on the E / S / SMS lines (nodal and elemental) of every
+ * golden log of examples/static/ex{A..G}.  strain / stress: [gp][6]; gp_* : [n_elem][8][6]. */
+void orc_UPDATE_C3_lin(int etype, int nn, const double *ecoord, const double *utot, double E, double nu, int bbar,
+                       const double *TT, const double *T0, double alp, double ref_temp, double *qf, double *strain,
+                       double *stress);
+void orc_UpdateST_C3D8IC(int nn, const double *ecoord, const double *edisp, double E, double nu, const double *TT,
+                         const double *T0, double alp, double ref_temp, double *qf, double *strain, double *stress);
+int orc_update_linear(const orc_mesh *mesh, const orc_section *sections, const double *utot, const double *TT,
+                      const double *T0, double alp, double ref_temp, double *gp_strain, double *gp_stress,
+                      double *QFORCE);
+int orc_nodal_extrapolation(int etype, double *inv);
+double orc_get_mises(const double *s);
+int orc_nodal_stress_3d(const orc_mesh *mesh, const double *gp_strain, const double *gp_stress, double *STRAIN,
+                        double *STRESS, double *MISES, double *ESTRAIN, double *ESTRESS, double *EMISES);
+
+
 #ifdef __cplusplus
 }
 #endif

@@ -295,3 +295,54 @@ def set_num_threads(n: int):
 
 def num_threads() -> int:
     return lib().orc_num_threads()
+
+
+# ---- strain / stress recovery of the linear static analysis (fstr_UpdateNewton INFINITE + fstr_NodalStress3D) -------
+def update_linear(mesh, utot, TT=None, T0=None, alpha=0.0, reftemp=0.0):
+    """Gauss-point strain / stress [n_elem][8][6] and QFORCE(3*n_node) at utot = unode + dunode."""
+    L = lib()
+    cm, sec = c_mesh(mesh), c_sections(mesh)
+    u = np.ascontiguousarray(utot, np.float64)
+    e = np.zeros((mesh.n_elem, 8, 6)); s = np.zeros((mesh.n_elem, 8, 6)); q = np.zeros(3 * mesh.n_node)
+    tt = np.ascontiguousarray(TT, np.float64) if TT is not None else None
+    t0 = np.ascontiguousarray(T0, np.float64) if T0 is not None else None
+    L.orc_update_linear.argtypes = [C.POINTER(orc_mesh), C.POINTER(orc_section), c_dbl_p, c_dbl_p, c_dbl_p, C.c_double,
+                                    C.c_double, c_dbl_p, c_dbl_p, c_dbl_p]
+    rc = L.orc_update_linear(C.byref(cm.s), sec, _dp(u), _dp(tt), _dp(t0), float(alpha), float(reftemp), _dp(e), _dp(s), _dp(q))
+    assert rc == 0, rc
+    return e, s, q
+
+
+def nodal_stress_3d(mesh, gp_strain, gp_stress):
+    """fstr_NodalStress3D -> dict(STRAIN (n_node,6), STRESS, MISES, ESTRAIN (n_elem,6), ESTRESS, EMISES)."""
+    L = lib()
+    cm = c_mesh(mesh)
+    ge = np.ascontiguousarray(gp_strain, np.float64); gs = np.ascontiguousarray(gp_stress, np.float64)
+    out = dict(STRAIN=np.zeros((mesh.n_node, 6)), STRESS=np.zeros((mesh.n_node, 6)), MISES=np.zeros(mesh.n_node),
+               ESTRAIN=np.zeros((mesh.n_elem, 6)), ESTRESS=np.zeros((mesh.n_elem, 6)), EMISES=np.zeros(mesh.n_elem))
+    L.orc_nodal_stress_3d.argtypes = [C.POINTER(orc_mesh)] + [c_dbl_p] * 8
+    rc = L.orc_nodal_stress_3d(C.byref(cm.s), _dp(ge), _dp(gs), *[_dp(out[k]) for k in
+                                                                  ("STRAIN", "STRESS", "MISES", "ESTRAIN", "ESTRESS", "EMISES")])
+    assert rc == 0, rc
+    return out
+
+
+def element_update_linear(kind, ecoord, u, E, nu, etype=361, TT=None, T0=None, alpha=0.0, reftemp=0.0):
+    """One element: kind 'IC' / 'FI' / 'BBAR' / 'C3' -> (strain [ngp][6], stress [ngp][6], qf [3 nn])."""
+    L = lib()
+    ec = np.ascontiguousarray(ecoord, np.float64); uu = np.ascontiguousarray(u, np.float64)
+    nn = ec.shape[0]
+    ngp = 8 if etype == 361 else 4
+    e = np.zeros((ngp, 6)); s = np.zeros((ngp, 6)); q = np.zeros(3 * nn)
+    tt = np.ascontiguousarray(TT, np.float64) if TT is not None else None
+    t0 = np.ascontiguousarray(T0, np.float64) if T0 is not None else None
+    if kind == "IC":
+        L.orc_UpdateST_C3D8IC.argtypes = [C.c_int, c_dbl_p, c_dbl_p, C.c_double, C.c_double, c_dbl_p, c_dbl_p, C.c_double,
+                                          C.c_double, c_dbl_p, c_dbl_p, c_dbl_p]
+        L.orc_UpdateST_C3D8IC(nn, _dp(ec), _dp(uu), E, nu, _dp(tt), _dp(t0), alpha, reftemp, _dp(q), _dp(e), _dp(s))
+    else:
+        L.orc_UPDATE_C3_lin.argtypes = [C.c_int, C.c_int, c_dbl_p, c_dbl_p, C.c_double, C.c_double, C.c_int, c_dbl_p, c_dbl_p,
+                                        C.c_double, C.c_double, c_dbl_p, c_dbl_p, c_dbl_p]
+        L.orc_UPDATE_C3_lin(etype, nn, _dp(ec), _dp(uu), E, nu, int(kind == "BBAR"), _dp(tt), _dp(t0), alpha, reftemp,
+                            _dp(q), _dp(e), _dp(s))
+    return e, s, q

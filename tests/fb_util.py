@@ -37,6 +37,60 @@ def load_golden_mesh(name, elemopt361=kel361IC):
     return m, cnt, meta
 
 
+def oracle_solve_deck(name):
+    """Any linear golden deck (exA-exG: CLOAD, face pressure, volume loads, thermal load) through the ORACLE:
+    K, load vector, Dirichlet elimination, CG.  Returns mesh, the solved matrix (X = displacement), meta and the
+    temperature fields (TT, T0, alpha, reftemp) or None."""
+    from oracle import oracle as orc
+    from frontistr_b200 import hecmw
+    mesh, cnt, meta = load_golden_mesh(name)
+    A = orc.mat_con(mesh)
+    orc.stiffmatrix(mesh, A)
+    thermal = None
+    if "thermal" in meta:
+        th = meta["thermal"]
+        thermal = (np.full(mesh.n_node, th["temperature"]), np.full(mesh.n_node, th["initial"]), th["alpha"], th["reftemp"])
+        orc.ass_thermal_load(mesh, A, *thermal)
+    elif "pressure" in meta:
+        pr = meta["pressure"]
+        orc.ass_dload_pressure(mesh, A, pr["elems"], pr["face"], pr["value"])
+    elif "dload" in meta:
+        orc.ass_dload_volume(mesh, A, meta["dload"]["ltype"], meta["dload"]["params"], meta["rho"])
+    else:
+        hecmw.fstr_ass_load_cload(mesh, A, cnt["cload"])
+    n, d, v = hecmw.boundary_dofs(mesh, cnt["boundary"])
+    for i in range(len(n)):
+        orc.mat_ass_bc(A, int(n[i]), int(d[i]), float(v[i]))
+    apply_solver_card(A, cnt["solver"])
+    A.Iarray[20] = 0; A.Iarray[21] = 0
+    orc.precond_clear()
+    r = orc.solve(mesh, A)
+    orc.precond_clear()
+    assert r["error"] == 0 and A.Iarray[80] == 1
+    return mesh, A, meta, thermal
+
+
+STRESS_KEYS = ("11", "22", "33", "12", "23", "13")
+
+
+def check_golden_stress(out, meta, digits_rel=1.0e-4):
+    """The 26 strain / stress / Mises max/min lines of a golden log (nodal + elemental) against the dict returned by
+    (oracle or product) fstr_NodalStress3D: the harness tolerance 1e-4 absolute AND the 5 printed digits."""
+    g = meta["golden_stress"]
+    worst = 0.0
+    for where, E, S, M in (("node", "STRAIN", "STRESS", "MISES"), ("elem", "ESTRAIN", "ESTRESS", "EMISES")):
+        for k, key in enumerate(STRESS_KEYS):
+            for arr, tag in ((out[E][:, k], "E" + key), (out[S][:, k], "S" + key)):
+                for got, want in ((arr.max(), g[where][tag][0]), (arr.min(), g[where][tag][1])):
+                    assert abs(got - want) <= meta["tolerance_abs"] + digits_rel * abs(want), (where, tag, got, want)
+                    if abs(want) > 1.0e-6:
+                        worst = max(worst, abs(got - want) / abs(want))
+        for got, want in ((out[M].max(), g[where]["SMS"][0]), (out[M].min(), g[where]["SMS"][1])):
+            # (exF has stress-free nodes: min SMS ~ 1e-8 is the CG tolerance, not a digit to match)
+            assert abs(got - want) <= digits_rel * abs(want) + 1e-6, (where, "SMS", got, want)
+    return worst
+
+
 def load_dist_fixture(name, rank):
     d = np.load(os.path.join(GOLDEN, "%s_%d.npz" % (name, rank)))
     m = hecmwST_local_mesh()

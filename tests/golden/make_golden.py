@@ -91,6 +91,27 @@ def parse_log(path, which=1):
     return out
 
 
+def parse_log_stress(path, which=1):
+    """The strain / stress / Mises max/min lines of the `which`-th '##### Global Summary' block: nodal values
+    (fstrSOLID%STRAIN/STRESS/MISES) and, after '##### @Element', elemental ones (ESTRAIN/ESTRESS/EMISES) — the
+    output of fstr_UpdateNewton + fstr_NodalStress3D, compared by the reference's harness like U1-U3."""
+    with open(path) as f:
+        txt = f.read()
+    blk = txt.split("##### Global Summary")[which]
+    out = {"node": {}, "elem": {}}
+    where = "node"
+    for line in blk.splitlines()[1:]:
+        if line.strip().startswith("##### @Element"):
+            where = "elem"
+            continue
+        m = re.match(r"\s*//([ES]\d\d|SMS)\s+(\S+)\s+(\S+)\s*$", line)
+        if m:
+            out[where][m.group(1)] = [float(m.group(2)), float(m.group(3))]
+        elif line.strip().startswith("####") or line.strip().startswith("#####"):
+            break
+    return out
+
+
 def main():
     meta = {}
     for name, msh, cnt, log in DECKS:
@@ -212,6 +233,12 @@ def main():
                             elem_node_item=d.elem_node_item, neighbor_pe=d.neighbor_pe,
                             import_index=d.import_index, import_item=d.import_item,
                             export_index=d.export_index, export_item=d.export_item, my_rank=d.my_rank, PETOT=d.PETOT)
+    # strain / stress / Mises lines of the linear decks (exA-exG)
+    for name, d in meta.items():
+        log = d["source"].get("log")
+        if log and "nlgeom" not in d:
+            d["golden_stress"] = parse_log_stress(os.path.join(REF, log))
+            assert len(d["golden_stress"]["node"]) == 13 and len(d["golden_stress"]["elem"]) == 13, name
     with open(os.path.join(OUT, "golden.json"), "w") as f:
         json.dump(meta, f, indent=1)
     print("wrote", sorted(os.listdir(OUT)))

@@ -316,3 +316,21 @@ def test_patch_test_every_element_formulation(form):
     U = A.X.reshape(-1, 3)
     assert len(bnd) < mesh.n_node
     assert np.abs(U - uex).max() <= 1e-9 * np.abs(uex).max()
+
+
+LINEAR_DECKS = ["A361", "A342", "B361", "B342", "C361", "C342", "D361", "D342", "E361", "E342", "F361", "F342", "G361", "G342"]
+
+
+@pytest.mark.parametrize("name", LINEAR_DECKS)
+def test_oracle_strain_stress_mises_match_reference_log(name):
+    """fstr_UpdateNewton (INFINITE: UpdateST_C3D8IC for the default 361 IC element, UPDATE_C3 for 342) +
+    fstr_NodalStress3D restated in the oracle, on the displacement the oracle's own K / load / BC / CG path
+    produced: ALL 26 strain / stress / von-Mises max/min lines (nodal and elemental) of every linear golden log
+    of examples/static/ex{A..G}, to the 5 printed digits.  Strains are derivatives of u, so this pins the
+    displacement FIELD (not only its extrema) and, for exF, the thermal strain handling."""
+    from oracle import oracle as orc
+    mesh, A, meta, thermal = util.oracle_solve_deck(name)
+    TT, T0, alp, ref = thermal if thermal else (None, None, 0.0, 0.0)
+    e, s, q = orc.update_linear(mesh, A.X, TT, T0, alp, ref)
+    out = orc.nodal_stress_3d(mesh, e, s)
+    util.check_golden_stress(out, meta)
