@@ -8,7 +8,11 @@
 // element and every call (hecmw_mat_ass.f90:81-121) depends on topology only: it is done once per
 // structure into slot[e*nn*nn + i*nn + j].
 #pragma once
+#ifdef FB_EMUL_KERNELS
+#include "kernel_emul.hpp"   // TEST-ONLY host stand-in (libfistr_b200_emul.so); the warp-cooperative kernels are left out
+#else
 #include "common.cuh"
+#endif
 #include "element_math.cuh"
 
 namespace fb {
@@ -103,6 +107,7 @@ gather_sum_kernel(size_t nblk, const unsigned *__restrict__ gptr, const unsigned
   }
 }
 
+#ifndef FB_EMUL_KERNELS   // warp-cooperative kernels (shuffles, shared memory): device only
 // One element per warp.  sect[3*s..] = D11, D12, D44 of section s; sect_form[s] = elemopt361.
 // ICINV (IC element only): calInverse in registers + shuffles (1) or through shared memory (0), see element_math.cuh.
 template <int FORM, int WARPS, int ICINV = 1>
@@ -317,6 +322,154 @@ update_tl_kernel(int e0, int e1, const int *__restrict__ elem_node_index, const 
     if (lane < 3 * NN) atomicAdd(qforce + 3 * (size_t)(conn[lane / 3] - 1) + lane % 3, q);
     __syncwarp();
   }
+}
+
+// ---- linear strain / stress recovery: fstr_UpdateNewton (nlgeom_flag == INFINITE) + fstr_NodalStress3D ------------
+// (fstr_Update.f90:25-293, fstr_NodalStress.f90:13-272), SURVEY 8(f) rank 2.  One element per warp.  The element's
+// internal force goes to eqf[3*p + c] with p the element's position in elem_node_item (NOT added to the nodes here):
+// the nodes gather their contributions afterwards in ascending element order through the node incidence (below),
+// which is the reference's own 1-thread summation order and needs no atomics.
+// sectA[s] = thermal expansion coefficient of section s; temp / temp0 == nullptr: no !TEMPERATURE.
+template <int FORM, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+update_lin_kernel(int e0, int e1, const int *__restrict__ elem_node_index, const int *__restrict__ elem_node_item,
+                  const double *__restrict__ node, const double *__restrict__ utot, const int *__restrict__ section_ID,
+                  const double *__restrict__ sectD, const double *__restrict__ sectA, const int *__restrict__ sect_form,
+                  const double *__restrict__ temp, const double *__restrict__ temp0, double ref_temp,
+                  double *__restrict__ gp_strain, double *__restrict__ gp_stress, double *__restrict__ eqf) {
+  using namespace elem;
+  constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ScratchTL &S = reinterpret_cast<ScratchTL *>(smem_raw)[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const int wg = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  const int nw = gridDim.x * WARPS;
+  const bool has_temp = temp != nullptr;
+  for (int e = e0 + wg; e < e1; e += nw) {
+    const int sec = section_ID[e] - 1;
+    if (FORM != FORM_TET10 && sect_form[sec] != FORM) continue;   // warp-uniform
+    const double D11 = sectD[3 * sec], D12 = sectD[3 * sec + 1], D44 = sectD[3 * sec + 2];
+    const double alpha = has_temp ? sectA[sec] : 0.0;
+    const int p0 = elem_node_index[e];
+    const int *conn = elem_node_item + p0;
+    if (lane < NN) {
+      const size_t nd = (size_t)(conn[lane] - 1);
+#pragma unroll
+      for (int c = 0; c < 3; c++) { S.xc[3 * lane + c] = node[3 * nd + c]; S.uc[3 * lane + c] = utot[3 * nd + c]; }
+      if (has_temp) { S.tc[lane] = temp[nd]; S.t0c[lane] = temp0[nd]; }
+    }
+    __syncwarp();
+    const double q = element_update_lin_warp<FORM>(lane, S, D11, D12, D44, alpha, ref_temp, has_temp,
+                                                   gp_strain + 48 * (size_t)e, gp_stress + 48 * (size_t)e);
+    if (lane < 3 * NN) eqf[3 * (size_t)p0 + lane] = q;
+    __syncwarp();
+  }
+}
+
+template <int WARPS, int ICINV>
+__global__ void __launch_bounds__(WARPS * 32)
+update_ic_kernel(int e0, int e1, const int *__restrict__ elem_node_index, const int *__restrict__ elem_node_item,
+                 const double *__restrict__ node, const double *__restrict__ utot, const int *__restrict__ section_ID,
+                 const double *__restrict__ sectD, const double *__restrict__ sectA, const int *__restrict__ sect_form,
+                 const double *__restrict__ temp, const double *__restrict__ temp0, double ref_temp,
+                 double *__restrict__ gp_strain, double *__restrict__ gp_stress, double *__restrict__ eqf) {
+  using namespace elem;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Scratch &S = reinterpret_cast<Scratch *>(smem_raw)[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const int wg = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  const int nw = gridDim.x * WARPS;
+  const bool has_temp = temp != nullptr;
+  for (int e = e0 + wg; e < e1; e += nw) {
+    const int sec = section_ID[e] - 1;
+    if (sect_form[sec] != FORM_IC) continue;   // warp-uniform
+    const double D11 = sectD[3 * sec], D12 = sectD[3 * sec + 1], D44 = sectD[3 * sec + 2];
+    const double alpha = has_temp ? sectA[sec] : 0.0;
+    const int p0 = elem_node_index[e];
+    const int *conn = elem_node_item + p0;
+    if (lane < 8) {
+      const size_t nd = (size_t)(conn[lane] - 1);
+#pragma unroll
+      for (int c = 0; c < 3; c++) { S.xc[3 * lane + c] = node[3 * nd + c]; S.uc[3 * lane + c] = utot[3 * nd + c]; }
+      if (has_temp) { S.tc[lane] = temp[nd]; S.t0c[lane] = temp0[nd]; }
+    }
+    __syncwarp();
+    const double q = element_update_ic_warp<ICINV>(lane, S, D11, D12, D44, alpha, ref_temp, has_temp,
+                                                   gp_strain + 48 * (size_t)e, gp_stress + 48 * (size_t)e);
+    if (lane < 24) eqf[3 * (size_t)p0 + lane] = q;
+    __syncwarp();
+  }
+}
+
+#endif   // !FB_EMUL_KERNELS
+
+// ---- node incidence (topology only): node -> the positions p in elem_node_item that name it, ascending --------
+// Built with the gather_count / gather_fill / gather_sort kernels above from nslot[p] = elem_node_item[p] - 1.
+__global__ void __launch_bounds__(256)
+node_slot_kernel(size_t nconn, const int *__restrict__ elem_node_item, unsigned *__restrict__ nslot) {
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < nconn; p += (size_t)gridDim.x * blockDim.x)
+    nslot[p] = (unsigned)(elem_node_item[p] - 1);
+}
+__global__ void __launch_bounds__(256)
+pos_elem_kernel(int n_elem, const int *__restrict__ elem_node_index, int *__restrict__ pos_elem) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_elem; e += gridDim.x * blockDim.x)
+    for (int p = elem_node_index[e]; p < elem_node_index[e + 1]; p++) pos_elem[p] = e;
+}
+// QFORCE(3*node + c) = sum over the incident (element, local node) pairs, ascending element order
+__global__ void __launch_bounds__(256)
+node_gather3_kernel(int n_node, const unsigned *__restrict__ nptr, const unsigned *__restrict__ npos,
+                    const double *__restrict__ eqf, double *__restrict__ out) {
+  const size_t total = 3 * (size_t)n_node;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = t / 3;
+    const unsigned c = (unsigned)(t - 3 * n);
+    double acc = 0.0;
+    for (unsigned k = nptr[n]; k < nptr[n + 1]; k++) acc += eqf[3 * (size_t)npos[k] + c];
+    out[t] = acc;
+  }
+}
+// fstr_NodalStress3D, nodal part: thread (node, c) with c < 6 strain, c >= 6 stress.  Extrapolates the Gauss-point
+// values of every incident element to this node (NodalStress_INV3), sums them in ascending element order and divides
+// by their number (:204-228).
+__global__ void __launch_bounds__(256)
+nodal_stress_kernel(int n_node, const unsigned *__restrict__ nptr, const unsigned *__restrict__ npos,
+                    const int *__restrict__ pos_elem, const int *__restrict__ elem_node_index,
+                    const double *__restrict__ gp_strain, const double *__restrict__ gp_stress, elem::NodalExtrap X,
+                    double *__restrict__ STRAIN, double *__restrict__ STRESS) {
+  const size_t total = 12 * (size_t)n_node;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = t / 12;
+    const int c12 = (int)(t - 12 * n), c = c12 % 6;
+    const double *gp = (c12 < 6) ? gp_strain : gp_stress;
+    const unsigned k0 = nptr[n], k1 = nptr[n + 1];
+    double acc = 0.0;
+    for (unsigned k = k0; k < k1; k++) {
+      const int p = (int)npos[k], e = pos_elem[p], pe = elem_node_index[e];
+      acc = acc + elem::nodal_extrapolate(X, elem_node_index[e + 1] - pe, p - pe, gp + 48 * (size_t)e, c);
+    }
+    if (k1 > k0) acc = acc / (double)(k1 - k0);
+    ((c12 < 6) ? STRAIN : STRESS)[6 * n + c] = acc;
+  }
+}
+// elemental part (ElementStress_C3, static_LIB_3d.f90:881-913): average over the Gauss points
+__global__ void __launch_bounds__(256)
+elem_stress_kernel(int n_elem, const int *__restrict__ elem_node_index, const double *__restrict__ gp_strain,
+                   const double *__restrict__ gp_stress, double *__restrict__ ESTRAIN, double *__restrict__ ESTRESS) {
+  const size_t total = 12 * (size_t)n_elem;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t e = t / 12;
+    const int c12 = (int)(t - 12 * e), c = c12 % 6;
+    const int ni = (elem_node_index[e + 1] - elem_node_index[e] == 8) ? 8 : 4;
+    const double *gp = ((c12 < 6) ? gp_strain : gp_stress) + 48 * e;
+    double acc = 0.0;
+    for (int i = 0; i < ni; i++) acc = acc + gp[6 * i + c];
+    ((c12 < 6) ? ESTRAIN : ESTRESS)[6 * e + c] = acc / ni;
+  }
+}
+__global__ void __launch_bounds__(256)
+mises_kernel(size_t n, const double *__restrict__ stress, double *__restrict__ mises) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    mises[i] = elem::mises_of(stress + 6 * i);
 }
 
 // ---- hecmw_mat_ass_bc, batched ---------------------------------------------------------------

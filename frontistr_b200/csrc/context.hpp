@@ -79,6 +79,13 @@ struct Context {
   DevBuf<elem::MatlTL> m_matl;           // nonlinear path: per-section material records
   DevBuf<double> m_u, m_qf;              // nonlinear path: nodal displacement in, internal force out
   int nl_n_elem = 0;
+  // linear strain / stress recovery (update_3d / nodal_stress_3d): node incidence of the resident mesh, per-position
+  // element internal force, section expansion coefficients, nodal temperatures
+  DevBuf<unsigned> nptr, npos;
+  DevBuf<int> pos_elem;
+  DevBuf<double> eqf, m_sectA, m_temp, m_temp0;
+  const void *key_node_inc = nullptr;    // elem_node_item the incidence was built from
+  int upd_n_node = 0, upd_n_elem = 0;    // mesh of the last update call (what nodal_stress_3d works on)
   bool gather_valid = false;
   DevBuf<unsigned> slot;
   DevBuf<int> m_eni, m_enn, m_sec, m_form;

@@ -60,6 +60,13 @@ struct alignas(16) Scratch {
   double Kaa[9 * 9];        // IC: K(alpha, alpha) -> inverse, row-major [r][c]
   double W[24 * 10];        // IC: Kda * Kaa^-1, row stride 10
   double piv[12];           // IC, shared-memory inverse only: IP(0..8), LR, PIVOT
+  // ---- UpdateST_C3D8IC only (strain / stress recovery of the IC element)
+  double uc[10 * 3];        // nodal displacement unode + dunode
+  double tc[10], t0c[10];   // nodal temperature / initial temperature
+  double cd[12];            // enhanced-mode amplitudes -Kaa^-1 Kad u (9 used)
+  double tf[12];            // Kad u, then Kaa^-1 tv(24:32) (9 used)
+  double tv[36];            // thermal load vector incl. the enhanced modes (33 used)
+  double eth[8];            // thermal strain per Gauss point
 };
 
 FB_HD void hex_shape_deriv(double x, double y, double z, double (*d)[3]) {
@@ -481,6 +488,7 @@ struct alignas(16) ScratchTL {
   double Dm[8 * 36];        // material tangent per Gauss point, row-major 6x6
   double sg[8 * 6];         // 2nd Piola-Kirchhoff stress per Gauss point (xx yy zz xy yz zx)
   double qf[8 * 30];        // update: internal-force contribution of every Gauss point
+  double tc[10], t0c[10];   // linear update with !TEMPERATURE: nodal temperature / initial temperature
 };
 
 enum Material { MAT_ELASTIC = 0, MAT_MOONEYRIVLIN = 1 };
@@ -727,6 +735,238 @@ FB_WARP_FN double element_update_tl_warp(int lane, ScratchTL &S, const MatlTL &M
   return q;
 }
 #endif
+
+// =============================================================================================
+// Strain / stress recovery of the LINEAR static analysis: fstr_UpdateNewton with nlgeom_flag == INFINITE
+// (fstr_Update.f90:25-293): UPDATE_C3 (static_LIB_3d.f90:516-837) for 361 FI / 342, Update_C3D8Bbar
+// (static_LIB_C3D8.f90:203-552), UpdateST_C3D8IC (static_LIB_3dIC.f90:220-455).  Isotropic elastic material, thermal
+// strain alpha (T - Tref) - alpha (T0 - Tref) when nodal temperatures are given.  SURVEY 8(f) rank 2.
+// =============================================================================================
+FB_HD void hex_shape_func(double x, double y, double z, double *f) {   // ShapeFunc_hex8n, hex8n.f90:9-21
+  const double sx[8] = {-1, 1, 1, -1, -1, 1, 1, -1};
+  const double sy[8] = {-1, -1, 1, 1, -1, -1, 1, 1};
+  const double sz[8] = {-1, -1, -1, -1, 1, 1, 1, 1};
+  for (int n = 0; n < 8; n++) f[n] = 0.125 * (1.0 + sx[n] * x) * (1.0 + sy[n] * y) * (1.0 + sz[n] * z);
+}
+FB_HD void tet10_shape_func(double xi, double et, double ze, double *s) {   // ShapeFunc_tet10n, tet10n.f90:9-26
+  const double a = 1.0 - xi - et - ze;
+  s[0] = (2.0 * a - 1.0) * a; s[1] = xi * (2.0 * xi - 1.0); s[2] = et * (2.0 * et - 1.0); s[3] = ze * (2.0 * ze - 1.0);
+  s[4] = 4.0 * xi * a; s[5] = 4.0 * xi * et; s[6] = 4.0 * et * a; s[7] = 4.0 * ze * a; s[8] = 4.0 * xi * ze; s[9] = 4.0 * et * ze;
+}
+// thermal strain at Gauss point g from the nodal temperatures (static_LIB_3d.f90:597-633)
+template <int FORM>
+FB_HD double gauss_thermal_strain(int g, const double *tc, const double *t0c, double alpha, double ref_temp) {
+  constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
+  double H[10];
+  if (FORM == FORM_TET10) tet10_shape_func((g == 1) ? kTetB : kTetA, (g == 2) ? kTetB : kTetA, (g == 3) ? kTetB : kTetA, H);
+  else hex_shape_func((g & 1) ? kGaussHex : -kGaussHex, (g & 2) ? kGaussHex : -kGaussHex, (g & 4) ? kGaussHex : -kGaussHex, H);
+  double ttc = 0.0, tt0 = 0.0;
+  for (int n = 0; n < NN; n++) { ttc += tc[n] * H[n]; tt0 += t0c[n] * H[n]; }
+  return alpha * (ttc - ref_temp) - alpha * (tt0 - ref_temp);
+}
+
+// lane g < NGP of UPDATE_C3 / Update_C3D8Bbar with flag == INFINITE; S.F holds dudx of the point (tl_phase_state)
+template <int FORM>
+FB_HD void lin_phase_update(int lane, ScratchTL &S, double D11, double D12, double D44, double alpha, double ref_temp,
+                            bool has_temp, double *gp_strain, double *gp_stress) {
+  constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
+  constexpr int NGP = (FORM == FORM_TET10) ? 4 : 8;
+  if (lane >= NGP) return;
+  const double *gd = S.gd + lane * NN * 3;
+  const double *F = S.F + 9 * lane;
+  double dvol = 0.0;
+  if (FORM == FORM_BBAR) {   // dilatation at the centroid, static_LIB_C3D8.f90:270-274,295
+    const double *bb = S.bb + lane * 8 * 3;
+    double tr = 0.0;
+    for (int n = 0; n < 8; n++)
+      for (int c = 0; c < 3; c++) tr += S.uc[3 * n + c] * (gd[3 * n + c] + 3.0 * bb[3 * n + c]);
+    dvol = tr / 3.0 - (F[0] + F[4] + F[8]) / 3.0;
+  }
+  const double eth = has_temp ? gauss_thermal_strain<FORM>(lane, S.tc, S.t0c, alpha, ref_temp) : 0.0;
+  double ds[6];
+  ds[0] = (F[0] + dvol) - eth; ds[1] = (F[4] + dvol) - eth; ds[2] = (F[8] + dvol) - eth;
+  ds[3] = F[1] + F[3]; ds[4] = F[5] + F[7]; ds[5] = F[6] + F[2];
+  double sg[6];
+  sg[0] = D11 * ds[0] + D12 * ds[1] + D12 * ds[2];
+  sg[1] = D12 * ds[0] + D11 * ds[1] + D12 * ds[2];
+  sg[2] = D12 * ds[0] + D12 * ds[1] + D11 * ds[2];
+  sg[3] = D44 * ds[3]; sg[4] = D44 * ds[4]; sg[5] = D44 * ds[5];
+  for (int k = 0; k < 6; k++) { gp_strain[6 * lane + k] = ds[k] + (k < 3 ? eth : 0.0); gp_stress[6 * lane + k] = sg[k]; }
+  const double w = S.wdet[lane];
+  const double zeroF[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // BL0 only
+  for (int n = 0; n < NN; n++) {
+    double B[6][3];
+    tl_build_B(gd + 3 * n, FORM == FORM_BBAR ? S.bb + (lane * 8 + n) * 3 : nullptr, zeroF, B);
+    for (int c = 0; c < 3; c++) {
+      double s = 0.0;
+      for (int r = 0; r < 6; r++) s += sg[r] * B[r][c];
+      S.qf[30 * lane + 3 * n + c] = s * w;
+    }
+  }
+}
+
+#ifdef FB_WARP_FN
+// One element of the linear update (361 FI / B-bar, 342): S.xc, S.uc (= unode + dunode) and, if has_temp, S.tc / S.t0c
+// filled and synchronised.  Writes the strain / stress of every Gauss point; lane t < 3 nn returns qf[t].
+template <int FORM>
+FB_WARP_FN double element_update_lin_warp(int lane, ScratchTL &S, double D11, double D12, double D44, double alpha,
+                                          double ref_temp, bool has_temp, double *gp_strain, double *gp_stress) {
+  constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
+  constexpr int NGP = (FORM == FORM_TET10) ? 4 : 8;
+  MatlTL M;
+  M.mtype = MAT_ELASTIC; M.D11 = D11; M.D12 = D12; M.D44 = D44; M.c[0] = M.c[1] = M.c[2] = 0.0;
+  phase_geometry<FORM>(lane, S);
+  FB_SYNCWARP();
+  tl_phase_state<FORM>(lane, S, M, nullptr, nullptr);   // dudx per Gauss point
+  FB_SYNCWARP();
+  lin_phase_update<FORM>(lane, S, D11, D12, D44, alpha, ref_temp, has_temp, gp_strain, gp_stress);
+  FB_SYNCWARP();
+  double q = 0.0;
+  if (lane < 3 * NN)
+    for (int g = 0; g < NGP; g++) q += S.qf[30 * g + lane];
+  return q;
+}
+
+// UpdateST_C3D8IC: S.xc, S.uc (and S.tc / S.t0c) filled and synchronised.  The enhanced-mode amplitudes are
+// recovered from the element's own K(d,alpha), K(alpha,alpha) exactly as the reference does (:329-335), then strain
+// = B [u; alpha] at the 8 Gauss points.  Lane t < 24 returns qf[t] = (K [u; alpha])_t (- thermal load vector).
+template <int ICINV>
+FB_WARP_FN double element_update_ic_warp(int lane, Scratch &S, double D11, double D12, double D44, double alpha,
+                                         double ref_temp, bool has_temp, double *gp_strain, double *gp_stress) {
+  double kb[2][9];
+  element_stiffness_warp<FORM_IC, ICINV>(lane, S, D11, D12, D44, kb, false);   // K(d,d) blocks, not condensed
+  ic_phase_coupling(lane, S, D11, D12, D44);
+  FB_SYNCWARP();
+  if (ICINV == 1) ic_inverse_warp(lane, S);
+  else ic_inverse_smem_warp(lane, S);
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    const int t = r * 32 + lane;
+#pragma unroll
+    for (int a = 0; a < 9; a++) S.stage[t * 9 + a] = kb[r][a];
+  }
+  if (has_temp && lane < 8) S.eth[lane] = gauss_thermal_strain<FORM_IC>(lane, S.tc, S.t0c, alpha, ref_temp);
+  FB_SYNCWARP();
+  if (lane < 9) {   // tmpforce = Kad u, :332
+    double s = 0.0;
+    for (int r = 0; r < 24; r++) s += S.Kda[r * 10 + lane] * S.uc[r];
+    S.tf[lane] = s;
+  }
+  FB_SYNCWARP();
+  if (lane < 9) {   // cdisp(25:33) = -Kaa^-1 tmpforce, :335
+    double s = 0.0;
+    for (int k = 0; k < 9; k++) s += S.Kaa[lane * 9 + k] * S.tf[k];
+    S.cd[lane] = -s;
+  }
+  if (has_temp) {   // TLOAD_C3D8IC tmpvect (static_LIB_3dIC.f90:560-590): thermal stress (D11 + 2 D12) eth on the normal rows
+    for (int j = lane; j < 33; j += 32) {
+      const int n = j / 3, c = j % 3;
+      double s = 0.0;
+      for (int g = 0; g < 8; g++) s += ((D11 + D12 + D12) * S.eth[g]) * S.gd[(g * 11 + n) * 3 + c] * S.wdet[g];
+      S.tv[j] = s;
+    }
+  }
+  FB_SYNCWARP();
+  double q = 0.0;
+  if (lane < 24) {   // qf = K(1:24, 1:33) cdisp, :338
+    const int i = lane / 3, a = lane % 3;
+    for (int j = 0; j < 8; j++)
+      for (int b = 0; b < 3; b++) q += S.stage[(i * 8 + j) * 9 + 3 * a + b] * S.uc[3 * j + b];
+    for (int k = 0; k < 9; k++) q += S.Kda[lane * 10 + k] * S.cd[k];
+  }
+  if (has_temp) {   // qf -= TLOAD_C3D8IC = tmpvect(1:24) - Kda Kaa^-1 tmpvect(25:33), :340-342
+    FB_SYNCWARP();
+    if (lane < 9) {
+      double s = 0.0;
+      for (int k = 0; k < 9; k++) s += S.Kaa[lane * 9 + k] * S.tv[24 + k];
+      S.tf[lane] = s;
+    }
+    FB_SYNCWARP();
+    if (lane < 24) {
+      double s = 0.0;
+      for (int k = 0; k < 9; k++) s += S.Kda[lane * 10 + k] * S.tf[k];
+      q -= S.tv[lane] - s;
+    }
+  }
+  if (lane < 8) {   // strain = B cdisp, stress = D (strain - eth), :346-452
+    const double *gd = S.gd + lane * 11 * 3;
+    double e[6] = {0, 0, 0, 0, 0, 0};
+    for (int n = 0; n < 11; n++) {
+      const double *u = (n < 8) ? S.uc + 3 * n : S.cd + 3 * (n - 8);
+      const double g1 = gd[3 * n], g2 = gd[3 * n + 1], g3 = gd[3 * n + 2];
+      e[0] += g1 * u[0]; e[1] += g2 * u[1]; e[2] += g3 * u[2];
+      e[3] += g2 * u[0]; e[3] += g1 * u[1];
+      e[4] += g3 * u[1]; e[4] += g2 * u[2];
+      e[5] += g3 * u[0]; e[5] += g1 * u[2];
+    }
+    const double eth = has_temp ? S.eth[lane] : 0.0;
+    const double d0 = e[0] - eth, d1 = e[1] - eth, d2 = e[2] - eth;
+    double *eo = gp_strain + 6 * lane, *so = gp_stress + 6 * lane;
+    for (int k = 0; k < 6; k++) eo[k] = e[k];
+    so[0] = D11 * d0 + D12 * d1 + D12 * d2;
+    so[1] = D12 * d0 + D11 * d1 + D12 * d2;
+    so[2] = D12 * d0 + D12 * d1 + D11 * d2;
+    so[3] = D44 * e[3]; so[4] = D44 * e[4]; so[5] = D44 * e[5];
+  }
+  return q;
+}
+#endif
+
+// ---- fstr_NodalStress3D (fstr_NodalStress.f90:13-272) for 361 / 342 -------------------------------------------
+// Extrapolation matrices: the inverse (inverse_func, :714-748: Gauss-Jordan without pivoting) of the hex8n (342: tet4n)
+// shape functions evaluated at the Gauss points, :64-81.
+struct NodalExtrap {
+  double inv8[64];   // 361: [node][gauss point]
+  double inv4[16];   // 342: [vertex][gauss point]
+};
+FB_HD void inverse_func(int n, double *a, double *inv_a) {
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) inv_a[i * n + j] = (i == j) ? 1.0 : 0.0;
+  for (int i = 0; i < n; i++) {
+    double buf = 1.0 / a[i * n + i];
+    for (int j = 0; j < n; j++) { a[i * n + j] = a[i * n + j] * buf; inv_a[i * n + j] = inv_a[i * n + j] * buf; }
+    for (int j = 0; j < n; j++)
+      if (i != j) {
+        buf = a[j * n + i];
+        for (int k = 0; k < n; k++) {
+          a[j * n + k] = a[j * n + k] - a[i * n + k] * buf;
+          inv_a[j * n + k] = inv_a[j * n + k] - inv_a[i * n + k] * buf;
+        }
+      }
+  }
+}
+inline void nodal_extrap_build(NodalExtrap &X) {   // host, once
+  double f8[64], f4[16];
+  for (int g = 0; g < 8; g++)
+    hex_shape_func((g & 1) ? kGaussHex : -kGaussHex, (g & 2) ? kGaussHex : -kGaussHex, (g & 4) ? kGaussHex : -kGaussHex, f8 + 8 * g);
+  inverse_func(8, f8, X.inv8);
+  for (int g = 0; g < 4; g++) {   // ShapeFunc_tet4n at the 342 Gauss points, tet4n.f90:11-16
+    const double xi = (g == 1) ? kTetB : kTetA, et = (g == 2) ? kTetB : kTetA, ze = (g == 3) ? kTetB : kTetA;
+    f4[4 * g] = 1.0 - xi - et - ze; f4[4 * g + 1] = xi; f4[4 * g + 2] = et; f4[4 * g + 3] = ze;
+  }
+  inverse_func(4, f4, X.inv4);
+}
+// value of component c (of [gp][6] data `src` of ONE element) extrapolated to local node j (NodalStress_INV3, :337-400)
+FB_HD double nodal_extrapolate(const NodalExtrap &X, int nn, int j, const double *src, int c) {
+  if (nn == 8) {
+    double v = 0.0;
+    for (int i = 0; i < 8; i++) v = v + X.inv8[j * 8 + i] * src[6 * i + c];
+    return v;
+  }
+  const int ma[6] = {0, 1, 2, 0, 1, 2}, mb[6] = {1, 2, 0, 3, 3, 3};   // mid-edge nodes 5..10 of tet10n, :361-378
+  const int a = (j < 4) ? j : ma[j - 4], b = (j < 4) ? j : mb[j - 4];
+  double va = 0.0, vb = 0.0;
+  for (int i = 0; i < 4; i++) va = va + X.inv4[a * 4 + i] * src[6 * i + c];
+  if (j < 4) return va;
+  for (int i = 0; i < 4; i++) vb = vb + X.inv4[b * 4 + i] * src[6 * i + c];
+  return (va + vb) / 2.0;
+}
+FB_HD double mises_of(const double *s) {   // get_mises, fstr_NodalStress.f90:483-500
+  const double ps = (s[0] + s[1] + s[2]) / 3.0;
+  const double sm = 0.5 * ((s[0] - ps) * (s[0] - ps) + (s[1] - ps) * (s[1] - ps) + (s[2] - ps) * (s[2] - ps)) +
+                    s[3] * s[3] + s[4] * s[4] + s[5] * s[5];
+  return sqrt(3.0 * sm);
+}
 
 // isotropic elastic constants, ElasticLinear.f90:48-59
 FB_HD void elastic_constants(double EE, double PP, double &D11, double &D12, double &D44) {

@@ -10,7 +10,8 @@
 #include <vector>
 
 #define FB_EMUL_WARP 1
-#include "element_math.cuh"
+#define FB_EMUL_KERNELS 1
+#include "assembly.cuh"   // element_math.cuh + the grid-stride kernels, run on the host through kernel_emul.hpp
 
 using namespace fb::elem;
 
@@ -118,7 +119,92 @@ static void run_update_tl(const double *ecoord, const double *utot, const MatlTL
   });
 }
 
+template <int FORM>
+static void run_update_lin(const double *ecoord, const double *utot, double E, double nu, const double *TT, const double *T0,
+                           double alpha, double ref_temp, double *qf, double *strain, double *stress) {
+  constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
+  static ScratchTL S;
+  std::memset(&S, 0, sizeof S);
+  double D11, D12, D44;
+  elastic_constants(E, nu, D11, D12, D44);
+  for (int k = 0; k < 3 * NN; k++) { S.xc[k] = ecoord[k]; S.uc[k] = utot[k]; }
+  if (TT) for (int k = 0; k < NN; k++) { S.tc[k] = TT[k]; S.t0c[k] = T0[k]; }
+  fb::emulwarp::run_warp([&](int lane) {
+    const double q = element_update_lin_warp<FORM>(lane, S, D11, D12, D44, alpha, ref_temp, TT != nullptr, strain, stress);
+    if (lane < 3 * NN) qf[lane] = q;
+  });
+}
+template <int ICINV>
+static void run_update_ic(const double *ecoord, const double *utot, double E, double nu, const double *TT, const double *T0,
+                          double alpha, double ref_temp, double *qf, double *strain, double *stress) {
+  static Scratch S;
+  std::memset(&S, 0, sizeof S);
+  double D11, D12, D44;
+  elastic_constants(E, nu, D11, D12, D44);
+  for (int k = 0; k < 24; k++) { S.xc[k] = ecoord[k]; S.uc[k] = utot[k]; }
+  if (TT) for (int k = 0; k < 8; k++) { S.tc[k] = TT[k]; S.t0c[k] = T0[k]; }
+  fb::emulwarp::run_warp([&](int lane) {
+    const double q = element_update_ic_warp<ICINV>(lane, S, D11, D12, D44, alpha, ref_temp, TT != nullptr, strain, stress);
+    if (lane < 24) qf[lane] = q;
+  });
+}
+
 extern "C" {
+
+// linear strain / stress update of one element exactly as the CUDA warp executes it (form 3 = IC with the
+// register/shuffle inverse, 30 = IC with the shared-memory inverse); TT / T0 may be NULL
+int fbemul_element_update_lin(int form, const double *ecoord, const double *utot, double E, double nu, const double *TT,
+                              const double *T0, double alpha, double ref_temp, double *qf, double *strain, double *stress) {
+  switch (form) {
+    case FORM_FI: run_update_lin<FORM_FI>(ecoord, utot, E, nu, TT, T0, alpha, ref_temp, qf, strain, stress); return 0;
+    case FORM_BBAR: run_update_lin<FORM_BBAR>(ecoord, utot, E, nu, TT, T0, alpha, ref_temp, qf, strain, stress); return 0;
+    case FORM_TET10: run_update_lin<FORM_TET10>(ecoord, utot, E, nu, TT, T0, alpha, ref_temp, qf, strain, stress); return 0;
+    case FORM_IC: run_update_ic<1>(ecoord, utot, E, nu, TT, T0, alpha, ref_temp, qf, strain, stress); return 0;
+    case 30: run_update_ic<0>(ecoord, utot, E, nu, TT, T0, alpha, ref_temp, qf, strain, stress); return 0;
+  }
+  return -1;
+}
+// fstr_NodalStress3D building blocks of the CUDA kernels: extrapolation matrices and one extrapolated value
+int fbemul_nodal_extrap(double *inv8, double *inv4) {
+  NodalExtrap X;
+  nodal_extrap_build(X);
+  std::memcpy(inv8, X.inv8, sizeof X.inv8); std::memcpy(inv4, X.inv4, sizeof X.inv4);
+  return 0;
+}
+double fbemul_nodal_extrapolate(int nn, int j, const double *src, int c) {
+  NodalExtrap X;
+  nodal_extrap_build(X);
+  return nodal_extrapolate(X, nn, j, src, c);
+}
+double fbemul_mises(const double *s) { return mises_of(s); }
+
+// The post-processing kernels of update_3d / nodal_stress_3d (assembly.cuh) run UNCHANGED on the host, threads in a
+// scrambled order: node incidence (node_slot / pos_elem / gather_count / scan / gather_fill / gather_sort), QFORCE
+// gather, nodal extrapolation + averaging, elemental averages, von Mises.  Same launch sequence as api_assembly.inc.
+int fbemul_nodal_pipeline(int n_node, int n_elem, const int *elem_node_index, const int *elem_node_item,
+                          const double *gp_strain, const double *gp_stress, const double *eqf, unsigned seed, double *QFORCE,
+                          double *STRAIN, double *STRESS, double *MISES, double *ESTRAIN, double *ESTRESS, double *EMISES) {
+  using namespace fb;
+  const size_t nconn = (size_t)elem_node_index[n_elem];
+  std::vector<unsigned> nslot(nconn), cursor((size_t)n_node + 1, 0u), nptr((size_t)n_node + 1, 0u), npos(nconn);
+  std::vector<int> pos_elem(nconn);
+  emul_launch(3, 64, seed, node_slot_kernel, nconn, elem_node_item, nslot.data());
+  emul_launch(2, 64, seed + 1, pos_elem_kernel, n_elem, elem_node_index, pos_elem.data());
+  emul_launch(3, 64, seed + 2, gather_count_kernel, nconn, (const unsigned *)nslot.data(), cursor.data());
+  for (int i = 0; i < n_node; i++) nptr[i + 1] = nptr[i] + cursor[i];   // cub::DeviceScan::ExclusiveSum
+  std::fill(cursor.begin(), cursor.end(), 0u);
+  emul_launch(3, 64, seed + 3, gather_fill_kernel, nconn, (const unsigned *)nslot.data(), (const unsigned *)nptr.data(), cursor.data(), npos.data());
+  emul_launch(2, 64, seed + 4, gather_sort_kernel, (size_t)n_node, (const unsigned *)nptr.data(), npos.data());
+  emul_launch(3, 64, seed + 5, node_gather3_kernel, n_node, (const unsigned *)nptr.data(), (const unsigned *)npos.data(), eqf, QFORCE);
+  NodalExtrap X;
+  nodal_extrap_build(X);
+  emul_launch(5, 64, seed + 6, nodal_stress_kernel, n_node, (const unsigned *)nptr.data(), (const unsigned *)npos.data(),
+              (const int *)pos_elem.data(), elem_node_index, gp_strain, gp_stress, X, STRAIN, STRESS);
+  emul_launch(5, 64, seed + 7, elem_stress_kernel, n_elem, elem_node_index, gp_strain, gp_stress, ESTRAIN, ESTRESS);
+  emul_launch(2, 64, seed + 8, mises_kernel, (size_t)n_node, (const double *)STRESS, MISES);
+  emul_launch(2, 64, seed + 9, mises_kernel, (size_t)n_elem, (const double *)ESTRESS, EMISES);
+  return 0;
+}
 
 // total-Lagrangian tangent stiffness / update of one element exactly as the CUDA warp executes them
 int fbemul_element_stiffness_tl(int form, const double *ecoord, const double *u, const double *gp_strain,

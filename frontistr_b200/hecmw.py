@@ -162,6 +162,45 @@ def fstr_StiffMatrix(hecMESH, hecMAT, to_host: bool = True):
     return dict(kernel_ms=float(t[0]), total_ms=float(t[1]))
 
 
+# ---- strain / stress recovery of the linear static analysis ---------------------------------------------------
+def fstr_UpdateNewton_linear(hecMESH, unode, dunode, temperature=None, temperature0=None, ref_temp=0.0):
+    """fstr_UpdateNewton with nlgeom_flag == INFINITE (fstr_Update.f90:25-293): strain / stress of every Gauss point
+    at unode + dunode (kept on the device) and QFORCE (returned).  Sections may carry "alpha" (expansion coefficient)."""
+    m = hecMESH
+    eti, ett = _i32(m.elem_type_index), _i32(m.elem_type_item)
+    if not hasattr(m, "_conn") or m._conn[2] is not m.elem_node_item:
+        m._conn = (_i32(m.elem_node_index), _i32(m.elem_node_item), m.elem_node_item)
+    eni, enn = m._conn[0], m._conn[1]
+    sec = _i32(m.section_ID)
+    ns = len(m.sections)
+    form = np.array([s["elemopt361"] for s in m.sections], np.int32)
+    E = np.array([s["E"] for s in m.sections], np.float64)
+    nu = np.array([s["nu"] for s in m.sections], np.float64)
+    alpha = np.array([s.get("alpha", 0.0) for s in m.sections], np.float64)
+    node = np.ascontiguousarray(m.node, np.float64)
+    un = np.ascontiguousarray(unode, np.float64) if unode is not None else None
+    dun = np.ascontiguousarray(dunode, np.float64) if dunode is not None else None
+    tt = np.ascontiguousarray(temperature, np.float64) if temperature is not None else None
+    t0 = np.ascontiguousarray(temperature0, np.float64) if temperature0 is not None else None
+    qf = np.zeros(3 * m.n_node)
+    check(_lib.lib().fistr_b200_update_3d(m.n_node, dp(node), m.n_elem, m.n_elem_type, ip(eti), ip(ett), ip(eni), ip(enn),
+                                   ip(sec), ns, ip(form), dp(E), dp(nu), dp(alpha) if tt is not None else None,
+                                   dp(un) if un is not None else None, dp(dun) if dun is not None else None,
+                                   dp(tt) if tt is not None else None, dp(t0) if t0 is not None else None,
+                                   C.c_double(ref_temp), dp(qf)))
+    return qf
+
+
+def fstr_NodalStress3D(hecMESH):
+    """fstr_NodalStress3D (fstr_NodalStress.f90:13-272) on the Gauss-point state of the last update: dict with
+    STRAIN / STRESS (n_node, 6), MISES (n_node), ESTRAIN / ESTRESS (n_elem, 6), EMISES (n_elem)."""
+    m = hecMESH
+    out = dict(STRAIN=np.zeros((m.n_node, 6)), STRESS=np.zeros((m.n_node, 6)), MISES=np.zeros(m.n_node),
+               ESTRAIN=np.zeros((m.n_elem, 6)), ESTRESS=np.zeros((m.n_elem, 6)), EMISES=np.zeros(m.n_elem))
+    check(_lib.lib().fistr_b200_nodal_stress_3d(*[dp(out[k]) for k in ("STRAIN", "STRESS", "MISES", "ESTRAIN", "ESTRESS", "EMISES")]))
+    return out
+
+
 # ---- nonlinear static (total Lagrangian): fstr_StiffMatrix / fstr_UpdateNewton under NLGEOM, fstr_Newton ----------
 def _nl_args(m):
     eti, ett = _i32(m.elem_type_index), _i32(m.elem_type_item)

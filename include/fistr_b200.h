@@ -116,6 +116,26 @@ int fistr_b200_nl_update_3d(int n_node, const double *node, int n_elem, int n_el
                             const int *sect_mtype, const double *sect_hyper, const double *unode,
                             const double *dunode, double *QFORCE);
 
+/* ---- strain / stress recovery of the linear static analysis, SURVEY 8(f) rank 2 -----------------------------------
+ * update_3d       = fstr_UpdateNewton with nlgeom_flag == INFINITE (fistr1/src/analysis/static/fstr_Update.f90:25-293):
+ *                   UpdateST_C3D8IC (lib/static_LIB_3dIC.f90:220-455) for 361 elemopt361 = 3, UPDATE_C3
+ *                   (lib/static_LIB_3d.f90:516-837) for 361 FI and 342, Update_C3D8Bbar (lib/static_LIB_C3D8.f90:203-552):
+ *                   strain and stress of every Gauss point at unode + dunode (kept on the device, [element][8][6], the
+ *                   same state the nl_* entry points use) and QFORCE(3*n_node), summed per node in ascending element
+ *                   order.  sect_alpha / temperature / temperature0 (all NULL: no !TEMPERATURE): isotropic thermal strain
+ *                   alpha (T - ref_temp) - alpha (T0 - ref_temp).  QFORCE may be NULL.
+ * nodal_stress_3d = fstr_NodalStress3D (fistr1/src/analysis/static/fstr_NodalStress.f90:13-272) on the mesh and
+ *                   Gauss-point state of the last update_3d / nl_update_3d call: NodalStress_INV3 extrapolation
+ *                   (:337-400), nodal averaging, ElementStress_C3, von Mises.  STRAIN / STRESS (6*n_node),
+ *                   MISES (n_node), ESTRAIN / ESTRESS (6*n_elem), EMISES (n_elem); any pointer may be NULL. */
+int fistr_b200_update_3d(int n_node, const double *node, int n_elem, int n_elem_type, const int *elem_type_index,
+                         const int *elem_type_item, const int *elem_node_index, const int *elem_node_item,
+                         const int *section_ID, int n_sect, const int *sect_elemopt361, const double *sect_E,
+                         const double *sect_nu, const double *sect_alpha, const double *unode, const double *dunode,
+                         const double *temperature, const double *temperature0, double ref_temp, double *QFORCE);
+int fistr_b200_nodal_stress_3d(double *STRAIN, double *STRESS, double *MISES, double *ESTRAIN, double *ESTRESS,
+                               double *EMISES);
+
 /* ---- hecmw_mat_ass_bc (hecmw_mat_ass.f90:292-429), batched over the constrained DOFs that
  * fstr_AddBC (fistr1/src/analysis/static/fstr_AddBC.f90:54-109) visits.  Operates on the
  * device-resident matrix and RHS. */

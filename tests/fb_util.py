@@ -70,6 +70,36 @@ def oracle_solve_deck(name):
     return mesh, A, meta, thermal
 
 
+def product_solve_deck(hecmw, name):
+    """The same decks through the product's C-ABI (assembly, BC elimination and CG on the device; the right-hand side
+    of the distributed-load decks comes from the restated load routines, which are the caller side of the path)."""
+    from oracle import oracle as orc
+    mesh, cnt, meta = load_golden_mesh(name)
+    A = hecmw.hecmw_mat_con(mesh)
+    A.fstr_mat_init().hecMAT_init()
+    hecmw.mat_structure(mesh, A)
+    hecmw.fstr_StiffMatrix(mesh, A, to_host=False)
+    thermal = None
+    if "thermal" in meta:
+        th = meta["thermal"]
+        thermal = (np.full(mesh.n_node, th["temperature"]), np.full(mesh.n_node, th["initial"]), th["alpha"], th["reftemp"])
+        orc.ass_thermal_load(mesh, A, *thermal)
+    elif "pressure" in meta:
+        orc.ass_dload_pressure(mesh, A, meta["pressure"]["elems"], meta["pressure"]["face"], meta["pressure"]["value"])
+    elif "dload" in meta:
+        orc.ass_dload_volume(mesh, A, meta["dload"]["ltype"], meta["dload"]["params"], meta["rho"])
+    else:
+        hecmw.fstr_ass_load_cload(mesh, A, cnt["cload"])
+    hecmw.mat_upload(A, values=False, rhs=True)
+    n, d, v = hecmw.boundary_dofs(mesh, cnt["boundary"])
+    hecmw.hecmw_mat_ass_bc(n, d, v)
+    apply_solver_card(A, cnt["solver"])
+    A.Iarray[20] = 0; A.Iarray[21] = 0
+    r = hecmw.hecmw_solve(mesh, A, device_resident=True)
+    assert r["error"] == 0 and A.Iarray[80] == 1
+    return mesh, A, meta, thermal
+
+
 STRESS_KEYS = ("11", "22", "33", "12", "23", "13")
 
 

@@ -56,6 +56,23 @@ class ShadowBackend:
         r["profile"] = np.zeros(4)
         return r
 
+    def fstr_UpdateNewton_linear(self, mesh, unode, dunode, temperature=None, temperature0=None, ref_temp=0.0):
+        from oracle import oracle as orc
+        u = (0.0 if unode is None else np.asarray(unode)) + (0.0 if dunode is None else np.asarray(dunode))
+        eo = so = qo = None
+        for isec, sct in enumerate(mesh.sections):      # the oracle takes ONE expansion coefficient per run
+            e, s, q = orc.update_linear(mesh, u, temperature, temperature0, sct.get("alpha", 0.0), ref_temp)
+            if eo is None:
+                eo, so, qo = e.copy(), s.copy(), q
+            sel = np.asarray(mesh.section_ID) == isec + 1
+            eo[sel], so[sel] = e[sel], s[sel]
+        self._gp = (mesh, eo, so)
+        return qo
+
+    def fstr_NodalStress3D(self, mesh):
+        from oracle import oracle as orc
+        return orc.nodal_stress_3d(self._gp[0], self._gp[1], self._gp[2])
+
     def hecmw_matvec(self, X, n_internal3):
         from oracle import oracle as orc
         return orc.matvec(self._A, np.ascontiguousarray(X, float))[:n_internal3]

@@ -28,6 +28,17 @@ def test_dry_run_ic_inverse_variants():
     G.test_ic_inverse_register_kernel_matches_the_oracle(ShadowBackend())
 
 
+@pytest.mark.parametrize("name", ["A361", "B342", "F361", "F342"])
+def test_dry_run_linear_update_and_nodal_stress(name):
+    import test_gpu_z_unvalidated as Z
+    Z.test_linear_update_and_nodal_stress_golden_decks(ShadowBackend(), name)
+
+
+def test_dry_run_linear_update_mixed():
+    import test_gpu_z_unvalidated as Z
+    Z.test_linear_update_mixed_types_and_sections(ShadowBackend())
+
+
 def test_dry_run_mixed_types_and_sections():
     import test_gpu_z_unvalidated as Z
     Z.test_assembly_mixed_types_and_sections(ShadowBackend())

@@ -180,6 +180,124 @@ def test_ic_shared_memory_inverse_equals_register_inverse_and_oracle():
         assert np.abs(mine - ref).max() <= 1e-13 * np.abs(ref).max(), trial
 
 
+def test_linear_update_emulation_equals_oracle():
+    """Strain / stress recovery of the linear analysis as the CUDA warp executes it (element_math.cuh:
+    element_update_lin_warp for 361 FI / B-bar and 342, element_update_ic_warp for the IC element with either
+    calInverse; same source, lock-step host threads) against the oracle's restatement of UPDATE_C3 / Update_C3D8Bbar /
+    UpdateST_C3D8IC — Gauss-point strain, stress and the element internal force, with and without thermal strain.
+    (The oracle side is pinned on the E / S / SMS lines of the 14 linear golden logs, tests/test_oracle_golden.py.)"""
+    from oracle import oracle as orc
+    import __graft_entry__ as g
+    em = C.CDLL(g.build_emul())
+    dp = C.POINTER(C.c_double)
+    d = lambda a: a.ctypes.data_as(dp) if a is not None else None
+    rng = np.random.default_rng(3)
+    base = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], float)
+    ed = [(0, 1), (1, 2), (2, 0), (0, 3), (1, 3), (2, 3)]
+    for trial in range(5):
+        for form, kind, et in ((3, "IC", 361), (30, "IC", 361), (1, "FI", 361), (2, "BBAR", 361), (10, "C3", 342)):
+            if et == 361:
+                ec = np.ascontiguousarray(base * [0.7, 1.3, 0.9] + 0.15 * rng.standard_normal((8, 3)))
+            else:
+                vv = v + 0.1 * rng.standard_normal((4, 3))
+                ec = np.ascontiguousarray(np.vstack([vv, [(vv[a] + vv[b]) / 2 for a, b in ed]]))
+            nn = ec.shape[0]
+            u = np.ascontiguousarray(0.01 * rng.standard_normal((nn, 3)))
+            for thermal in (False, True):
+                TT = np.ascontiguousarray(20 + 100 * rng.random(nn)) if thermal else None
+                T0 = np.ascontiguousarray(20 + 5 * rng.random(nn)) if thermal else None
+                e0, s0, q0 = orc.element_update_linear(kind, ec, u, 4000.0, 0.3, etype=et, TT=TT, T0=T0, alpha=1e-5, reftemp=20.0)
+                e1 = np.zeros_like(e0); s1 = np.zeros_like(s0); q1 = np.zeros_like(q0)
+                assert em.fbemul_element_update_lin(form, d(ec), d(u), C.c_double(4000.0), C.c_double(0.3), d(TT), d(T0),
+                                                    C.c_double(1e-5), C.c_double(20.0), d(q1), d(e1), d(s1)) == 0
+                for a, b in ((e0, e1), (s0, s1), (q0, q1)):
+                    assert np.abs(a - b).max() <= 1e-13 * np.abs(a).max(), (form, thermal)
+
+
+def test_internal_force_of_the_linear_update_is_K_times_u():
+    """QFORCE of fstr_UpdateNewton equals K u for every element formulation (no thermal strain): ties the restated
+    update to the restated stiffness (UpdateST_C3D8IC condenses the same enhanced modes STF_C3D8IC does)."""
+    from oracle import oracle as orc
+    rng = np.random.default_rng(9)
+    for elemopt, mk in ((3, lambda: meshgen.hex_cube(3)), (1, lambda: meshgen.hex_cube(3, elemopt361=1)),
+                        (2, lambda: meshgen.hex_cube(3, elemopt361=2)), (0, lambda: meshgen.tet10_cube(2))):
+        mesh = util.distort(mk()) if elemopt else mk()
+        A = orc.mat_con(mesh)
+        orc.stiffmatrix(mesh, A)
+        u = rng.standard_normal(3 * mesh.n_node) * 1e-3
+        y = orc.matvec(A, u)
+        e, s, q = orc.update_linear(mesh, u)
+        assert np.abs(q - y).max() <= 1e-11 * np.abs(y).max(), elemopt
+
+
+def test_nodal_stress_building_blocks_equal_oracle():
+    """fstr_NodalStress3D pieces of the CUDA kernels (element_math.cuh: nodal_extrap_build = inverse_func of the
+    shape functions at the Gauss points, nodal_extrapolate incl. the tet10 mid-edge averaging, mises_of) against the
+    oracle's restatement (same operations in the same order: equal up to FMA contraction of the two compilers)."""
+    from oracle import oracle as orc
+    import __graft_entry__ as g
+    em = C.CDLL(g.build_emul())
+    em.fbemul_nodal_extrapolate.restype = C.c_double
+    em.fbemul_mises.restype = C.c_double
+    L = orc.lib()
+    L.orc_get_mises.restype = C.c_double
+    dp = C.POINTER(C.c_double)
+    inv8 = np.zeros(64); inv4 = np.zeros(16)
+    assert em.fbemul_nodal_extrap(inv8.ctypes.data_as(dp), inv4.ctypes.data_as(dp)) == 0
+    for et, mine in ((361, inv8), (342, inv4)):
+        ref = np.zeros(64)
+        ni = L.orc_nodal_extrapolation(et, ref.ctypes.data_as(dp))
+        assert np.abs(mine[:ni * ni] - ref[:ni * ni]).max() <= 1e-15 * np.abs(ref).max()
+        # an extrapolation matrix reproduces a field that is (tri)linear in the natural coordinates: rows sum to 1
+        assert np.allclose(mine[:ni * ni].reshape(ni, ni).sum(axis=1), 1.0, atol=1e-13)
+    rng = np.random.default_rng(2)
+    for trial in range(5):
+        s6 = rng.standard_normal(6) * 100
+        a, b = em.fbemul_mises(s6.ctypes.data_as(dp)), L.orc_get_mises(s6.ctypes.data_as(dp))
+        assert abs(a - b) <= 4e-16 * abs(b)      # FMA contraction of the two compilers
+
+
+def test_nodal_stress_kernels_run_on_the_host_equal_oracle():
+    """The post-processing kernels of update_3d / nodal_stress_3d (assembly.cuh: node incidence built by node_slot /
+    pos_elem / gather_count / gather_fill / gather_sort, node_gather3_kernel, nodal_stress_kernel, elem_stress_kernel,
+    mises_kernel) compiled UNCHANGED for the host (csrc/kernel_emul.hpp) and launched in the product's own sequence,
+    threads in a scrambled order, against the oracle's fstr_NodalStress3D: on a mesh that mixes 361 and 342 elements
+    with three sections, and on the two exA golden decks (whose results the golden logs pin).  Tolerance 1e-14: the
+    sums run in the same (ascending element) order as the reference's."""
+    from oracle import oracle as orc
+    import __graft_entry__ as g
+    from test_gpu_z_unvalidated import mixed_mesh
+    em = C.CDLL(g.build_emul())
+    dp, ipt = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    rng = np.random.default_rng(4)
+    cases = [(mixed_mesh(), None)]
+    for name in ("A361", "A342"):
+        mesh, A, meta, _ = util.oracle_solve_deck(name)
+        cases.append((mesh, (A.X.copy(), meta)))
+    for seed, (mesh, solved) in enumerate(cases):
+        u = solved[0] if solved else 1e-3 * rng.standard_normal(3 * mesh.n_node)
+        e, s, q = orc.update_linear(mesh, u)
+        ref = orc.nodal_stress_3d(mesh, e, s)
+        eni = np.ascontiguousarray(mesh.elem_node_index, np.int32); enn = np.ascontiguousarray(mesh.elem_node_item, np.int32)
+        eqf = rng.standard_normal(3 * len(enn))
+        out = dict(STRAIN=np.zeros((mesh.n_node, 6)), STRESS=np.zeros((mesh.n_node, 6)), MISES=np.zeros(mesh.n_node),
+                   ESTRAIN=np.zeros((mesh.n_elem, 6)), ESTRESS=np.zeros((mesh.n_elem, 6)), EMISES=np.zeros(mesh.n_elem))
+        qf = np.zeros(3 * mesh.n_node)
+        assert em.fbemul_nodal_pipeline(mesh.n_node, mesh.n_elem, eni.ctypes.data_as(ipt), enn.ctypes.data_as(ipt),
+                                        e.ctypes.data_as(dp), s.ctypes.data_as(dp), eqf.ctypes.data_as(dp), 100 + seed,
+                                        qf.ctypes.data_as(dp), *[out[k].ctypes.data_as(dp) for k in
+                                                                 ("STRAIN", "STRESS", "MISES", "ESTRAIN", "ESTRESS", "EMISES")]) == 0
+        for k in out:
+            assert np.abs(out[k] - ref[k]).max() <= 1e-14 * np.abs(ref[k]).max(), k
+        qref = np.zeros(3 * mesh.n_node)      # ascending-position (= ascending element) sum per node, like the kernel
+        for p in range(len(enn)):
+            qref[3 * (enn[p] - 1): 3 * enn[p]] += eqf[3 * p: 3 * p + 3]
+        assert np.array_equal(qf, qref)
+        if solved:
+            util.check_golden_stress(out, solved[1])
+
+
 def test_tl_element_emulation_equals_oracle():
     """The total-Lagrangian element code of the CUDA kernels (element_math.cuh: element_stiffness_tl_warp /
     element_update_tl_warp, run in lock step on the host) against the oracle's restatement of STF_C3 / STF_C3D8Bbar /
