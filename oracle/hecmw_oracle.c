@@ -1724,6 +1724,19 @@ void orc_UPDATE_C3_TL(int etype, int nn, const double *ecoord, const double *u, 
  * for ONE loading step of `substeps` equal sub-steps, no amplitude table, single subdomain.
  * Element option for 361: B-bar (the NLGEOM default) when sections[].elemopt361 == 2, full integration when 1.
  * Returns 0, or -1 "Fail to Converge", -2 unsupported element option, >0 solver code. */
+/* Gauss-point state [substep][2: strain, stress][n_elem][8][6] of the last orc_nlgeom_static run (for the nodal
+ * strain / stress lines of the exI golden logs) */
+static double *g_nl_state = NULL;
+static size_t g_nl_state_elems = 0;
+static int g_nl_state_steps = 0;
+int orc_nlgeom_fetch_state(int substep /* 1-based */, double *strain, double *stress) {
+  if (!g_nl_state || substep < 1 || substep > g_nl_state_steps) return -1;
+  const size_t n = g_nl_state_elems * 48;
+  memcpy(strain, g_nl_state + (size_t)(substep - 1) * 2 * n, sizeof(double) * n);
+  memcpy(stress, g_nl_state + (size_t)(substep - 1) * 2 * n + n, sizeof(double) * n);
+  return 0;
+}
+
 int orc_nlgeom_static(const orc_mesh *mesh, const orc_section *sections, orc_matrix *mat, int nbc,
                       const int *bc_node, const int *bc_dof, const double *bc_val, int ncl, const int *cl_node,
                       const int *cl_dof, const double *cl_val, int nsp, const int *sp_node, const int *sp_dof,
@@ -1736,6 +1749,9 @@ int orc_nlgeom_static(const orc_mesh *mesh, const orc_section *sections, orc_mat
   double *gstrain = calloc((size_t)n_elem * 8 * 6, sizeof(double)), *gstress = calloc((size_t)n_elem * 8 * 6, sizeof(double));
   int rc = 0, cg_total = 0;
   memset(unode, 0, sizeof(double) * n3);
+  free(g_nl_state);
+  g_nl_state = calloc((size_t)substeps * 2 * (size_t)n_elem * 48 + 1, sizeof(double));
+  g_nl_state_elems = (size_t)n_elem; g_nl_state_steps = substeps;
   double time = 0.0;
   const double dt = 1.0 / substeps; /* fstr_ctrl_common.f90:224 */
   for (int sub = 1; sub <= substeps && rc == 0; sub++) {
@@ -1851,6 +1867,11 @@ int orc_nlgeom_static(const orc_mesh *mesh, const orc_section *sections, orc_mat
     if (newton_iters) newton_iters[sub - 1] = iter;
     for (int i = 0; i < n3; i++) unode[i] += dunode[i];
     if (unode_steps) memcpy(unode_steps + (size_t)(sub - 1) * n3, unode, sizeof(double) * n3);
+    if (g_nl_state) {
+      const size_t n = (size_t)n_elem * 48;
+      memcpy(g_nl_state + (size_t)(sub - 1) * 2 * n, gstrain, sizeof(double) * n);
+      memcpy(g_nl_state + (size_t)(sub - 1) * 2 * n + n, gstress, sizeof(double) * n);
+    }
     time += dt;
   }
 #undef SPRING_K

@@ -137,6 +137,9 @@ int orc_nlgeom_static(const orc_mesh *mesh, const orc_section *sections, orc_mat
                       const double *sp_val, int substeps, double converg, int max_iter,
                       double *unode, double *unode_steps, int *newton_iters, int *cg_iters_total);
 
+/* Gauss-point strain / stress [n_elem][8][6] after sub-step `substep` (1-based) of the last orc_nlgeom_static run */
+int orc_nlgeom_fetch_state(int substep, double *strain, double *stress);
+
 /* ---- strain / stress recovery of the linear static analysis: fstr_UpdateNewton with
  * nlgeom_flag == INFINITE and fstr_NodalStress3D; pinned on the E / S / SMS lines (nodal and elemental) of every
  * golden log of examples/static/ex{A..G}.  strain / stress: [gp][6]; gp_* : [n_elem][8][6]. */

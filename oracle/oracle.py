@@ -259,6 +259,13 @@ def nlgeom_static(mesh, A, boundary, cload, substeps=10, converg=1.0e-3, max_ite
     return dict(error=rc, unode=un, unode_steps=steps, newton_iters=nit, cg_iters=cg.value)
 
 
+def nlgeom_state(mesh, substep: int):
+    """Gauss-point strain / stress [n_elem][8][6] after sub-step `substep` (1-based) of the last nlgeom_static run."""
+    e = np.zeros((mesh.n_elem, 8, 6)); s = np.zeros((mesh.n_elem, 8, 6))
+    assert lib().orc_nlgeom_fetch_state(int(substep), _dp(e), _dp(s)) == 0
+    return e, s
+
+
 def precond_clear():
     lib().orc_precond_clear()
 

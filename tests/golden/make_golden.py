@@ -239,6 +239,13 @@ def main():
         if log and "nlgeom" not in d:
             d["golden_stress"] = parse_log_stress(os.path.join(REF, log))
             assert len(d["golden_stress"]["node"]) == 13 and len(d["golden_stress"]["elem"]) == 13, name
+    # ... and of every sub-step of the nonlinear decks (Green-Lagrange strain / 2nd Piola-Kirchhoff stress of the
+    # total-Lagrangian update, through the same fstr_NodalStress3D)
+    for name in ("I361", "I342", "SB1"):
+        d = meta[name]
+        d["golden_stress_steps"] = [parse_log_stress(os.path.join(REF, d["source"]["log"]), k)
+                                    for k in range(1, d["nlgeom"]["substeps"] + 1)]
+        assert all(len(x["node"]) == 13 and len(x["elem"]) == 13 for x in d["golden_stress_steps"]), name
     with open(os.path.join(OUT, "golden.json"), "w") as f:
         json.dump(meta, f, indent=1)
     print("wrote", sorted(os.listdir(OUT)))

@@ -147,6 +147,7 @@ def patch_nonlinear(monkeypatch):
     monkeypatch.setattr(hecmw, "mat_upload", lambda A, values=True, rhs=True: None)
     monkeypatch.setattr(hecmw, "fstr_StiffMatrix_NL", stiff_nl)
     monkeypatch.setattr(hecmw, "fstr_UpdateNewton", update)
+    monkeypatch.setattr(hecmw, "fstr_NodalStress3D", lambda m: orc.nodal_stress_3d(m, st["e"], st["s"]))
     monkeypatch.setattr(hecmw, "hecmw_mat_ass_bc", ass_bc)
     monkeypatch.setattr(hecmw, "hecmw_solve", solve)
     return hecmw

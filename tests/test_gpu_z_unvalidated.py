@@ -64,6 +64,11 @@ def test_nlgeom_newton_matches_oracle_and_golden(gpu, name):
         for d, key in enumerate(("U1", "U2", "U3")):
             assert abs(U[:, d].max() - gold[key][0]) <= g["tolerance_abs"]
             assert abs(U[:, d].min() - gold[key][1]) <= g["tolerance_abs"]
+    # nodal / elemental strain, stress, von Mises of the final state (fstr_NodalStress3D on the device-resident
+    # Green-Lagrange strain / 2nd Piola-Kirchhoff stress) against the last block of the reference's log
+    if g.get("golden_stress_steps"):
+        out = gpu.fstr_NodalStress3D(mesh)
+        util.check_golden_stress(out, dict(golden_stress=g["golden_stress_steps"][-1], tolerance_abs=g["tolerance_abs"]))
 
 
 def test_tl_tangent_and_update_match_oracle_elementwise(gpu):

@@ -185,6 +185,11 @@ def test_nlgeom_newton_against_reference_logs(name):
             assert abs(U[:, d].max() - gold[key][0]) <= g["tolerance_abs"], (k, key)
             assert abs(U[:, d].min() - gold[key][1]) <= g["tolerance_abs"], (k, key)
             assert abs(U[:, d].min() - gold[key][1]) <= 6e-5 * max(abs(gold[key][1]), 1e-3)   # printed digits
+    # ... and the 26 strain / stress / von-Mises lines of every sub-step: Green-Lagrange strain and 2nd Piola-Kirchhoff
+    # stress of the restated total-Lagrangian update through the restated fstr_NodalStress3D
+    for k, gold in enumerate(g["golden_stress_steps"]):
+        e, s = orc.nlgeom_state(mesh, k + 1)
+        util.check_golden_stress(orc.nodal_stress_3d(mesh, e, s), dict(golden_stress=gold, tolerance_abs=g["tolerance_abs"]))
 
 
 def test_mooney_rivlin_is_the_derivative_of_its_energy():
