@@ -91,6 +91,56 @@ module hecmw_b200_if
       integer(c_int) :: elem_type_index(0:*), elem_type_item(*), elem_node_index(0:*), elem_node_item(*)
       integer(c_int) :: section_ID(*), sect_elemopt361(*)
     end function
+    ! ---- fstr_UpdateNewton (nlgeom_flag == INFINITE) + fstr_NodalStress3D: strain / stress recovery -------------
+    ! Arguments that may be absent are C pointers by value: pass c_loc(array) or c_null_ptr
+    ! (sect_alpha / temperature / temperature0: no !TEMPERATURE; QFORCE and any output of nodal_stress_3d: not wanted).
+    integer(c_int) function fistr_b200_update_3d(n_node, node, n_elem, n_elem_type, elem_type_index, &
+        elem_type_item, elem_node_index, elem_node_item, section_ID, n_sect, sect_elemopt361, sect_E, sect_nu, &
+        sect_alpha, unode, dunode, temperature, temperature0, ref_temp, QFORCE) bind(C, name="fistr_b200_update_3d")
+      import :: c_int, c_double, c_ptr
+      integer(c_int), value :: n_node, n_elem, n_elem_type, n_sect
+      real(c_double) :: node(*), sect_E(*), sect_nu(*), unode(*), dunode(*)
+      integer(c_int) :: elem_type_index(0:*), elem_type_item(*), elem_node_index(0:*), elem_node_item(*)
+      integer(c_int) :: section_ID(*), sect_elemopt361(*)
+      type(c_ptr), value :: sect_alpha, temperature, temperature0, QFORCE
+      real(c_double), value :: ref_temp
+    end function
+    integer(c_int) function fistr_b200_nodal_stress_3d(STRAIN, STRESS, MISES, ESTRAIN, ESTRESS, EMISES) &
+        bind(C, name="fistr_b200_nodal_stress_3d")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: STRAIN, STRESS, MISES, ESTRAIN, ESTRESS, EMISES   ! fstrSOLID%STRAIN(6*n_node) ... EMISES(n_elem)
+    end function
+
+    ! ---- geometrically nonlinear static (total Lagrangian): fstr_StiffMatrix / fstr_UpdateNewton under NLGEOM ---
+    integer(c_int) function fistr_b200_nl_state_reset(n_elem) bind(C, name="fistr_b200_nl_state_reset")
+      import :: c_int
+      integer(c_int), value :: n_elem
+    end function
+    integer(c_int) function fistr_b200_nl_state_download(strain, stress) bind(C, name="fistr_b200_nl_state_download")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: strain, stress          ! [n_elem][8][6] each, or c_null_ptr
+    end function
+    integer(c_int) function fistr_b200_nl_stiffmatrix_3d(n_node, node, n_elem, n_elem_type, elem_type_index, &
+        elem_type_item, elem_node_index, elem_node_item, section_ID, n_sect, sect_elemopt361, sect_E, sect_nu, &
+        sect_mtype, sect_hyper, u, D, AL, AU, time_ms) bind(C, name="fistr_b200_nl_stiffmatrix_3d")
+      import :: c_int, c_double, c_ptr
+      integer(c_int), value :: n_node, n_elem, n_elem_type, n_sect
+      real(c_double) :: node(*), sect_E(*), sect_nu(*), u(*), time_ms(2)
+      integer(c_int) :: elem_type_index(0:*), elem_type_item(*), elem_node_index(0:*), elem_node_item(*)
+      integer(c_int) :: section_ID(*), sect_elemopt361(*)
+      type(c_ptr), value :: sect_mtype, sect_hyper, D, AL, AU   ! c_null_ptr: all elastic / matrix stays on the device
+    end function
+    integer(c_int) function fistr_b200_nl_update_3d(n_node, node, n_elem, n_elem_type, elem_type_index, &
+        elem_type_item, elem_node_index, elem_node_item, section_ID, n_sect, sect_elemopt361, sect_E, sect_nu, &
+        sect_mtype, sect_hyper, unode, dunode, QFORCE) bind(C, name="fistr_b200_nl_update_3d")
+      import :: c_int, c_double, c_ptr
+      integer(c_int), value :: n_node, n_elem, n_elem_type, n_sect
+      real(c_double) :: node(*), sect_E(*), sect_nu(*), unode(*), dunode(*), QFORCE(*)
+      integer(c_int) :: elem_type_index(0:*), elem_type_item(*), elem_node_index(0:*), elem_node_item(*)
+      integer(c_int) :: section_ID(*), sect_elemopt361(*)
+      type(c_ptr), value :: sect_mtype, sect_hyper
+    end function
+
     integer(c_int) function fistr_b200_mat_ass_bc(nbc, inode, idof, rhs) bind(C, name="fistr_b200_mat_ass_bc")
       import :: c_int, c_double
       integer(c_int), value :: nbc

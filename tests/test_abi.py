@@ -69,3 +69,36 @@ def test_fortran_interface_matches_header():
     names = set(re.findall(r'bind\(C,\s*name="(fistr_b200_\w+)"\)', txt))
     assert len(names) >= 18
     assert names <= set(declared_symbols())
+
+
+def test_fortran_interface_argument_lists_match_header():
+    """Arity and value/reference passing of every bind(C) interface in integration/hecmw_b200_if.f90 against the C
+    prototype: a C scalar (int, double, int64_t) must be `value` in Fortran, a C pointer must NOT be (or be a
+    `type(c_ptr), value`).  Stands in for the Fortran compiler this image does not have."""
+    h = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "fistr_b200.h")).read(), flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|int64_t|const char \*)\s*(fistr_b200_\w+)\s*\(([^;]*?)\)\s*;", h, flags=re.S):
+        args = [a.strip() for a in m.group(2).replace("\n", " ").split(",")]
+        if args == ["void"]:
+            args = []
+        protos[m.group(1)] = ["*" in a or "[" in a for a in args]          # True = pointer
+    f = open(os.path.join(ROOT, "integration", "hecmw_b200_if.f90")).read()
+    f = re.sub(r"!.*", "", f)
+    f = re.sub(r"&\s*\n\s*", " ", f)
+    checked = 0
+    for m in re.finditer(r"function\s+(fistr_b200_\w+)\s*\(([^)]*)\)\s*bind\(C[^\n]*\n(.*?)end function", f, flags=re.S | re.I):
+        name, dummies, body = m.group(1), [a.strip().lower() for a in m.group(2).split(",") if a.strip()], m.group(3)
+        assert name in protos, name
+        assert len(dummies) == len(protos[name]), (name, len(dummies), len(protos[name]))
+        by_value = set()
+        for line in body.splitlines():
+            if "::" in line and re.search(r",\s*value", line.split("::")[0], flags=re.I):
+                is_cptr = "c_ptr" in line.split("::")[0].lower()
+                for v in re.split(r",(?![^()]*\))", line.split("::")[1]):
+                    by_value.add((re.sub(r"\(.*", "", v).strip().lower(), is_cptr))
+        for dname, is_ptr in zip(dummies, protos[name]):
+            val = (dname, False) in by_value
+            cptr = (dname, True) in by_value
+            assert (is_ptr and (cptr or not val)) or (not is_ptr and val and not cptr), (name, dname, is_ptr, val, cptr)
+        checked += 1
+    assert checked >= 24
