@@ -9,7 +9,7 @@
 // structure into slot[e*nn*nn + i*nn + j].
 #pragma once
 #ifdef FB_EMUL_KERNELS
-#include "kernel_emul.hpp"   // TEST-ONLY host stand-in (libfistr_b200_emul.so); the warp-cooperative kernels are left out
+#include "kernel_emul.hpp"   // TEST-ONLY host stand-in (libfistr_b200_emul.so): the kernels below run on host threads
 #else
 #include "common.cuh"
 #endif
@@ -107,7 +107,6 @@ gather_sum_kernel(size_t nblk, const unsigned *__restrict__ gptr, const unsigned
   }
 }
 
-#ifndef FB_EMUL_KERNELS   // warp-cooperative kernels (shuffles, shared memory): device only
 // One element per warp.  sect[3*s..] = D11, D12, D44 of section s; sect_form[s] = elemopt361.
 // ICINV (IC element only): calInverse in registers + shuffles (1) or through shared memory (0), see element_math.cuh.
 template <int FORM, int WARPS, int ICINV = 1>
@@ -122,7 +121,7 @@ stiff_kernel(int e0, int e1, const int *__restrict__ elem_node_index, const int 
   constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
   constexpr int NB = NN * NN;
   constexpr int ROUNDS = (NB + 31) / 32;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FB_DYNAMIC_SMEM(smem_raw);
   Scratch &S = reinterpret_cast<Scratch *>(smem_raw)[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const int wg = blockIdx.x * WARPS + (threadIdx.x >> 5);
@@ -189,7 +188,7 @@ stiff_kernel(int e0, int e1, const int *__restrict__ elem_node_index, const int 
 // (api_assembly.inc: ic_inverse_mode) uses the register/shuffle kernel only if the two agree to rounding.
 __global__ void __launch_bounds__(32) ic_selftest_kernel(double *__restrict__ out) {
   using namespace elem;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FB_DYNAMIC_SMEM(smem_raw);
   Scratch &S = *reinterpret_cast<Scratch *>(smem_raw);
   const int lane = threadIdx.x & 31;
   double D11, D12, D44;
@@ -241,7 +240,7 @@ stiff_tl_kernel(int e0, int e1, const int *__restrict__ elem_node_index, const i
   constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
   constexpr int NB = NN * NN;
   constexpr int ROUNDS = (NB + 31) / 32;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FB_DYNAMIC_SMEM(smem_raw);
   ScratchTL &S = reinterpret_cast<ScratchTL *>(smem_raw)[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const int wg = blockIdx.x * WARPS + (threadIdx.x >> 5);
@@ -302,7 +301,7 @@ update_tl_kernel(int e0, int e1, const int *__restrict__ elem_node_index, const 
                  double *__restrict__ gp_strain, double *__restrict__ gp_stress, double *__restrict__ qforce) {
   using namespace elem;
   constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FB_DYNAMIC_SMEM(smem_raw);
   ScratchTL &S = reinterpret_cast<ScratchTL *>(smem_raw)[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const int wg = blockIdx.x * WARPS + (threadIdx.x >> 5);
@@ -339,7 +338,7 @@ update_lin_kernel(int e0, int e1, const int *__restrict__ elem_node_index, const
                   double *__restrict__ gp_strain, double *__restrict__ gp_stress, double *__restrict__ eqf) {
   using namespace elem;
   constexpr int NN = (FORM == FORM_TET10) ? 10 : 8;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FB_DYNAMIC_SMEM(smem_raw);
   ScratchTL &S = reinterpret_cast<ScratchTL *>(smem_raw)[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const int wg = blockIdx.x * WARPS + (threadIdx.x >> 5);
@@ -374,7 +373,7 @@ update_ic_kernel(int e0, int e1, const int *__restrict__ elem_node_index, const 
                  const double *__restrict__ temp, const double *__restrict__ temp0, double ref_temp,
                  double *__restrict__ gp_strain, double *__restrict__ gp_stress, double *__restrict__ eqf) {
   using namespace elem;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FB_DYNAMIC_SMEM(smem_raw);
   Scratch &S = reinterpret_cast<Scratch *>(smem_raw)[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const int wg = blockIdx.x * WARPS + (threadIdx.x >> 5);
@@ -400,8 +399,6 @@ update_ic_kernel(int e0, int e1, const int *__restrict__ elem_node_index, const 
     __syncwarp();
   }
 }
-
-#endif   // !FB_EMUL_KERNELS
 
 // ---- node incidence (topology only): node -> the positions p in elem_node_item that name it, ascending --------
 // Built with the gather_count / gather_fill / gather_sort kernels above from nslot[p] = elem_node_item[p] - 1.

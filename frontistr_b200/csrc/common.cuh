@@ -10,6 +10,9 @@
 
 namespace fb {
 
+// dynamic shared memory of a kernel (the TEST-ONLY host stand-in kernel_emul.hpp maps it to a host buffer)
+#define FB_DYNAMIC_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+
 constexpr int kWarp = 32;
 constexpr int kNumSM = 148;  // B200: 2 dies x 74 SMs (queried at init; this is the sizing default)
 

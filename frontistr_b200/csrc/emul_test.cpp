@@ -46,6 +46,22 @@ static void run_warp(F f) {   // f(lane) on 32 threads in lock step
 }
 } }
 
+// kernel<<<grid, warps*32, smem>>>(args...) for the one-element-per-warp kernels: every warp of every block by 32 host
+// threads in lock step, warps one after the other (the warps of these kernels never talk to each other)
+template <class K, class... A>
+static void emul_launch_warps(unsigned grid, unsigned warps, size_t smem_bytes, K kernel, A... args) {
+  std::vector<unsigned char> buf(smem_bytes + 64);
+  unsigned char *smem = buf.data() + (16 - reinterpret_cast<uintptr_t>(buf.data()) % 16) % 16;
+  fb::emul_smem() = smem;
+  for (unsigned b = 0; b < grid; b++)
+    for (unsigned w = 0; w < warps; w++)
+      fb::emulwarp::run_warp([&](int lane) {
+        fb::gridDim.x = grid; fb::blockDim.x = warps * 32; fb::blockIdx.x = b; fb::threadIdx.x = w * 32 + (unsigned)lane;
+        kernel(args...);
+      });
+  fb::emul_smem() = nullptr;
+}
+
 // calInverse(9) exactly as the CUDA warp executes it (same source: element_math.cuh ic_inverse_warp)
 static void emul_inverse_warp(Scratch &S) {
   fb::emulwarp::run_warp([&S](int lane) { ic_inverse_warp(lane, S); });
@@ -203,6 +219,236 @@ int fbemul_nodal_pipeline(int n_node, int n_elem, const int *elem_node_index, co
   emul_launch(5, 64, seed + 7, elem_stress_kernel, n_elem, elem_node_index, gp_strain, gp_stress, ESTRAIN, ESTRESS);
   emul_launch(2, 64, seed + 8, mises_kernel, (size_t)n_node, (const double *)STRESS, MISES);
   emul_launch(2, 64, seed + 9, mises_kernel, (size_t)n_elem, (const double *)ESTRESS, EMISES);
+  return 0;
+}
+
+static int nn_of(int etype) { return etype == 342 ? 10 : 8; }
+
+// fistr_b200_stiffmatrix_3d on the host: the SAME kernels in the SAME launch sequence as api_assembly.inc
+// (slot_build_kernel; stiff_kernel<FORM> per element-type block and formulation; gather map + gather_sum_kernel, or the
+// atomic scatter) through kernel_emul.hpp.  vals = [ D | AL | AU ].  Returns the slot-table error flag.
+int fbemul_stiffmatrix(int n_node, const double *node, int n_elem, int n_elem_type, const int *elem_type_index,
+                       const int *elem_type_item, const int *elem_node_index, const int *elem_node_item,
+                       const int *section_ID, int n_sect, const int *sect_form, const double *sect_E, const double *sect_nu,
+                       int NP, int NPL, int NPU, const int *indexL, const int *itemL, const int *indexU, const int *itemU,
+                       int gather, int icinv, double *vals) {
+  using namespace fb;
+  (void)n_node;
+  std::vector<size_t> slot_base((size_t)n_elem_type + 1, 0);
+  for (int it = 0; it < n_elem_type; it++) {
+    const int nn = nn_of(elem_type_item[it]);
+    slot_base[it + 1] = slot_base[it] + (size_t)(elem_type_index[it + 1] - elem_type_index[it]) * nn * nn;
+  }
+  const size_t ncontrib = slot_base.back(), nblk = (size_t)NP + NPL + NPU;
+  std::vector<unsigned> slot(ncontrib);
+  std::vector<double> sectD(3 * (size_t)n_sect), ke(gather ? 9 * ncontrib : 1);
+  for (int s = 0; s < n_sect; s++) elastic_constants(sect_E[s], sect_nu[s], sectD[3 * s], sectD[3 * s + 1], sectD[3 * s + 2]);
+  int err = 0;
+  for (int it = 0; it < n_elem_type; it++) {
+    const int nn = nn_of(elem_type_item[it]), e0 = elem_type_index[it], e1 = elem_type_index[it + 1];
+    if (e1 > e0)
+      emul_launch(3, 64, 7u + it, slot_build_kernel, e0, e1, nn, elem_node_index, elem_node_item, NP, NPL, indexL, itemL, indexU,
+                  itemU, slot.data(), slot_base[it], &err);
+  }
+  std::fill(vals, vals + 9 * nblk, 0.0);
+  constexpr int WARPS = 4;
+  const size_t smem = sizeof(Scratch) * WARPS;
+  double *ke_out = gather ? ke.data() : nullptr;
+  for (int it = 0; it < n_elem_type; it++) {
+    const int e0 = elem_type_index[it], e1 = elem_type_index[it + 1];
+    if (e1 <= e0) continue;
+#define FB_ARGS e0, e1, elem_node_index, elem_node_item, node, section_ID, (const double *)sectD.data(), sect_form, \
+                (const unsigned *)slot.data(), slot_base[it], vals, ke_out, 0
+    if (elem_type_item[it] == 342) emul_launch_warps(2, WARPS, smem, stiff_kernel<FORM_TET10, WARPS, 1>, FB_ARGS);
+    else {
+      bool has[4] = {false, false, false, false};
+      for (int s = 0; s < n_sect; s++) has[sect_form[s]] = true;
+      if (has[3]) {
+        if (icinv) emul_launch_warps(2, WARPS, smem, stiff_kernel<FORM_IC, WARPS, 1>, FB_ARGS);
+        else emul_launch_warps(2, WARPS, smem, stiff_kernel<FORM_IC, WARPS, 0>, FB_ARGS);
+      }
+      if (has[1]) emul_launch_warps(2, WARPS, smem, stiff_kernel<FORM_FI, WARPS, 1>, FB_ARGS);
+      if (has[2]) emul_launch_warps(2, WARPS, smem, stiff_kernel<FORM_BBAR, WARPS, 1>, FB_ARGS);
+    }
+#undef FB_ARGS
+  }
+  if (gather) {
+    std::vector<unsigned> cursor(nblk + 1, 0u), gptr(nblk + 1, 0u), gsrc(ncontrib);
+    emul_launch(3, 64, 21, gather_count_kernel, ncontrib, (const unsigned *)slot.data(), cursor.data());
+    for (size_t i = 0; i < nblk; i++) gptr[i + 1] = gptr[i] + cursor[i];
+    std::fill(cursor.begin(), cursor.end(), 0u);
+    emul_launch(3, 64, 22, gather_fill_kernel, ncontrib, (const unsigned *)slot.data(), (const unsigned *)gptr.data(), cursor.data(), gsrc.data());
+    emul_launch(3, 64, 23, gather_sort_kernel, nblk, (const unsigned *)gptr.data(), gsrc.data());
+    emul_launch(4, 64, 24, gather_sum_kernel, nblk, (const unsigned *)gptr.data(), (const unsigned *)gsrc.data(), (const double *)ke.data(), vals);
+  }
+  return err;
+}
+
+// fistr_b200_update_3d + fistr_b200_nodal_stress_3d on the host: update_lin_kernel / update_ic_kernel per block and
+// formulation, node incidence, QFORCE gather, nodal / elemental strain, stress, von Mises — the launch sequence of
+// api_assembly.inc.  sect_alpha / temp / temp0 may be NULL.
+int fbemul_update_pipeline(int n_node, const double *node, int n_elem, int n_elem_type, const int *elem_type_index,
+                           const int *elem_type_item, const int *elem_node_index, const int *elem_node_item,
+                           const int *section_ID, int n_sect, const int *sect_form, const double *sect_E, const double *sect_nu,
+                           const double *sect_alpha, const double *utot, const double *temp, const double *temp0,
+                           double ref_temp, int icinv, double *gp_strain, double *gp_stress, double *QFORCE, double *STRAIN,
+                           double *STRESS, double *MISES, double *ESTRAIN, double *ESTRESS, double *EMISES) {
+  using namespace fb;
+  const size_t nconn = (size_t)elem_node_index[n_elem];
+  std::vector<double> sectD(3 * (size_t)n_sect), eqf(3 * nconn, 0.0);
+  for (int s = 0; s < n_sect; s++) elastic_constants(sect_E[s], sect_nu[s], sectD[3 * s], sectD[3 * s + 1], sectD[3 * s + 2]);
+  constexpr int WL = 2, WI = 4;
+  for (int it = 0; it < n_elem_type; it++) {
+    const int e0 = elem_type_index[it], e1 = elem_type_index[it + 1];
+    if (e1 <= e0) continue;
+#define FB_ARGS e0, e1, elem_node_index, elem_node_item, node, utot, section_ID, (const double *)sectD.data(), sect_alpha, \
+                sect_form, temp, temp0, ref_temp, gp_strain, gp_stress, eqf.data()
+    if (elem_type_item[it] == 342) emul_launch_warps(2, WL, sizeof(ScratchTL) * WL, update_lin_kernel<FORM_TET10, WL>, FB_ARGS);
+    else {
+      bool has[4] = {false, false, false, false};
+      for (int s = 0; s < n_sect; s++) has[sect_form[s]] = true;
+      if (has[3]) {
+        if (icinv) emul_launch_warps(2, WI, sizeof(Scratch) * WI, update_ic_kernel<WI, 1>, FB_ARGS);
+        else emul_launch_warps(2, WI, sizeof(Scratch) * WI, update_ic_kernel<WI, 0>, FB_ARGS);
+      }
+      if (has[1]) emul_launch_warps(2, WL, sizeof(ScratchTL) * WL, update_lin_kernel<FORM_FI, WL>, FB_ARGS);
+      if (has[2]) emul_launch_warps(2, WL, sizeof(ScratchTL) * WL, update_lin_kernel<FORM_BBAR, WL>, FB_ARGS);
+    }
+#undef FB_ARGS
+  }
+  return fbemul_nodal_pipeline(n_node, n_elem, elem_node_index, elem_node_item, gp_strain, gp_stress, eqf.data(), 55u, QFORCE,
+                               STRAIN, STRESS, MISES, ESTRAIN, ESTRESS, EMISES);
+}
+
+// fistr_b200_nl_stiffmatrix_3d / fistr_b200_nl_update_3d on the host (stiff_tl_kernel / update_tl_kernel, launch
+// sequence of api_assembly.inc).  sect_mtype / sect_hyper may be NULL.  gp_strain / gp_stress: [n_elem][8][6] state.
+static std::vector<MatlTL> make_matls(int n_sect, const double *sect_E, const double *sect_nu, const int *sect_mtype,
+                                      const double *sect_hyper) {
+  std::vector<MatlTL> ml((size_t)n_sect);
+  for (int s = 0; s < n_sect; s++) ml[s] = make_matl(sect_mtype ? sect_mtype[s] : 0, sect_E[s], sect_nu[s], sect_hyper ? sect_hyper + 3 * s : nullptr);
+  return ml;
+}
+int fbemul_nl_stiffmatrix(int n_node, const double *node, int n_elem, int n_elem_type, const int *elem_type_index,
+                          const int *elem_type_item, const int *elem_node_index, const int *elem_node_item,
+                          const int *section_ID, int n_sect, const int *sect_form, const double *sect_E, const double *sect_nu,
+                          const int *sect_mtype, const double *sect_hyper, const double *u, const double *gp_strain,
+                          const double *gp_stress, int NP, int NPL, int NPU, const int *indexL, const int *itemL,
+                          const int *indexU, const int *itemU, int gather, double *vals) {
+  using namespace fb;
+  (void)n_node; (void)n_elem;
+  std::vector<size_t> slot_base((size_t)n_elem_type + 1, 0);
+  for (int it = 0; it < n_elem_type; it++) {
+    const int nn = nn_of(elem_type_item[it]);
+    slot_base[it + 1] = slot_base[it] + (size_t)(elem_type_index[it + 1] - elem_type_index[it]) * nn * nn;
+  }
+  const size_t ncontrib = slot_base.back(), nblk = (size_t)NP + NPL + NPU;
+  std::vector<unsigned> slot(ncontrib);
+  std::vector<double> ke(gather ? 9 * ncontrib : 1);
+  const std::vector<MatlTL> ml = make_matls(n_sect, sect_E, sect_nu, sect_mtype, sect_hyper);
+  int err = 0;
+  for (int it = 0; it < n_elem_type; it++) {
+    const int nn = nn_of(elem_type_item[it]), e0 = elem_type_index[it], e1 = elem_type_index[it + 1];
+    if (e1 > e0)
+      emul_launch(3, 64, 7u + it, slot_build_kernel, e0, e1, nn, elem_node_index, elem_node_item, NP, NPL, indexL, itemL, indexU,
+                  itemU, slot.data(), slot_base[it], &err);
+  }
+  std::fill(vals, vals + 9 * nblk, 0.0);
+  constexpr int WARPS = 2;
+  const size_t smem = sizeof(ScratchTL) * WARPS;
+  double *ke_out = gather ? ke.data() : nullptr;
+  for (int it = 0; it < n_elem_type; it++) {
+    const int e0 = elem_type_index[it], e1 = elem_type_index[it + 1];
+    if (e1 <= e0) continue;
+#define FB_ARGS e0, e1, elem_node_index, elem_node_item, node, u, section_ID, (const MatlTL *)ml.data(), sect_form, gp_strain, \
+                gp_stress, (const unsigned *)slot.data(), slot_base[it], vals, ke_out
+    if (elem_type_item[it] == 342) emul_launch_warps(2, WARPS, smem, stiff_tl_kernel<FORM_TET10, WARPS>, FB_ARGS);
+    else {
+      bool has[4] = {false, false, false, false};
+      for (int s = 0; s < n_sect; s++) has[sect_form[s]] = true;
+      if (has[1]) emul_launch_warps(2, WARPS, smem, stiff_tl_kernel<FORM_FI, WARPS>, FB_ARGS);
+      if (has[2]) emul_launch_warps(2, WARPS, smem, stiff_tl_kernel<FORM_BBAR, WARPS>, FB_ARGS);
+    }
+#undef FB_ARGS
+  }
+  if (gather) {
+    std::vector<unsigned> cursor(nblk + 1, 0u), gptr(nblk + 1, 0u), gsrc(ncontrib);
+    emul_launch(3, 64, 21, gather_count_kernel, ncontrib, (const unsigned *)slot.data(), cursor.data());
+    for (size_t i = 0; i < nblk; i++) gptr[i + 1] = gptr[i] + cursor[i];
+    std::fill(cursor.begin(), cursor.end(), 0u);
+    emul_launch(3, 64, 22, gather_fill_kernel, ncontrib, (const unsigned *)slot.data(), (const unsigned *)gptr.data(), cursor.data(), gsrc.data());
+    emul_launch(3, 64, 23, gather_sort_kernel, nblk, (const unsigned *)gptr.data(), gsrc.data());
+    emul_launch(4, 64, 24, gather_sum_kernel, nblk, (const unsigned *)gptr.data(), (const unsigned *)gsrc.data(), (const double *)ke.data(), vals);
+  }
+  return err;
+}
+int fbemul_nl_update(int n_node, const double *node, int n_elem, int n_elem_type, const int *elem_type_index,
+                     const int *elem_type_item, const int *elem_node_index, const int *elem_node_item, const int *section_ID,
+                     int n_sect, const int *sect_form, const double *sect_E, const double *sect_nu, const int *sect_mtype,
+                     const double *sect_hyper, const double *utot, double *gp_strain, double *gp_stress, double *QFORCE) {
+  using namespace fb;
+  (void)n_elem;
+  const std::vector<MatlTL> ml = make_matls(n_sect, sect_E, sect_nu, sect_mtype, sect_hyper);
+  std::fill(QFORCE, QFORCE + 3 * (size_t)n_node, 0.0);
+  constexpr int WARPS = 2;
+  const size_t smem = sizeof(ScratchTL) * WARPS;
+  for (int it = 0; it < n_elem_type; it++) {
+    const int e0 = elem_type_index[it], e1 = elem_type_index[it + 1];
+    if (e1 <= e0) continue;
+#define FB_ARGS e0, e1, elem_node_index, elem_node_item, node, utot, section_ID, (const MatlTL *)ml.data(), sect_form, gp_strain, \
+                gp_stress, QFORCE
+    if (elem_type_item[it] == 342) emul_launch_warps(2, WARPS, smem, update_tl_kernel<FORM_TET10, WARPS>, FB_ARGS);
+    else {
+      bool has[4] = {false, false, false, false};
+      for (int s = 0; s < n_sect; s++) has[sect_form[s]] = true;
+      if (has[1]) emul_launch_warps(2, WARPS, smem, update_tl_kernel<FORM_FI, WARPS>, FB_ARGS);
+      if (has[2]) emul_launch_warps(2, WARPS, smem, update_tl_kernel<FORM_BBAR, WARPS>, FB_ARGS);
+    }
+#undef FB_ARGS
+  }
+  return 0;
+}
+
+// fistr_b200_mat_ass_bc on the host: bc_kernel<0>, bc_kernel<1>, bc_set_rhs_kernel as api_assembly.inc launches them
+int fbemul_mat_ass_bc(int nbc, const int *inode, const int *idof, const double *rhs, int NP, int NPL, const int *indexL,
+                      const int *itemL, const int *indexU, const int *itemU, double *vals, double *B) {
+  using namespace fb;
+  std::vector<int> nodes, dofs, ptr(1, 0);
+  std::vector<double> v;
+  for (int c = 0; c < nbc; c++) {
+    if (idof[c] > 3) continue;
+    const int n = inode[c];
+    nodes.push_back(n); dofs.push_back(idof[c]); v.push_back(rhs[c]);
+    ptr.push_back(ptr.back() + 1 + (indexL[n] - indexL[n - 1]) + (indexU[n] - indexU[n - 1]));
+  }
+  const int m = (int)nodes.size();
+  if (m == 0) return 0;
+  emul_launch(3, 64, 31, bc_kernel<0>, m, (const int *)nodes.data(), (const int *)dofs.data(), (const double *)v.data(),
+              (const int *)ptr.data(), NP, NPL, indexL, itemL, indexU, itemU, vals, B);
+  emul_launch(3, 64, 32, bc_kernel<1>, m, (const int *)nodes.data(), (const int *)dofs.data(), (const double *)v.data(),
+              (const int *)ptr.data(), NP, NPL, indexL, itemL, indexU, itemU, vals, B);
+  emul_launch((unsigned)(m + 63) / 64, 64, 33, bc_set_rhs_kernel, m, (const int *)nodes.data(), (const int *)dofs.data(),
+              (const double *)v.data(), B);
+  return 0;
+}
+
+// number of misaligned double2 accesses seen so far by the emulated kernels (must stay 0), and a negative control
+long fbemul_misaligned_count(void) { return emul_misaligned_count(); }
+long fbemul_misaligned_probe(void) {
+  alignas(16) double buf[6] = {1, 2, 3, 4, 5, 6};
+  const long before = emul_misaligned_count();
+  double2 *good = reinterpret_cast<double2 *>(buf), *bad = reinterpret_cast<double2 *>(buf + 1);
+  good[1] = good[0];           // aligned: not counted
+  volatile double sink = good[1].x;
+  (void)sink;
+  bad[1] = bad[0];             // 8-byte aligned only: counted (source and destination)
+  const long seen = emul_misaligned_count() - before;
+  emul_misaligned_count() = before;
+  return seen;
+}
+
+// the device self-test of the two calInverse implementations (assembly.cuh: ic_selftest_kernel): out[0] max diff, out[1] max entry
+int fbemul_ic_selftest(double *out) {
+  emul_launch_warps(1, 1, sizeof(Scratch), fb::ic_selftest_kernel, out);
   return 0;
 }
 

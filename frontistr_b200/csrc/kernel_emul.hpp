@@ -1,8 +1,12 @@
 // TEST-ONLY stand-in for the CUDA execution model, used when assembly.cuh is compiled by g++ into
-// libfistr_b200_emul.so (FB_EMUL_KERNELS): lets the grid-stride kernels that have no intra-block cooperation
-// (slot / gather maps, node incidence, nodal stress ...) run UNCHANGED on the host, one "thread" after the other in
-// a scrambled order, so their index arithmetic is exercised by the CPU unit tests without a GPU.  The product
-// library never sees this header.
+// libfistr_b200_emul.so (FB_EMUL_KERNELS).  Two launchers:
+//   emul_launch       : grid-stride kernels without intra-block cooperation (slot / gather maps, node incidence, nodal
+//                       stress ...) run UNCHANGED, one "thread" after the other in a scrambled order;
+//   emul_launch_warps : the one-element-per-warp kernels (stiff / update / self-test) run UNCHANGED, every warp by 32
+//                       host threads in lock step (__syncwarp / shuffles = barriers, emul_test.cpp), warps one after
+//                       the other, dynamic shared memory = a host buffer per block
+// so that the kernels' own index arithmetic, staging and store patterns are exercised by the CPU unit tests without
+// a GPU.  The product library never sees this header.
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
@@ -19,15 +23,42 @@
 #define __launch_bounds__(...)
 #define __restrict__
 
+// CUDA's 16-byte vector of two doubles.  Every copy checks that both addresses are 16-byte aligned (a misaligned
+// double2 access is a hardware fault on the GPU: "misaligned address"); violations are counted, never ignored.
+inline long &emul_misaligned_count() { static long n = 0; return n; }
+struct alignas(16) double2 {
+  double x, y;
+  double2() = default;
+  double2(const double2 &o) { check(&o); x = o.x; y = o.y; }
+  double2 &operator=(const double2 &o) { check(this); check(&o); x = o.x; y = o.y; return *this; }
+  static void check(const void *p) { if (reinterpret_cast<uintptr_t>(p) % 16 != 0) __atomic_fetch_add(&emul_misaligned_count(), 1L, __ATOMIC_RELAXED); }
+};
+
 namespace fb {
+namespace emulwarp {   // lock-step warp collectives, defined in emul_test.cpp
+double shfl(double v, int src);
+int shfl(int v, int src);
+void syncwarp();
+}
 constexpr int kWarp = 32;
 struct EmulDim { unsigned x = 1, y = 1, z = 1; };
 inline thread_local EmulDim threadIdx, blockIdx, blockDim, gridDim;
 
-inline unsigned atomicAdd(unsigned *p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }
-inline int atomicAdd(int *p, int v) { const int o = *p; *p = o + v; return o; }
-inline double atomicAdd(double *p, double v) { const double o = *p; *p = o + v; return o; }
-inline int atomicExch(int *p, int v) { const int o = *p; *p = v; return o; }
+// real atomics: the lanes of an emulated warp are concurrent host threads
+inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline double atomicAdd(double *p, double v) {
+  uint64_t *q = reinterpret_cast<uint64_t *>(p), o = __atomic_load_n(q, __ATOMIC_RELAXED), n;
+  double od, nd;
+  do { __builtin_memcpy(&od, &o, 8); nd = od + v; __builtin_memcpy(&n, &nd, 8); }
+  while (!__atomic_compare_exchange_n(q, &o, n, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+  return od;
+}
+inline int atomicExch(int *p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
+inline unsigned char *&emul_smem() { static unsigned char *p = nullptr; return p; }   // dynamic shared memory of the running block
+#define FB_DYNAMIC_SMEM(name) unsigned char *name = fb::emul_smem()
+inline void __syncwarp() { emulwarp::syncwarp(); }
+inline double __shfl_xor_sync(unsigned, double v, int o) { return emulwarp::shfl(v, (int)((threadIdx.x & 31) ^ (unsigned)o)); }
 inline double ld_stream(const double *p) { return *p; }
 inline int ld_stream(const int *p) { return *p; }
 

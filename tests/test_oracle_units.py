@@ -298,6 +298,96 @@ def test_nodal_stress_kernels_run_on_the_host_equal_oracle():
             util.check_golden_stress(out, solved[1])
 
 
+def _emul_mesh_args(mesh):
+    ipt, dpt = C.POINTER(C.c_int), C.POINTER(C.c_double)
+    a = dict(eti=np.ascontiguousarray(mesh.elem_type_index, np.int32), ett=np.ascontiguousarray(mesh.elem_type_item, np.int32),
+             eni=np.ascontiguousarray(mesh.elem_node_index, np.int32), enn=np.ascontiguousarray(mesh.elem_node_item, np.int32),
+             sec=np.ascontiguousarray(mesh.section_ID, np.int32), node=np.ascontiguousarray(mesh.node, np.float64),
+             form=np.array([s["elemopt361"] for s in mesh.sections], np.int32),
+             E=np.array([s["E"] for s in mesh.sections], np.float64), nu=np.array([s["nu"] for s in mesh.sections], np.float64))
+    args = (mesh.n_node, a["node"].ctypes.data_as(dpt), mesh.n_elem, mesh.n_elem_type, a["eti"].ctypes.data_as(ipt),
+            a["ett"].ctypes.data_as(ipt), a["eni"].ctypes.data_as(ipt), a["enn"].ctypes.data_as(ipt), a["sec"].ctypes.data_as(ipt),
+            len(mesh.sections), a["form"].ctypes.data_as(ipt), a["E"].ctypes.data_as(dpt), a["nu"].ctypes.data_as(dpt))
+    return a, args
+
+
+def test_assembly_kernels_run_on_the_host_equal_oracle():
+    """fistr_b200_stiffmatrix_3d end to end on the HOST: slot_build_kernel, stiff_kernel<IC/FI/BBAR/TET10> (every warp
+    by 32 lock-step host threads, dynamic shared memory = a host buffer, shuffles and __syncwarp = barriers), the
+    gather map and gather_sum_kernel — or the atomic scatter — compiled UNCHANGED from assembly.cuh through
+    csrc/kernel_emul.hpp and launched in the product's own sequence.  K against the oracle to 1e-13 for both calInverse
+    variants of the IC kernel, gather and scatter; every double2 access of the kernels is checked for 16-byte
+    alignment (the fault class that took the GPUs down in round 1) with a negative control of the checker."""
+    from oracle import oracle as orc
+    import __graft_entry__ as g
+    from test_gpu_z_unvalidated import mixed_mesh
+    em = C.CDLL(g.build_emul())
+    em.fbemul_misaligned_count.restype = C.c_long; em.fbemul_misaligned_probe.restype = C.c_long
+    ipt, dpt = C.POINTER(C.c_int), C.POINTER(C.c_double)
+    assert em.fbemul_misaligned_probe() == 2          # the checker sees a misaligned source and destination
+    meshes = [util.distort(meshgen.hex_cube(3)), meshgen.tet10_cube(2), mixed_mesh(), meshgen.hex_cube(2, nx=5, ny=1, nz=1)]
+    for mesh in meshes:
+        Ao = orc.mat_con(mesh)
+        orc.stiffmatrix(mesh, Ao)
+        ref = np.concatenate([Ao.D, Ao.AL, Ao.AU])
+        keep, args = _emul_mesh_args(mesh)
+        for gather, icinv in ((1, 1), (1, 0), (0, 1)):
+            vals = np.zeros_like(ref)
+            rc = em.fbemul_stiffmatrix(*args, Ao.NP, Ao.NPL, Ao.NPU, Ao.indexL.ctypes.data_as(ipt), Ao.itemL.ctypes.data_as(ipt),
+                                       Ao.indexU.ctypes.data_as(ipt), Ao.itemU.ctypes.data_as(ipt), gather, icinv,
+                                       vals.ctypes.data_as(dpt))
+            assert rc == 0
+            assert np.abs(vals - ref).max() <= 1e-13 * np.abs(ref).max(), (gather, icinv)
+    assert em.fbemul_misaligned_count() == 0
+    out = np.zeros(2)
+    assert em.fbemul_ic_selftest(out.ctypes.data_as(dpt)) == 0
+    assert out[1] > 1e3 and out[0] <= 1e-12 * out[1]        # the library's gate is 1e-10
+
+
+def test_update_kernels_run_on_the_host_equal_oracle_and_golden_logs():
+    """fistr_b200_update_3d + fistr_b200_nodal_stress_3d end to end on the HOST (update_ic_kernel / update_lin_kernel
+    by lock-step warps, node incidence, gathers, nodal stress — unchanged kernels, the API's launch sequence): Gauss-point
+    strain / stress, QFORCE and all nodal / elemental fields against the oracle; on the golden decks also against the
+    26 strain / stress / Mises lines of the reference's logs (IC hex, tet10, with thermal strain for exF)."""
+    from oracle import oracle as orc
+    import __graft_entry__ as g
+    from test_gpu_z_unvalidated import mixed_mesh
+    em = C.CDLL(g.build_emul())
+    em.fbemul_misaligned_count.restype = C.c_long
+    dpt = C.POINTER(C.c_double)
+    d = lambda a: a.ctypes.data_as(dpt) if a is not None else None
+    rng = np.random.default_rng(8)
+    cases = []
+    for name in ("A361", "A342", "F361", "F342"):
+        mesh, A, meta, thermal = util.oracle_solve_deck(name)
+        cases.append((mesh, A.X.copy(), thermal, meta))
+    mm = mixed_mesh()
+    cases.append((mm, 1e-3 * rng.standard_normal(3 * mm.n_node), (20 + 80 * rng.random(mm.n_node), np.full(mm.n_node, 20.0), 2e-5, 20.0), None))
+    for mesh, u, thermal, meta in cases:
+        TT, T0, alp, ref = thermal if thermal else (None, None, 0.0, 0.0)
+        e0, s0, q0 = orc.update_linear(mesh, u, TT, T0, alp, ref)
+        o0 = orc.nodal_stress_3d(mesh, e0, s0)
+        keep, args = _emul_mesh_args(mesh)
+        alpha = np.full(len(mesh.sections), alp)
+        for icinv in (1, 0):
+            e1 = np.zeros_like(e0); s1 = np.zeros_like(s0); q1 = np.zeros_like(q0)
+            out = {k: np.zeros_like(v) for k, v in o0.items()}
+            rc = em.fbemul_update_pipeline(*args, d(alpha) if thermal else None, d(np.ascontiguousarray(u)), d(TT), d(T0),
+                                           C.c_double(ref), icinv, d(e1), d(s1), d(q1),
+                                           *[d(out[k]) for k in ("STRAIN", "STRESS", "MISES", "ESTRAIN", "ESTRESS", "EMISES")])
+            assert rc == 0
+            ngp = np.where(np.diff(mesh.elem_node_index) == 8, 8, 4)      # 342 fills 4 of the 8 slots
+            for el in range(mesh.n_elem):
+                assert np.abs(e1[el, :ngp[el]] - e0[el, :ngp[el]]).max() <= 1e-12 * np.abs(e0).max()
+                assert np.abs(s1[el, :ngp[el]] - s0[el, :ngp[el]]).max() <= 1e-12 * np.abs(s0).max()
+            assert np.abs(q1 - q0).max() <= 1e-12 * np.abs(q0).max()
+            for k in out:
+                assert np.abs(out[k] - o0[k]).max() <= 1e-12 * np.abs(o0[k]).max(), k
+            if meta:
+                util.check_golden_stress(out, meta)
+    assert em.fbemul_misaligned_count() == 0
+
+
 def test_tl_element_emulation_equals_oracle():
     """The total-Lagrangian element code of the CUDA kernels (element_math.cuh: element_stiffness_tl_warp /
     element_update_tl_warp, run in lock step on the host) against the oracle's restatement of STF_C3 / STF_C3D8Bbar /
