@@ -101,3 +101,27 @@ def test_partitioned_solve_with_real_tables():
         g = p.global_node_ID - 1
         assert util.rel_l2(Ap.X.reshape(-1, 3), A.X.reshape(-1, 3)[g]) < 1e-8    # halo included (update_m_R)
     orc.precond_clear()
+
+
+def test_strain_stress_recovery_needs_no_exchange_on_partitioned_meshes():
+    """SURVEY 8(e) for the strain / stress recovery path: every rank updates the elements of its own local mesh
+    (hecmw_part1 keeps every element that touches an internal node, i.e. the overlap elements are duplicated) and
+    averages over them, exactly as the reference does per MPI rank.  Nodal strain / stress / Mises at the INTERNAL
+    nodes of every subdomain then equal the serial result without any communication, and so does QFORCE at internal
+    nodes (what hecmw_update_3_R afterwards copies into the neighbours' halos).  Oracle on the 8 subdomains of the
+    reference's RCB partition vs the serial run, hex (IC) and tet10."""
+    from oracle import oracle as orc
+    rng = np.random.default_rng(3)
+    for mesh in (util.distort(meshgen.hex_cube(6)), meshgen.tet10_cube(3)):
+        u = 1e-3 * rng.standard_normal(3 * mesh.n_node)
+        e, s, q = orc.update_linear(mesh, u)
+        ref = orc.nodal_stress_3d(mesh, e, s)
+        for p in partition.partition(mesh, "xyz"):
+            g = p.global_node_ID - 1
+            ul = u.reshape(-1, 3)[g].reshape(-1)
+            el, sl, ql = orc.update_linear(p, ul)
+            out = orc.nodal_stress_3d(p, el, sl)
+            ni = p.nn_internal
+            for k in ("STRAIN", "STRESS", "MISES"):
+                assert np.abs(out[k][:ni] - ref[k][g[:ni]]).max() <= 1e-12 * np.abs(ref[k]).max(), k
+            assert np.abs(ql.reshape(-1, 3)[:ni] - q.reshape(-1, 3)[g[:ni]]).max() <= 1e-12 * np.abs(q).max()
