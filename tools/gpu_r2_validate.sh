@@ -7,6 +7,7 @@ timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -8 | tee gpurun_out/pyt
 FISTR_B200_RUN_NL_GPU=1 timeout 900 python -m pytest tests/test_gpu_z_unvalidated.py -m gpu -q -rA 2>&1 | tail -25 | tee gpurun_out/pytest_gpu_nl.log
 timeout 600 python tools/asm_probe.py --n 100 2>&1 | tee gpurun_out/asm_probe.log
 timeout 600 python tools/asm_probe.py --tet 40 --probes 0,1 2>&1 | tee -a gpurun_out/asm_probe.log
+timeout 600 python tools/post_probe.py --n 100 --tet 40 2>&1 | tee gpurun_out/post_probe.log
 timeout 600 python tools/perf_probe.py --tet 40 --variants 2 --sigma 0,256,1024,4096 --solve 0 2>&1 | tee gpurun_out/probe_tet40_sigma.log
 timeout 900 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"; cat gpurun_out/bench_n1.json
 for c in 0 2 3; do timeout 900 python tools/run_configs.py --config $c 2>&1 | tail -1 | tee gpurun_out/config_$c.json; done
