@@ -317,14 +317,30 @@ FB_WARP_FN void ic_inverse_warp(int lane, Scratch &S) {
     for (int I = 0; I < 9; I++) w[I] = FB_SHFL(a[I], K);
     gj_update(c, K, a, w);
   }
+  // Un-permutation (utilities.f90:301-314): the reference exchanges columns I and K = IP(I) for I = 1..N in turn.  The
+  // net effect is ONE column permutation; it is composed here in registers (ip is identical in every lane, so this is
+  // warp-uniform integer work) and applied with a single round of shuffles - none at all when no row was ever
+  // swapped, which is the normal case for the positive definite K(alpha,alpha).
+  int col[9];            // col[p] = the column (= lane) whose content ends up at position p
+  bool moved = false;
+#pragma unroll
+  for (int p = 0; p < 9; p++) col[p] = p;
 #pragma unroll
   for (int I = 0; I < 9; I++) {
-    const int K = gj_unpermute_step(I, ip);   // warp-uniform (ip is identical in every lane)
+    const int K = gj_unpermute_step(I, ip);
     if (K >= 0) {
-      const int other = (lane == I) ? K : ((lane == K) ? I : lane);
+      moved = true;
 #pragma unroll
-      for (int r = 0; r < 9; r++) a[r] = FB_SHFL(a[r], other);
+      for (int J = 0; J < 9; J++)
+        if (J == K) { const int t = col[J]; col[J] = col[I]; col[I] = t; }
     }
+  }
+  if (moved) {           // warp-uniform
+    int src = lane;
+#pragma unroll
+    for (int p = 0; p < 9; p++) if (p == lane) src = col[p];
+#pragma unroll
+    for (int r = 0; r < 9; r++) a[r] = FB_SHFL(a[r], src);
   }
   FB_SYNCWARP();
   if (lane < 9) {
