@@ -263,17 +263,17 @@ FB_HD void gj_swap_rows(int K, int LR, double (&a)[9], int (&ip)[9]) {
       const int q = ip[K]; ip[K] = ip[I]; ip[I] = q;
     }
 }
-// w[I] = A(I,K) after the row swap (column K, broadcast from lane K); w[K] is the pivot
-FB_HD void gj_update(int c, int K, double (&a)[9], const double (&w)[9]) {
-  const double PIVOT = w[K];
+// Step K of the elimination on column c (held by this lane).  w[I] = A(I,K) after the row swap (column K, broadcast
+// from lane K); w[K] is the pivot; qn[I] = -w[I] / PIVOT, the new column K, each entry divided by a different lane
+// (ic_inverse_warp) so that lane K does not have to run eight FP64 divisions one after the other while 31 lanes wait.
+FB_HD void gj_update(int c, int K, double (&a)[9], const double (&w)[9], const double (&qn)[9], double rpivot, double akc) {
   if (c == K) {
 #pragma unroll
     for (int I = 0; I < 9; I++)
-      if (I != K) { if (w[I] != 0.0) a[I] = -w[I] / PIVOT; }
-    a[K] = 1.0 / PIVOT;
+      if (I != K) { if (w[I] != 0.0) a[I] = qn[I]; }     // -W / PIVOT
+    a[K] = rpivot;                                        // 1 / PIVOT
   } else {
-    const double akc = a[K] / PIVOT;
-    a[K] = akc;
+    a[K] = akc;                                           // A(K,c) / PIVOT
 #pragma unroll
     for (int I = 0; I < 9; I++)
       if (I != K) { if (w[I] != 0.0) a[I] = a[I] - w[I] * akc; }
@@ -312,10 +312,17 @@ FB_WARP_FN void ic_inverse_warp(int lane, Scratch &S) {
     gj_pivot_local(K, a, LR, pivot);
     LR = FB_SHFL(LR, K);
     gj_swap_rows(K, LR, a, ip);
-    double w[9];
+    double w[9], qn[9];
 #pragma unroll
     for (int I = 0; I < 9; I++) w[I] = FB_SHFL(a[I], K);
-    gj_update(c, K, a, w);
+    // three divisions per lane, all lanes in parallel: lane I supplies -W(I) / PIVOT of the new column K
+    double wc = 0.0;
+#pragma unroll
+    for (int I = 0; I < 9; I++) if (I == c) wc = w[I];
+    const double q = -wc / w[K], rpivot = 1.0 / w[K], akc = a[K] / w[K];
+#pragma unroll
+    for (int I = 0; I < 9; I++) qn[I] = FB_SHFL(q, I);
+    gj_update(c, K, a, w, qn, rpivot, akc);
   }
   // Un-permutation (utilities.f90:301-314): the reference exchanges columns I and K = IP(I) for I = 1..N in turn.  The
   // net effect is ONE column permutation; it is composed here in registers (ip is identical in every lane, so this is
