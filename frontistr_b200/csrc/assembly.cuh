@@ -108,7 +108,8 @@ gather_sum_kernel(size_t nblk, const unsigned *__restrict__ gptr, const unsigned
 }
 
 // One element per warp.  sect[3*s..] = D11, D12, D44 of section s; sect_form[s] = elemopt361.
-// ICINV (IC element only): calInverse in registers + shuffles (1) or through shared memory (0), see element_math.cuh.
+// ICINV (IC element only): calInverse in registers + shuffles (1) or through shared memory (0), or LDL^T solves (2);
+// see element_math.cuh.
 template <int FORM, int WARPS, int ICINV = 1>
 __global__ void __launch_bounds__(WARPS * 32)
 stiff_kernel(int e0, int e1, const int *__restrict__ elem_node_index, const int *__restrict__ elem_node_item,
@@ -183,9 +184,10 @@ stiff_kernel(int e0, int e1, const int *__restrict__ elem_node_index, const int 
   }
 }
 
-// Device self-test of the IC element: the condensed stiffness of a few distorted hexahedra through BOTH calInverse
-// implementations (one warp, one block).  out[0] = max |K_shuffle - K_smem|, out[1] = max |K_smem|.  The host
-// (api_assembly.inc: ic_inverse_mode) uses the register/shuffle kernel only if the two agree to rounding.
+// Device self-test of the IC element: the condensed stiffness of a few distorted hexahedra through ALL THREE ways of
+// condensing (one warp, one block).  out[0] = max |K_shuffle - K_smem|, out[1] = max |K_smem|, out[2] = max |K_ldlt -
+// K_smem|.  The host (api_assembly.inc: ic_inverse_mode) uses a kernel other than the shared-memory one only if it
+// agrees with it to rounding.
 __global__ void __launch_bounds__(32) ic_selftest_kernel(double *__restrict__ out) {
   using namespace elem;
   FB_DYNAMIC_SMEM(smem_raw);
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(32) ic_selftest_kernel(double *__restrict__ ou
   const int lane = threadIdx.x & 31;
   double D11, D12, D44;
   elastic_constants(210000.0, 0.3, D11, D12, D44);
-  double maxdiff = 0.0, maxabs = 0.0;
+  double maxd1 = 0.0, maxd2 = 0.0, maxabs = 0.0;
   for (int trial = 0; trial < 4; trial++) {
     if (lane < 8) {
       const double corner[3] = {(double)((lane ^ (lane >> 1)) & 1), (double)((lane >> 1) & 1), (double)((lane >> 2) & 1)};
@@ -204,24 +206,31 @@ __global__ void __launch_bounds__(32) ic_selftest_kernel(double *__restrict__ ou
     double ka[2][9], kb[2][9];
     element_stiffness_warp<FORM_IC, 0>(lane, S, D11, D12, D44, ka);
     __syncwarp();
-    element_stiffness_warp<FORM_IC, 1>(lane, S, D11, D12, D44, kb);
-    __syncwarp();
 #pragma unroll
-    for (int r = 0; r < 2; r++)
+    for (int variant = 1; variant <= 2; variant++) {
+      if (variant == 1) element_stiffness_warp<FORM_IC, 1>(lane, S, D11, D12, D44, kb);
+      else element_stiffness_warp<FORM_IC, 2>(lane, S, D11, D12, D44, kb);
+      __syncwarp();
 #pragma unroll
-      for (int a = 0; a < 9; a++) {
-        const double d = fabs(ka[r][a] - kb[r][a]);
-        maxdiff = (d != d || maxdiff != maxdiff) ? d + maxdiff : fmax(maxdiff, d);   // NaN-propagating max
-        maxabs = fmax(maxabs, fabs(ka[r][a]));
-      }
+      for (int r = 0; r < 2; r++)
+#pragma unroll
+        for (int a = 0; a < 9; a++) {
+          const double d = fabs(ka[r][a] - kb[r][a]);
+          double &m = (variant == 1) ? maxd1 : maxd2;
+          m = (d != d || m != m) ? d + m : fmax(m, d);   // NaN-propagating max
+          maxabs = fmax(maxabs, fabs(ka[r][a]));
+        }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    const double d = __shfl_xor_sync(0xffffffffu, maxdiff, o), m = __shfl_xor_sync(0xffffffffu, maxabs, o);
-    maxdiff = (d != d || maxdiff != maxdiff) ? d + maxdiff : fmax(maxdiff, d);
+    const double d1 = __shfl_xor_sync(0xffffffffu, maxd1, o), d2 = __shfl_xor_sync(0xffffffffu, maxd2, o);
+    const double m = __shfl_xor_sync(0xffffffffu, maxabs, o);
+    maxd1 = (d1 != d1 || maxd1 != maxd1) ? d1 + maxd1 : fmax(maxd1, d1);
+    maxd2 = (d2 != d2 || maxd2 != maxd2) ? d2 + maxd2 : fmax(maxd2, d2);
     maxabs = fmax(maxabs, m);
   }
-  if (lane == 0) { out[0] = maxdiff; out[1] = maxabs; }
+  if (lane == 0) { out[0] = maxd1; out[1] = maxabs; out[2] = maxd2; }
 }
 
 // ---- geometrically nonlinear (total Lagrangian) assembly and update, SURVEY 8(f) rank 2 -----------

@@ -427,6 +427,67 @@ FB_WARP_FN void ic_inverse_smem_warp(int lane, Scratch &S) {
 }
 #endif
 
+#ifdef FB_WARP_FN
+// ---- third way to W = Kda * Kaa^-1 (ICINV == 2): no inverse at all.  K(alpha,alpha) is symmetric positive definite
+// for every valid element, so W^T = Kaa^-1 Kad is obtained from an LDL^T factorisation and 24 triangular solves.
+// Every lane factorises the 9x9 matrix redundantly in registers (165 FMA, 9 divisions, NO cross-lane traffic and no
+// barrier), then lane r < 24 solves for row r of W.  This is NOT the reference's operation order (calInverse is a
+// pivoted Gauss-Jordan): W differs from the reference-order result in the last bits (backward stable, cond(Kaa) is
+// O(10)), far inside the 1e-12 gate on K.  A non-positive or non-finite pivot (distorted / inverted element) makes
+// the function return false in ALL lanes (they computed the same numbers) and the caller takes the reference-order
+// path for that element.  The library uses this kernel only if its device self-test agrees with the shared-memory
+// reference-order kernel AND it is the fastest (api_assembly.inc).
+FB_WARP_FN bool ic_w_ldlt_warp(int lane, Scratch &S) {
+  double L[36], d[9], dinv[9];          // L(i,j), j < i, packed at i (i - 1) / 2 + j
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 9; j++) {
+    double v[9];
+    double dj = S.Kaa[j * 9 + j];
+#pragma unroll
+    for (int k = 0; k < 9; k++)
+      if (k < j) { v[k] = L[j * (j - 1) / 2 + k] * d[k]; dj -= L[j * (j - 1) / 2 + k] * v[k]; }
+    d[j] = dj;
+    ok = ok && (dj > 0.0) && (dj < 1.0e300);
+    dinv[j] = 1.0 / dj;
+#pragma unroll
+    for (int i = 0; i < 9; i++)
+      if (i > j) {
+        double t = S.Kaa[i * 9 + j];
+#pragma unroll
+        for (int k = 0; k < 9; k++)
+          if (k < j) t -= L[i * (i - 1) / 2 + k] * v[k];
+        L[i * (i - 1) / 2 + j] = t * dinv[j];
+      }
+  }
+  if (!ok) return false;
+  if (lane < 24) {
+    double x[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) {         // L y = b
+      double t = S.Kda[lane * 10 + i];
+#pragma unroll
+      for (int k = 0; k < 9; k++)
+        if (k < i) t -= L[i * (i - 1) / 2 + k] * x[k];
+      x[i] = t;
+    }
+#pragma unroll
+    for (int i = 0; i < 9; i++) x[i] *= dinv[i];
+#pragma unroll
+    for (int i = 8; i >= 0; i--) {        // L^T x = z
+      double t = x[i];
+#pragma unroll
+      for (int k = 0; k < 9; k++)
+        if (k > i) t -= L[k * (k - 1) / 2 + i] * x[k];
+      x[i] = t;
+    }
+#pragma unroll
+    for (int i = 0; i < 9; i++) S.W[lane * 10 + i] = x[i];
+  }
+  return true;
+}
+#endif
+
 // W = Kda * Kaa^-1   (tmpk, static_LIB_3dIC.f90:212): 216 entries over 32 lanes
 FB_HD void ic_phase_W(int lane, Scratch &S) {
   for (int t = lane; t < 216; t += 32) {
@@ -457,7 +518,8 @@ FB_HD void ic_condense_block(const Scratch &S, int i, int j, double *k9) {
 // The whole element: executed by the 32 lanes of one warp after S.xc holds the element coordinates (and the
 // warp has synchronised).  On return lane `l` holds in kb[r] the 3x3 block t = 32 r + l (i = t / nn, j = t % nn)
 // of the element stiffness matrix.  This is the body of assembly.cuh:stiff_kernel AND of the host emulation.
-// ICINV selects the calInverse implementation of the IC element: 1 = registers + shuffles, 0 = shared memory.
+// ICINV selects how the IC element gets W = Kda Kaa^-1: calInverse in registers + shuffles (1) or through shared
+// memory (0), both in the reference's operation order, or LDL^T solves without forming the inverse (2).
 template <int FORM, int ICINV = 1>
 FB_WARP_FN void element_stiffness_warp(int lane, Scratch &S, double D11, double D12, double D44,
                                        double (&kb)[((FORM == FORM_TET10 ? 100 : 64) + 31) / 32][9],
@@ -479,10 +541,14 @@ FB_WARP_FN void element_stiffness_warp(int lane, Scratch &S, double D11, double 
   if (FORM == FORM_IC && condense) {
     ic_phase_coupling(lane, S, D11, D12, D44);
     FB_SYNCWARP();
-    if (ICINV == 1) ic_inverse_warp(lane, S);
-    else ic_inverse_smem_warp(lane, S);
-    FB_SYNCWARP();
-    ic_phase_W(lane, S);
+    bool have_w = false;
+    if (ICINV == 2) have_w = ic_w_ldlt_warp(lane, S);     // warp-uniform result
+    if (!have_w) {
+      if (ICINV == 1) ic_inverse_warp(lane, S);
+      else ic_inverse_smem_warp(lane, S);
+      FB_SYNCWARP();
+      ic_phase_W(lane, S);
+    }
     FB_SYNCWARP();
 #pragma unroll
     for (int r = 0; r < ROUNDS; r++) {

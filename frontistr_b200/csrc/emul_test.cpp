@@ -264,7 +264,8 @@ int fbemul_stiffmatrix(int n_node, const double *node, int n_elem, int n_elem_ty
       bool has[4] = {false, false, false, false};
       for (int s = 0; s < n_sect; s++) has[sect_form[s]] = true;
       if (has[3]) {
-        if (icinv) emul_launch_warps(2, WARPS, smem, stiff_kernel<FORM_IC, WARPS, 1>, FB_ARGS);
+        if (icinv == 1) emul_launch_warps(2, WARPS, smem, stiff_kernel<FORM_IC, WARPS, 1>, FB_ARGS);
+        else if (icinv == 2) emul_launch_warps(2, WARPS, smem, stiff_kernel<FORM_IC, WARPS, 2>, FB_ARGS);
         else emul_launch_warps(2, WARPS, smem, stiff_kernel<FORM_IC, WARPS, 0>, FB_ARGS);
       }
       if (has[1]) emul_launch_warps(2, WARPS, smem, stiff_kernel<FORM_FI, WARPS, 1>, FB_ARGS);
@@ -446,7 +447,8 @@ long fbemul_misaligned_probe(void) {
   return seen;
 }
 
-// the device self-test of the two calInverse implementations (assembly.cuh: ic_selftest_kernel): out[0] max diff, out[1] max entry
+// the device self-test of the three condensation kernels (assembly.cuh: ic_selftest_kernel):
+// out[0] max |K_reg - K_smem|, out[1] max entry, out[2] max |K_ldlt - K_smem|
 int fbemul_ic_selftest(double *out) {
   emul_launch_warps(1, 1, sizeof(Scratch), fb::ic_selftest_kernel, out);
   return 0;
@@ -487,6 +489,12 @@ int fbemul_element_stiffness(int form, const double *ecoord, double E, double nu
 // IC element through the shared-memory calInverse (the arbiter of the device self-test)
 int fbemul_element_stiffness_ic_smem(const double *ecoord, double E, double nu, double *K) {
   run_element<FORM_IC, 0>(ecoord, E, nu, K);
+  return 0;
+}
+// IC element condensed through LDL^T solves (ICINV == 2; falls back to the shared-memory calInverse by itself when
+// K(alpha,alpha) is not positive definite)
+int fbemul_element_stiffness_ic_ldlt(const double *ecoord, double E, double nu, double *K) {
+  run_element<FORM_IC, 2>(ecoord, E, nu, K);
   return 0;
 }
 int fbemul_inverse9_smem(double *A /* row-major 9x9, in place */) {

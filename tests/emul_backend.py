@@ -52,7 +52,7 @@ class EmulBackend:
         return self.opts.get(key, -1)
 
     def _icinv(self):
-        return self.opts.get("ic_inverse", -1) if self.opts.get("ic_inverse", -1) in (0, 1) else 1
+        return self.opts.get("ic_inverse", -1) if self.opts.get("ic_inverse", -1) in (0, 1, 2) else 1
 
     # ---- marshalling
     def _mesh_args(self, m):
@@ -127,7 +127,7 @@ class EmulBackend:
         out = dict(STRAIN=np.zeros((mesh.n_node, 6)), STRESS=np.zeros((mesh.n_node, 6)), MISES=np.zeros(mesh.n_node),
                    ESTRAIN=np.zeros((mesh.n_elem, 6)), ESTRESS=np.zeros((mesh.n_elem, 6)), EMISES=np.zeros(mesh.n_elem))
         rc = self.em.fbemul_update_pipeline(*args, _d(k["alpha"]) if tt is not None else None, _d(u), _d(tt), _d(t0),
-                                            C.c_double(ref_temp), self._icinv(), _d(e), _d(s), _d(q),
+                                            C.c_double(ref_temp), min(self._icinv(), 1), _d(e), _d(s), _d(q),
                                             *[_d(out[n]) for n in ("STRAIN", "STRESS", "MISES", "ESTRAIN", "ESTRESS", "EMISES")])
         assert rc == 0 and self.em.fbemul_misaligned_count() == 0
         self._gp = (e, s)

@@ -23,7 +23,7 @@ class ShadowBackend:
 
     def get_option(self, key):
         if key == "ic_inverse_active":      # the library reports which calInverse kernel it used
-            return self.opts.get("ic_inverse", -1) if self.opts.get("ic_inverse", -1) in (0, 1) else 1
+            return self.opts.get("ic_inverse", -1) if self.opts.get("ic_inverse", -1) in (0, 1, 2) else 1
         return self.opts.get(key, -1)
 
     def mat_structure(self, mesh, A):

@@ -180,6 +180,30 @@ def test_ic_shared_memory_inverse_equals_register_inverse_and_oracle():
         assert np.abs(mine - ref).max() <= 1e-13 * np.abs(ref).max(), trial
 
 
+def test_ic_ldlt_condensation_equals_oracle_and_falls_back_on_indefinite_elements():
+    """Third IC kernel (ICINV == 2, element_math.cuh: ic_w_ldlt_warp): W = Kda Kaa^-1 from an LDL^T factorisation that
+    every lane computes redundantly, no inverse, no cross-lane traffic.  Not the reference's operation order, so it is
+    compared with the oracle at 1e-13 (the kernels in reference order reach 1e-14) on 40 strongly distorted hexahedra;
+    on INVERTED elements (negative Jacobian => K(alpha,alpha) negative definite) the function must notice the
+    non-positive pivot and hand the element to the reference-order path, i.e. reproduce the oracle there as well."""
+    from oracle import oracle as orc
+    import __graft_entry__ as g
+    em = C.CDLL(g.build_emul())
+    dp = C.POINTER(C.c_double)
+    rng = np.random.default_rng(21)
+    base = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)
+    for trial in range(40):
+        sc = rng.uniform(0.2, 3.0, 3)
+        ec = np.ascontiguousarray(base * sc + 0.22 * sc.min() * rng.standard_normal((8, 3)))
+        if trial % 8 == 7:
+            ec = np.ascontiguousarray(ec[[4, 5, 6, 7, 0, 1, 2, 3]])      # bottom and top face swapped: det J < 0 everywhere
+        K0 = orc.element_stiffness("IC", ec, 210000.0, 0.3)
+        K2 = np.zeros_like(K0)
+        assert em.fbemul_element_stiffness_ic_ldlt(ec.ctypes.data_as(dp), C.c_double(210000.0), C.c_double(0.3), K2.ctypes.data_as(dp)) == 0
+        assert np.isfinite(K2).all()
+        assert np.abs(K0 - K2).max() <= 1e-13 * np.abs(K0).max(), trial
+
+
 def test_linear_update_emulation_equals_oracle():
     """Strain / stress recovery of the linear analysis as the CUDA warp executes it (element_math.cuh:
     element_update_lin_warp for 361 FI / B-bar and 342, element_update_ic_warp for the IC element with either
@@ -331,7 +355,7 @@ def test_assembly_kernels_run_on_the_host_equal_oracle():
         orc.stiffmatrix(mesh, Ao)
         ref = np.concatenate([Ao.D, Ao.AL, Ao.AU])
         keep, args = _emul_mesh_args(mesh)
-        for gather, icinv in ((1, 1), (1, 0), (0, 1)):
+        for gather, icinv in ((1, 1), (1, 0), (0, 1), (1, 2)):
             vals = np.zeros_like(ref)
             rc = em.fbemul_stiffmatrix(*args, Ao.NP, Ao.NPL, Ao.NPU, Ao.indexL.ctypes.data_as(ipt), Ao.itemL.ctypes.data_as(ipt),
                                        Ao.indexU.ctypes.data_as(ipt), Ao.itemU.ctypes.data_as(ipt), gather, icinv,
@@ -339,9 +363,9 @@ def test_assembly_kernels_run_on_the_host_equal_oracle():
             assert rc == 0
             assert np.abs(vals - ref).max() <= 1e-13 * np.abs(ref).max(), (gather, icinv)
     assert em.fbemul_misaligned_count() == 0
-    out = np.zeros(2)
+    out = np.zeros(3)
     assert em.fbemul_ic_selftest(out.ctypes.data_as(dpt)) == 0
-    assert out[1] > 1e3 and out[0] <= 1e-12 * out[1]        # the library's gate is 1e-10
+    assert out[1] > 1e3 and out[0] <= 1e-12 * out[1] and out[2] <= 1e-12 * out[1]        # the library's gate is 1e-10
 
 
 def test_update_kernels_run_on_the_host_equal_oracle_and_golden_logs():

@@ -18,8 +18,10 @@ for name, mk in cases:
     mesh = mk()
     A = hecmw.hecmw_mat_con(mesh); A.fstr_mat_init()
     hecmw.mat_structure(mesh, A)
-    for probe in [int(x) for x in args.probes.split(",")]:
-        hecmw.set_option("asm_probe", probe)
-        ts = [hecmw.fstr_StiffMatrix(mesh, A, to_host=False)["kernel_ms"] for _ in range(3)]
-        print("%-5s n_elem=%d probe=%d: kernel %.3f ms -> %.1f M elem/s" % (name, mesh.n_elem, probe, min(ts), mesh.n_elem / min(ts) / 1e3), flush=True)
-    hecmw.set_option("asm_probe", 0)
+    for icv in ((0, 1, 2) if name == "IC" else (-1,)):      # IC: the three condensation kernels (element_math.cuh)
+        hecmw.set_option("ic_inverse", icv)
+        for probe in [int(x) for x in args.probes.split(",")]:
+            hecmw.set_option("asm_probe", probe)
+            ts = [hecmw.fstr_StiffMatrix(mesh, A, to_host=False)["kernel_ms"] for _ in range(3)]
+            print("%-5s%s n_elem=%d probe=%d: kernel %.3f ms -> %.1f M elem/s" % (name, "" if icv < 0 else " ic_inverse=%d" % icv, mesh.n_elem, probe, min(ts), mesh.n_elem / min(ts) / 1e3), flush=True)
+    hecmw.set_option("asm_probe", 0); hecmw.set_option("ic_inverse", -1)
