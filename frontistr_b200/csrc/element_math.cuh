@@ -530,6 +530,15 @@ FB_WARP_FN void element_stiffness_warp(int lane, Scratch &S, double D11, double 
   constexpr int ROUNDS = (NB + 31) / 32;
   phase_geometry<FORM>(lane, S);
   FB_SYNCWARP();
+  // ICINV == 2: the coupling blocks and W first, while the node blocks kb[] are not live yet (the LDL^T factors
+  // occupy ~110 registers); the results are the same numbers in either order
+  constexpr bool W_FIRST = (FORM == FORM_IC && ICINV == 2);
+  bool have_w = false;
+  if (W_FIRST && condense) {
+    ic_phase_coupling(lane, S, D11, D12, D44);
+    FB_SYNCWARP();
+    have_w = ic_w_ldlt_warp(lane, S);     // warp-uniform result
+  }
 #pragma unroll
   for (int r = 0; r < ROUNDS; r++) {
     const int t = r * 32 + lane;
@@ -539,11 +548,11 @@ FB_WARP_FN void element_stiffness_warp(int lane, Scratch &S, double D11, double 
     }
   }
   if (FORM == FORM_IC && condense) {
-    ic_phase_coupling(lane, S, D11, D12, D44);
-    FB_SYNCWARP();
-    bool have_w = false;
-    if (ICINV == 2) have_w = ic_w_ldlt_warp(lane, S);     // warp-uniform result
-    if (!have_w) {
+    if (!W_FIRST) {
+      ic_phase_coupling(lane, S, D11, D12, D44);
+      FB_SYNCWARP();
+    }
+    if (!have_w) {                        // reference-order paths (and the fall-back of the LDL^T kernel)
       if (ICINV == 1) ic_inverse_warp(lane, S);
       else ic_inverse_smem_warp(lane, S);
       FB_SYNCWARP();
