@@ -177,8 +177,14 @@ spmv_sell1_kernel(int N, int nslice, const long long *__restrict__ slice_ptr,
   grid_reduce<1, BLOCK>(dot, partial, counter, [=](double(&o)[1]) { if (red_out) *red_out = o[0]; });
 }
 
-// variant 2: pair-interleaved columns, double2 / int2 loads
-template <int MODE, int BLOCK>
+// variant 2: pair-interleaved columns, double2 / int2 loads.
+// PEER = true is the instantiation launched in peer-memory mode (a.halo_seq != 0): the halo rows of x are then written
+// by OTHER GPUs while this kernel runs, so the slices that read them must not take x through the non-coherent L1 /
+// read-only path the compiler picks for `const __restrict__` data (an interior warp of the same SM may have pulled the
+// sector that straddles rows N-1 | N before the neighbour's store landed).  Those slices gather x with ld.global.cg
+// (L2, the point of coherence for peer stores) after their acquire on the neighbours' flags.  PEER = false compiles to
+// exactly the kernel that was measured in round 1.
+template <int MODE, int BLOCK, bool PEER = false>
 __global__ void __launch_bounds__(BLOCK)
 spmv_sell2_kernel(int N, int nslice, const long long *__restrict__ slice_ptr,
                   const double *__restrict__ val, const int *__restrict__ col,
@@ -196,6 +202,7 @@ spmv_sell2_kernel(int N, int nslice, const long long *__restrict__ slice_ptr,
   bool halo_ready = (a.halo_seq == 0);
   for (int s = wg; s < nslice; s += nw) {
     if (!halo_ready && halo_slice[s]) { p2p_wait_halo_warp(pv, nb, a.halo_seq); halo_ready = true; }
+    const bool via_l2 = PEER && halo_slice[s];
     const long long p0 = slice_ptr[s], p1 = slice_ptr[s + 1];
     const double2 *v = reinterpret_cast<const double2 *>(val) + p0 * 288 + lane;
     const int2 *cp = reinterpret_cast<const int2 *>(col) + p0 * 32 + lane;
@@ -207,8 +214,14 @@ spmv_sell2_kernel(int N, int nslice, const long long *__restrict__ slice_ptr,
 #pragma unroll
       for (int k = 0; k < 9; k++) a[k] = ld_stream2(v + k * 32);
       const double *xa = x + 3 * (size_t)c.x, *xb = x + 3 * (size_t)c.y;
-      const double xa0 = xa[0], xa1 = xa[1], xa2 = xa[2];
-      const double xb0 = xb[0], xb1 = xb[1], xb2 = xb[2];
+      double xa0, xa1, xa2, xb0, xb1, xb2;
+      if (PEER && via_l2) {
+        xa0 = __ldcg(xa); xa1 = __ldcg(xa + 1); xa2 = __ldcg(xa + 2);
+        xb0 = __ldcg(xb); xb1 = __ldcg(xb + 1); xb2 = __ldcg(xb + 2);
+      } else {
+        xa0 = xa[0]; xa1 = xa[1]; xa2 = xa[2];
+        xb0 = xb[0]; xb1 = xb[1]; xb2 = xb[2];
+      }
       FB_ROW_FMA(y0, a[0].x, a[1].x, a[2].x, xa0, xa1, xa2);
       FB_ROW_FMA(y1, a[3].x, a[4].x, a[5].x, xa0, xa1, xa2);
       FB_ROW_FMA(y2, a[6].x, a[7].x, a[8].x, xa0, xa1, xa2);
