@@ -8,11 +8,7 @@
 // element and every call (hecmw_mat_ass.f90:81-121) depends on topology only: it is done once per
 // structure into slot[e*nn*nn + i*nn + j].
 #pragma once
-#ifdef FB_EMUL_KERNELS
-#include "kernel_emul.hpp"   // TEST-ONLY host stand-in (libfistr_b200_emul.so): the kernels below run on host threads
-#else
-#include "common.cuh"
-#endif
+#include "common.cuh"   // (under FB_EMUL_KERNELS: the TEST-ONLY host stand-in kernel_emul.hpp, libfistr_b200_emul.so)
 #include "element_math.cuh"
 
 namespace fb {

@@ -1,6 +1,10 @@
 // Common device/host helpers for the fistr_b200 kernels (sm_100a only).
 #pragma once
+#ifdef FB_EMUL_KERNELS
+#include "kernel_emul.hpp"   // TEST-ONLY host stand-in for the CUDA execution model (libfistr_b200_emul.so)
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <cstdio>
 #include <cstdlib>
@@ -10,10 +14,12 @@
 
 namespace fb {
 
+#ifndef FB_EMUL_KERNELS
 // dynamic shared memory of a kernel (the TEST-ONLY host stand-in kernel_emul.hpp maps it to a host buffer)
 #define FB_DYNAMIC_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 
 constexpr int kWarp = 32;
+#endif
 constexpr int kNumSM = 148;  // B200: 2 dies x 74 SMs (queried at init; this is the sizing default)
 
 extern thread_local std::string g_last_error;
@@ -40,6 +46,7 @@ extern int64_t g_launch_count;
     }                                                                                      \
   } while (0)
 
+#ifndef FB_EMUL_KERNELS   // (host versions in kernel_emul.hpp)
 // ---- streaming loads: values/indices are touched once per SpMV, keep them out of L1 so the
 // gathered x vector owns it.
 __device__ __forceinline__ double ld_stream(const double *p) {
@@ -68,6 +75,7 @@ __device__ __forceinline__ int4 ld_stream4(const int4 *p) {
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
+#endif
 
 // ---- reductions -------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
@@ -147,6 +155,7 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], double *partial, un
   }
 }
 
+#ifndef FB_EMUL_KERNELS   // (a malloc-backed stand-in lives in kernel_emul.hpp)
 template <class T>
 struct DevBuf {
   T *p = nullptr;
@@ -177,5 +186,6 @@ struct DevBuf {
     owned = true;
   }
 };
+#endif
 
 }  // namespace fb

@@ -11,17 +11,117 @@
 
 #define FB_EMUL_WARP 1
 #define FB_EMUL_KERNELS 1
-#include "assembly.cuh"   // element_math.cuh + the grid-stride kernels, run on the host through kernel_emul.hpp
+#include "assembly.cuh"   // element_math.cuh + the assembly / update kernels, run on the host through kernel_emul.hpp
+#include "spmv.cuh"       // + SpMV, CG and peer-memory kernels (cg_kernels.cuh, p2p.cuh)
 
 using namespace fb::elem;
 
-// ---- lock-step warp emulation: 32 host threads, every collective is a barrier-separated exchange -----
-namespace fb { namespace emulwarp {
+// ---- execution models behind the warp / block collectives -------------------------------------------------------
+// (a) emul_launch_warps: 32 host threads per warp, every collective is a pthread-barrier-separated exchange;
+// (b) emul_launch_blocks: the threads of a block are cooperative fibers (ucontext) of the calling host thread; a fiber
+//     that reaches __syncthreads / __syncwarp / a shuffle parks itself and the scheduler releases the block (warp) once
+//     every live fiber of it has arrived.  Everything is per host thread, so several host threads = several "GPUs".
+#include <ucontext.h>
+
+#include <chrono>
+#include <functional>
+#include <memory>
+
+namespace fb {
+thread_local std::string g_last_error;
+int64_t g_launch_count = 0;
+unsigned long long p2p_now_ns() {
+  return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+namespace emulwarp {
 static pthread_barrier_t g_bar;
 static thread_local int t_lane = 0;
 static double g_slot_d[32];
 static int g_slot_i[32];
+
+struct Fiber {
+  ucontext_t ctx;
+  std::unique_ptr<char[]> stack;
+  int state = 0;   // 0 runnable, 1 parked at the block barrier, 2 parked at the warp barrier, 3 finished
+};
+struct FiberBlock {
+  std::vector<Fiber> f;
+  ucontext_t main;
+  int cur = -1;
+  unsigned grid = 1, block = 1, bidx = 0;
+  std::function<void()> body;
+  std::vector<double> slot_d;
+  std::vector<int> slot_i;
+};
+static thread_local FiberBlock *t_fb = nullptr;   // non-null while this host thread runs a fiber block
+
+static void fiber_yield(int state) {
+  FiberBlock &B = *t_fb;
+  B.f[B.cur].state = state;
+  swapcontext(&B.f[B.cur].ctx, &B.main);
+}
+static void fiber_entry() {
+  FiberBlock &B = *t_fb;
+  B.body();
+  B.f[B.cur].state = 3;
+  swapcontext(&B.f[B.cur].ctx, &B.main);
+}
+static void run_fiber_block(FiberBlock &B) {
+  constexpr size_t STACK = 96 * 1024;
+  const int n = (int)B.block;
+  B.f.resize(n);
+  B.slot_d.assign(n, 0.0); B.slot_i.assign(n, 0);
+  t_fb = &B;
+  for (int i = 0; i < n; i++) {
+    Fiber &F = B.f[i];
+    F.stack.reset(new char[STACK]);
+    getcontext(&F.ctx);
+    F.ctx.uc_stack.ss_sp = F.stack.get(); F.ctx.uc_stack.ss_size = STACK; F.ctx.uc_link = &B.main;
+    makecontext(&F.ctx, fiber_entry, 0);
+    F.state = 0;
+  }
+  for (;;) {
+    bool ran = false, alive = false;
+    for (int i = 0; i < n; i++) {
+      if (B.f[i].state != 0) continue;
+      B.cur = i;
+      fb::gridDim.x = B.grid; fb::blockDim.x = B.block; fb::blockIdx.x = B.bidx; fb::threadIdx.x = (unsigned)i;
+      swapcontext(&B.main, &B.f[i].ctx);
+      ran = true;
+    }
+    // release barriers whose every live participant has arrived
+    bool all_block = true, any_block = false;
+    for (int i = 0; i < n; i++) {
+      if (B.f[i].state != 3) alive = true;
+      if (B.f[i].state == 1) any_block = true;
+      else if (B.f[i].state != 3) all_block = false;
+    }
+    if (!alive) break;
+    bool released = false;
+    if (any_block && all_block) { for (int i = 0; i < n; i++) if (B.f[i].state == 1) B.f[i].state = 0; released = true; }
+    for (int w = 0; w * 32 < n; w++) {
+      bool all = true, any = false;
+      for (int i = w * 32; i < std::min(n, w * 32 + 32); i++) {
+        if (B.f[i].state == 2) any = true;
+        else if (B.f[i].state != 3) all = false;
+      }
+      if (any && all) { for (int i = w * 32; i < std::min(n, w * 32 + 32); i++) if (B.f[i].state == 2) B.f[i].state = 0; released = true; }
+    }
+    if (!ran && !released) { fprintf(stderr, "emul: fiber block dead-locked (divergent barrier)\n"); abort(); }
+  }
+  t_fb = nullptr;
+}
+
 double shfl(double v, int src) {
+  if (t_fb) {
+    FiberBlock &B = *t_fb;
+    const int me = B.cur, base = me & ~31;
+    B.slot_d[me] = v;
+    fiber_yield(2);
+    const double r = B.slot_d[base + (src & 31)];
+    fiber_yield(2);
+    return r;
+  }
   g_slot_d[t_lane] = v;
   pthread_barrier_wait(&g_bar);
   const double r = g_slot_d[src & 31];
@@ -29,13 +129,26 @@ double shfl(double v, int src) {
   return r;
 }
 int shfl(int v, int src) {
+  if (t_fb) {
+    FiberBlock &B = *t_fb;
+    const int me = B.cur, base = me & ~31;
+    B.slot_i[me] = v;
+    fiber_yield(2);
+    const int r = B.slot_i[base + (src & 31)];
+    fiber_yield(2);
+    return r;
+  }
   g_slot_i[t_lane] = v;
   pthread_barrier_wait(&g_bar);
   const int r = g_slot_i[src & 31];
   pthread_barrier_wait(&g_bar);
   return r;
 }
-void syncwarp() { pthread_barrier_wait(&g_bar); }
+void syncwarp() { if (t_fb) fiber_yield(2); else pthread_barrier_wait(&g_bar); }
+void syncthreads() {
+  if (!t_fb) { fprintf(stderr, "emul: __syncthreads outside emul_launch_blocks\n"); abort(); }
+  fiber_yield(1);
+}
 template <class F>
 static void run_warp(F f) {   // f(lane) on 32 threads in lock step
   pthread_barrier_init(&g_bar, nullptr, 32);
@@ -45,6 +158,18 @@ static void run_warp(F f) {   // f(lane) on 32 threads in lock step
   pthread_barrier_destroy(&g_bar);
 }
 } }
+
+// kernel<<<grid, block>>>(args...) for block-cooperative kernels: blocks one after the other, the threads of a block as
+// fibers of the calling host thread (see above)
+template <class K, class... A>
+static void emul_launch_blocks(unsigned grid, unsigned block, K kernel, A... args) {
+  for (unsigned b = 0; b < grid; b++) {
+    fb::emulwarp::FiberBlock B;
+    B.grid = grid; B.block = block; B.bidx = b;
+    B.body = [&]() { kernel(args...); };
+    fb::emulwarp::run_fiber_block(B);
+  }
+}
 
 // kernel<<<grid, warps*32, smem>>>(args...) for the one-element-per-warp kernels: every warp of every block by 32 host
 // threads in lock step, warps one after the other (the warps of these kernels never talk to each other)
@@ -429,6 +554,153 @@ int fbemul_mat_ass_bc(int nbc, const int *inode, const int *idof, const double *
               (const int *)ptr.data(), NP, NPL, indexL, itemL, indexU, itemU, vals, B);
   emul_launch((unsigned)(m + 63) / 64, 64, 33, bc_set_rhs_kernel, m, (const int *)nodes.data(), (const int *)dofs.data(),
               (const double *)v.data(), B);
+  return 0;
+}
+
+// =============================================================================================
+// The fused CG iteration of fistr_b200_solve_33 in PEER-MEMORY mode on R emulated GPUs: R host threads, each running
+// the product's kernels (sell_fill_kernel, diag_setup_kernel, cg_precond_dot_kernel, cg_update_p_kernel,
+// spmv_sell2_kernel<0, BLOCK, PEER>, cg_fused_update_kernel, cg_check_kernel; UNCHANGED, blocks of fibers) in the launch
+// order and with the sequence numbering of api_solver.inc, the arenas (tagged partial sums, halo flags, p vectors)
+// wired as p2p_setup does.  No NCCL: the three scalars of the set-up are summed on the host; `iters` < 50 so that no
+// true-residual iteration (which the product runs over NCCL) falls inside.  Ranks run de-synchronised (random spins
+// between launches; break_halo_wait = negative control).  Output per rank: X (3*NP) after `iters` iterations, the residual history, the error word.
+// =============================================================================================
+struct P2PRank {
+  int N, NP, nslice;
+  std::vector<long long> sp;
+  std::vector<int> rowperm, col, exp_peer, exp_remote;
+  std::vector<double> val, alu, X, R, Z, Q, sendbuf, red, partial, hist;
+  std::vector<unsigned char> halo_slice, arena;
+  std::vector<unsigned> counter;
+  fb::CgCtl ctl;
+  int err[4];
+};
+
+int fbemul_p2p_cg(int R, const int *N, const int *NP, const double *const *D, const double *const *AL, const double *const *AU,
+                  const int *const *indexL, const int *const *itemL, const int *const *indexU, const int *const *itemU,
+                  const double *const *Bv, const int *n_nbr, const int *const *nbr_pe, const int *const *imp_index,
+                  const int *const *imp_item, const int *const *exp_index, const int *const *exp_item, int iters, double tol,
+                  int sigma, int peer_kernel, unsigned seed, int break_halo_wait, double *const *X_out, double *const *hist_out, int *err_out) {
+  using namespace fb;
+  constexpr int BLOCK = 256;
+  if (R < 1 || R > kP2PMaxRanks || iters >= 50) return -1;
+  constexpr size_t OFF_FLAGS = sizeof(P2PEntry) * P2P_NQ * 2 * kP2PMaxRanks, OFF_P = 4096;
+  std::vector<P2PRank> rk(R);
+  for (int r = 0; r < R; r++) {
+    rk[r].N = N[r]; rk[r].NP = NP[r];
+    rk[r].arena.assign(OFF_P + sizeof(double) * (3 * (size_t)NP[r] + 8) + 64, 0);
+  }
+  auto arena_base = [&](int r) { unsigned char *b = rk[r].arena.data(); return b + (64 - reinterpret_cast<uintptr_t>(b) % 64) % 64; };
+  pthread_barrier_t bar;
+  pthread_barrier_init(&bar, nullptr, R);
+  std::vector<double> gsum(R, 0.0);
+  auto allreduce = [&](int me, double v) {   // host stand-in of the set-up all-reduces (rank order, like the device path)
+    gsum[me] = v;
+    pthread_barrier_wait(&bar);
+    double s = 0.0;
+    for (int r = 0; r < R; r++) s += gsum[r];
+    pthread_barrier_wait(&bar);
+    return s;
+  };
+  std::vector<std::thread> th;
+  for (int me = 0; me < R; me++)
+    th.emplace_back([&, me]() {
+      P2PRank &K = rk[me];
+      std::mt19937 rng(seed * 977u + me);
+      auto jitter = [&]() { volatile unsigned x = 0; for (unsigned i = 0, n = rng() % 20000; i < n; i++) x += i; if (rng() % 5 == 0) std::this_thread::yield(); };
+      const int n = K.N, np = K.NP;
+      const size_t n3 = 3 * (size_t)n, np3 = 3 * (size_t)np + 8;
+      // ---- private SELL copy (build_sell)
+      sell_layout(n, indexL[me], indexU[me], sigma, 2, K.rowperm, K.sp);
+      K.nslice = (n + 31) / 32;
+      const size_t cols = (size_t)K.sp[K.nslice] * 2;
+      K.val.assign(cols * 288 + 2, 0.0); K.col.assign(cols * 32 + 2, 0); K.halo_slice.assign((size_t)K.nslice + 1, 0);
+      double *val = K.val.data() + ((reinterpret_cast<uintptr_t>(K.val.data()) % 16) ? 1 : 0);   // 16-byte aligned, like cudaMalloc
+      int *col = K.col.data() + ((reinterpret_cast<uintptr_t>(K.col.data()) % 8) ? 1 : 0);
+      const int *rp = K.rowperm.empty() ? nullptr : K.rowperm.data();
+      if (K.nslice > 0)
+        emul_launch_blocks((unsigned)((K.nslice * 32 + 255) / 256), 256, sell_fill_kernel<2>, n, D[me], AL[me], AU[me], indexL[me], itemL[me],
+                           indexU[me], itemU[me], (const long long *)K.sp.data(), val, col, K.halo_slice.data(), rp);
+      // ---- DIAG factors
+      K.alu.assign(9 * (size_t)std::max(n, 1), 0.0);
+      if (n > 0) emul_launch((unsigned)((n + 63) / 64), 64, 3u + me, diag_setup_kernel, n, D[me], 1.0, K.alu.data(), (size_t)n);
+      // ---- work vectors, control block, peer view (p2p_setup)
+      K.X.assign(np3, 0.0); K.R.assign(np3, 0.0); K.Z.assign(np3, 0.0); K.Q.assign(np3, 0.0);
+      K.red.assign(RED_COUNT, 0.0); K.partial.assign(65536, 0.0); K.counter.assign(4, 0u); K.hist.assign((size_t)iters + 2, 0.0);
+      memset(&K.ctl, 0, sizeof K.ctl); K.ctl.tol = tol;
+      memset(K.err, 0, sizeof K.err);
+      P2PView pv;
+      pv.nranks = R; pv.me = me; pv.err = K.err;
+      for (int r = 0; r < R; r++) {
+        unsigned char *b = arena_base(r);
+        pv.ar[r] = (P2PEntry *)b; pv.hflag[r] = (unsigned long long *)(b + OFF_FLAGS); pv.vecP[r] = (double *)(b + OFF_P);
+      }
+      double *P = pv.vecP[me];
+      P2PNeighbors nb;
+      nb.n = n_nbr[me];
+      for (int a = 0; a < nb.n; a++) nb.rank[a] = nbr_pe[me][a];
+      const int nexp = nb.n ? exp_index[me][nb.n] : 0;
+      K.exp_peer.assign((size_t)std::max(nexp, 1), 0); K.exp_remote.assign((size_t)std::max(nexp, 1), 0);
+      K.sendbuf.assign(3 * (size_t)std::max(nexp, 1), 0.0);
+      for (int a = 0; a < nb.n; a++) {
+        const int q = nbr_pe[me][a];
+        int b = -1;
+        for (int t = 0; t < n_nbr[q]; t++) if (nbr_pe[q][t] == me) b = t;
+        for (int e = exp_index[me][a]; e < exp_index[me][a + 1]; e++) {
+          K.exp_peer[e] = q;
+          K.exp_remote[e] = imp_item[q][imp_index[q][b] + (e - exp_index[me][a])] - 1;
+        }
+      }
+      pthread_barrier_wait(&bar);   // every arena is wired before anybody stores into a peer
+      double *red = K.red.data();
+      const int gvec = 2, gnode = 2, gsp = 3;
+      // ---- b.b, r0 = b - A x0 = b, z1 = Minv r0, rho1 (solve_33 set-up)
+      {
+        double s = 0.0;
+        for (size_t i = 0; i < n3; i++) { K.R[i] = Bv[me][i]; s = std::fma(Bv[me][i], Bv[me][i], s); }
+        red[RED_BNRM2] = allreduce(me, s);
+      }
+      emul_launch_blocks(gnode, BLOCK, cg_precond_dot_kernel<BLOCK>, n, (const double *)K.alu.data(), (size_t)n, (const double *)K.R.data(),
+                         K.Z.data(), K.partial.data(), K.counter.data(), red + 3, (const int *)nullptr);
+      red[3] = allreduce(me, red[3]);
+      // ---- iterations (api_solver.inc: the p2p branch of the launch loop)
+      unsigned long long seq_pq = 0, seq_rrrz = 0, halo_seq = 0, pending = 0;
+      int *phase = &K.ctl.phase;
+      for (int k = 1; k <= iters; k++) {
+        P2PArgs ap, as, af;
+        ap.consume_seq = pending; pending = 0;
+        ap.halo_seq = ++halo_seq; as.halo_seq = break_halo_wait ? 0 : ap.halo_seq;   // negative control: SpMV does not wait for the neighbours
+        as.publish_seq = ++seq_pq; af.consume_seq = as.publish_seq; af.publish_seq = ++seq_rrrz;
+        jitter();
+        emul_launch_blocks(gvec, BLOCK, cg_update_p_kernel<BLOCK>, k, n3, (const double *)K.Z.data(), P, red, &K.ctl, K.hist.data(), iters + 1,
+                           nexp, exp_item[me], K.sendbuf.data(), pv, nb, ap, (const int *)K.exp_peer.data(), (const int *)K.exp_remote.data(),
+                           K.counter.data() + 1);
+        jitter();
+        if (peer_kernel)
+          emul_launch_blocks(gsp, BLOCK, spmv_sell2_kernel<0, BLOCK, true>, n, K.nslice, (const long long *)K.sp.data(), (const double *)val,
+                             (const int *)col, (const double *)P, (const double *)nullptr, K.Q.data(), K.partial.data(), K.counter.data(),
+                             red + RED_PQ, (const int *)phase, pv, nb, as, (const unsigned char *)K.halo_slice.data(), rp);
+        else
+          emul_launch_blocks(gsp, BLOCK, spmv_sell2_kernel<0, BLOCK, false>, n, K.nslice, (const long long *)K.sp.data(), (const double *)val,
+                             (const int *)col, (const double *)P, (const double *)nullptr, K.Q.data(), K.partial.data(), K.counter.data(),
+                             red + RED_PQ, (const int *)phase, pv, nb, as, (const unsigned char *)K.halo_slice.data(), rp);
+        jitter();
+        emul_launch_blocks(gnode, BLOCK, cg_fused_update_kernel<BLOCK>, k, n, (const double *)P, (const double *)K.Q.data(), K.X.data(),
+                           K.R.data(), K.Z.data(), (const double *)K.alu.data(), (size_t)n, red, &K.ctl, K.partial.data(), K.counter.data(), pv, af);
+        pending = af.publish_seq;
+      }
+      {
+        P2PArgs ac;
+        ac.consume_seq = pending;
+        emul_launch_blocks(1, 32, cg_check_kernel, iters + 1, red, &K.ctl, K.hist.data(), iters + 1, pv, ac);
+      }
+      memcpy(X_out[me], K.X.data(), sizeof(double) * 3 * (size_t)np);
+      memcpy(hist_out[me], K.hist.data(), sizeof(double) * (size_t)iters);
+      err_out[me] = K.err[0] | (K.ctl.phase << 8);
+    });
+  for (auto &t : th) t.join();
+  pthread_barrier_destroy(&bar);
   return 0;
 }
 

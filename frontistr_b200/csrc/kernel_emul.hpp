@@ -5,8 +5,13 @@
 //   emul_launch_warps : the one-element-per-warp kernels (stiff / update / self-test) run UNCHANGED, every warp by 32
 //                       host threads in lock step (__syncwarp / shuffles = barriers, emul_test.cpp), warps one after
 //                       the other, dynamic shared memory = a host buffer per block
-// so that the kernels' own index arithmetic, staging and store patterns are exercised by the CPU unit tests without
-// a GPU.  The product library never sees this header.
+//   emul_launch_blocks: block-cooperative kernels (SpMV, CG, grid reductions; __syncthreads, static __shared__, warp
+//                       shuffles / ballots) run UNCHANGED: the threads of a block are cooperative fibers of ONE host
+//                       thread that switch at every barrier / collective, blocks one after the other.  Several host
+//                       threads can each run their own launches concurrently = several "GPUs" (ranks), which is how
+//                       the peer-memory protocol of p2p.cuh is exercised with 2 / 4 / 8 ranks;
+// so that the kernels' own index arithmetic, staging, store patterns and inter-rank protocol are exercised by the CPU
+// unit tests without a GPU.  The product library never sees this header.
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
@@ -16,12 +21,22 @@
 #include <random>
 #include <vector>
 
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
 #define __global__
 #define __device__
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __restrict__
+#define __shared__ static thread_local   /* one block at a time per host thread (= per emulated GPU) */
+
+struct int2 { int x, y; };
+struct int4 { int x, y, z, w; };
 
 // CUDA's 16-byte vector of two doubles.  Every copy checks that both addresses are 16-byte aligned (a misaligned
 // double2 access is a hardware fault on the GPU: "misaligned address"); violations are counted, never ignored.
@@ -35,10 +50,11 @@ struct alignas(16) double2 {
 };
 
 namespace fb {
-namespace emulwarp {   // lock-step warp collectives, defined in emul_test.cpp
+namespace emulwarp {   // warp collectives, defined in emul_test.cpp: lock-step host threads (emul_launch_warps) or fibers (emul_launch_blocks)
 double shfl(double v, int src);
 int shfl(int v, int src);
 void syncwarp();
+void syncthreads();
 }
 constexpr int kWarp = 32;
 struct EmulDim { unsigned x = 1, y = 1, z = 1; };
@@ -58,9 +74,34 @@ inline int atomicExch(int *p, int v) { return __atomic_exchange_n(p, v, __ATOMIC
 inline unsigned char *&emul_smem() { static unsigned char *p = nullptr; return p; }   // dynamic shared memory of the running block
 #define FB_DYNAMIC_SMEM(name) unsigned char *name = fb::emul_smem()
 inline void __syncwarp() { emulwarp::syncwarp(); }
+inline void __syncthreads() { emulwarp::syncthreads(); }
 inline double __shfl_xor_sync(unsigned, double v, int o) { return emulwarp::shfl(v, (int)((threadIdx.x & 31) ^ (unsigned)o)); }
+inline double __shfl_sync(unsigned, double v, int src) { return emulwarp::shfl(v, src); }
+inline int __shfl_sync(unsigned, int v, int src) { return emulwarp::shfl(v, src); }
+inline unsigned __ballot_sync(unsigned, bool pred) {
+  unsigned bits = 0;
+  for (int l = 0; l < 32; l++) bits |= (unsigned)(emulwarp::shfl(pred ? 1 : 0, l) & 1) << l;
+  return bits;
+}
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline double __ldcg(const double *p) { return *(const volatile double *)p; }
 inline double ld_stream(const double *p) { return *p; }
 inline int ld_stream(const int *p) { return *p; }
+inline double2 ld_stream2(const double2 *p) { return *p; }
+inline int2 ld_stream2(const int2 *p) { return *p; }
+inline int4 ld_stream4(const int4 *p) { return *p; }
+
+// malloc-backed stand-in of the product's device buffer (only so that host structs holding DevBuf members compile)
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  bool owned = true;
+  int alloc(size_t count) { release(); p = (T *)calloc(count ? count : 1, sizeof(T)); n = count; return p ? 0 : -1; }
+  void view(T *ptr, size_t count) { release(); p = ptr; n = count; owned = false; }
+  void release() { if (p && owned) free(p); p = nullptr; n = 0; owned = true; }
+};
 
 // kernel<<<grid, block>>>(args...): every (block, thread) pair runs to completion, in a seeded random order
 template <class K, class... A>

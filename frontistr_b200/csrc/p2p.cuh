@@ -44,6 +44,14 @@ struct P2PNeighbors {
   int rank[kP2PMaxRanks];
 };
 
+#ifdef FB_EMUL_KERNELS   // TEST-ONLY host stand-ins: the "GPUs" are host threads, system scope = process memory
+inline unsigned long long ld_acquire_sys(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void st_release_sys(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline void st_relaxed_sys(double *p, double v) { uint64_t b; __builtin_memcpy(&b, &v, 8); __atomic_store_n(reinterpret_cast<uint64_t *>(p), b, __ATOMIC_RELAXED); }
+inline double ld_relaxed_sys(const double *p) { const uint64_t b = __atomic_load_n(reinterpret_cast<const uint64_t *>(p), __ATOMIC_RELAXED); double v; __builtin_memcpy(&v, &b, 8); return v; }
+inline void st_relaxed_sys(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
+unsigned long long p2p_now_ns();   // emul_test.cpp (steady clock)
+#else
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -65,11 +73,12 @@ __device__ __forceinline__ unsigned long long p2p_now_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-constexpr unsigned long long kP2PTimeoutNs = 2000000000ull;   // 2 s; once any wait on this GPU has timed out, later waits give up at once
-
 __device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+
+#endif
+constexpr unsigned long long kP2PTimeoutNs = 2000000000ull;   // 2 s; once any wait on this GPU has timed out, later waits give up at once
 
 // ONE WARP (all 32 lanes call): lane r hands this rank's partial sums to rank r (itself included):
 // values, one system-scope fence, then the tag (fence + relaxed store = release pattern).
