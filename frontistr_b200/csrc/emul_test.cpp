@@ -704,6 +704,55 @@ int fbemul_p2p_cg(int R, const int *N, const int *NP, const double *const *D, co
   return 0;
 }
 
+// fistr_b200_matvec_33 on one emulated GPU: the private SELL copy (sell_layout + sell_fill_kernel) and the SpMV kernel of
+// the chosen variant (0 native, 1 SELL, 2 pair-interleaved SELL; sigma > 1: SELL-C-sigma), mode 0 y = A x / 1 y = b - A x,
+// launched as api_internal.inc: build_sell / launch_spmv do.  red_out receives the fused dot product.
+int fbemul_spmv(int N, int NP, const double *D, const double *AL, const double *AU, const int *indexL, const int *itemL,
+                const int *indexU, const int *itemU, int variant, int sigma, int mode, const double *x, const double *b,
+                double *y, double *red_out) {
+  using namespace fb;
+  (void)NP;
+  constexpr int BLOCK = 256;
+  std::vector<double> partial(65536, 0.0);
+  std::vector<unsigned> counter(4, 0u);
+  double red = 0.0;
+  if (variant == 0) {
+    if (mode == 0) emul_launch_blocks(3, BLOCK, spmv_native_kernel<0, BLOCK>, N, D, AL, AU, indexL, itemL, indexU, itemU, x, b, y, partial.data(), counter.data(), &red, (const int *)nullptr);
+    else emul_launch_blocks(3, BLOCK, spmv_native_kernel<1, BLOCK>, N, D, AL, AU, indexL, itemL, indexU, itemU, x, b, y, partial.data(), counter.data(), &red, (const int *)nullptr);
+  } else {
+    std::vector<int> rowperm;
+    std::vector<long long> sp;
+    sell_layout(N, indexL, indexU, sigma, variant, rowperm, sp);
+    const int nslice = (N + 31) / 32;
+    const size_t cols = (size_t)sp[nslice] * (variant == 2 ? 2 : 1);
+    std::vector<double> valv(cols * 288 + 2, 0.0);
+    std::vector<int> colv(cols * 32 + 2, 0);
+    std::vector<unsigned char> halo((size_t)nslice + 1, 0);
+    double *val = valv.data() + ((reinterpret_cast<uintptr_t>(valv.data()) % 16) ? 1 : 0);
+    int *col = colv.data() + ((reinterpret_cast<uintptr_t>(colv.data()) % 8) ? 1 : 0);
+    const int *rp = rowperm.empty() ? nullptr : rowperm.data();
+    const unsigned fb_blocks = (unsigned)((nslice * 32 + 255) / 256);
+    if (nslice > 0) {
+      if (variant == 2) emul_launch_blocks(fb_blocks, 256, sell_fill_kernel<2>, N, D, AL, AU, indexL, itemL, indexU, itemU, (const long long *)sp.data(), val, col, halo.data(), rp);
+      else emul_launch_blocks(fb_blocks, 256, sell_fill_kernel<1>, N, D, AL, AU, indexL, itemL, indexU, itemU, (const long long *)sp.data(), val, col, halo.data(), rp);
+    }
+    P2PView pv; P2PNeighbors nb; P2PArgs pa;
+#define FB_S1 N, nslice, (const long long *)sp.data(), (const double *)val, (const int *)col, x, b, y, partial.data(), counter.data(), &red, (const int *)nullptr, rp
+#define FB_S2 N, nslice, (const long long *)sp.data(), (const double *)val, (const int *)col, x, b, y, partial.data(), counter.data(), &red, (const int *)nullptr, pv, nb, pa, (const unsigned char *)halo.data(), rp
+    if (variant == 1) {
+      if (mode == 0) emul_launch_blocks(3, BLOCK, spmv_sell1_kernel<0, BLOCK>, FB_S1);
+      else emul_launch_blocks(3, BLOCK, spmv_sell1_kernel<1, BLOCK>, FB_S1);
+    } else {
+      if (mode == 0) emul_launch_blocks(3, BLOCK, spmv_sell2_kernel<0, BLOCK, false>, FB_S2);
+      else emul_launch_blocks(3, BLOCK, spmv_sell2_kernel<1, BLOCK, false>, FB_S2);
+    }
+#undef FB_S1
+#undef FB_S2
+  }
+  if (red_out) *red_out = red;
+  return 0;
+}
+
 // number of misaligned double2 accesses seen so far by the emulated kernels (must stay 0), and a negative control
 long fbemul_misaligned_count(void) { return emul_misaligned_count(); }
 long fbemul_misaligned_probe(void) {

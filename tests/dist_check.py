@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--precond", type=int, default=3)
     ap.add_argument("--tol", type=float, default=1e-10)
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"])
+    ap.add_argument("--stress", action="store_true", help="also run the strain / stress recovery (update_3d + nodal_stress_3d) on "
+                    "every rank and compare the internal nodes with the oracle's serial fstr_NodalStress3D")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -54,6 +56,14 @@ def main():
     t = torch.tensor([halo_err], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ok = True
+    sg = None
+    if args.stress:      # every rank works on its own local mesh (overlap elements included): no exchange needed
+        hecmw.fstr_UpdateNewton_linear(m, None, A.X)
+        ns = hecmw.fstr_NodalStress3D(m)
+        sg = torch.zeros((gmesh.n_node, 13), dtype=torch.float64, device="cuda")
+        loc = np.concatenate([ns["STRAIN"], ns["STRESS"], ns["MISES"][:, None]], axis=1)[: m.nn_internal]
+        sg[own] = torch.from_numpy(np.ascontiguousarray(loc)).cuda()
+        dist.all_reduce(sg)
     if rank == 0:
         from oracle import oracle as orc
         Ao = util.oracle_problem(gmesh, cnt)
@@ -62,6 +72,13 @@ def main():
         err = util.rel_l2(xgl.reshape(-1), Ao.X)
         it_ok = abs(r["iter"] - ro["iter"]) <= 2 if args.precond == 3 else True   # SSOR is subdomain-local
         ok = (r["error"] == 0 and it_ok and err <= 1e-9 and r["resid2"] < args.tol and float(t.item()) == 0.0)
+        if sg is not None:
+            e, s_, q = orc.update_linear(gmesh, xgl.reshape(-1))
+            no = orc.nodal_stress_3d(gmesh, e, s_)
+            ref = np.concatenate([no["STRAIN"], no["STRESS"], no["MISES"][:, None]], axis=1)
+            serr = float(np.abs(sg.cpu().numpy() - ref).max() / np.abs(ref).max())
+            ok = ok and serr <= 1e-10
+            print("     nodal strain / stress / Mises on the partitioned mesh vs serial oracle: max rel dev %.2e" % serr, flush=True)
         print("%s dist_check world=%d comm=%s mesh=%s precond=%d: iter gpu=%d oracle=%d  rel_l2=%.2e  resid2=%.2e  halo_err=%.1e  neighbors=%d"
               % ("PASS" if ok else "FAIL", world, args.comm, ("tet%d" % args.tet) if args.tet else ("hex%d" % args.n), args.precond,
                  r["iter"], ro["iter"], err, r["resid2"], float(t.item()), m.n_neighbor_pe), flush=True)

@@ -1,8 +1,9 @@
 """TEST INFRASTRUCTURE: a CPU stand-in for the `gpu` fixture whose assembly / Dirichlet elimination / strain-stress
 update / nodal-stress entry points execute the PRODUCT'S OWN CUDA KERNELS on the host (libfistr_b200_emul.so:
 assembly.cuh compiled unchanged through csrc/kernel_emul.hpp — warps as 32 lock-step host threads, grid-stride
-kernels thread after thread in scrambled order — and launched in the sequence of csrc/api_assembly.inc).  Only the
-Krylov solve and the SpMV (block-cooperative kernels, all validated on hardware in round 1) are delegated to the oracle.
+kernels thread after thread in scrambled order — and launched in the sequence of csrc/api_assembly.inc).  The SpMV runs the
+product's kernels too (blocks of fibers); only the Krylov solve is delegated to the oracle (the CG kernels are exercised
+separately, on several emulated ranks, by tests/test_p2p_kernels_emulated.py).
 
 Used to run the bodies of GPU tests whose kernels have not run on hardware yet, so that what they assert is checked
 against real kernel code before a GPU minute is spent.  It is NOT the product path and proves nothing about launch
@@ -114,8 +115,17 @@ class EmulBackend:
         return r
 
     def hecmw_matvec(self, X, n_internal3):
-        from oracle import oracle as orc
-        return orc.matvec(self._A, np.ascontiguousarray(X, float))[:n_internal3]
+        """fistr_b200_matvec_33 (single rank): SELL repack + the SpMV kernel of the selected variant, on the host."""
+        A = self._A
+        x = np.ascontiguousarray(X, np.float64)
+        y = np.zeros(3 * A.NP)
+        red = C.c_double(0.0)
+        v = self.opts.get("spmv_variant", 2)
+        rc = self.em.fbemul_spmv(A.N, A.NP, _d(A.D), _d(A.AL), _d(A.AU), _i(A.indexL), _i(A.itemL), _i(A.indexU), _i(A.itemU),
+                                 int(v if v in (0, 1, 2) else 2), int(max(self.opts.get("sell_sigma", 0), 0)), 0, _d(x), None, _d(y),
+                                 C.byref(red))
+        assert rc == 0 and self.em.fbemul_misaligned_count() == 0
+        return y[:n_internal3]
 
     # ---- linear strain / stress recovery
     def fstr_UpdateNewton_linear(self, mesh, unode, dunode, temperature=None, temperature0=None, ref_temp=0.0):

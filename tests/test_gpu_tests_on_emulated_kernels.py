@@ -53,3 +53,16 @@ def test_emulated_nonlinear_newton_loop_reproduces_the_reference_logs(name):
     same Newton iteration counts as the oracle's loop, the reference's exI golden log at every sub-step, and the
     strain / stress / Mises lines of the final state."""
     Z.test_nlgeom_newton_matches_oracle_and_golden(EmulBackend(), name)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("name", ["hex5_ic", "tet3", "hex1", "hex_ragged"])
+def test_emulated_spmv_bitwise(name, variant):
+    """The SpMV kernels (native, SELL, pair-interleaved SELL incl. the repack kernel) on the host: bit-identical to the
+    oracle, as on the GPU (same fma chain per row)."""
+    G.test_spmv_bitwise(EmulBackend(), name, variant)
+
+
+@pytest.mark.parametrize("meshname", ["tet3", "hex_ragged"])
+def test_emulated_sell_c_sigma(meshname):
+    Z.test_sell_sigma_is_bitwise_identical_per_row(EmulBackend(), meshname)
