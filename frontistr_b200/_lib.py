@@ -29,17 +29,21 @@ def lib():
         if not os.path.exists(SO_PATH):
             raise FistrB200Error(-2, "%s not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
                                      "there is no CPU fallback" % SO_PATH)
-        L = C.CDLL(SO_PATH)
-        L.fistr_b200_last_error.restype = C.c_char_p
-        L.fistr_b200_launch_count.restype = C.c_int64
-        L.fistr_b200_get_option.restype = C.c_int64
-        L.fistr_b200_set_option.argtypes = [C.c_char_p, C.c_int64]
-        L.fistr_b200_get_option.argtypes = [C.c_char_p]
-        L.fistr_b200_host_register.argtypes = [C.c_void_p, C.c_int64]
-        L.fistr_b200_host_unregister.argtypes = [C.c_void_p]
-        L.fistr_b200_precond_33_setup.argtypes = [C.c_int, C.c_double, C.c_int]
-        _lib = L
+        _lib = declare(C.CDLL(SO_PATH))
     return _lib
+
+
+def declare(L):
+    """ctypes prototypes of the entry points whose defaults (int arguments, int result) do not fit"""
+    L.fistr_b200_last_error.restype = C.c_char_p
+    L.fistr_b200_launch_count.restype = C.c_int64
+    L.fistr_b200_get_option.restype = C.c_int64
+    L.fistr_b200_set_option.argtypes = [C.c_char_p, C.c_int64]
+    L.fistr_b200_get_option.argtypes = [C.c_char_p]
+    L.fistr_b200_host_register.argtypes = [C.c_void_p, C.c_int64]
+    L.fistr_b200_host_unregister.argtypes = [C.c_void_p]
+    L.fistr_b200_precond_33_setup.argtypes = [C.c_int, C.c_double, C.c_int]
+    return L
 
 
 def check(rc: int, allow_solver_codes: bool = False) -> int:

@@ -155,7 +155,6 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], double *partial, un
   }
 }
 
-#ifndef FB_EMUL_KERNELS   // (a malloc-backed stand-in lives in kernel_emul.hpp)
 template <class T>
 struct DevBuf {
   T *p = nullptr;
@@ -186,6 +185,5 @@ struct DevBuf {
     owned = true;
   }
 };
-#endif
 
 }  // namespace fb

@@ -1,0 +1,83 @@
+// TEST-ONLY host stand-in for the part of the CUDA runtime (and of cub::DeviceScan) that the fistr_b200 library uses.
+// "Device memory" is host memory, streams execute immediately, events are wall-clock stamps, one "device" with two
+// "SMs" (so that launch grids stay small).  Together with kernel_emul.hpp (kernels as fibers) and the launch-syntax
+// rewrite of tools/build_hostemu.py it lets the WHOLE library — C-ABI, caches, option handling, launch sequences —
+// be compiled by g++ into frontistr_b200/libfistr_b200_hostemu.so, which tests/test_gpu_suite_on_host_api.py loads in
+// place of the product library to run the GPU test bodies on the CPU.  Never part of the product build.
+#pragma once
+#include <chrono>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorNotSupported = 801 };
+typedef struct CUstream_st_emul *cudaStream_t;
+struct cudaEventEmul { double t; };
+typedef cudaEventEmul *cudaEvent_t;
+enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+enum { cudaStreamNonBlocking = 1, cudaHostRegisterPortable = 1, cudaIpcMemLazyEnablePeerAccess = 1 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+struct cudaIpcMemHandle_t { char reserved[64]; };
+struct cudaDeviceProp {
+  char name[256];
+  int multiProcessorCount;
+  size_t totalGlobalMem;
+};
+
+inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : (e == cudaErrorMemoryAllocation ? "out of memory" : "not supported by the host emulation"); }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaDeviceReset() { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
+  memset(p, 0, sizeof *p);
+  strcpy(p->name, "host emulation (TEST ONLY)");
+  p->multiProcessorCount = 2;
+  p->totalGlobalMem = (size_t)8 << 30;
+  return cudaSuccess;
+}
+inline cudaError_t cudaMalloc(void **p, size_t bytes) {
+  void *q = nullptr;
+  if (posix_memalign(&q, 256, bytes ? bytes : 1)) { *p = nullptr; return cudaErrorMemoryAllocation; }
+  memset(q, 0xA5, bytes);   // like device memory: NOT zeroed (a poison pattern makes a missing initialisation visible)
+  *p = q;
+  return cudaSuccess;
+}
+template <class T>
+inline cudaError_t cudaMalloc(T **p, size_t bytes) { return cudaMalloc((void **)p, bytes); }
+inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { if (n) memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemset(void *d, int v, size_t n) { if (n) memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t = nullptr) { if (n) memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = nullptr; return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+inline double cuda_shim_now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new cudaEventEmul{0.0}; return cudaSuccess; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = cuda_shim_now_ms(); return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t - a->t); return cudaSuccess; }
+template <class F>
+inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+inline cudaError_t cudaHostRegister(void *, size_t, unsigned) { return cudaSuccess; }
+inline cudaError_t cudaHostUnregister(void *) { return cudaSuccess; }
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorNotSupported; }
+inline cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
+
+namespace cub {
+struct DeviceScan {
+  // two-phase API as in CUB: d_temp == nullptr only reports the scratch size
+  template <class In, class Out>
+  static cudaError_t ExclusiveSum(void *d_temp, size_t &temp_bytes, In in, Out out, int n, cudaStream_t = nullptr) {
+    if (!d_temp) { temp_bytes = 64; return cudaSuccess; }
+    typename std::remove_reference<decltype(out[0])>::type run = 0;
+    for (int i = 0; i < n; i++) { const auto v = in[i]; out[i] = run; run += v; }
+    return cudaSuccess;
+  }
+};
+}  // namespace cub

@@ -16,160 +16,11 @@
 
 using namespace fb::elem;
 
-// ---- execution models behind the warp / block collectives -------------------------------------------------------
-// (a) emul_launch_warps: 32 host threads per warp, every collective is a pthread-barrier-separated exchange;
-// (b) emul_launch_blocks: the threads of a block are cooperative fibers (ucontext) of the calling host thread; a fiber
-//     that reaches __syncthreads / __syncwarp / a shuffle parks itself and the scheduler releases the block (warp) once
-//     every live fiber of it has arrived.  Everything is per host thread, so several host threads = several "GPUs".
-#include <ucontext.h>
-
-#include <chrono>
-#include <functional>
-#include <memory>
-
 namespace fb {
 thread_local std::string g_last_error;
 int64_t g_launch_count = 0;
-unsigned long long p2p_now_ns() {
-  return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
-namespace emulwarp {
-static pthread_barrier_t g_bar;
-static thread_local int t_lane = 0;
-static double g_slot_d[32];
-static int g_slot_i[32];
-
-struct Fiber {
-  ucontext_t ctx;
-  std::unique_ptr<char[]> stack;
-  int state = 0;   // 0 runnable, 1 parked at the block barrier, 2 parked at the warp barrier, 3 finished
-};
-struct FiberBlock {
-  std::vector<Fiber> f;
-  ucontext_t main;
-  int cur = -1;
-  unsigned grid = 1, block = 1, bidx = 0;
-  std::function<void()> body;
-  std::vector<double> slot_d;
-  std::vector<int> slot_i;
-};
-static thread_local FiberBlock *t_fb = nullptr;   // non-null while this host thread runs a fiber block
-
-static void fiber_yield(int state) {
-  FiberBlock &B = *t_fb;
-  B.f[B.cur].state = state;
-  swapcontext(&B.f[B.cur].ctx, &B.main);
-}
-static void fiber_entry() {
-  FiberBlock &B = *t_fb;
-  B.body();
-  B.f[B.cur].state = 3;
-  swapcontext(&B.f[B.cur].ctx, &B.main);
-}
-static void run_fiber_block(FiberBlock &B) {
-  constexpr size_t STACK = 96 * 1024;
-  const int n = (int)B.block;
-  B.f.resize(n);
-  B.slot_d.assign(n, 0.0); B.slot_i.assign(n, 0);
-  t_fb = &B;
-  for (int i = 0; i < n; i++) {
-    Fiber &F = B.f[i];
-    F.stack.reset(new char[STACK]);
-    getcontext(&F.ctx);
-    F.ctx.uc_stack.ss_sp = F.stack.get(); F.ctx.uc_stack.ss_size = STACK; F.ctx.uc_link = &B.main;
-    makecontext(&F.ctx, fiber_entry, 0);
-    F.state = 0;
-  }
-  for (;;) {
-    bool ran = false, alive = false;
-    for (int i = 0; i < n; i++) {
-      if (B.f[i].state != 0) continue;
-      B.cur = i;
-      fb::gridDim.x = B.grid; fb::blockDim.x = B.block; fb::blockIdx.x = B.bidx; fb::threadIdx.x = (unsigned)i;
-      swapcontext(&B.main, &B.f[i].ctx);
-      ran = true;
-    }
-    // release barriers whose every live participant has arrived
-    bool all_block = true, any_block = false;
-    for (int i = 0; i < n; i++) {
-      if (B.f[i].state != 3) alive = true;
-      if (B.f[i].state == 1) any_block = true;
-      else if (B.f[i].state != 3) all_block = false;
-    }
-    if (!alive) break;
-    bool released = false;
-    if (any_block && all_block) { for (int i = 0; i < n; i++) if (B.f[i].state == 1) B.f[i].state = 0; released = true; }
-    for (int w = 0; w * 32 < n; w++) {
-      bool all = true, any = false;
-      for (int i = w * 32; i < std::min(n, w * 32 + 32); i++) {
-        if (B.f[i].state == 2) any = true;
-        else if (B.f[i].state != 3) all = false;
-      }
-      if (any && all) { for (int i = w * 32; i < std::min(n, w * 32 + 32); i++) if (B.f[i].state == 2) B.f[i].state = 0; released = true; }
-    }
-    if (!ran && !released) { fprintf(stderr, "emul: fiber block dead-locked (divergent barrier)\n"); abort(); }
-  }
-  t_fb = nullptr;
-}
-
-double shfl(double v, int src) {
-  if (t_fb) {
-    FiberBlock &B = *t_fb;
-    const int me = B.cur, base = me & ~31;
-    B.slot_d[me] = v;
-    fiber_yield(2);
-    const double r = B.slot_d[base + (src & 31)];
-    fiber_yield(2);
-    return r;
-  }
-  g_slot_d[t_lane] = v;
-  pthread_barrier_wait(&g_bar);
-  const double r = g_slot_d[src & 31];
-  pthread_barrier_wait(&g_bar);
-  return r;
-}
-int shfl(int v, int src) {
-  if (t_fb) {
-    FiberBlock &B = *t_fb;
-    const int me = B.cur, base = me & ~31;
-    B.slot_i[me] = v;
-    fiber_yield(2);
-    const int r = B.slot_i[base + (src & 31)];
-    fiber_yield(2);
-    return r;
-  }
-  g_slot_i[t_lane] = v;
-  pthread_barrier_wait(&g_bar);
-  const int r = g_slot_i[src & 31];
-  pthread_barrier_wait(&g_bar);
-  return r;
-}
-void syncwarp() { if (t_fb) fiber_yield(2); else pthread_barrier_wait(&g_bar); }
-void syncthreads() {
-  if (!t_fb) { fprintf(stderr, "emul: __syncthreads outside emul_launch_blocks\n"); abort(); }
-  fiber_yield(1);
-}
-template <class F>
-static void run_warp(F f) {   // f(lane) on 32 threads in lock step
-  pthread_barrier_init(&g_bar, nullptr, 32);
-  std::vector<std::thread> th;
-  for (int lane = 0; lane < 32; lane++) th.emplace_back([lane, &f]() { t_lane = lane; f(lane); });
-  for (auto &t : th) t.join();
-  pthread_barrier_destroy(&g_bar);
-}
-} }
-
-// kernel<<<grid, block>>>(args...) for block-cooperative kernels: blocks one after the other, the threads of a block as
-// fibers of the calling host thread (see above)
-template <class K, class... A>
-static void emul_launch_blocks(unsigned grid, unsigned block, K kernel, A... args) {
-  for (unsigned b = 0; b < grid; b++) {
-    fb::emulwarp::FiberBlock B;
-    B.grid = grid; B.block = block; B.bidx = b;
-    B.body = [&]() { kernel(args...); };
-    fb::emulwarp::run_fiber_block(B);
-  }
-}
+#include "kernel_emul_impl.hpp"   // lock-step warps (host threads) and blocks of fibers; fb::EmulCfg
 
 // kernel<<<grid, warps*32, smem>>>(args...) for the one-element-per-warp kernels: every warp of every block by 32 host
 // threads in lock step, warps one after the other (the warps of these kernels never talk to each other)

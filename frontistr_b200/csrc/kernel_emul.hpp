@@ -21,6 +21,10 @@
 #include <random>
 #include <vector>
 
+#include <type_traits>
+
+#include "cuda_shim.hpp"   // host stand-in of the CUDA runtime subset the library uses
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -91,17 +95,6 @@ inline int ld_stream(const int *p) { return *p; }
 inline double2 ld_stream2(const double2 *p) { return *p; }
 inline int2 ld_stream2(const int2 *p) { return *p; }
 inline int4 ld_stream4(const int4 *p) { return *p; }
-
-// malloc-backed stand-in of the product's device buffer (only so that host structs holding DevBuf members compile)
-template <class T>
-struct DevBuf {
-  T *p = nullptr;
-  size_t n = 0;
-  bool owned = true;
-  int alloc(size_t count) { release(); p = (T *)calloc(count ? count : 1, sizeof(T)); n = count; return p ? 0 : -1; }
-  void view(T *ptr, size_t count) { release(); p = ptr; n = count; owned = false; }
-  void release() { if (p && owned) free(p); p = nullptr; n = 0; owned = true; }
-};
 
 // kernel<<<grid, block>>>(args...): every (block, thread) pair runs to completion, in a seeded random order
 template <class K, class... A>

@@ -1,0 +1,249 @@
+// TEST-ONLY: implementation of the execution models behind kernel_emul.hpp.  Included by exactly one translation unit
+// per shared library (emul_test.cpp for libfistr_b200_emul.so, the rewritten capi.cu for libfistr_b200_hostemu.so).
+#pragma once
+#include <pthread.h>
+#include <ucontext.h>
+
+#include <chrono>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+// ---- execution models behind the warp / block collectives -------------------------------------------------------
+// (a) emul_launch_warps: 32 host threads per warp, every collective is a pthread-barrier-separated exchange;
+// (b) emul_launch_blocks: the threads of a block are cooperative fibers (ucontext) of the calling host thread; a fiber
+//     that reaches __syncthreads / __syncwarp / a shuffle parks itself and the scheduler releases the block (warp) once
+//     every live fiber of it has arrived.  Everything is per host thread, so several host threads = several "GPUs".
+
+namespace fb {
+unsigned long long p2p_now_ns() {
+  return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+namespace emulwarp {
+static pthread_barrier_t g_bar;
+static thread_local int t_lane = 0;
+static double g_slot_d[32];
+static int g_slot_i[32];
+
+// Context switch.  glibc's swapcontext saves / restores the signal mask with two system calls per switch, and a block
+// of 256 fibers switches ~10^4 times per kernel: on x86-64 a 12-instruction switch of the callee-saved registers is
+// used instead (about 50x faster); ucontext stays as the portable fall-back.
+#if defined(__x86_64__) && !defined(FB_EMUL_UCONTEXT)
+#define FB_EMUL_ASM_SWITCH 1
+extern "C" void fb_emul_ctx_switch(void **save_sp, void *load_sp);
+asm(R"(
+.text
+.hidden fb_emul_ctx_switch
+.globl fb_emul_ctx_switch
+.type fb_emul_ctx_switch,@function
+fb_emul_ctx_switch:
+  pushq %rbp
+  pushq %rbx
+  pushq %r12
+  pushq %r13
+  pushq %r14
+  pushq %r15
+  movq %rsp, (%rdi)
+  movq %rsi, %rsp
+  popq %r15
+  popq %r14
+  popq %r13
+  popq %r12
+  popq %rbx
+  popq %rbp
+  ret
+.size fb_emul_ctx_switch,.-fb_emul_ctx_switch
+)");
+#endif
+
+struct Fiber {
+#ifdef FB_EMUL_ASM_SWITCH
+  void *sp = nullptr;
+#else
+  ucontext_t ctx;
+#endif
+  std::unique_ptr<char[]> stack;
+  int state = 0;   // 0 runnable, 1 parked at the block barrier, 2 parked at the warp barrier, 3 finished
+};
+struct FiberBlock {
+  std::vector<Fiber> f;
+#ifdef FB_EMUL_ASM_SWITCH
+  void *main_sp = nullptr;
+#else
+  ucontext_t main;
+#endif
+  int cur = -1;
+  unsigned grid = 1, block = 1, bidx = 0;
+  std::function<void()> body;
+  std::vector<double> slot_d;
+  std::vector<int> slot_i;
+};
+static thread_local FiberBlock *t_fb = nullptr;   // non-null while this host thread runs a fiber block
+
+static void fiber_to_main(FiberBlock &B) {
+#ifdef FB_EMUL_ASM_SWITCH
+  fb_emul_ctx_switch(&B.f[B.cur].sp, B.main_sp);
+#else
+  swapcontext(&B.f[B.cur].ctx, &B.main);
+#endif
+}
+static void fiber_yield(int state) {
+  FiberBlock &B = *t_fb;
+  B.f[B.cur].state = state;
+  fiber_to_main(B);
+}
+static void fiber_entry() {
+  FiberBlock &B = *t_fb;
+  B.body();
+  B.f[B.cur].state = 3;
+  fiber_to_main(B);
+  abort();   // a finished fiber is never resumed
+}
+static thread_local std::vector<Fiber> t_fiber_pool;   // stacks are reused from launch to launch
+static void run_fiber_block(FiberBlock &B) {
+  constexpr size_t STACK = 96 * 1024;
+  const int n = (int)B.block;
+  B.f.swap(t_fiber_pool);
+  if ((int)B.f.size() < n) B.f.resize(n);
+  B.slot_d.assign(n, 0.0); B.slot_i.assign(n, 0);
+  t_fb = &B;
+  for (int i = 0; i < n; i++) {
+    Fiber &F = B.f[i];
+    if (!F.stack) F.stack.reset(new char[STACK]);
+#ifdef FB_EMUL_ASM_SWITCH
+    {   // initial frame: six callee-saved registers (zero) below the "return address" fiber_entry; at its first
+        // instruction rsp == 8 (mod 16), as after a call
+      uintptr_t top = (reinterpret_cast<uintptr_t>(F.stack.get()) + STACK) & ~(uintptr_t)15;
+      void **a = reinterpret_cast<void **>(top - 16);
+      a[0] = reinterpret_cast<void *>(&fiber_entry);
+      a[1] = nullptr;
+      for (int r = 1; r <= 6; r++) a[-r] = nullptr;
+      F.sp = a - 6;
+    }
+#else
+    getcontext(&F.ctx);
+    F.ctx.uc_stack.ss_sp = F.stack.get(); F.ctx.uc_stack.ss_size = STACK; F.ctx.uc_link = &B.main;
+    makecontext(&F.ctx, fiber_entry, 0);
+#endif
+    F.state = 0;
+  }
+  for (;;) {
+    bool ran = false, alive = false;
+    for (int i = 0; i < n; i++) {
+      if (B.f[i].state != 0) continue;
+      B.cur = i;
+      fb::gridDim.x = B.grid; fb::blockDim.x = B.block; fb::blockIdx.x = B.bidx; fb::threadIdx.x = (unsigned)i;
+#ifdef FB_EMUL_ASM_SWITCH
+      fb_emul_ctx_switch(&B.main_sp, B.f[i].sp);
+#else
+      swapcontext(&B.main, &B.f[i].ctx);
+#endif
+      ran = true;
+    }
+    // release barriers whose every live participant has arrived
+    bool all_block = true, any_block = false;
+    for (int i = 0; i < n; i++) {
+      if (B.f[i].state != 3) alive = true;
+      if (B.f[i].state == 1) any_block = true;
+      else if (B.f[i].state != 3) all_block = false;
+    }
+    if (!alive) break;
+    bool released = false;
+    if (any_block && all_block) { for (int i = 0; i < n; i++) if (B.f[i].state == 1) B.f[i].state = 0; released = true; }
+    for (int w = 0; w * 32 < n; w++) {
+      bool all = true, any = false;
+      for (int i = w * 32; i < std::min(n, w * 32 + 32); i++) {
+        if (B.f[i].state == 2) any = true;
+        else if (B.f[i].state != 3) all = false;
+      }
+      if (any && all) { for (int i = w * 32; i < std::min(n, w * 32 + 32); i++) if (B.f[i].state == 2) B.f[i].state = 0; released = true; }
+    }
+    if (!ran && !released) { fprintf(stderr, "emul: fiber block dead-locked (divergent barrier)\n"); abort(); }
+  }
+  t_fb = nullptr;
+  B.f.swap(t_fiber_pool);
+}
+
+double shfl(double v, int src) {
+  if (t_fb) {
+    FiberBlock &B = *t_fb;
+    const int me = B.cur, base = me & ~31;
+    B.slot_d[me] = v;
+    fiber_yield(2);
+    const double r = B.slot_d[base + (src & 31)];
+    fiber_yield(2);
+    return r;
+  }
+  g_slot_d[t_lane] = v;
+  pthread_barrier_wait(&g_bar);
+  const double r = g_slot_d[src & 31];
+  pthread_barrier_wait(&g_bar);
+  return r;
+}
+int shfl(int v, int src) {
+  if (t_fb) {
+    FiberBlock &B = *t_fb;
+    const int me = B.cur, base = me & ~31;
+    B.slot_i[me] = v;
+    fiber_yield(2);
+    const int r = B.slot_i[base + (src & 31)];
+    fiber_yield(2);
+    return r;
+  }
+  g_slot_i[t_lane] = v;
+  pthread_barrier_wait(&g_bar);
+  const int r = g_slot_i[src & 31];
+  pthread_barrier_wait(&g_bar);
+  return r;
+}
+void syncwarp() { if (t_fb) fiber_yield(2); else pthread_barrier_wait(&g_bar); }
+void syncthreads() {
+  if (!t_fb) { fprintf(stderr, "emul: __syncthreads outside emul_launch_blocks\n"); abort(); }
+  fiber_yield(1);
+}
+template <class F>
+static void run_warp(F f) {   // f(lane) on 32 threads in lock step
+  pthread_barrier_init(&g_bar, nullptr, 32);
+  std::vector<std::thread> th;
+  for (int lane = 0; lane < 32; lane++) th.emplace_back([lane, &f]() { t_lane = lane; f(lane); });
+  for (auto &t : th) t.join();
+  pthread_barrier_destroy(&g_bar);
+}
+} }
+
+// kernel<<<grid, block>>>(args...) for block-cooperative kernels: blocks one after the other, the threads of a block as
+// fibers of the calling host thread (see above)
+template <class K, class... A>
+static void emul_launch_blocks(unsigned grid, unsigned block, K kernel, A... args) {
+  for (unsigned b = 0; b < grid; b++) {
+    fb::emulwarp::FiberBlock B;
+    B.grid = grid; B.block = block; B.bidx = b;
+    B.body = [&]() { kernel(args...); };
+    fb::emulwarp::run_fiber_block(B);
+  }
+}
+
+
+// `kernel<<<grid, block, smem, stream>>>(args...)` after the rewrite of tools/build_hostemu.py:
+//   fb::EmulCfg(grid, block, smem, stream).launch([&]() { kernel(args...); });
+namespace fb {
+struct EmulCfg {
+  unsigned grid, block;
+  size_t smem;
+  EmulCfg(long long g, long long b, size_t s = 0, cudaStream_t = nullptr) : grid((unsigned)g), block((unsigned)b), smem(s) {}
+  template <class F>
+  void launch(F body) const {
+    std::vector<unsigned char> buf(smem + 64);
+    unsigned char *sm = buf.data() + (16 - reinterpret_cast<uintptr_t>(buf.data()) % 16) % 16;
+    for (unsigned b = 0; b < grid; b++) {
+      emulwarp::FiberBlock B;
+      B.grid = grid; B.block = block; B.bidx = b;
+      B.body = body;
+      emul_smem() = sm;
+      emulwarp::run_fiber_block(B);
+    }
+    emul_smem() = nullptr;
+  }
+};
+}  // namespace fb
