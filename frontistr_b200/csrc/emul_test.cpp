@@ -30,11 +30,12 @@ static void emul_launch_warps(unsigned grid, unsigned warps, size_t smem_bytes, 
   unsigned char *smem = buf.data() + (16 - reinterpret_cast<uintptr_t>(buf.data()) % 16) % 16;
   fb::emul_smem() = smem;
   for (unsigned b = 0; b < grid; b++)
-    for (unsigned w = 0; w < warps; w++)
-      fb::emulwarp::run_warp([&](int lane) {
-        fb::gridDim.x = grid; fb::blockDim.x = warps * 32; fb::blockIdx.x = b; fb::threadIdx.x = w * 32 + (unsigned)lane;
-        kernel(args...);
-      });
+    for (unsigned w = 0; w < warps; w++) {
+      fb::emulwarp::FiberBlock B;
+      B.grid = grid; B.block = 32; B.blockdim = warps * 32; B.tid0 = w * 32; B.bidx = b;
+      B.body = [&]() { kernel(args...); };
+      fb::emulwarp::run_fiber_block(B);
+    }
   fb::emul_smem() = nullptr;
 }
 

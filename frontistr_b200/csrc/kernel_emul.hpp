@@ -3,7 +3,7 @@
 //   emul_launch       : grid-stride kernels without intra-block cooperation (slot / gather maps, node incidence, nodal
 //                       stress ...) run UNCHANGED, one "thread" after the other in a scrambled order;
 //   emul_launch_warps : the one-element-per-warp kernels (stiff / update / self-test) run UNCHANGED, every warp by 32
-//                       host threads in lock step (__syncwarp / shuffles = barriers, emul_test.cpp), warps one after
+//                       fibers in lock step (__syncwarp / shuffles = switch points, kernel_emul_impl.hpp), warps one after
 //                       the other, dynamic shared memory = a host buffer per block
 //   emul_launch_blocks: block-cooperative kernels (SpMV, CG, grid reductions; __syncthreads, static __shared__, warp
 //                       shuffles / ballots) run UNCHANGED: the threads of a block are cooperative fibers of ONE host
@@ -54,7 +54,7 @@ struct alignas(16) double2 {
 };
 
 namespace fb {
-namespace emulwarp {   // warp collectives, defined in emul_test.cpp: lock-step host threads (emul_launch_warps) or fibers (emul_launch_blocks)
+namespace emulwarp {   // warp / block collectives, implemented in kernel_emul_impl.hpp (fibers)
 double shfl(double v, int src);
 int shfl(int v, int src);
 void syncwarp();

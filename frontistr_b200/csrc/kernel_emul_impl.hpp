@@ -11,7 +11,7 @@
 #include <vector>
 
 // ---- execution models behind the warp / block collectives -------------------------------------------------------
-// (a) emul_launch_warps: 32 host threads per warp, every collective is a pthread-barrier-separated exchange;
+// (a) emul_launch_warps: the 32 lanes of a warp as fibers (FB_EMUL_PTHREAD_WARPS: 32 host threads and pthread barriers instead);
 // (b) emul_launch_blocks: the threads of a block are cooperative fibers (ucontext) of the calling host thread; a fiber
 //     that reaches __syncthreads / __syncwarp / a shuffle parks itself and the scheduler releases the block (warp) once
 //     every live fiber of it has arrived.  Everything is per host thread, so several host threads = several "GPUs".
@@ -74,7 +74,8 @@ struct FiberBlock {
   ucontext_t main;
 #endif
   int cur = -1;
-  unsigned grid = 1, block = 1, bidx = 0;
+  unsigned grid = 1, block = 1, bidx = 0;   // block = number of fibers run together
+  unsigned blockdim = 0, tid0 = 0;          // reported blockDim.x (0: = block) and threadIdx.x of fiber 0 (one warp of a larger block)
   std::function<void()> body;
   std::vector<double> slot_d;
   std::vector<int> slot_i;
@@ -133,7 +134,7 @@ static void run_fiber_block(FiberBlock &B) {
     for (int i = 0; i < n; i++) {
       if (B.f[i].state != 0) continue;
       B.cur = i;
-      fb::gridDim.x = B.grid; fb::blockDim.x = B.block; fb::blockIdx.x = B.bidx; fb::threadIdx.x = (unsigned)i;
+      fb::gridDim.x = B.grid; fb::blockDim.x = B.blockdim ? B.blockdim : B.block; fb::blockIdx.x = B.bidx; fb::threadIdx.x = B.tid0 + (unsigned)i;
 #ifdef FB_EMUL_ASM_SWITCH
       fb_emul_ctx_switch(&B.main_sp, B.f[i].sp);
 #else
@@ -203,12 +204,19 @@ void syncthreads() {
   fiber_yield(1);
 }
 template <class F>
-static void run_warp(F f) {   // f(lane) on 32 threads in lock step
+static void run_warp(F f) {   // f(lane) on the 32 lanes of one warp in lock step (fibers; FB_EMUL_PTHREAD_WARPS: host threads)
+#ifdef FB_EMUL_PTHREAD_WARPS
   pthread_barrier_init(&g_bar, nullptr, 32);
   std::vector<std::thread> th;
   for (int lane = 0; lane < 32; lane++) th.emplace_back([lane, &f]() { t_lane = lane; f(lane); });
   for (auto &t : th) t.join();
   pthread_barrier_destroy(&g_bar);
+#else
+  FiberBlock B;
+  B.block = 32;
+  B.body = [&f]() { f((int)(fb::threadIdx.x & 31)); };
+  run_fiber_block(B);
+#endif
 }
 } }
 

@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE: a CPU stand-in for the `gpu` fixture whose assembly / Dirichlet elimination / strain-stress
 update / nodal-stress entry points execute the PRODUCT'S OWN CUDA KERNELS on the host (libfistr_b200_emul.so:
-assembly.cuh compiled unchanged through csrc/kernel_emul.hpp — warps as 32 lock-step host threads, grid-stride
+assembly.cuh compiled unchanged through csrc/kernel_emul.hpp — warps as 32 lock-step fibers, grid-stride
 kernels thread after thread in scrambled order — and launched in the sequence of csrc/api_assembly.inc).  The SpMV runs the
 product's kernels too (blocks of fibers); only the Krylov solve is delegated to the oracle (the CG kernels are exercised
 separately, on several emulated ranks, by tests/test_p2p_kernels_emulated.py).

@@ -1,6 +1,6 @@
 """Runs the bodies of GPU tests on the CPU with tests/emul_backend.py in place of the `gpu` fixture: assembly, Dirichlet
 elimination, strain / stress update and nodal stress execute the product's OWN kernels (assembly.cuh compiled unchanged
-for the host, warps as lock-step host threads), only the Krylov solve is the oracle's.  Covers the kernels that have not
+for the host, warps as lock-step fibers), only the Krylov solve is the oracle's.  Covers the kernels that have not
 run on hardware yet (register/shuffle IC condensation, linear strain / stress recovery, total-Lagrangian tangent and
 update incl. the whole Newton loop of the reference's exI decks) and, as a control, ones that have."""
 import numpy as np

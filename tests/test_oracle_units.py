@@ -118,7 +118,7 @@ def test_element_emulation_equals_oracle():
 
 
 def test_ic_element_emulation_on_many_distorted_elements():
-    """The IC element exactly as the CUDA warp executes it (same source, lock-step host threads) against the oracle
+    """The IC element exactly as the CUDA warp executes it (same source, lock-step fibers) against the oracle
     on 80 strongly distorted / anisotropic hexahedra — the register + shuffle condensation must never lose accuracy
     whatever pivots K_aa asks for."""
     from oracle import oracle as orc
@@ -207,7 +207,7 @@ def test_ic_ldlt_condensation_equals_oracle_and_falls_back_on_indefinite_element
 def test_linear_update_emulation_equals_oracle():
     """Strain / stress recovery of the linear analysis as the CUDA warp executes it (element_math.cuh:
     element_update_lin_warp for 361 FI / B-bar and 342, element_update_ic_warp for the IC element with either
-    calInverse; same source, lock-step host threads) against the oracle's restatement of UPDATE_C3 / Update_C3D8Bbar /
+    calInverse; same source, lock-step fibers) against the oracle's restatement of UPDATE_C3 / Update_C3D8Bbar /
     UpdateST_C3D8IC — Gauss-point strain, stress and the element internal force, with and without thermal strain.
     (The oracle side is pinned on the E / S / SMS lines of the 14 linear golden logs, tests/test_oracle_golden.py.)"""
     from oracle import oracle as orc
@@ -337,7 +337,7 @@ def _emul_mesh_args(mesh):
 
 def test_assembly_kernels_run_on_the_host_equal_oracle():
     """fistr_b200_stiffmatrix_3d end to end on the HOST: slot_build_kernel, stiff_kernel<IC/FI/BBAR/TET10> (every warp
-    by 32 lock-step host threads, dynamic shared memory = a host buffer, shuffles and __syncwarp = barriers), the
+    by 32 lock-step fibers, dynamic shared memory = a host buffer, shuffles and __syncwarp = barriers), the
     gather map and gather_sum_kernel — or the atomic scatter — compiled UNCHANGED from assembly.cuh through
     csrc/kernel_emul.hpp and launched in the product's own sequence.  K against the oracle to 1e-13 for both calInverse
     variants of the IC kernel, gather and scatter; every double2 access of the kernels is checked for 16-byte
@@ -468,7 +468,7 @@ def test_tl_element_emulation_equals_oracle():
 
 
 def test_warp_inverse_equals_calInverse_with_pivoting():
-    """calInverse(9) as the CUDA warp executes it (same source, run in lock step by 32 host threads: one column
+    """calInverse(9) as the CUDA warp executes it (same source, run in lock step by 32 fibers: one column
     per lane, shuffles) against the oracle's restatement of utilities.f90:247-316 — on matrices that force row
     pivoting at every step, so the swap / IP bookkeeping / un-permutation paths are all exercised.  Bit-exact
     up to FMA contraction differences of the two compilers (1e-13 relative)."""
