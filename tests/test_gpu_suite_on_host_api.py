@@ -100,3 +100,47 @@ def test_gpu_test_body_through_the_host_compiled_library(host_api, modname, name
             mod.np = real
     else:
         getattr(mod, name)(host_api, **kw)
+
+
+def test_smoke_and_bench_through_the_host_compiled_library(host_api, monkeypatch, capsys):
+    """What the driver runs on the GPU box at round end, on the CPU through the host-compiled library:
+    __graft_entry__.smoke() (assembly + BC + CG of a 6^3 IC cube against the oracle) and the complete N=1 flow of
+    bench.py (set-up, device-resident arm, end-to-end arm with host matrices, CPU-baseline leg, the JSON line) on a 6^3
+    cube.  torch.cuda and nvidia-smi are stubbed; every number in the line is meaningless here, only the flow, the keys
+    and the host-side bookkeeping are checked."""
+    import argparse
+    import json
+
+    import torch
+
+    import __graft_entry__ as g
+    import bench
+    g.smoke()
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *_: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *_: None)
+
+    class NoSampler:
+        def __init__(self, *_):
+            pass
+
+        def start(self):
+            return self
+
+        def stop(self):
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["stub"]}
+    monkeypatch.setattr(bench, "ClockSampler", NoSampler)
+    monkeypatch.setattr(host_api, "fp64_peak", lambda: 1.0)
+    args = argparse.Namespace(gpus=1, steps=1, warmup=1, impl="b200", n=6, tol=1.0e-8, precond=3, maxit=20000, ref_iters=0,
+                              no_cpu_baseline=False, no_e2e=False, comm="auto")
+    bench.run_b200(args)
+    line = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")][-1]
+    d = json.loads(line)
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline", "assembly"):
+        assert key in d, key
+    assert d["n_gpus"] == 1 and d["dtype"] == "f64" and d["gpu_launches"] > 0 and d["value"] > 0
+    assert d["e2e"]["value"] and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert d["roofline"]["bound"] == "hbm" and d["roofline"]["achieved"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+    assert d["assembly"]["ic_inverse"] in ("LDL^T solves", "calInverse in registers+shuffles", "calInverse through shared memory")
+    assert d["iterations_per_step"] > 10 and d["resid_true"] < 1.0e-8
