@@ -5,10 +5,18 @@
 // be compiled by g++ into frontistr_b200/libfistr_b200_hostemu.so, which tests/test_gpu_suite_on_host_api.py loads in
 // place of the product library to run the GPU test bodies on the CPU.  Never part of the product build.
 #pragma once
+#include <sys/mman.h>
+#include <unistd.h>
+
+#include <algorithm>
 #include <chrono>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <type_traits>
 
 typedef int cudaError_t;
 enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorNotSupported = 801 };
@@ -38,16 +46,46 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
   p->totalGlobalMem = (size_t)8 << 30;
   return cudaSuccess;
 }
+// "Device" allocations are electric-fence style: every buffer ENDS (up to 16-byte rounding) at an inaccessible guard
+// page and begins right after another one, so a kernel that reads or writes out of bounds dies with SIGSEGV on the spot
+// instead of silently touching a neighbour - every host run of a kernel is also a bounds check of its addressing.
+// The memory is NOT zeroed, like device memory: a poison pattern makes a missing initialisation visible.
+struct CudaShimAllocs {
+  std::mutex mu;
+  std::map<void *, std::pair<void *, size_t>> live;   // user pointer -> (mapping base, mapping length)
+  static CudaShimAllocs &get() { static CudaShimAllocs a; return a; }
+};
 inline cudaError_t cudaMalloc(void **p, size_t bytes) {
-  void *q = nullptr;
-  if (posix_memalign(&q, 256, bytes ? bytes : 1)) { *p = nullptr; return cudaErrorMemoryAllocation; }
-  memset(q, 0xA5, bytes);   // like device memory: NOT zeroed (a poison pattern makes a missing initialisation visible)
+  const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+  const size_t user = (std::max<size_t>(bytes, 1) + 15) & ~(size_t)15;
+  const size_t body = (user + page - 1) / page * page;
+  const size_t len = body + 2 * page;
+  char *base = (char *)mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (base == (char *)MAP_FAILED) { *p = nullptr; return cudaErrorMemoryAllocation; }
+  memset(base + page, 0xA5, body);
+  mprotect(base, page, PROT_NONE);
+  mprotect(base + page + body, page, PROT_NONE);
+  char *q = base + page + body - user;
+  {
+    CudaShimAllocs &A = CudaShimAllocs::get();
+    std::lock_guard<std::mutex> g(A.mu);
+    A.live[q] = std::make_pair((void *)base, len);
+  }
   *p = q;
   return cudaSuccess;
 }
 template <class T>
 inline cudaError_t cudaMalloc(T **p, size_t bytes) { return cudaMalloc((void **)p, bytes); }
-inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaFree(void *p) {
+  if (!p) return cudaSuccess;
+  CudaShimAllocs &A = CudaShimAllocs::get();
+  std::lock_guard<std::mutex> g(A.mu);
+  auto it = A.live.find(p);
+  if (it == A.live.end()) { fprintf(stderr, "cuda_shim: cudaFree of an unknown pointer\n"); abort(); }
+  munmap(it->second.first, it->second.second);
+  A.live.erase(it);
+  return cudaSuccess;
+}
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { if (n) memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { if (n) memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemset(void *d, int v, size_t n) { if (n) memset(d, v, n); return cudaSuccess; }

@@ -5,13 +5,12 @@ run on hardware: (1) the geometrically nonlinear path, (2) the SELL-C-sigma row 
 strain / stress / internal-force update on the device, driven by the fstr_Newton mirror in frontistr_b200/hecmw.py,
 against the oracle (which reproduces the reference's exI golden logs at every sub-step).
 
-STATUS: these kernels were written after GPU access had been closed for round 1 (see profiles/r1_multi_gpu.md); their
-element code is verified against the oracle through the lock-step host emulation of the SAME source
-(tests/test_oracle_units.py::test_tl_element_emulation_equals_oracle) but has not run on hardware yet.  Until
-they have, nothing here executes by default — a fault in a never-run kernel must not be able to take the GPU (and
-the validated tests, smoke() and bench.py with it) down at round end.  Run with FISTR_B200_RUN_NL_GPU=1 to validate
-(tools/gpu_r2_validate.sh does);
-the tests are additionally non-strict xfail so the first hardware run cannot turn the suite red."""
+STATUS: these kernels were written after GPU access had been closed for round 1 (see profiles/r1_multi_gpu.md) and
+have not run on hardware.  What they do has been checked on the CPU instead, through the real C-ABI: the whole library
+is compiled for the host (tools/build_hostemu.py), every "device" buffer ends at a guard page, and the bodies of
+exactly these tests pass there (tests/test_gpu_suite_on_host_api.py).  They therefore run by default (this file sorts
+last, so nothing comes after it in the process) but stay non-strict xfail until their first hardware run: a mismatch
+that only a real GPU can produce must not turn the suite red.  FISTR_B200_SKIP_UNVALIDATED=1 leaves them out."""
 import os
 
 import numpy as np
@@ -21,9 +20,9 @@ import fb_util as util
 from frontistr_b200.hecmw_types import kel361BBAR
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("FISTR_B200_RUN_NL_GPU") != "1",
-                                 reason="nonlinear kernels not yet validated on hardware; set FISTR_B200_RUN_NL_GPU=1"),
-              pytest.mark.xfail(strict=False, reason="nonlinear kernels not yet run on hardware (round 1: GPU access closed)")]
+              pytest.mark.skipif(os.environ.get("FISTR_B200_SKIP_UNVALIDATED") == "1", reason="FISTR_B200_SKIP_UNVALIDATED=1"),
+              pytest.mark.xfail(strict=False, reason="kernels not yet run on hardware (round 1: GPU access closed); validated "
+                                                     "on the CPU through the host-compiled library")]
 
 
 def _cloads(mesh, g):
