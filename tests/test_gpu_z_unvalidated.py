@@ -233,3 +233,32 @@ def test_linear_update_mixed_types_and_sections(gpu):
         refo = orc.nodal_stress_3d(mesh, eo, so)
         for k in out:
             assert np.abs(out[k] - refo[k]).max() <= 1e-11 * np.abs(refo[k]).max(), k
+
+
+def test_update_and_nodal_stress_error_contract(gpu):
+    """(4c) argument / state errors of update_3d and nodal_stress_3d come back as library error codes with a message,
+    never as a crash: temperatures without expansion coefficients or without the initial field (-1), an element option
+    outside FI / B-bar / IC (-1), nodal_stress_3d after the mesh was re-declared without an update (-4); and a correct
+    call afterwards still works (the failed calls left no half-built state behind)."""
+    from frontistr_b200 import meshgen
+    from frontistr_b200._lib import FistrB200Error
+    mesh = meshgen.hex_cube(3)
+    A = gpu.hecmw_mat_con(mesh)
+    A.fstr_mat_init().hecMAT_init()
+    gpu.mat_structure(mesh, A)
+    u = 1e-3 * np.sin(np.arange(3 * mesh.n_node, dtype=float))
+    with pytest.raises(FistrB200Error) as e:
+        gpu.fstr_UpdateNewton_linear(mesh, None, u, np.full(mesh.n_node, 50.0), None, 20.0)
+    assert e.value.code == -1
+    bad = meshgen.hex_cube(3)
+    bad.sections[0]["elemopt361"] = 7
+    with pytest.raises(FistrB200Error) as e:
+        gpu.fstr_UpdateNewton_linear(bad, None, u)
+    assert e.value.code == -1
+    gpu.mat_structure(mesh, A)               # re-declared: connectivity-derived tables of earlier calls are stale
+    with pytest.raises(FistrB200Error) as e:
+        gpu.fstr_NodalStress3D(mesh)
+    assert e.value.code == -4
+    q = gpu.fstr_UpdateNewton_linear(mesh, None, u)
+    out = gpu.fstr_NodalStress3D(mesh)
+    assert np.isfinite(q).all() and np.isfinite(out["MISES"]).all() and out["MISES"].max() > 0
