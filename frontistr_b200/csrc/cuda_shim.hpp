@@ -49,7 +49,8 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
 // "Device" allocations are electric-fence style: every buffer ENDS (up to 16-byte rounding) at an inaccessible guard
 // page and begins right after another one, so a kernel that reads or writes out of bounds dies with SIGSEGV on the spot
 // instead of silently touching a neighbour - every host run of a kernel is also a bounds check of its addressing.
-// The memory is NOT zeroed, like device memory: a poison pattern makes a missing initialisation visible.
+// The memory is NOT zeroed, like device memory: it is filled with 0xFF bytes (NaN as a double, -1 as an int), so that a
+// value that is used without having been written shows up in the results.
 struct CudaShimAllocs {
   std::mutex mu;
   std::map<void *, std::pair<void *, size_t>> live;   // user pointer -> (mapping base, mapping length)
@@ -62,7 +63,7 @@ inline cudaError_t cudaMalloc(void **p, size_t bytes) {
   const size_t len = body + 2 * page;
   char *base = (char *)mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
   if (base == (char *)MAP_FAILED) { *p = nullptr; return cudaErrorMemoryAllocation; }
-  memset(base + page, 0xA5, body);
+  memset(base + page, 0xFF, body);   // doubles read as NaN, ints as -1
   mprotect(base, page, PROT_NONE);
   mprotect(base + page + body, page, PROT_NONE);
   char *q = base + page + body - user;
