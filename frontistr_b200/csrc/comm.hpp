@@ -6,6 +6,9 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <string>
+#ifdef FB_EMUL_KERNELS
+#include "nccl_shim.hpp"   // TEST-ONLY (host-compiled library): ranks = processes meeting in shared memory
+#endif
 
 namespace fb {
 
@@ -26,6 +29,23 @@ struct Nccl {
   int (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
 
+#ifdef FB_EMUL_KERNELS
+  bool load(std::string &) {   // TEST-ONLY binding to the shared-memory stand-in
+    using namespace ncclshim;
+    if (GetUniqueId) return true;
+    GetUniqueId = [](ncclUniqueId_ *id) { return ncclshim::GetUniqueId(id); };
+    CommInitRank = [](ncclComm_t_ *c, int n, ncclUniqueId_ id, int r) { return ncclshim::CommInitRank((Comm **)c, n, id.internal, r); };
+    CommDestroy = [](ncclComm_t_ c) { return ncclshim::CommDestroy((Comm *)c); };
+    AllReduce = [](const void *s, void *r, size_t n, int dt, int op, ncclComm_t_ c, cudaStream_t) { return ncclshim::AllReduce(s, r, n, dt, op, (Comm *)c, nullptr); };
+    AllGather = [](const void *s, void *r, size_t n, int dt, ncclComm_t_ c, cudaStream_t) { return ncclshim::AllGather(s, r, n, dt, (Comm *)c, nullptr); };
+    Send = [](const void *b, size_t n, int dt, int peer, ncclComm_t_ c, cudaStream_t) { return ncclshim::Send(b, n, dt, peer, (Comm *)c, nullptr); };
+    Recv = [](void *b, size_t n, int dt, int peer, ncclComm_t_ c, cudaStream_t) { return ncclshim::Recv(b, n, dt, peer, (Comm *)c, nullptr); };
+    GroupStart = []() { return ncclshim::GroupStart(); };
+    GroupEnd = []() { return ncclshim::GroupEnd(); };
+    GetErrorString = [](int) -> const char * { return "ncclshim error"; };
+    return true;
+  }
+#else
   bool load(std::string &err) {
     if (h) return true;
     const char *names[] = {"libnccl.so.2", "libnccl.so"};
@@ -50,6 +70,7 @@ struct Nccl {
 #undef FB_SYM
     return true;
   }
+#endif
 };
 
 }  // namespace fb

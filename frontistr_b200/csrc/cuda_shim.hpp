@@ -5,7 +5,9 @@
 // be compiled by g++ into frontistr_b200/libfistr_b200_hostemu.so, which tests/test_gpu_suite_on_host_api.py loads in
 // place of the product library to run the GPU test bodies on the CPU.  Never part of the product build.
 #pragma once
+#include <fcntl.h>
 #include <sys/mman.h>
+#include <sys/syscall.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -51,18 +53,27 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
 // instead of silently touching a neighbour - every host run of a kernel is also a bounds check of its addressing.
 // The memory is NOT zeroed, like device memory: it is filled with 0xFF bytes (NaN as a double, -1 as an int), so that a
 // value that is used without having been written shows up in the results.
+// The pages come from a memfd mapped MAP_SHARED, so that another PROCESS (= another emulated GPU) can map the same
+// buffer: cudaIpcGetMemHandle hands out (pid, fd, length, offset of the user pointer) and cudaIpcOpenMemHandle maps
+// /proc/<pid>/fd/<fd>.
+struct CudaShimAlloc { void *base; size_t len; int fd; size_t user_off; };
 struct CudaShimAllocs {
   std::mutex mu;
-  std::map<void *, std::pair<void *, size_t>> live;   // user pointer -> (mapping base, mapping length)
+  std::map<void *, CudaShimAlloc> live;      // user pointer -> mapping
+  std::map<void *, size_t> peer;             // pointers returned by cudaIpcOpenMemHandle -> mapping length (base = ptr - off)
+  std::map<void *, void *> peer_base;
   static CudaShimAllocs &get() { static CudaShimAllocs a; return a; }
 };
+struct CudaShimIpc { int pid, fd; unsigned long long len, off; };
 inline cudaError_t cudaMalloc(void **p, size_t bytes) {
   const size_t page = (size_t)sysconf(_SC_PAGESIZE);
   const size_t user = (std::max<size_t>(bytes, 1) + 15) & ~(size_t)15;
   const size_t body = (user + page - 1) / page * page;
   const size_t len = body + 2 * page;
-  char *base = (char *)mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
-  if (base == (char *)MAP_FAILED) { *p = nullptr; return cudaErrorMemoryAllocation; }
+  const int fd = (int)syscall(SYS_memfd_create, "fb_cuda_shim", 0u);
+  if (fd < 0 || ftruncate(fd, (off_t)len) != 0) { if (fd >= 0) close(fd); *p = nullptr; return cudaErrorMemoryAllocation; }
+  char *base = (char *)mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  if (base == (char *)MAP_FAILED) { close(fd); *p = nullptr; return cudaErrorMemoryAllocation; }
   memset(base + page, 0xFF, body);   // doubles read as NaN, ints as -1
   mprotect(base, page, PROT_NONE);
   mprotect(base + page + body, page, PROT_NONE);
@@ -70,7 +81,7 @@ inline cudaError_t cudaMalloc(void **p, size_t bytes) {
   {
     CudaShimAllocs &A = CudaShimAllocs::get();
     std::lock_guard<std::mutex> g(A.mu);
-    A.live[q] = std::make_pair((void *)base, len);
+    A.live[q] = CudaShimAlloc{(void *)base, len, fd, (size_t)(q - base)};
   }
   *p = q;
   return cudaSuccess;
@@ -83,7 +94,8 @@ inline cudaError_t cudaFree(void *p) {
   std::lock_guard<std::mutex> g(A.mu);
   auto it = A.live.find(p);
   if (it == A.live.end()) { fprintf(stderr, "cuda_shim: cudaFree of an unknown pointer\n"); abort(); }
-  munmap(it->second.first, it->second.second);
+  munmap(it->second.base, it->second.len);
+  close(it->second.fd);
   A.live.erase(it);
   return cudaSuccess;
 }
@@ -104,9 +116,42 @@ template <class F>
 inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 inline cudaError_t cudaHostRegister(void *, size_t, unsigned) { return cudaSuccess; }
 inline cudaError_t cudaHostUnregister(void *) { return cudaSuccess; }
-inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorNotSupported; }
-inline cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
-inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) {
+  CudaShimAllocs &A = CudaShimAllocs::get();
+  std::lock_guard<std::mutex> g(A.mu);
+  auto it = A.live.find(p);
+  if (it == A.live.end()) return cudaErrorNotSupported;
+  CudaShimIpc k{(int)getpid(), it->second.fd, (unsigned long long)it->second.len, (unsigned long long)it->second.user_off};
+  memset(h, 0, sizeof *h);
+  memcpy(h, &k, sizeof k);
+  return cudaSuccess;
+}
+inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) {
+  CudaShimIpc k;
+  memcpy(&k, &h, sizeof k);
+  char path[64];
+  snprintf(path, sizeof path, "/proc/%d/fd/%d", k.pid, k.fd);
+  const int fd = open(path, O_RDWR);
+  if (fd < 0) return cudaErrorNotSupported;
+  char *base = (char *)mmap(nullptr, (size_t)k.len, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (base == (char *)MAP_FAILED) return cudaErrorNotSupported;
+  CudaShimAllocs &A = CudaShimAllocs::get();
+  std::lock_guard<std::mutex> g(A.mu);
+  A.peer[base + k.off] = (size_t)k.len;
+  A.peer_base[base + k.off] = base;
+  *p = base + k.off;
+  return cudaSuccess;
+}
+inline cudaError_t cudaIpcCloseMemHandle(void *p) {
+  CudaShimAllocs &A = CudaShimAllocs::get();
+  std::lock_guard<std::mutex> g(A.mu);
+  auto it = A.peer.find(p);
+  if (it == A.peer.end()) return cudaSuccess;
+  munmap(A.peer_base[p], it->second);
+  A.peer_base.erase(p); A.peer.erase(it);
+  return cudaSuccess;
+}
 
 namespace cub {
 struct DeviceScan {

@@ -18,7 +18,12 @@
 
 namespace fb {
 unsigned long long p2p_now_ns() {
-  return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  // FB_EMUL_P2P_TIMEOUT=1 (test of the time-out handling): every look at the clock jumps 10 s ahead, so the first wait that
+  // has to spin at all gives up
+  static const bool jump = getenv("FB_EMUL_P2P_TIMEOUT") != nullptr;
+  static thread_local unsigned long long skew = 0;
+  if (jump) skew += 10000000000ull;
+  return skew + (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 namespace emulwarp {
 static pthread_barrier_t g_bar;

@@ -25,17 +25,28 @@ def main():
     ap.add_argument("--precond", type=int, default=3)
     ap.add_argument("--tol", type=float, default=1e-10)
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"])
+    ap.add_argument("--host", action="store_true", help="TEST ONLY: no GPUs - every rank loads the host-compiled library "
+                    "(tools/build_hostemu.py; NCCL and CUDA IPC are shared-memory stand-ins) and torch.distributed runs on gloo")
     ap.add_argument("--stress", action="store_true", help="also run the strain / stress recovery (update_3d + nodal_stress_3d) on "
                     "every rank and compare the internal nodes with the oracle's serial fstr_NodalStress3D")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
-    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(lr)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", os.environ["RANK"]))
+    dev = "cpu" if args.host else "cuda"
+    if args.host:
+        import ctypes
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import build_hostemu
+        from frontistr_b200 import _lib
+        _lib._lib = _lib.declare(ctypes.CDLL(build_hostemu.build()))
+        dist.init_process_group("gloo")
+    else:
+        torch.cuda.set_device(lr)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     import fb_util as util
     from frontistr_b200 import hecmw, meshgen, partition
-    hecmw.init(lr)
+    hecmw.init(0 if args.host else lr)
     hecmw.set_option("p2p", 2 if args.comm == "p2p" else 0)   # 2 = fail loudly if peer memory cannot be mapped
     hecmw.comm_init_from_torch()
     gmesh = meshgen.tet10_cube(args.tet) if args.tet else util.distort(meshgen.hex_cube(args.n))
@@ -46,23 +57,23 @@ def main():
     A = util.product_problem(hecmw, m, cnt, to_host=False)
     r = hecmw.hecmw_solve(m, A, device_resident=True)
     # halo consistency: X on external nodes must equal the owner's value (hecmw_update_m_R at CG exit)
-    xg = torch.zeros(3 * gmesh.n_node, dtype=torch.float64, device="cuda")
-    own = torch.from_numpy(m.global_node_ID[: m.nn_internal].astype(np.int64) - 1).cuda()
-    xl = torch.from_numpy(A.X.reshape(-1, 3)[: m.nn_internal].copy()).cuda()
+    xg = torch.zeros(3 * gmesh.n_node, dtype=torch.float64, device=dev)
+    own = torch.from_numpy(m.global_node_ID[: m.nn_internal].astype(np.int64) - 1).to(dev)
+    xl = torch.from_numpy(A.X.reshape(-1, 3)[: m.nn_internal].copy()).to(dev)
     xg.view(-1, 3)[own] = xl
     dist.all_reduce(xg)
     xgl = xg.cpu().numpy().reshape(-1, 3)
     halo_err = float(np.abs(A.X.reshape(-1, 3) - xgl[m.global_node_ID - 1]).max())
-    t = torch.tensor([halo_err], dtype=torch.float64, device="cuda")
+    t = torch.tensor([halo_err], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ok = True
     sg = None
     if args.stress:      # every rank works on its own local mesh (overlap elements included): no exchange needed
         hecmw.fstr_UpdateNewton_linear(m, None, A.X)
         ns = hecmw.fstr_NodalStress3D(m)
-        sg = torch.zeros((gmesh.n_node, 13), dtype=torch.float64, device="cuda")
+        sg = torch.zeros((gmesh.n_node, 13), dtype=torch.float64, device=dev)
         loc = np.concatenate([ns["STRAIN"], ns["STRESS"], ns["MISES"][:, None]], axis=1)[: m.nn_internal]
-        sg[own] = torch.from_numpy(np.ascontiguousarray(loc)).cuda()
+        sg[own] = torch.from_numpy(np.ascontiguousarray(loc)).to(dev)
         dist.all_reduce(sg)
     if rank == 0:
         from oracle import oracle as orc
@@ -79,8 +90,8 @@ def main():
             serr = float(np.abs(sg.cpu().numpy() - ref).max() / np.abs(ref).max())
             ok = ok and serr <= 1e-10
             print("     nodal strain / stress / Mises on the partitioned mesh vs serial oracle: max rel dev %.2e" % serr, flush=True)
-        print("%s dist_check world=%d comm=%s mesh=%s precond=%d: iter gpu=%d oracle=%d  rel_l2=%.2e  resid2=%.2e  halo_err=%.1e  neighbors=%d"
-              % ("PASS" if ok else "FAIL", world, args.comm, ("tet%d" % args.tet) if args.tet else ("hex%d" % args.n), args.precond,
+        print("%s dist_check world=%d comm=%s%s mesh=%s precond=%d: iter gpu=%d oracle=%d  rel_l2=%.2e  resid2=%.2e  halo_err=%.1e  neighbors=%d"
+              % ("PASS" if ok else "FAIL", world, args.comm, (" p2p_active=%d" % hecmw.get_option("p2p_active")) + (" HOST-EMULATION" if args.host else ""), ("tet%d" % args.tet) if args.tet else ("hex%d" % args.n), args.precond,
                  r["iter"], ro["iter"], err, r["resid2"], float(t.item()), m.n_neighbor_pe), flush=True)
     hecmw.comm_finalize()
     dist.destroy_process_group()
