@@ -479,7 +479,8 @@ mises_kernel(size_t n, const double *__restrict__ stress, double *__restrict__ m
 // 1..nL the L entries, then the U entries.  STAGE 0 subtracts K(:,c)*rhs from B (reading the
 // still-unmodified matrix); STAGE 1 zeroes row/column and puts 1 on the diagonal; the caller then
 // writes B(c) = rhs.  Equals the reference's one-constraint-at-a-time elimination because a
-// constraint only ever zeroes its own row and column.
+// constraint only ever zeroes its own row and column — provided every DOF appears ONCE in the batch: the host side
+// (api_assembly.inc) folds repeated DOFs into one entry that eliminates with the first value and sets the last.
 template <int STAGE>
 __global__ void __launch_bounds__(256)
 bc_kernel(int nbc, const int *__restrict__ bc_node, const int *__restrict__ bc_dof,

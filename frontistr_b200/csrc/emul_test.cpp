@@ -6,6 +6,7 @@
 #include <pthread.h>
 
 #include <cstring>
+#include <map>
 #include <thread>
 #include <vector>
 
@@ -391,11 +392,16 @@ int fbemul_mat_ass_bc(int nbc, const int *inode, const int *idof, const double *
                       const int *itemL, const int *indexU, const int *itemU, double *vals, double *B) {
   using namespace fb;
   std::vector<int> nodes, dofs, ptr(1, 0);
-  std::vector<double> v;
+  std::vector<double> v, vlast;      // a DOF named twice: eliminate with its first value, set B(c) to its last (api_assembly.inc)
+  std::map<long long, int> seen;
   for (int c = 0; c < nbc; c++) {
     if (idof[c] > 3) continue;
     const int n = inode[c];
-    nodes.push_back(n); dofs.push_back(idof[c]); v.push_back(rhs[c]);
+    const long long key = 3LL * n + idof[c];
+    auto it = seen.find(key);
+    if (it != seen.end()) { vlast[it->second] = rhs[c]; continue; }
+    seen[key] = (int)nodes.size();
+    nodes.push_back(n); dofs.push_back(idof[c]); v.push_back(rhs[c]); vlast.push_back(rhs[c]);
     ptr.push_back(ptr.back() + 1 + (indexL[n] - indexL[n - 1]) + (indexU[n] - indexU[n - 1]));
   }
   const int m = (int)nodes.size();
@@ -405,7 +411,7 @@ int fbemul_mat_ass_bc(int nbc, const int *inode, const int *idof, const double *
   emul_launch(3, 64, 32, bc_kernel<1>, m, (const int *)nodes.data(), (const int *)dofs.data(), (const double *)v.data(),
               (const int *)ptr.data(), NP, NPL, indexL, itemL, indexU, itemU, vals, B);
   emul_launch((unsigned)(m + 63) / 64, 64, 33, bc_set_rhs_kernel, m, (const int *)nodes.data(), (const int *)dofs.data(),
-              (const double *)v.data(), B);
+              (const double *)vlast.data(), B);
   return 0;
 }
 

@@ -125,6 +125,25 @@ def test_bc_elimination_matches_oracle(gpu):
     assert np.array_equal(A.D == 0.0, Ao.D == 0.0) and np.array_equal(A.AL == 0.0, Ao.AL == 0.0)
 
 
+def test_bc_elimination_same_dof_named_twice(gpu):
+    """Overlapping node groups make decks name one DOF in several !BOUNDARY lines, possibly with different values.  The
+    reference eliminates one constraint at a time (fstr_AddBC.f90:54-109): the second visit of a DOF finds its column
+    already zeroed, so nothing more goes to the right-hand side and only B(c) is overwritten — eliminate with the FIRST
+    value, end up with the LAST.  The batched device elimination must give the same matrix and right-hand side
+    (found by tests/test_host_api_fuzz.py)."""
+    mesh = util.distort(meshgen.hex_cube(4))
+    cnt = util.cube_cnt()
+    cnt["boundary"] = [("FIX", 1, 3, 0.0), ("CL1", 1, 2, 0.125), ("CL1", 2, 3, -0.5), ("FIX", 2, 2, 0.25), ("CL1", 3, 3, 0.75)]
+    A = util.product_problem(gpu, mesh, cnt, to_host=True)
+    Ao = util.oracle_problem(mesh, cnt)
+    scale = np.abs(Ao.D).max()
+    for k in ("D", "AL", "AU"):
+        assert np.abs(getattr(A, k) - getattr(Ao, k)).max() <= 1e-12 * scale, k
+    assert np.abs(A.B - Ao.B).max() <= 1e-12 * max(scale, np.abs(Ao.B).max())
+    fix, cl = mesh.node_group["FIX"], mesh.node_group["CL1"]
+    assert np.all(A.B[3 * (fix - 1) + 1] == 0.25) and np.all(A.B[3 * (cl - 1) + 2] == 0.75) and np.all(A.B[3 * (cl - 1) + 1] == -0.5)
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("name", ["hex5_ic", "tet3", "hex1", "hex_ragged"])
 def test_spmv_bitwise(gpu, name, variant):

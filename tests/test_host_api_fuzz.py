@@ -1,0 +1,165 @@
+"""Randomised meshes through the host-compiled library (tools/build_hostemu.py) against the oracle: element-type blocks in
+either order (361 / 342, one of them possibly empty), 1-3 sections with random 361 formulations and materials, ragged
+block dimensions, random distortion, optional temperature field.  Checks fstr_StiffMatrix (gather and scatter),
+fstr_UpdateNewton (linear) and fstr_NodalStress3D; seeds are fixed, so a failure is reproducible."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import fb_util as util
+from frontistr_b200 import meshgen
+from frontistr_b200.hecmw_types import hecmwST_local_mesh
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+@pytest.fixture(scope="module")
+def host_api():
+    import build_hostemu
+    from frontistr_b200 import _lib, hecmw
+    saved = _lib._lib
+    _lib._lib = _lib.declare(C.CDLL(build_hostemu.build()))
+    try:
+        hecmw.init(0)
+        yield hecmw
+        hecmw.finalize()
+    finally:
+        _lib._lib = saved
+
+
+def random_mesh(rng):
+    blocks = []
+    if rng.random() < 0.8:
+        blocks.append(util.distort(meshgen.hex_cube(2, nx=int(rng.integers(1, 5)), ny=int(rng.integers(1, 4)), nz=int(rng.integers(1, 4))),
+                                   amp=float(rng.uniform(0.0, 0.2)), seed=int(rng.integers(1 << 30))))
+    if rng.random() < 0.6 or not blocks:
+        blocks.append(meshgen.tet10_cube(int(rng.integers(1, 3))))
+    if rng.random() < 0.5:
+        blocks.reverse()                                   # 342 block before the 361 block
+    m = hecmwST_local_mesh()
+    nodes, eni, enn, eti, ett, off, eoff = [], [0], [], [0], [], 0, 0
+    for k, b in enumerate(blocks):
+        nodes.append(b.node.reshape(-1, 3) + [3.0 * k, 0.0, 0.0])
+        enn.append(b.elem_node_item + off)
+        eni += list(eni[-1] + np.asarray(b.elem_node_index[1:]))
+        eoff += b.n_elem
+        eti.append(eoff); ett.append(int(b.elem_type_item[0]))
+        off += b.n_node
+    if rng.random() < 0.3:                                  # an empty element-type block in the table
+        eti.append(eoff); ett.append(361 if ett[-1] == 342 else 342)
+    m.node = np.ascontiguousarray(np.vstack(nodes).reshape(-1))
+    m.n_node = m.nn_internal = off
+    m.n_elem = eoff
+    m.elem_node_index = np.array(eni, np.int32); m.elem_node_item = np.concatenate(enn).astype(np.int32)
+    m.elem_type_index = np.array(eti, np.int32); m.elem_type_item = np.array(ett, np.int32); m.n_elem_type = len(ett)
+    nsec = int(rng.integers(1, 4))
+    m.section_ID = rng.integers(1, nsec + 1, m.n_elem).astype(np.int32)
+    m.sections = [dict(elemopt361=int(rng.integers(1, 4)), E=float(rng.uniform(1e3, 3e5)), nu=float(rng.uniform(0.1, 0.4)),
+                       alpha=float(rng.uniform(1e-6, 3e-5))) for _ in range(nsec)]
+    m.global_node_ID = np.arange(1, m.n_node + 1, dtype=np.int32)
+    m.node_group = {}
+    return m
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_mesh_assembly_update_and_nodal_stress(host_api, seed):
+    from oracle import oracle as orc
+    gpu = host_api
+    rng = np.random.default_rng(1000 + seed)
+    mesh = random_mesh(rng)
+    Ao = orc.mat_con(mesh)
+    orc.stiffmatrix(mesh, Ao)
+    ref = np.concatenate([Ao.D, Ao.AL, Ao.AU])
+    A = gpu.hecmw_mat_con(mesh)
+    for k in ("indexL", "itemL", "indexU", "itemU"):
+        assert np.array_equal(getattr(A, k), getattr(Ao, k))
+    A.fstr_mat_init().hecMAT_init()
+    gpu.mat_structure(mesh, A)
+    for gather in (1, 0):
+        gpu.set_option("asm_gather", gather)
+        gpu.fstr_StiffMatrix(mesh, A, to_host=True)
+        K = np.concatenate([A.D, A.AL, A.AU])
+        assert np.abs(K - ref).max() <= 1e-12 * np.abs(ref).max(), (seed, gather)
+    gpu.set_option("asm_gather", 1)
+    u = 1e-3 * rng.standard_normal(3 * mesh.n_node)
+    thermal = rng.random() < 0.5
+    TT = 20 + 80 * rng.random(mesh.n_node) if thermal else None
+    T0 = np.full(mesh.n_node, 20.0) if thermal else None
+    qf = gpu.fstr_UpdateNewton_linear(mesh, 0.5 * u, 0.5 * u, TT, T0, 20.0)
+    out = gpu.fstr_NodalStress3D(mesh)
+    eo = so = qo = None
+    for isec, sct in enumerate(mesh.sections):              # the oracle takes one expansion coefficient per run
+        e, s, q = orc.update_linear(mesh, u, TT, T0, sct["alpha"], 20.0)
+        if eo is None:
+            eo, so, qo = e.copy(), s.copy(), np.zeros_like(q)
+        sel = mesh.section_ID == isec + 1
+        eo[sel], so[sel] = e[sel], s[sel]
+    refo = orc.nodal_stress_3d(mesh, eo, so)
+    for k in out:
+        assert np.abs(out[k] - refo[k]).max() <= 1e-11 * max(np.abs(refo[k]).max(), 1e-300), (seed, k)
+    if not thermal or len(mesh.sections) == 1:              # (QFORCE of the oracle is per single alpha)
+        e, s, q = orc.update_linear(mesh, u, TT, T0, mesh.sections[0]["alpha"], 20.0)
+        assert np.abs(qf - q).max() <= 1e-11 * np.abs(q).max(), seed
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_constraints_and_solve(host_api, seed):
+    """Random Dirichlet sets (several DOFs per node, non-zero prescribed values), random nodal loads, PRECOND 1 / 3,
+    iterPREmax 1 / 2: hecmw_mat_ass_bc and hecmw_solve through the library against the oracle — same iteration count
+    (+-2), same solution, same flags."""
+    from oracle import oracle as orc
+    from frontistr_b200.mshio import apply_solver_card
+    gpu = host_api
+    rng = np.random.default_rng(5000 + seed)
+    mesh = util.distort(meshgen.hex_cube(2, nx=int(rng.integers(2, 6)), ny=int(rng.integers(2, 4)), nz=int(rng.integers(2, 4))),
+                        amp=0.1, seed=seed) if seed % 3 else meshgen.tet10_cube(2)
+    xyz = mesh.node.reshape(-1, 3)
+    fixed = np.nonzero(xyz[:, 0] <= xyz[:, 0].min() + 1e-9)[0] + 1          # clamp one face so that K is regular
+    extra = rng.choice(np.arange(1, mesh.n_node + 1), size=min(4, mesh.n_node), replace=False)
+    bn = list(np.repeat(fixed, 3)) + list(extra)
+    bd = [1, 2, 3] * len(fixed) + list(rng.integers(1, 4, len(extra)))
+    bv = [0.0] * (3 * len(fixed)) + list(rng.uniform(-1e-3, 1e-3, len(extra)))
+    precond = int(rng.choice([1, 3])); ipm = int(rng.choice([1, 2]))
+    cnt = util.cube_cnt(tol=1e-10, precond=precond, iterpremax=ipm)
+    load = rng.standard_normal(3 * mesh.n_node)
+
+    def setup(be, A):
+        A.B[:] = load
+        be.mat_upload(A, values=False, rhs=True)
+        be.hecmw_mat_ass_bc(np.array(bn, np.int32), np.array(bd, np.int32), np.array(bv))
+        apply_solver_card(A, cnt["solver"]); A.Iarray[20] = 0; A.Iarray[21] = 0
+
+    A = gpu.hecmw_mat_con(mesh)
+    A.fstr_mat_init().hecMAT_init()
+    gpu.mat_structure(mesh, A)
+    gpu.fstr_StiffMatrix(mesh, A, to_host=False)
+    setup(gpu, A)
+    r = gpu.hecmw_solve(mesh, A, device_resident=True)
+    Ao = orc.mat_con(mesh)
+    orc.stiffmatrix(mesh, Ao)
+    Ao.B[:] = load
+    for n, d, v in zip(bn, bd, bv):
+        orc.mat_ass_bc(Ao, int(n), int(d), float(v))
+    apply_solver_card(Ao, cnt["solver"]); Ao.Iarray[20] = 0; Ao.Iarray[21] = 0
+    orc.lib().orc_set_ssor_threads(2)        # multicolour ordering, as the library (and the reference with > 1 thread) uses
+    orc.precond_clear()
+    ro = orc.solve(mesh, Ao)
+    orc.precond_clear()
+    orc.lib().orc_set_ssor_threads(0)
+    assert r["error"] == ro["error"], (r["error"], ro["error"], precond, ipm)
+    if r["error"] != 0:
+        return        # same HEC-MW code on both sides (e.g. 3003 when the random system makes SSOR x2 indefinite)
+    assert A.Iarray[80] == 1
+    assert abs(r["iter"] - ro["iter"]) <= 2, (r["iter"], ro["iter"], precond, ipm)
+    assert util.rel_l2(A.X, Ao.X) <= 1e-8
+    idx = 3 * (np.array(bn) - 1) + np.array(bd) - 1
+    # a DOF constrained twice keeps the value of its last constraint, as in the reference's one-at-a-time elimination
+    last = {}
+    for i, v in zip(idx, bv):
+        last[int(i)] = v
+    for i, v in last.items():
+        assert abs(A.X[i] - v) <= 1e-12 + 1e-9 * abs(v)
