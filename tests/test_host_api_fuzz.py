@@ -145,11 +145,9 @@ def test_random_constraints_and_solve(host_api, seed):
     for n, d, v in zip(bn, bd, bv):
         orc.mat_ass_bc(Ao, int(n), int(d), float(v))
     apply_solver_card(Ao, cnt["solver"]); Ao.Iarray[20] = 0; Ao.Iarray[21] = 0
-    orc.lib().orc_set_ssor_threads(2)        # multicolour ordering, as the library (and the reference with > 1 thread) uses
     orc.precond_clear()
-    ro = orc.solve(mesh, Ao)
+    ro = orc.solve(mesh, Ao, ssor_threads=2)     # multicolour ordering, as the library (and the reference with > 1 thread) uses
     orc.precond_clear()
-    orc.lib().orc_set_ssor_threads(0)
     assert r["error"] == ro["error"], (r["error"], ro["error"], precond, ipm)
     if r["error"] != 0:
         return        # same HEC-MW code on both sides (e.g. 3003 when the random system makes SSOR x2 indefinite)
@@ -163,3 +161,57 @@ def test_random_constraints_and_solve(host_api, seed):
         last[int(i)] = v
     for i, v in last.items():
         assert abs(A.X[i] - v) <= 1e-12 + 1e-9 * abs(v)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_total_lagrangian_states(host_api, seed):
+    """Total-Lagrangian tangent and update at random finite displacement states: 361 FI / B-bar and 342, elastic and
+    Mooney-Rivlin sections mixed in one mesh.  Gauss-point Green-Lagrange strain and 2nd Piola-Kirchhoff stress, QFORCE
+    and the assembled tangent (material + initial-stress stiffness at the stored state) against the oracle's element
+    routines, element by element."""
+    from oracle import oracle as orc
+    gpu = host_api
+    rng = np.random.default_rng(9000 + seed)
+    mesh = random_mesh(rng)
+    for sct in mesh.sections:
+        sct["elemopt361"] = int(rng.integers(1, 3))                  # FI or B-bar (IC aborts under NLGEOM, as in the reference)
+        if rng.random() < 0.5:
+            sct.update(mtype=1, hyper=(float(rng.uniform(0.1, 0.3)), float(rng.uniform(0.2, 0.6)), float(rng.uniform(0.05, 0.2))), E=1.0, nu=0.3)
+    unode = 0.03 * rng.standard_normal(3 * mesh.n_node)
+    dunode = 0.01 * rng.standard_normal(3 * mesh.n_node)
+    A = gpu.hecmw_mat_con(mesh)
+    A.fstr_mat_init().hecMAT_init()
+    gpu.mat_structure(mesh, A)
+    gpu.nl_state_reset(mesh)
+    qf = gpu.fstr_UpdateNewton(mesh, unode, dunode)
+    gpu.fstr_StiffMatrix_NL(mesh, A, unode + dunode)
+    gpu.mat_download(A, values=True, rhs=False)
+    e_gpu, s_gpu = gpu.nl_state_download(mesh)
+    L = orc.lib()
+    d = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    sec = orc.c_sections(mesh)
+    Ao = orc.mat_con(mesh)
+    cm = orc.c_matrix(Ao)
+    qf_o = np.zeros(3 * mesh.n_node)
+    xyz = mesh.node.reshape(-1, 3)
+    for it in range(mesh.n_elem_type):
+        et = int(mesh.elem_type_item[it])
+        for e in range(int(mesh.elem_type_index[it]), int(mesh.elem_type_index[it + 1])):
+            nod = np.ascontiguousarray(mesh.elem_node_item[mesh.elem_node_index[e]: mesh.elem_node_index[e + 1]], np.int32)
+            nn, ngp = len(nod), (8 if et == 361 else 4)
+            s_ = sec[int(mesh.section_ID[e]) - 1]
+            bbar = int(et == 361 and s_.elemopt361 == 2)
+            ec = np.ascontiguousarray(xyz[nod - 1])
+            u = np.ascontiguousarray(unode.reshape(-1, 3)[nod - 1]); du = np.ascontiguousarray(dunode.reshape(-1, 3)[nod - 1])
+            q = np.zeros(3 * nn); ee = np.zeros((8, 6)); ss = np.zeros((8, 6)); K = np.zeros((3 * nn, 3 * nn))
+            L.orc_UPDATE_C3_TL(et, nn, d(ec), d(u), d(du), C.byref(s_), bbar, d(q), d(ee), d(ss))
+            assert np.abs(e_gpu[e, :ngp] - ee[:ngp]).max() <= 1e-12 * max(np.abs(ee).max(), 1e-30), (seed, e)
+            assert np.abs(s_gpu[e, :ngp] - ss[:ngp]).max() <= 1e-11 * max(np.abs(ss).max(), 1e-30), (seed, e)
+            np.add.at(qf_o.reshape(-1, 3), nod - 1, q.reshape(nn, 3))
+            tot = np.ascontiguousarray(u + du)
+            L.orc_STF_C3_TL(et, nn, d(ec), d(tot), d(ee), d(ss), C.byref(s_), bbar, d(K))
+            L.orc_mat_ass_elem(C.byref(cm.s), nn, nod.ctypes.data_as(C.POINTER(C.c_int)), d(K), 3 * nn)
+    assert np.abs(qf - qf_o).max() <= 1e-11 * np.abs(qf_o).max()
+    scale = np.abs(Ao.D).max()
+    for k in ("D", "AL", "AU"):
+        assert np.abs(getattr(A, k) - getattr(Ao, k)).max() <= 1e-11 * scale, (seed, k)
