@@ -215,3 +215,45 @@ def test_random_total_lagrangian_states(host_api, seed):
     scale = np.abs(Ao.D).max()
     for k in ("D", "AL", "AU"):
         assert np.abs(getattr(A, k) - getattr(Ao, k)).max() <= 1e-11 * scale, (seed, k)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_solve_sequences_with_recycle_flags(host_api, seed):
+    """The preconditioner recycling state machine (Iarray(96/97/98), hecmw_mat_recycle_precond_setting,
+    matrix_misc.f90:678-697; DIAG_33.f90:38-41, SSOR_33.f90:72-80): sequences of solves on one hecmwST_matrix in which the
+    values are rescaled, the "numeric factorisation needed" / "symbolic needed" flags are set or — as a caller bug —
+    NOT set (the stale factors are then reused, in the reference as here), and the preconditioner type changes.  Error
+    code, iteration count, flags after the call and solution of every solve against the oracle run through the same
+    sequence."""
+    from oracle import oracle as orc
+    gpu = host_api
+    rng = np.random.default_rng(7000 + seed)
+    mesh = util.distort(meshgen.hex_cube(3), amp=0.1, seed=seed) if seed % 2 else meshgen.tet10_cube(2)
+    cnt = util.cube_cnt(tol=1e-9, precond=int(rng.choice([1, 3])))
+    A = util.product_problem(gpu, mesh, cnt, to_host=True)
+    Ao = util.oracle_problem(mesh, cnt)
+    orc.precond_clear()
+    gpu.hecmw_precond_clear()
+    for step in range(5):
+        if step > 0:
+            if rng.random() < 0.6:                    # values change (a Newton iteration, a new load step)
+                f = float(rng.uniform(0.5, 2.0))
+                for M in (A, Ao):
+                    M.D *= f; M.AL *= f; M.AU *= f
+                if rng.random() < 0.7:
+                    A.Iarray[96] = Ao.Iarray[96] = int(rng.choice([1, 2]))       # numfact flag, as fstr_Newton sets it
+            if rng.random() < 0.2:
+                A.Iarray[97] = Ao.Iarray[97] = 1                                 # symbolic flag
+            if rng.random() < 0.25:
+                p = int(rng.choice([1, 2, 3]))
+                A.Iarray[2] = Ao.Iarray[2] = p
+        A.X[:] = 0.0; Ao.X[:] = 0.0
+        r = gpu.hecmw_solve(mesh, A)
+        ro = orc.solve(mesh, Ao, ssor_threads=2)
+        assert r["error"] == ro["error"], (seed, step, r["error"], ro["error"])
+        assert abs(r["iter"] - ro["iter"]) <= 2, (seed, step, r["iter"], ro["iter"], int(A.Iarray[2]))
+        assert [int(A.Iarray[k]) for k in (80, 81, 95, 96, 97)] == [int(Ao.Iarray[k]) for k in (80, 81, 95, 96, 97)], (seed, step)
+        if r["error"] == 0:
+            assert util.rel_l2(A.X, Ao.X) <= 1e-7, (seed, step)
+    orc.precond_clear()
+    gpu.hecmw_precond_clear()
