@@ -257,3 +257,40 @@ def test_random_solve_sequences_with_recycle_flags(host_api, seed):
             assert util.rel_l2(A.X, Ao.X) <= 1e-7, (seed, step)
     orc.precond_clear()
     gpu.hecmw_precond_clear()
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_spmv_and_preconditioners(host_api, seed):
+    """hecmw_matvec_33 (every SpMV variant, random SELL-C-sigma window) bit-identical to the oracle; DIAG apply
+    bit-identical; SSOR: same colouring / permutation as the oracle's multicolour ordering and the same result to rounding
+    (the host compiler contracts the 3x3 block solve differently from nvcc) — on random mixed meshes."""
+    from oracle import oracle as orc
+    gpu = host_api
+    rng = np.random.default_rng(3000 + seed)
+    mesh = random_mesh(rng)
+    Ao = orc.mat_con(mesh)
+    orc.stiffmatrix(mesh, Ao)
+    for k in range(mesh.n_node):                      # make the diagonal blocks safely regular (free-floating blocks are singular)
+        Ao.D[9 * k + 0] *= 1.5; Ao.D[9 * k + 4] *= 1.5; Ao.D[9 * k + 8] *= 1.5
+    gpu.mat_structure(mesh, Ao); gpu.mat_upload(Ao)
+    x = np.sin(np.arange(1, 3 * Ao.NP + 1, dtype=float) * (1 + seed))
+    yo = orc.matvec(Ao, x)[: 3 * Ao.N]
+    for variant in (0, 1, 2):
+        for sigma in (0, int(rng.choice([32, 64, 96, 1024]))):
+            gpu.set_option("spmv_variant", variant); gpu.set_option("sell_sigma", sigma)
+            assert np.array_equal(gpu.hecmw_matvec(x, 3 * Ao.N), yo), (seed, variant, sigma)
+    gpu.set_option("spmv_variant", 2); gpu.set_option("sell_sigma", 0)
+    z = np.cos(np.arange(3 * Ao.NP, dtype=float)); z[3 * Ao.N:] = 0
+    gpu.hecmw_precond_setup(3, 1.0, 10)
+    zd = z.copy(); gpu.hecmw_precond_apply(zd)
+    pc = orc.Precond(Ao, precond=3)
+    zo = z.copy(); pc.apply(zo)
+    assert np.abs(zd[: 3 * Ao.N] - zo[: 3 * Ao.N]).max() <= 1e-13 * np.abs(zo).max()
+    gpu.hecmw_precond_setup(1, 1.0, 10)
+    pc = orc.Precond(Ao, precond=1, ncolor_in=10, nthreads=2)
+    nc, perm = gpu.precond_info(Ao.N)
+    assert nc == pc.ncolor and np.array_equal(perm, pc.perm())
+    zs = z.copy(); gpu.hecmw_precond_apply(zs)
+    zo = z.copy(); pc.apply(zo)
+    assert np.abs(zs[: 3 * Ao.N] - zo[: 3 * Ao.N]).max() <= 1e-12 * np.abs(zo).max()
+    gpu.hecmw_precond_clear()
