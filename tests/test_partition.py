@@ -125,3 +125,44 @@ def test_strain_stress_recovery_needs_no_exchange_on_partitioned_meshes():
             for k in ("STRAIN", "STRESS", "MISES"):
                 assert np.abs(out[k][:ni] - ref[k][g[:ni]]).max() <= 1e-12 * np.abs(ref[k]).max(), k
             assert np.abs(ql.reshape(-1, 3)[:ni] - q.reshape(-1, 3)[g[:ni]]).max() <= 1e-12 * np.abs(q).max()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_partition_fuzz_against_the_real_hecmw_part1(seed, tmp_path):
+    """Random ragged / distorted meshes and random RCB axis strings split by the REAL reference partitioner
+    (oracle/_ref/hecmw_part1, compiled from the reference's sources by oracle/build_ref.sh — present in the build
+    container only, skipped elsewhere) and by the in-process partitioner: identical local numbering, element
+    selection, neighbour / import / export tables on every rank, and byte-identical HECMW-DMD-ASCII files."""
+    import hashlib
+    import subprocess
+    part1 = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "hecmw_part1")
+    if not os.path.exists(part1):
+        pytest.skip("oracle/_ref/hecmw_part1 not built (needs /root/reference)")
+    from frontistr_b200 import mshio
+    rng = np.random.default_rng(200 + seed)
+    if seed % 3 == 2:
+        mesh = meshgen.tet10_cube(int(rng.integers(2, 4)))
+    else:
+        mesh = util.distort(meshgen.hex_cube(3, nx=int(rng.integers(2, 8)), ny=int(rng.integers(2, 6)), nz=int(rng.integers(2, 6))),
+                            amp=float(rng.uniform(0.0, 0.2)), seed=seed)
+    axes = "".join(rng.choice(list("xyz"), size=int(rng.integers(1, 4))))
+    nd = 1 << len(axes)
+    tmp = str(tmp_path)
+    meshgen.write_msh(mesh, os.path.join(tmp, "cube.msh"))
+    open(os.path.join(tmp, "hecmw_ctrl.dat"), "w").write(
+        "!MESH, NAME=part_in, TYPE=HECMW-ENTIRE\n cube.msh\n!MESH, NAME=part_out, TYPE=HECMW-DIST\n cube_p\n")
+    open(os.path.join(tmp, "hecmw_part_ctrl.dat"), "w").write("!PARTITION,TYPE=NODE-BASED,METHOD=RCB,DOMAIN=%d\n %s\n" % (nd, ",".join(axes)))
+    subprocess.check_call([part1], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    mesh = mshio.read_msh(os.path.join(tmp, "cube.msh"))        # what the tool saw: coordinates as printed in the file
+    dom = partition.rcb_domains(mesh, axes)
+    parts = [partition.local_mesh(mesh, dom, r, nd) for r in range(nd)]
+    for r, p in enumerate(parts):
+        ref = mshio.read_dist_mesh(os.path.join(tmp, "cube_p.%d" % r))
+        assert (p.n_node, p.nn_internal) == (ref.n_node, ref.nn_internal), (axes, r)
+        for k in ("global_node_ID", "node_ID", "elem_type_index", "elem_type_item", "elem_node_index", "elem_node_item",
+                  "neighbor_pe", "import_index", "import_item", "export_index", "export_item"):
+            assert np.array_equal(np.asarray(getattr(p, k)).reshape(-1), np.asarray(getattr(ref, k)).reshape(-1)), (axes, r, k)
+        mine = os.path.join(tmp, "mine.%d" % r)
+        mshio.write_dist_mesh(mine, p, mesh, dom)
+        with open(mine, "rb") as f1, open(os.path.join(tmp, "cube_p.%d" % r), "rb") as f2:
+            assert hashlib.sha256(f1.read()).hexdigest() == hashlib.sha256(f2.read()).hexdigest(), (axes, r)
