@@ -7,7 +7,7 @@ nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out
 SAN="compute-sanitizer --error-exitcode 9 --print-limit 5"
 timeout 1200 $SAN python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "assembly or bc_elimination" > gpurun_out/gate_asm.log 2>&1
 rc1=$?; tail -5 gpurun_out/gate_asm.log; echo "gate asm rc=$rc1"
-FISTR_B200_RUN_NL_GPU=1 timeout 1500 $SAN python -m pytest tests/test_gpu_z_unvalidated.py -m gpu -q -rA > gpurun_out/gate_nl.log 2>&1
+FISTR_B200_RUN_NL_GPU=1 timeout 1500 $SAN python -m pytest tests/test_gpu_z_unvalidated.py -m gpu -q -rA -k "not I342 and not cylinder and not B3 and not C3 and not D3 and not E3 and not G3" > gpurun_out/gate_nl.log 2>&1
 rc2=$?; tail -30 gpurun_out/gate_nl.log; echo "gate nl rc=$rc2"
 if grep -q "Invalid\|Misaligned\|========= Error" gpurun_out/gate_asm.log gpurun_out/gate_nl.log || [ $rc1 -eq 9 ] || [ $rc2 -eq 9 ]; then
   echo "GATE: memory errors found, stopping"; grep -m 20 "=========" gpurun_out/gate_asm.log gpurun_out/gate_nl.log; exit 9
