@@ -247,6 +247,11 @@ struct EmulCfg {
   EmulCfg(long long g, long long b, size_t s = 0, cudaStream_t = nullptr) : grid((unsigned)g), block((unsigned)b), smem(s) {}
   template <class F>
   void launch(F body) const {
+    // what the CUDA runtime would refuse at launch ("invalid configuration argument" / "too much shared data")
+    if (grid == 0 || block == 0 || block > 1024 || smem > 227 * 1024) {
+      fprintf(stderr, "emul: invalid launch configuration <<<%u, %u, %zu>>>\n", grid, block, smem);
+      abort();
+    }
     std::vector<unsigned char> buf(smem + 64);
     unsigned char *sm = buf.data() + (16 - reinterpret_cast<uintptr_t>(buf.data()) % 16) % 16;
     for (unsigned b = 0; b < grid; b++) {
