@@ -78,7 +78,7 @@ struct Context {
   DevBuf<double> gp_strain, gp_stress;   // nonlinear path: Gauss-point state [element][8][6]
   DevBuf<elem::MatlTL> m_matl;           // nonlinear path: per-section material records
   DevBuf<double> m_u, m_qf;              // nonlinear path: nodal displacement in, internal force out
-  int nl_n_elem = 0;
+  int nl_n_elem = -1;                    // elements the Gauss-point state is sized for (-1: none yet; 0 is a valid, empty mesh)
   // linear strain / stress recovery (update_3d / nodal_stress_3d): node incidence of the resident mesh, per-position
   // element internal force, section expansion coefficients, nodal temperatures
   DevBuf<unsigned> nptr, npos;
