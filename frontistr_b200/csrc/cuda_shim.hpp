@@ -127,6 +127,10 @@ inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) {
   return cudaSuccess;
 }
 inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) {
+  // FB_EMUL_IPC_FAIL_RANK=<r> (test of the mapping-failure path): the process whose RANK is r cannot map its peers
+  if (const char *fr = getenv("FB_EMUL_IPC_FAIL_RANK"))
+    if (const char *me = getenv("RANK"))
+      if (atoi(fr) == atoi(me)) return cudaErrorNotSupported;
   CudaShimIpc k;
   memcpy(&k, &h, sizeof k);
   char path[64];

@@ -24,7 +24,8 @@ def main():
     ap.add_argument("--tet", type=int, default=0)
     ap.add_argument("--precond", type=int, default=3)
     ap.add_argument("--tol", type=float, default=1e-10)
-    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"])
+    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl", "p2p-or-nccl"],
+                    help="p2p: peer memory or fail loudly; p2p-or-nccl: peer memory if every rank can map it, else NCCL (bench.py's auto)")
     ap.add_argument("--host", action="store_true", help="TEST ONLY: no GPUs - every rank loads the host-compiled library "
                     "(tools/build_hostemu.py; NCCL and CUDA IPC are shared-memory stand-ins) and torch.distributed runs on gloo")
     ap.add_argument("--stress", action="store_true", help="also run the strain / stress recovery (update_3d + nodal_stress_3d) on "
@@ -47,7 +48,7 @@ def main():
     import fb_util as util
     from frontistr_b200 import hecmw, meshgen, partition
     hecmw.init(0 if args.host else lr)
-    hecmw.set_option("p2p", 2 if args.comm == "p2p" else 0)   # 2 = fail loudly if peer memory cannot be mapped
+    hecmw.set_option("p2p", {"p2p": 2, "p2p-or-nccl": 1, "nccl": 0}[args.comm])   # 2 = fail loudly if peer memory cannot be mapped
     hecmw.comm_init_from_torch()
     gmesh = meshgen.tet10_cube(args.tet) if args.tet else util.distort(meshgen.hex_cube(args.n))
     axes = {2: "x", 4: "xy", 8: "xyz"}[world]

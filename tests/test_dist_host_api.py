@@ -43,6 +43,13 @@ def test_peer_memory_transport_4_ranks_tet10_with_strain_stress_recovery():
     assert "p2p_active=1" in lines[-1] and any("nodal strain" in ln for ln in lines)
 
 
+def test_one_rank_cannot_map_its_peers_everybody_stays_on_the_collective_transport():
+    """p2p_setup: rank 2 of 4 fails to open the peers' arenas; the verdict is all-reduced, every rank releases what it had
+    mapped and the solve runs over the collective transport (p2p_active=0) with the same result."""
+    lines = _torchrun(4, "dist_check.py", "--host", "--hex", "6", "--comm", "p2p-or-nccl", env={"FB_EMUL_IPC_FAIL_RANK": "2"})
+    assert "p2p_active=0" in lines[-1]
+
+
 def test_collective_transport_ssor_2_ranks():
     lines = _torchrun(2, "dist_check.py", "--host", "--hex", "6", "--comm", "nccl", "--precond", "1")
     assert "p2p_active=0" in lines[-1]
