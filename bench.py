@@ -58,10 +58,11 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--comm", default="auto", choices=["auto", "p2p", "nccl"],
                     help="N>1 transport of the halo exchange + dot-product all-reduce: peer-memory stores issued by the CG "
-                         "kernels (p2p) or NCCL.  auto = p2p (run on a B200 box at N=2; at N=4/8 validated through the host-compiled "
-                         "library, tests/test_dist_host_api.py) with two safety nets: the library itself stays on NCCL if the "
-                         "arenas cannot be mapped on every rank, and a peer-memory wait that times out makes all ranks fall back "
-                         "to NCCL together (noted as comm_note in the line)")
+                         "kernels (p2p) or NCCL.  auto = what has RUN ON HARDWARE at that N: p2p at N=2, NCCL at N>2 (p2p at "
+                         "N=4/8 is validated only through the host-compiled library, tests/test_dist_host_api.py: ask for it with "
+                         "--comm p2p).  Two safety nets under p2p: the library itself stays on NCCL if the arenas cannot be "
+                         "mapped on every rank, and a peer-memory wait that times out makes all ranks fall back to NCCL "
+                         "together (noted as comm_note in the line)")
     return ap.parse_args()
 
 
@@ -241,7 +242,7 @@ def run_b200(args):
 
     hecmw.init(local_rank)
     if world > 1:
-        use_p2p = args.comm in ("p2p", "auto")
+        use_p2p = args.comm == "p2p" or (args.comm == "auto" and world == 2)
         hecmw.set_option("p2p", 1 if use_p2p else 0)
         hecmw.comm_init_from_torch()
     dev = hecmw.device_info()

@@ -55,7 +55,7 @@ def test_collective_transport_ssor_2_ranks():
     assert "p2p_active=0" in lines[-1]
 
 
-@pytest.mark.parametrize("world,comm,inject", [(2, "auto", False), (8, "auto", True)])
+@pytest.mark.parametrize("world,comm,inject", [(2, "auto", False), (4, "auto", False), (8, "p2p", True)])
 def test_bench_flow_multi_rank(world, comm, inject):
     """bench.py's multi-rank flow (partition, set-up, device-resident and end-to-end arms, max-over-ranks timing, JSON
     line of rank 0).  inject: every peer-memory wait that has to spin times out at once — all ranks must learn of it at
