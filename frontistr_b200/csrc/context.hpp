@@ -7,6 +7,7 @@
 
 #include "../../include/fistr_b200.h"
 #include "assembly.cuh"
+#include "bilu.cuh"
 #include "cg_kernels.cuh"
 #include "comm.hpp"
 #include "common.cuh"
@@ -59,9 +60,10 @@ struct Context {
   bool sell_valid = false;
   DevBuf<double> alu;      // DIAG: SoA [9][alu_ld]
   size_t alu_ld = 0;
-  int pc_kind = 0;         // 0 none, 3 DIAG, 1 SSOR
+  int pc_kind = 0;         // 0 none, 3 DIAG, 1 SSOR, 10 BILU(0)
   double pc_sigma = 0.0;
   Ssor ssor;
+  Bilu bilu;
 
   // ---- reductions / control
   DevBuf<double> red, partial, hist;

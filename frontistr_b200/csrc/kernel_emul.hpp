@@ -74,6 +74,11 @@ inline double atomicAdd(double *p, double v) {
   while (!__atomic_compare_exchange_n(q, &o, n, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
   return od;
 }
+inline int atomicMax(int *p, int v) {
+  int o = __atomic_load_n(p, __ATOMIC_RELAXED);
+  while (o < v && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+  return o;
+}
 inline int atomicExch(int *p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
 inline unsigned char *&emul_smem() { static unsigned char *p = nullptr; return p; }   // dynamic shared memory of the running block
 #define FB_DYNAMIC_SMEM(name) unsigned char *name = fb::emul_smem()

@@ -171,7 +171,9 @@ int fistr_b200_matvec_33(const double *X, double *Y);
 int fistr_b200_matvec_bench(int nrep, int flush_l2, double *ms_mean, double *ms_min);
 
 /* ---- hecmw_precond_33_{setup,apply,clear} (precond/33/hecmw_precond_33.f90:27-115;
- * DIAG precond/33/hecmw_precond_DIAG_33.f90:27-159; SSOR precond/33/hecmw_precond_SSOR_33.f90:55-467) */
+ * DIAG (precond = 3) precond/33/hecmw_precond_DIAG_33.f90:27-159; SSOR (1, 2) precond/33/hecmw_precond_SSOR_33.f90:55-467;
+ * BILU(0) (10) precond/33/hecmw_precond_BILU_33.f90:35-362 - a zero pivot block, where the reference stops the program
+ * (:1509), returns 2001; 11 / 12 (ILU(1), ILU(2)) return 1001) */
 int fistr_b200_precond_33_setup(int precond, double sigma_diag, int ncolor_in);
 int fistr_b200_precond_33_apply(double *ZP /* 3*NP in/out */);
 int fistr_b200_precond_33_clear(void);

@@ -3,6 +3,7 @@
  * CPU restatement of the FrontISTR / HEC-MW linear-static hot path.
  * Parity pinning: reference golden logs (exA ... displacements) + independent
  * direct solve; iteration counts / K entries are pinned by restatement only.
+ * PRECOND = 10 (BILU(0)): PARITY UNPINNED - no reference deck or log selects it.
  * Citations are file:line in the reference tree (ricosjp/FrontISTR).
  */
 #include "hecmw_oracle.h"
@@ -773,9 +774,12 @@ static double inner_product(int ndom, const orc_mesh *meshes, double **X, double
 /* preconditioners                                                             */
 /* ------------------------------------------------------------------------- */
 struct orc_precond {
-  int kind; /* 3 = DIAG, 1/2 = SSOR */
+  int kind; /* 3 = DIAG, 1/2 = SSOR, 10 = BILU(0) */
   int N;
   double *ALU;
+  /* BILU(0): factor values and a private copy of the matrix's pattern (BILU_33.f90:216-225) */
+  double *Dlu0, *ALlu0, *AUlu0;
+  int *inumFI1L, *FI1L, *inumFI1U, *FI1U;
   /* SSOR private permuted copy */
   double *D, *AL, *AU;
   int *indexL, *indexU, *itemL, *itemU;
@@ -959,6 +963,110 @@ static int bsearch_int(const int *array, int is, int iE, int val) { /* 1-based p
   return -1;
 }
 
+/* ILU1b33, precond/33/hecmw_precond_BILU_33.f90:1539-1596: RHS = Aik * (Dk^-1 * Akj), Dk held as the 3x3 LU of ILU1a33
+ * (:1492-1530, reciprocal pivots on the diagonal) - column by column through the same substitution as the apply. */
+static void bilu_update_block(const double *Dk, const double *Aik, const double *Akj, double *Aij) {
+  for (int c = 0; c < 3; c++) {
+    double X1 = Akj[c], X2 = Akj[3 + c], X3 = Akj[6 + c];
+    block_solve(Dk, &X1, &X2, &X3);
+    for (int r = 0; r < 3; r++)
+      Aij[3 * r + c] -= fma(Aik[3 * r + 2], X3, fma(Aik[3 * r + 1], X2, Aik[3 * r] * X1));
+  }
+}
+
+/* ILU1a33, BILU_33.f90:1492-1530.  Returns 1 on a zero pivot (the reference stops the program there). */
+static int bilu_lu3(double *a) {
+  for (int k = 0; k < 3; k++) {
+    if (a[4 * k] == 0.0) return 1;
+    a[4 * k] = 1.0 / a[4 * k];
+    for (int i = k + 1; i < 3; i++) {
+      a[3 * i + k] = a[3 * i + k] * a[4 * k];
+      for (int j = k + 1; j < 3; j++) a[3 * i + j] = fma(-a[3 * i + k], a[3 * k + j], a[3 * i + j]);
+    }
+  }
+  return 0;
+}
+
+/* FORM_ILU0_33, BILU_33.f90:183-362: IKJ block factorisation over ALL NP rows in the pattern of A; L and U blocks are
+ * kept unscaled (the pivot block is applied in the solve), the diagonal block is overwritten by its 3x3 LU.
+ * PARITY UNPINNED: no deck of the reference's test tree selects PRECOND=10 and there is no Fortran compiler here, so
+ * this part of the oracle is checked only against an independent dense model of the same reading (tests/). */
+static int bilu0_setup(orc_precond *pc, const orc_matrix *m, double SIGMA_DIAG) {
+  const int NP = m->NP;
+  pc->Dlu0 = malloc(sizeof(double) * 9 * (size_t)(NP > 0 ? NP : 1));
+  pc->ALlu0 = malloc(sizeof(double) * 9 * (size_t)(m->NPL > 0 ? m->NPL : 1));
+  pc->AUlu0 = malloc(sizeof(double) * 9 * (size_t)(m->NPU > 0 ? m->NPU : 1));
+  memcpy(pc->Dlu0, m->D, sizeof(double) * 9 * (size_t)NP);
+  memcpy(pc->ALlu0, m->AL, sizeof(double) * 9 * (size_t)m->NPL);
+  memcpy(pc->AUlu0, m->AU, sizeof(double) * 9 * (size_t)m->NPU);
+  pc->inumFI1L = malloc(sizeof(int) * ((size_t)NP + 1)); pc->inumFI1U = malloc(sizeof(int) * ((size_t)NP + 1));
+  pc->FI1L = malloc(sizeof(int) * (size_t)(m->NPL > 0 ? m->NPL : 1)); pc->FI1U = malloc(sizeof(int) * (size_t)(m->NPU > 0 ? m->NPU : 1));
+  memcpy(pc->inumFI1L, m->indexL, sizeof(int) * ((size_t)NP + 1)); memcpy(pc->inumFI1U, m->indexU, sizeof(int) * ((size_t)NP + 1));
+  memcpy(pc->FI1L, m->itemL, sizeof(int) * (size_t)m->NPL); memcpy(pc->FI1U, m->itemU, sizeof(int) * (size_t)m->NPU);
+  int *IW1 = calloc((size_t)NP + 1, sizeof(int)), *IW2 = calloc((size_t)NP + 1, sizeof(int));
+  int bad = 0;
+  for (int i = 1; i <= NP; i++) {
+    double *Di = pc->Dlu0 + 9 * (size_t)(i - 1);
+    Di[0] *= SIGMA_DIAG; Di[4] *= SIGMA_DIAG; Di[8] *= SIGMA_DIAG;
+  }
+  for (int i = 1; i <= NP && !bad; i++) {
+    double *Di = pc->Dlu0 + 9 * (size_t)(i - 1);
+    for (int k = m->indexL[i - 1] + 1; k <= m->indexL[i]; k++) IW1[m->itemL[k - 1]] = k;
+    for (int k = m->indexU[i - 1] + 1; k <= m->indexU[i]; k++) IW2[m->itemU[k - 1]] = k;
+    for (int kk = m->indexL[i - 1] + 1; kk <= m->indexL[i]; kk++) {
+      const int k = m->itemL[kk - 1];
+      const double *Dk = pc->Dlu0 + 9 * (size_t)(k - 1);
+      const double *Aik = pc->ALlu0 + 9 * (size_t)(kk - 1);
+      for (int jj = m->indexU[k - 1] + 1; jj <= m->indexU[k]; jj++) {
+        const int j = m->itemU[jj - 1];
+        const double *Akj = pc->AUlu0 + 9 * (size_t)(jj - 1);
+        /* :291 skips every j that is in neither L(i) nor U(i) BEFORE the j == i case of :305 is looked at, and i is in
+         * neither of its own lists: the pivot block never receives an update in the reference (the same guard stands in
+         * the nn / 44 / 66 variants).  Restated as it behaves, not as the comment above it reads. */
+        if (j == i) continue;
+        if (j < i) { if (IW1[j]) bilu_update_block(Dk, Aik, Akj, pc->ALlu0 + 9 * (size_t)(IW1[j] - 1)); }
+        else if (IW2[j]) bilu_update_block(Dk, Aik, Akj, pc->AUlu0 + 9 * (size_t)(IW2[j] - 1));
+      }
+    }
+    bad = bilu_lu3(Di);
+    for (int k = m->indexL[i - 1] + 1; k <= m->indexL[i]; k++) IW1[m->itemL[k - 1]] = 0;
+    for (int k = m->indexU[i - 1] + 1; k <= m->indexU[i]; k++) IW2[m->itemU[k - 1]] = 0;
+  }
+  free(IW1); free(IW2);
+  return bad;
+}
+
+/* hecmw_precond_BILU_33_apply, BILU_33.f90:91-158 */
+static void bilu0_apply(const orc_precond *pc, double *WW /* 1-based */) {
+  const int N = pc->N;
+  for (int i = 1; i <= N; i++) {
+    double SW1 = WW[3 * (size_t)i - 2], SW2 = WW[3 * (size_t)i - 1], SW3 = WW[3 * (size_t)i];
+    for (int j = pc->inumFI1L[i - 1] + 1; j <= pc->inumFI1L[i]; j++) {
+      const size_t k = (size_t)pc->FI1L[j - 1];
+      const double *a = pc->ALlu0 + 9 * (size_t)(j - 1);
+      const double X1 = WW[3 * k - 2], X2 = WW[3 * k - 1], X3 = WW[3 * k];
+      SW1 = fma(-a[2], X3, fma(-a[1], X2, fma(-a[0], X1, SW1)));
+      SW2 = fma(-a[5], X3, fma(-a[4], X2, fma(-a[3], X1, SW2)));
+      SW3 = fma(-a[8], X3, fma(-a[7], X2, fma(-a[6], X1, SW3)));
+    }
+    block_solve(pc->Dlu0 + 9 * (size_t)(i - 1), &SW1, &SW2, &SW3);
+    WW[3 * (size_t)i - 2] = SW1; WW[3 * (size_t)i - 1] = SW2; WW[3 * (size_t)i] = SW3;
+  }
+  for (int i = N; i >= 1; i--) {
+    double SW1 = 0.0, SW2 = 0.0, SW3 = 0.0;
+    for (int j = pc->inumFI1U[i]; j >= pc->inumFI1U[i - 1] + 1; j--) {
+      const size_t k = (size_t)pc->FI1U[j - 1];
+      const double *a = pc->AUlu0 + 9 * (size_t)(j - 1);
+      const double X1 = WW[3 * k - 2], X2 = WW[3 * k - 1], X3 = WW[3 * k];
+      SW1 = fma(a[2], X3, fma(a[1], X2, fma(a[0], X1, SW1)));
+      SW2 = fma(a[5], X3, fma(a[4], X2, fma(a[3], X1, SW2)));
+      SW3 = fma(a[8], X3, fma(a[7], X2, fma(a[6], X1, SW3)));
+    }
+    block_solve(pc->Dlu0 + 9 * (size_t)(i - 1), &SW1, &SW2, &SW3);
+    WW[3 * (size_t)i - 2] -= SW1; WW[3 * (size_t)i - 1] -= SW2; WW[3 * (size_t)i] -= SW3;
+  }
+}
+
 orc_precond *orc_precond_setup(const orc_matrix *mat, int precond, double sigma_diag, int ncolor_in,
                                int nthreads_emulated) {
   orc_precond *pc = calloc(1, sizeof(*pc));
@@ -969,6 +1077,10 @@ orc_precond *orc_precond_setup(const orc_matrix *mat, int precond, double sigma_
     pc->ALU = calloc(9 * (size_t)mat->NP, sizeof(double));
     memcpy(pc->ALU, mat->D, sizeof(double) * 9 * (size_t)N);
     block_lu(N, pc->ALU, sigma_diag);
+    return pc;
+  }
+  if (precond == 10) { /* hecmw_precond_BILU_33_setup, BILU_33.f90:35-89 */
+    if (bilu0_setup(pc, mat, sigma_diag)) { orc_precond_free(pc); return NULL; }
     return pc;
   }
   /* hecmw_precond_SSOR_33_setup, precond/33/hecmw_precond_SSOR_33.f90:55-220 */
@@ -1042,7 +1154,7 @@ orc_precond *orc_precond_setup(const orc_matrix *mat, int precond, double sigma_
   return pc;
 }
 
-int orc_precond_ncolor(const orc_precond *pc) { return pc->kind == 3 ? 0 : pc->NColor; }
+int orc_precond_ncolor(const orc_precond *pc) { return (pc->kind == 3 || pc->kind == 10) ? 0 : pc->NColor; }
 void orc_precond_perm(const orc_precond *pc, int *perm) {
   if (pc->perm) memcpy(perm, pc->perm, sizeof(int) * pc->N);
 }
@@ -1058,6 +1170,7 @@ void orc_precond_apply(const orc_precond *pc, double *ZPv) {
       block_solve(pc->ALU + 9 * (size_t)(i - 1), &ZP[3 * (size_t)i - 2], &ZP[3 * (size_t)i - 1], &ZP[3 * (size_t)i]);
     return;
   }
+  if (pc->kind == 10) { bilu0_apply(pc, ZP); return; }
   /* hecmw_precond_SSOR_33_apply, SSOR_33.f90:222-420: rows visited in the new order colour by
    * colour; inside a colour rows are independent, so a serial visit equals the threaded one. */
   const int *itemL = pc->itemL - 1, *itemU = pc->itemU - 1;
@@ -1105,6 +1218,8 @@ void orc_precond_apply(const orc_precond *pc, double *ZPv) {
 void orc_precond_free(orc_precond *pc) {
   if (!pc) return;
   free(pc->ALU); free(pc->D); free(pc->AL); free(pc->AU);
+  free(pc->Dlu0); free(pc->ALlu0); free(pc->AUlu0);
+  free(pc->inumFI1L); free(pc->FI1L); free(pc->inumFI1U); free(pc->FI1U);
   free(pc->indexL); free(pc->indexU); free(pc->itemL); free(pc->itemU);
   free(pc->COLORindex); free(pc->perm); free(pc->iperm);
   free(pc);
@@ -1204,7 +1319,7 @@ int orc_solve(int ndom, const orc_mesh *meshes, orc_matrix *mats, int *iter_out,
   }
   IA(m0, 81) = 0; IA(m0, 82) = 0;
   if (METHOD != 1) return 1001;
-  if (!(PRECOND == 1 || PRECOND == 2 || PRECOND == 3)) return 1001;
+  if (!(PRECOND == 1 || PRECOND == 2 || PRECOND == 3 || PRECOND == 10)) return 1001;
 
   g_time_Ax = g_time_precond = g_time_comm = 0.0;
   double S_TIME = wtime();
@@ -1231,6 +1346,13 @@ int orc_solve(int ndom, const orc_mesh *meshes, orc_matrix *mats, int *iter_out,
       int nth = g_ssor_threads > 0 ? g_ssor_threads : orc_num_threads();
       for (int d = 0; d < ndom; d++)
         g_pcs[d] = orc_precond_setup(&mats[d], PRECOND, SIGMA_DIAG, IA(m0, 34), nth);
+      for (int d = 0; d < ndom; d++)
+        if (!g_pcs[d]) { /* zero pivot in the BILU set-up: the reference stops the program (BILU_33.f90:1509) */
+          for (int e = 0; e < ndom; e++) { free(R[e]); free(Z[e]); free(P[e]); free(WK[e]); }
+          free(R); free(Z); free(P); free(WK); free(X); free(B);
+          g_pcs_n = ndom; precond_clear_all();
+          return 2001;
+        }
     }
     IA(m0, 98) = 0; IA(m0, 97) = 0;
   }

@@ -22,6 +22,9 @@
  * law (tests/test_oracle_*).
  * Nothing in the reference tree pins CG iteration counts or K entries; for
  * those quantities the parity is "pinned by restatement only".
+ * PRECOND = 10 (block ILU(0), hecmw_precond_BILU_33): PARITY UNPINNED - no deck or
+ * log of the reference selects it; checked only against an independent dense model
+ * of the same reading of FORM_ILU0_33 (tests/test_oracle_units.py).
  *
  * All citations are relative to the reference tree root (ricosjp/FrontISTR).
  * Index arrays hold the reference's 1-based node ids verbatim; index*[0..NP]

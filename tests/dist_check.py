@@ -82,7 +82,13 @@ def main():
         orc.precond_clear()
         ro = orc.solve(gmesh, Ao)
         err = util.rel_l2(xgl.reshape(-1), Ao.X)
-        it_ok = abs(r["iter"] - ro["iter"]) <= 2 if args.precond == 3 else True   # SSOR is subdomain-local
+        it_ok = abs(r["iter"] - ro["iter"]) <= 2
+        if args.precond != 3:   # SSOR / BILU are subdomain-local: the count to meet is the oracle's on the SAME decomposition
+            parts = partition.partition(gmesh, axes)
+            orc.precond_clear()
+            rp = orc.solve(parts, [util.oracle_problem(p_, cnt) for p_ in parts], ssor_threads=2)
+            it_ok = rp["error"] == 0 and abs(r["iter"] - rp["iter"]) <= 2
+            print("     oracle on the same %d subdomains: %d iterations" % (world, rp["iter"]), flush=True)
         ok = (r["error"] == 0 and it_ok and err <= 1e-9 and r["resid2"] < args.tol and float(t.item()) == 0.0)
         if sg is not None:
             e, s_, q = orc.update_linear(gmesh, xgl.reshape(-1))

@@ -51,8 +51,16 @@ def test_one_rank_cannot_map_its_peers_everybody_stays_on_the_collective_transpo
 
 
 def test_collective_transport_ssor_2_ranks():
+    """Subdomain-local preconditioner: the iteration count to meet is the oracle's on the same two subdomains."""
     lines = _torchrun(2, "dist_check.py", "--host", "--hex", "6", "--comm", "nccl", "--precond", "1")
     assert "p2p_active=0" in lines[-1]
+
+
+def test_bilu0_2_ranks():
+    """PRECOND = 10 on two subdomains (the factorisation runs over internal AND halo rows, the substitution over internal
+    rows): same iteration count as the oracle on the same decomposition, solution equal to the serial one."""
+    lines = _torchrun(2, "dist_check.py", "--host", "--hex", "6", "--comm", "p2p", "--precond", "10")
+    assert "precond=10" in lines[-1]
 
 
 @pytest.mark.parametrize("world,comm,inject", [(2, "auto", False), (4, "auto", False), (8, "p2p", True)])

@@ -262,3 +262,66 @@ def test_update_and_nodal_stress_error_contract(gpu):
     q = gpu.fstr_UpdateNewton_linear(mesh, None, u)
     out = gpu.fstr_NodalStress3D(mesh)
     assert np.isfinite(q).all() and np.isfinite(out["MISES"]).all() and out["MISES"].max() > 0
+
+
+# (4) PRECOND = 10, block ILU(0) (second half): level-scheduled factorisation and substitution
+# kernels of csrc/bilu.cuh against the oracle's row-after-row restatement of hecmw_precond_BILU_33.
+
+@pytest.mark.parametrize("sigma_diag", [1.0, 1.3])
+@pytest.mark.parametrize("name", ["hex5_ic", "tet3", "hex_ragged", "hex1"])
+def test_precond_bilu0_matches_oracle(gpu, name, sigma_diag):
+    """Same operation order row by row: the application agrees to the last bits (a few ulp of the largest entry: the
+    compilers decide whether 'x -= a * t' is one fma)."""
+    from oracle import oracle as orc
+    from frontistr_b200 import meshgen
+    mesh = {"hex5_ic": lambda: util.distort(meshgen.hex_cube(5)), "tet3": lambda: meshgen.tet10_cube(3),
+            "hex_ragged": lambda: meshgen.hex_cube(3, nx=7, ny=2, nz=1), "hex1": lambda: meshgen.hex_cube(1)}[name]()
+    Ao = util.oracle_problem(mesh, util.cube_cnt())
+    gpu.mat_structure(mesh, Ao); gpu.mat_upload(Ao)
+    gpu.hecmw_precond_setup(10, sigma_diag)
+    z = np.cos(np.arange(3 * Ao.NP, dtype=float))
+    zo = z.copy()
+    gpu.hecmw_precond_apply(z)
+    orc.Precond(Ao, precond=10, sigma_diag=sigma_diag).apply(zo)
+    assert np.abs(z - zo)[: 3 * Ao.N].max() <= 8 * np.finfo(float).eps * np.abs(zo).max()
+    assert gpu.get_option("bilu_levels") >= 1
+    gpu.hecmw_precond_clear()
+
+
+@pytest.mark.parametrize("iterpremax", [1, 2])
+@pytest.mark.parametrize("meshname", ["hex12", "tet4"])
+def test_solve_bilu0_matches_oracle(gpu, meshname, iterpremax):
+    """CG + BILU(0): the same iteration count as the oracle (+-1), displacements within 1e-9 relative L2."""
+    from oracle import oracle as orc
+    from frontistr_b200 import meshgen
+    mesh = util.distort(meshgen.hex_cube(12)) if meshname == "hex12" else meshgen.tet10_cube(4)
+    cnt = util.cube_cnt(tol=1e-10, precond=10, iterpremax=iterpremax)
+    A = util.product_problem(gpu, mesh, cnt, to_host=True)
+    r = gpu.hecmw_solve(mesh, A)
+    Ao = util.oracle_problem(mesh, cnt)
+    orc.precond_clear()
+    ro = orc.solve(mesh, Ao, hist_len=10000)
+    orc.precond_clear()
+    assert r["error"] == 0 and ro["error"] == 0
+    assert abs(r["iter"] - ro["iter"]) <= 1
+    assert r["resid2"] < 1e-10 and A.Iarray[80] == 1
+    assert util.rel_l2(A.X[: 3 * A.N], Ao.X[: 3 * A.N]) <= 1e-9
+    n = min(len(r["hist"]), len(ro["hist"]))
+    assert np.allclose(r["hist"][: n // 2], ro["hist"][: n // 2], rtol=1e-6)
+
+
+def test_bilu0_zero_pivot_and_recycle(gpu):
+    """A zero pivot block stops the reference in the set-up (BILU_33.f90:1509): error 2001 here; the numeric set-up obeys
+    the recycle flags like the other preconditioners; PRECOND = 11 / 12 stay outside the path (1001)."""
+    from frontistr_b200 import meshgen
+    mesh = meshgen.hex_cube(4)
+    A = util.product_problem(gpu, mesh, util.cube_cnt(precond=10), to_host=True)
+    r = gpu.hecmw_solve(mesh, A)
+    assert r["error"] == 0 and A.Iarray[97] == 0
+    Zd = A.copy(); Zd.D[0] = 0.0; Zd.Iarray[97] = 1
+    assert gpu.hecmw_solve(mesh, Zd)["error"] == 2001
+    for pc in (11, 12):
+        M = A.copy(); M.Iarray[2] = pc; M.Iarray[97] = 1
+        assert gpu.hecmw_solve(mesh, M)["error"] == 1001
+    A.Iarray[97] = 1
+    assert gpu.hecmw_solve(mesh, A)["error"] == 0

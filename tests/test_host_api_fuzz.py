@@ -123,7 +123,7 @@ def test_random_constraints_and_solve(host_api, seed):
     bn = list(np.repeat(fixed, 3)) + list(extra)
     bd = [1, 2, 3] * len(fixed) + list(rng.integers(1, 4, len(extra)))
     bv = [0.0] * (3 * len(fixed)) + list(rng.uniform(-1e-3, 1e-3, len(extra)))
-    precond = int(rng.choice([1, 3])); ipm = int(rng.choice([1, 2]))
+    precond = int(rng.choice([1, 3, 10])); ipm = int(rng.choice([1, 2]))
     cnt = util.cube_cnt(tol=1e-10, precond=precond, iterpremax=ipm)
     load = rng.standard_normal(3 * mesh.n_node)
 
@@ -229,7 +229,7 @@ def test_random_solve_sequences_with_recycle_flags(host_api, seed):
     gpu = host_api
     rng = np.random.default_rng(7000 + seed)
     mesh = util.distort(meshgen.hex_cube(3), amp=0.1, seed=seed) if seed % 2 else meshgen.tet10_cube(2)
-    cnt = util.cube_cnt(tol=1e-9, precond=int(rng.choice([1, 3])))
+    cnt = util.cube_cnt(tol=1e-9, precond=int(rng.choice([1, 3, 10])))
     A = util.product_problem(gpu, mesh, cnt, to_host=True)
     Ao = util.oracle_problem(mesh, cnt)
     orc.precond_clear()
@@ -245,7 +245,7 @@ def test_random_solve_sequences_with_recycle_flags(host_api, seed):
             if rng.random() < 0.2:
                 A.Iarray[97] = Ao.Iarray[97] = 1                                 # symbolic flag
             if rng.random() < 0.25:
-                p = int(rng.choice([1, 2, 3]))
+                p = int(rng.choice([1, 2, 3, 10]))
                 A.Iarray[2] = Ao.Iarray[2] = p
         A.X[:] = 0.0; Ao.X[:] = 0.0
         r = gpu.hecmw_solve(mesh, A)
@@ -263,7 +263,7 @@ def test_random_solve_sequences_with_recycle_flags(host_api, seed):
 def test_random_spmv_and_preconditioners(host_api, seed):
     """hecmw_matvec_33 (every SpMV variant, random SELL-C-sigma window) bit-identical to the oracle; DIAG apply
     bit-identical; SSOR: same colouring / permutation as the oracle's multicolour ordering and the same result to rounding
-    (the host compiler contracts the 3x3 block solve differently from nvcc) — on random mixed meshes."""
+    (the host compiler contracts the 3x3 block solve differently from nvcc); BILU(0) likewise — on random mixed meshes."""
     from oracle import oracle as orc
     gpu = host_api
     rng = np.random.default_rng(3000 + seed)
@@ -293,4 +293,9 @@ def test_random_spmv_and_preconditioners(host_api, seed):
     zs = z.copy(); gpu.hecmw_precond_apply(zs)
     zo = z.copy(); pc.apply(zo)
     assert np.abs(zs[: 3 * Ao.N] - zo[: 3 * Ao.N]).max() <= 1e-12 * np.abs(zo).max()
+    sd = float(rng.choice([1.0, 1.2]))                # BILU(0): level-scheduled kernels against the row-after-row oracle
+    gpu.hecmw_precond_setup(10, sd, 10)
+    zb = z.copy(); gpu.hecmw_precond_apply(zb)
+    zo = z.copy(); orc.Precond(Ao, precond=10, sigma_diag=sd).apply(zo)
+    assert np.abs(zb[: 3 * Ao.N] - zo[: 3 * Ao.N]).max() <= 1e-12 * np.abs(zo).max()
     gpu.hecmw_precond_clear()
