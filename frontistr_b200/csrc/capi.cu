@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "context.hpp"

@@ -12,6 +12,7 @@
 #include "comm.hpp"
 #include "common.cuh"
 #include "matcon.hpp"
+#include "matcon_dev.cuh"
 #include "p2p.cuh"
 #include "partition.hpp"
 #include "spmv.cuh"
@@ -97,6 +98,12 @@ struct Context {
 
   // ---- hecmw_mat_con result held between _count and _fill
   MatCon con;
+  struct ConDev {   // the same result built on the device (option matcon_device), held until _fill
+    bool ready = false;
+    int N = 0, NP = 0, NPL = 0, NPU = 0;
+    DevBuf<int> indexL, indexU, itemL, itemU;
+    void clear() { ready = false; indexL.release(); indexU.release(); itemL.release(); itemU.release(); }
+  } con_dev;
   LocalMesh part;   // hecmw_part1 result of one rank held between _count and _fill
 
   // ---- peer-memory communication of the fused CG loop (p2p.cuh)

@@ -168,4 +168,16 @@ struct DeviceScan {
     return cudaSuccess;
   }
 };
+struct DeviceRadixSort {
+  // ascending on the bits [begin_bit, end_bit) of the key, stable - as CUB's
+  template <class K>
+  static cudaError_t SortKeys(void *d_temp, size_t &temp_bytes, const K *in, K *out, int n, int begin_bit = 0,
+                              int end_bit = (int)sizeof(K) * 8, cudaStream_t = nullptr) {
+    if (!d_temp) { temp_bytes = 64; return cudaSuccess; }
+    const K mask = (end_bit - begin_bit >= (int)sizeof(K) * 8) ? ~(K)0 : (((K)1 << (end_bit - begin_bit)) - 1);
+    for (int i = 0; i < n; i++) out[i] = in[i];
+    std::stable_sort(out, out + n, [=](K a, K b) { return ((a >> begin_bit) & mask) < ((b >> begin_bit) & mask); });
+    return cudaSuccess;
+  }
+};
 }  // namespace cub

@@ -51,7 +51,9 @@ int fistr_b200_comm_finalize(void);
 
 /* ---- hecmw_mat_con (hecmw1/src/solver/matrix/hecmw_mat_con.f90:23-268) -----------------------
  * count builds the node graph and keeps it; fill copies it into caller-allocated arrays
- * indexL/indexU(0:NP), itemL(NPL), itemU(NPU) — sorted ascending per row, 1-based. */
+ * indexL/indexU(0:NP), itemL(NPL), itemU(NPU) — sorted ascending per row, 1-based.
+ * Built on the host by default (usable without a GPU); option "matcon_device" = 1 builds it on the
+ * device (sort of node-pair keys), same arrays. */
 int fistr_b200_mat_con_count(int n_node, int nn_internal, int n_elem_type, const int *elem_type_index,
                              const int *elem_type_item, const int *elem_node_index,
                              const int *elem_node_item, int *N, int *NP, int *NPL, int *NPU);

@@ -325,3 +325,70 @@ def test_bilu0_zero_pivot_and_recycle(gpu):
         assert gpu.hecmw_solve(mesh, M)["error"] == 1001
     A.Iarray[97] = 1
     assert gpu.hecmw_solve(mesh, A)["error"] == 0
+
+
+# (5) hecmw_mat_con on the device: pair keys + radix sort + scans (csrc/matcon_dev.cuh), selected with
+# option matcon_device=1, against the oracle's restatement of the reference's table-building algorithm.
+
+@pytest.mark.parametrize("name", ["hex6", "tet3", "hex_ragged", "hex1", "A361", "A342", "mixed_with_loose_nodes", "empty"])
+def test_mat_con_on_the_device_is_identical(gpu, name):
+    """Index work: bit-exact.  Covers a mixed 361 + 342 mesh with an empty element-type block and nodes that belong to no
+    element (empty rows), a single element, and a mesh without elements."""
+    from oracle import oracle as orc
+    from frontistr_b200 import meshgen
+    from frontistr_b200.hecmw_types import hecmwST_local_mesh
+    if name in ("A361", "A342"):
+        mesh = util.load_golden_mesh(name)[0]
+    elif name == "mixed_with_loose_nodes":
+        h, t = meshgen.hex_cube(2, nx=3, ny=2, nz=2), meshgen.tet10_cube(2)
+        mesh = hecmwST_local_mesh()
+        loose = 5
+        mesh.n_node = mesh.nn_internal = h.n_node + loose + t.n_node
+        mesh.node = np.concatenate([h.node, np.zeros(3 * loose), t.node + 5.0])
+        mesh.elem_node_item = np.concatenate([t.elem_node_item + h.n_node + loose, h.elem_node_item]).astype(np.int32)
+        mesh.elem_node_index = np.concatenate([t.elem_node_index, t.elem_node_index[-1] + h.elem_node_index[1:]]).astype(np.int32)
+        mesh.elem_type_index = np.array([0, t.n_elem, t.n_elem, t.n_elem + h.n_elem], np.int32)
+        mesh.elem_type_item = np.array([342, 341, 361], np.int32)
+        mesh.n_elem, mesh.n_elem_type = t.n_elem + h.n_elem, 3
+        mesh.section_ID = np.ones(mesh.n_elem, np.int32)
+    elif name == "empty":
+        mesh = meshgen.hex_cube(1)
+        mesh.n_elem = 0
+        mesh.elem_type_index = np.array([0, 0], np.int32)
+        mesh.elem_node_index = np.array([0], np.int32); mesh.elem_node_item = np.zeros(0, np.int32)
+    else:
+        mesh = {"hex6": lambda: meshgen.hex_cube(6), "tet3": lambda: meshgen.tet10_cube(3),
+                "hex_ragged": lambda: meshgen.hex_cube(3, nx=7, ny=2, nz=1), "hex1": lambda: meshgen.hex_cube(1)}[name]()
+    gpu.set_option("matcon_device", 1)
+    try:
+        A = gpu.hecmw_mat_con(mesh)
+    finally:
+        gpu.set_option("matcon_device", 0)
+    H = gpu.hecmw_mat_con(mesh)                                   # host version of the library
+    for X in ((H,) if name == "empty" else (H, orc.mat_con(mesh))):   # and the restated reference algorithm
+        assert (A.N, A.NP, A.NPL, A.NPU) == (X.N, X.NP, X.NPL, X.NPU)
+        for k in ("indexL", "itemL", "indexU", "itemU"):
+            assert np.array_equal(getattr(A, k), getattr(X, k)), k
+
+
+def test_mat_con_on_the_device_error_contract(gpu):
+    from frontistr_b200 import meshgen
+    from frontistr_b200._lib import FistrB200Error
+    gpu.set_option("matcon_device", 1)
+    try:
+        bad = meshgen.hex_cube(2)
+        bad.elem_node_item = bad.elem_node_item.copy(); bad.elem_node_item[5] = bad.n_node + 1      # node id out of range
+        with pytest.raises(FistrB200Error) as e:
+            gpu.hecmw_mat_con(bad)
+        assert e.value.code == -1
+        bad = meshgen.hex_cube(2)
+        bad.elem_type_item = np.array([999], np.int32)                                               # unknown element type
+        with pytest.raises(FistrB200Error) as e:
+            gpu.hecmw_mat_con(bad)
+        assert e.value.code == -1
+        ok = meshgen.hex_cube(2)
+        A = gpu.hecmw_mat_con(ok)                                                                    # nothing half-built left behind
+    finally:
+        gpu.set_option("matcon_device", 0)
+    H = gpu.hecmw_mat_con(ok)
+    assert np.array_equal(A.itemL, H.itemL) and np.array_equal(A.indexU, H.indexU)

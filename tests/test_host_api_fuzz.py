@@ -299,3 +299,27 @@ def test_random_spmv_and_preconditioners(host_api, seed):
     zo = z.copy(); orc.Precond(Ao, precond=10, sigma_diag=sd).apply(zo)
     assert np.abs(zb[: 3 * Ao.N] - zo[: 3 * Ao.N]).max() <= 1e-12 * np.abs(zo).max()
     gpu.hecmw_precond_clear()
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_mat_con_on_the_device(host_api, seed):
+    """hecmw_mat_con built on the "device" (pair keys, radix sort, scans; option matcon_device=1) is identical to the oracle's
+    restatement of the reference algorithm and to the library's host version — on random mixed meshes and on the local
+    meshes of a random partition (halo rows, nn_internal < n_node)."""
+    from oracle import oracle as orc
+    from frontistr_b200 import partition
+    gpu = host_api
+    rng = np.random.default_rng(9000 + seed)
+    meshes = [random_mesh(rng)]
+    g = meshgen.hex_cube(2, nx=int(rng.integers(2, 6)), ny=int(rng.integers(1, 4)), nz=int(rng.integers(1, 4))) if seed % 2 else meshgen.tet10_cube(2)
+    meshes += partition.partition(g, str(rng.choice(["x", "xy", "z"])))
+    for mesh in meshes:
+        gpu.set_option("matcon_device", 1)
+        try:
+            A = gpu.hecmw_mat_con(mesh)
+        finally:
+            gpu.set_option("matcon_device", 0)
+        for X in (gpu.hecmw_mat_con(mesh), orc.mat_con(mesh)):
+            assert (A.N, A.NP, A.NPL, A.NPU) == (X.N, X.NP, X.NPL, X.NPU), seed
+            for k in ("indexL", "itemL", "indexU", "itemU"):
+                assert np.array_equal(getattr(A, k), getattr(X, k)), (seed, k)
