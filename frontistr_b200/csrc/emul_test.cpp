@@ -27,16 +27,16 @@ int64_t g_launch_count = 0;
 // threads in lock step, warps one after the other (the warps of these kernels never talk to each other)
 template <class K, class... A>
 static void emul_launch_warps(unsigned grid, unsigned warps, size_t smem_bytes, K kernel, A... args) {
-  std::vector<unsigned char> buf(smem_bytes + 64);
-  unsigned char *smem = buf.data() + (16 - reinterpret_cast<uintptr_t>(buf.data()) % 16) % 16;
-  fb::emul_smem() = smem;
-  for (unsigned b = 0; b < grid; b++)
+  fb::EmulSmem sm(smem_bytes);   // ends at a guard page, 0xFF-filled
+  for (unsigned b = 0; b < grid; b++) {
+    fb::emul_smem() = sm.fresh();
     for (unsigned w = 0; w < warps; w++) {
       fb::emulwarp::FiberBlock B;
       B.grid = grid; B.block = 32; B.blockdim = warps * 32; B.tid0 = w * 32; B.bidx = b;
       B.body = [&]() { kernel(args...); };
       fb::emulwarp::run_fiber_block(B);
     }
+  }
   fb::emul_smem() = nullptr;
 }
 

@@ -2,9 +2,15 @@
 // per shared library (emul_test.cpp for libfistr_b200_emul.so, the rewritten capi.cu for libfistr_b200_hostemu.so).
 #pragma once
 #include <pthread.h>
+#include <sys/mman.h>
+#include <unistd.h>
 #include <ucontext.h>
 
+#include <algorithm>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <functional>
 #include <memory>
 #include <thread>
@@ -241,6 +247,30 @@ static void emul_launch_blocks(unsigned grid, unsigned block, K kernel, A... arg
 // `kernel<<<grid, block, smem, stream>>>(args...)` after the rewrite of tools/build_hostemu.py:
 //   fb::EmulCfg(grid, block, smem, stream).launch([&]() { kernel(args...); });
 namespace fb {
+// Dynamic shared memory of an emulated block, electric-fence style like the "device" allocations of cuda_shim.hpp: the
+// buffer ENDS at an inaccessible page, so an index past the launch's shared-memory size dies on the spot (on hardware: an
+// out-of-range shared address, Xid 13), and it is refilled with 0xFF bytes for every block (NaN as a double, -1 as an int):
+// shared memory is not zeroed on hardware either.
+struct EmulSmem {
+  unsigned char *base = nullptr, *user = nullptr;
+  size_t len = 0, bytes = 0;
+  explicit EmulSmem(size_t n) {
+    const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+    bytes = (std::max<size_t>(n, 16) + 15) & ~(size_t)15;
+    const size_t body = (bytes + page - 1) / page * page;
+    len = body + 2 * page;
+    base = (unsigned char *)mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (base == (unsigned char *)MAP_FAILED) { fprintf(stderr, "emul: mmap of %zu bytes of shared memory failed\n", len); abort(); }
+    mprotect(base, page, PROT_NONE);
+    mprotect(base + page + body, page, PROT_NONE);
+    user = base + page + body - bytes;
+  }
+  ~EmulSmem() { if (base) munmap(base, len); }
+  EmulSmem(const EmulSmem &) = delete;
+  EmulSmem &operator=(const EmulSmem &) = delete;
+  unsigned char *fresh() { memset(user, 0xFF, bytes); return user; }
+};
+
 struct EmulCfg {
   unsigned grid, block;
   size_t smem;
@@ -252,13 +282,12 @@ struct EmulCfg {
       fprintf(stderr, "emul: invalid launch configuration <<<%u, %u, %zu>>>\n", grid, block, smem);
       abort();
     }
-    std::vector<unsigned char> buf(smem + 64);
-    unsigned char *sm = buf.data() + (16 - reinterpret_cast<uintptr_t>(buf.data()) % 16) % 16;
+    EmulSmem sm(smem);
     for (unsigned b = 0; b < grid; b++) {
       emulwarp::FiberBlock B;
       B.grid = grid; B.block = block; B.bidx = b;
       B.body = body;
-      emul_smem() = sm;
+      emul_smem() = sm.fresh();
       emulwarp::run_fiber_block(B);
     }
     emul_smem() = nullptr;
