@@ -323,3 +323,87 @@ def test_random_mat_con_on_the_device(host_api, seed):
             assert (A.N, A.NP, A.NPL, A.NPU) == (X.N, X.NP, X.NPL, X.NPU), seed
             for k in ("indexL", "itemL", "indexU", "itemU"):
                 assert np.array_equal(getattr(A, k), getattr(X, k)), (seed, k)
+
+
+def _exact_bilu0(A, z):
+    """FORM_ILU0_33 + hecmw_precond_BILU_33_apply (precond/33/hecmw_precond_BILU_33.f90:91-158, 183-362) with every fma
+    rounded exactly once (rational arithmetic), in the operation order csrc/bilu.cuh documents."""
+    from fractions import Fraction as Fr
+
+    def fma(a, b, c):
+        return float(Fr(a) * Fr(b) + Fr(c))
+
+    def solve3(a, X1, X2, X3):
+        X2 = fma(-a[3], X1, X2); X3 = fma(-a[7], X2, fma(-a[6], X1, X3)); X3 = a[8] * X3
+        X2 = a[4] * fma(-a[5], X3, X2); X1 = a[0] * fma(-a[1], X2, fma(-a[2], X3, X1))
+        return X1, X2, X3
+
+    def upd(Dk, Aik, Akj, Aij):
+        for c in range(3):
+            X1, X2, X3 = solve3(Dk, Akj[c], Akj[3 + c], Akj[6 + c])
+            for r in range(3):
+                Aij[3 * r + c] -= fma(Aik[3 * r + 2], X3, fma(Aik[3 * r + 1], X2, Aik[3 * r] * X1))
+
+    NP, N = A.NP, A.N
+    D = [[float(v) for v in A.D[9 * i:9 * i + 9]] for i in range(NP)]
+    AL = [[float(v) for v in A.AL[9 * i:9 * i + 9]] for i in range(A.NPL)]
+    AU = [[float(v) for v in A.AU[9 * i:9 * i + 9]] for i in range(A.NPU)]
+    for i in range(NP):
+        Lr = {A.itemL[k] - 1: k for k in range(A.indexL[i], A.indexL[i + 1])}
+        Ur = {A.itemU[k] - 1: k for k in range(A.indexU[i], A.indexU[i + 1])}
+        for kk in range(A.indexL[i], A.indexL[i + 1]):
+            k = A.itemL[kk] - 1
+            for jj in range(A.indexU[k], A.indexU[k + 1]):
+                j = A.itemU[jj] - 1
+                if j < i and j in Lr:
+                    upd(D[k], AL[kk], AU[jj], AL[Lr[j]])
+                elif j > i and j in Ur:
+                    upd(D[k], AL[kk], AU[jj], AU[Ur[j]])
+        a = D[i]
+        for k in range(3):
+            a[4 * k] = 1.0 / a[4 * k]
+            for r in range(k + 1, 3):
+                a[3 * r + k] = a[3 * r + k] * a[4 * k]
+                for c in range(k + 1, 3):
+                    a[3 * r + c] = fma(-a[3 * r + k], a[3 * k + c], a[3 * r + c])
+    w = [float(v) for v in z]
+    for i in range(N):
+        s = w[3 * i:3 * i + 3]
+        for j in range(A.indexL[i], A.indexL[i + 1]):
+            k, a = A.itemL[j] - 1, AL[j]
+            for r in range(3):
+                s[r] = fma(-a[3 * r + 2], w[3 * k + 2], fma(-a[3 * r + 1], w[3 * k + 1], fma(-a[3 * r], w[3 * k], s[r])))
+        w[3 * i:3 * i + 3] = solve3(D[i], *s)
+    for i in range(N - 1, -1, -1):
+        s = [0.0, 0.0, 0.0]
+        for j in range(A.indexU[i + 1] - 1, A.indexU[i] - 1, -1):
+            k, a = A.itemU[j] - 1, AU[j]
+            for r in range(3):
+                s[r] = fma(a[3 * r + 2], w[3 * k + 2], fma(a[3 * r + 1], w[3 * k + 1], fma(a[3 * r], w[3 * k], s[r])))
+        t = solve3(D[i], *s)
+        for r in range(3):
+            w[3 * i + r] -= t[r]
+    return np.array(w)
+
+
+@pytest.mark.parametrize("name", ["hex1", "hex2", "tet1"])
+def test_bilu0_kernels_against_an_exactly_rounded_model(host_api, name):
+    """The level-scheduled BILU(0) kernels, run on the host, reproduce BIT FOR BIT a model of the reference's row-after-row
+    algorithm in which every multiply-add is rounded exactly once: the level schedule changes no operation and no order.
+    (The oracle, compiled with contraction across statements like the reference, differs from both in the last bits.)"""
+    from oracle import oracle as orc
+    gpu = host_api
+    mesh = {"hex1": lambda: meshgen.hex_cube(1), "hex2": lambda: util.distort(meshgen.hex_cube(2)),
+            "tet1": lambda: meshgen.tet10_cube(1)}[name]()
+    A = util.oracle_problem(mesh, util.cube_cnt())
+    gpu.mat_structure(mesh, A); gpu.mat_upload(A)
+    gpu.hecmw_precond_setup(10, 1.0)
+    z0 = np.cos(np.arange(3 * A.NP, dtype=float))
+    z = z0.copy()
+    gpu.hecmw_precond_apply(z)
+    gpu.hecmw_precond_clear()
+    zm = _exact_bilu0(A, z0)
+    assert np.array_equal(z, zm)
+    zo = z0.copy()
+    orc.Precond(A, precond=10).apply(zo)
+    assert np.abs(zo - zm).max() <= 8 * np.finfo(float).eps * np.abs(zm).max()
