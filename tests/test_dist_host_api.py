@@ -13,16 +13,21 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-_port = [29600]
+
+
+def _free_port():
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
 
 
 def _torchrun(nproc, script, *args, env=None, timeout=600):
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import build_hostemu
     build_hostemu.build()                      # once, before the ranks race to build it
-    _port[0] += 1
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
-           "--master-port", str(_port[0]), os.path.join(ROOT, "tests", script)] + list(args)
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", script)] + list(args)
     e = dict(os.environ); e.update(env or {}); e.setdefault("OMP_NUM_THREADS", "1")
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=e, cwd=ROOT)
     lines = [ln for ln in (out.stdout + out.stderr).splitlines() if ln.startswith(("PASS", "FAIL", "     nodal"))]
