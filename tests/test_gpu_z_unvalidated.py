@@ -267,24 +267,33 @@ def test_update_and_nodal_stress_error_contract(gpu):
 # (4) PRECOND = 10, block ILU(0) (second half): level-scheduled factorisation and substitution
 # kernels of csrc/bilu.cuh against the oracle's row-after-row restatement of hecmw_precond_BILU_33.
 
+@pytest.mark.parametrize("chain_rows", [256, 0, 12])
 @pytest.mark.parametrize("sigma_diag", [1.0, 1.3])
 @pytest.mark.parametrize("name", ["hex5_ic", "tet3", "hex_ragged", "hex1"])
-def test_precond_bilu0_matches_oracle(gpu, name, sigma_diag):
+def test_precond_bilu0_matches_oracle(gpu, name, sigma_diag, chain_rows):
     """Same operation order row by row: the application agrees to the last bits (a few ulp of the largest entry: the
-    compilers decide whether 'x -= a * t' is one fma)."""
+    compilers decide whether 'x -= a * t' is one fma).  chain_rows: levels of at most that many rows share single-block
+    launches (256 = default: every level of these small meshes; 0 = one launch per level; 12 = a mixture)."""
     from oracle import oracle as orc
     from frontistr_b200 import meshgen
     mesh = {"hex5_ic": lambda: util.distort(meshgen.hex_cube(5)), "tet3": lambda: meshgen.tet10_cube(3),
             "hex_ragged": lambda: meshgen.hex_cube(3, nx=7, ny=2, nz=1), "hex1": lambda: meshgen.hex_cube(1)}[name]()
     Ao = util.oracle_problem(mesh, util.cube_cnt())
     gpu.mat_structure(mesh, Ao); gpu.mat_upload(Ao)
-    gpu.hecmw_precond_setup(10, sigma_diag)
+    gpu.set_option("bilu_chain_rows", chain_rows)
+    try:
+        gpu.hecmw_precond_setup(10, sigma_diag)
+    finally:
+        gpu.set_option("bilu_chain_rows", 256)
     z = np.cos(np.arange(3 * Ao.NP, dtype=float))
     zo = z.copy()
     gpu.hecmw_precond_apply(z)
     orc.Precond(Ao, precond=10, sigma_diag=sigma_diag).apply(zo)
     assert np.abs(z - zo)[: 3 * Ao.N].max() <= 8 * np.finfo(float).eps * np.abs(zo).max()
-    assert gpu.get_option("bilu_levels") >= 1
+    nlev, nlaunch = gpu.get_option("bilu_levels"), gpu.get_option("bilu_launches_per_apply")
+    assert nlev >= 1 and (nlaunch == 2 * nlev if chain_rows == 0 else nlaunch <= 2 * nlev)
+    if chain_rows == 256 and nlev > 1:
+        assert nlaunch == 2                      # one chained launch per sweep on these small meshes
     gpu.hecmw_precond_clear()
 
 

@@ -386,8 +386,9 @@ def _exact_bilu0(A, z):
     return np.array(w)
 
 
+@pytest.mark.parametrize("chain_rows", [256, 0, 5])
 @pytest.mark.parametrize("name", ["hex1", "hex2", "tet1"])
-def test_bilu0_kernels_against_an_exactly_rounded_model(host_api, name):
+def test_bilu0_kernels_against_an_exactly_rounded_model(host_api, name, chain_rows):
     """The level-scheduled BILU(0) kernels, run on the host, reproduce BIT FOR BIT a model of the reference's row-after-row
     algorithm in which every multiply-add is rounded exactly once: the level schedule changes no operation and no order.
     (The oracle, compiled with contraction across statements like the reference, differs from both in the last bits.)"""
@@ -397,7 +398,11 @@ def test_bilu0_kernels_against_an_exactly_rounded_model(host_api, name):
             "tet1": lambda: meshgen.tet10_cube(1)}[name]()
     A = util.oracle_problem(mesh, util.cube_cnt())
     gpu.mat_structure(mesh, A); gpu.mat_upload(A)
-    gpu.hecmw_precond_setup(10, 1.0)
+    gpu.set_option("bilu_chain_rows", chain_rows)     # chained single-block launches / one launch per level / a mixture
+    try:
+        gpu.hecmw_precond_setup(10, 1.0)
+    finally:
+        gpu.set_option("bilu_chain_rows", 256)
     z0 = np.cos(np.arange(3 * A.NP, dtype=float))
     z = z0.copy()
     gpu.hecmw_precond_apply(z)
