@@ -32,4 +32,4 @@ for pc in (3, 1, 10):
     r = hecmw.hecmw_solve(mesh, A, device_resident=True)
     print("CG PRECOND=%2d hex%d: error=%d iter=%d  set-up %.3f s  solver %.3f s%s" % (
         pc, args.solve_n, r["error"], r["iter"], r["times"][0], r["times"][1],
-        ("  levels=%d" % hecmw.get_option("bilu_levels")) if pc == 10 else ""), flush=True)
+        ("  levels=%d launches/apply=%d" % (hecmw.get_option("bilu_levels"), hecmw.get_option("bilu_launches_per_apply"))) if pc == 10 else ""), flush=True)
