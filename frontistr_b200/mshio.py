@@ -14,6 +14,7 @@ This is host-side plumbing for tests/bench; the reference's own readers stay in 
 from __future__ import annotations
 
 import re
+import warnings
 
 import numpy as np
 
@@ -212,7 +213,31 @@ class _Tok:
         self._fill()
         return float(self.buf.pop(0))
 
+    def _bulk(self, n, dtype):
+        """Arrays are written a fixed number of values per line and start on a fresh line (print_int_ary /
+        print_double_ary, hecmw_io_dist.c:1819-1886): take the lines the array must occupy and let numpy parse them in
+        one go.  Anything that does not add up (ragged lines, a pending token buffer) goes through the token loop."""
+        if self.buf or n < 64 or self.li >= len(self.lines):
+            return None
+        per = len(self.lines[self.li].split())
+        if per == 0:
+            return None
+        nl = -(-n // per)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")            # a malformed token ends the parse early: caught by the size check
+            try:
+                arr = np.fromstring(" ".join(self.lines[self.li:self.li + nl]), dtype=dtype, sep=" ")
+            except ValueError:
+                return None
+        if arr.size != n:
+            return None
+        self.li += nl
+        return arr
+
     def ia(self, n):
+        fast = self._bulk(n, np.int64)
+        if fast is not None:
+            return fast
         out = np.empty(n, np.int64)
         k = 0
         while k < n:
@@ -224,6 +249,9 @@ class _Tok:
         return out
 
     def fa(self, n):
+        fast = self._bulk(n, np.float64)
+        if fast is not None:
+            return fast
         out = np.empty(n, np.float64)
         k = 0
         while k < n:
@@ -321,9 +349,9 @@ def read_dist_mesh(path: str, elemopt361: int = kel361IC, E=None, nu=None) -> he
     m.elem_node_index = elem_node_index.astype(np.int32)
     eni = elem_node_item.astype(np.int32)
     # hecmw2fstr_mesh_conv: 342 file order -> FrontISTR order
-    for e in np.nonzero(elem_type == 342)[0]:
-        s = elem_node_index[e]
-        eni[s:s + 10] = eni[s:s + 10][TABLE342]
+    s342 = elem_node_index[:-1][elem_type == 342]
+    if s342.size:
+        eni[s342[:, None] + np.arange(10)[None, :]] = eni[s342[:, None] + np.asarray(TABLE342)[None, :]]
     m.elem_node_item = eni
     m.section_ID = section_ID.astype(np.int32)
     m.sections = [dict(elemopt361=elemopt361, E=E, nu=nu)]
@@ -343,29 +371,26 @@ def read_dist_mesh(path: str, elemopt361: int = kel361IC, E=None, nu=None) -> he
 # be handed to an unmodified fistr1.  Byte-identical to the real tool for the meshes meshgen.write_msh emits
 # (tests/test_partition.py::test_dist_writer_equals_hecmw_part1).
 # ---------------------------------------------------------------------------------------------------
+def _fmt_rows(tok, cols):
+    """`cols` tokens per line, a blank between tokens; a ragged last line ends with a blank before its newline - what the
+    '%d' / '%.16E' + (' ' | newline every `cols`) loops of print_int_ary / print_double_ary produce."""
+    n = len(tok)
+    if not n:
+        return ""
+    full = n - n % cols
+    out = [" ".join(tok[i:i + cols]) + "\n" for i in range(0, full, cols)]
+    if n % cols:
+        out.append(" ".join(tok[full:]) + " \n")
+    return "".join(out)
+
+
 def _fmt_int_ary(vals, cols=10):
     """print_int_ary (hecmw_io_dist.c:1819-1843): '%d' + (' ' | newline every `cols`), trailing newline if ragged."""
-    vals = [int(v) for v in vals]
-    if not vals:
-        return ""
-    s = []
-    for i, v in enumerate(vals):
-        s.append("%d%s" % (v, " " if (i + 1) % cols else "\n"))
-    if len(vals) % cols:
-        s.append("\n")
-    return "".join(s)
+    return _fmt_rows(list(map(str, np.asarray(vals, dtype=np.int64).tolist())), cols)
 
 
 def _fmt_dbl_ary(vals, cols):
-    vals = [float(v) for v in vals]
-    if not vals:
-        return ""
-    s = []
-    for i, v in enumerate(vals):
-        s.append("%.16E%s" % (v, " " if (i + 1) % cols else "\n"))
-    if len(vals) % cols:
-        s.append("\n")
-    return "".join(s)
+    return _fmt_rows(["%.16E" % v for v in np.asarray(vals, dtype=np.float64).tolist()], cols)
 
 
 def write_dist_mesh(path: str, local: hecmwST_local_mesh, global_mesh: hecmwST_local_mesh, domain: np.ndarray,

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import fb_util as util
-from frontistr_b200 import meshgen, partition
+from frontistr_b200 import meshgen, mshio, partition
 
 CASES = {"hex5_xy": lambda: meshgen.hex_cube(5), "hex6_xyz": lambda: meshgen.hex_cube(6),
          "hex7_zyx": lambda: meshgen.hex_cube(7), "tet2_xy": lambda: meshgen.tet10_cube(2),
@@ -166,3 +166,24 @@ def test_partition_fuzz_against_the_real_hecmw_part1(seed, tmp_path):
         mshio.write_dist_mesh(mine, p, mesh, dom)
         with open(mine, "rb") as f1, open(os.path.join(tmp, "cube_p.%d" % r), "rb") as f2:
             assert hashlib.sha256(f1.read()).hexdigest() == hashlib.sha256(f2.read()).hexdigest(), (axes, r)
+
+
+@pytest.mark.parametrize("kind", ["hex", "tet"])
+def test_dist_reader_bulk_parse_equals_token_loop(tmp_path, monkeypatch, kind):
+    """read_dist_mesh parses whole arrays with numpy where the file layout allows it; the token-by-token loop it falls back
+    to must give the same mesh (incl. the 342 file order -> FrontISTR order permutation)."""
+    mesh = meshgen.hex_cube(6) if kind == "hex" else meshgen.tet10_cube(3)
+    dom = partition.rcb_domains(mesh, "xy")
+    path = str(tmp_path / "m.2")
+    mshio.write_dist_mesh(path, partition.local_mesh(mesh, dom, 2, 4), mesh, dom)
+    fast = mshio.read_dist_mesh(path)
+    monkeypatch.setattr(mshio._Tok, "_bulk", lambda self, n, dtype: None)
+    slow = mshio.read_dist_mesh(path)
+    for k in ("n_node", "nn_internal", "n_elem", "n_neighbor_pe", "my_rank", "PETOT"):
+        assert getattr(fast, k) == getattr(slow, k), k
+    for k in ("node", "global_node_ID", "node_ID", "elem_type_index", "elem_type_item", "elem_node_index", "elem_node_item",
+              "section_ID", "neighbor_pe", "import_index", "import_item", "export_index", "export_item"):
+        a, b = np.asarray(getattr(fast, k)), np.asarray(getattr(slow, k))
+        assert a.dtype == b.dtype and np.array_equal(a, b), k
+    loc = partition.local_mesh(mesh, dom, 2, 4)
+    assert np.array_equal(fast.elem_node_item, loc.elem_node_item) and np.array_equal(fast.node, loc.node)
