@@ -37,6 +37,143 @@ def _opts(header: str) -> dict:
 
 
 def read_msh(path: str, elemopt361: int = kel361IC) -> hecmwST_local_mesh:
+    """HEC-MW entire mesh (.msh) reader for the cards the hot path needs (!NODE, !ELEMENT 361 / 342, !NGROUP, !MATERIAL /
+    !ITEM, !SECTION; hecmw1/src/common/hecmw_io_hec.c).  The !NODE and !ELEMENT blocks - all but a few lines of a large
+    mesh - are parsed block-wise with numpy; the result is the one of the line-by-line reader (unused nodes dropped and
+    nodes renumbered in ascending global id, elements sorted by id inside their type, hecmw_io_mesh.c:3039-3060)."""
+    try:
+        return _read_msh_bulk(path, elemopt361)
+    except _Irregular:
+        return _read_msh_line_by_line(path, elemopt361)
+
+
+class _Irregular(Exception):
+    pass
+
+
+def _numbers(lines, dtype):
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")               # a token numpy cannot read ends the parse with a warning
+        try:
+            return np.fromstring(" ".join(lines).replace(",", " "), dtype=dtype, sep=" ")
+        except (ValueError, DeprecationWarning) as e:
+            raise _Irregular(str(e))
+
+
+def _read_msh_bulk(path: str, elemopt361: int) -> hecmwST_local_mesh:
+    with open(path) as f:
+        lines = f.read().split("\n")
+    # cut the file into (header line, data lines) blocks
+    blocks, cur = [], None
+    for raw in lines:
+        line = raw.strip()
+        if not line or line.startswith("!!") or line.startswith("#"):
+            continue
+        if line.startswith("!"):
+            cur = (line, [])
+            blocks.append(cur)
+            if line.split(",")[0].strip().upper() == "!END":
+                break
+        elif cur is not None:
+            cur[1].append(line)
+    node_id, node_xyz = [], []
+    elems = {}                      # etype -> [ids], [connectivity rows]
+    ngroups, materials, sections = {}, {}, []
+    mat_name = None
+    for head, data in blocks:
+        key = head.split(",")[0].strip().upper()
+        opts = _opts(head)
+        if key == "!NODE":
+            v = _numbers(data, np.float64)
+            if v.size % 4:
+                raise _Irregular("!NODE block")
+            v = v.reshape(-1, 4)
+            ids = v[:, 0].astype(np.int64)
+            if not np.array_equal(ids, v[:, 0]):
+                raise _Irregular("node id")
+            node_id.append(ids); node_xyz.append(v[:, 1:])
+        elif key == "!ELEMENT":
+            et = int(opts["TYPE"])
+            if et not in (361, 342):
+                raise NotImplementedError("element type %d is outside the hot-path scope" % et)
+            nn = 8 if et == 361 else 10
+            v = _numbers(data, np.int64)
+            if v.size % (nn + 1):
+                raise _Irregular("!ELEMENT block")
+            v = v.reshape(-1, nn + 1)
+            e = elems.setdefault(et, ([], []))
+            e[0].append(v[:, 0]); e[1].append(v[:, 1:])
+        elif key == "!NGROUP":
+            g = ngroups.setdefault(opts["NGRP"], [])
+            for line in data:
+                vals = [t.strip() for t in line.split(",") if t.strip() != ""]
+                if opts.get("GENERATE"):
+                    a_, b_, s_ = int(vals[0]), int(vals[1]), int(vals[2]) if len(vals) > 2 else 1
+                    g.extend(range(a_, b_ + 1, s_))
+                else:
+                    g.extend(int(t) for t in vals)
+        elif key == "!MATERIAL":
+            mat_name = opts.get("NAME")
+            materials.setdefault(mat_name, {})
+        elif key == "!ITEM" or key.startswith("!ITEM="):
+            if data and "E" not in materials[mat_name]:
+                vals = [t.strip() for t in data[0].split(",") if t.strip() != ""]
+                materials[mat_name]["E"] = float(vals[0]); materials[mat_name]["nu"] = float(vals[1])
+        elif key == "!SECTION":
+            sections.append(dict(opts))
+    if not elems or not node_id:
+        raise _Irregular("no !NODE / !ELEMENT block")
+    nid = np.concatenate(node_id); xyz = np.concatenate(node_xyz)
+    order = np.argsort(nid, kind="stable")
+    nid_s = nid[order]
+    last = np.ones(nid_s.size, bool)
+    last[:-1] = nid_s[1:] != nid_s[:-1]              # a node defined twice: the later definition stands
+    nid_s, xyz_s = nid_s[last], xyz[order][last]
+    types = sorted(elems)
+    conn = {}
+    for et in types:
+        ids = np.concatenate(elems[et][0]); c = np.concatenate(elems[et][1])
+        if np.unique(ids).size != ids.size:
+            raise _Irregular("element defined twice")
+        conn[et] = c[np.argsort(ids, kind="stable")]
+    used = np.unique(np.concatenate([conn[et].reshape(-1) for et in types]))
+    pos = np.searchsorted(nid_s, used)
+    if pos.size and (pos.max() >= nid_s.size or not np.array_equal(nid_s[pos], used)):
+        raise KeyError("element node without a !NODE definition")
+    m = hecmwST_local_mesh()
+    m.n_node = m.nn_internal = int(used.size)
+    m.node = np.ascontiguousarray(xyz_s[pos], np.float64).reshape(-1)
+    m.global_node_ID = used.astype(np.int32)
+    tindex, nindex, items = [0], [np.zeros(1, np.int64)], []
+    for et in types:
+        c = (np.searchsorted(used, conn[et]) + 1).astype(np.int32)
+        if et == 342:
+            c = c[:, TABLE342]                         # hecmw2fstr_mesh_conv: file order -> FrontISTR order
+        items.append(c.reshape(-1))
+        nindex.append(int(nindex[-1][-1]) + c.shape[1] * np.arange(1, c.shape[0] + 1, dtype=np.int64))
+        tindex.append(tindex[-1] + c.shape[0])
+    m.n_elem = tindex[-1]
+    m.n_elem_type = len(types)
+    m.elem_type_index = np.array(tindex, np.int32)
+    m.elem_type_item = np.array(types, np.int32)
+    m.elem_node_index = np.concatenate(nindex).astype(np.int32)
+    m.elem_node_item = np.concatenate(items).astype(np.int32)
+    m.section_ID = np.ones(m.n_elem, np.int32)
+    sec = sections[0] if sections else {}
+    mat = materials.get(sec.get("MATERIAL"), next(iter(materials.values())) if materials else {})
+    m.sections = [dict(elemopt361=elemopt361, E=mat.get("E", 0.0), nu=mat.get("nu", 0.0))]
+    m.node_group = {}
+    for k, v in ngroups.items():                     # nodes removed as unused also leave their groups (hecmw_io_mesh.c:3039-3060)
+        v = np.asarray(v, np.int64)
+        p = np.searchsorted(used, v)
+        ok = (p < used.size) & (used[np.minimum(p, max(used.size - 1, 0))] == v) if v.size else np.zeros(0, bool)
+        m.node_group[k] = (p[ok] + 1).astype(np.int32)
+    return m
+
+
+def _read_msh_line_by_line(path: str, elemopt361: int = kel361IC) -> hecmwST_local_mesh:
+    """The plain reader: one Python pass over the lines.  read_msh falls back to it for anything its bulk parse does not
+    recognise as regular."""
     nodes = {}
     elems = {}       # etype -> list[(eid, [nodes])]
     ngroups = {}

@@ -187,3 +187,87 @@ def test_dist_reader_bulk_parse_equals_token_loop(tmp_path, monkeypatch, kind):
         assert a.dtype == b.dtype and np.array_equal(a, b), k
     loc = partition.local_mesh(mesh, dom, 2, 4)
     assert np.array_equal(fast.elem_node_item, loc.elem_node_item) and np.array_equal(fast.node, loc.node)
+
+
+_MSH_KEYS = ("node", "global_node_ID", "elem_type_index", "elem_type_item", "elem_node_index", "elem_node_item", "section_ID")
+
+
+def _same_mesh(a, b):
+    assert a.n_node == b.n_node and a.n_elem == b.n_elem and a.sections == b.sections
+    for k in _MSH_KEYS:
+        x, y = np.asarray(getattr(a, k)), np.asarray(getattr(b, k))
+        assert x.dtype == y.dtype and np.array_equal(x, y), k
+    assert a.node_group.keys() == b.node_group.keys()
+    for k in a.node_group:
+        assert np.array_equal(a.node_group[k], b.node_group[k]), k
+
+
+def test_msh_reader_bulk_parse_equals_line_by_line(tmp_path):
+    """read_msh parses the !NODE / !ELEMENT blocks with numpy; the line-by-line reader it falls back to is the statement
+    of what must come out: generated hex and tet10 meshes, and a hand-written file with comments, blank lines, trailing
+    commas, a node that no element uses (dropped, ids renumbered), a node defined twice (the later one stands), elements
+    out of id order, a GENERATE node group and a group naming the unused node."""
+    for k, mesh in enumerate((meshgen.hex_cube(5), meshgen.tet10_cube(3))):
+        p = str(tmp_path / ("g%d.msh" % k))
+        meshgen.write_msh(mesh, p)
+        _same_mesh(mshio._read_msh_bulk(p, 3), mshio._read_msh_line_by_line(p, 3))
+        assert np.array_equal(mshio.read_msh(p).elem_node_item, mesh.elem_node_item)
+    quirky = """!HEADER
+ a hand-written mesh
+!NODE
+  1, 0.0, 0.0, 0.0
+  2, 1.0, 0.0, 0.0,
+  3, 1.0, 1.0, 0.0
+  4, 0.0, 1.0, 0.0
+
+  5, 0.0, 0.0, 1.0
+  6, 1.0, 0.0, 1.0
+  7, 1.0, 1.0, 1.0
+  8, 0.0, 1.0, 1.0
+ 77, 9.0, 9.0, 9.0
+!! a comment between cards
+  9, 0.0, 0.0, 2.0
+ 10, 1.0, 0.0, 2.0
+ 11, 1.0, 1.0, 2.0
+ 12, 0.0, 1.0, 2.5
+ 12, 0.0, 1.0, 2.0
+!ELEMENT, TYPE=361, EGRP=ALL
+ 20, 5, 6, 7, 8, 9, 10, 11, 12
+ 10, 1, 2, 3, 4, 5, 6, 7, 8,
+!NGROUP, NGRP=FIX
+ 1, 2, 3, 4, 77
+!NGROUP, NGRP=TOP, GENERATE
+ 9, 12, 1
+!MATERIAL, NAME=M1, ITEM=1
+!ITEM=1, SUBITEM=2
+ 2.1E5, 0.3
+!SECTION, TYPE=SOLID, EGRP=ALL, MATERIAL=M1
+!END
+"""
+    p = str(tmp_path / "quirky.msh")
+    open(p, "w").write(quirky)
+    fast, slow = mshio._read_msh_bulk(p, 3), mshio._read_msh_line_by_line(p, 3)
+    _same_mesh(fast, slow)
+    assert fast.n_node == 12 and fast.node[3 * 11 + 2] == 2.0 and list(fast.node_group["FIX"]) == [1, 2, 3, 4]
+    assert list(fast.elem_node_item[:8]) == [1, 2, 3, 4, 5, 6, 7, 8] and fast.sections[0]["E"] == 2.1e5
+    # a token numpy cannot read: the bulk parse steps aside, the result is the line-by-line reader's error or mesh
+    bad = quirky.replace("  3, 1.0, 1.0, 0.0", "  3, 1.0, 1.0, 0.0D0")
+    open(p, "w").write(bad)
+    with pytest.raises(mshio._Irregular):
+        mshio._read_msh_bulk(p, 3)
+    with pytest.raises(ValueError):
+        mshio.read_msh(p)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/examples"), reason="reference tree not present")
+def test_msh_reader_bulk_parse_on_the_reference_example_meshes():
+    import glob
+    n = 0
+    for f in sorted(glob.glob("/root/reference/examples/static/ex[A-G]/*.msh")):
+        try:
+            slow = mshio._read_msh_line_by_line(f, 3)
+        except (NotImplementedError, IndexError, KeyError, ValueError):
+            continue                                  # element types / cards outside the hot-path scope
+        _same_mesh(mshio._read_msh_bulk(f, 3), slow)
+        n += 1
+    assert n >= 10
