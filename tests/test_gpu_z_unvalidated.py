@@ -1,5 +1,6 @@
 """GPU tests of device code that was written after GPU access had been closed for round 1 and has therefore never
-run on hardware: (1) the geometrically nonlinear path, (2) the SELL-C-sigma row ordering of the SpMV copy.
+run on hardware: (1) the geometrically nonlinear path, (2) the SELL-C-sigma row ordering of the SpMV copy, (3) the linear
+strain / stress recovery, (4) the BILU(0) preconditioner, (5) hecmw_mat_con on the device.
 
 (1) GPU parity of the geometrically nonlinear path: total-Lagrangian tangent assembly and
 strain / stress / internal-force update on the device, driven by the fstr_Newton mirror in frontistr_b200/hecmw.py,
