@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--tet", type=int, default=0)
     ap.add_argument("--precond", type=int, default=3)
     ap.add_argument("--tol", type=float, default=1e-10)
+    ap.add_argument("--iterpremax", type=int, default=1, help="sweeps of the preconditioner (precond_33.f90:86-114); > 1 exchanges Z between sweeps")
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl", "p2p-or-nccl"],
                     help="p2p: peer memory or fail loudly; p2p-or-nccl: peer memory if every rank can map it, else NCCL (bench.py's auto)")
     ap.add_argument("--host", action="store_true", help="TEST ONLY: no GPUs - every rank loads the host-compiled library "
@@ -54,7 +55,7 @@ def main():
     axes = {2: "x", 4: "xy", 8: "xyz"}[world]
     dom = partition.rcb_domains(gmesh, axes)
     m = partition.local_mesh(gmesh, dom, rank, world)
-    cnt = util.cube_cnt(tol=args.tol, precond=args.precond)
+    cnt = util.cube_cnt(tol=args.tol, precond=args.precond, iterpremax=args.iterpremax)
     A = util.product_problem(hecmw, m, cnt, to_host=False)
     r = hecmw.hecmw_solve(m, A, device_resident=True)
     # halo consistency: X on external nodes must equal the owner's value (hecmw_update_m_R at CG exit)
@@ -90,6 +91,10 @@ def main():
             it_ok = rp["error"] == 0 and abs(r["iter"] - rp["iter"]) <= 2
             print("     oracle on the same %d subdomains: %d iterations" % (world, rp["iter"]), flush=True)
         ok = (r["error"] == 0 and it_ok and err <= 1e-9 and r["resid2"] < args.tol and float(t.item()) == 0.0)
+        if r["error"] != 0 and r["error"] == ro["error"] and it_ok and err <= 1e-9:
+            # the reference algorithm gives up the same way on this system (e.g. 3003 for two DIAG sweeps on tet10): parity
+            print("     both the library and the oracle stop with error %d after %d iterations" % (r["error"], r["iter"]), flush=True)
+            ok = float(t.item()) == 0.0
         if sg is not None:
             e, s_, q = orc.update_linear(gmesh, xgl.reshape(-1))
             no = orc.nodal_stress_3d(gmesh, e, s_)
