@@ -58,45 +58,6 @@ def test_assembly_gather_equals_scatter_and_is_reproducible(gpu, name):
     assert np.abs(Ks[1][0] - Ks[0][0]).max() <= 1e-13 * scale
 
 
-def test_ic_inverse_selftest_picks_a_kernel_that_matches_the_oracle(gpu):
-    """The IC kernel exists with three ways of condensing the enhanced modes (calInverse through shared memory = the
-    reference's order and the kernel that ran on hardware, the same in registers + shuffles, LDL^T solves); unless the
-    option "ic_inverse" forces one, the library compares them on the device once per process and reports its choice.
-    Whatever it chose must match the oracle (1e-12, as test_assembly_matches_oracle), and so must the shared-memory
-    kernel when forced."""
-    mesh = util.distort(meshgen.hex_cube(5))
-    cnt = util.cube_cnt()
-    Ao = util.oracle_problem(mesh, cnt, apply_bc=False)
-    ref = np.concatenate([Ao.D, Ao.AL, Ao.AU])
-    for mode in (-1, 0):
-        gpu.set_option("ic_inverse", mode)
-        A = util.product_problem(gpu, mesh, cnt, to_host=True, apply_bc=False)
-        active = gpu.get_option("ic_inverse_active")
-        assert active in (0, 1, 2) and (mode < 0 or active == mode)
-        K = np.concatenate([A.D, A.AL, A.AU])
-        assert np.abs(K - ref).max() <= 1e-12 * np.abs(ref).max(), (mode, active)
-    gpu.set_option("ic_inverse", -1)
-
-
-@pytest.mark.xfail(strict=False, reason="register/shuffle and LDL^T condensation kernels: first hardware run (the library "
-                                        "falls back to the shared-memory kernel by itself if its device self-test fails)")
-@pytest.mark.parametrize("variant", [1, 2])
-def test_ic_inverse_register_kernel_matches_the_oracle(gpu, variant):
-    mesh = util.distort(meshgen.hex_cube(5))
-    cnt = util.cube_cnt()
-    Ao = util.oracle_problem(mesh, cnt, apply_bc=False)
-    ref = np.concatenate([Ao.D, Ao.AL, Ao.AU])
-    try:
-        gpu.set_option("ic_inverse", variant)
-        A = util.product_problem(gpu, mesh, cnt, to_host=True, apply_bc=False)
-    finally:
-        gpu.set_option("ic_inverse", -1)
-    K = np.concatenate([A.D, A.AL, A.AU])
-    assert np.abs(K - ref).max() <= 1e-12 * np.abs(ref).max()
-    key = "ic_selftest_ppb" if variant == 1 else "ic_selftest_ppb_ldlt"
-    assert gpu.get_option(key) in (-1, 0) or gpu.get_option(key) < 100
-
-
 def test_assembly_golden_decks(gpu):
     for name in ("A361", "A342"):
         mesh, cnt, _ = util.load_golden_mesh(name)
@@ -371,7 +332,11 @@ def test_large_properties(gpu):
     symmetry x.Ay == y.Ax, solve reaches the tolerance on the TRUE residual, and SpMV variants agree bitwise."""
     mesh = meshgen.hex_cube(64)
     cnt = util.cube_cnt(tol=1e-8)
-    A = util.product_problem(gpu, mesh, cnt, to_host=False)
+    gpu.set_option("ic_inverse", 0)        # 2.6e5 IC elements would start the library's kernel selection (a test of its own,
+    try:                                   # tests/test_gpu_z_unvalidated.py): this test keeps to the kernel that has run on hardware
+        A = util.product_problem(gpu, mesh, cnt, to_host=False)
+    finally:
+        gpu.set_option("ic_inverse", -1)
     n3 = 3 * A.N
     x = np.sin(np.arange(1, n3 + 1, dtype=float)); y = np.cos(0.37 * np.arange(1, n3 + 1, dtype=float))
     ys = {}

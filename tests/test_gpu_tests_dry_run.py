@@ -5,6 +5,7 @@ says nothing about the product."""
 import pytest
 
 import test_gpu_parity as G
+import test_gpu_z_unvalidated as Z
 from shadow_backend import ShadowBackend
 
 
@@ -24,9 +25,9 @@ def test_dry_run_solve_matches_oracle(meshname, precond, fused):
 
 
 def test_dry_run_ic_inverse_variants():
-    G.test_ic_inverse_selftest_picks_a_kernel_that_matches_the_oracle(ShadowBackend())
-    G.test_ic_inverse_register_kernel_matches_the_oracle(ShadowBackend(), 1)
-    G.test_ic_inverse_register_kernel_matches_the_oracle(ShadowBackend(), 2)
+    Z.test_ic_inverse_selftest_picks_a_kernel_that_matches_the_oracle(ShadowBackend())
+    Z.test_ic_inverse_register_kernel_matches_the_oracle(ShadowBackend(), 1)
+    Z.test_ic_inverse_register_kernel_matches_the_oracle(ShadowBackend(), 2)
 
 
 @pytest.mark.parametrize("name", ["A361", "B342", "F361", "F342"])

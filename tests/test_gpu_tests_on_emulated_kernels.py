@@ -21,9 +21,9 @@ def test_emulated_gather_equals_scatter():
 
 
 def test_emulated_ic_inverse_variants():
-    G.test_ic_inverse_selftest_picks_a_kernel_that_matches_the_oracle(EmulBackend())
-    G.test_ic_inverse_register_kernel_matches_the_oracle(EmulBackend(), 1)
-    G.test_ic_inverse_register_kernel_matches_the_oracle(EmulBackend(), 2)
+    Z.test_ic_inverse_selftest_picks_a_kernel_that_matches_the_oracle(EmulBackend())
+    Z.test_ic_inverse_register_kernel_matches_the_oracle(EmulBackend(), 1)
+    Z.test_ic_inverse_register_kernel_matches_the_oracle(EmulBackend(), 2)
 
 
 def test_emulated_bc_elimination():

@@ -402,3 +402,50 @@ def test_mat_con_on_the_device_error_contract(gpu):
         gpu.set_option("matcon_device", 0)
     H = gpu.hecmw_mat_con(ok)
     assert np.array_equal(A.itemL, H.itemL) and np.array_equal(A.indexU, H.indexU)
+
+
+# (6) the three ways of condensing the enhanced modes of the IC element and the library's selection among them (only the
+# shared-memory kernel has run on hardware; it is what every other test and smoke() use)
+
+def test_ic_inverse_selftest_picks_a_kernel_that_matches_the_oracle(gpu):
+    """The IC kernel exists with three ways of condensing the enhanced modes (calInverse through shared memory = the
+    reference's order and the kernel that ran on hardware, the same in registers + shuffles, LDL^T solves); unless the
+    option "ic_inverse" forces one, the library compares and times them on the device once per process - at the first IC
+    block of at least "ic_pick_min_elems" elements (lowered here) - and reports its choice; until then it uses the first.
+    Whatever it chose must match the oracle (1e-12, as test_assembly_matches_oracle), and so must the shared-memory
+    kernel when forced."""
+    from frontistr_b200 import meshgen
+    mesh = util.distort(meshgen.hex_cube(5))
+    cnt = util.cube_cnt()
+    Ao = util.oracle_problem(mesh, cnt, apply_bc=False)
+    ref = np.concatenate([Ao.D, Ao.AL, Ao.AU])
+    gpu.set_option("ic_pick_min_elems", 64)     # the selection normally waits for an IC block of 2^16 elements
+    try:
+        for mode in (-1, 0):
+            gpu.set_option("ic_inverse", mode)
+            A = util.product_problem(gpu, mesh, cnt, to_host=True, apply_bc=False)
+            active = gpu.get_option("ic_inverse_active")
+            assert active in (0, 1, 2) and (mode < 0 or active == mode)
+            K = np.concatenate([A.D, A.AL, A.AU])
+            assert np.abs(K - ref).max() <= 1e-12 * np.abs(ref).max(), (mode, active)
+        assert gpu.get_option("ic_selftest_ppb") >= 0 and gpu.get_option("ic_time_us_smem") >= 0    # the selection did run
+    finally:
+        gpu.set_option("ic_inverse", -1); gpu.set_option("ic_pick_min_elems", 1 << 16)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_ic_inverse_register_kernel_matches_the_oracle(gpu, variant):
+    from frontistr_b200 import meshgen
+    mesh = util.distort(meshgen.hex_cube(5))
+    cnt = util.cube_cnt()
+    Ao = util.oracle_problem(mesh, cnt, apply_bc=False)
+    ref = np.concatenate([Ao.D, Ao.AL, Ao.AU])
+    try:
+        gpu.set_option("ic_inverse", variant)
+        A = util.product_problem(gpu, mesh, cnt, to_host=True, apply_bc=False)
+    finally:
+        gpu.set_option("ic_inverse", -1)
+    K = np.concatenate([A.D, A.AL, A.AU])
+    assert np.abs(K - ref).max() <= 1e-12 * np.abs(ref).max()
+    key = "ic_selftest_ppb" if variant == 1 else "ic_selftest_ppb_ldlt"
+    assert gpu.get_option(key) in (-1, 0) or gpu.get_option(key) < 100
