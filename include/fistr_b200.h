@@ -37,7 +37,15 @@ extern "C" {
 int fistr_b200_init(int device_ordinal);
 int fistr_b200_finalize(void);
 const char *fistr_b200_last_error(void);
-/* integer tuning knobs ("spmv_variant", "cg_fused", "launch_count_reset", ...) */
+/* Integer knobs and read-outs (unknown keys read as -1).
+ *   set: "spmv_variant" 0|1|2 (2), "sell_sigma" rows of the SELL-C-sigma sorting window (0 = off), "spmv_blocks_per_sm" (8),
+ *        "cg_fused" 0|1 (1), "cg_check_interval" iterations per launch batch, "time_ax" 0|1, "asm_gather" 0|1 (1),
+ *        "asm_probe" development switches of the assembly kernel (0), "ic_inverse" -1 auto | 0 | 1 | 2 (-1),
+ *        "ic_pick_min_elems" IC block size that starts the kernel selection (65536), "p2p" 0 NCCL | 1 peer memory if
+ *        every rank can map it | 2 peer memory or fail (1), "matcon_device" 0|1 (0), "bilu_chain_rows" (256),
+ *        "launch_count_reset"
+ *   get: "ic_inverse_active", "ic_selftest_ppb", "ic_selftest_ppb_ldlt", "ic_time_us_smem|reg|ldlt", "ic_time_elems",
+ *        "bilu_levels", "bilu_launches_per_apply", "update_kernel_us", "nodal_stress_kernel_us", "p2p_active" */
 int fistr_b200_set_option(const char *key, int64_t value);
 int64_t fistr_b200_get_option(const char *key);
 
