@@ -2,6 +2,9 @@
 # Safety gate before any kernel that has never run on hardware is launched uninstrumented: the small GPU tests that
 # exercise it run under compute-sanitizer (memcheck squashes a bad access instead of faulting the GPU).  Only when
 # the gate is clean does the validation script proper run.
+# Gate 1: assembly + Dirichlet elimination of the validated suite (the element kernels were refactored after their last
+# hardware run).  Gate 2: tests/test_gpu_z_unvalidated.py = everything that has never run on a GPU (nonlinear path, linear
+# strain / stress recovery, SELL-C-sigma, BILU(0), device hecmw_mat_con, the IC kernel selection and its two new kernels).
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt
 SAN="compute-sanitizer --error-exitcode 9 --print-limit 5"
