@@ -61,6 +61,13 @@ def test_collective_transport_ssor_2_ranks():
     assert "p2p_active=0" in lines[-1]
 
 
+def test_two_preconditioner_sweeps_2_ranks():
+    """iterPREmax = 2 (precond_33.f90:110-113): between the sweeps Z is halo-exchanged and ZP = R - A Z is formed on every rank;
+    same iteration count as the oracle on the same two subdomains."""
+    lines = _torchrun(2, "dist_check.py", "--host", "--hex", "6", "--comm", "p2p", "--precond", "1", "--iterpremax", "2")
+    assert "precond=1" in lines[-1]
+
+
 def test_bilu0_2_ranks():
     """PRECOND = 10 on two subdomains (the factorisation runs over internal AND halo rows, the substitution over internal
     rows): same iteration count as the oracle on the same decomposition, solution equal to the serial one."""
