@@ -56,7 +56,7 @@ def parse_args():
     ap.add_argument("--ref-iters", type=int, default=0, help="CG iterations per reference-arm step (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-ic-probe", action="store_true", help="skip the post-line run of the IC kernel selection (N = 1)")
+    ap.add_argument("--ic-probe", action="store_true", help="opt-in: after the line, run the IC kernel selection (self-test + timing; N = 1)")
     ap.add_argument("--comm", default="auto", choices=["auto", "p2p", "nccl"],
                     help="N>1 transport of the halo exchange + dot-product all-reduce: peer-memory stores issued by the CG "
                          "kernels (p2p) or NCCL.  auto = what has RUN ON HARDWARE at that N: p2p at N=2, NCCL at N>2 (p2p at "
@@ -430,7 +430,7 @@ def run_b200(args):
                                     "(atomic scatter-add incl. matrix zeroing if gather=0); 150 kflop/element (SURVEY a5)"},
                "setup_s": {"mesh+partition": t_mesh, "mat_con": t_con}, "device": dev["name"]}
         print(json.dumps(out), flush=True)
-    if world == 1 and not getattr(args, "no_ic_probe", False):
+    if world == 1 and getattr(args, "ic_probe", False):
         try:
             hecmw.set_option("ic_inverse", -1)
             t = hecmw.fstr_StiffMatrix(mesh, A, to_host=False)

@@ -9,9 +9,10 @@ against the oracle (which reproduces the reference's exI golden logs at every su
 STATUS: these kernels were written after GPU access had been closed for round 1 (see profiles/r1_multi_gpu.md) and
 have not run on hardware.  What they do has been checked on the CPU instead, through the real C-ABI: the whole library
 is compiled for the host (tools/build_hostemu.py), every "device" buffer ends at a guard page, and the bodies of
-exactly these tests pass there (tests/test_gpu_suite_on_host_api.py).  They therefore run by default (this file sorts
-last, so nothing comes after it in the process) but stay non-strict xfail until their first hardware run: a mismatch
-that only a real GPU can produce must not turn the suite red.  FISTR_B200_SKIP_UNVALIDATED=1 leaves them out."""
+exactly these tests pass there (tests/test_gpu_suite_on_host_api.py).  They are OPT-IN: skipped unless
+FISTR_B200_RUN_UNVALIDATED=1 (or the older FISTR_B200_RUN_NL_GPU=1 the scripts export), and the first run of each is
+under compute-sanitizer on one GPU (tools/gpu_gate.sh).  A test moves to tests/test_gpu_parity.py only after it has
+passed there.  No xfail: a mismatch is a failure."""
 import os
 
 import numpy as np
@@ -20,10 +21,9 @@ import pytest
 import fb_util as util
 from frontistr_b200.hecmw_types import kel361BBAR
 
+_OPT_IN = os.environ.get("FISTR_B200_RUN_UNVALIDATED") == "1" or os.environ.get("FISTR_B200_RUN_NL_GPU") == "1"
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("FISTR_B200_SKIP_UNVALIDATED") == "1", reason="FISTR_B200_SKIP_UNVALIDATED=1"),
-              pytest.mark.xfail(strict=False, reason="kernels not yet run on hardware (round 1: GPU access closed); validated "
-                                                     "on the CPU through the host-compiled library")]
+              pytest.mark.skipif(not _OPT_IN, reason="never-on-hardware kernels are opt-in: FISTR_B200_RUN_UNVALIDATED=1")]
 
 
 def _cloads(mesh, g):
