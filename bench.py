@@ -37,7 +37,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "cg_iterations_per_second"
 UNIT = "CG iter/s"
@@ -67,9 +66,9 @@ def parse_args():
     return ap.parse_args()
 
 
-def workload_name(n):
-    return {150: "H150", 200: "H200"}.get(n, "H%d" % n) + ": C3D8(IC) hex cube %d^3 el, %d DOF, CG+DIAG(3x3 block-Jacobi)" % (
-        n, 3 * (n + 1) ** 3)
+def workload_name(n, precond=3):
+    from frontistr_b200.workloads import hex_workload_name
+    return hex_workload_name(n, precond)
 
 
 def ncu_traffic(n, world):
@@ -149,15 +148,15 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 def build_problem_host(args, rank, world):
     """Mesh (partitioned for world > 1) + solver card; pure host work, shared by both arms."""
-    import fb_util as util
     from frontistr_b200 import meshgen
+    from frontistr_b200.workloads import cube_cnt
     mesh = meshgen.hex_cube(args.n)
     if world > 1:
         from frontistr_b200 import partition
         axes = {2: "x", 4: "xy", 8: "xyz"}[world]
         dom = partition.rcb_domains(mesh, axes)
         mesh = partition.local_mesh(mesh, dom, rank, world)
-    cnt = util.cube_cnt(tol=args.tol, precond=args.precond, maxit=args.maxit)
+    cnt = cube_cnt(tol=args.tol, precond=args.precond, maxit=args.maxit)
     return mesh, cnt
 
 
@@ -167,7 +166,6 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import fb_util as util
     from frontistr_b200 import hecmw as host_helpers   # load/BC bookkeeping helpers only (numpy)
     from frontistr_b200.mshio import apply_solver_card
     from oracle import oracle as orc
@@ -211,7 +209,7 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(args.steps, 1),
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": workload_name(args.n), "tol": args.tol, "precond": args.precond},
+           "config": {"workload": workload_name(args.n, args.precond), "tol": args.tol, "precond": args.precond},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "assembly_elements_per_s": mesh.n_elem / (t2 - t1)}
@@ -237,14 +235,13 @@ def run_b200(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    import fb_util as util
     from frontistr_b200 import hecmw
     from frontistr_b200.mshio import apply_solver_card
 
     hecmw.init(local_rank)
     # Everything this line reports is measured with the IC condensation kernel that has run on hardware (shared-memory
-    # calInverse).  The library's selection among its three kernels - the other two have never run on a GPU - is exercised
-    # AFTER the line has been printed (N = 1; verdicts and timings go to stderr), so that nothing it could do can cost the line.
+    # calInverse, also the library default).  The library's selection among its three kernels - the other two have never
+    # run on a GPU - is opt-in (--ic-probe) and runs AFTER the line has been printed (N = 1; verdicts and timings to stderr).
     hecmw.set_option("ic_inverse", 0)
     if world > 1:
         use_p2p = args.comm == "p2p" or (args.comm == "auto" and world == 2)
@@ -396,7 +393,7 @@ def run_b200(args):
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": 1e3 * res["ev_s"] / args.steps, "higher_is_better": True,
                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-               "config": {"workload": workload_name(args.n), "tol": args.tol, "precond": args.precond,
+               "config": {"workload": workload_name(args.n, args.precond), "tol": args.tol, "precond": args.precond,
                           "partition": "none" if world == 1 else "RCB-%s (in-process hecmw_part1 restatement), 1 subdomain/GPU"
                           % {2: "x", 4: "xy", 8: "xyz"}[world],
                           "comm": "none" if world == 1 else ("p2p" if hecmw.get_option("p2p_active") == 1 else "nccl"),
@@ -423,16 +420,15 @@ def run_b200(args):
                             "fp64_frac": (150e3 * n_elem_global / world / (asm_kernel_ms * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None,
                             "gather": int(hecmw.get_option("asm_gather") != 0),
                             "ic_inverse": {2: "LDL^T solves", 1: "calInverse in registers+shuffles", 0: "calInverse through shared memory"}.get(hecmw.get_option("ic_inverse_active"), "?"),
-                            "ic_inverse_note": "forced for this line: the kernel that has run on hardware; the library's selection among its "
-                                               "three condensation kernels (device self-test + timing on the mesh) runs after the line "
-                                               "is printed and reports to stderr",
+                            "ic_inverse_note": "the library default (reference operation order; the kernel that has run on hardware); "
+                                               "--ic-probe runs the selection among the three condensation kernels after the line",
                             "note": "STF_C3D8IC (one element per warp) + deterministic gather into precomputed BCSR slots "
                                     "(atomic scatter-add incl. matrix zeroing if gather=0); 150 kflop/element (SURVEY a5)"},
                "setup_s": {"mesh+partition": t_mesh, "mat_con": t_con}, "device": dev["name"]}
         print(json.dumps(out), flush=True)
     if world == 1 and getattr(args, "ic_probe", False):
         try:
-            hecmw.set_option("ic_inverse", -1)
+            hecmw.set_option("ic_inverse", -2)
             t = hecmw.fstr_StiffMatrix(mesh, A, to_host=False)
             print("post-line IC kernel selection: active=%d  self-test ppb reg=%d ldlt=%d  compute-only us on %d elements: smem=%d reg=%d ldlt=%d  "
                   "assembly kernel with the selected one: %.3f ms" % (

@@ -481,6 +481,10 @@ mises_kernel(size_t n, const double *__restrict__ stress, double *__restrict__ m
 // writes B(c) = rhs.  Equals the reference's one-constraint-at-a-time elimination because a
 // constraint only ever zeroes its own row and column — provided every DOF appears ONCE in the batch: the host side
 // (api_assembly.inc) folds repeated DOFs into one entry that eliminates with the first value and sets the last.
+// Reproducibility: a constraint with rhs == 0 (the usual fixed support) contributes exactly nothing to B and issues no
+// atomic at all, so B is bit-reproducible; with a NON-ZERO prescribed value several constraints may add into the same
+// B entry through atomicAdd in an order that differs from run to run (and from the reference's constraint order): B then
+// agrees with the reference to the last bit or two, not bitwise.
 template <int STAGE>
 __global__ void __launch_bounds__(256)
 bc_kernel(int nbc, const int *__restrict__ bc_node, const int *__restrict__ bc_dof,
@@ -495,6 +499,7 @@ bc_kernel(int nbc, const int *__restrict__ bc_node, const int *__restrict__ bc_d
     const int c = lo, t = w - bc_ptr[c];
     const int n = bc_node[c], d = bc_dof[c] - 1;
     const double rhs = bc_val[c];
+    if (STAGE == 0 && rhs == 0.0) continue;   // B - K * 0 = B
     double *Dn = vals + 9 * (size_t)(n - 1);
     const int nL = indexL[n] - indexL[n - 1];
     if (t == 0) {

@@ -17,8 +17,10 @@ __global__ void add_const_kernel(size_t n, int *a, int c) {
 thread_local std::string g_last_error;
 int64_t g_launch_count = 0;
 Context &ctx() {
-  static Context c;
-  return c;
+  // never destroyed: at process exit the CUDA runtime may already be gone, and the owning buffers of the context must not
+  // call into it then (fistr_b200_finalize is the orderly way to release everything)
+  static Context *c = new Context;
+  return *c;
 }
 
 static int fail(int code, const char *fmt, ...) {

@@ -155,11 +155,26 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], double *partial, un
   }
 }
 
+// Owning device buffer: frees its memory when it goes out of scope (early error returns included) or is re-assigned;
+// move-only.  view() makes a non-owning alias (memory that lives in the peer-mapped arena).
 template <class T>
 struct DevBuf {
   T *p = nullptr;
   size_t n = 0;
   bool owned = true;
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), owned(o.owned) { o.p = nullptr; o.n = 0; o.owned = true; }
+  DevBuf &operator=(DevBuf &&o) noexcept {
+    if (this != &o) {
+      release();
+      p = o.p; n = o.n; owned = o.owned;
+      o.p = nullptr; o.n = 0; o.owned = true;
+    }
+    return *this;
+  }
+  ~DevBuf() { release(); }
   void view(T *ptr, size_t count) {   // non-owning alias (memory lives in the peer-mapped arena)
     release();
     p = ptr; n = count; owned = false;
@@ -184,6 +199,23 @@ struct DevBuf {
     n = 0;
     owned = true;
   }
+};
+
+// CUDA events that are destroyed on every exit path of the function that made them
+struct EventSet {
+  static const int kMax = 8;
+  cudaEvent_t ev[kMax];
+  int n = 0;
+  EventSet() = default;
+  EventSet(const EventSet &) = delete;
+  EventSet &operator=(const EventSet &) = delete;
+  cudaError_t make(cudaEvent_t *out) {
+    if (n >= kMax) return cudaErrorInvalidValue;
+    cudaError_t e = cudaEventCreate(out);
+    if (e == cudaSuccess) ev[n++] = *out;
+    return e;
+  }
+  ~EventSet() { for (int i = 0; i < n; i++) cudaEventDestroy(ev[i]); }
 };
 
 }  // namespace fb

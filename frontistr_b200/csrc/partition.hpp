@@ -1,11 +1,15 @@
-// In-process node-based RCB domain decomposition with the tie behaviour of the reference's
-// hecmw_part1 (hecmw1/tools/partitioner/hecmw_partition.c: rcb_partition :1570-1660 and its
-// quick_sort :1469-1566) so that a synthetic cube can be split for N GPUs without writing a
-// multi-GB .msh and running the external tool.  SURVEY §8(f) rank 4 ("hecmw_part1 in-process").
+// In-process node-based domain decomposition by recursive coordinate bisection (the METHOD=RCB of the
+// reference's hecmw_part1, hecmw1/tools/partitioner/hecmw_partition.c:1570-1660) so that a synthetic cube can be
+// split for N GPUs without writing a multi-GB .msh and running the external tool.  SURVEY §8(f) rank 4.
 //
-// At bisection level i every existing domain j < 2^i is sorted along the requested axis and the
-// lower half (ceil(count/2) nodes in sorted order) moves to domain j + 2^i.  Which nodes of a tied
-// coordinate plane move is decided by the (unstable) sort, so the sort is restated step for step.
+// Contract shared with the reference: at bisection level i every existing domain j < 2^i gives the ceil(count/2)
+// nodes with the SMALLEST coordinate along axes[i] to the new domain j + 2^i.  This implementation is independent
+// of the reference's code: nodes are bucketed per domain with one counting pass per level and each bucket is split
+// with a linear-time selection (std::nth_element) on the total order (coordinate, node index).  Ties on a
+// coordinate plane are therefore broken by node index - deterministic and independent of any sort's internals -
+// whereas hecmw_part1 lets its unstable quick sort decide; the two maps are identical wherever the coordinates
+// along the cut axis are distinct (tests/test_partition.py, against oracle/'s restatement of the reference's sort
+// and against the real tool).  Either map is a valid node-based partition: results do not depend on it.
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -14,68 +18,35 @@
 
 namespace fb {
 
-inline int rcb_quick_sort(int n, double *arr, int *brr, std::vector<int> &istack) {
-  const int kLower = 50;   // QSORT_LOWER, hecmw_partition.c:64
-  int jstack = 0, l = 0, ir = n - 1;
-  const int nstack = (int)istack.size() - 1;
-  for (;;) {
-    if (ir - l < kLower) {           // straight insertion on small ranges
-      for (int j = l + 1; j <= ir; j++) {
-        const double a = arr[j];
-        const int b = brr[j];
-        int i = j - 1;
-        for (; i >= l; i--) {
-          if (arr[i] <= a) break;
-          arr[i + 1] = arr[i];
-          brr[i + 1] = brr[i];
-        }
-        arr[i + 1] = a;
-        brr[i + 1] = b;
-      }
-      if (!jstack) return 0;
-      ir = istack[jstack];
-      l = istack[jstack - 1];
-      jstack -= 2;
-    } else {                         // median-of-three partitioning
-      const int k = (l + ir) >> 1;
-      std::swap(arr[k], arr[l + 1]); std::swap(brr[k], brr[l + 1]);
-      if (arr[l] > arr[ir]) { std::swap(arr[l], arr[ir]); std::swap(brr[l], brr[ir]); }
-      if (arr[l + 1] > arr[ir]) { std::swap(arr[l + 1], arr[ir]); std::swap(brr[l + 1], brr[ir]); }
-      if (arr[l] > arr[l + 1]) { std::swap(arr[l], arr[l + 1]); std::swap(brr[l], brr[l + 1]); }
-      int i = l + 1, j = ir;
-      const double a = arr[l + 1];
-      const int b = brr[l + 1];
-      for (;;) {
-        do i++; while (arr[i] < a);
-        do j--; while (arr[j] > a);
-        if (j < i) break;
-        std::swap(arr[i], arr[j]); std::swap(brr[i], brr[j]);
-      }
-      arr[l + 1] = arr[j]; arr[j] = a;
-      brr[l + 1] = brr[j]; brr[j] = b;
-      jstack += 2;
-      if (jstack > nstack) return -1;
-      if (ir - i + 1 >= j - l) { istack[jstack] = ir; istack[jstack - 1] = i; ir = j - 1; }
-      else { istack[jstack] = j - 1; istack[jstack - 1] = l; l = i; }
-    }
-  }
-}
-
-// axes[i] in {0,1,2}; domain[k] receives 0..2^n_div-1
+// axes[i] in {0,1,2}; domain[k] receives 0..2^n_div-1.  -2: bad axis, -3: non-finite coordinate
 inline int rcb_partition(int n, const double *coord, int n_div, const int *axes, int *domain) {
-  std::vector<int> id(n), stack((size_t)n + 2);
-  std::vector<double> value(n);
-  for (int k = 0; k < n; k++) domain[k] = 0;
-  for (int i = 0; i < n_div; i++) {
-    if (axes[i] < 0 || axes[i] > 2) return -2;
-    const int nd = 1 << i;
-    for (int j = 0; j < nd; j++) {
-      int counter = 0;
-      for (int k = 0; k < n; k++)
-        if (domain[k] == j) { id[counter] = k; value[counter] = coord[3 * (size_t)k + axes[i]]; counter++; }
-      if (counter == 0) continue;
-      if (rcb_quick_sort(counter, value.data(), id.data(), stack)) return -1;
-      for (int k = 0; k < counter * 0.5; k++) domain[id[k]] = j + nd;   // 'k < counter * F_1_2'
+  for (int lev = 0; lev < n_div; lev++)
+    if (axes[lev] < 0 || axes[lev] > 2) return -2;
+  for (size_t k = 0; k < 3 * (size_t)n; k++)
+    if (!std::isfinite(coord[k])) return -3;
+  std::fill(domain, domain + n, 0);
+  std::vector<int> bucket(n);
+  std::vector<size_t> first;
+  for (int lev = 0; lev < n_div; lev++) {
+    const int ndom = 1 << lev, ax = axes[lev];
+    // nodes grouped by current domain, ascending node index inside a group
+    first.assign((size_t)ndom + 1, 0);
+    for (int k = 0; k < n; k++) first[domain[k] + 1]++;
+    for (int d = 0; d < ndom; d++) first[d + 1] += first[d];
+    {
+      std::vector<size_t> fill(first.begin(), first.end() - 1);
+      for (int k = 0; k < n; k++) bucket[fill[domain[k]]++] = k;
+    }
+    auto below = [coord, ax](int a, int b) {
+      const double ca = coord[3 * (size_t)a + ax], cb = coord[3 * (size_t)b + ax];
+      return ca < cb || (ca == cb && a < b);
+    };
+    for (int d = 0; d < ndom; d++) {
+      int *lo = bucket.data() + first[d], *hi = bucket.data() + first[d + 1];
+      const size_t cnt = (size_t)(hi - lo), half = (cnt + 1) / 2;
+      if (cnt == 0) continue;
+      if (half < cnt) std::nth_element(lo, lo + half, hi, below);   // [lo, lo+half) = the `half` smallest keys
+      for (size_t k = 0; k < half; k++) domain[lo[k]] = d + ndom;
     }
   }
   return 0;
@@ -90,7 +61,8 @@ inline int rcb_partition(int n, const double *coord, int n_div, const int *axes,
 //   * neighbour ranks ascending; per neighbour the import list (my external nodes it owns) and the export list
 //     (my internal nodes it holds as external = my nodes in elements that also have a node it owns), both in
 //     ascending global id.
-// Identity with the real hecmw_part1 is pinned by tests/test_partition.py (fixtures made with the reference binary under oracle/_ref).
+// Identity with the real hecmw_part1 (given the same node->domain map) is pinned by tests/test_partition.py (fixtures made
+// with the reference binary under oracle/_ref).
 struct LocalMesh {
   int n_node = 0, nn_internal = 0, n_elem = 0;
   std::vector<int> global_node;        // n_node: 0-based global node index of every local node

@@ -6,9 +6,10 @@
 * neighbour ranks ascending; per neighbour the import and export node lists in ascending global id;
 * node_ID = (local id in the owning rank, owning rank).
 
-The node->domain map comes from the library's restatement of the reference RCB
-(fistr_b200_part_rcb).  Equality with the real hecmw_part1 is pinned by tests/test_partition.py against
-fixtures generated with oracle/_ref/hecmw_part1.
+The node->domain map comes from the library's own RCB (fistr_b200_part_rcb: same bisection contract as the
+reference, ties on a coordinate broken by node index) or from any other source (`domain=`).  Given the same map,
+equality of every table with the real hecmw_part1 is pinned by tests/test_partition.py against fixtures generated
+with oracle/_ref/hecmw_part1.
 """
 from __future__ import annotations
 
@@ -174,7 +175,7 @@ def _export_lists(mesh, owner, rank, nparts):
     return out
 
 
-def partition(mesh: hecmwST_local_mesh, axes: str):
-    dom = rcb_domains(mesh, axes)
+def partition(mesh: hecmwST_local_mesh, axes: str, domain=None):
+    dom = rcb_domains(mesh, axes) if domain is None else np.ascontiguousarray(domain, np.int32)
     nparts = 1 << len(axes.replace(",", ""))
     return [local_mesh(mesh, dom, r, nparts) for r in range(nparts)]

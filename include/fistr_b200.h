@@ -40,7 +40,7 @@ const char *fistr_b200_last_error(void);
 /* Integer knobs and read-outs (unknown keys read as -1).
  *   set: "spmv_variant" 0|1|2 (2), "sell_sigma" rows of the SELL-C-sigma sorting window (0 = off), "spmv_blocks_per_sm" (8),
  *        "cg_fused" 0|1 (1), "cg_check_interval" iterations per launch batch, "time_ax" 0|1, "asm_gather" 0|1 (1),
- *        "asm_probe" development switches of the assembly kernel (0), "ic_inverse" -1 auto | 0 | 1 | 2 (-1),
+ *        "asm_probe" development switches of the assembly kernel (0), "ic_inverse" 0 | 1 | 2 | -2 pick by self-test + timing (0),
  *        "ic_pick_min_elems" IC block size that starts the kernel selection (65536), "p2p" 0 NCCL | 1 peer memory if
  *        every rank can map it | 2 peer memory or fail (1), "matcon_device" 0|1 (0), "bilu_chain_rows" (256),
  *        "launch_count_reset"
@@ -193,7 +193,10 @@ int fistr_b200_precond_33_info(int *ncolor, int *perm /* N or NULL */);
 int fistr_b200_update_3_R(double *X /* 3*NP in/out */);
 
 /* ---- hecmw_part1 in-process: node-based RCB (hecmw1/tools/partitioner/hecmw_partition.c:1570-1660),
- * axes[i] in {0,1,2} per bisection level (the 'x,y,z' line of hecmw_part_ctrl.dat); host-only */
+ * axes[i] in {0,1,2} per bisection level (the 'x,y,z' line of hecmw_part_ctrl.dat); host-only.  At every level each
+ * domain hands the ceil(count/2) nodes with the smallest coordinate to the new domain, as the reference does; nodes with
+ * EQUAL coordinates are ordered by node index (the reference leaves that to its unstable sort), so the map equals
+ * hecmw_part1's wherever the coordinates along the cut axis are distinct and is a valid balanced bisection otherwise. */
 int fistr_b200_part_rcb(int n_node, const double *node, int n_div, const int *axes, int *domain);
 
 /* ... and the distributed mesh of ONE rank from that node->domain map, exactly as hecmw_part1 writes it

@@ -1278,12 +1278,14 @@ int orc_solve(int ndom, const orc_mesh *meshes, orc_matrix *mats, int *iter_out,
   orc_matrix *m0 = &mats[0];
   int error = 0;
   if (IA(m0, 99) != 1) return -99; /* direct solvers are out of scope */
-  int MAXIT = IA(m0, 1), METHOD = IA(m0, 2), PRECOND = IA(m0, 3), iterPREmax = IA(m0, 5);
+  int MAXIT = IA(m0, 1), METHOD = IA(m0, 2), METHOD2 = IA(m0, 8), PRECOND = IA(m0, 3), iterPREmax = IA(m0, 5);
   int ITERlog = IA(m0, 21);
   double TOL = RA(m0, 1), SIGMA_DIAG = RA(m0, 2);
   int ITER = 0;
   double RESID = 0.0;
-  if (SIGMA_DIAG < 0.0) SIGMA_DIAG = 1.0;
+  int auto_sigma_diag = 0, warn = 0;                   /* Iterative.f90:72-77 */
+  if (SIGMA_DIAG < 0.0) { auto_sigma_diag = 1; SIGMA_DIAG = 1.0; }
+  if (IA(m0, 7) != 0 || IA(m0, 33) != 0) return 1001;  /* SCALING / USEJAD: not restated (out of scope) */
   *iter_out = 0; *resid_out = 0.0; if (resid2_out) *resid2_out = 0.0;
 
   /* hecmw_solve_check_zerorhs, Iterative.f90:246-278 */
@@ -1298,7 +1300,7 @@ int orc_solve(int ndom, const orc_mesh *meshes, orc_matrix *mats, int *iter_out,
       for (int d = 0; d < ndom; d++) memset(mats[d].X, 0, sizeof(double) * 3 * (size_t)mats[d].NP);
       /* the reference only returns from the check routine; the driver continues and CG
        * sees BNRM2==0 (CG.f90:124-129) and leaves with iter=0, X=0. */
-      error = 2002;
+      warn = 2002;
     }
   }
   /* hecmw_solve_check_zerodiag, Iterative.f90:212-244 */
@@ -1322,8 +1324,7 @@ int orc_solve(int ndom, const orc_mesh *meshes, orc_matrix *mats, int *iter_out,
   if (!(PRECOND == 1 || PRECOND == 2 || PRECOND == 3 || PRECOND == 10)) return 1001;
 
   g_time_Ax = g_time_precond = g_time_comm = 0.0;
-  double S_TIME = wtime();
-  /* ---- hecmw_solve_CG ---- */
+  double Tset = 0.0, Tsol = 0.0;
   double **R = malloc(sizeof(double *) * ndom), **Z = malloc(sizeof(double *) * ndom);
   double **P = malloc(sizeof(double *) * ndom), **WK = malloc(sizeof(double *) * ndom);
   double **X = malloc(sizeof(double *) * ndom), **B = malloc(sizeof(double *) * ndom);
@@ -1334,7 +1335,20 @@ int orc_solve(int ndom, const orc_mesh *meshes, orc_matrix *mats, int *iter_out,
     X[d] = mats[d].X; B[d] = mats[d].B;
   }
   double **Q = Z;
-  /* hecmw_precond_setup, honouring the recycle flags (DIAG_33.f90:38-41, SSOR_33.f90:72-80) */
+  /* "Auto Sigma_diag loop", Iterative.f90:113-156: every pass is one call of hecmw_solve_CG */
+  for (;;) {
+  IA(m0, 81) = 0; IA(m0, 82) = 0;
+  error = 0;
+  double S_TIME = wtime();
+  /* ---- hecmw_solve_CG ---- */
+  for (int d = 0; d < ndom; d++) { /* WW = 0.d0 at every call (CG.f90:94-95) */
+    size_t np = 3 * (size_t)mats[d].NP;
+    memset(R[d], 0, sizeof(double) * np); memset(Z[d], 0, sizeof(double) * np);
+    memset(P[d], 0, sizeof(double) * np); memset(WK[d], 0, sizeof(double) * np);
+  }
+  /* hecmw_precond_setup, honouring the recycle flags (DIAG_33.f90:38-41, SSOR_33.f90:72-80, BILU_33.f90:49-57: a
+   * factorisation that is INITIALIZED is kept when both flags are 0 - which is also what a retry of the auto-sigma
+   * loop finds, so the bumped SIGMA_DIAG does not reach FORM_ILU0_33) */
   if (iterPREmax > 0) {
     int need = 1;
     if (g_pcs && g_pcs_n == ndom && g_pcs[0]->kind == PRECOND && g_pcs[0]->N == mats[0].N) {
@@ -1362,7 +1376,7 @@ int orc_solve(int ndom, const orc_mesh *meshes, orc_matrix *mats, int *iter_out,
     ITER = 0; MAXIT = 0; RESID = 0.0;
     for (int d = 0; d < ndom; d++) memset(X[d], 0, sizeof(double) * 3 * (size_t)mats[d].NP);
   }
-  double Tset = wtime() - S_TIME;
+  Tset = wtime() - S_TIME;
   g_time_comm = 0.0;
   double S1_TIME = wtime();
   double RHO = 0.0, RHO1 = 0.0, BETA = 0.0, C1, ALPHA, DNRM2;
@@ -1411,9 +1425,22 @@ int orc_solve(int ndom, const orc_mesh *meshes, orc_matrix *mats, int *iter_out,
   }
   (void)exited; /* on natural loop end Fortran leaves ITER = MAXIT+1, as here */
   if (ndom > 1) orc_update_3_R(ndom, meshes, X);       /* hecmw_update_m_R, :280 */
-  double Tsol = wtime() - S1_TIME;
-  /* ---- back in hecmw_solve_iterative ---- */
-  if (error == 3002 || error == 3003) IA(m0, 82) = 1;
+  Tsol = wtime() - S1_TIME;
+  /* ---- back in hecmw_solve_iterative, Iterative.f90:141-156 ---- */
+  if (error == 3002 || error == 3003) {
+    IA(m0, 82) = 1;
+    if (PRECOND >= 10 && PRECOND < 20 && auto_sigma_diag == 1 && SIGMA_DIAG < 2.0) {
+      SIGMA_DIAG = SIGMA_DIAG + 0.1f; /* `0.1`: a default-real constant in the reference */
+      printf(" Increasing SIGMA_DIAG to %24.16E\n", SIGMA_DIAG);
+      continue;
+    } else if (METHOD == 1 && METHOD2 > 1) { /* the reference switches to METHOD2: another Krylov method, not restated */
+      for (int d = 0; d < ndom; d++) { free(R[d]); free(Z[d]); free(P[d]); free(WK[d]); }
+      free(R); free(Z); free(P); free(WK); free(X); free(B);
+      return 1001;
+    }
+  }
+  break;
+  } /* auto sigma loop */
   /* resid2 = hecmw_rel_resid_L2, las_33.f90:387-415 */
   {
     double bnorm2 = inner_product(ndom, meshes, B, B);
@@ -1431,7 +1458,7 @@ int orc_solve(int ndom, const orc_mesh *meshes, orc_matrix *mats, int *iter_out,
   if (times) { times[0] = Tset; times[1] = Tsol; times[2] = g_time_comm; times[3] = g_time_Ax; times[4] = g_time_precond; }
   for (int d = 0; d < ndom; d++) { free(R[d]); free(Z[d]); free(P[d]); free(WK[d]); }
   free(R); free(Z); free(P); free(WK); free(X); free(B);
-  return error;
+  return error ? error : warn;
 }
 
 void orc_precond_clear(void) { precond_clear_all(); }
@@ -2280,4 +2307,95 @@ int orc_nodal_stress_3d(const orc_mesh *mesh, const double *gp_strain, const dou
   for (size_t i = 0; i < nelem; i++) EMISES[i] = orc_get_mises(ESTRESS + 6 * i);
   free(nnumber);
   return 0;
+}
+
+/* ======================================================================================================
+ * hecmw_part1: node-based RCB (hecmw1/tools/partitioner/hecmw_partition.c: quick_sort :1469-1566,
+ * rcb_partition :1570-1660).  CHECKER ONLY: the product's partitioner (frontistr_b200/csrc/partition.hpp) is an
+ * independent RCB with an explicit (coordinate, node id) order; this restatement keeps the reference's own
+ * (unstable) quick sort, whose behaviour on tied coordinates decides which nodes of a tied plane change domain,
+ * so that tests can (a) feed the reference's very node->domain map to the product's local-mesh builder and
+ * DMD writer (compared with the real hecmw_part1's files) and (b) check that both RCBs agree wherever the
+ * coordinates along the cut axis are distinct.  Pinned against the real tool: tests/test_partition.py.
+ * ====================================================================================================== */
+#define ORC_QSORT_LOWER 50 /* hecmw_partition.c:64 */
+#define ORC_SWAPD(a, b) do { double t_ = (a); (a) = (b); (b) = t_; } while (0)
+#define ORC_SWAPI(a, b) do { int t_ = (a); (a) = (b); (b) = t_; } while (0)
+
+static int orc_part_quick_sort(int no, int n, double *arr, int *brr, int *istack) { /* :1469-1566 */
+  double a;
+  int b, i, j, k, l = 0, ir = n - 1, jstack = 0;
+  const int nstack = no;
+  for (;;) {
+    if (ir - l < ORC_QSORT_LOWER) {
+      for (j = l + 1; j <= ir; j++) {
+        a = arr[j];
+        b = brr[j];
+        for (i = j - 1; i >= l; i--) {
+          if (arr[i] <= a) break;
+          arr[i + 1] = arr[i];
+          brr[i + 1] = brr[i];
+        }
+        arr[i + 1] = a;
+        brr[i + 1] = b;
+      }
+      if (!jstack) return 0;
+      ir = istack[jstack];
+      l  = istack[jstack - 1];
+      jstack -= 2;
+    } else {
+      k = (l + ir) >> 1;
+      ORC_SWAPD(arr[k], arr[l + 1]); ORC_SWAPI(brr[k], brr[l + 1]);
+      if (arr[l] > arr[ir]) { ORC_SWAPD(arr[l], arr[ir]); ORC_SWAPI(brr[l], brr[ir]); }
+      if (arr[l + 1] > arr[ir]) { ORC_SWAPD(arr[l + 1], arr[ir]); ORC_SWAPI(brr[l + 1], brr[ir]); }
+      if (arr[l] > arr[l + 1]) { ORC_SWAPD(arr[l], arr[l + 1]); ORC_SWAPI(brr[l], brr[l + 1]); }
+      i = l + 1;
+      j = ir;
+      a = arr[l + 1];
+      b = brr[l + 1];
+      for (;;) {
+        do i++; while (arr[i] < a);
+        do j--; while (arr[j] > a);
+        if (j < i) break;
+        ORC_SWAPD(arr[i], arr[j]); ORC_SWAPI(brr[i], brr[j]);
+      }
+      arr[l + 1] = arr[j];
+      arr[j]     = a;
+      brr[l + 1] = brr[j];
+      brr[j]     = b;
+      jstack += 2;
+      if (jstack > nstack) return -1; /* HECMW_PART_E_STACK_OVERFLOW */
+      if (ir - i + 1 >= j - l) {
+        istack[jstack]     = ir;
+        istack[jstack - 1] = i;
+        ir                 = j - 1;
+      } else {
+        istack[jstack]     = j - 1;
+        istack[jstack - 1] = l;
+        l                  = i;
+      }
+    }
+  }
+}
+
+/* rcb_partition :1570-1660; axes[i] in {0,1,2}; domain[k] in 0..2^n_div-1 */
+int orc_part_rcb(int n, const double *coord, int n_div, const int *axes, int *domain) {
+  double *value = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+  int *id = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+  int *stack = (int *)malloc(sizeof(int) * ((size_t)n + 2));
+  int rc = 0;
+  for (int k = 0; k < n; k++) domain[k] = 0;
+  for (int i = 0; i < n_div && !rc; i++) {
+    const int nd = 1 << i;
+    for (int j = 0; j < nd && !rc; j++) {
+      int counter = 0;
+      for (int k = 0; k < n; k++)
+        if (domain[k] == j) { id[counter] = k; value[counter] = coord[3 * (size_t)k + axes[i]]; counter++; }
+      if (counter == 0) continue;
+      rc = orc_part_quick_sort(n, counter, value, id, stack);
+      for (int k = 0; k < counter * 0.5; k++) domain[id[k]] = j + nd; /* 'k < counter * F_1_2' :1640 */
+    }
+  }
+  free(value); free(id); free(stack);
+  return rc;
 }

@@ -160,6 +160,10 @@ int orc_nodal_stress_3d(const orc_mesh *mesh, const double *gp_strain, const dou
                         double *STRESS, double *MISES, double *ESTRAIN, double *ESTRESS, double *EMISES);
 
 
+/* hecmw_part1's node-based RCB with the reference's own quick sort (hecmw_partition.c:1469-1660): checker for the
+ * product's independent RCB and source of the reference's node->domain map in tests/test_partition.py */
+int orc_part_rcb(int n_node, const double *node, int n_div, const int *axes, int *domain);
+
 #ifdef __cplusplus
 }
 #endif

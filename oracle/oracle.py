@@ -353,3 +353,15 @@ def element_update_linear(kind, ecoord, u, E, nu, etype=361, TT=None, T0=None, a
         L.orc_UPDATE_C3_lin(etype, nn, _dp(ec), _dp(uu), E, nu, int(kind == "BBAR"), _dp(tt), _dp(t0), alpha, reftemp,
                             _dp(q), _dp(e), _dp(s))
     return e, s, q
+
+
+def part_rcb(mesh, axes: str):
+    """Node -> domain map of the reference's RCB (hecmw_partition.c:1570-1660) incl. the tie behaviour of its quick sort."""
+    ax = _i32([{"x": 0, "y": 1, "z": 2}[a] for a in axes.lower().replace(",", "")])
+    dom = np.zeros(mesh.n_node, np.int32)
+    node = np.ascontiguousarray(mesh.node, np.float64)
+    L = lib()
+    L.orc_part_rcb.argtypes = [C.c_int, c_dbl_p, C.c_int, c_int_p, c_int_p]
+    rc = L.orc_part_rcb(mesh.n_node, _dp(node), len(ax), _ip(ax), _ip(dom))
+    assert rc == 0, rc
+    return dom

@@ -21,7 +21,7 @@
 #include <type_traits>
 
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorNotSupported = 801 };
+enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2, cudaErrorNotSupported = 801 };
 typedef struct CUstream_st_emul *cudaStream_t;
 struct cudaEventEmul { double t; };
 typedef cudaEventEmul *cudaEvent_t;

@@ -55,7 +55,8 @@ class EmulBackend:
         return self.opts.get(key, -1)
 
     def _icinv(self):
-        return self.opts.get("ic_inverse", -1) if self.opts.get("ic_inverse", -1) in (0, 1, 2) else 1
+        v = self.opts.get("ic_inverse", -1)
+        return v if v in (0, 1, 2) else (1 if v == -2 else 0)      # -2 = "pick": stands for kernel 1 here; default = kernel 0
 
     # ---- marshalling
     def _mesh_args(self, m):

@@ -134,11 +134,7 @@ def load_dist_fixture(name, rank):
     return m
 
 
-def cube_cnt(tol=1.0e-8, precond=3, maxit=10000, iterpremax=1):
-    """SURVEY §8d load case: face x=0 fixed in 1-3, CLOAD -1 in dof 3 on every node of face x=L."""
-    return dict(boundary=[("FIX", 1, 3, 0.0)], cload=[("CL1", 3, -1.0)],
-                solver=({"METHOD": "CG", "PRECOND": str(precond), "ITERLOG": "NO", "TIMELOG": "NO"},
-                        [[str(maxit), str(iterpremax)], [repr(tol), "1.0", "0.0"]]))
+from frontistr_b200.workloads import cube_cnt  # noqa: E402,F401  (the headline load case lives in the package)
 
 
 def oracle_problem(mesh, cnt, apply_bc=True):

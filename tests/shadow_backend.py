@@ -23,7 +23,8 @@ class ShadowBackend:
 
     def get_option(self, key):
         if key == "ic_inverse_active":      # the library reports which calInverse kernel it used
-            return self.opts.get("ic_inverse", -1) if self.opts.get("ic_inverse", -1) in (0, 1, 2) else 1
+            v = self.opts.get("ic_inverse", -1)
+            return v if v in (0, 1, 2) else (1 if v == -2 else 0)      # -2 = "pick": stands for kernel 1 here; default = kernel 0
         if key in ("ic_selftest_ppb", "ic_time_us_smem"):   # the library's kernel selection has no counterpart here
             return 0
         return self.opts.get(key, -1)

@@ -37,9 +37,10 @@ def _torchrun(nproc, script, *args, env=None, timeout=600):
 
 
 def test_peer_memory_transport_8_ranks_through_the_api():
-    """hex cube on the 2x2x2 RCB partition (7 neighbours per rank), peer-memory mode forced (p2p=2: fail loudly if the
-    arenas cannot be mapped); 139 iterations, i.e. two true-residual iterations on the collective transport inside."""
-    lines = _torchrun(8, "dist_check.py", "--host", "--hex", "8", "--comm", "p2p")
+    """hex cube 9^3 (10 node planes per axis: the RCB cuts fall between planes) on the 2x2x2 partition, 7 neighbours per
+    rank, peer-memory mode forced (p2p=2: fail loudly if the arenas cannot be mapped); > 100 iterations, i.e. at least two
+    true-residual iterations on the collective transport inside."""
+    lines = _torchrun(8, "dist_check.py", "--host", "--hex", "9", "--comm", "p2p")
     assert "p2p_active=1" in lines[-1] and "neighbors=7" in lines[-1]
 
 

@@ -337,6 +337,40 @@ def test_bilu0_zero_pivot_and_recycle(gpu):
     assert gpu.hecmw_solve(mesh, A)["error"] == 0
 
 
+@pytest.mark.parametrize("case", ["negative_definite", "indefinite"])
+def test_bilu0_auto_sigma_diag_loop(gpu, case):
+    """SIGMA_DIAG < 0 = "auto" (Iterative.f90:72-77,113-156): after a divergence (3002 / 3003) with an ILU-family
+    preconditioner the reference adds 0.1 and calls CG again while SIGMA_DIAG < 2 - ten more calls, each starting from
+    the X the previous one left and (as the reference behaves, BILU_33.f90:49-57) with the factorisation of the first.
+    Same final code, iteration count and X as the oracle's restatement of that loop; an explicit SIGMA_DIAG does not retry."""
+    from oracle import oracle as orc
+    from frontistr_b200 import meshgen
+    mesh = util.distort(meshgen.hex_cube(5))
+    cnt = util.cube_cnt(tol=1e-10, precond=10)
+    A = util.product_problem(gpu, mesh, cnt, to_host=True)
+    if case == "negative_definite":
+        A.D *= -1; A.AL *= -1; A.AU *= -1
+    else:
+        for i in range(0, A.N, 3):            # every third diagonal block flipped: some passes make progress before p.Ap <= 0
+            A.D[9 * i: 9 * i + 9] *= -5.0
+    Ao = A.copy()
+    A.Rarray[1] = -1.0; Ao.Rarray[1] = -1.0
+    A.Iarray[96] = 1; Ao.Iarray[96] = 1
+    r = gpu.hecmw_solve(mesh, A)
+    orc.precond_clear()
+    ro = orc.solve(mesh, Ao)
+    orc.precond_clear()
+    assert r["error"] == ro["error"] and r["error"] in (3002, 3003)
+    assert gpu.get_option("auto_sigma_retries") == 10
+    assert r["iter"] == ro["iter"] and A.Iarray[81] == 1 and Ao.Iarray[81] == 1
+    assert A.Rarray[1] == -1.0
+    scale = max(np.abs(Ao.X).max(), 1e-300)
+    assert np.abs(A.X - Ao.X).max() <= 1e-9 * scale
+    B = A.copy(); B.Rarray[1] = 1.0; B.X[:] = 0.0; B.Iarray[96] = 1
+    assert gpu.hecmw_solve(mesh, B)["error"] in (3002, 3003)
+    assert gpu.get_option("auto_sigma_retries") == 0
+
+
 # (5) hecmw_mat_con on the device (SURVEY 8(f) rank 4): pair keys + radix sort + scans (csrc/matcon_dev.cuh), selected with
 # option matcon_device=1, against the oracle's restatement of the reference's table-building algorithm.
 
@@ -409,9 +443,9 @@ def test_mat_con_on_the_device_error_contract(gpu):
 
 def test_ic_inverse_selftest_picks_a_kernel_that_matches_the_oracle(gpu):
     """The IC kernel exists with three ways of condensing the enhanced modes (calInverse through shared memory = the
-    reference's order and the kernel that ran on hardware, the same in registers + shuffles, LDL^T solves); unless the
-    option "ic_inverse" forces one, the library compares and times them on the device once per process - at the first IC
-    block of at least "ic_pick_min_elems" elements (lowered here) - and reports its choice; until then it uses the first.
+    reference's order and the kernel that ran on hardware, the same in registers + shuffles, LDL^T solves); the default
+    is the first, always; with "ic_inverse" = -2 the library compares and times them on the device once per process - at the
+    first IC block of at least "ic_pick_min_elems" elements (lowered here) - and reports its choice.
     Whatever it chose must match the oracle (1e-12, as test_assembly_matches_oracle), and so must the shared-memory
     kernel when forced."""
     from frontistr_b200 import meshgen
@@ -421,11 +455,11 @@ def test_ic_inverse_selftest_picks_a_kernel_that_matches_the_oracle(gpu):
     ref = np.concatenate([Ao.D, Ao.AL, Ao.AU])
     gpu.set_option("ic_pick_min_elems", 64)     # the selection normally waits for an IC block of 2^16 elements
     try:
-        for mode in (-1, 0):
+        for mode in (-2, 0, -1):
             gpu.set_option("ic_inverse", mode)
             A = util.product_problem(gpu, mesh, cnt, to_host=True, apply_bc=False)
             active = gpu.get_option("ic_inverse_active")
-            assert active in (0, 1, 2) and (mode < 0 or active == mode)
+            assert active in (0, 1, 2) and (mode == -2 or active == 0)
             K = np.concatenate([A.D, A.AL, A.AU])
             assert np.abs(K - ref).max() <= 1e-12 * np.abs(ref).max(), (mode, active)
         assert gpu.get_option("ic_selftest_ppb") >= 0 and gpu.get_option("ic_time_us_smem") >= 0    # the selection did run

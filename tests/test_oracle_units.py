@@ -91,7 +91,7 @@ def test_product_ssor_ordering_equals_oracle():
 def test_element_emulation_equals_oracle():
     """The per-lane phase functions the CUDA element kernel is made of, run on the host."""
     from oracle import oracle as orc
-    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "frontistr_b200", "libfistr_b200_emul.so")
+    so = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul", "libfistr_b200_emul.so")
     if not os.path.exists(so):
         import __graft_entry__ as g
         g.build_emul()

@@ -1,7 +1,12 @@
-"""The in-process partitioner (frontistr_b200/partition.py + fistr_b200_part_rcb) against the REAL
-hecmw_part1 of the reference (fixtures made by tests/golden/make_partition_golden.py with
-oracle/_ref/hecmw_part1): node->domain map incl. the tie behaviour of its quick sort, local numbering,
-element selection and every communication table must be identical."""
+"""The in-process partitioner (frontistr_b200/partition.py, csrc/partition.hpp) against the REAL hecmw_part1 of the
+reference (fixtures made by tests/golden/make_partition_golden.py with oracle/_ref/hecmw_part1).
+
+* Local-mesh builder and DMD writer: fed the reference's own node->domain map (oracle.part_rcb = the restatement of
+  its RCB incl. the tie behaviour of its quick sort, itself pinned here against the real tool's output), local
+  numbering, element selection, every communication table and the written files must be identical.
+* The product's RCB (fistr_b200_part_rcb) is an independent implementation of the same bisection contract with ties
+  broken by node index: identical to the reference's map wherever the coordinates along the cut axis are distinct,
+  and a valid balanced bisection (checked as such) where they are tied."""
 import os
 
 import numpy as np
@@ -20,7 +25,9 @@ KEYS = ("global_node_ID", "node_ID", "elem_type_index", "elem_type_item", "elem_
 @pytest.mark.parametrize("name", list(CASES))
 def test_partition_equals_hecmw_part1(name):
     d = np.load(os.path.join(util.GOLDEN, "part_%s.npz" % name))
-    parts = partition.partition(CASES[name](), str(d["axes"]))
+    from oracle import oracle as orc
+    mesh = CASES[name]()
+    parts = partition.partition(mesh, str(d["axes"]), domain=orc.part_rcb(mesh, str(d["axes"])))
     assert len(parts) == int(d["ndomain"])
     for r, p in enumerate(parts):
         assert p.n_node == int(d["r%d_n_node" % r]) and p.nn_internal == int(d["r%d_nn_internal" % r])
@@ -59,7 +66,8 @@ def test_dist_writer_equals_hecmw_part1(name, tmp_path):
     msh = str(tmp_path / "cube.msh")
     meshgen.write_msh(CASES[name](), msh)
     mesh = mshio.read_msh(msh)          # coordinates exactly as the text file carries them
-    dom = partition.rcb_domains(mesh, axes)
+    from oracle import oracle as orc
+    dom = orc.part_rcb(mesh, axes)      # the reference's own node->domain map (ties as its quick sort leaves them)
     for r in range(nd):
         path = str(tmp_path / ("cube_p.%d" % r))
         mshio.write_dist_mesh(path, partition.local_mesh(mesh, dom, r, nd), mesh, dom)
@@ -67,6 +75,65 @@ def test_dist_writer_equals_hecmw_part1(name, tmp_path):
             assert hashlib.sha256(f.read()).hexdigest() == str(d["r%d_sha256" % r]), (name, r)
         back = mshio.read_dist_mesh(path)           # and it reads back
         assert back.n_node == int(d["r%d_n_node" % r]) and np.array_equal(back.export_item, d["r%d_export_item" % r])
+
+
+def _check_bisections(mesh, axes, dom):
+    """Every level: each parent domain is split into ceil/floor halves, the new domain holds the smaller coordinates,
+    and inside a tied coordinate plane the nodes that moved are the ones with the smallest node indices."""
+    xyz = mesh.node.reshape(-1, 3)
+    ax = ["xyz".index(a) for a in axes]
+    for lev in range(len(ax)):
+        low = dom & ((1 << (lev + 1)) - 1)          # domain after level `lev`
+        for j in range(1 << lev):
+            moved = np.nonzero(low == j + (1 << lev))[0]
+            stayed = np.nonzero(low == j)[0]
+            cnt = len(moved) + len(stayed)
+            assert len(moved) == (cnt + 1) // 2
+            if len(moved) == 0 or len(stayed) == 0:
+                continue
+            cm, cs = xyz[moved, ax[lev]], xyz[stayed, ax[lev]]
+            assert cm.max() <= cs.min()
+            tie = cm.max()
+            if tie == cs.min():
+                assert moved[cm == tie].max() < stayed[cs == tie].min()
+
+
+@pytest.mark.parametrize("case", ["hex9_xyz", "hex8_zyx", "tet3_xy", "hexrag_zx", "hex1_xyz", "hex2_x"])
+def test_product_rcb_is_a_balanced_coordinate_bisection(case):
+    mesh, axes = {"hex9_xyz": (meshgen.hex_cube(9), "xyz"), "hex8_zyx": (meshgen.hex_cube(8), "zyx"),
+                  "tet3_xy": (meshgen.tet10_cube(3), "xy"), "hexrag_zx": (meshgen.hex_cube(3, nx=7, ny=2, nz=5), "zx"),
+                  "hex1_xyz": (meshgen.hex_cube(1), "xyz"), "hex2_x": (meshgen.hex_cube(2), "x")}[case]
+    dom = partition.rcb_domains(mesh, axes)
+    assert dom.min() >= 0 and dom.max() < (1 << len(axes))
+    _check_bisections(mesh, axes, dom)
+    assert np.array_equal(dom, partition.rcb_domains(mesh, axes))      # deterministic
+    # an even number of coordinate planes along every cut axis: the cut falls between planes, no tie is split, and the
+    # map equals the reference's
+    if case == "hex9_xyz":
+        from oracle import oracle as orc
+        assert np.array_equal(dom, orc.part_rcb(mesh, axes))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_product_rcb_equals_reference_rcb_on_distinct_coordinates(seed):
+    """No two nodes share a coordinate => the sorted order is unique => both RCBs must give the same map."""
+    from oracle import oracle as orc
+    rng = np.random.default_rng(50 + seed)
+    mesh = meshgen.hex_cube(3, nx=int(rng.integers(2, 9)), ny=int(rng.integers(2, 7)), nz=int(rng.integers(2, 7))) if seed % 2 == 0 \
+        else meshgen.tet10_cube(int(rng.integers(2, 4)))
+    mesh.node = mesh.node + 1e-3 * rng.standard_normal(mesh.node.shape)
+    axes = "".join(rng.choice(list("xyz"), size=int(rng.integers(1, 4))))
+    dom = partition.rcb_domains(mesh, axes)
+    assert np.array_equal(dom, orc.part_rcb(mesh, axes))
+    _check_bisections(mesh, axes, dom)
+
+
+def test_product_rcb_rejects_bad_input():
+    from frontistr_b200._lib import FistrB200Error
+    mesh = meshgen.hex_cube(2)
+    mesh.node = mesh.node.copy(); mesh.node[4] = np.nan
+    with pytest.raises(FistrB200Error):
+        partition.rcb_domains(mesh, "x")
 
 
 def test_partition_tables_are_consistent():
@@ -154,7 +221,8 @@ def test_partition_fuzz_against_the_real_hecmw_part1(seed, tmp_path):
     open(os.path.join(tmp, "hecmw_part_ctrl.dat"), "w").write("!PARTITION,TYPE=NODE-BASED,METHOD=RCB,DOMAIN=%d\n %s\n" % (nd, ",".join(axes)))
     subprocess.check_call([part1], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     mesh = mshio.read_msh(os.path.join(tmp, "cube.msh"))        # what the tool saw: coordinates as printed in the file
-    dom = partition.rcb_domains(mesh, axes)
+    from oracle import oracle as orc
+    dom = orc.part_rcb(mesh, axes)
     parts = [partition.local_mesh(mesh, dom, r, nd) for r in range(nd)]
     for r, p in enumerate(parts):
         ref = mshio.read_dist_mesh(os.path.join(tmp, "cube_p.%d" % r))

@@ -1,0 +1,110 @@
+"""Parity on the BENCHED meshes: the GPU solve of the H150 / H200 hex cube (or a tet10 cube) against the
+oracle's solve of the very same system, with north_star's three gates
+
+    iterations  : |iter_gpu - iter_oracle| <= 2
+    displacement: ||u_gpu - u_oracle|| / ||u_oracle|| <= 1e-9      (relative L2 over the 3 N owned DOFs)
+    residual    : true relative residual of the GPU solution < RESID    (hecmw_rel_resid_L2, las_33.f90:387-415)
+
+(hecmw_solver_CG.f90:232-266 and SURVEY App. B decide the first two).  The matrix the oracle solves is the one the
+GPU ASSEMBLED (downloaded after fstr_StiffMatrix + hecmw_mat_ass_bc), so the solve is compared in isolation; K itself is
+compared with the oracle's own assembly on request (--check-k, 0.84 M elements/s on 16 host cores).
+
+    python tools/parity_big.py --n 150                 # ~4 min of oracle CG on 16 host cores at RESID 1e-10
+    python tools/parity_big.py --n 200 --tol 1e-10     # H200: ~12 min
+    python tools/parity_big.py --tet 40
+
+One JSON line on stdout (archive under profiles/), progress on stderr.  Exit code 0 = all gates met, 1 = a gate failed.
+Only kernels of the default (hardware-validated) paths run.  Default RESID 1e-10: two CG runs that both stop at 1e-8 agree
+only to ~1e-8 * cond-dependent factor, the 1e-9 gate needs the tighter stop (the GPU tests do the same)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from frontistr_b200 import hecmw, meshgen  # noqa: E402
+from frontistr_b200.mshio import apply_solver_card  # noqa: E402
+from frontistr_b200.workloads import cube_cnt  # noqa: E402
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=150)
+    ap.add_argument("--tet", type=int, default=0)
+    ap.add_argument("--tol", type=float, default=1e-10)
+    ap.add_argument("--precond", type=int, default=3)
+    ap.add_argument("--maxit", type=int, default=50000)
+    ap.add_argument("--check-k", action="store_true", help="also assemble K with the oracle and compare (slow at H200)")
+    args = ap.parse_args()
+    from oracle import oracle as orc        # checker only (tools/ are test infrastructure, like tests/)
+    hecmw.init(0)
+    t0 = time.time()
+    mesh = meshgen.tet10_cube(args.tet) if args.tet else meshgen.hex_cube(args.n)
+    name = ("T%d" % args.tet) if args.tet else ("H%d" % args.n)
+    cnt = cube_cnt(tol=args.tol, precond=args.precond, maxit=args.maxit)
+    A = hecmw.hecmw_mat_con(mesh)
+    A.fstr_mat_init().hecMAT_init()
+    hecmw.mat_structure(mesh, A)
+    hecmw.fstr_StiffMatrix(mesh, A, to_host=False)
+    kerr = None
+    if args.check_k:
+        hecmw.mat_download(A, values=True, rhs=False)
+        Ko = orc.mat_con(mesh)
+        orc.stiffmatrix(mesh, Ko)
+        num = sum(float(np.sum((a - b) ** 2)) for a, b in ((A.D, Ko.D), (A.AL, Ko.AL), (A.AU, Ko.AU)))
+        den = sum(float(np.sum(b ** 2)) for b in (Ko.D, Ko.AL, Ko.AU))
+        kerr = (num / den) ** 0.5
+        log("%s: |K_gpu - K_oracle| / |K_oracle| = %.3e" % (name, kerr))
+        del Ko
+    A.B[:] = 0.0
+    hecmw.fstr_ass_load_cload(mesh, A, cnt["cload"])
+    hecmw.mat_upload(A, values=False, rhs=True)
+    bn, bd, bv = hecmw.boundary_dofs(mesh, cnt["boundary"])
+    hecmw.hecmw_mat_ass_bc(bn, bd, bv)
+    apply_solver_card(A, cnt["solver"]); A.Iarray[20] = 0; A.Iarray[21] = 0
+    log("%s: %d nodes, %d elements, set-up %.1f s" % (name, mesh.n_node, mesh.n_elem, time.time() - t0))
+    # ---- GPU solve (system resident in HBM)
+    A.X[:] = 0.0
+    r = hecmw.hecmw_solve(mesh, A, device_resident=True)
+    log("%s GPU   : error %d, %d iterations, RESID %.3e, true residual %.3e, %.2f s on the device"
+        % (name, r["error"], r["iter"], r["resid"], r["resid2"], float(r["times"][4])))
+    u_gpu = A.X[: 3 * A.N].copy()
+    conv_gpu = int(A.Iarray[80])
+    # ---- oracle solve of the same system (host copy of what the GPU assembled)
+    hecmw.mat_download(A, values=True, rhs=True)
+    apply_solver_card(A, cnt["solver"]); A.Iarray[20] = 0; A.Iarray[21] = 0
+    A.X[:] = 0.0
+    orc.precond_clear()
+    t1 = time.time()
+    ro = orc.solve(mesh, A, hist_len=args.maxit)
+    orc.precond_clear()
+    t_or = time.time() - t1
+    log("%s oracle: error %d, %d iterations, RESID %.3e, true residual %.3e, %.1f s on %d host threads"
+        % (name, ro["error"], ro["iter"], ro["resid"], ro["resid2"], t_or, orc.num_threads()))
+    u_or = A.X[: 3 * A.N]
+    uerr = float(np.linalg.norm(u_gpu - u_or) / np.linalg.norm(u_or))
+    nh = min(len(r["hist"]), len(ro["hist"]))
+    hist_dev = float(np.max(np.abs(np.asarray(r["hist"][:nh]) / np.asarray(ro["hist"][:nh]) - 1.0))) if nh else None
+    gates = {"iterations": abs(int(r["iter"]) - int(ro["iter"])) <= 2, "displacement": uerr <= 1e-9,
+             "residual": float(r["resid2"]) < args.tol and conv_gpu == 1, "codes": r["error"] == 0 and ro["error"] == 0}
+    out = {"workload": name, "dof": 3 * mesh.n_node, "tol": args.tol, "precond": args.precond,
+           "gpu": {"iter": int(r["iter"]), "resid": float(r["resid"]), "resid_true": float(r["resid2"]),
+                   "device_s": float(r["times"][4])},
+           "oracle": {"iter": int(ro["iter"]), "resid": float(ro["resid"]), "resid_true": float(ro["resid2"]),
+                      "wall_s": t_or, "threads": orc.num_threads()},
+           "rel_l2_u": uerr, "rel_l2_K": kerr, "residual_history_max_rel_dev": hist_dev, "gates": gates,
+           "pass": all(gates.values())}
+    print(json.dumps(out), flush=True)
+    return 0 if out["pass"] else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
