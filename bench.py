@@ -4,8 +4,9 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n 150]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1], SURVEY §8d "H150"): synthetic C3D8 hex cube, 150^3 elements
-(10.3 M DOF), E=210000, nu=0.3, face x=0 fixed, CLOAD -1 (dof 3) on face x=1, C3D8 incompatible-mode
+Workload (BASELINE.json configs[2], SURVEY §8d "H200", north_star's ">= 20 M-DOF C3D8 cube"; `--n 150` = configs[1],
+"H150"): synthetic C3D8 hex cube, 200^3 elements (24.4 M DOF, ~75 GB on one GPU) at EVERY N so that N = 1, 2, 4, 8 is strong
+scaling of one mesh, E=210000, nu=0.3, face x=0 fixed, CLOAD -1 (dof 3) on face x=1, C3D8 incompatible-mode
 elements (the reference default for linear static), `!SOLVER, METHOD=CG, PRECOND=3` (3x3 block-Jacobi
 "DIAG"), RESID=1e-8.  One STEP = one complete hecmw_solve of that system (all CG iterations to
 convergence, X0 = 0) — the reference's `solve_LINEQ` call.
@@ -14,7 +15,7 @@ Metric: CG iterations per second (whole job).
   value : matrix and RHS already resident in HBM (assembled there by the library's own
           fstr_StiffMatrix + hecmw_mat_ass_bc kernels); timed region = K solves.
   e2e   : the literal drop-in call: fistr_b200_solve_33 with HOST hecMAT%D/AL/AU/B/X (pinned) — the
-          6.6 GB matrix upload, the private SELL repack, the preconditioner set-up and the download
+          matrix upload (15.6 GB at H200, 6.6 GB at H150), the private SELL repack, the preconditioner set-up and the download
           of X are all inside the timed region, every step.
 For N > 1 the same global mesh is partitioned with the in-process restatement of hecmw_part1's RCB
 (one subdomain per GPU; halo exchange + dot-product all-reduce over NCCL/NVLink): strong scaling.
@@ -48,7 +49,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", "--hex", dest="n", type=int, default=150, help="hex cube edge in elements (150 = configs[1], 200 = configs[2])")
+    ap.add_argument("--n", "--hex", dest="n", type=int, default=None,
+                    help="hex cube edge in elements: 200 = configs[2] / north_star's >= 20 M-DOF target (default at every N, so that the "
+                         "driver's N = 1, 2, 4, 8 runs are strong scaling of ONE mesh; it fits one GPU at ~75 GB), 150 = configs[1]")
     ap.add_argument("--tol", type=float, default=1.0e-8)
     ap.add_argument("--precond", type=int, default=3)
     ap.add_argument("--maxit", type=int, default=20000)
@@ -56,6 +59,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ic-probe", action="store_true", help="opt-in: after the line, run the IC kernel selection (self-test + timing; N = 1)")
+    ap.add_argument("--partition", default="rcb", choices=["rcb", "kmetis", "pmetis"],
+                    help="N>1: METHOD of hecmw_part1's node-based decomposition.  rcb = x / xy / xyz bisection (the ideal 2x2x2 split "
+                         "of a cube; needs N = 2, 4, 8); kmetis / pmetis = the reference's node graph through METIS 5 (any N)")
     ap.add_argument("--comm", default="auto", choices=["auto", "p2p", "nccl"],
                     help="N>1 transport of the halo exchange + dot-product all-reduce: peer-memory stores issued by the CG "
                          "kernels (p2p) or NCCL.  auto = what has RUN ON HARDWARE at that N: p2p at N=2, NCCL at N>2 (p2p at "
@@ -153,11 +159,16 @@ def build_problem_host(args, rank, world):
     mesh = meshgen.hex_cube(args.n)
     if world > 1:
         from frontistr_b200 import partition
-        axes = {2: "x", 4: "xy", 8: "xyz"}[world]
-        dom = partition.rcb_domains(mesh, axes)
+        if getattr(args, "partition", "rcb") == "rcb":
+            dom = partition.rcb_domains(mesh, {2: "x", 4: "xy", 8: "xyz"}[world])
+        else:
+            dom, _ = partition.metis_domains(mesh, world, args.partition)
         mesh = partition.local_mesh(mesh, dom, rank, world)
     cnt = cube_cnt(tol=args.tol, precond=args.precond, maxit=args.maxit)
     return mesh, cnt
+
+
+DEFAULT_N, FALLBACK_N = 200, 150
 
 
 def run_reference(args):
@@ -166,6 +177,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.n is None:
+        args.n = DEFAULT_N
     from frontistr_b200 import hecmw as host_helpers   # load/BC bookkeeping helpers only (numpy)
     from frontistr_b200.mshio import apply_solver_card
     from oracle import oracle as orc
@@ -228,8 +241,8 @@ def run_b200(args):
             raise SystemExit("bench.py --gpus %d must be launched with torch.distributed.run --nproc-per-node %d"
                              % (args.gpus, args.gpus))
         args.gpus = world
-    if world not in (1, 2, 4, 8):
-        raise SystemExit("RCB partitioning needs a power-of-two rank count (hecmw_part_get_control.c:271-340)")
+    if world not in (1, 2, 4, 8) and getattr(args, "partition", "rcb") == "rcb":
+        raise SystemExit("RCB partitioning needs a power-of-two rank count (hecmw_part_get_control.c:271-340); use --partition kmetis")
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -269,26 +282,45 @@ def run_b200(args):
         return float(t.item())
 
     # ---- problem set-up: mat_con (host), fstr_StiffMatrix + hecmw_mat_ass_bc (device) -------------
-    t0 = time.time()
-    mesh, cnt = build_problem_host(args, rank, world)
-    t_mesh = time.time() - t0
-    t0 = time.time()
-    A = hecmw.hecmw_mat_con(mesh)
-    t_con = time.time() - t0
-    A.fstr_mat_init().hecMAT_init()
-    bn, bd, bv = hecmw.boundary_dofs(mesh, cnt["boundary"])
+    from frontistr_b200._lib import FistrB200Error
+    explicit_n = args.n is not None
+    if not explicit_n:
+        args.n = DEFAULT_N
+    workload_note = None
+    while True:
+        try:
+            t0 = time.time()
+            mesh, cnt = build_problem_host(args, rank, world)
+            t_mesh = time.time() - t0
+            t0 = time.time()
+            A = hecmw.hecmw_mat_con(mesh)
+            t_con = time.time() - t0
+            A.fstr_mat_init().hecMAT_init()
+            bn, bd, bv = hecmw.boundary_dofs(mesh, cnt["boundary"])
 
-    def setup_system(reps):
-        """structure -> device, assembly (reps times), load vector, Dirichlet elimination: the system the solves work on"""
-        hecmw.mat_structure(mesh, A)
-        t = [hecmw.fstr_StiffMatrix(mesh, A, to_host=False) for _ in range(reps)]
-        A.B[:] = 0.0
-        hecmw.fstr_ass_load_cload(mesh, A, cnt["cload"])
-        hecmw.mat_upload(A, values=False, rhs=True)
-        hecmw.hecmw_mat_ass_bc(bn, bd, bv)
-        return t
+            def setup_system(reps):
+                """structure -> device, assembly (reps times), load vector, Dirichlet elimination: the system the solves work on"""
+                hecmw.mat_structure(mesh, A)
+                t = [hecmw.fstr_StiffMatrix(mesh, A, to_host=False) for _ in range(reps)]
+                A.B[:] = 0.0
+                hecmw.fstr_ass_load_cload(mesh, A, cnt["cload"])
+                hecmw.mat_upload(A, values=False, rhs=True)
+                hecmw.hecmw_mat_ass_bc(bn, bd, bv)
+                return t
 
-    asm = setup_system(3)   # 2 warm-ups + 1 reported
+            asm = setup_system(3)   # 2 warm-ups + 1 reported
+            break
+        except (FistrB200Error, MemoryError) as exc:
+            # the default mesh (H200, ~75 GB on one GPU) did not fit this device / host: say so and measure configs[1]
+            if explicit_n or world > 1 or args.n == FALLBACK_N:
+                raise
+            workload_note = "default H%d could not be set up on this box (%s): fell back to H%d" % (args.n, str(exc)[:120], FALLBACK_N)
+            print("bench.py: " + workload_note, file=sys.stderr, flush=True)
+            mesh = A = None
+            hecmw.finalize()
+            hecmw.init(local_rank)
+            hecmw.set_option("ic_inverse", 0)
+            args.n = FALLBACK_N
     asm_kernel_ms = allmax(asm[-1]["kernel_ms"])
     asm_total_ms = allmax(asm[-1]["total_ms"])
     n_elem_global = args.n ** 3
@@ -394,10 +426,12 @@ def run_b200(args):
                "warmup": args.warmup, "ms_per_step": 1e3 * res["ev_s"] / args.steps, "higher_is_better": True,
                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": {"workload": workload_name(args.n, args.precond), "tol": args.tol, "precond": args.precond,
-                          "partition": "none" if world == 1 else "RCB-%s (in-process hecmw_part1 restatement), 1 subdomain/GPU"
-                          % {2: "x", 4: "xy", 8: "xyz"}[world],
+                          "partition": "none" if world == 1 else (
+                              ("RCB-%s" % {2: "x", 4: "xy", 8: "xyz"}[world]) if getattr(args, "partition", "rcb") == "rcb"
+                              else args.partition.upper() + " (METIS 5)") + ", node-based, in-process hecmw_part1, 1 subdomain/GPU",
                           "comm": "none" if world == 1 else ("p2p" if hecmw.get_option("p2p_active") == 1 else "nccl"),
                           **({"comm_note": comm_note} if comm_note else {}),
+                          **({"workload_note": workload_note} if workload_note else {}),
                           "l2": "inputs larger than L2: %.2f GB matrix streamed per SpMV per GPU vs 126 MB L2"
                           % (spmv_bytes_global / world / 1e9)},
                "iterations_per_step": res["iters"] // args.steps, "resid": float(last["resid"]),

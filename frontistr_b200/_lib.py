@@ -73,5 +73,5 @@ EXPORTED = [
     "fistr_b200_matvec_bench", "fistr_b200_precond_33_setup", "fistr_b200_precond_33_apply",
     "fistr_b200_precond_33_clear", "fistr_b200_precond_33_info", "fistr_b200_update_3_R",
     "fistr_b200_launch_count", "fistr_b200_device_info", "fistr_b200_fp64_peak",
-    "fistr_b200_hbm_copy_peak", "fistr_b200_part_rcb", "fistr_b200_part_local_count", "fistr_b200_part_local_fill", "fistr_b200_debug_ssor_order", "fistr_b200_debug_sell_layout",
+    "fistr_b200_hbm_copy_peak", "fistr_b200_part_rcb", "fistr_b200_part_metis", "fistr_b200_part_metis_available", "fistr_b200_part_local_count", "fistr_b200_part_local_fill", "fistr_b200_debug_ssor_order", "fistr_b200_debug_sell_layout",
 ]

@@ -15,6 +15,7 @@
 #include "matcon_dev.cuh"
 #include "p2p.cuh"
 #include "partition.hpp"
+#include "partition_metis.hpp"
 #include "spmv.cuh"
 #include "ssor.cuh"
 

@@ -32,6 +32,55 @@ def rcb_domains(mesh: hecmwST_local_mesh, axes: str) -> np.ndarray:
     return dom
 
 
+def metis_available() -> bool:
+    return bool(_lib.lib().fistr_b200_part_metis_available())
+
+
+def metis_domains(mesh: hecmwST_local_mesh, n_domain: int, method: str = "KMETIS"):
+    """`!PARTITION,TYPE=NODE-BASED,METHOD=KMETIS|PMETIS,DOMAIN=n` of hecmw_part_ctrl.dat: the reference's node graph of
+    element edges partitioned by METIS 5 (csrc/partition_metis.hpp).  Returns (domain per node, edge cut)."""
+    import ctypes as C
+    meth = {"PMETIS": 1, "KMETIS": 2}[method.upper()]
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    eti, ett = i32(mesh.elem_type_index), i32(mesh.elem_type_item)
+    eni, enn = i32(mesh.elem_node_index), i32(mesh.elem_node_item)
+    dom = np.zeros(mesh.n_node, np.int32)
+    cut = C.c_longlong(0)
+    check(_lib.lib().fistr_b200_part_metis(meth, int(n_domain), mesh.n_node, mesh.n_elem_type, ip(eti), ip(ett), ip(eni), ip(enn),
+                                           ip(dom), C.byref(cut)))
+    return dom, int(cut.value)
+
+
+def domains_from_control(mesh: hecmwST_local_mesh, ctrl_text: str):
+    """The node->domain map hecmw_part1 would compute for this hecmw_part_ctrl.dat content
+    (`!PARTITION,TYPE=NODE-BASED,METHOD={RCB|KMETIS|PMETIS},DOMAIN=n[,DEPTH=1][,UCD=...]`, RCB followed by a line of axes
+    `x,y,z`; parser hecmw1/tools/partitioner/hecmw_part_get_control.c:76-460).  Returns (domain, n_domain).
+    Node-based, depth 1 only - what the solver path uses."""
+    lines = [ln.strip() for ln in ctrl_text.splitlines() if ln.strip() and not ln.strip().startswith(("#", "!!"))]
+    head = next((ln for ln in lines if ln.upper().startswith("!PARTITION")), None)
+    if head is None:
+        raise ValueError("hecmw_part_ctrl.dat: no !PARTITION line")
+    opts = {}
+    for tok in head.split(",")[1:]:
+        k, _, v = tok.partition("=")
+        opts[k.strip().upper()] = v.strip()
+    if opts.get("TYPE", "NODE-BASED").upper() != "NODE-BASED":
+        raise ValueError("only TYPE=NODE-BASED is on this path (got %s)" % opts["TYPE"])
+    if int(opts.get("DEPTH", "1")) != 1:
+        raise ValueError("only DEPTH=1 is on this path")
+    nd = int(opts["DOMAIN"])
+    method = opts.get("METHOD", "").upper()
+    if method == "RCB":
+        rest = lines[lines.index(head) + 1:]
+        axes = "".join(rest[0].replace(",", " ").split()).lower() if rest else ""
+        if nd != 1 << len(axes):
+            raise ValueError("RCB: DOMAIN=%d needs %d axes (hecmw_part_get_control.c:271-340)" % (nd, max(nd.bit_length() - 1, 0)))
+        return rcb_domains(mesh, axes), nd
+    if method in ("KMETIS", "PMETIS"):
+        return metis_domains(mesh, nd, method)[0], nd
+    raise ValueError("METHOD must be RCB, KMETIS or PMETIS")
+
+
 def local_mesh(mesh: hecmwST_local_mesh, domain: np.ndarray, rank: int, nparts: int) -> hecmwST_local_mesh:
     """The distributed mesh of `rank` (what hecmw_part1 writes to <name>.<rank>), built by the library's native
     host code (csrc/partition.hpp: LocalMesh) from the node->domain map."""
@@ -175,7 +224,9 @@ def _export_lists(mesh, owner, rank, nparts):
     return out
 
 
-def partition(mesh: hecmwST_local_mesh, axes: str, domain=None):
+def partition(mesh: hecmwST_local_mesh, axes: str, domain=None, nparts=None):
+    """All local meshes of an RCB split along `axes`, or of any node->domain map given as `domain` (+ nparts)."""
     dom = rcb_domains(mesh, axes) if domain is None else np.ascontiguousarray(domain, np.int32)
-    nparts = 1 << len(axes.replace(",", ""))
+    if nparts is None:
+        nparts = 1 << len(axes.replace(",", ""))
     return [local_mesh(mesh, dom, r, nparts) for r in range(nparts)]

@@ -199,6 +199,19 @@ int fistr_b200_update_3_R(double *X /* 3*NP in/out */);
  * hecmw_part1's wherever the coordinates along the cut axis are distinct and is a valid balanced bisection otherwise. */
 int fistr_b200_part_rcb(int n_node, const double *node, int n_div, const int *axes, int *domain);
 
+/* METHOD=PMETIS (method 1, METIS_PartGraphRecursive) / KMETIS (method 2, METIS_PartGraphKway) of hecmw_part1, node-based
+ * (hecmw1/tools/partitioner/hecmw_partition.c:2140-2300, 2727-2850; node graph of element edges as built by
+ * hecmw_mesh_edge_info.c + create_node_graph :1715-1830; unit weights, default options).  domain[k] in 0..n_domain-1;
+ * any n_domain >= 1.  Connectivity as everywhere in this header (FrontISTR-internal node order).  METIS 5 is linked from
+ * the CUDA toolkit's libmetis_static.a when the build finds it: fistr_b200_part_metis_available() says whether; without it
+ * the call fails with FISTR_B200_ERR_STATE (the reference's partitioner without -DHECMW_PART_WITH_METIS refuses too,
+ * hecmw_part_get_control.c:449-460).  Identical to the real hecmw_part1 linked to the same METIS (tests/test_partition.py).
+ * host-only */
+int fistr_b200_part_metis(int method, int n_domain, int n_node, int n_elem_type, const int *elem_type_index,
+                          const int *elem_type_item, const int *elem_node_index, const int *elem_node_item, int *domain,
+                          long long *edgecut /* may be NULL */);
+int fistr_b200_part_metis_available(void);
+
 /* ... and the distributed mesh of ONE rank from that node->domain map, exactly as hecmw_part1 writes it
  * (hecmw1/src/common/hecmw_io_dist.c:1991-2284: internal nodes first, then external; elements touching an
  * internal node; neighbour / import / export tables).  _count builds and returns

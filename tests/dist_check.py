@@ -21,6 +21,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--hex", dest="n", type=int, default=24)
+    ap.add_argument("--partition", default="rcb", choices=["rcb", "kmetis", "pmetis"])
     ap.add_argument("--tet", type=int, default=0)
     ap.add_argument("--precond", type=int, default=3)
     ap.add_argument("--tol", type=float, default=1e-10)
@@ -52,8 +53,11 @@ def main():
     hecmw.set_option("p2p", {"p2p": 2, "p2p-or-nccl": 1, "nccl": 0}[args.comm])   # 2 = fail loudly if peer memory cannot be mapped
     hecmw.comm_init_from_torch()
     gmesh = meshgen.tet10_cube(args.tet) if args.tet else util.distort(meshgen.hex_cube(args.n))
-    axes = {2: "x", 4: "xy", 8: "xyz"}[world]
-    dom = partition.rcb_domains(gmesh, axes)
+    if args.partition == "rcb":
+        axes = {2: "x", 4: "xy", 8: "xyz"}[world]
+        dom = partition.rcb_domains(gmesh, axes)
+    else:      # METHOD=KMETIS / PMETIS: every rank computes the same (deterministic) map; any world size
+        dom, _ = partition.metis_domains(gmesh, world, args.partition)
     m = partition.local_mesh(gmesh, dom, rank, world)
     cnt = util.cube_cnt(tol=args.tol, precond=args.precond, iterpremax=args.iterpremax)
     A = util.product_problem(hecmw, m, cnt, to_host=False)

@@ -46,5 +46,42 @@ def main():
         print("wrote part_%s.npz" % name)
 
 
+METIS_CASES = {"hex6_k8": (lambda: meshgen.hex_cube(6), "KMETIS", 8), "hex5_p3": (lambda: meshgen.hex_cube(5), "PMETIS", 3),
+               "tet3_k4": (lambda: meshgen.tet10_cube(3), "KMETIS", 4), "tet2_p2": (lambda: meshgen.tet10_cube(2), "PMETIS", 2),
+               "hexrag_k5": (lambda: meshgen.hex_cube(3, nx=7, ny=4, nz=5), "KMETIS", 5)}
+
+
+def main_metis():
+    """part_metis_<case>.npz: node -> domain map and the per-rank files' sha256 of the REAL hecmw_part1 built with METIS
+    (oracle/_ref/hecmw_part1_metis: the reference's partitioner + the CUDA toolkit's METIS 5 archive through the 32-bit
+    front of oracle/metis_shim)."""
+    out = os.path.dirname(os.path.abspath(__file__))
+    part = os.path.join(ROOT, "oracle", "_ref", "hecmw_part1_metis")
+    for name, (maker, method, nd) in METIS_CASES.items():
+        mesh = maker()
+        with tempfile.TemporaryDirectory() as tmp:
+            meshgen.write_msh(mesh, os.path.join(tmp, "cube.msh"))
+            open(os.path.join(tmp, "hecmw_ctrl.dat"), "w").write(
+                "!MESH, NAME=part_in, TYPE=HECMW-ENTIRE\n cube.msh\n!MESH, NAME=part_out, TYPE=HECMW-DIST\n cube_p\n")
+            open(os.path.join(tmp, "hecmw_part_ctrl.dat"), "w").write("!PARTITION,TYPE=NODE-BASED,METHOD=%s,DOMAIN=%d\n" % (method, nd))
+            subprocess.check_call([part], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            dom = np.full(mesh.n_node, -1, np.int32)
+            data = {"method": method, "ndomain": nd}
+            for r in range(nd):
+                with open(os.path.join(tmp, "cube_p.%d" % r), "rb") as f:
+                    data["r%d_sha256" % r] = hashlib.sha256(f.read()).hexdigest()
+                d = mshio.read_dist_mesh(os.path.join(tmp, "cube_p.%d" % r))
+                dom[d.global_node_ID[: d.nn_internal] - 1] = r
+                for k in KEYS:
+                    data["r%d_%s" % (r, k)] = getattr(d, k)
+            assert dom.min() >= 0
+            data["domain"] = dom
+        np.savez_compressed(os.path.join(out, "part_metis_%s.npz" % name), **data)
+        print("wrote part_metis_%s.npz" % name)
+
+
 if __name__ == "__main__":
-    main()
+    if "--metis" in sys.argv:
+        main_metis()
+    else:
+        main()

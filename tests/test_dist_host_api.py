@@ -82,3 +82,17 @@ def test_bench_flow_multi_rank(world, comm, inject):
     line of rank 0).  inject: every peer-memory wait that has to spin times out at once — all ranks must learn of it at
     the same batch boundary, fall back to the collective transport together and still deliver the line."""
     _torchrun(world, "host_bench_check.py", "--hex", "8", "--comm", comm, env={"FB_EMUL_P2P_TIMEOUT": "1"} if inject else None)
+
+
+def test_kmetis_partition_3_ranks_through_the_api():
+    """METHOD=KMETIS with a rank count RCB cannot serve (3): irregular subdomain shapes, ranks that are not all neighbours of
+    each other, import lists that need not be the contiguous tail - solved through the product's own exchange / all-reduce /
+    CG loop against the oracle's serial solve."""
+    from frontistr_b200 import partition
+    if not partition.metis_available():
+        import pytest
+        pytest.skip("library built without METIS")
+    lines = _torchrun(3, "dist_check.py", "--host", "--hex", "7", "--comm", "nccl", "--partition", "kmetis")
+    assert lines[-1].startswith("PASS") and "world=3" in lines[-1]
+    lines = _torchrun(5, "dist_check.py", "--host", "--tet", "3", "--comm", "p2p", "--partition", "pmetis")
+    assert lines[-1].startswith("PASS") and "p2p_active=1" in lines[-1]

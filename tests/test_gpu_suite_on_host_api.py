@@ -146,3 +146,55 @@ def test_smoke_and_bench_through_the_host_compiled_library(host_api, monkeypatch
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
     assert d["assembly"]["ic_inverse"] == "calInverse through shared memory"       # the line is measured with the validated kernel
     assert d["iterations_per_step"] > 10 and d["resid_true"] < 1.0e-8
+
+
+def test_bench_default_workload_falls_back_when_it_does_not_fit(host_api, monkeypatch, capsys):
+    """bench.py without --n measures the north_star mesh (H200); if that cannot be set up on the box (allocation error from
+    the library) an N = 1 run releases everything, falls back to configs[1] and says so in config.workload_note.  Driven here
+    with tiny stand-in sizes and an injected allocation failure on the first structure upload."""
+    import argparse
+    import json
+
+    import torch
+
+    import bench
+    from frontistr_b200._lib import FistrB200Error
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *_: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *_: None)
+
+    class NoSampler:
+        def __init__(self, *_):
+            pass
+
+        def start(self):
+            return self
+
+        def stop(self):
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["stub"]}
+    monkeypatch.setattr(bench, "ClockSampler", NoSampler)
+    monkeypatch.setattr(host_api, "fp64_peak", lambda: 1.0)
+    monkeypatch.setattr(bench, "DEFAULT_N", 7)
+    monkeypatch.setattr(bench, "FALLBACK_N", 5)
+    real = host_api.mat_structure
+    calls = {"n": 0}
+
+    def flaky(mesh, A):
+        calls["n"] += 1
+        if calls["n"] == 1:
+            raise FistrB200Error(-2, "cudaMalloc(injected): out of memory")
+        return real(mesh, A)
+    monkeypatch.setattr(host_api, "mat_structure", flaky)
+    args = argparse.Namespace(gpus=1, steps=1, warmup=1, impl="b200", n=None, tol=1.0e-8, precond=3, maxit=20000, ref_iters=0,
+                              no_cpu_baseline=True, no_e2e=True, comm="auto")
+    bench.run_b200(args)
+    cap = capsys.readouterr()
+    d = json.loads([ln for ln in cap.out.splitlines() if ln.startswith("{")][-1])
+    assert "fell back to H5" in d["config"]["workload_note"] and d["config"]["workload"].startswith("H5:")
+    assert d["value"] > 0 and d["resid_true"] < 1.0e-8
+    # an explicit --n never falls back
+    calls["n"] = 0
+    args = argparse.Namespace(gpus=1, steps=1, warmup=1, impl="b200", n=7, tol=1.0e-8, precond=3, maxit=20000, ref_iters=0,
+                              no_cpu_baseline=True, no_e2e=True, comm="auto")
+    with pytest.raises(FistrB200Error):
+        bench.run_b200(args)
+    host_api.finalize(); host_api.init(0)

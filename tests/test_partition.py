@@ -339,3 +339,130 @@ def test_msh_reader_bulk_parse_on_the_reference_example_meshes():
         _same_mesh(mshio._read_msh_bulk(f, 3), slow)
         n += 1
     assert n >= 10
+
+
+# ---- METHOD=KMETIS / PMETIS (north_star: "the repo's own METIS partitioner") -------------------------------------------
+METIS_CASES = {"hex6_k8": lambda: meshgen.hex_cube(6), "hex5_p3": lambda: meshgen.hex_cube(5),
+               "tet3_k4": lambda: meshgen.tet10_cube(3), "tet2_p2": lambda: meshgen.tet10_cube(2),
+               "hexrag_k5": lambda: meshgen.hex_cube(3, nx=7, ny=4, nz=5)}
+needs_metis = pytest.mark.skipif(not partition.metis_available(), reason="library built without METIS (no libmetis_static.a in the toolkit)")
+
+
+@needs_metis
+@pytest.mark.parametrize("name", list(METIS_CASES))
+def test_metis_partition_equals_hecmw_part1_with_metis(name, tmp_path):
+    """fistr_b200_part_metis (the reference's node graph of element edges -> METIS 5, csrc/partition_metis.hpp) against
+    fixtures written by the REAL hecmw_part1 built with the same METIS (tests/golden/make_partition_golden.py --metis):
+    identical node->domain map for KMETIS and PMETIS, 2..8 domains incl. non-powers of two, hex and tet10 (whose
+    connectivity hecmw_part1 sees in file order); then identical local meshes / communication tables and byte-identical
+    HECMW-DMD-ASCII files from that map."""
+    import hashlib
+    d = np.load(os.path.join(util.GOLDEN, "part_metis_%s.npz" % name))
+    method, nd = str(d["method"]), int(d["ndomain"])
+    msh = str(tmp_path / "cube.msh")
+    meshgen.write_msh(METIS_CASES[name](), msh)
+    mesh = mshio.read_msh(msh)
+    dom, cut = partition.metis_domains(mesh, nd, method)
+    assert np.array_equal(dom, d["domain"]) and cut > 0
+    for r in range(nd):
+        p = partition.local_mesh(mesh, dom, r, nd)
+        for k in KEYS:
+            assert np.array_equal(np.asarray(getattr(p, k)).reshape(-1), np.asarray(d["r%d_%s" % (r, k)]).reshape(-1)), (r, k)
+        path = str(tmp_path / ("cube_p.%d" % r))
+        mshio.write_dist_mesh(path, p, mesh, dom)
+        with open(path, "rb") as f:
+            assert hashlib.sha256(f.read()).hexdigest() == str(d["r%d_sha256" % r]), (name, r)
+
+
+@needs_metis
+@pytest.mark.parametrize("seed", range(6))
+def test_metis_partition_fuzz_against_the_real_tool(seed, tmp_path):
+    """Random meshes / domain counts through the real hecmw_part1 + METIS (build container only) and through the library."""
+    import subprocess
+    part1 = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "hecmw_part1_metis")
+    if not os.path.exists(part1):
+        pytest.skip("oracle/_ref/hecmw_part1_metis not built (needs /root/reference)")
+    rng = np.random.default_rng(900 + seed)
+    if seed % 3 == 2:
+        mesh = meshgen.tet10_cube(int(rng.integers(2, 5)))
+    else:
+        mesh = util.distort(meshgen.hex_cube(3, nx=int(rng.integers(2, 9)), ny=int(rng.integers(2, 7)), nz=int(rng.integers(2, 7))),
+                            amp=float(rng.uniform(0.0, 0.2)), seed=seed)
+    method = ("KMETIS", "PMETIS")[seed % 2]
+    nd = int(rng.integers(2, 9))
+    tmp = str(tmp_path)
+    meshgen.write_msh(mesh, os.path.join(tmp, "cube.msh"))
+    open(os.path.join(tmp, "hecmw_ctrl.dat"), "w").write(
+        "!MESH, NAME=part_in, TYPE=HECMW-ENTIRE\n cube.msh\n!MESH, NAME=part_out, TYPE=HECMW-DIST\n cube_p\n")
+    open(os.path.join(tmp, "hecmw_part_ctrl.dat"), "w").write("!PARTITION,TYPE=NODE-BASED,METHOD=%s,DOMAIN=%d\n" % (method, nd))
+    subprocess.check_call([part1], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    mesh = mshio.read_msh(os.path.join(tmp, "cube.msh"))
+    dom, _ = partition.metis_domains(mesh, nd, method)
+    for r in range(nd):
+        ref = mshio.read_dist_mesh(os.path.join(tmp, "cube_p.%d" % r))
+        p = partition.local_mesh(mesh, dom, r, nd)
+        assert (p.n_node, p.nn_internal) == (ref.n_node, ref.nn_internal), (method, nd, r)
+        for k in KEYS:
+            assert np.array_equal(np.asarray(getattr(p, k)).reshape(-1), np.asarray(getattr(ref, k)).reshape(-1)), (method, nd, r, k)
+
+
+@needs_metis
+@pytest.mark.parametrize("method,nd", [("KMETIS", 3), ("KMETIS", 8), ("PMETIS", 5)])
+def test_metis_partition_is_valid_and_solves(method, nd):
+    """Every node owned once, parts balanced within METIS' own tolerance, tables consistent, and the oracle's CG on the nd
+    subdomains reproduces the serial solve (the partition does not change the result)."""
+    from oracle import oracle as orc
+    mesh = util.distort(meshgen.hex_cube(7))
+    dom, cut = partition.metis_domains(mesh, nd, method)
+    counts = np.bincount(dom, minlength=nd)
+    assert counts.min() > 0 and counts.max() <= 1.05 * mesh.n_node / nd + 2
+    parts = partition.partition(mesh, "", domain=dom, nparts=nd)
+    owned = np.concatenate([p.global_node_ID[: p.nn_internal] for p in parts])
+    assert np.array_equal(np.sort(owned), np.arange(1, mesh.n_node + 1))
+    for p in parts:
+        for a, q in enumerate(p.neighbor_pe):
+            qm = parts[q]
+            b = int(np.nonzero(qm.neighbor_pe == p.my_rank)[0][0])
+            exp = p.global_node_ID[p.export_item[p.export_index[a]: p.export_index[a + 1]] - 1]
+            imp = qm.global_node_ID[qm.import_item[qm.import_index[b]: qm.import_index[b + 1]] - 1]
+            assert np.array_equal(exp, imp)
+    cnt = util.cube_cnt(tol=1e-10)
+    A = util.oracle_problem(mesh, cnt)
+    orc.precond_clear()
+    r1 = orc.solve(mesh, A)
+    mats = [util.oracle_problem(p, cnt) for p in parts]
+    orc.precond_clear()
+    r = orc.solve(parts, mats)
+    orc.precond_clear()
+    assert r["error"] == 0 and abs(r["iter"] - r1["iter"]) <= 2
+    for p, Ap in zip(parts, mats):
+        assert util.rel_l2(Ap.X.reshape(-1, 3), A.X.reshape(-1, 3)[p.global_node_ID - 1]) < 1e-8
+
+
+def test_metis_error_contract():
+    from frontistr_b200._lib import FistrB200Error
+    mesh = meshgen.hex_cube(2)
+    if partition.metis_available():
+        dom, cut = partition.metis_domains(mesh, 1)
+        assert not dom.any() and cut == 0
+        bad = meshgen.hex_cube(2); bad.elem_type_item = np.array([731], np.int32)
+        with pytest.raises(FistrB200Error):
+            partition.metis_domains(bad, 2)
+        bad = meshgen.hex_cube(2); bad.elem_node_item = bad.elem_node_item.copy(); bad.elem_node_item[3] = 999
+        with pytest.raises(FistrB200Error):
+            partition.metis_domains(bad, 2)
+    with pytest.raises(KeyError):
+        partition.metis_domains(mesh, 2, "RCB")
+
+
+def test_domains_from_control_file_text():
+    mesh = meshgen.hex_cube(6)
+    dom, nd = partition.domains_from_control(mesh, "!PARTITION,TYPE=NODE-BASED,METHOD=RCB,DOMAIN=4\n x,z\n")
+    assert nd == 4 and np.array_equal(dom, partition.rcb_domains(mesh, "xz"))
+    if partition.metis_available():      # tutorial/02_elastic_hinge_parallel/hecmw_part_ctrl.dat
+        dom, nd = partition.domains_from_control(mesh, "!PARTITION,TYPE=NODE-BASED,METHOD=PMETIS,DOMAIN=4,UCD=part.inp\n")
+        assert nd == 4 and np.array_equal(dom, partition.metis_domains(mesh, 4, "PMETIS")[0])
+    for bad in ("!PARTITION,TYPE=ELEMENT-BASED,METHOD=RCB,DOMAIN=2\n x\n", "!PARTITION,TYPE=NODE-BASED,METHOD=RCB,DOMAIN=3\n x\n",
+                "!PARTITION,TYPE=NODE-BASED,METHOD=FOO,DOMAIN=2\n", "nothing here"):
+        with pytest.raises(ValueError):
+            partition.domains_from_control(mesh, bad)
