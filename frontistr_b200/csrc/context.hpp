@@ -14,6 +14,7 @@
 #include "matcon.hpp"
 #include "matcon_dev.cuh"
 #include "p2p.cuh"
+#include "scaling.cuh"
 #include "partition.hpp"
 #include "partition_metis.hpp"
 #include "spmv.cuh"
@@ -52,6 +53,7 @@ struct Context {
 
   // ---- values: [D | AL | AU], RHS, solution, CG work vectors
   DevBuf<double> vals, B, X, R, Z, P, Q, WK;
+  DevBuf<double> scale;    // SCALING=YES: s = 1 / sqrt(|diag|), 3*NP (scaling.cuh)
   bool values_on_device = false;
   double *dD() { return vals.p; }
   double *dAL() { return vals.p + 9 * (size_t)NP; }

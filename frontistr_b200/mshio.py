@@ -308,6 +308,13 @@ def apply_solver_card(hecMAT: hecmwST_matrix, solver) -> None:
         I[20] = yn[opts["ITERLOG"].upper()]
     if "TIMELOG" in opts:
         I[21] = yn[opts["TIMELOG"].upper()]
+    if "SCALING" in opts:                 # svIarray(7), fstr_ctrl_common.f90:123
+        I[6] = yn[opts["SCALING"].upper()]
+    if "USEJAD" in opts:                  # svIarray(33) :126 (refused by the library: it keeps its own SELL copy)
+        I[32] = yn[opts["USEJAD"].upper()]
+    if "METHOD2" in opts:                 # svIarray(8) :129: the Krylov method to switch to after CG diverged
+        m2 = opts["METHOD2"].upper()
+        I[7] = int(m2) if m2.isdigit() else _METHODS[m2]
     if len(lines) > 0:
         v = lines[0]
         if len(v) > 0: I[0] = int(v[0])

@@ -153,9 +153,24 @@ int fistr_b200_mat_ass_bc(int nbc, const int *inode, const int *idof, const doub
 
 /* ---- hecmw_solve (hecmw1/src/solver/hecmw_solver.f90:9-78 -> hecmw_solve_iterative
  * iterative/hecmw_solver_Iterative.f90:13-210 -> hecmw_solve_CG iterative/hecmw_solver_CG.f90:19-312).
- * Reads ITER/METHOD/PRECOND/iterPREmax/ITERLOG/TIMELOG/NCOLOR_IN and flags 96/97/98 from Iarray,
+ * Reads ITER/METHOD/METHOD2/PRECOND/iterPREmax/SCALING/ITERLOG/TIMELOG/USEJAD/NCOLOR_IN and flags 96/97/98 from Iarray,
  * RESID/SIGMA_DIAG from Rarray (slot map hecmw_matrix_misc.f90:89-121); writes X(1:3*NP) including
  * halo, Iarray(81/82/96/97/98).  D/AL/AU/B == NULL means "use the device-resident copy".
+ *   METHOD  : 1 (CG) only; anything else returns 1001 (HECMW_SOLVER_ERROR_INCONS_PC, the reference's code for an
+ *             undefined METHOD, Iterative.f90:136-138).
+ *   PRECOND : 1, 2 SSOR | 3 DIAG | 10 BILU(0); others 1001.
+ *   SIGMA_DIAG < 0 ("auto", Iterative.f90:72-77): starts at 1.0; after a divergence (3002 / 3003) with PRECOND 10..19 the
+ *             reference's loop adds 0.1 and calls CG again while SIGMA_DIAG < 2, each call starting from the X the last
+ *             one left (Iterative.f90:141-156) - reproduced as the reference behaves, incl. the fact that
+ *             hecmw_precond_BILU_33_setup keeps the first factorisation (BILU_33.f90:49-57).  get_option
+ *             "auto_sigma_retries" = calls repeated by the last solve.
+ *   METHOD2 : > 1 asks for a switch to BiCGSTAB / GMRES / GPBiCG after CG diverged (Iterative.f90:150-153): those solvers
+ *             are outside this path, the call then returns 1001.  Not looked at unless CG diverges.
+ *   SCALING : Iarray(7) != 0: hecmw_solver_scaling_fw_33 / _bk_33 (las/hecmw_solver_scaling_33.f90) around the CG loop,
+ *             in place on the device-resident matrix / B / X, scale vector halo-exchanged; host D/AL/AU given by the
+ *             caller are not written back (the reference scales and un-scales hecMAT%D/AL/AU in place, which leaves
+ *             them within an ulp or two of their values).
+ *   USEJAD  : Iarray(33) != 0 returns 1001: the library always multiplies from its own private SELL copy.
  * Collective over all ranks of the communicator.  time_out[5] = set-up, solver, comm, matvec seconds
  * (the TIMELOG summary, Iterative.f90:192-208; matvec = sampled CUDA-event SpMV time x iterations) and
  * [4] = CUDA-event time of the whole call on the library stream, H2D/D2H copies included. */

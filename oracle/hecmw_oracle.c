@@ -1270,6 +1270,50 @@ static void precond_clear_all(void) {
   g_pcs = NULL; g_pcs_n = 0;
 }
 
+/* hecmw_solver_scaling_fw_33 / _bk_33 (las/hecmw_solver_scaling_33.f90:20-124, 126-206) on ndom rank-emulated
+ * subdomains: scale = 1/sqrt(|diag|) on the owned rows, halo-updated, then every entry a(ip,iq) * scale(ip) * scale(iq) */
+static void scaling_matrix(orc_matrix *m, const double *scale, int back) {
+  for (int i = 1; i <= m->NP; i++) {
+    const double *sp = scale + 3 * (size_t)(i - 1);
+    double *d = m->D + 9 * (size_t)(i - 1);
+    for (int e = 0; e < 9; e++) d[e] = back ? d[e] / (sp[e / 3] * sp[e % 3]) : d[e] * sp[e / 3] * sp[e % 3];
+    for (int part = 0; part < 2; part++) {
+      const int *index = part ? m->indexU : m->indexL, *item = part ? m->itemU : m->itemL;
+      double *A = part ? m->AU : m->AL;
+      for (int k = index[i - 1]; k < index[i]; k++) {
+        const double *sq = scale + 3 * (size_t)(item[k] - 1);
+        double *a = A + 9 * (size_t)k;
+        for (int e = 0; e < 9; e++) a[e] = back ? a[e] / (sp[e / 3] * sq[e % 3]) : a[e] * sp[e / 3] * sq[e % 3];
+      }
+    }
+  }
+}
+static double **scaling_fw(int ndom, const orc_mesh *meshes, orc_matrix *mats) {
+  double **scale = malloc(sizeof(double *) * ndom);
+  for (int d = 0; d < ndom; d++) {
+    orc_matrix *m = &mats[d];
+    scale[d] = calloc(3 * (size_t)m->NP + 1, sizeof(double));
+    for (int i = 0; i < m->N; i++)
+      for (int c = 0; c < 3; c++) scale[d][3 * (size_t)i + c] = 1.0 / sqrt(fabs(m->D[9 * (size_t)i + 4 * c]));
+  }
+  if (ndom > 1) orc_update_3_R(ndom, meshes, scale);
+  for (int d = 0; d < ndom; d++) {
+    orc_matrix *m = &mats[d];
+    scaling_matrix(m, scale[d], 0);
+    for (size_t i = 0; i < 3 * (size_t)m->N; i++) m->B[i] = m->B[i] * scale[d][i];
+  }
+  return scale;
+}
+static void scaling_bk(int ndom, orc_matrix *mats, double **scale) {
+  for (int d = 0; d < ndom; d++) {
+    orc_matrix *m = &mats[d];
+    for (size_t i = 0; i < 3 * (size_t)m->N; i++) { m->X[i] = m->X[i] * scale[d][i]; m->B[i] = m->B[i] / scale[d][i]; }
+    scaling_matrix(m, scale[d], 1);
+    free(scale[d]);
+  }
+  free(scale);
+}
+
 static int g_ssor_threads = 0; /* 0: follow OpenMP thread count like the reference */
 void orc_set_ssor_threads(int n) { g_ssor_threads = n; }
 
@@ -1285,7 +1329,9 @@ int orc_solve(int ndom, const orc_mesh *meshes, orc_matrix *mats, int *iter_out,
   double RESID = 0.0;
   int auto_sigma_diag = 0, warn = 0;                   /* Iterative.f90:72-77 */
   if (SIGMA_DIAG < 0.0) { auto_sigma_diag = 1; SIGMA_DIAG = 1.0; }
-  if (IA(m0, 7) != 0 || IA(m0, 33) != 0) return 1001;  /* SCALING / USEJAD: not restated (out of scope) */
+  if (IA(m0, 33) != 0) return 1001;                    /* USEJAD: not restated (out of scope) */
+  const int SCALING = IA(m0, 7) != 0;
+  double **scale = NULL;
   *iter_out = 0; *resid_out = 0.0; if (resid2_out) *resid2_out = 0.0;
 
   /* hecmw_solve_check_zerorhs, Iterative.f90:246-278 */
@@ -1346,6 +1392,7 @@ int orc_solve(int ndom, const orc_mesh *meshes, orc_matrix *mats, int *iter_out,
     memset(R[d], 0, sizeof(double) * np); memset(Z[d], 0, sizeof(double) * np);
     memset(P[d], 0, sizeof(double) * np); memset(WK[d], 0, sizeof(double) * np);
   }
+  if (SCALING) scale = scaling_fw(ndom, meshes, mats); /* hecmw_solver_scaling_fw, CG.f90:99 */
   /* hecmw_precond_setup, honouring the recycle flags (DIAG_33.f90:38-41, SSOR_33.f90:72-80, BILU_33.f90:49-57: a
    * factorisation that is INITIALIZED is kept when both flags are 0 - which is also what a retry of the auto-sigma
    * loop finds, so the bumped SIGMA_DIAG does not reach FORM_ILU0_33) */
@@ -1424,6 +1471,7 @@ int orc_solve(int ndom, const orc_mesh *meshes, orc_matrix *mats, int *iter_out,
     RHO1 = RHO;
   }
   (void)exited; /* on natural loop end Fortran leaves ITER = MAXIT+1, as here */
+  if (SCALING) { scaling_bk(ndom, mats, scale); scale = NULL; } /* hecmw_solver_scaling_bk, :275 */
   if (ndom > 1) orc_update_3_R(ndom, meshes, X);       /* hecmw_update_m_R, :280 */
   Tsol = wtime() - S1_TIME;
   /* ---- back in hecmw_solve_iterative, Iterative.f90:141-156 ---- */

@@ -22,6 +22,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--hex", dest="n", type=int, default=24)
     ap.add_argument("--partition", default="rcb", choices=["rcb", "kmetis", "pmetis"])
+    ap.add_argument("--scaling", action="store_true", help="!SOLVER SCALING=YES (Iarray(7) = 1): the scale vector is halo-exchanged")
     ap.add_argument("--tet", type=int, default=0)
     ap.add_argument("--precond", type=int, default=3)
     ap.add_argument("--tol", type=float, default=1e-10)
@@ -61,6 +62,7 @@ def main():
     m = partition.local_mesh(gmesh, dom, rank, world)
     cnt = util.cube_cnt(tol=args.tol, precond=args.precond, iterpremax=args.iterpremax)
     A = util.product_problem(hecmw, m, cnt, to_host=False)
+    A.Iarray[6] = 1 if args.scaling else 0
     r = hecmw.hecmw_solve(m, A, device_resident=True)
     # halo consistency: X on external nodes must equal the owner's value (hecmw_update_m_R at CG exit)
     xg = torch.zeros(3 * gmesh.n_node, dtype=torch.float64, device=dev)
@@ -84,17 +86,25 @@ def main():
     if rank == 0:
         from oracle import oracle as orc
         Ao = util.oracle_problem(gmesh, cnt)
+        Ao.Iarray[6] = 1 if args.scaling else 0
         orc.precond_clear()
         ro = orc.solve(gmesh, Ao)
         err = util.rel_l2(xgl.reshape(-1), Ao.X)
         it_ok = abs(r["iter"] - ro["iter"]) <= 2
         if args.precond != 3:   # SSOR / BILU are subdomain-local: the count to meet is the oracle's on the SAME decomposition
-            parts = partition.partition(gmesh, axes)
+            parts = partition.partition(gmesh, "", domain=dom, nparts=world)
+            mats = [util.oracle_problem(p_, cnt) for p_ in parts]
+            for a_ in mats:
+                a_.Iarray[6] = 1 if args.scaling else 0
             orc.precond_clear()
-            rp = orc.solve(parts, [util.oracle_problem(p_, cnt) for p_ in parts], ssor_threads=2)
+            rp = orc.solve(parts, mats, ssor_threads=2)
             it_ok = rp["error"] == 0 and abs(r["iter"] - rp["iter"]) <= 2
             print("     oracle on the same %d subdomains: %d iterations" % (world, rp["iter"]), flush=True)
-        ok = (r["error"] == 0 and it_ok and err <= 1e-9 and r["resid2"] < args.tol and float(t.item()) == 0.0)
+        # SCALING: CG stops on the residual of the SCALED system; the true residual of the back-scaled one is the oracle's, not < tol
+        res_ok = (0.5 * ro["resid2"] <= r["resid2"] <= 2.0 * ro["resid2"]) if args.scaling else r["resid2"] < args.tol
+        if args.scaling:
+            print("     true residual of the back-scaled system: library %.3e, serial oracle %.3e" % (r["resid2"], ro["resid2"]), flush=True)
+        ok = (r["error"] == 0 and it_ok and err <= 1e-9 and res_ok and float(t.item()) == 0.0)
         if r["error"] != 0 and r["error"] == ro["error"] and it_ok and err <= 1e-9:
             # the reference algorithm gives up the same way on this system (e.g. 3003 for two DIAG sweeps on tet10): parity
             print("     both the library and the oracle stop with error %d after %d iterations" % (r["error"], r["iter"]), flush=True)

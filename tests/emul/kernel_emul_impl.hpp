@@ -140,9 +140,33 @@ static void run_fiber_block(FiberBlock &B) {
 #endif
     F.state = 0;
   }
+  // Order in which the runnable fibers of a scheduling round get the processor: ascending (default), descending
+  // (FB_EMUL_FIBER_ORDER=reverse) or a fresh random permutation per round (FB_EMUL_FIBER_ORDER=random[:seed]).  Between two
+  // barriers / shuffles the lanes of a real warp are NOT ordered, so a kernel whose result depends on this order has an
+  // intra-warp (or intra-block) race - a missing __syncwarp / __syncthreads - that the default order would hide.  The
+  // test-suite runs the emulated kernels under all three (tests/test_emul_fiber_order.py).
+  static const int order_mode = []() {
+    const char *e = getenv("FB_EMUL_FIBER_ORDER");
+    return !e ? 0 : (!strncmp(e, "reverse", 7) ? 1 : (!strncmp(e, "random", 6) ? 2 : 0));
+  }();
+  static thread_local unsigned long long rng = []() {
+    const char *e = getenv("FB_EMUL_FIBER_ORDER");
+    const char *c = e ? strchr(e, ':') : nullptr;
+    return 0x9E3779B97F4A7C15ull ^ (c ? strtoull(c + 1, nullptr, 10) * 0xD1B54A32D192ED03ull : 0ull);
+  }();
+  std::vector<int> order(n);
+  for (int i = 0; i < n; i++) order[i] = i;
   for (;;) {
     bool ran = false, alive = false;
-    for (int i = 0; i < n; i++) {
+    if (order_mode == 1) { for (int i = 0; i < n; i++) order[i] = n - 1 - i; }
+    else if (order_mode == 2) {
+      for (int i = n - 1; i > 0; i--) {
+        rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+        std::swap(order[i], order[(int)(rng % (unsigned long long)(i + 1))]);
+      }
+    }
+    for (int oi = 0; oi < n; oi++) {
+      const int i = order[oi];
       if (B.f[i].state != 0) continue;
       B.cur = i;
       fb::gridDim.x = B.grid; fb::blockDim.x = B.blockdim ? B.blockdim : B.block; fb::blockIdx.x = B.bidx; fb::threadIdx.x = B.tid0 + (unsigned)i;

@@ -96,3 +96,12 @@ def test_kmetis_partition_3_ranks_through_the_api():
     assert lines[-1].startswith("PASS") and "world=3" in lines[-1]
     lines = _torchrun(5, "dist_check.py", "--host", "--tet", "3", "--comm", "p2p", "--partition", "pmetis")
     assert lines[-1].startswith("PASS") and "p2p_active=1" in lines[-1]
+
+
+def test_scaling_4_ranks_through_the_api():
+    """SCALING=YES on 4 ranks: the scale of the external nodes comes from their owners (hecmw_update_3_R inside
+    hecmw_solver_scaling_fw_33); DIAG and the subdomain-local SSOR, against the oracle with the same option."""
+    lines = _torchrun(4, "dist_check.py", "--host", "--hex", "7", "--comm", "nccl", "--scaling")
+    assert lines[-1].startswith("PASS")
+    lines = _torchrun(2, "dist_check.py", "--host", "--tet", "3", "--comm", "p2p", "--scaling", "--precond", "1")
+    assert lines[-1].startswith("PASS")

@@ -371,6 +371,48 @@ def test_bilu0_auto_sigma_diag_loop(gpu, case):
     assert gpu.get_option("auto_sigma_retries") == 0
 
 
+# (4b) !SOLVER SCALING=YES: symmetric diagonal scaling around the CG loop, csrc/scaling.cuh
+
+@pytest.mark.parametrize("precond", [3, 1, 10])
+@pytest.mark.parametrize("meshname", ["hex8_two_materials", "tet3"])
+def test_solve_with_scaling_matches_oracle(gpu, meshname, precond):
+    """hecmw_solver_scaling_fw_33 / _bk_33 (las/hecmw_solver_scaling_33.f90) around hecmw_solve_CG: same iteration count as
+    the oracle (+-2; it differs from the unscaled count), displacements within 1e-9, the same true residual of the
+    BACK-scaled system (CG stops on the scaled residual, so with a stiffness contrast it may stay above RESID: same
+    converged flag as the oracle), and the matrix left on the device equals the oracle's round-tripped matrix."""
+    from oracle import oracle as orc
+    from frontistr_b200 import meshgen
+    if meshname == "tet3":
+        mesh = meshgen.tet10_cube(3)
+    else:
+        mesh = util.distort(meshgen.hex_cube(8))
+        mesh.sections = [dict(mesh.sections[0]), dict(mesh.sections[0], E=2.1e9)]      # stiffness contrast 1e4: scaling matters
+        mesh.section_ID = np.where(np.arange(mesh.n_elem) % 3 == 0, 2, 1).astype(np.int32)
+    cnt = util.cube_cnt(tol=1e-10, precond=precond)
+    A = util.product_problem(gpu, mesh, cnt, to_host=True)
+    Ao = A.copy()
+    K0 = np.concatenate([A.D, A.AL, A.AU])
+    A.Iarray[6] = 1; Ao.Iarray[6] = 1
+    r = gpu.hecmw_solve(mesh, A, device_resident=True)
+    orc.precond_clear()
+    ro = orc.solve(mesh, Ao)
+    orc.precond_clear()
+    assert r["error"] == 0 and ro["error"] == 0
+    assert abs(r["iter"] - ro["iter"]) <= 2
+    assert r["resid"] <= 1e-10 and abs(r["resid2"] - ro["resid2"]) <= 0.05 * ro["resid2"] and A.Iarray[80] == Ao.Iarray[80]
+    assert util.rel_l2(A.X[: 3 * A.N], Ao.X[: 3 * A.N]) <= 1e-9
+    gpu.mat_download(A, values=True, rhs=True)
+    K1 = np.concatenate([A.D, A.AL, A.AU])
+    Ko = np.concatenate([Ao.D, Ao.AL, Ao.AU])
+    assert np.array_equal(K1, Ko)                                        # same operations in the same order
+    assert np.abs(K1 - K0).max() <= 4e-16 * np.abs(K0).max() and np.abs(A.B - Ao.B).max() == 0.0
+    # the unscaled solve of the same system needs a different number of iterations on the two-material mesh: the option is live
+    if meshname != "tet3" and precond == 3:
+        U = A.copy(); U.Iarray[6] = 0; U.X[:] = 0.0; U.Iarray[96] = 1
+        ru = gpu.hecmw_solve(mesh, U)
+        assert ru["error"] == 0 and util.rel_l2(U.X[: 3 * U.N], A.X[: 3 * A.N]) <= 1e-8
+
+
 # (5) hecmw_mat_con on the device (SURVEY 8(f) rank 4): pair keys + radix sort + scans (csrc/matcon_dev.cuh), selected with
 # option matcon_device=1, against the oracle's restatement of the reference's table-building algorithm.
 
