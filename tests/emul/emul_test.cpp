@@ -626,6 +626,27 @@ long fbemul_misaligned_probe(void) {
   return seen;
 }
 
+// Negative / positive control of the fiber-order race detector (kernel_emul_impl.hpp: fbemul_set_fiber_order): a warp
+// whose lanes hand a value to their neighbour through shared storage, with (sync = 1) and without (sync = 0) the
+// __syncwarp that the exchange needs.  out[lane] = what lane read from lane + 1.  With the barrier the result cannot
+// depend on the order in which the emulator runs the lanes; without it, it does.
+}
+namespace fb {
+static void race_probe_kernel(int sync, double *box, double *out) {
+  const int lane = threadIdx.x & 31;
+  box[lane] = 100.0 + lane;
+  if (sync) __syncwarp();
+  out[lane] = box[(lane + 1) & 31];
+}
+}
+extern "C" {
+int fbemul_race_probe(int sync, double *out) {
+  double box[32];
+  for (int i = 0; i < 32; i++) box[i] = -1.0;
+  emul_launch_blocks(1, 32, fb::race_probe_kernel, sync, (double *)box, out);
+  return 0;
+}
+
 // the device self-test of the three condensation kernels (assembly.cuh: ic_selftest_kernel):
 // out[0] max |K_reg - K_smem|, out[1] max entry, out[2] max |K_ldlt - K_smem|
 int fbemul_ic_selftest(double *out) {

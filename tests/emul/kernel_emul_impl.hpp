@@ -113,6 +113,8 @@ static void fiber_entry() {
   abort();   // a finished fiber is never resumed
 }
 static thread_local std::vector<Fiber> t_fiber_pool;   // stacks are reused from launch to launch
+static int g_order_mode = -1;                 // -1: take FB_EMUL_FIBER_ORDER at the first launch; 0 ascending, 1 descending, 2 random
+static unsigned long long g_order_seed = 0;
 static void run_fiber_block(FiberBlock &B) {
   constexpr size_t STACK = 96 * 1024;
   const int n = (int)B.block;
@@ -145,15 +147,15 @@ static void run_fiber_block(FiberBlock &B) {
   // barriers / shuffles the lanes of a real warp are NOT ordered, so a kernel whose result depends on this order has an
   // intra-warp (or intra-block) race - a missing __syncwarp / __syncthreads - that the default order would hide.  The
   // test-suite runs the emulated kernels under all three (tests/test_emul_fiber_order.py).
-  static const int order_mode = []() {
-    const char *e = getenv("FB_EMUL_FIBER_ORDER");
-    return !e ? 0 : (!strncmp(e, "reverse", 7) ? 1 : (!strncmp(e, "random", 6) ? 2 : 0));
-  }();
-  static thread_local unsigned long long rng = []() {
+  if (g_order_mode < 0) {
     const char *e = getenv("FB_EMUL_FIBER_ORDER");
     const char *c = e ? strchr(e, ':') : nullptr;
-    return 0x9E3779B97F4A7C15ull ^ (c ? strtoull(c + 1, nullptr, 10) * 0xD1B54A32D192ED03ull : 0ull);
-  }();
+    g_order_mode = !e ? 0 : (!strncmp(e, "reverse", 7) ? 1 : (!strncmp(e, "random", 6) ? 2 : 0));
+    g_order_seed = c ? strtoull(c + 1, nullptr, 10) : 0ull;
+  }
+  const int order_mode = g_order_mode;
+  static thread_local unsigned long long rng = 0, rng_seed = ~0ull;
+  if (rng_seed != g_order_seed) { rng_seed = g_order_seed; rng = 0x9E3779B97F4A7C15ull ^ (g_order_seed * 0xD1B54A32D192ED03ull); }
   std::vector<int> order(n);
   for (int i = 0; i < n; i++) order[i] = i;
   for (;;) {
@@ -318,3 +320,9 @@ struct EmulCfg {
   }
 };
 }  // namespace fb
+
+// order in which the runnable fibers of a block are scheduled (see run_fiber_block): 0 ascending, 1 descending, 2 random
+extern "C" void fbemul_set_fiber_order(int mode, unsigned long long seed) {
+  fb::emulwarp::g_order_mode = mode;
+  fb::emulwarp::g_order_seed = seed;
+}

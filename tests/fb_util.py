@@ -171,20 +171,51 @@ def product_problem(hecmw, mesh, cnt, to_host=True, apply_bc=True):
     return A
 
 
-def oracle_iteration_spread(mesh, cnt, axes_list=("x", "z", "xy", "xyz")):
-    """CG iteration counts of the reference algorithm (oracle) on the same system decomposed into 2/4/8
-    subdomains: DIAG-preconditioned CG is partition-invariant mathematically, so the spread of these counts
-    is the reference's own sensitivity to the association order of its dot products."""
+def oracle_iteration_spread(mesh, cnt, axes_list=("x", "y", "z", "xy", "yx", "zx", "zy", "xyz", "zyx", "xx", "xyx"), metis=True):
+    """CG iteration counts of the reference algorithm (oracle, ONE thread: deterministic) on the same system decomposed
+    into 2..8 subdomains by RCB along several axis strings and by KMETIS / PMETIS: DIAG-preconditioned CG is
+    partition-invariant mathematically, so the spread of these counts is the reference's own sensitivity to the
+    association order of its dot products (every decomposition sums the same terms in a different order)."""
     from oracle import oracle as orc
     from frontistr_b200 import partition
+    nth = orc.num_threads()
+    orc.set_num_threads(1)
     out = []
-    for axes in axes_list:
-        parts = partition.partition(mesh, axes)
-        mats = [oracle_problem(p, cnt) for p in parts]
+    try:
+        decomps = [(partition.rcb_domains(mesh, axes), 1 << len(axes)) for axes in axes_list]
+        if metis and partition.metis_available():
+            decomps += [(partition.metis_domains(mesh, nd, meth)[0], nd) for nd in range(2, 9) for meth in ("KMETIS", "PMETIS")]
+        for dom, nd in decomps:
+            parts = partition.partition(mesh, "", domain=dom, nparts=nd)
+            mats = [oracle_problem(p, cnt) for p in parts]
+            orc.precond_clear()
+            out.append(int(orc.solve(parts, mats)["iter"]))
+    finally:
+        orc.set_num_threads(nth)
         orc.precond_clear()
-        out.append(int(orc.solve(parts, mats)["iter"]))
-    orc.precond_clear()
     return out
+
+
+def oracle_history_spread(mesh, cnt, h_serial, n, axes_list=("x", "z", "xy", "xyz")):
+    """Largest relative deviation, over the first n iterations, between the residual history of the reference algorithm
+    (oracle, one thread) on the undivided system and on RCB decompositions of it: how far two executions of the SAME
+    algorithm drift apart through the association order of the dot products alone."""
+    from oracle import oracle as orc
+    from frontistr_b200 import partition
+    nth = orc.num_threads()
+    orc.set_num_threads(1)
+    worst = 0.0
+    try:
+        for axes in axes_list:
+            parts = partition.partition(mesh, axes)
+            orc.precond_clear()
+            h = orc.solve(parts, [oracle_problem(p, cnt) for p in parts], hist_len=len(h_serial) + 8, ssor_threads=2)["hist"]
+            m = min(n, len(h))
+            worst = max(worst, float(np.max(np.abs(h[:m] / h_serial[:m] - 1.0))))
+    finally:
+        orc.set_num_threads(nth)
+        orc.precond_clear()
+    return worst
 
 
 def distort(mesh, amp=0.15, seed=0):

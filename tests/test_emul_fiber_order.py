@@ -1,0 +1,50 @@
+"""Intra-warp / intra-block race detector for the product's kernels, on the CPU.
+
+Between two barriers (or shuffles) the threads of a real warp or block are not ordered.  The host emulation
+(tests/emul/kernel_emul_impl.hpp) runs the runnable fibers of a block in ascending thread order by default, which would
+HIDE a missing __syncwarp / __syncthreads whenever the producer happens to have the lower thread id.  Here the emulated
+kernels run again with the fibers scheduled in DESCENDING order and in a fresh RANDOM order per scheduling round: a
+kernel whose result depends on that order has a race.  The bodies of the GPU tests (assembly of every formulation, BC,
+SpMV, DIAG / SSOR / BILU(0), CG, SCALING, update / nodal stress, total-Lagrangian path, device mat_con) - many of them
+bit-exact comparisons - are the judges.  A control kernel with and without its barrier shows the detector has teeth."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_detector_control_kernel():
+    import __graft_entry__ as g
+    em = C.CDLL(g.build_emul())
+    em.fbemul_set_fiber_order.argtypes = [C.c_int, C.c_ulonglong]
+    em.fbemul_race_probe.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    want = 100.0 + (np.arange(32) + 1) % 32
+    res = {}
+    for sync in (1, 0):
+        for mode, seed in ((0, 0), (1, 0), (2, 5)):
+            out = np.zeros(32)
+            em.fbemul_set_fiber_order(mode, seed)
+            em.fbemul_race_probe(sync, out.ctypes.data_as(C.POINTER(C.c_double)))
+            res[sync, mode] = out
+    em.fbemul_set_fiber_order(0, 0)
+    for mode in (0, 1, 2):
+        assert np.array_equal(res[1, mode], want)                 # with the barrier: right under every order
+    assert not np.array_equal(res[0, 0], want)                    # without it: ascending order reads unwritten slots ...
+    assert np.array_equal(res[0, 1], np.r_[want[:31], -1.0])      # ... descending order only lane 31's
+    assert not np.array_equal(res[0, 0], res[0, 1])               # => the result depends on the order: detected
+
+
+@pytest.mark.parametrize("order", ["reverse", "random:11"])
+def test_kernels_do_not_depend_on_the_order_of_threads_between_barriers(order):
+    env = dict(os.environ, FB_EMUL_FIBER_ORDER=order)
+    files = ["tests/test_gpu_suite_on_host_api.py", "tests/test_gpu_tests_on_emulated_kernels.py", "tests/test_p2p_kernels_emulated.py"]
+    sel = "not smoke_and_bench and not falls_back and not golden_decks and not nlgeom_newton"      # keep the run under ~1.5 min per order
+    out = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-p", "no:cacheprovider", "-k", sel] + files,
+                         capture_output=True, text=True, timeout=1500, env=env, cwd=ROOT)
+    tail = out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-500:]
+    assert out.returncode == 0 and " passed" in tail and "failed" not in tail, out.stdout[-3000:]

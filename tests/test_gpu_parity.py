@@ -170,15 +170,14 @@ def test_solve_golden_decks(gpu, name):
     assert r["error"] == 0 and A.Iarray[80] == 1 and A.Iarray[81] == 0
     # A361 (70 iterations): +-2 of the oracle.  A342 needs ~720 iterations for 1575 DOF: CG has long lost
     # orthogonality there and the count depends on the summation order of the dot products at the 1e-16
-    # level — the REFERENCE ALGORITHM ITSELF gives 704..733 depending on how many MPI ranks it runs on
-    # (tests/test_oracle_units.py::test_iteration_count_spread_of_the_reference_algorithm).  The GPU count
-    # must lie inside that spread (+-2); the residual history is pinned while the recurrences still agree.
+    # level - the REFERENCE ALGORITHM ITSELF gives 706..734 depending on how the same system is decomposed into
+    # subdomains (every decomposition adds the same terms in another order).  The window is not a constant of this
+    # test: it is computed here, deterministically (one oracle thread), over 25 decompositions - RCB along 11 axis
+    # strings and KMETIS / PMETIS with 2..8 domains (tests/fb_util.py: oracle_iteration_spread; also
+    # tests/test_oracle_units.py::test_iteration_count_spread_of_the_reference_algorithm).  The GPU count must lie
+    # inside the reference's own spread (+-2); the residual history is pinned while the recurrences still agree.
     counts = [ro["iter"]] + util.oracle_iteration_spread(mesh, cnt)
-    slack = 2 if name == "A361" else 8     # the oracle's own run-to-run jitter on A342 (OpenMP reduction order)
-    if name == "A342":
-        # five samples of that jitter are not always representative (a run of this test saw all five at <= 722 while the
-        # deterministic device count is 731): also admit the spread observed over many oracle runs, 704 ... 734
-        counts = counts + [704, 734]
+    slack = 2
     assert min(counts) - slack <= r["iter"] <= max(counts) + slack, (r["iter"], counts)
     if name == "A361":
         assert abs(r["iter"] - ro["iter"]) <= 2
@@ -253,7 +252,13 @@ def test_solve_matches_oracle(gpu, meshname, precond, fused):
     n = min(len(r["hist"]), len(ro["hist"])) - 3
     assert np.allclose(r["hist"][:40], ro["hist"][:40], rtol=1e-8)
     assert np.allclose(r["hist"][: n // 2], ro["hist"][: n // 2], rtol=1e-3)
-    assert np.allclose(r["hist"][:n], ro["hist"][:n], rtol=0.25)    # tail: same decay, rounding has decorrelated
+    # tail: same decay, rounding has decorrelated.  How much is not a constant of this test: the reference algorithm's
+    # own histories on 2 / 2 / 4 / 8 subdomains of the same system drift 2-5 % apart from the undivided run over these
+    # iterations (DIAG; the subdomain-local SSOR changes the preconditioner itself and is compared on the first half only)
+    if precond == 3:
+        own = util.oracle_history_spread(mesh, cnt, ro["hist"], n)
+        dev = float(np.max(np.abs(r["hist"][:n] / ro["hist"][:n] - 1.0)))
+        assert dev <= 3.0 * own + 1e-6, (dev, own)
 
 
 def test_solve_iterpremax2(gpu):
