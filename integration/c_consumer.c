@@ -29,6 +29,15 @@ int main(void) {
   int n0 = 0;
   for (int i = 0; i < 12; i++) n0 += (domain[i] == 0);
   if (n0 != 6) { printf("rcb split %d\n", n0); return 5; }
+  /* METHOD=KMETIS of hecmw_part1 (when the build found the CUDA toolkit's METIS archive): 3 domains, every node owned */
+  if (fistr_b200_part_metis_available()) {
+    long long cut = 0;
+    int cnt[3] = {0, 0, 0};
+    rc = fistr_b200_part_metis(2, 3, 12, 1, elem_type_index, elem_type_item, elem_node_index, elem_node_item, domain, &cut);
+    if (rc != FISTR_B200_OK) { printf("part_metis rc=%d (%s)\n", rc, fistr_b200_last_error()); return 6; }
+    for (int i = 0; i < 12; i++) { if (domain[i] < 0 || domain[i] > 2) return 7; cnt[domain[i]]++; }
+    if (cnt[0] + cnt[1] + cnt[2] != 12 || cut <= 0) return 8;
+  }
   /* compute entry points must fail loudly without a device, never fall back to the CPU */
   rc = fistr_b200_init(0);
   printf("c_consumer ok: NPL=%d NPU=%d init rc=%d (%s)\n", NPL, NPU, rc, rc ? fistr_b200_last_error() : "gpu present");
