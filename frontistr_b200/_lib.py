@@ -43,6 +43,8 @@ def declare(L):
     L.fistr_b200_host_register.argtypes = [C.c_void_p, C.c_int64]
     L.fistr_b200_host_unregister.argtypes = [C.c_void_p]
     L.fistr_b200_precond_33_setup.argtypes = [C.c_int, C.c_double, C.c_int]
+    L.fistr_b200_mat_dump.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p]
+    L.fistr_b200_debug_format_e20.argtypes = [C.c_double, C.c_char_p]
     return L
 
 
@@ -64,7 +66,7 @@ EXPORTED = [
     "fistr_b200_init", "fistr_b200_finalize", "fistr_b200_last_error", "fistr_b200_set_option",
     "fistr_b200_get_option", "fistr_b200_comm_get_unique_id", "fistr_b200_comm_init",
     "fistr_b200_comm_finalize", "fistr_b200_mat_con_count", "fistr_b200_mat_con_fill",
-    "fistr_b200_mat_structure", "fistr_b200_mat_upload", "fistr_b200_mat_download",
+    "fistr_b200_mat_structure", "fistr_b200_mat_upload", "fistr_b200_mat_download", "fistr_b200_mat_dump", "fistr_b200_debug_format_e20",
     "fistr_b200_host_register", "fistr_b200_host_unregister",
     "fistr_b200_stiffmatrix_3d", "fistr_b200_mat_ass_bc", "fistr_b200_nl_state_reset",
     "fistr_b200_nl_state_download", "fistr_b200_nl_stiffmatrix_3d", "fistr_b200_nl_update_3d", "fistr_b200_update_3d",

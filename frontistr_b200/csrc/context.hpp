@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "matcon.hpp"
 #include "matcon_dev.cuh"
+#include "matdump.hpp"
 #include "p2p.cuh"
 #include "scaling.cuh"
 #include "partition.hpp"

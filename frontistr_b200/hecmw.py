@@ -347,6 +347,12 @@ def hecmw_solve(hecMESH, hecMAT, device_resident: bool = False):
     return dict(error=rc, iter=it.value, resid=rs.value, resid2=r2.value, times=times, hist=hist[:nh], profile=prof)
 
 
+def hecmw_mat_dump(dump_type: int, what: int = 1, numcall: int = 0, directory: str = ""):
+    """hecmw_mat_dump + hecmw_mat_dump_rhs (what=1) / hecmw_mat_dump_solution (what=2) of the device-resident system
+    (matrix/hecmw_matrix_dump.f90); dump_type 1 MM, 2 CSR, 3 BSR."""
+    check(_lib.lib().fistr_b200_mat_dump(int(dump_type), int(what), int(numcall), directory.encode()))
+
+
 def hecmw_matvec(X: np.ndarray, n_internal3: int) -> np.ndarray:
     x = np.ascontiguousarray(X, np.float64)
     y = np.zeros(n_internal3)

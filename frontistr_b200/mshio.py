@@ -13,6 +13,7 @@ This is host-side plumbing for tests/bench; the reference's own readers stay in 
 """
 from __future__ import annotations
 
+import os
 import re
 import warnings
 
@@ -312,6 +313,11 @@ def apply_solver_card(hecMAT: hecmwST_matrix, solver) -> None:
         I[6] = yn[opts["SCALING"].upper()]
     if "USEJAD" in opts:                  # svIarray(33) :126 (refused by the library: it keeps its own SELL copy)
         I[32] = yn[opts["USEJAD"].upper()]
+    if "DUMPTYPE" in opts:                # svIarray(31) :124: 0..3 or NONE / MM / CSR / BSR
+        d = opts["DUMPTYPE"].upper()
+        I[30] = int(d) if d.isdigit() else {"NONE": 0, "MM": 1, "CSR": 2, "BSR": 3}[d]
+    if "DUMPEXIT" in opts:                # svIarray(32) :125
+        I[31] = yn[opts["DUMPEXIT"].upper()]
     if "METHOD2" in opts:                 # svIarray(8) :129: the Krylov method to switch to after CG diverged
         m2 = opts["METHOD2"].upper()
         I[7] = int(m2) if m2.isdigit() else _METHODS[m2]
@@ -649,3 +655,34 @@ def write_dist_mesh(path: str, local: hecmwST_local_mesh, global_mesh: hecmwST_l
     with open(path, "w") as f:
         f.write("".join(out))
 
+
+
+def read_mat_dump(path: str):
+    """Reads a file written by hecmw_mat_dump / _rhs / _solution (hecmw1/src/solver/matrix/hecmw_matrix_dump.f90; here
+    csrc/matdump.hpp) - also one written by a genuine fistr1 run with `!SOLVER, DUMPTYPE=...`.
+    .rhs / .sol -> 1-D array.  .bsr -> dict(nrow, ncol, ndof, index, item (1-based block columns), value [nnz, ndof, ndof]).
+    .csr -> dict(nrow, ncol, index, item (1-based), value).  .mm -> dict(nrow, ncol, row, col (1-based), value)."""
+    ext = os.path.splitext(path)[1].lower()
+    with open(path) as f:
+        lines = f.read().split("\n")
+    if ext in (".rhs", ".sol"):
+        return np.array([float(x) for x in lines if x.strip()])
+    body = [ln for ln in lines if ln.strip() and not ln.startswith("%")]
+    head = [int(x) for x in body[0].split()]
+    if ext == ".mm":
+        nrow, ncol, nnz = head
+        t = np.array([ln.split() for ln in body[1: 1 + nnz]])
+        return dict(nrow=nrow, ncol=ncol, row=t[:, 0].astype(np.int64), col=t[:, 1].astype(np.int64), value=t[:, 2].astype(float))
+    if ext == ".csr":
+        nrow, ncol, nnz = head
+        index = np.array(body[1: 2 + nrow], np.int64)
+        item = np.array(body[2 + nrow: 2 + nrow + nnz], np.int64)
+        value = np.array(body[2 + nrow + nnz: 2 + nrow + 2 * nnz], float)
+        return dict(nrow=nrow, ncol=ncol, index=index, item=item, value=value)
+    if ext == ".bsr":
+        nrow, ncol, nnz, ndof = head
+        index = np.array(body[1: 2 + nrow], np.int64)
+        item = np.array(body[2 + nrow: 2 + nrow + nnz], np.int64)
+        value = np.array(body[2 + nrow + nnz: 2 + nrow + nnz + nnz * ndof * ndof], float).reshape(nnz, ndof, ndof)
+        return dict(nrow=nrow, ncol=ncol, ndof=ndof, index=index, item=item, value=value)
+    raise ValueError("unknown dump file type: " + path)

@@ -180,6 +180,17 @@ int fistr_b200_solve_33(int N, int NP, int NPL, int NPU, const double *D, const 
                         int n_neighbor_pe, const int *neighbor_pe, const int *import_index,
                         const int *import_item, const int *export_index, const int *export_item,
                         int my_rank, int petot, int *iter_out, double *resid_out, double *time_out);
+/* hecmw_mat_dump + hecmw_mat_dump_rhs (what = 1) / hecmw_mat_dump_solution (what = 2) of the DEVICE-RESIDENT system
+ * (hecmw1/src/solver/matrix/hecmw_matrix_dump.f90:30-372): text files dump_matrix_<call>_<rank>.{mm|csr|bsr, rhs, sol} in
+ * dir (NULL or "" = working directory), all NP rows, values in Fortran's E20.12E3 format one per line.  dump_type 1
+ * MatrixMarket, 2 scalar CSR, 3 block CSR.  numcall <= 0: the library's own count of solve calls (the reference's
+ * NumCall).  fistr_b200_solve_33 calls it by itself when Iarray(31) (DUMPTYPE) != 0 - before the CG loop and, for the
+ * solution, after the final residual - writing into $FISTR_B200_DUMP_DIR or the working directory; with Iarray(32)
+ * (DUMPEXIT) != 0 it then returns FISTR_B200_ERR_STATE without solving (the reference stops the program there). */
+int fistr_b200_mat_dump(int dump_type, int what, int numcall, const char *dir);
+/* host-only: v in Fortran's E20.12E3 edit descriptor as the dump files carry it; out receives 20 characters + 0 */
+int fistr_b200_debug_format_e20(double v, char *out);
+
 /* residual history of the last solve (RESID per iteration, what ITERLOG=YES prints, CG.f90:245) */
 int fistr_b200_solve_history(double *hist, int max_len);
 /* CUDA-event profile of the last solve (needs the "time_ax" option or TIMELOG): mean seconds per sampled

@@ -102,3 +102,19 @@ def test_fortran_interface_argument_lists_match_header():
             assert (is_ptr and (cptr or not val)) or (not is_ptr and val and not cptr), (name, dname, is_ptr, val, cptr)
         checked += 1
     assert checked >= 24
+
+
+def test_fortran_e20_12e3_number_format():
+    """The dump files (hecmw_matrix_dump.f90: lineFormat "(e20.12e3)") carry numbers as [-]0.dddddddddddd E+eee in 20 columns:
+    leading-zero mantissa of 12 digits, three-digit exponent, correctly rounded."""
+    from frontistr_b200 import _lib
+    L = _lib.lib()
+    buf = C.create_string_buffer(24)
+    cases = {1.0: " 0.100000000000E+001", -1234.5: "-0.123450000000E+004", 0.0: " 0.000000000000E+000",
+             1e-300: " 0.100000000000E-299", 999.9999999999995: " 0.100000000000E+004", 210000.0: " 0.210000000000E+006",
+             -0.5: "-0.500000000000E+000", 1.0 / 3.0: " 0.333333333333E+000", 2.0 / 3.0: " 0.666666666667E+000",
+             6.02214076e23: " 0.602214076000E+024", -1e-5: "-0.100000000000E-004"}
+    for v, want in cases.items():
+        L.fistr_b200_debug_format_e20(v, buf)
+        assert buf.value.decode() == want, (v, buf.value, want)
+        assert len(want) == 20 and abs(float(want) - v) <= 5e-12 * abs(v)

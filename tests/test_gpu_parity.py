@@ -1,6 +1,8 @@
 """GPU parity tests proper: every call goes through the C-ABI (frontistr_b200/libfistr_b200.so) and is
 compared with the oracle on the same inputs.  Integer/index results must be bit-exact; floating-point
 tolerances are written next to each assertion."""
+import os
+
 import numpy as np
 import pytest
 
@@ -327,6 +329,75 @@ def test_solver_status_codes(gpu):
         orc.precond_clear()
         mat.X[:] = 0.0
         assert orc.solve(mesh, mat)["error"] == want
+
+
+def test_matrix_dump_files(gpu):
+    import pathlib
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        old = os.environ.get("FISTR_B200_DUMP_DIR")
+        os.environ["FISTR_B200_DUMP_DIR"] = tmp
+        try:
+            _matrix_dump_files(gpu, pathlib.Path(tmp))
+        finally:
+            if old is None:
+                del os.environ["FISTR_B200_DUMP_DIR"]
+            else:
+                os.environ["FISTR_B200_DUMP_DIR"] = old
+
+
+def _matrix_dump_files(gpu, tmp_path):
+    """`!SOLVER, DUMPTYPE=MM|CSR|BSR` (hecmw_mat_dump / _rhs / _solution, matrix/hecmw_matrix_dump.f90): the files the solve
+    writes - names, headers, entry order (L, D, U per row; all NP rows), Fortran E20.12E3 numbers - read back to the matrix,
+    right-hand side and solution that went through the solve; DUMPEXIT returns without solving."""
+    from frontistr_b200 import mshio
+    from frontistr_b200._lib import FistrB200Error
+    mesh = util.distort(meshgen.hex_cube(3))
+    A = util.product_problem(gpu, mesh, util.cube_cnt(tol=1e-10), to_host=True)
+    import glob
+    got = {}
+    for dtype, ext in ((1, "mm"), (2, "csr"), (3, "bsr")):
+        M = A.copy(); M.Iarray[30] = dtype; M.X[:] = 0.0; M.Iarray[96] = 1
+        assert gpu.hecmw_solve(mesh, M)["error"] == 0
+        files = sorted(glob.glob(str(tmp_path / ("dump_matrix_*_0.%s" % ext))))
+        assert len(files) == 1
+        stem = files[0][: -len(ext) - 1]
+        got[ext] = mshio.read_mat_dump(files[0])
+        rhs, sol = mshio.read_mat_dump(stem + ".rhs"), mshio.read_mat_dump(stem + ".sol")
+        assert len(rhs) == 3 * A.NP and np.allclose(rhs, A.B, rtol=1e-11, atol=0) and np.allclose(sol, M.X, rtol=1e-11, atol=1e-300)
+        with open(files[0]) as f:
+            first = f.readline().rstrip("\n")
+        assert first == {"mm": "%%MatrixMarket matrix coordinate real general", "csr": "%%CSR matrix real general",
+                         "bsr": "%%Block-CSR matrix real general"}[ext]
+        with open(stem + ".rhs") as f:
+            ln = f.readline().rstrip("\n")
+        assert len(ln) == 20 and ln[1:3] == "0." and ln[15] == "E" and ln[16] in "+-"      # E20.12E3
+    # dense reconstruction from each format equals the hecmwST_matrix
+    n3 = 3 * A.NP
+    K = np.zeros((n3, n3))
+    for i in range(A.NP):
+        K[3 * i: 3 * i + 3, 3 * i: 3 * i + 3] = A.D[9 * i: 9 * i + 9].reshape(3, 3)
+        for k in range(A.indexL[i], A.indexL[i + 1]):
+            j = A.itemL[k] - 1; K[3 * i: 3 * i + 3, 3 * j: 3 * j + 3] = A.AL[9 * k: 9 * k + 9].reshape(3, 3)
+        for k in range(A.indexU[i], A.indexU[i + 1]):
+            j = A.itemU[k] - 1; K[3 * i: 3 * i + 3, 3 * j: 3 * j + 3] = A.AU[9 * k: 9 * k + 9].reshape(3, 3)
+    tol = 1e-11 * np.abs(K).max()
+    mm = got["mm"]; Kmm = np.zeros_like(K); Kmm[mm["row"] - 1, mm["col"] - 1] = mm["value"]
+    assert mm["nrow"] == n3 and np.abs(Kmm - K).max() <= tol
+    csr = got["csr"]; Kc = np.zeros_like(K)
+    for r in range(n3):
+        Kc[r, csr["item"][csr["index"][r]: csr["index"][r + 1]] - 1] = csr["value"][csr["index"][r]: csr["index"][r + 1]]
+    assert np.abs(Kc - K).max() <= tol and np.all(np.diff(csr["item"][csr["index"][0]: csr["index"][1]]) > 0)
+    bsr = got["bsr"]; Kb = np.zeros_like(K)
+    for i in range(A.NP):
+        for k in range(bsr["index"][i], bsr["index"][i + 1]):
+            j = bsr["item"][k] - 1; Kb[3 * i: 3 * i + 3, 3 * j: 3 * j + 3] = bsr["value"][k]
+    assert bsr["ndof"] == 3 and bsr["nrow"] == A.NP and np.abs(Kb - K).max() <= tol
+    # DUMPEXIT: the dump is written, nothing is solved
+    E = A.copy(); E.Iarray[30] = 3; E.Iarray[31] = 1; E.X[:] = 7.0
+    with pytest.raises(FistrB200Error):
+        gpu.hecmw_solve(mesh, E)
+    assert np.all(E.X == 7.0)
 
 
 def test_precond_recycle_flags(gpu):
