@@ -64,11 +64,13 @@ def parse_args():
                          "of a cube; needs N = 2, 4, 8); kmetis / pmetis = the reference's node graph through METIS 5 (any N)")
     ap.add_argument("--comm", default="auto", choices=["auto", "p2p", "nccl"],
                     help="N>1 transport of the halo exchange + dot-product all-reduce: peer-memory stores issued by the CG "
-                         "kernels (p2p) or NCCL.  auto = what has RUN ON HARDWARE at that N: p2p at N=2, NCCL at N>2 (p2p at "
-                         "N=4/8 is validated only through the host-compiled library, tests/test_dist_host_api.py: ask for it with "
-                         "--comm p2p).  Two safety nets under p2p: the library itself stays on NCCL if the arenas cannot be "
-                         "mapped on every rank, and a peer-memory wait that times out makes all ranks fall back to NCCL "
-                         "together (noted as comm_note in the line)")
+                         "kernels (p2p) or NCCL.  auto = NCCL at every N: it is the transport whose kernels (the same ones as at "
+                         "N = 1) have run on hardware at N = 2 and 8; the peer-memory kernels were reworked after their only "
+                         "hardware run (N = 2, round 1) and since then have run only through the host-compiled library "
+                         "(tests/test_dist_host_api.py, tests/test_p2p_kernels_emulated.py) - ask for them with --comm p2p after "
+                         "tools/gpu_r2_p2p.sh has passed.  Two safety nets under p2p: the library itself stays on NCCL if the "
+                         "arenas cannot be mapped on every rank, and a peer-memory wait that times out makes all ranks fall back "
+                         "to NCCL together (noted as comm_note in the line)")
     return ap.parse_args()
 
 
@@ -257,7 +259,7 @@ def run_b200(args):
     # run on a GPU - is opt-in (--ic-probe) and runs AFTER the line has been printed (N = 1; verdicts and timings to stderr).
     hecmw.set_option("ic_inverse", 0)
     if world > 1:
-        use_p2p = args.comm == "p2p" or (args.comm == "auto" and world == 2)
+        use_p2p = args.comm == "p2p"      # auto = NCCL at every N: the peer-memory kernels of HEAD have not run on hardware
         hecmw.set_option("p2p", 1 if use_p2p else 0)
         hecmw.comm_init_from_torch()
     dev = hecmw.device_info()
