@@ -80,10 +80,12 @@ def workload_name(n, precond=3):
 
 
 def ncu_traffic(n, world):
-    """dram__bytes_read+write per launch of the dominant kernel from the committed ncu --set full capture
-    (only valid for the workload it was captured on)."""
-    p = os.path.join(ROOT, "profiles", "r1_spmv_sell2_full.json")
-    if n == 150 and world == 1 and os.path.exists(p):
+    """dram__bytes_read+write per launch of the dominant kernel, from a committed `ncu --set full` capture of THIS kernel on
+    THIS workload (profiles/r2_spmv_sell2_full_H<n>.json, written by the capture script) - or null.  The round-1 capture
+    (profiles/r1_spmv_sell2_full.json: 7.427 GB per launch at H150 = 1.039 x algorithmic) is of an earlier build of the
+    kernel and is deliberately NOT reported as this run's traffic."""
+    p = os.path.join(ROOT, "profiles", "r2_spmv_sell2_full_H%d.json" % n)
+    if world == 1 and os.path.exists(p):
         with open(p) as f:
             return float(json.load(f)["traffic_bytes_per_launch"])
     return None

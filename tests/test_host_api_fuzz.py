@@ -106,11 +106,11 @@ def test_random_mesh_assembly_update_and_nodal_stress(host_api, seed):
         assert np.abs(qf - q).max() <= 1e-11 * np.abs(q).max(), seed
 
 
-@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("seed", range(16))
 def test_random_constraints_and_solve(host_api, seed):
-    """Random Dirichlet sets (several DOFs per node, non-zero prescribed values), random nodal loads, PRECOND 1 / 3,
-    iterPREmax 1 / 2: hecmw_mat_ass_bc and hecmw_solve through the library against the oracle — same iteration count
-    (+-2), same solution, same flags."""
+    """Random Dirichlet sets (several DOFs per node, non-zero prescribed values), random nodal loads, PRECOND 1 / 3 / 10,
+    iterPREmax 1 / 2, every fourth case with SCALING=YES: hecmw_mat_ass_bc and hecmw_solve through the library against the
+    oracle — same iteration count (+-2), same solution, same flags."""
     from oracle import oracle as orc
     from frontistr_b200.mshio import apply_solver_card
     gpu = host_api
@@ -132,7 +132,9 @@ def test_random_constraints_and_solve(host_api, seed):
         be.mat_upload(A, values=False, rhs=True)
         be.hecmw_mat_ass_bc(np.array(bn, np.int32), np.array(bd, np.int32), np.array(bv))
         apply_solver_card(A, cnt["solver"]); A.Iarray[20] = 0; A.Iarray[21] = 0
+        A.Iarray[6] = scaling
 
+    scaling = 1 if seed % 4 == 1 else 0
     A = gpu.hecmw_mat_con(mesh)
     A.fstr_mat_init().hecMAT_init()
     gpu.mat_structure(mesh, A)
@@ -145,13 +147,14 @@ def test_random_constraints_and_solve(host_api, seed):
     for n, d, v in zip(bn, bd, bv):
         orc.mat_ass_bc(Ao, int(n), int(d), float(v))
     apply_solver_card(Ao, cnt["solver"]); Ao.Iarray[20] = 0; Ao.Iarray[21] = 0
+    Ao.Iarray[6] = scaling
     orc.precond_clear()
     ro = orc.solve(mesh, Ao, ssor_threads=2)     # multicolour ordering, as the library (and the reference with > 1 thread) uses
     orc.precond_clear()
     assert r["error"] == ro["error"], (r["error"], ro["error"], precond, ipm)
     if r["error"] != 0:
         return        # same HEC-MW code on both sides (e.g. 3003 when the random system makes SSOR x2 indefinite)
-    assert A.Iarray[80] == 1
+    assert A.Iarray[80] == Ao.Iarray[80] and (scaling or A.Iarray[80] == 1)
     assert abs(r["iter"] - ro["iter"]) <= 2, (r["iter"], ro["iter"], precond, ipm)
     assert util.rel_l2(A.X, Ao.X) <= 1e-8
     idx = 3 * (np.array(bn) - 1) + np.array(bd) - 1
