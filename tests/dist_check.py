@@ -22,6 +22,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--hex", dest="n", type=int, default=24)
     ap.add_argument("--partition", default="rcb", choices=["rcb", "kmetis", "pmetis"])
+    ap.add_argument("--empty-last-rank", action="store_true", help="the last rank owns no node at all (N = NP = 0): the mesh is "
+                    "split over world-1 domains with KMETIS (or RCB if world-1 is 2 / 4)")
     ap.add_argument("--scaling", action="store_true", help="!SOLVER SCALING=YES (Iarray(7) = 1): the scale vector is halo-exchanged")
     ap.add_argument("--tet", type=int, default=0)
     ap.add_argument("--precond", type=int, default=3)
@@ -54,7 +56,11 @@ def main():
     hecmw.set_option("p2p", {"p2p": 2, "p2p-or-nccl": 1, "nccl": 0}[args.comm])   # 2 = fail loudly if peer memory cannot be mapped
     hecmw.comm_init_from_torch()
     gmesh = meshgen.tet10_cube(args.tet) if args.tet else util.distort(meshgen.hex_cube(args.n))
-    if args.partition == "rcb":
+    if args.empty_last_rank:
+        nd = world - 1
+        dom = (partition.rcb_domains(gmesh, {2: "x", 4: "xy"}[nd]) if nd in (2, 4) else
+               (np.zeros(gmesh.n_node, np.int32) if nd == 1 else partition.metis_domains(gmesh, nd, "KMETIS")[0]))
+    elif args.partition == "rcb":
         axes = {2: "x", 4: "xy", 8: "xyz"}[world]
         dom = partition.rcb_domains(gmesh, axes)
     else:      # METHOD=KMETIS / PMETIS: every rank computes the same (deterministic) map; any world size
@@ -71,7 +77,7 @@ def main():
     xg.view(-1, 3)[own] = xl
     dist.all_reduce(xg)
     xgl = xg.cpu().numpy().reshape(-1, 3)
-    halo_err = float(np.abs(A.X.reshape(-1, 3) - xgl[m.global_node_ID - 1]).max())
+    halo_err = float(np.abs(A.X.reshape(-1, 3) - xgl[m.global_node_ID - 1]).max(initial=0.0))
     t = torch.tensor([halo_err], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ok = True

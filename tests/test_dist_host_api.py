@@ -105,3 +105,13 @@ def test_scaling_4_ranks_through_the_api():
     assert lines[-1].startswith("PASS")
     lines = _torchrun(2, "dist_check.py", "--host", "--tet", "3", "--comm", "p2p", "--scaling", "--precond", "1")
     assert lines[-1].startswith("PASS")
+
+
+def test_a_rank_that_owns_no_node():
+    """N = NP = 0 on the last rank (an odd partition can leave a rank empty): its kernels still launch (one block each), so
+    every grid reduction writes its zero partial and publishes its tag, and it opens and closes the same (empty) send /
+    recv groups as everybody else - collective and peer-memory transport, DIAG and the level-scheduled BILU(0)."""
+    lines = _torchrun(3, "dist_check.py", "--host", "--hex", "5", "--comm", "p2p", "--empty-last-rank")
+    assert lines[-1].startswith("PASS") and "p2p_active=1" in lines[-1]
+    lines = _torchrun(3, "dist_check.py", "--host", "--hex", "5", "--comm", "nccl", "--empty-last-rank", "--precond", "10")
+    assert lines[-1].startswith("PASS")
