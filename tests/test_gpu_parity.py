@@ -400,6 +400,25 @@ def _matrix_dump_files(gpu, tmp_path):
     assert np.all(E.X == 7.0)
 
 
+def test_structure_size_limits(gpu):
+    """Maximum sizes: blocks are addressed by 32-bit slots ([D | AL | AU], csrc/assembly.cuh), so a structure with
+    NP + NPL + NPU >= 2^32 - 2 is refused before anything is allocated; so are negative / inconsistent sizes."""
+    import ctypes as C
+    from frontistr_b200 import _lib
+    L = _lib.lib()
+    one = np.zeros(2, np.int32)
+    ip_ = one.ctypes.data_as(C.POINTER(C.c_int))
+    big = 2 ** 31 - 1
+    for N, NP, NPL, NPU in ((1, 1, big, big), (2, 1, 0, 0), (-1, 1, 0, 0), (1, 1, -5, 0)):
+        rc = L.fistr_b200_mat_structure(N, NP, NPL, NPU, ip_, ip_, ip_, ip_, 0, None, None, None, None, None)
+        assert rc == -1, (N, NP, NPL, NPU, rc)
+    assert b"32-bit slots" in L.fistr_b200_last_error() or b"bad sizes" in L.fistr_b200_last_error()
+    # the library is still usable afterwards
+    mesh = meshgen.hex_cube(2)
+    A = util.product_problem(gpu, mesh, util.cube_cnt(), to_host=True)
+    assert gpu.hecmw_solve(mesh, A)["error"] == 0
+
+
 def test_precond_recycle_flags(gpu):
     """Iarray(96/97/98) policy (matrix_misc.f90:678-697): numeric set-up reused up to 3 solves."""
     mesh = meshgen.hex_cube(4)
