@@ -31,6 +31,7 @@ extern int64_t g_launch_count;
     if (_e != cudaSuccess) {                                                               \
       fb::g_last_error = std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" +        \
                          __FILE__ + ":" + std::to_string(__LINE__) + ")";                  \
+      cudaGetLastError(); /* reported here; do not let a later launch check see it again */ \
       return FISTR_B200_ERR_CUDA;                                                          \
     }                                                                                      \
   } while (0)
@@ -38,7 +39,7 @@ extern int64_t g_launch_count;
 #define FB_LAUNCH_CHECK()                                                                  \
   do {                                                                                     \
     ++fb::g_launch_count;                                                                  \
-    cudaError_t _e = cudaPeekAtLastError();                                                \
+    cudaError_t _e = cudaGetLastError(); /* returns AND resets a non-sticky error */        \
     if (_e != cudaSuccess) {                                                               \
       fb::g_last_error = std::string("kernel launch: ") + cudaGetErrorString(_e) + " (" +  \
                          __FILE__ + ":" + std::to_string(__LINE__) + ")";                  \
@@ -186,6 +187,7 @@ struct DevBuf {
     cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
     if (e != cudaSuccess) {
       g_last_error = std::string("cudaMalloc(") + std::to_string(count * sizeof(T)) + "): " + cudaGetErrorString(e);
+      cudaGetLastError();   // reported through the return value: a later launch check must not see it again
       p = nullptr;
       n = 0;
       return -1;
