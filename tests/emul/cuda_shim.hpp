@@ -56,7 +56,7 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
 // The pages come from a memfd mapped MAP_SHARED, so that another PROCESS (= another emulated GPU) can map the same
 // buffer: cudaIpcGetMemHandle hands out (pid, fd, length, offset of the user pointer) and cudaIpcOpenMemHandle maps
 // /proc/<pid>/fd/<fd>.
-struct CudaShimAlloc { void *base; size_t len; int fd; size_t user_off; };
+struct CudaShimAlloc { void *base; size_t len; int fd; size_t user_off; size_t bytes; };
 struct CudaShimAllocs {
   std::mutex mu;
   std::map<void *, CudaShimAlloc> live;      // user pointer -> mapping
@@ -65,7 +65,20 @@ struct CudaShimAllocs {
   static CudaShimAllocs &get() { static CudaShimAllocs a; return a; }
 };
 struct CudaShimIpc { int pid, fd; unsigned long long len, off; };
+// FB_EMUL_DEVICE_BYTES=<n>: the emulated device holds at most n bytes of live allocations; a cudaMalloc beyond that fails
+// with cudaErrorMemoryAllocation (tests of the out-of-memory paths: scratch fall-backs, bench.py's workload fall-back)
+inline size_t cuda_shim_capacity() {
+  const char *e = getenv("FB_EMUL_DEVICE_BYTES");
+  return e ? (size_t)strtoull(e, nullptr, 10) : ~(size_t)0;
+}
+inline size_t &cuda_shim_live_bytes() { static size_t b = 0; return b; }
 inline cudaError_t cudaMalloc(void **p, size_t bytes) {
+  {
+    CudaShimAllocs &A = CudaShimAllocs::get();
+    std::lock_guard<std::mutex> g(A.mu);
+    if (cuda_shim_live_bytes() + bytes > cuda_shim_capacity()) { *p = nullptr; return cudaErrorMemoryAllocation; }
+    cuda_shim_live_bytes() += bytes;
+  }
   const size_t page = (size_t)sysconf(_SC_PAGESIZE);
   const size_t user = (std::max<size_t>(bytes, 1) + 15) & ~(size_t)15;
   const size_t body = (user + page - 1) / page * page;
@@ -81,7 +94,7 @@ inline cudaError_t cudaMalloc(void **p, size_t bytes) {
   {
     CudaShimAllocs &A = CudaShimAllocs::get();
     std::lock_guard<std::mutex> g(A.mu);
-    A.live[q] = CudaShimAlloc{(void *)base, len, fd, (size_t)(q - base)};
+    A.live[q] = CudaShimAlloc{(void *)base, len, fd, (size_t)(q - base), bytes};
   }
   *p = q;
   return cudaSuccess;
@@ -96,6 +109,7 @@ inline cudaError_t cudaFree(void *p) {
   if (it == A.live.end()) { fprintf(stderr, "cuda_shim: cudaFree of an unknown pointer\n"); abort(); }
   munmap(it->second.base, it->second.len);
   close(it->second.fd);
+  cuda_shim_live_bytes() -= it->second.bytes;
   A.live.erase(it);
   return cudaSuccess;
 }

@@ -198,3 +198,46 @@ def test_bench_default_workload_falls_back_when_it_does_not_fit(host_api, monkey
     with pytest.raises(FistrB200Error):
         bench.run_b200(args)
     host_api.finalize(); host_api.init(0)
+
+
+@pytest.mark.parametrize("capacity", [3_000_000, 6_000_000])
+def test_bench_falls_back_on_a_real_allocation_failure(host_api, monkeypatch, capsys, capacity):
+    """The same through the library's own out-of-memory path: the emulated device is given a capacity
+    (FB_EMUL_DEVICE_BYTES, tests/emul/cuda_shim.hpp) that the stand-in default mesh exceeds - at 3 MB already in the set-up,
+    at 6 MB only when the first solve allocates its private SELL copy (the gather scratch had fallen back to the atomic
+    scatter before) - while the fall-back mesh fits.  The library reports -2, releases everything on finalize and comes
+    back clean: the line is measured on the fall-back workload."""
+    import argparse
+    import json
+
+    import torch
+
+    import bench
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *_: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *_: None)
+
+    class NoSampler:
+        def __init__(self, *_):
+            pass
+
+        def start(self):
+            return self
+
+        def stop(self):
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["stub"]}
+    monkeypatch.setattr(bench, "ClockSampler", NoSampler)
+    monkeypatch.setattr(host_api, "fp64_peak", lambda: 1.0)
+    monkeypatch.setattr(bench, "DEFAULT_N", 10)
+    monkeypatch.setattr(bench, "FALLBACK_N", 5)
+    host_api.finalize(); host_api.init(0)          # start from an empty device
+    monkeypatch.setenv("FB_EMUL_DEVICE_BYTES", str(capacity))
+    args = argparse.Namespace(gpus=1, steps=1, warmup=1, impl="b200", n=None, tol=1.0e-8, precond=3, maxit=20000, ref_iters=0,
+                              no_cpu_baseline=True, no_e2e=True, comm="auto", partition="rcb")
+    try:
+        bench.run_b200(args)
+    finally:
+        monkeypatch.delenv("FB_EMUL_DEVICE_BYTES")
+    d = json.loads([ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")][-1])
+    assert "fell back to H5" in d["config"]["workload_note"] and "out of memory" in d["config"]["workload_note"]
+    assert d["config"]["workload"].startswith("H5:") and d["value"] > 0 and d["resid_true"] < 1.0e-8
+    host_api.finalize(); host_api.init(0)

@@ -415,3 +415,39 @@ def test_bilu0_kernels_against_an_exactly_rounded_model(host_api, name, chain_ro
     zo = z0.copy()
     orc.Precond(A, precond=10).apply(zo)
     assert np.abs(zo - zm).max() <= 8 * np.finfo(float).eps * np.abs(zm).max()
+
+
+@pytest.mark.parametrize("precond", [3, 1, 10])
+def test_out_of_memory_is_an_error_code_at_any_point(host_api, precond, monkeypatch):
+    """The emulated device gets capacities from 20 KB to 8 MB (FB_EMUL_DEVICE_BYTES, tests/emul/cuda_shim.hpp), so that the
+    allocation that fails is a different one each time - structure, work vectors, gather maps (falls back to the atomic
+    scatter), element scratch, SELL copy, preconditioner copy, history.  Every run ends either with the right solution or
+    with FISTR_B200_ERR_CUDA (-2, "out of memory") - never a crash, a hang or a wrong answer - and after finalize / init
+    the library works again (every buffer is owned: nothing leaks across the failure)."""
+    from oracle import oracle as orc
+    from frontistr_b200._lib import FistrB200Error
+    gpu = host_api
+    mesh = util.distort(meshgen.hex_cube(6))
+    cnt = util.cube_cnt(tol=1e-10, precond=precond)
+    Ao = util.oracle_problem(mesh, cnt)
+    orc.precond_clear()
+    ro = orc.solve(mesh, Ao, ssor_threads=2)
+    orc.precond_clear()
+    outcomes = set()
+    for cap in (20_000, 150_000, 500_000, 800_000, 1_200_000, 1_800_000, 2_500_000, 3_200_000, 4_000_000, 8_000_000):
+        gpu.finalize(); gpu.init(0)
+        monkeypatch.setenv("FB_EMUL_DEVICE_BYTES", str(cap))
+        try:
+            A = util.product_problem(gpu, mesh, cnt, to_host=True)
+            r = gpu.hecmw_solve(mesh, A)
+            assert r["error"] == 0 and abs(r["iter"] - ro["iter"]) <= 2 and util.rel_l2(A.X, Ao.X) <= 1e-8
+            outcomes.add("ok")
+        except FistrB200Error as e:
+            assert e.code == -2 and "out of memory" in str(e), str(e)
+            outcomes.add("oom")
+        finally:
+            monkeypatch.delenv("FB_EMUL_DEVICE_BYTES")
+    assert outcomes == {"ok", "oom"}
+    gpu.finalize(); gpu.init(0)
+    A = util.product_problem(gpu, mesh, cnt, to_host=True)
+    assert gpu.hecmw_solve(mesh, A)["error"] == 0
