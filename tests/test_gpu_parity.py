@@ -400,6 +400,37 @@ def _matrix_dump_files(gpu, tmp_path):
     assert np.all(E.X == 7.0)
 
 
+def test_assembly_error_contract(gpu):
+    """A malformed mesh is an error code, never a device fault: node ids outside 1..n_node, an element with the wrong
+    number of nodes, a section id out of range, an element option outside 1..3, an element type outside the path; and an
+    element whose node pair is missing from the matrix graph is the reference's "cannot find connectivity"
+    (hecmw_mat_ass.f90:86-90) = FISTR_B200_ERR_CONNECTIVITY."""
+    from frontistr_b200._lib import FistrB200Error
+
+    def fresh():
+        m = meshgen.hex_cube(3)
+        A_ = gpu.hecmw_mat_con(m); A_.fstr_mat_init().hecMAT_init()
+        gpu.mat_structure(m, A_)
+        return m, A_
+    cases = []
+    m, A = fresh(); m.elem_node_item = m.elem_node_item.copy(); m.elem_node_item[5] = m.n_node + 1; cases.append((m, A, -1))
+    m, A = fresh(); m.elem_node_item = m.elem_node_item.copy(); m.elem_node_item[9] = 0; cases.append((m, A, -1))
+    m, A = fresh(); m.elem_node_index = m.elem_node_index.copy(); m.elem_node_index[2] += 1; cases.append((m, A, -1))
+    m, A = fresh(); m.section_ID = m.section_ID.copy(); m.section_ID[0] = 2; cases.append((m, A, -1))
+    m, A = fresh(); m.sections = [dict(m.sections[0], elemopt361=4)]; cases.append((m, A, -1))
+    m, A = fresh(); m.elem_type_item = np.array([351], np.int32); cases.append((m, A, -1))
+    # valid ids, but the pair (1, n_node) is not an edge of the matrix graph the structure was built from
+    m, A = fresh(); m.elem_node_item = m.elem_node_item.copy(); m.elem_node_item[0] = m.n_node; cases.append((m, A, -5))
+    for m, A, code in cases:
+        with pytest.raises(FistrB200Error) as ei:
+            gpu.fstr_StiffMatrix(m, A, to_host=False)
+        assert ei.value.code == code, (ei.value.code, code, str(ei.value))
+    # and the library is fine afterwards
+    mesh = util.distort(meshgen.hex_cube(3))
+    A = util.product_problem(gpu, mesh, util.cube_cnt(), to_host=True)
+    assert gpu.hecmw_solve(mesh, A)["error"] == 0
+
+
 def test_structure_size_limits(gpu):
     """Maximum sizes: blocks are addressed by 32-bit slots ([D | AL | AU], csrc/assembly.cuh), so a structure with
     NP + NPL + NPU >= 2^32 - 2 is refused before anything is allocated; so are negative / inconsistent sizes."""
@@ -413,6 +444,29 @@ def test_structure_size_limits(gpu):
         rc = L.fistr_b200_mat_structure(N, NP, NPL, NPU, ip_, ip_, ip_, ip_, 0, None, None, None, None, None)
         assert rc == -1, (N, NP, NPL, NPU, rc)
     assert b"32-bit slots" in L.fistr_b200_last_error() or b"bad sizes" in L.fistr_b200_last_error()
+    # a malformed graph or halo table is refused before it reaches a kernel: column out of range, L entry above the
+    # diagonal, unsorted row, index array that does not end at NPL, import entry that names an internal node
+    from frontistr_b200._lib import FistrB200Error
+    m0 = meshgen.hex_cube(2)
+    A0 = gpu.hecmw_mat_con(m0)
+
+    def declare(A_, m_):
+        A_.fstr_mat_init().hecMAT_init()
+        gpu.mat_structure(m_, A_)
+    bad = []
+    Ab = A0.copy(); Ab.itemL = A0.itemL.copy(); Ab.itemL[3] = A0.NP + 7; bad.append((Ab, m0))
+    Ab = A0.copy(); Ab.itemL = A0.itemL.copy(); Ab.itemL[0] = A0.NP; bad.append((Ab, m0))
+    Ab = A0.copy(); Ab.itemU = A0.itemU.copy(); Ab.itemU[[0, 1]] = Ab.itemU[[1, 0]]; bad.append((Ab, m0))
+    Ab = A0.copy(); Ab.indexU = A0.indexU.copy(); Ab.indexU[-1] -= 1; bad.append((Ab, m0))
+    from frontistr_b200 import partition
+    mh = partition.local_mesh(m0, partition.rcb_domains(m0, "x"), 0, 2)
+    mb = partition.local_mesh(m0, partition.rcb_domains(m0, "x"), 0, 2); mb.import_item = mb.import_item.copy(); mb.import_item[0] = 1
+    bad.append((gpu.hecmw_mat_con(mb), mb))
+    for Ab, mb_ in bad:
+        with pytest.raises(FistrB200Error) as ei:
+            declare(Ab, mb_)
+        assert ei.value.code == -1 and "mat_structure" in str(ei.value)
+    declare(gpu.hecmw_mat_con(mh), mh)            # the untouched local mesh of rank 0 is accepted
     # the library is still usable afterwards
     mesh = meshgen.hex_cube(2)
     A = util.product_problem(gpu, mesh, util.cube_cnt(), to_host=True)
