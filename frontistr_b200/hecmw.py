@@ -338,7 +338,7 @@ def hecmw_solve(hecMESH, hecMAT, device_resident: bool = False):
                                m.n_neighbor_pe, ip(c["nb"]), ip(c["ii"]), ip(c["it"]), ip(c["ei"]), ip(c["et"]),
                                m.my_rank, m.PETOT, C.byref(it), C.byref(rs), dp(times))
     check(rc, allow_solver_codes=True)
-    hist = np.zeros(max(int(A.Iarray[0]), 1))
+    hist = np.zeros(max(min(int(A.Iarray[0]), 1 << 22), 1))      # the library keeps at most 4 Mi entries
     nh = L.fistr_b200_solve_history(dp(hist), len(hist))
     r2 = C.c_double()
     L.fistr_b200_solve_resid2(C.byref(r2))

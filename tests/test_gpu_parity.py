@@ -307,6 +307,10 @@ def test_solver_status_codes(gpu):
     Nn = A.copy(); Nn.D *= -1; Nn.AL *= -1; Nn.AU *= -1
     r = gpu.hecmw_solve(mesh, Nn)
     assert r["error"] in (3002, 3003) and Nn.Iarray[81] == 1
+    # NIER set to "unlimited" must not cost a history buffer of that size
+    Big = A.copy(); Big.Iarray[0] = 2 ** 31 - 1
+    r = gpu.hecmw_solve(mesh, Big)
+    assert r["error"] == 0 and Big.Iarray[80] == 1 and len(r["hist"]) == r["iter"]
     # zero diagonal entry -> 2001
     Zd = A.copy(); Zd.D[4] = 0.0
     r = gpu.hecmw_solve(mesh, Zd)
