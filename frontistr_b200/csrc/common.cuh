@@ -205,7 +205,7 @@ struct DevBuf {
 
 // CUDA events that are destroyed on every exit path of the function that made them
 struct EventSet {
-  static const int kMax = 8;
+  static const int kMax = 24;
   cudaEvent_t ev[kMax];
   int n = 0;
   EventSet() = default;

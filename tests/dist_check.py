@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--partition", default="rcb", choices=["rcb", "kmetis", "pmetis"])
     ap.add_argument("--empty-last-rank", action="store_true", help="the last rank owns no node at all (N = NP = 0): the mesh is "
                     "split over world-1 domains with KMETIS (or RCB if world-1 is 2 / 4)")
+    ap.add_argument("--timelog", type=int, default=0, help="TIMELOG of the !SOLVER card: 1 YES, 2 VERBOSE (statistics over the ranks)")
     ap.add_argument("--scaling", action="store_true", help="!SOLVER SCALING=YES (Iarray(7) = 1): the scale vector is halo-exchanged")
     ap.add_argument("--tet", type=int, default=0)
     ap.add_argument("--precond", type=int, default=3)
@@ -69,6 +70,7 @@ def main():
     cnt = util.cube_cnt(tol=args.tol, precond=args.precond, iterpremax=args.iterpremax)
     A = util.product_problem(hecmw, m, cnt, to_host=False)
     A.Iarray[6] = 1 if args.scaling else 0
+    A.Iarray[21] = args.timelog
     r = hecmw.hecmw_solve(m, A, device_resident=True)
     # halo consistency: X on external nodes must equal the owner's value (hecmw_update_m_R at CG exit)
     xg = torch.zeros(3 * gmesh.n_node, dtype=torch.float64, device=dev)
