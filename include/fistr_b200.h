@@ -172,7 +172,9 @@ int fistr_b200_mat_ass_bc(int nbc, const int *inode, const int *idof, const doub
  *             them within an ulp or two of their values).
  *   USEJAD  : Iarray(33) != 0 returns 1001: the library always multiplies from its own private SELL copy.
  * Collective over all ranks of the communicator.  time_out[5] = set-up, solver, comm, matvec seconds
- * (the TIMELOG summary, Iterative.f90:192-208; matvec = sampled CUDA-event SpMV time x iterations) and
+ * (the TIMELOG summary, Iterative.f90:192-208; comm / matvec / precond = CUDA-event times of the sampled iterations x
+ * iterations, measured when TIMELOG or the "time_ax" option asks; TIMELOG = 2 (VERBOSE) prints max / min / avg / std dev
+ * of set-up and solver time over the ranks and reports the maxima, CG.f90:132-145,296-310) and
  * [4] = CUDA-event time of the whole call on the library stream, H2D/D2H copies included. */
 int fistr_b200_solve_33(int N, int NP, int NPL, int NPU, const double *D, const double *AL,
                         const double *AU, const int *indexL, const int *itemL, const int *indexU,
