@@ -71,7 +71,7 @@ EXPORTED = [
     "fistr_b200_stiffmatrix_3d", "fistr_b200_mat_ass_bc", "fistr_b200_nl_state_reset",
     "fistr_b200_nl_state_download", "fistr_b200_nl_stiffmatrix_3d", "fistr_b200_nl_update_3d", "fistr_b200_update_3d",
     "fistr_b200_nodal_stress_3d", "fistr_b200_solve_33",
-    "fistr_b200_solve_history", "fistr_b200_solve_resid2", "fistr_b200_solve_profile", "fistr_b200_matvec_33",
+    "fistr_b200_solve_history", "fistr_b200_solve_resid2", "fistr_b200_solve_profile", "fistr_b200_matvec_33", "fistr_b200_matresid_33",
     "fistr_b200_matvec_bench", "fistr_b200_precond_33_setup", "fistr_b200_precond_33_apply",
     "fistr_b200_precond_33_clear", "fistr_b200_precond_33_info", "fistr_b200_update_3_R",
     "fistr_b200_launch_count", "fistr_b200_device_info", "fistr_b200_fp64_peak",

@@ -360,6 +360,16 @@ def hecmw_matvec(X: np.ndarray, n_internal3: int) -> np.ndarray:
     return y
 
 
+def hecmw_matresid(X: np.ndarray, B, n_internal3: int):
+    """hecmw_matresid + hecmw_rel_resid_L2: (R = B - A X on the owned rows, sqrt(r.r / b.b)); B = None: the resident RHS."""
+    x = np.ascontiguousarray(X, np.float64)
+    b = None if B is None else np.ascontiguousarray(B, np.float64)
+    r = np.zeros(n_internal3)
+    rel = C.c_double()
+    check(_lib.lib().fistr_b200_matresid_33(dp(x), dp(b) if b is not None else None, dp(r), C.byref(rel)))
+    return r, rel.value
+
+
 def matvec_bench(nrep=20, flush_l2=False):
     a, b = C.c_double(), C.c_double()
     check(_lib.lib().fistr_b200_matvec_bench(int(nrep), int(flush_l2), C.byref(a), C.byref(b)))

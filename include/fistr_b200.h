@@ -205,6 +205,10 @@ int fistr_b200_solve_resid2(double *resid2);
  * halo exchange of X then Y(1:3N) = A X.  Uses the device-resident matrix; X is read for 3*NP
  * values (halo part overwritten by the exchange when petot>1), Y receives 3*N values. */
 int fistr_b200_matvec_33(const double *X, double *Y);
+/* ---- hecmw_matresid (las/hecmw_solver_las.f90:105-122, las_33.f90:358-380) and hecmw_rel_resid_L2 (las.f90:129-158):
+ * halo exchange of X, R(1:3N) = B - A X, *rel_resid = sqrt(r.r / b.b) over all ranks (b.b == 0 counts as 1).
+ * B == NULL uses the device-resident right-hand side; R and rel_resid may be NULL.  Collective. */
+int fistr_b200_matresid_33(const double *X, const double *B, double *R, double *rel_resid);
 /* SpMV micro-benchmark on the resident matrix: nrep launches, x_i = sin(i); returns mean ms/launch */
 int fistr_b200_matvec_bench(int nrep, int flush_l2, double *ms_mean, double *ms_min);
 

@@ -125,6 +125,27 @@ def test_spmv_bitwise(gpu, name, variant):
     assert np.array_equal(y, yo)
 
 
+@pytest.mark.parametrize("name", ["hex5_ic", "tet3"])
+def test_matresid_and_rel_resid_L2(gpu, name):
+    """hecmw_matresid / hecmw_rel_resid_L2 (las_33.f90:358-415) as entry points of their own: R = B - A X bit-identical to
+    B minus the oracle's matvec (same accumulation order, same subtraction), the relative residual to 1e-14; with the
+    resident right-hand side and with one passed in; zero right-hand side -> norm 1."""
+    from oracle import oracle as orc
+    mesh = _meshes()[name]()
+    cnt = util.cube_cnt()
+    A = util.product_problem(gpu, mesh, cnt, to_host=True)
+    n3 = 3 * A.N
+    x = np.cos(0.7 * np.arange(1, 3 * A.NP + 1, dtype=float)); b2 = np.sin(np.arange(1, 3 * A.NP + 1, dtype=float))
+    y = orc.matvec(A, x)                 # the oracle's SpMV on the very matrix that is resident on the device
+    for b_arg, b in ((None, A.B), (b2, b2)):
+        r, rel = gpu.hecmw_matresid(x, b_arg, n3)
+        assert np.array_equal(r, b[:n3] - y[:n3])
+        want = np.sqrt(np.dot(r, r) / np.dot(b[:n3], b[:n3]))
+        assert abs(rel - want) <= 1e-14 * want
+    r, rel = gpu.hecmw_matresid(x, np.zeros(3 * A.NP), n3)
+    assert np.array_equal(r, -y[:n3]) and abs(rel - np.sqrt(np.dot(y[:n3], y[:n3]))) <= 1e-14 * rel
+
+
 def test_precond_diag_bitwise(gpu):
     from oracle import oracle as orc
     mesh = util.distort(meshgen.hex_cube(5))
