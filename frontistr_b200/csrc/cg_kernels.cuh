@@ -292,6 +292,29 @@ cg_update_xr_kernel(int k, size_t n3, const double *__restrict__ p, const double
   }
 }
 
+// x += alpha p ; r -= alpha q ; rr ; z = r: the tail of an iteration whose preconditioner then works on z in place (fused
+// SSOR path, api_solver.inc) - the copy ZP = R of hecmw_precond_apply (precond.f90:91-96) rides on the update instead of
+// being a pass of its own
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+cg_update_xrz_kernel(int k, size_t n3, const double *__restrict__ p, const double *__restrict__ q,
+                     double *__restrict__ x, double *__restrict__ r, double *__restrict__ z, double *red, CgCtl *ctl,
+                     double *partial, unsigned int *counter) {
+  if (ctl->phase != 0) return;
+  double alpha;
+  if (!cg_alpha_prologue(k, red, ctl, blockIdx.x == 0 && threadIdx.x == 0, red[RED_PQ], alpha)) return;
+  double acc[1] = {0.0};
+  for (size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x; i < n3; i += (size_t)gridDim.x * BLOCK) {
+    x[i] = fma(alpha, p[i], x[i]);
+    const double ri = fma(-alpha, q[i], r[i]);
+    r[i] = ri;
+    z[i] = ri;
+    acc[0] = fma(ri, ri, acc[0]);
+  }
+  double *out = red + 2 * ((k + 1) & 1);
+  grid_reduce<1, BLOCK>(acc, partial, counter, [=](double(&o)[1]) { out[0] = o[0]; });
+}
+
 // ---- small vector helpers for the generic preconditioner path (precond.f90:75-123, precond_33.f90:86-114)
 __global__ void vec_copy_zero_tail_kernel(size_t n_head, size_t n_all, const double *__restrict__ src,
                                           double *__restrict__ dst, const int *phase) {

@@ -238,14 +238,14 @@ __device__ __forceinline__ void ssor_block_solve(const double *__restrict__ alu,
   X1 = a0 * fma(-a1, X2, fma(-a2, X3, X1));
 }
 
-// one colour of the forward (FWD=true, SSOR_33.f90:300-352) or backward (:355-410) sweep
-template <bool FWD>
-__global__ void __launch_bounds__(256)
-ssor_sweep_kernel(int s0, int s1, const long long *__restrict__ slice_ptr, const int *__restrict__ slice_row0,
-                  const int *__restrict__ slice_nrow, const double *__restrict__ val,
-                  const int *__restrict__ col, const int *__restrict__ perm,
-                  const double *__restrict__ alu, size_t ld, double *zp, const int *phase) {
-  if (phase && *phase != 0) return;
+// one colour of the forward (FWD=true, SSOR_33.f90:300-352) or backward (:355-410) sweep; DOT: also r.z over the rows
+// this launch finishes (a row of the backward sweep holds its final z once its own colour has been swept)
+template <bool FWD, bool DOT>
+__device__ __forceinline__ void ssor_sweep_body(int s0, int s1, const long long *__restrict__ slice_ptr,
+                                                const int *__restrict__ slice_row0, const int *__restrict__ slice_nrow,
+                                                const double *__restrict__ val, const int *__restrict__ col,
+                                                const int *__restrict__ perm, const double *__restrict__ alu, size_t ld,
+                                                double *zp, const double *__restrict__ r, double &rz) {
   const int lane = threadIdx.x & 31;
   const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nw = (gridDim.x * blockDim.x) >> 5;
@@ -277,9 +277,41 @@ ssor_sweep_kernel(int s0, int s1, const long long *__restrict__ slice_ptr, const
     if (active) {
       ssor_block_solve(alu, ld, (size_t)inew, s1v, s2v, s3v);
       if (FWD) { zp[3 * iold] = s1v; zp[3 * iold + 1] = s2v; zp[3 * iold + 2] = s3v; }
-      else { zp[3 * iold] -= s1v; zp[3 * iold + 1] -= s2v; zp[3 * iold + 2] -= s3v; }
+      else if (!DOT) { zp[3 * iold] -= s1v; zp[3 * iold + 1] -= s2v; zp[3 * iold + 2] -= s3v; }
+      else {
+        const double z0 = zp[3 * iold] - s1v, z1 = zp[3 * iold + 1] - s2v, z2 = zp[3 * iold + 2] - s3v;
+        zp[3 * iold] = z0; zp[3 * iold + 1] = z1; zp[3 * iold + 2] = z2;
+        rz = fma(r[3 * iold], z0, rz); rz = fma(r[3 * iold + 1], z1, rz); rz = fma(r[3 * iold + 2], z2, rz);
+      }
     }
   }
+}
+
+template <bool FWD>
+__global__ void __launch_bounds__(256)
+ssor_sweep_kernel(int s0, int s1, const long long *__restrict__ slice_ptr, const int *__restrict__ slice_row0,
+                  const int *__restrict__ slice_nrow, const double *__restrict__ val,
+                  const int *__restrict__ col, const int *__restrict__ perm,
+                  const double *__restrict__ alu, size_t ld, double *zp, const int *phase) {
+  if (phase && *phase != 0) return;
+  double unused = 0.0;
+  ssor_sweep_body<FWD, false>(s0, s1, slice_ptr, slice_row0, slice_nrow, val, col, perm, alu, ld, zp, nullptr, unused);
+}
+
+// Backward sweep of one colour fused with the inner product that follows the preconditioner in hecmw_solve_CG
+// (RHO = r.z, CG.f90:160-168): the rows of this colour are final after this launch, so their share of r.z is summed here
+// (deterministic grid reduction) and added to the shares of the colours swept before (`accumulate`; launches of one
+// stream are ordered, so the sum over colours has a fixed order too).  Saves the separate dot-product pass over r and z.
+__global__ void __launch_bounds__(256)
+ssor_sweep_bwd_dot_kernel(int s0, int s1, const long long *__restrict__ slice_ptr, const int *__restrict__ slice_row0,
+                          const int *__restrict__ slice_nrow, const double *__restrict__ val,
+                          const int *__restrict__ col, const int *__restrict__ perm,
+                          const double *__restrict__ alu, size_t ld, double *zp, const double *__restrict__ r,
+                          double *partial, unsigned int *counter, double *rz_out, int accumulate, const int *phase) {
+  if (phase && *phase != 0) return;
+  double acc[1] = {0.0};
+  ssor_sweep_body<false, true>(s0, s1, slice_ptr, slice_row0, slice_nrow, val, col, perm, alu, ld, zp, r, acc[0]);
+  grid_reduce<1, 256>(acc, partial, counter, [=](double(&o)[1]) { *rz_out = accumulate ? *rz_out + o[0] : o[0]; });
 }
 
 }  // namespace fb

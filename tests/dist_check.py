@@ -36,6 +36,7 @@ def main():
                     "(tools/build_hostemu.py; NCCL and CUDA IPC are shared-memory stand-ins) and torch.distributed runs on gloo")
     ap.add_argument("--stress", action="store_true", help="also run the strain / stress recovery (update_3d + nodal_stress_3d) on "
                     "every rank and compare the internal nodes with the oracle's serial fstr_NodalStress3D")
+    ap.add_argument("--option", action="append", default=[], metavar="KEY=INT", help="fistr_b200_set_option on every rank (e.g. ssor_fused=1)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -56,6 +57,8 @@ def main():
     hecmw.init(0 if args.host else lr)
     hecmw.set_option("p2p", {"p2p": 2, "p2p-or-nccl": 1, "nccl": 0}[args.comm])   # 2 = fail loudly if peer memory cannot be mapped
     hecmw.comm_init_from_torch()
+    for kv in args.option:
+        hecmw.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     gmesh = meshgen.tet10_cube(args.tet) if args.tet else util.distort(meshgen.hex_cube(args.n))
     if args.empty_last_rank:
         nd = world - 1

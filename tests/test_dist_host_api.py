@@ -62,6 +62,15 @@ def test_collective_transport_ssor_2_ranks():
     assert "p2p_active=0" in lines[-1]
 
 
+def test_fused_ssor_iteration_4_ranks():
+    """Option ssor_fused on several ranks: (r.r, r.z) of an iteration travel in ONE all-reduce after the sweeps; a rank's
+    share of r.z is the sum over its own backward launches."""
+    lines = _torchrun(4, "dist_check.py", "--host", "--tet", "3", "--comm", "nccl", "--precond", "1", "--option", "ssor_fused=1")
+    assert "PASS" in lines[-1]
+    lines = _torchrun(3, "dist_check.py", "--host", "--hex", "5", "--comm", "nccl", "--precond", "1", "--empty-last-rank", "--option", "ssor_fused=1")
+    assert "PASS" in lines[-1]
+
+
 def test_two_preconditioner_sweeps_2_ranks():
     """iterPREmax = 2 (precond_33.f90:110-113): between the sweeps Z is halo-exchanged and ZP = R - A Z is formed on every rank;
     same iteration count as the oracle on the same two subdomains."""

@@ -199,8 +199,12 @@ def test_solve_golden_decks(gpu, name):
     # strings and KMETIS / PMETIS with 2..8 domains (tests/fb_util.py: oracle_iteration_spread; also
     # tests/test_oracle_units.py::test_iteration_count_spread_of_the_reference_algorithm).  The GPU count must lie
     # inside the reference's own spread (+-2); the residual history is pinned while the recurrences still agree.
+    # 26 executions sample the reference's range, they do not bound it: the oracle itself, run with 16 OpenMP threads on
+    # A342, has given 739 against a sampled 706..734.  The window is therefore the sampled range extended by its own width
+    # on either side (never less than +-2): zero-width samples (A361: every decomposition gives the same count) keep the
+    # north_star gate, chaotic ones get the room the reference algorithm takes for itself.
     counts = [ro["iter"]] + util.oracle_iteration_spread(mesh, cnt)
-    slack = 2
+    slack = max(2, max(counts) - min(counts))
     assert min(counts) - slack <= r["iter"] <= max(counts) + slack, (r["iter"], counts)
     if name == "A361":
         assert abs(r["iter"] - ro["iter"]) <= 2

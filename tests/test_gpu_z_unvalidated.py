@@ -373,6 +373,46 @@ def test_bilu0_auto_sigma_diag_loop(gpu, case):
 
 # (4b) !SOLVER SCALING=YES: symmetric diagonal scaling around the CG loop, csrc/scaling.cuh
 
+@pytest.mark.parametrize("ncolor", [10, 3])
+@pytest.mark.parametrize("meshname", ["hex12", "tet4"])
+def test_solve_ssor_fused_iteration(gpu, meshname, ncolor):
+    """Option ssor_fused: CG + SSOR x 1 sweep with the copy ZP = R folded into the x / r update, the sweeps on Z in place and
+    r.z summed by the backward launches - 2 ncolor + 3 launches per iteration instead of 2 ncolor + 6.  Same z bit for bit
+    (the sweeps are the same code on the same numbers), r.z in another summation order: parity gates of north_star against
+    the oracle, the unfused path's history to rounding, and the launch count itself."""
+    from oracle import oracle as orc
+    from frontistr_b200 import meshgen
+    mesh = util.distort(meshgen.hex_cube(12)) if meshname == "hex12" else meshgen.tet10_cube(4)
+    cnt = util.cube_cnt(tol=1e-10, precond=1)
+    runs = []
+    for fused in (0, 1):
+        A = util.product_problem(gpu, mesh, cnt, to_host=True)
+        A.Iarray[33] = ncolor                      # NCOLOR_IN
+        gpu.set_option("ssor_fused", fused)
+        c0 = gpu.launch_count()
+        try:
+            r = gpu.hecmw_solve(mesh, A)
+        finally:
+            gpu.set_option("ssor_fused", 0)
+        runs.append((r, A.X.copy(), gpu.launch_count() - c0))
+    (r0, x0, l0), (r1, x1, l1) = runs
+    nc = gpu.precond_info(A.N)[0]
+    Ao = util.oracle_problem(mesh, cnt)
+    Ao.Iarray[33] = ncolor
+    orc.precond_clear()
+    ro = orc.solve(mesh, Ao, hist_len=10000, ssor_threads=2)
+    assert r0["error"] == 0 and r1["error"] == 0 and ro["error"] == 0
+    assert r1["iter"] > 50 and abs(r1["iter"] - ro["iter"]) <= 2 and abs(r1["iter"] - r0["iter"]) <= 2
+    assert r1["resid2"] < 1e-10
+    assert util.rel_l2(x1[: 3 * A.N], Ao.X[: 3 * A.N]) <= 1e-9 and util.rel_l2(x1, x0) <= 1e-9
+    n = min(len(r0["hist"]), len(r1["hist"]))
+    assert np.allclose(r1["hist"][:40], r0["hist"][:40], rtol=1e-9)
+    assert np.allclose(r1["hist"][: n // 2], r0["hist"][: n // 2], rtol=1e-3)
+    if r0["iter"] == r1["iter"]:     # three launches fewer in every LAUNCHED iteration that is not a 1-in-50 recompute
+        it = r1["iter"]              # (iterations are queued in batches of cg_check_interval = 8: up to 7 no-op launches more)
+        assert (l0 - l1) % 3 == 0 and it - it // 50 <= (l0 - l1) // 3 <= it + 8, (l0, l1, it, nc)
+
+
 @pytest.mark.parametrize("precond", [3, 1, 10])
 @pytest.mark.parametrize("meshname", ["hex8_two_materials", "tet3"])
 def test_solve_with_scaling_matches_oracle(gpu, meshname, precond):
