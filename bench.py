@@ -62,7 +62,7 @@ def parse_args():
     ap.add_argument("--partition", default="rcb", choices=["rcb", "kmetis", "pmetis"],
                     help="N>1: METHOD of hecmw_part1's node-based decomposition.  rcb = x / xy / xyz bisection (the ideal 2x2x2 split "
                          "of a cube; needs N = 2, 4, 8); kmetis / pmetis = the reference's node graph through METIS 5 (any N)")
-    ap.add_argument("--comm", default="auto", choices=["auto", "p2p", "nccl"],
+    ap.add_argument("--comm", default="auto", choices=["auto", "p2p", "nccl", "nccl-zhalo"],
                     help="N>1 transport of the halo exchange + dot-product all-reduce: peer-memory stores issued by the CG "
                          "kernels (p2p) or NCCL.  auto = NCCL at every N: it is the transport whose kernels (the same ones as at "
                          "N = 1) have run on hardware at N = 2 and 8; the peer-memory kernels were reworked after their only "
@@ -70,7 +70,8 @@ def parse_args():
                          "(tests/test_dist_host_api.py, tests/test_p2p_kernels_emulated.py) - ask for them with --comm p2p after "
                          "tools/gpu_r2_p2p.sh has passed.  Two safety nets under p2p: the library itself stays on NCCL if the "
                          "arenas cannot be mapped on every rank, and a peer-memory wait that times out makes all ranks fall back "
-                         "to NCCL together (noted as comm_note in the line)")
+                         "to NCCL together (noted as comm_note in the line).  nccl-zhalo = NCCL with the z-halo schedule "
+                         "(csrc/cg_zhalo.cuh: 2 communication steps per iteration instead of 3; opt-in, never run on hardware)")
     return ap.parse_args()
 
 
@@ -263,6 +264,7 @@ def run_b200(args):
     if world > 1:
         use_p2p = args.comm == "p2p"      # auto = NCCL at every N: the peer-memory kernels of HEAD have not run on hardware
         hecmw.set_option("p2p", 1 if use_p2p else 0)
+        hecmw.set_option("comm_zhalo", 1 if args.comm == "nccl-zhalo" else 0)
         hecmw.comm_init_from_torch()
     dev = hecmw.device_info()
 
@@ -441,7 +443,8 @@ def run_b200(args):
                           "partition": "none" if world == 1 else (
                               ("RCB-%s" % {2: "x", 4: "xy", 8: "xyz"}[world]) if getattr(args, "partition", "rcb") == "rcb"
                               else args.partition.upper() + " (METIS 5)") + ", node-based, in-process hecmw_part1, 1 subdomain/GPU",
-                          "comm": "none" if world == 1 else ("p2p" if hecmw.get_option("p2p_active") == 1 else "nccl"),
+                          "comm": "none" if world == 1 else ("p2p" if hecmw.get_option("p2p_active") == 1 else
+                                                            ("nccl-zhalo" if hecmw.get_option("comm_zhalo") == 1 else "nccl")),
                           **({"comm_note": comm_note} if comm_note else {}),
                           **({"workload_note": workload_note} if workload_note else {}),
                           "l2": "inputs larger than L2: %.2f GB matrix streamed per SpMV per GPU vs 126 MB L2"

@@ -9,6 +9,7 @@
 #include "assembly.cuh"
 #include "bilu.cuh"
 #include "cg_kernels.cuh"
+#include "cg_zhalo.cuh"
 #include "comm.hpp"
 #include "common.cuh"
 #include "matcon.hpp"
@@ -72,6 +73,7 @@ struct Context {
 
   // ---- reductions / control
   DevBuf<double> red, partial, hist;
+  DevBuf<double> rtab;     // z-halo schedule (cg_zhalo.cuh): every rank's (r.r, r.z) partials, [parity][rank][2]
   DevBuf<unsigned> counter;
   DevBuf<CgCtl> ctl;
   DevBuf<int> flag;
@@ -127,6 +129,7 @@ struct Context {
   Nccl nccl;
   ncclComm_t_ comm = nullptr;
   int rank = 0, petot = 1;
+  int64_t comm_steps = 0;   // NCCL communication steps issued so far (grouped send/recv or all-reduce): read-out "comm_steps"
 
   int64_t get(const char *k, int64_t dflt) const {
     auto it = opt.find(k);

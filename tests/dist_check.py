@@ -74,7 +74,9 @@ def main():
     A = util.product_problem(hecmw, m, cnt, to_host=False)
     A.Iarray[6] = 1 if args.scaling else 0
     A.Iarray[21] = args.timelog
+    cs0 = hecmw.get_option("comm_steps")
     r = hecmw.hecmw_solve(m, A, device_resident=True)
+    comm_steps = hecmw.get_option("comm_steps") - cs0
     # halo consistency: X on external nodes must equal the owner's value (hecmw_update_m_R at CG exit)
     xg = torch.zeros(3 * gmesh.n_node, dtype=torch.float64, device=dev)
     own = torch.from_numpy(m.global_node_ID[: m.nn_internal].astype(np.int64) - 1).to(dev)
@@ -127,9 +129,9 @@ def main():
             serr = float(np.abs(sg.cpu().numpy() - ref).max() / np.abs(ref).max())
             ok = ok and serr <= 1e-10
             print("     nodal strain / stress / Mises on the partitioned mesh vs serial oracle: max rel dev %.2e" % serr, flush=True)
-        print("%s dist_check world=%d comm=%s%s mesh=%s precond=%d: iter gpu=%d oracle=%d  rel_l2=%.2e  resid2=%.2e  halo_err=%.1e  neighbors=%d"
+        print("%s dist_check world=%d comm=%s%s mesh=%s precond=%d: iter gpu=%d oracle=%d  rel_l2=%.2e  resid2=%.2e  halo_err=%.1e  neighbors=%d  comm_steps/iter=%.2f"
               % ("PASS" if ok else "FAIL", world, args.comm, (" p2p_active=%d" % hecmw.get_option("p2p_active")) + (" HOST-EMULATION" if args.host else ""), ("tet%d" % args.tet) if args.tet else ("hex%d" % args.n), args.precond,
-                 r["iter"], ro["iter"], err, r["resid2"], float(t.item()), m.n_neighbor_pe), flush=True)
+                 r["iter"], ro["iter"], err, r["resid2"], float(t.item()), m.n_neighbor_pe, comm_steps / max(r["iter"], 1)), flush=True)
     hecmw.comm_finalize()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

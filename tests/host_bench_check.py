@@ -51,7 +51,7 @@ def main():
         bench.run_b200(args)
     if int(os.environ["RANK"]) == 0:
         d = json.loads([ln for ln in buf.getvalue().splitlines() if ln.startswith("{")][-1])
-        want = "p2p" if a.comm == "p2p" else "nccl"   # auto: the transport whose kernels have run on hardware
+        want = a.comm if a.comm in ("p2p", "nccl-zhalo") else "nccl"   # auto: the transport whose kernels have run on hardware
         gave_up = os.environ.get("FB_EMUL_P2P_TIMEOUT") is not None and want == "p2p"
         if gave_up:      # injected time-outs: the run must have fallen back to NCCL collectively and still produced its line
             want = "nccl"

@@ -62,6 +62,23 @@ def test_collective_transport_ssor_2_ranks():
     assert "p2p_active=0" in lines[-1]
 
 
+def _steps_per_iter(line):
+    return float(line.split("comm_steps/iter=")[1].split()[0])
+
+
+def test_zhalo_schedule_two_communication_steps_per_iteration():
+    """Option comm_zhalo of the collective transport (csrc/cg_zhalo.cuh): the export rows of z travel with the (r.r, r.z)
+    partials in one grouped send/recv, p = z + beta p runs over all NP rows - parity against the oracle as on every other
+    transport, and 2 communication steps per iteration (+ the 1-in-50 true-residual iterations) where the default makes 3."""
+    base = _torchrun(4, "dist_check.py", "--host", "--hex", "9", "--comm", "nccl")
+    assert "PASS" in base[-1] and 2.9 < _steps_per_iter(base[-1]) < 3.4
+    for world, args in ((8, ("--hex", "9")), (4, ("--tet", "3")), (3, ("--hex", "7", "--partition", "kmetis")),
+                        (3, ("--hex", "5", "--empty-last-rank"))):
+        lines = _torchrun(world, "dist_check.py", "--host", "--comm", "nccl", "--option", "comm_zhalo=1", *args)
+        assert "PASS" in lines[-1] and "p2p_active=0" in lines[-1]
+        assert 1.9 < _steps_per_iter(lines[-1]) < 2.4, lines[-1]
+
+
 def test_fused_ssor_iteration_4_ranks():
     """Option ssor_fused on several ranks: (r.r, r.z) of an iteration travel in ONE all-reduce after the sweeps; a rank's
     share of r.z is the sum over its own backward launches."""
@@ -85,7 +102,7 @@ def test_bilu0_2_ranks():
     assert "precond=10" in lines[-1]
 
 
-@pytest.mark.parametrize("world,comm,inject", [(2, "auto", False), (4, "auto", False), (8, "p2p", True)])
+@pytest.mark.parametrize("world,comm,inject", [(2, "auto", False), (4, "auto", False), (8, "p2p", True), (4, "nccl-zhalo", False)])
 def test_bench_flow_multi_rank(world, comm, inject):
     """bench.py's multi-rank flow (partition, set-up, device-resident and end-to-end arms, max-over-ranks timing, JSON
     line of rank 0).  inject: every peer-memory wait that has to spin times out at once — all ranks must learn of it at
