@@ -229,24 +229,32 @@ __device__ __forceinline__ bool cg_alpha_prologue(int k, const double *red, CgCt
 
 // Fused tail of iteration k for PRECOND=3, iterPREmax=1:
 //   x += alpha p ; r -= alpha q ; rr = r.r ; z = Minv r ; rz = r.z        (CG.f90:219-240 + :160-168)
-template <int BLOCK>
+// PEER = true: the instantiation of the peer-memory transport (p.q taken from / (r.r, r.z) published to the peer tables
+// when the launch's P2PArgs say so).  PEER = false (one GPU, NCCL) contains none of it - in particular not the 240-byte
+// copy of the P2PView into every thread's stack frame that the by-value capture of the publication costs.
+template <int BLOCK, bool PEER = false>
 __global__ void __launch_bounds__(BLOCK)
 cg_fused_update_kernel(int k, int N, const double *__restrict__ p, const double *__restrict__ q,
                        double *__restrict__ x, double *__restrict__ r, double *__restrict__ z,
                        const double *__restrict__ alu, size_t ld, double *red, CgCtl *ctl,
-                       double *partial, unsigned int *counter, P2PView pv, P2PArgs a) {
+                       double *partial, unsigned int *counter, const __grid_constant__ P2PView pv, P2PArgs a) {
   if (ctl->phase != 0) return;
-  double alpha, c1;
-  if (a.consume_seq) {        // p.q = sum over all ranks' partials (peer table), block-uniform
-    __shared__ double s_pq;
-    if (threadIdx.x < 32) {
-      double s0, s1;
-      p2p_consume_warp(pv, P2P_Q_PQ, a.consume_seq, s0, s1);
-      if (threadIdx.x == 0) s_pq = s0;
+  double alpha, c1 = 0.0;
+  bool from_table = false;
+  if constexpr (PEER) {
+    if (a.consume_seq) {        // p.q = sum over all ranks' partials (peer table), block-uniform
+      __shared__ double s_pq;
+      if (threadIdx.x < 32) {
+        double s0, s1;
+        p2p_consume_warp(pv, P2P_Q_PQ, a.consume_seq, s0, s1);
+        if (threadIdx.x == 0) s_pq = s0;
+      }
+      __syncthreads();
+      c1 = s_pq;
+      from_table = true;
     }
-    __syncthreads();
-    c1 = s_pq;
-  } else c1 = red[RED_PQ];
+  }
+  if (!from_table) c1 = red[RED_PQ];
   if (!cg_alpha_prologue(k, red, ctl, blockIdx.x == 0 && threadIdx.x == 0, c1, alpha)) return;
   double acc[2] = {0.0, 0.0};
   for (size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x; i < (size_t)N; i += (size_t)gridDim.x * BLOCK) {
@@ -261,10 +269,15 @@ cg_fused_update_kernel(int k, int N, const double *__restrict__ p, const double 
     acc[1] = fma(r0, a, acc[1]); acc[1] = fma(r1, b, acc[1]); acc[1] = fma(r2, c, acc[1]);
   }
   double *out = red + 2 * ((k + 1) & 1);
-  grid_reduce<2, BLOCK, true>(acc, partial, counter, [=](double(&o)[2]) {
-    if (a.publish_seq) p2p_publish_warp(pv, P2P_Q_RRRZ, a.publish_seq, o[0], o[1]);
-    else if (threadIdx.x == 0) { out[0] = o[0]; out[1] = o[1]; }
-  });
+  if constexpr (PEER) {
+    const P2PView *ppv = &pv;   // (__grid_constant__: an address in the constant bank, no per-thread copy of the table)
+    grid_reduce<2, BLOCK, true>(acc, partial, counter, [=](double(&o)[2]) {
+      if (a.publish_seq) p2p_publish_warp(*ppv, P2P_Q_RRRZ, a.publish_seq, o[0], o[1]);
+      else if (threadIdx.x == 0) { out[0] = o[0]; out[1] = o[1]; }
+    });
+  } else {
+    grid_reduce<2, BLOCK>(acc, partial, counter, [=](double(&o)[2]) { out[0] = o[0]; out[1] = o[1]; });
+  }
 }
 
 // x += alpha p only (iterations where r is recomputed from b - A x, CG.f90:227-233), or

@@ -182,26 +182,33 @@ spmv_sell1_kernel(int N, int nslice, const long long *__restrict__ slice_ptr,
 // by OTHER GPUs while this kernel runs, so the slices that read them must not take x through the non-coherent L1 /
 // read-only path the compiler picks for `const __restrict__` data (an interior warp of the same SM may have pulled the
 // sector that straddles rows N-1 | N before the neighbour's store landed).  Those slices gather x with ld.global.cg
-// (L2, the point of coherence for peer stores) after their acquire on the neighbours' flags.  PEER = false compiles to
-// exactly the kernel that was measured in round 1.
+// (L2, the point of coherence for peer stores) after their acquire on the neighbours' flags.  PEER = false (one GPU, NCCL)
+// contains no peer-memory code at all: the wait, the publication and - what they cost every thread even when never
+// taken - the copy of the P2PView / P2PNeighbors tables into a 280-byte stack frame are compiled out (`if constexpr`;
+// checked with cuobjdump: STACK:0, no STL / LDL).
 template <int MODE, int BLOCK, bool PEER = false>
 __global__ void __launch_bounds__(BLOCK)
 spmv_sell2_kernel(int N, int nslice, const long long *__restrict__ slice_ptr,
                   const double *__restrict__ val, const int *__restrict__ col,
                   const double *__restrict__ x, const double *__restrict__ b, double *__restrict__ y,
                   double *partial, unsigned int *counter, double *red_out, const int *phase,
-                  P2PView pv, P2PNeighbors nb, P2PArgs a, const unsigned char *__restrict__ halo_slice,
-                  const int *__restrict__ rowperm) {
+                  const __grid_constant__ P2PView pv, const __grid_constant__ P2PNeighbors nb, P2PArgs a,
+                  const unsigned char *__restrict__ halo_slice, const int *__restrict__ rowperm) {
   if (phase && *phase != 0) return;
   const int lane = threadIdx.x & 31;
   const int wg = (blockIdx.x * BLOCK + threadIdx.x) >> 5;
   const int nw = (gridDim.x * BLOCK) >> 5;
   double dot[1] = {0.0};
+  // (the peer tables are __grid_constant__ parameters: they are indexed, and their address is captured by the publication
+  // below, in the constant bank - not through a per-thread copy in local memory)
   // peer-memory mode: the neighbours store their export values of x straight into our halo rows; only a warp
   // about to process a slice that reads halo columns waits for their flags — interior slices overlap the exchange
-  bool halo_ready = (a.halo_seq == 0);
+  // (PEER = false carries none of this: no wait, no publication, no copy of the peer tables into the thread's stack frame)
+  bool halo_ready = !PEER || (a.halo_seq == 0);
   for (int s = wg; s < nslice; s += nw) {
-    if (!halo_ready && halo_slice[s]) { p2p_wait_halo_warp(pv, nb, a.halo_seq); halo_ready = true; }
+    if constexpr (PEER) {
+      if (!halo_ready && halo_slice[s]) { p2p_wait_halo_warp(pv, nb, a.halo_seq); halo_ready = true; }
+    }
     const bool via_l2 = PEER && halo_slice[s];
     const long long p0 = slice_ptr[s], p1 = slice_ptr[s + 1];
     const double2 *v = reinterpret_cast<const double2 *>(val) + p0 * 288 + lane;
@@ -241,10 +248,15 @@ spmv_sell2_kernel(int N, int nslice, const long long *__restrict__ slice_ptr,
       y[r3] = y0; y[r3 + 1] = y1; y[r3 + 2] = y2;
     }
   }
-  grid_reduce<1, BLOCK, true>(dot, partial, counter, [=](double(&o)[1]) {
-    if (a.publish_seq) p2p_publish_warp(pv, P2P_Q_PQ, a.publish_seq, o[0], 0.0);
-    else if (red_out && threadIdx.x == 0) *red_out = o[0];
-  });
+  if constexpr (PEER) {
+    const P2PView *ppv = &pv;
+    grid_reduce<1, BLOCK, true>(dot, partial, counter, [=](double(&o)[1]) {
+      if (a.publish_seq) p2p_publish_warp(*ppv, P2P_Q_PQ, a.publish_seq, o[0], 0.0);
+      else if (red_out && threadIdx.x == 0) *red_out = o[0];
+    });
+  } else {
+    grid_reduce<1, BLOCK>(dot, partial, counter, [=](double(&o)[1]) { if (red_out) *red_out = o[0]; });
+  }
 }
 
 // variant 0: no private copy — one thread per scalar row straight on D/AL/AU (same accumulation

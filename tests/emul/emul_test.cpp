@@ -535,16 +535,12 @@ int fbemul_p2p_cg(int R, const int *N, const int *NP, const double *const *D, co
                            nexp, exp_item[me], K.sendbuf.data(), pv, nb, ap, (const int *)K.exp_peer.data(), (const int *)K.exp_remote.data(),
                            K.counter.data() + 1);
         jitter();
-        if (peer_kernel)
-          emul_launch_blocks(gsp, BLOCK, spmv_sell2_kernel<0, BLOCK, true>, n, K.nslice, (const long long *)K.sp.data(), (const double *)val,
-                             (const int *)col, (const double *)P, (const double *)nullptr, K.Q.data(), K.partial.data(), K.counter.data(),
-                             red + RED_PQ, (const int *)phase, pv, nb, as, (const unsigned char *)K.halo_slice.data(), rp);
-        else
-          emul_launch_blocks(gsp, BLOCK, spmv_sell2_kernel<0, BLOCK, false>, n, K.nslice, (const long long *)K.sp.data(), (const double *)val,
-                             (const int *)col, (const double *)P, (const double *)nullptr, K.Q.data(), K.partial.data(), K.counter.data(),
-                             red + RED_PQ, (const int *)phase, pv, nb, as, (const unsigned char *)K.halo_slice.data(), rp);
+        (void)peer_kernel;   // (the PEER = false instantiations carry no peer-memory code since round 2: they cannot run this loop)
+        emul_launch_blocks(gsp, BLOCK, spmv_sell2_kernel<0, BLOCK, true>, n, K.nslice, (const long long *)K.sp.data(), (const double *)val,
+                           (const int *)col, (const double *)P, (const double *)nullptr, K.Q.data(), K.partial.data(), K.counter.data(),
+                           red + RED_PQ, (const int *)phase, pv, nb, as, (const unsigned char *)K.halo_slice.data(), rp);
         jitter();
-        emul_launch_blocks(gnode, BLOCK, cg_fused_update_kernel<BLOCK>, k, n, (const double *)P, (const double *)K.Q.data(), K.X.data(),
+        emul_launch_blocks(gnode, BLOCK, cg_fused_update_kernel<BLOCK, true>, k, n, (const double *)P, (const double *)K.Q.data(), K.X.data(),
                            K.R.data(), K.Z.data(), (const double *)K.alu.data(), (size_t)n, red, &K.ctl, K.partial.data(), K.counter.data(), pv, af);
         pending = af.publish_seq;
       }

@@ -37,6 +37,7 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __restrict__
+#define __grid_constant__
 #define __shared__ static thread_local   /* one block at a time per host thread (= per emulated GPU) */
 
 struct int2 { int x, y; };

@@ -1,6 +1,9 @@
 // TEST-ONLY: implementation of the execution models behind kernel_emul.hpp.  Included by exactly one translation unit
 // per shared library (emul_test.cpp for libfistr_b200_emul.so, the rewritten capi.cu for libfistr_b200_hostemu.so).
 #pragma once
+#include <map>
+#include <mutex>
+#include <string>
 #include <pthread.h>
 #include <sys/mman.h>
 #include <unistd.h>
@@ -297,10 +300,26 @@ struct EmulSmem {
   unsigned char *fresh() { memset(user, 0xFF, bytes); return user; }
 };
 
+// every launch configuration the library has used in this process, per kernel as named at the launch site: the largest
+// block, dynamic shared memory and grid (tests/test_gpu_suite_on_host_api.py holds them against the resource usage of the
+// kernels nvcc compiled for sm_100a - registers x threads, shared-memory opt-in - which no CPU run can exercise)
+struct EmulLaunchStat { unsigned block = 0, grid = 0; size_t smem = 0; long long count = 0; };
+inline std::map<std::string, EmulLaunchStat> &emul_launch_log() { static std::map<std::string, EmulLaunchStat> m; return m; }
+
 struct EmulCfg {
   unsigned grid, block;
   size_t smem;
   EmulCfg(long long g, long long b, size_t s = 0, cudaStream_t = nullptr) : grid((unsigned)g), block((unsigned)b), smem(s) {}
+  template <class F>
+  void launch(const char *name, F body) const {
+    {
+      static std::mutex mu;
+      std::lock_guard<std::mutex> lk(mu);
+      EmulLaunchStat &st = emul_launch_log()[name];
+      st.block = std::max(st.block, block); st.grid = std::max(st.grid, grid); st.smem = std::max(st.smem, smem); st.count++;
+    }
+    launch(body);
+  }
   template <class F>
   void launch(F body) const {
     // what the CUDA runtime would refuse at launch ("invalid configuration argument" / "too much shared data")
@@ -320,6 +339,16 @@ struct EmulCfg {
   }
 };
 }  // namespace fb
+
+// "name\tblock\tsmem\tgrid\tcount\n" per kernel launched so far; returns the length needed (call again with a larger buffer)
+extern "C" int fbemul_launch_log(char *buf, int len) {
+  std::string out;
+  for (const auto &kv : fb::emul_launch_log())
+    out += kv.first + "\t" + std::to_string(kv.second.block) + "\t" + std::to_string(kv.second.smem) + "\t" +
+           std::to_string(kv.second.grid) + "\t" + std::to_string(kv.second.count) + "\n";
+  if (buf && len > 0) { strncpy(buf, out.c_str(), (size_t)len - 1); buf[len - 1] = 0; }
+  return (int)out.size() + 1;
+}
 
 // order in which the runnable fibers of a block are scheduled (see run_fiber_block): 0 ascending, 1 descending, 2 random
 extern "C" void fbemul_set_fiber_order(int mode, unsigned long long seed) {

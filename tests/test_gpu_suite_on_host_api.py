@@ -241,3 +241,80 @@ def test_bench_falls_back_on_a_real_allocation_failure(host_api, monkeypatch, ca
     assert "fell back to H5" in d["config"]["workload_note"] and "out of memory" in d["config"]["workload_note"]
     assert d["config"]["workload"].startswith("H5:") and d["value"] > 0 and d["resid_true"] < 1.0e-8
     host_api.finalize(); host_api.init(0)
+
+
+def _compiled_kernel_resources():
+    """{kernel base name: [(demangled name, registers, static shared bytes, local bytes, launch-bound threads or None)]} of the
+    PRODUCT library as nvcc compiled it for sm_100a (cuobjdump --dump-resource-usage; launch bounds from the sources)."""
+    import re
+    import subprocess
+
+    import __graft_entry__ as g
+    so = g.build_product()
+    txt = subprocess.run(["cuobjdump", "--dump-resource-usage", so], capture_output=True, text=True, check=True).stdout
+    names = re.findall(r"Function (\S+):", txt)
+    usage = re.findall(r"REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", txt)
+    assert names and len(names) == len(usage)
+    dem = subprocess.run(["cu++filt"] + names, capture_output=True, text=True, check=True).stdout.splitlines()
+    # __launch_bounds__ of every kernel, from the sources (template arguments of the bound are resolved per launch below)
+    bounds = {}
+    src_dir = os.path.join(ROOT, "frontistr_b200", "csrc")
+    for f in os.listdir(src_dir):
+        with open(os.path.join(src_dir, f)) as fh:
+            s = fh.read()
+        for m in re.finditer(r"__launch_bounds__\(([^)]*)\)\s*(\w+)\s*\(", s):
+            bounds[m.group(2)] = m.group(1).strip()
+    out = {}
+    for d, (reg, stack, shared, local) in zip(dem, usage):
+        base = re.sub(r"^void\s+", "", d).split("(")[0].split("<")[0].split("::")[-1]
+        out.setdefault(base, []).append((d, int(reg), int(shared), int(local) + int(stack), bounds.get(base)))
+    return out
+
+
+def test_launch_configurations_fit_the_compiled_kernels(host_api):
+    """What no CPU run can exercise - `too many resources requested for launch`, `invalid argument` for more than 48 KB of
+    dynamic shared memory without the opt-in - checked statically: every launch configuration the host-compiled library has
+    used in THIS process (kernel as named at the launch site, largest block / dynamic shared memory; the bodies of the GPU
+    tests above have run by now) is held against the resource usage of the same kernel in the product library nvcc built
+    for sm_100a: registers x threads <= 65536 (worst instantiation of the template), block <= its __launch_bounds__,
+    static + dynamic shared memory <= 48 KB unless the sources opt the kernel in with cudaFuncSetAttribute (then <= 227 KB),
+    no local-memory frame beyond 4 KB per thread."""
+    import re
+    from frontistr_b200 import _lib
+    lib = _lib.lib()._lib if hasattr(_lib.lib(), "_lib") else _lib.lib()
+    buf = C.create_string_buffer(1 << 16)
+    need = lib.fbemul_launch_log(buf, len(buf))
+    assert need <= len(buf)
+    launched = [ln.split("\t") for ln in buf.value.decode().splitlines()]
+    assert launched, "no kernel launch recorded"
+    res = _compiled_kernel_resources()
+    src = ""
+    for f in os.listdir(os.path.join(ROOT, "frontistr_b200", "csrc")):
+        with open(os.path.join(ROOT, "frontistr_b200", "csrc", f)) as fh:
+            src += fh.read()
+    opted_in = set(re.findall(r"cudaFuncSetAttribute\(\s*(\w+)", src))
+    checked, problems = 0, []
+    for name, block, smem, grid, count in launched:
+        block, smem, grid = int(block), int(smem), int(grid)
+        base = name.split("<")[0].split("::")[-1].strip()
+        if base not in res:
+            problems.append("%s: launched on the host but not found in the compiled library" % name)
+            continue
+        checked += 1
+        reg = max(r[1] for r in res[base])
+        shared = max(r[2] for r in res[base])
+        frame = max(r[3] for r in res[base])
+        if reg * block > 65536:
+            problems.append("%s: %d registers x %d threads > 65536" % (name, reg, block))
+        bound = res[base][0][4]
+        if bound and bound.isdigit() and block > int(bound):
+            problems.append("%s: block %d > __launch_bounds__(%s)" % (name, block, bound))
+        limit = 227 * 1024 if base in opted_in else 48 * 1024
+        if shared + smem > limit:
+            problems.append("%s: %d B static + %d B dynamic shared memory > %d (opt-in: %s)" % (name, shared, smem, limit, base in opted_in))
+        if frame > 4096:
+            problems.append("%s: %d B local-memory frame per thread" % (name, frame))
+        if grid > 2147483647:
+            problems.append("%s: grid %d" % (name, grid))
+    assert not problems, "\n".join(problems)
+    assert checked >= 1

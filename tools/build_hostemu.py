@@ -4,7 +4,7 @@ its caches, option handling and launch sequences, and every kernel) compiled by 
   * kernels run as blocks of cooperative fibers (tests/emul/kernel_emul.hpp, kernel_emul_impl.hpp),
   * the CUDA runtime subset the library uses is a host shim (tests/emul/cuda_shim.hpp; "device memory" = host memory filled
     with a poison pattern, streams execute immediately),
-  * the only SOURCE transformation is the launch syntax:   K<<<cfg>>>(args);  ->  fb::EmulCfg(cfg).launch([&]() { K(args); });
+  * the only SOURCE transformation is the launch syntax:   K<<<cfg>>>(args);  ->  fb::EmulCfg(cfg).launch("K", [&]() { K(args); });
     applied to copies of capi.cu / api_*.inc under tests/emul/_hostemu/ (git-ignored).
 
 tests/test_gpu_suite_on_host_api.py loads the result IN PLACE OF the product library (by patching the loader from the
@@ -23,7 +23,8 @@ OUT_SO = os.path.join(EMUL, "libfistr_b200_hostemu.so")
 
 
 def rewrite_launches(text):
-    """K<<<cfg>>>(args)  ->  fb::EmulCfg(cfg).launch([&]() { K(args); })   (K may carry template arguments)"""
+    """K<<<cfg>>>(args)  ->  fb::EmulCfg(cfg).launch("K", [&]() { K(args); })   (K may carry template arguments; the name is
+    recorded with the launch configuration, see fbemul_launch_log)"""
     out, pos, n = [], 0, 0
     while True:
         i = text.find("<<<", pos)
@@ -62,7 +63,7 @@ def rewrite_launches(text):
             b += 1
         args = text[a + 1:b]
         out.append(text[pos:k])
-        out.append("fb::EmulCfg(%s).launch([&]() { %s(%s); })" % (cfg, name, args))
+        out.append('fb::EmulCfg(%s).launch("%s", [&]() { %s(%s); })' % (cfg, " ".join(name.split()), name, args))
         pos = b + 1
         n += 1
     return "".join(out), n
