@@ -38,7 +38,7 @@ int fistr_b200_init(int device_ordinal);
 int fistr_b200_finalize(void);
 const char *fistr_b200_last_error(void);
 /* Integer knobs and read-outs (unknown keys read as -1).
- *   set: "spmv_variant" 0|1|2 (2), "sell_sigma" rows of the SELL-C-sigma sorting window (0 = off), "spmv_blocks_per_sm" (8),
+ *   set: "spmv_variant" 0|1|2 (2), "sell_sigma" rows of the SELL-C-sigma sorting window (0 = off, -1 = 1024 if the natural order pads > 10 %), "spmv_blocks_per_sm" (8),
  *        "cg_fused" 0|1 (1), "ssor_fused" 0|1 SSOR x 1 sweep in 2 ncolor + 3 launches per iteration (0), "cg_check_interval" iterations per launch batch, "time_ax" 0|1, "asm_gather" 0|1 (1),
  *        "asm_probe" development switches of the assembly kernel (0), "ic_inverse" 0 | 1 | 2 | -2 pick by self-test + timing (0),
  *        "ic_pick_min_elems" IC block size that starts the kernel selection (65536), "p2p" 0 NCCL | 1 peer memory if
