@@ -4,6 +4,9 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# several processes share the cores during the suite (torchrun ranks, the background runs below): the oracle's OpenMP team
+# must sleep, not spin, at its barriers (read by libgomp when the oracle library is loaded)
+os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
 for _p in (ROOT, os.path.join(ROOT, "tests")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
@@ -11,6 +14,23 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_finish(session):
+    """The two long subprocess runs of tests/test_emul_fiber_order.py (race detector with reversed fibers, UBSan build:
+    ~1.5 min each, mostly waiting on one core) are started as soon as the collection shows that they are wanted, so that
+    they overlap the rest of the CPU suite instead of extending it; the tests themselves only collect the results."""
+    wanted = {it.name for it in session.items if it.nodeid.startswith("tests/test_emul_fiber_order.py") or "test_emul_fiber_order.py::" in it.nodeid}
+    if not wanted or os.environ.get("FB_EMUL_FIBER_ORDER") or os.environ.get("FB_EMUL_UBSAN"):   # (not from inside those runs)
+        return
+    import test_emul_fiber_order as T
+    T.start_background_runs(reverse=any("reverse" in n for n in wanted), ubsan=any("undefined_behaviour" in n for n in wanted))
+
+
+def pytest_sessionfinish(session, exitstatus):
+    mod = sys.modules.get("test_emul_fiber_order")
+    if mod is not None:
+        mod.stop_background_runs()
 
 
 @pytest.fixture(scope="session")

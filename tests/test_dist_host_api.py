@@ -72,8 +72,10 @@ def test_zhalo_schedule_two_communication_steps_per_iteration():
     transport, and 2 communication steps per iteration (+ the 1-in-50 true-residual iterations) where the default makes 3."""
     base = _torchrun(4, "dist_check.py", "--host", "--hex", "9", "--comm", "nccl")
     assert "PASS" in base[-1] and 2.9 < _steps_per_iter(base[-1]) < 3.4
-    for world, args in ((8, ("--hex", "9")), (4, ("--tet", "3")), (3, ("--hex", "7", "--partition", "kmetis")),
-                        (3, ("--hex", "5", "--empty-last-rank"))):
+    cases = [(8, ("--hex", "9")), (3, ("--hex", "5", "--empty-last-rank"))]
+    if os.environ.get("FISTR_B200_EMUL_FULL") == "1":      # (each launch costs ~10 s of process start-up)
+        cases += [(4, ("--tet", "3")), (3, ("--hex", "7", "--partition", "kmetis"))]
+    for world, args in cases:
         lines = _torchrun(world, "dist_check.py", "--host", "--comm", "nccl", "--option", "comm_zhalo=1", *args)
         assert "PASS" in lines[-1] and "p2p_active=0" in lines[-1]
         assert 1.9 < _steps_per_iter(lines[-1]) < 2.4, lines[-1]
@@ -84,8 +86,9 @@ def test_fused_ssor_iteration_4_ranks():
     share of r.z is the sum over its own backward launches."""
     lines = _torchrun(4, "dist_check.py", "--host", "--tet", "3", "--comm", "nccl", "--precond", "1", "--option", "ssor_fused=1")
     assert "PASS" in lines[-1]
-    lines = _torchrun(3, "dist_check.py", "--host", "--hex", "5", "--comm", "nccl", "--precond", "1", "--empty-last-rank", "--option", "ssor_fused=1")
-    assert "PASS" in lines[-1]
+    if os.environ.get("FISTR_B200_EMUL_FULL") == "1":
+        lines = _torchrun(3, "dist_check.py", "--host", "--hex", "5", "--comm", "nccl", "--precond", "1", "--empty-last-rank", "--option", "ssor_fused=1")
+        assert "PASS" in lines[-1]
 
 
 def test_two_preconditioner_sweeps_2_ranks():
