@@ -15,6 +15,8 @@ from frontistr_b200.hecmw_types import hecmwST_local_mesh
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
+# soak runs: FISTR_B200_FUZZ_OFFSET=k shifts every seed range by k (the default suite runs the ranges from 0)
+OFF = int(os.environ.get("FISTR_B200_FUZZ_OFFSET", "0"))
 
 
 @pytest.fixture(scope="module")
@@ -65,7 +67,7 @@ def random_mesh(rng):
     return m
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", range(OFF, OFF + 24))
 def test_random_mesh_assembly_update_and_nodal_stress(host_api, seed):
     from oracle import oracle as orc
     gpu = host_api
@@ -106,7 +108,7 @@ def test_random_mesh_assembly_update_and_nodal_stress(host_api, seed):
         assert np.abs(qf - q).max() <= 1e-11 * np.abs(q).max(), seed
 
 
-@pytest.mark.parametrize("seed", range(16))
+@pytest.mark.parametrize("seed", range(OFF, OFF + 16))
 def test_random_constraints_and_solve(host_api, seed):
     """Random Dirichlet sets (several DOFs per node, non-zero prescribed values), random nodal loads, PRECOND 1 / 3 / 10,
     iterPREmax 1 / 2, every fourth case with SCALING=YES: hecmw_mat_ass_bc and hecmw_solve through the library against the
@@ -140,7 +142,11 @@ def test_random_constraints_and_solve(host_api, seed):
     gpu.mat_structure(mesh, A)
     gpu.fstr_StiffMatrix(mesh, A, to_host=False)
     setup(gpu, A)
-    r = gpu.hecmw_solve(mesh, A, device_resident=True)
+    gpu.set_option("ssor_fused", seed % 2)        # (takes effect for PRECOND 1 x 1 sweep only)
+    try:
+        r = gpu.hecmw_solve(mesh, A, device_resident=True)
+    finally:
+        gpu.set_option("ssor_fused", 0)
     Ao = orc.mat_con(mesh)
     orc.stiffmatrix(mesh, Ao)
     Ao.B[:] = load
@@ -154,7 +160,15 @@ def test_random_constraints_and_solve(host_api, seed):
     assert r["error"] == ro["error"], (r["error"], ro["error"], precond, ipm)
     if r["error"] != 0:
         return        # same HEC-MW code on both sides (e.g. 3003 when the random system makes SSOR x2 indefinite)
-    assert A.Iarray[80] == Ao.Iarray[80] and (scaling or A.Iarray[80] == 1)
+    # Iarray(81) = "true residual < RESID" (Iterative.f90:164-170).  With SCALING the loop stops on the residual of the SCALED
+    # system, so the true residual of the back-scaled one can land on either side of RESID; library and oracle agree on it to
+    # a few per cent after ~100 iterations, which decides the flag differently when it falls within that distance of RESID
+    # (soak seed 813: 0.989e-10 vs 1.018e-10 at RESID = 1e-10)
+    tol = float(A.Rarray[0])
+    if min(abs(r["resid2"] / tol - 1.0), abs(ro["resid2"] / tol - 1.0)) > 0.1:
+        assert A.Iarray[80] == Ao.Iarray[80]
+    assert scaling or A.Iarray[80] == 1
+    assert abs(r["resid2"] - ro["resid2"]) <= 0.25 * ro["resid2"] + 1e-3 * tol
     assert abs(r["iter"] - ro["iter"]) <= 2, (r["iter"], ro["iter"], precond, ipm)
     assert util.rel_l2(A.X, Ao.X) <= 1e-8
     idx = 3 * (np.array(bn) - 1) + np.array(bd) - 1
@@ -166,7 +180,7 @@ def test_random_constraints_and_solve(host_api, seed):
         assert abs(A.X[i] - v) <= 1e-12 + 1e-9 * abs(v)
 
 
-@pytest.mark.parametrize("seed", range(10))
+@pytest.mark.parametrize("seed", range(OFF, OFF + 10))
 def test_random_total_lagrangian_states(host_api, seed):
     """Total-Lagrangian tangent and update at random finite displacement states: 361 FI / B-bar and 342, elastic and
     Mooney-Rivlin sections mixed in one mesh.  Gauss-point Green-Lagrange strain and 2nd Piola-Kirchhoff stress, QFORCE
@@ -220,7 +234,7 @@ def test_random_total_lagrangian_states(host_api, seed):
         assert np.abs(getattr(A, k) - getattr(Ao, k)).max() <= 1e-11 * scale, (seed, k)
 
 
-@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("seed", range(OFF, OFF + 8))
 def test_random_solve_sequences_with_recycle_flags(host_api, seed):
     """The preconditioner recycling state machine (Iarray(96/97/98), hecmw_mat_recycle_precond_setting,
     matrix_misc.f90:678-697; DIAG_33.f90:38-41, SSOR_33.f90:72-80): sequences of solves on one hecmwST_matrix in which the
@@ -262,7 +276,7 @@ def test_random_solve_sequences_with_recycle_flags(host_api, seed):
     gpu.hecmw_precond_clear()
 
 
-@pytest.mark.parametrize("seed", range(10))
+@pytest.mark.parametrize("seed", range(OFF, OFF + 10))
 def test_random_spmv_and_preconditioners(host_api, seed):
     """hecmw_matvec_33 (every SpMV variant, random SELL-C-sigma window) bit-identical to the oracle; DIAG apply
     bit-identical; SSOR: same colouring / permutation as the oracle's multicolour ordering and the same result to rounding
@@ -304,7 +318,7 @@ def test_random_spmv_and_preconditioners(host_api, seed):
     gpu.hecmw_precond_clear()
 
 
-@pytest.mark.parametrize("seed", range(10))
+@pytest.mark.parametrize("seed", range(OFF, OFF + 10))
 def test_random_mat_con_on_the_device(host_api, seed):
     """hecmw_mat_con built on the "device" (pair keys, radix sort, scans; option matcon_device=1) is identical to the oracle's
     restatement of the reference algorithm and to the library's host version — on random mixed meshes and on the local
