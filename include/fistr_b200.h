@@ -42,8 +42,9 @@ const char *fistr_b200_last_error(void);
  *        "cg_fused" 0|1 (1), "ssor_fused" 0|1 SSOR x 1 sweep in 2 ncolor + 3 launches per iteration (0), "cg_check_interval" iterations per launch batch, "time_ax" 0|1, "asm_gather" 0|1 (1),
  *        "asm_probe" development switches of the assembly kernel (0), "ic_inverse" 0 | 1 | 2 | -2 pick by self-test + timing (0),
  *        "ic_pick_min_elems" IC block size that starts the kernel selection (65536), "p2p" 0 NCCL | 1 peer memory if
- *        every rank can map it | 2 peer memory or fail (1), "comm_zhalo" 0|1 NCCL transport: z halo + (r.r, r.z) partials in one
- *        grouped send/recv, 2 communication steps per CG iteration instead of 3 (0), "matcon_device" 0|1 (0), "bilu_chain_rows" (256),
+ *        every rank can map it | 2 peer memory or fail (1), "p2p_loopback" 0|1 one rank: the peer-memory kernels against the
+ *        rank's own arena (their first run on a single GPU; set before mat_structure) (0), "comm_zhalo" 0|1 NCCL transport: z halo + (r.r, r.z) partials in one
+ *        grouped send/recv, 2 communication steps per CG iteration instead of 3; 2 = also on one rank (0), "matcon_device" 0|1 (0), "bilu_chain_rows" (256),
  *        "launch_count_reset"
  *   get: "ic_inverse_active", "ic_selftest_ppb", "ic_selftest_ppb_ldlt", "ic_time_us_smem|reg|ldlt", "ic_time_elems",
  *        "bilu_levels", "bilu_launches_per_apply", "update_kernel_us", "nodal_stress_kernel_us", "p2p_active",

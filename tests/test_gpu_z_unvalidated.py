@@ -376,6 +376,37 @@ def test_bilu0_auto_sigma_diag_loop(gpu, case):
 
 # (4b) !SOLVER SCALING=YES: symmetric diagonal scaling around the CG loop, csrc/scaling.cuh
 
+@pytest.mark.parametrize("mode", ["p2p_loopback", "comm_zhalo"])
+def test_multi_gpu_kernels_on_one_gpu_are_bit_identical_to_the_single_gpu_solve(gpu, mode):
+    """The kernels of the two multi-GPU transports get their FIRST hardware run here, on ONE GPU (and, through
+    tools/gpu_gate.sh, under compute-sanitizer), never at N > 1: `p2p_loopback` makes the rank its own and only peer - the
+    solve launches spmv_sell2_kernel<0,256,true>, cg_fused_update_kernel<256,true> and the signalling branch of
+    cg_update_p_kernel with live sequence numbers against its own arena; `comm_zhalo = 2` runs cg_update_p_zh /
+    cg_fused_update_zh / cg_check_zh with a table of one partial.  A sum of one term is the term and there is no halo, so
+    residual history and solution must equal the ordinary single-GPU solve bit for bit."""
+    from frontistr_b200 import meshgen
+    mesh = util.distort(meshgen.hex_cube(8))
+    cnt = util.cube_cnt(tol=1e-10)
+    A0 = util.product_problem(gpu, mesh, cnt, to_host=True)
+    r0 = gpu.hecmw_solve(mesh, A0)
+    gpu.set_option(mode, 2 if mode == "comm_zhalo" else 1)
+    try:
+        A1 = util.product_problem(gpu, mesh, cnt, to_host=True)       # (the arena is set up with the structure)
+        assert gpu.get_option("p2p_active") == (1 if mode == "p2p_loopback" else 0)
+        c0 = gpu.launch_count()
+        r1 = gpu.hecmw_solve(mesh, A1)
+        launches = gpu.launch_count() - c0
+    finally:
+        gpu.set_option(mode, 0)
+        A2 = util.product_problem(gpu, mesh, cnt, to_host=True)       # back to the ordinary set-up for whoever comes next
+    assert gpu.get_option("p2p_active") == 0
+    assert r0["error"] == 0 and r1["error"] == 0 and r1["iter"] == r0["iter"] > 50
+    assert np.array_equal(r1["hist"], r0["hist"]) and np.array_equal(A1.X, A0.X)
+    assert launches > 3 * r1["iter"]
+    r2 = gpu.hecmw_solve(mesh, A2)
+    assert np.array_equal(r2["hist"], r0["hist"])
+
+
 @pytest.mark.parametrize("ncolor", [10, 3])
 @pytest.mark.parametrize("meshname", ["hex12", "tet4"])
 def test_solve_ssor_fused_iteration(gpu, meshname, ncolor):
