@@ -20,17 +20,24 @@ def pytest_collection_finish(session):
     """The two long subprocess runs of tests/test_emul_fiber_order.py (race detector with reversed fibers, UBSan build:
     ~1.5 min each, mostly waiting on one core) are started as soon as the collection shows that they are wanted, so that
     they overlap the rest of the CPU suite instead of extending it; the tests themselves only collect the results."""
-    wanted = {it.name for it in session.items if it.nodeid.startswith("tests/test_emul_fiber_order.py") or "test_emul_fiber_order.py::" in it.nodeid}
-    if not wanted or os.environ.get("FB_EMUL_FIBER_ORDER") or os.environ.get("FB_EMUL_UBSAN"):   # (not from inside those runs)
+    if os.environ.get("FB_EMUL_FIBER_ORDER") or os.environ.get("FB_EMUL_UBSAN"):   # (not from inside those runs)
         return
-    import test_emul_fiber_order as T
-    T.start_background_runs(reverse=any("reverse" in n for n in wanted), ubsan=any("undefined_behaviour" in n for n in wanted))
+    wanted = {it.name for it in session.items if "test_emul_fiber_order.py::" in it.nodeid}
+    if wanted:
+        import test_emul_fiber_order as T
+        T.start_background_runs(reverse=any("reverse" in n for n in wanted), ubsan=any("undefined_behaviour" in n for n in wanted))
+    # likewise the torchrun launches of tests/test_dist_host_api.py (start-up dominated): two at a time, ahead of their tests
+    dist = {it.originalname for it in session.items if "test_dist_host_api.py::" in it.nodeid}
+    if dist:
+        import test_dist_host_api as D
+        D.start_background_runs(dist)
 
 
 def pytest_sessionfinish(session, exitstatus):
-    mod = sys.modules.get("test_emul_fiber_order")
-    if mod is not None:
-        mod.stop_background_runs()
+    for name in ("test_emul_fiber_order", "test_dist_host_api"):
+        mod = sys.modules.get(name)
+        if mod is not None:
+            mod.stop_background_runs()
 
 
 @pytest.fixture(scope="session")

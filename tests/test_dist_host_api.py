@@ -22,14 +22,68 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _torchrun(nproc, script, *args, env=None, timeout=600):
-    sys.path.insert(0, os.path.join(ROOT, "tools"))
-    import build_hostemu
-    build_hostemu.build()                      # once, before the ranks race to build it
+def _run(nproc, script, args, env, timeout):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(ROOT, "tests", script)] + list(args)
     e = dict(os.environ); e.update(env or {}); e.setdefault("OMP_NUM_THREADS", "1")
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=e, cwd=ROOT)
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=e, cwd=ROOT)
+
+
+_FUTURES = {}      # (nproc, script, args, env items) -> Future of the launches started ahead of the tests
+_POOL = None
+
+
+def _key(nproc, script, args, env):
+    return (nproc, script, tuple(args), tuple(sorted((env or {}).items())))
+
+
+def start_background_runs(selected_tests):
+    """Every launch costs ~10 s of process start-up (N interpreters importing torch) during which the cores are mostly idle:
+    the launches whose arguments are literals in this file are found by parsing it and started two at a time as soon as the
+    collection is known (tests/conftest.py); _torchrun then only waits for its result.  Anything else runs inline."""
+    import ast
+    import concurrent.futures
+    global _POOL
+    if _POOL is not None:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import build_hostemu
+    build_hostemu.build()                      # once, before the ranks race to build it
+    _POOL = concurrent.futures.ThreadPoolExecutor(max_workers=2)
+    with open(os.path.abspath(__file__)) as f:
+        tree = ast.parse(f.read())
+    for fn in tree.body:
+        if not isinstance(fn, ast.FunctionDef) or fn.name not in selected_tests:
+            continue
+        for node in ast.walk(fn):
+            if isinstance(node, ast.Call) and getattr(node.func, "id", "") == "_torchrun":
+                try:
+                    pos = [ast.literal_eval(a) for a in node.args]
+                    kw = {k.arg: ast.literal_eval(k.value) for k in node.keywords}
+                except (ValueError, SyntaxError):
+                    continue                    # arguments that are not literals: that launch runs inline
+                k = _key(pos[0], pos[1], pos[2:], kw.get("env"))
+                if k not in _FUTURES:
+                    _FUTURES[k] = _POOL.submit(_run, pos[0], pos[1], pos[2:], kw.get("env"), kw.get("timeout", 600))
+
+
+def stop_background_runs():
+    global _POOL
+    if _POOL is not None:
+        _POOL.shutdown(wait=False, cancel_futures=True)
+        _POOL = None
+    _FUTURES.clear()
+
+
+def _torchrun(nproc, script, *args, env=None, timeout=600):
+    fut = _FUTURES.pop(_key(nproc, script, args, env), None)
+    if fut is not None:
+        out = fut.result()
+    else:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import build_hostemu
+        build_hostemu.build()                      # once, before the ranks race to build it
+        out = _run(nproc, script, args, env, timeout)
     lines = [ln for ln in (out.stdout + out.stderr).splitlines() if ln.startswith(("PASS", "FAIL", "     nodal"))]
     assert out.returncode == 0 and any(ln.startswith("PASS") for ln in lines) and not any(ln.startswith("FAIL") for ln in lines), \
         (out.stdout + out.stderr)[-3000:]

@@ -168,7 +168,6 @@ def test_random_constraints_and_solve(host_api, seed):
     if min(abs(r["resid2"] / tol - 1.0), abs(ro["resid2"] / tol - 1.0)) > 0.1:
         assert A.Iarray[80] == Ao.Iarray[80]
     assert scaling or A.Iarray[80] == 1
-    assert abs(r["resid2"] - ro["resid2"]) <= 0.25 * ro["resid2"] + 1e-3 * tol
     assert abs(r["iter"] - ro["iter"]) <= 2, (r["iter"], ro["iter"], precond, ipm)
     assert util.rel_l2(A.X, Ao.X) <= 1e-8
     idx = 3 * (np.array(bn) - 1) + np.array(bd) - 1
