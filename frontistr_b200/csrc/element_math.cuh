@@ -25,14 +25,14 @@
 // TEST-ONLY host emulation (emul_test.cpp) defines FB_EMUL_WARP and supplies lock-step versions (32 host
 // threads + barriers), so the very same source is what the CPU unit tests execute.
 #if defined(FB_EMUL_WARP)
-namespace fb { namespace emulwarp {
-double shfl(double v, int src);
-int shfl(int v, int src);
-void syncwarp();
+namespace fb { namespace emulwarp {   // (declared with the call-site tag in tests/emul/kernel_emul.hpp)
+double shfl(double v, int src, unsigned long long site);
+int shfl(int v, int src, unsigned long long site);
+void syncwarp(unsigned long long site);
 } }
 #define FB_WARP_FN inline
-#define FB_SHFL(v, src) fb::emulwarp::shfl((v), (src))
-#define FB_SYNCWARP() fb::emulwarp::syncwarp()
+#define FB_SHFL(v, src) fb::emulwarp::shfl((v), (src), FB_EMUL_SITE)
+#define FB_SYNCWARP() fb::emulwarp::syncwarp(FB_EMUL_SITE)
 #elif defined(__CUDACC__)
 #define FB_WARP_FN __device__ __forceinline__
 #define FB_SHFL(v, src) __shfl_sync(0xffffffffu, (v), (src))

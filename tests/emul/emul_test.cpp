@@ -643,6 +643,28 @@ int fbemul_race_probe(int sync, double *out) {
   return 0;
 }
 
+// Control of the divergent-collective detector (kernel_emul_impl.hpp): mode 0 - every lane shuffles at the same call site
+// (fine); mode 1 - the lower and the upper half of the warp execute DIFFERENT __shfl_sync instructions with a full mask;
+// mode 2 - half of the lanes wait at a __syncwarp while the others shuffle.  Modes 1 and 2 are undefined behaviour on
+// hardware; an emulator that only counts arrivals would run them through.  The detector aborts the process.
+}
+namespace fb {
+static void divergent_probe_kernel(int mode, double *out) {
+  const int lane = threadIdx.x & 31;
+  double v = lane;
+  if (mode == 0) v = __shfl_sync(0xffffffffu, v, (lane + 1) & 31);
+  else if (lane < 16) v = __shfl_sync(0xffffffffu, v, (lane + 1) & 31);
+  else if (mode == 1) v = __shfl_sync(0xffffffffu, v, (lane + 2) & 31);
+  else __syncwarp();
+  out[lane] = v;
+}
+}
+extern "C" {
+int fbemul_divergent_probe(int mode, double *out) {
+  emul_launch_blocks(1, 32, fb::divergent_probe_kernel, mode, out);
+  return 0;
+}
+
 // the device self-test of the three condensation kernels (assembly.cuh: ic_selftest_kernel):
 // out[0] max |K_reg - K_smem|, out[1] max entry, out[2] max |K_ldlt - K_smem|
 int fbemul_ic_selftest(double *out) {

@@ -55,10 +55,20 @@ struct alignas(16) double2 {
 };
 
 namespace fb {
+// Every warp collective carries the call site it was issued from (file / line hash): when the lanes of a warp are released
+// the scheduler checks that all of them arrived at the SAME shuffle (a __shfl_sync whose participants sit at different
+// instructions, or some at a shuffle and others at a __syncwarp, exchanges garbage or hangs on hardware - in an emulator that
+// merely counts arrivals it would pass unnoticed).  __syncwarp may legitimately be reached from different places.
+constexpr unsigned long long emul_site(const char *file, int line) {
+  unsigned long long h = 1469598103934665603ull;
+  for (const char *c = file; *c; ++c) h = (h ^ (unsigned char)*c) * 1099511628211ull;
+  return ((h ^ (unsigned long long)line * 0x9E3779B97F4A7C15ull) << 2) >> 2;   // two low bits are the kind of collective
+}
+#define FB_EMUL_SITE fb::emul_site(__FILE__, __LINE__)
 namespace emulwarp {   // warp / block collectives, implemented in kernel_emul_impl.hpp (fibers)
-double shfl(double v, int src);
-int shfl(int v, int src);
-void syncwarp();
+double shfl(double v, int src, unsigned long long site = 0);
+int shfl(int v, int src, unsigned long long site = 0);
+void syncwarp(unsigned long long site = 0);
 void syncthreads();
 }
 constexpr int kWarp = 32;
@@ -83,16 +93,19 @@ inline int atomicMax(int *p, int v) {
 inline int atomicExch(int *p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
 inline unsigned char *&emul_smem() { static unsigned char *p = nullptr; return p; }   // dynamic shared memory of the running block
 #define FB_DYNAMIC_SMEM(name) unsigned char *name = fb::emul_smem()
-inline void __syncwarp() { emulwarp::syncwarp(); }
 inline void __syncthreads() { emulwarp::syncthreads(); }
-inline double __shfl_xor_sync(unsigned, double v, int o) { return emulwarp::shfl(v, (int)((threadIdx.x & 31) ^ (unsigned)o)); }
-inline double __shfl_sync(unsigned, double v, int src) { return emulwarp::shfl(v, src); }
-inline int __shfl_sync(unsigned, int v, int src) { return emulwarp::shfl(v, src); }
-inline unsigned __ballot_sync(unsigned, bool pred) {
+inline unsigned emul_ballot(bool pred, unsigned long long site) {
   unsigned bits = 0;
-  for (int l = 0; l < 32; l++) bits |= (unsigned)(emulwarp::shfl(pred ? 1 : 0, l) & 1) << l;
+  for (int l = 0; l < 32; l++) bits |= (unsigned)(emulwarp::shfl(pred ? 1 : 0, l, site) & 1) << l;
   return bits;
 }
+// (macros, so that the call site is the kernel's own line; the product uses full masks only - checked by the static_assert-like
+// runtime test in emul_check_mask)
+inline void emul_check_mask(unsigned m) { if (m != 0xffffffffu) { fprintf(stderr, "emul: warp collective with partial mask 0x%08x is not modelled\n", m); abort(); } }
+#define __syncwarp() fb::emulwarp::syncwarp(FB_EMUL_SITE)
+#define __shfl_xor_sync(m, v, o) (fb::emul_check_mask(m), fb::emulwarp::shfl((v), (int)((fb::threadIdx.x & 31) ^ (unsigned)(o)), FB_EMUL_SITE))
+#define __shfl_sync(m, v, s) (fb::emul_check_mask(m), fb::emulwarp::shfl((v), (s), FB_EMUL_SITE))
+#define __ballot_sync(m, p) (fb::emul_check_mask(m), fb::emul_ballot((p), FB_EMUL_SITE))
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline double __ldcg(const double *p) { return *(const volatile double *)p; }

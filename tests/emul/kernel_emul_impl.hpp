@@ -93,7 +93,9 @@ struct FiberBlock {
   std::function<void()> body;
   std::vector<double> slot_d;
   std::vector<int> slot_i;
+  std::vector<unsigned long long> site;     // per fiber: call site (<< 2) | kind of the warp collective it is parked at
 };
+enum { kKindSync = 0, kKindShflPut = 1, kKindShflGet = 2 };
 static thread_local FiberBlock *t_fb = nullptr;   // non-null while this host thread runs a fiber block
 
 static void fiber_to_main(FiberBlock &B) {
@@ -123,7 +125,7 @@ static void run_fiber_block(FiberBlock &B) {
   const int n = (int)B.block;
   B.f.swap(t_fiber_pool);
   if ((int)B.f.size() < n) B.f.resize(n);
-  B.slot_d.assign(n, 0.0); B.slot_i.assign(n, 0);
+  B.slot_d.assign(n, 0.0); B.slot_i.assign(n, 0); B.site.assign(n, 0ull);
   t_fb = &B;
   for (int i = 0; i < n; i++) {
     Fiber &F = B.f[i];
@@ -198,7 +200,24 @@ static void run_fiber_block(FiberBlock &B) {
         if (B.f[i].state == 2) any = true;
         else if (B.f[i].state != 3) all = false;
       }
-      if (any && all) { for (int i = w * 32; i < std::min(n, w * 32 + 32); i++) if (B.f[i].state == 2) B.f[i].state = 0; released = true; }
+      if (any && all) {
+        // all live lanes have arrived: they must be at the same collective.  Lanes of one shuffle at different call sites, or
+        // some lanes at a shuffle and others at a __syncwarp, is a divergent collective (undefined on hardware).
+        unsigned long long first = ~0ull;
+        for (int i = w * 32; i < std::min(n, w * 32 + 32); i++) {
+          if (B.f[i].state != 2) continue;
+          const unsigned long long t = B.site[i];
+          if (first == ~0ull) first = t;
+          const bool both_sync = (t & 3ull) == kKindSync && (first & 3ull) == kKindSync;
+          if (t != first && !both_sync && (t >> 2) != 0 && (first >> 2) != 0) {
+            fprintf(stderr, "emul: divergent warp collective in block %u warp %d: lane %d is at site %llx kind %llu, lane %d at site %llx kind %llu\n",
+                    B.bidx, w, i & 31, t >> 2, t & 3ull, 0, first >> 2, first & 3ull);
+            abort();
+          }
+        }
+        for (int i = w * 32; i < std::min(n, w * 32 + 32); i++) if (B.f[i].state == 2) B.f[i].state = 0;
+        released = true;
+      }
     }
     if (!ran && !released) { fprintf(stderr, "emul: fiber block dead-locked (divergent barrier)\n"); abort(); }
   }
@@ -206,13 +225,15 @@ static void run_fiber_block(FiberBlock &B) {
   B.f.swap(t_fiber_pool);
 }
 
-double shfl(double v, int src) {
+double shfl(double v, int src, unsigned long long site) {
   if (t_fb) {
     FiberBlock &B = *t_fb;
     const int me = B.cur, base = me & ~31;
     B.slot_d[me] = v;
+    B.site[me] = (site << 2) | kKindShflPut;
     fiber_yield(2);
     const double r = B.slot_d[base + (src & 31)];
+    B.site[me] = (site << 2) | kKindShflGet;
     fiber_yield(2);
     return r;
   }
@@ -222,13 +243,15 @@ double shfl(double v, int src) {
   pthread_barrier_wait(&g_bar);
   return r;
 }
-int shfl(int v, int src) {
+int shfl(int v, int src, unsigned long long site) {
   if (t_fb) {
     FiberBlock &B = *t_fb;
     const int me = B.cur, base = me & ~31;
     B.slot_i[me] = v;
+    B.site[me] = (site << 2) | kKindShflPut;
     fiber_yield(2);
     const int r = B.slot_i[base + (src & 31)];
+    B.site[me] = (site << 2) | kKindShflGet;
     fiber_yield(2);
     return r;
   }
@@ -238,7 +261,10 @@ int shfl(int v, int src) {
   pthread_barrier_wait(&g_bar);
   return r;
 }
-void syncwarp() { if (t_fb) fiber_yield(2); else pthread_barrier_wait(&g_bar); }
+void syncwarp(unsigned long long site) {
+  if (t_fb) { t_fb->site[t_fb->cur] = (site << 2) | kKindSync; fiber_yield(2); }
+  else pthread_barrier_wait(&g_bar);
+}
 void syncthreads() {
   if (!t_fb) { fprintf(stderr, "emul: __syncthreads outside emul_launch_blocks\n"); abort(); }
   fiber_yield(1);

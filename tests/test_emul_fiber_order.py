@@ -39,6 +39,22 @@ def test_detector_control_kernel():
     assert not np.array_equal(res[0, 0], res[0, 1])               # => the result depends on the order: detected
 
 
+def test_divergent_warp_collectives_are_detected():
+    """The lanes of a warp must meet at the SAME __shfl_sync (full masks throughout the product): lanes at different shuffle
+    instructions, or some at a shuffle and others at a __syncwarp, is undefined on hardware.  The emulation tags every
+    collective with its call site and aborts when the lanes it is about to release disagree - controls: one legal kernel,
+    two illegal ones (each in its own process: the detector aborts)."""
+    import __graft_entry__ as g
+    so = g.build_emul()
+    code = ("import ctypes as C, sys; em = C.CDLL(%r); out = (C.c_double * 32)(); "
+            "em.fbemul_divergent_probe(int(sys.argv[1]), out); print('returned', out[0])" % so)
+    ok = subprocess.run([sys.executable, "-c", code, "0"], capture_output=True, text=True, timeout=120)
+    assert ok.returncode == 0 and "returned 1.0" in ok.stdout, ok.stderr[-500:]
+    for mode in (1, 2):
+        bad = subprocess.run([sys.executable, "-c", code, str(mode)], capture_output=True, text=True, timeout=120)
+        assert bad.returncode != 0 and "divergent warp collective" in bad.stderr and "returned" not in bad.stdout, (mode, bad.stderr[-500:])
+
+
 # the two runs share the machine: the oracle's OpenMP team must not busy-wait on cores the other run is using
 _SHARE = dict(OMP_NUM_THREADS=str(max(1, (os.cpu_count() or 2) // 2)), OMP_WAIT_POLICY="PASSIVE")
 
