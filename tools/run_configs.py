@@ -23,7 +23,7 @@ from frontistr_b200 import hecmw, meshgen  # noqa: E402
 from frontistr_b200.mshio import apply_solver_card  # noqa: E402
 
 
-def linear_static(mesh, precond, tol, name, sigma=0, maxit=50000):
+def linear_static(mesh, precond, tol, name, sigma=0, maxit=50000, ssor_fused=0):
     t0 = time.time()
     A = hecmw.hecmw_mat_con(mesh)
     t_con = time.time() - t0
@@ -39,6 +39,8 @@ def linear_static(mesh, precond, tol, name, sigma=0, maxit=50000):
     apply_solver_card(A, cnt["solver"]); A.Iarray[20] = 0; A.Iarray[21] = 0
     hecmw.set_option("time_ax", 1)
     hecmw.set_option("sell_sigma", sigma)
+    hecmw.set_option("ssor_fused", ssor_fused)       # PRECOND 1 / 2 x 1 sweep: 2 ncolor + 3 launches per iteration (opt-in)
+    c0 = hecmw.launch_count()
     out = []
     for rep in range(2):
         A.X[:] = 0.0; A.Iarray[96] = 1
@@ -48,7 +50,8 @@ def linear_static(mesh, precond, tol, name, sigma=0, maxit=50000):
     nb = A.spmv_bytes()
     spmv_ms = 1e3 * float(r["times"][3]) / max(r["iter"], 1)
     return {"config": name, "nodes": mesh.n_node, "elements": mesh.n_elem, "dof": 3 * mesh.n_node, "precond": precond,
-            "sell_sigma": sigma, "mat_con_s": t_con, "assembly_kernel_ms": asm[-1]["kernel_ms"],
+            "sell_sigma": sigma, "ssor_fused": ssor_fused, "launches_per_iteration": (hecmw.launch_count() - c0) / max(sum(x["iter"] for x in out), 1),
+            "mat_con_s": t_con, "assembly_kernel_ms": asm[-1]["kernel_ms"],
             "assembly_elements_per_s": mesh.n_elem / (asm[-1]["kernel_ms"] * 1e-3), "error": r["error"], "iterations": r["iter"],
             "resid": r["resid"], "resid_true": r["resid2"], "solve_device_s": float(r["times"][4]),
             "cg_iterations_per_s": r["iter"] / float(r["times"][4]), "spmv_ms": spmv_ms,
@@ -60,12 +63,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", type=int, required=True)
     ap.add_argument("--sigma", type=int, default=0)
+    ap.add_argument("--ssor-fused", type=int, default=0, help="config 0: the fused SSOR iteration (option ssor_fused, opt-in)")
     ap.add_argument("--small", action="store_true", help="reduced sizes (smoke run of this tool)")
     args = ap.parse_args()
     hecmw.init(0)
     if args.config == 0:
         res = linear_static(meshgen.tet10_cube(8 if args.small else 30), 1, 1e-8, "tutorial/01 substitute: tet10 cube, CG+SSOR",
-                            args.sigma)
+                            args.sigma, ssor_fused=args.ssor_fused)
     elif args.config == 2:
         res = linear_static(meshgen.hex_cube(30 if args.small else 200), 3, 1e-8, "H200 on 1 GPU, CG+DIAG", args.sigma)
     elif args.config == 3:
