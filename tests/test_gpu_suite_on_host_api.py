@@ -84,6 +84,29 @@ def host_api():
         _lib._lib = saved
 
 
+def _launch_counts():
+    from frontistr_b200 import _lib
+    buf = C.create_string_buffer(1 << 16)
+    _lib.lib().fbemul_launch_log(buf, len(buf))
+    return {ln.split("\t")[0]: int(ln.split("\t")[4]) for ln in buf.value.decode().splitlines()}
+
+
+# kernels launched by the bodies of the DEFAULT GPU suite (tests/test_gpu_parity.py), collected while they run here
+_DEFAULT_SUITE_KERNELS = set()
+# ... and the kernels that suite may launch: every one of them is, by opcode histogram, identical to or within a few
+# instructions of a kernel of the two builds that ran on a B200 (profiles/r2_sass_vs_hardware_builds.md).  A kernel that is
+# new since then must not reach the driver's `pytest -m gpu` / smoke() / bench.py before it has run under
+# compute-sanitizer (tools/gpu_gate.sh): it belongs behind an option and into tests/test_gpu_z_unvalidated.py first.
+HARDWARE_RUN_KERNELS = {
+    "bc_kernel", "bc_set_rhs_kernel", "cg_check_kernel", "cg_fused_update_kernel", "cg_precond_dot_kernel", "cg_update_p_kernel",
+    "cg_update_xr_kernel", "diag_apply_kernel", "diag_setup_kernel", "dot_kernel", "gather_count_kernel", "gather_fill_kernel",
+    "gather_sort_kernel", "gather_sum_kernel", "sell_fill_kernel", "slot_build_kernel", "spmv_native_kernel", "spmv_sell1_kernel",
+    "spmv_sell2_kernel", "ssor_alu_kernel", "ssor_fill_kernel", "ssor_sweep_kernel", "stiff_kernel", "vec_add_kernel",
+    "vec_copy_zero_tail_kernel", "zero_diag_check_kernel", "gather3_kernel", "scatter3_kernel", "copy_kernel", "add_const_kernel",
+    "DeviceScanInitKernel", "DeviceScanKernel",
+}
+
+
 @pytest.mark.parametrize("modname,name,kw", _cases())
 def test_gpu_test_body_through_the_host_compiled_library(host_api, modname, name, kw):
     if name in SKIP:
@@ -91,6 +114,16 @@ def test_gpu_test_body_through_the_host_compiled_library(host_api, modname, name
     if any((name, str(v)) in SLOW for v in kw.values()) and os.environ.get("FISTR_B200_HOSTAPI_FULL") != "1":
         pytest.skip("slow on the host: set FISTR_B200_HOSTAPI_FULL=1")
     mod = sys.modules[modname]
+    before = _launch_counts() if modname == "test_gpu_parity" else None
+    try:
+        _run_body(host_api, mod, name, kw)
+    finally:
+        if before is not None:
+            after = _launch_counts()
+            _DEFAULT_SUITE_KERNELS.update(k for k, n in after.items() if n > before.get(k, 0))
+
+
+def _run_body(host_api, mod, name, kw):
     if name in ULP_INSTEAD_OF_BITWISE:
         real = mod.np
         mod.np = _NumpyWithUlpEqual(real)
@@ -100,6 +133,17 @@ def test_gpu_test_body_through_the_host_compiled_library(host_api, modname, name
             mod.np = real
     else:
         getattr(mod, name)(host_api, **kw)
+
+
+def test_default_gpu_suite_launches_only_kernels_that_have_run_on_hardware(host_api):
+    """The policy of round 2 as a test: whatever the driver's default `pytest -m gpu` launches (collected above while the
+    bodies of tests/test_gpu_parity.py ran) is on the list of hardware-run kernels; the IC element uses condensation kernel 0."""
+    if not _DEFAULT_SUITE_KERNELS:
+        pytest.skip("no body of the default GPU suite ran in this session")
+    base = {k.split("<")[0].split("::")[-1].strip() for k in _DEFAULT_SUITE_KERNELS}
+    assert base <= HARDWARE_RUN_KERNELS, sorted(base - HARDWARE_RUN_KERNELS)
+    ic = {k for k in _DEFAULT_SUITE_KERNELS if k.startswith("stiff_kernel<elem::FORM_IC")}
+    assert all(k.replace(" ", "").endswith(",0>") for k in ic), ic
 
 
 def test_smoke_and_bench_through_the_host_compiled_library(host_api, monkeypatch, capsys):
@@ -115,6 +159,7 @@ def test_smoke_and_bench_through_the_host_compiled_library(host_api, monkeypatch
 
     import __graft_entry__ as g
     import bench
+    before = _launch_counts()
     g.smoke()
     monkeypatch.setattr(torch.cuda, "set_device", lambda *_: None)
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *_: None)
@@ -133,6 +178,10 @@ def test_smoke_and_bench_through_the_host_compiled_library(host_api, monkeypatch
     args = argparse.Namespace(gpus=1, steps=1, warmup=1, impl="b200", n=6, tol=1.0e-8, precond=3, maxit=20000, ref_iters=0,
                               no_cpu_baseline=False, no_e2e=False, comm="auto")
     bench.run_b200(args)
+    # smoke() and the N = 1 bench launch only kernels that have run on hardware (see HARDWARE_RUN_KERNELS; bench.py also runs the
+    # FP64 peak microbenchmark, unchanged since the measured build and stubbed out here)
+    launched = {k.split("<")[0].split("::")[-1].strip() for k, n in _launch_counts().items() if n > before.get(k, 0)}
+    assert launched <= HARDWARE_RUN_KERNELS, sorted(launched - HARDWARE_RUN_KERNELS)
     cap = capsys.readouterr()
     line = [ln for ln in cap.out.splitlines() if ln.startswith("{")][-1]
     assert "post-line IC kernel selection" not in cap.err      # the never-on-hardware kernels are opt-in (--ic-probe)
