@@ -19,7 +19,7 @@ timeout 600 python tools/asm_probe.py --tet 40 --probes 0,1 2>&1 | tee -a gpurun
 timeout 600 python tools/post_probe.py --n 100 --tet 40 2>&1 | tee gpurun_out/post_probe.log
 timeout 600 python tools/perf_probe.py --tet 40 --variants 2 --sigma 0,256,1024,4096 --solve 0 2>&1 | tee gpurun_out/probe_tet40_sigma.log
 timeout 600 python tools/r2_new_paths_probe.py --n 100 --solve-n 60 2>&1 | tee gpurun_out/new_paths_probe.log
-timeout 1500 python tools/parity_big.py --n 150 > gpurun_out/parity_H150.json 2> gpurun_out/parity_H150.log; echo "parity rc=$?"; cat gpurun_out/parity_H150.log
+timeout 1500 python tools/parity_big.py --n 150 --spread-file profiles/r2_oracle_spread_H150.json > gpurun_out/parity_H150.json 2> gpurun_out/parity_H150.log; echo "parity rc=$?"; cat gpurun_out/parity_H150.log
 for c in 0 2 3; do timeout 900 python tools/run_configs.py --config $c 2>&1 | tail -1 | tee gpurun_out/config_$c.json; done
 timeout 900 python tools/run_configs.py --config 3 --sigma -1 2>&1 | tail -1 | tee gpurun_out/config_3_sigma_auto.json
 timeout 900 python tools/run_configs.py --config 0 --ssor-fused 1 2>&1 | tail -1 | tee gpurun_out/config_0_ssor_fused.json
