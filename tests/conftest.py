@@ -22,6 +22,8 @@ def pytest_collection_finish(session):
     they overlap the rest of the CPU suite instead of extending it; the tests themselves only collect the results."""
     if os.environ.get("FB_EMUL_FIBER_ORDER") or os.environ.get("FB_EMUL_UBSAN"):   # (not from inside those runs)
         return
+    if session.config.getoption("collectonly", False):
+        return
     wanted = {it.name for it in session.items if "test_emul_fiber_order.py::" in it.nodeid}
     if wanted:
         import test_emul_fiber_order as T
